@@ -1,0 +1,92 @@
+"""ctypes binding of the C-ABI library `lib/libatlas_b200.so` (declared in `include/atlas_b200.h`).
+
+There is NO CPU fallback: if the library cannot be loaded, or a call is made without a CUDA
+device, the functions here raise.  torch is used only for device memory and streams.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libatlas_b200.so")
+
+OK = 0
+MAX_TOPK = 1024
+EMBEDDINGS_DIM = 768
+
+_lib = None
+
+
+class AtlasB200Error(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (once) and return the ctypes handle; raise loudly if the CUDA library is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise AtlasB200Error(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback for this path)"
+        )
+    L = ctypes.CDLL(LIB_PATH)
+    c = ctypes
+    L.atlas_b200_last_error.restype = c.c_char_p
+    L.atlas_b200_version.restype = c.c_char_p
+    L.atlas_b200_launch_count.restype = c.c_uint64
+    L.atlas_b200_mips_workspace_bytes.restype = c.c_size_t
+    L.atlas_b200_mips_workspace_bytes.argtypes = [c.c_int64, c.c_int32, c.c_int32]
+    L.atlas_b200_mips_topk.restype = c.c_int
+    L.atlas_b200_mips_topk.argtypes = [
+        c.c_void_p, c.c_int64, c.c_int64, c.c_int32, c.c_void_p, c.c_int32, c.c_int32,
+        c.c_void_p, c.c_void_p, c.c_int64, c.c_int64, c.c_void_p, c.c_void_p, c.c_size_t, c.c_void_p,
+    ]
+    L.atlas_b200_mips_topk_exhaustive.restype = c.c_int
+    L.atlas_b200_mips_topk_exhaustive.argtypes = [
+        c.c_void_p, c.c_int64, c.c_int64, c.c_int32, c.c_void_p, c.c_int32, c.c_int32,
+        c.c_void_p, c.c_void_p, c.c_int64, c.c_int64, c.c_void_p, c.c_size_t, c.c_void_p,
+    ]
+    L.atlas_b200_topk_merge.restype = c.c_int
+    L.atlas_b200_topk_merge.argtypes = [
+        c.c_void_p, c.c_void_p, c.c_int64, c.c_int64, c.c_int32, c.c_int32, c.c_int32, c.c_int32, c.c_int32,
+        c.c_int32, c.c_void_p, c.c_void_p, c.c_void_p,
+    ]
+    L.atlas_b200_search_host.restype = c.c_int
+    L.atlas_b200_search_host.argtypes = [
+        c.c_void_p, c.c_int64, c.c_int64, c.c_int32, c.c_void_p, c.c_int32, c.c_int32,
+        c.c_void_p, c.c_void_p, c.c_int64, c.c_int64, c.c_void_p, c.c_size_t, c.c_void_p,
+    ]
+    L.atlas_b200_cast_f32.restype = c.c_int
+    L.atlas_b200_cast_f32.argtypes = [c.c_void_p, c.c_void_p, c.c_int64, c.c_int32, c.c_void_p]
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = [
+    "atlas_b200_last_error",
+    "atlas_b200_version",
+    "atlas_b200_launch_count",
+    "atlas_b200_mips_workspace_bytes",
+    "atlas_b200_mips_topk",
+    "atlas_b200_mips_topk_exhaustive",
+    "atlas_b200_topk_merge",
+    "atlas_b200_search_host",
+    "atlas_b200_cast_f32",
+]
+
+
+def check(rc):
+    if rc != OK:
+        raise AtlasB200Error(f"atlas_b200 error {rc}: {lib().atlas_b200_last_error().decode()}")
+
+
+def current_stream_ptr():
+    import torch
+
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(t, name):
+    if not t.is_cuda:
+        raise AtlasB200Error(f"{name} must be a CUDA tensor: atlas_b200 has no CPU path")

@@ -1,0 +1,48 @@
+// Host-side helpers shared by the C-ABI translation units: error reporting, launch counting,
+// TMA tensor-map creation through the runtime's driver entry point (so the library does not link
+// libcuda and still dlopen()s on a machine without a GPU driver).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+
+#include "../../include/atlas_b200.h"
+
+namespace abh {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+inline void count_launch(int n = 1) { g_launches.fetch_add(static_cast<uint64_t>(n), std::memory_order_relaxed); }
+
+#define AB_CUDA_CHECK(expr)                                                                       \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            abh::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return ATLAS_B200_ECUDA;                                                              \
+        }                                                                                         \
+    } while (0)
+
+#define AB_REQUIRE(cond, ...)           \
+    do {                                \
+        if (!(cond)) {                  \
+            abh::set_error(__VA_ARGS__); \
+            return ATLAS_B200_EINVAL;   \
+        }                               \
+    } while (0)
+
+// 2-D row-major tensor map: `rows` x `cols` elements of 2 bytes, row stride `ld` elements,
+// box = {box_cols, box_rows}, 128-byte swizzle (box_cols * 2 must be 128).
+int make_tmap_2d_16bit(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                       uint32_t box_rows, uint32_t box_cols, bool bf16);
+
+int num_sms();
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace abh

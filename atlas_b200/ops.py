@@ -1,0 +1,123 @@
+"""Thin torch-tensor wrappers over the C ABI (`include/atlas_b200.h`).
+
+torch owns the device memory and the stream; the arithmetic happens in `lib/libatlas_b200.so`.
+Nothing here falls back to torch ops: a missing library or a CPU tensor raises.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import AtlasB200Error, check, current_stream_ptr, lib, require_cuda
+
+DIM = _lib.EMBEDDINGS_DIM
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+class Workspace:
+    """Grow-only device scratch buffer reused across calls (kernels borrow it per launch)."""
+
+    def __init__(self):
+        self.buf = None
+
+    def get(self, nbytes, device):
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
+            self.buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        return self.buf
+
+
+_default_ws = Workspace()
+
+
+def _check_bank(bank):
+    require_cuda(bank, "bank")
+    if bank.dim() != 2 or bank.shape[1] != DIM or bank.stride(1) != 1:
+        raise AtlasB200Error(f"bank must be [n, {DIM}] with unit inner stride, got {tuple(bank.shape)} {bank.stride()}")
+    if bank.dtype not in (torch.float16, torch.bfloat16):
+        raise AtlasB200Error("bank must be fp16 (reference dtype, src/index.py:51) or bf16")
+    return 1 if bank.dtype == torch.bfloat16 else 0
+
+
+def cast_queries(queries, dtype):
+    """`allqueries.half()` (src/index.py:117) on the device through the library's cast kernel."""
+    require_cuda(queries, "queries")
+    if queries.dtype == dtype:
+        return queries.contiguous()
+    q32 = queries.float().contiguous()
+    out = torch.empty(q32.shape, dtype=dtype, device=q32.device)
+    check(lib().atlas_b200_cast_f32(_ptr(q32), _ptr(out), q32.numel(), 1 if dtype == torch.bfloat16 else 0,
+                                    current_stream_ptr()))
+    return out
+
+
+def mips_topk(bank, queries, k, id_base=0, id_stride=1, workspace=None, exhaustive=False):
+    """Exact top-k inner-product search of `queries` [nq, 768] in `bank` [n, 768] (one shard).
+
+    Returns (scores [nq,k] bank dtype desc, ids [nq,k] int64, status int32[1] device tensor).
+    `status != 0` means the fast path overflowed and the caller must retry with exhaustive=True
+    (see `search_shard`, which does that)."""
+    is_bf16 = _check_bank(bank)
+    n = bank.shape[0]
+    q = cast_queries(queries.reshape(-1, DIM), bank.dtype)
+    nq = q.shape[0]
+    ws = workspace or _default_ws
+    nbytes = lib().atlas_b200_mips_workspace_bytes(n, nq, k)
+    buf = ws.get(nbytes, bank.device)
+    out_s = torch.empty((nq, k), dtype=bank.dtype, device=bank.device)
+    out_i = torch.empty((nq, k), dtype=torch.int64, device=bank.device)
+    status = torch.zeros(1, dtype=torch.int32, device=bank.device)
+    if exhaustive:
+        check(lib().atlas_b200_mips_topk_exhaustive(
+            _ptr(bank), n, bank.stride(0), is_bf16, _ptr(q), nq, k, _ptr(out_s), _ptr(out_i), id_base, id_stride,
+            _ptr(buf), buf.numel(), current_stream_ptr()))
+    else:
+        check(lib().atlas_b200_mips_topk(
+            _ptr(bank), n, bank.stride(0), is_bf16, _ptr(q), nq, k, _ptr(out_s), _ptr(out_i), id_base, id_stride,
+            _ptr(status), _ptr(buf), buf.numel(), current_stream_ptr()))
+    return out_s, out_i, status
+
+
+def search_shard(bank, queries, k, id_base=0, id_stride=1, workspace=None):
+    """mips_topk + the overflow fallback (one host sync to read the status word)."""
+    s, i, status = mips_topk(bank, queries, k, id_base, id_stride, workspace)
+    if queries.numel() and int(status.item()) != 0:
+        s, i, _ = mips_topk(bank, queries, k, id_base, id_stride, workspace, exhaustive=True)
+    return s, i
+
+
+def topk_merge(scores_in, ids_in, world, nq_total, k, q_begin, nq_out, stride_s=None, stride_i=None):
+    """Merge W per-shard lists [W, nq_total, k] -> rows [q_begin, q_begin+nq_out) merged [nq_out, k]."""
+    require_cuda(scores_in, "scores_in")
+    out_s = torch.empty((nq_out, k), dtype=scores_in.dtype, device=scores_in.device)
+    out_i = torch.empty((nq_out, k), dtype=torch.int64, device=scores_in.device)
+    ss = nq_total * k if stride_s is None else stride_s
+    si = nq_total * k if stride_i is None else stride_i
+    check(lib().atlas_b200_topk_merge(_ptr(scores_in), _ptr(ids_in), ss, si,
+                                      1 if scores_in.dtype == torch.bfloat16 else 0, world, nq_total, k, q_begin,
+                                      nq_out, _ptr(out_s), _ptr(out_i), current_stream_ptr()))
+    return out_s, out_i
+
+
+def search_host(bank, queries_host, k, id_base=0, id_stride=1, workspace=None):
+    """The C-ABI end-to-end call with HOST buffers (H2D + cast + scan + select + D2H, synchronous).
+
+    queries_host: CPU float32 tensor [nq, 768] (pinned or pageable).  Returns CPU tensors
+    (scores float32 [nq,k] holding the 16-bit values, ids int64 [nq,k])."""
+    is_bf16 = _check_bank(bank)
+    if queries_host.is_cuda or queries_host.dtype != torch.float32:
+        raise AtlasB200Error("search_host takes a CPU float32 query tensor")
+    qh = queries_host.reshape(-1, DIM).contiguous()
+    nq = qh.shape[0]
+    n = bank.shape[0]
+    ws = workspace or _default_ws
+    nbytes = lib().atlas_b200_mips_workspace_bytes(n, nq, k)
+    buf = ws.get(nbytes, bank.device)
+    out_s = torch.empty((nq, k), dtype=torch.float32).pin_memory()
+    out_i = torch.empty((nq, k), dtype=torch.int64).pin_memory()
+    check(lib().atlas_b200_search_host(_ptr(bank), n, bank.stride(0), is_bf16, _ptr(qh), nq, k, _ptr(out_s),
+                                       _ptr(out_i), id_base, id_stride, _ptr(buf), buf.numel(),
+                                       current_stream_ptr()))
+    return out_s, out_i

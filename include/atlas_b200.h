@@ -1,0 +1,107 @@
+/* atlas_b200 — C ABI of the B200-native retrieve-then-read hot path.
+ *
+ * The reference (facebookresearch/atlas) is pure Python and has no FFI; its boundary for this path
+ * is the Python module surface.  This header is the C-ABI layer underneath our
+ * drop-in Python modules (`atlas_b200/index.py` etc.): plain pointers and sizes, no torch types.
+ * Every entry point cites the reference code it replaces.
+ *
+ * Conventions
+ *   - return value: 0 = ATLAS_B200_OK, otherwise an ATLAS_B200_E* code; `atlas_b200_last_error()`
+ *     returns a thread-local human-readable message.  Entry points never exit() or throw.
+ *   - all device pointers must belong to the current CUDA device; work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream) and is asynchronous unless
+ *     stated otherwise.
+ *   - memory is owned by the caller; kernels borrow pointers for the duration of the launch.
+ */
+#ifndef ATLAS_B200_H
+#define ATLAS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ATLAS_B200_OK 0
+#define ATLAS_B200_EINVAL 1      /* bad argument (k > n, misaligned pointer, ...)            */
+#define ATLAS_B200_ECUDA 2       /* a CUDA runtime / driver call failed                      */
+#define ATLAS_B200_EWORKSPACE 3  /* workspace too small                                      */
+#define ATLAS_B200_EUNSUPPORTED 4
+
+#define ATLAS_B200_EMBEDDINGS_DIM 768 /* src/retrievers.py:13 */
+#define ATLAS_B200_MAX_TOPK 1024
+
+const char* atlas_b200_last_error(void);
+const char* atlas_b200_version(void);
+
+/* Number of kernel launches issued by this library since load (bench.py's `gpu_launches`). */
+uint64_t atlas_b200_launch_count(void);
+
+/* --------------------------------------------------------------------------------------------
+ * Exact max-inner-product search over one shard of the passage bank.
+ *
+ * Replaces `DistributedIndex._compute_scores_and_indices` (src/index.py:113-120):
+ *     scores = torch.matmul(allqueries.half(), self.embeddings); torch.topk(scores, topk, dim=1)
+ * Semantics kept: fp16 operands, fp32 accumulation, ONE rounding of each score to fp16, selection on
+ * the fp16-rounded scores.  Tie order (unspecified in the reference) is pinned: score descending,
+ * then id ascending.  The [nq, n] score matrix is never materialised.
+ *
+ *   bank        device, [n, 768] row-major (row = passage = one column of the reference's
+ *               `embeddings[768, n]`), fp16 (is_bf16 = 0) or bf16 (1); 16-byte aligned.
+ *   ld          row stride of `bank` in elements (>= 768, multiple of 8).
+ *   queries     device, [nq, 768] row-major, same dtype as the bank, 16-byte aligned.
+ *   out_scores  device, [nq, k] in the bank dtype, descending.
+ *   out_ids     device, [nq, k] int64 = id_base + id_stride * row   (global line number of the
+ *               passage under the round-robin sharding of src/index_io.py:41 when
+ *               id_base = rank, id_stride = world_size).
+ *   status      device int32[1]: 0 on success; 1 if the candidate buffers overflowed (pathological
+ *               tie/ordering patterns) — results are then INVALID and the caller must call
+ *               atlas_b200_mips_topk_exhaustive().  Written on `stream`.
+ *   workspace   device scratch of at least atlas_b200_mips_workspace_bytes(n, nq, k) bytes.
+ * nq == 0 is allowed (no-op): every rank must call search every step (src/atlas.py:103-106).
+ * -------------------------------------------------------------------------------------------- */
+size_t atlas_b200_mips_workspace_bytes(int64_t n, int32_t nq, int32_t k);
+
+int atlas_b200_mips_topk(const void* bank, int64_t n, int64_t ld, int32_t is_bf16,
+                         const void* queries, int32_t nq, int32_t k,
+                         void* out_scores, int64_t* out_ids, int64_t id_base, int64_t id_stride,
+                         int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same contract, exact for ANY input (chunked scan, no thresholds); slower.  Used as the fallback
+ * when `status` reports overflow.  Synchronous with respect to nothing: enqueued on `stream`. */
+int atlas_b200_mips_topk_exhaustive(const void* bank, int64_t n, int64_t ld, int32_t is_bf16,
+                                    const void* queries, int32_t nq, int32_t k,
+                                    void* out_scores, int64_t* out_ids, int64_t id_base, int64_t id_stride,
+                                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* Merge of W per-shard top-k lists (replaces the second `torch.topk` over the concatenated
+ * [nq, W*k] candidates, src/index.py:144-156).  Shard w's lists are scores_in + w*shard_stride_scores
+ * ([nq_total, k] 16-bit) and ids_in + w*shard_stride_ids ([nq_total, k] int64) — strides in elements,
+ * so the blob produced by ONE NCCL all-gather of each rank's (scores | ids) buffer can be used in
+ * place.  Rows [q_begin, q_begin+nq_out) of every shard list are merged with the canonical order
+ * (score desc, id asc) into out_scores / out_ids [nq_out, k]. */
+int atlas_b200_topk_merge(const void* scores_in, const int64_t* ids_in,
+                          int64_t shard_stride_scores, int64_t shard_stride_ids, int32_t is_bf16,
+                          int32_t world, int32_t nq_total, int32_t k,
+                          int32_t q_begin, int32_t nq_out,
+                          void* out_scores, int64_t* out_ids, void* stream);
+
+/* End-to-end search of one shard with HOST buffers (the call bench.py times as `e2e`):
+ * queries_host [nq, 768] fp32 (what the reference's live retriever emits) are converted with
+ * round-to-nearest-even (`.half()`, src/index.py:117), copied to the device, searched, and the
+ * results copied back.  Synchronous.  out_scores_host is fp32 holding the fp16/bf16 values
+ * (`scores.tolist()`, src/index.py:152). */
+int atlas_b200_search_host(const void* bank, int64_t n, int64_t ld, int32_t is_bf16,
+                           const float* queries_host, int32_t nq, int32_t k,
+                           float* out_scores_host, int64_t* out_ids_host,
+                           int64_t id_base, int64_t id_stride,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* fp32 -> fp16/bf16 row conversion (`allqueries.half()`), device to device. */
+int atlas_b200_cast_f32(const float* src, void* dst, int64_t count, int32_t to_bf16, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ATLAS_B200_H */
