@@ -1,0 +1,211 @@
+"""Drop-in for `src.index.DistributedIndex` (reference src/index.py:43-160) on B200.
+
+Same public surface: `embeddings` ([768, N] fp16 CUDA, slice-assignable on dim 1),
+`doc_map`, `is_in_gpu`, `init_embeddings`, `search_knn`, `save_index`, `load_index`,
+`is_index_trained`, `train_index`.  What changes underneath:
+
+  * the bank is stored passage-major, `[N, 768]` row-major (1536 contiguous bytes per passage, what
+    TMA / tcgen05 want); `embeddings` is the transposed VIEW, so `index.embeddings[:, a:b] = emb.T`
+    (src/atlas.py:79) and `embeddings[:, s:e]` (src/index.py:85) keep working and write through;
+  * `_compute_scores_and_indices` is ONE fused scan (csrc/mips.cu) instead of matmul + topk: the
+    [nq, N] score matrix is never materialised;
+  * `search_knn` exchanges (fp16 score, int64 global id) pairs - one fixed-shape all-gather - instead
+    of pickled passage dicts through 4*W var-size gathers; passage text is resolved from a node-shared
+    store (atlas_b200/passage_store.py);
+  * ties are ordered canonically: score descending, then global passage id ascending.
+
+There is no CPU path: `is_in_gpu = False` (the reference's FAISS-only mode) raises.
+"""
+import math
+import os
+import pickle
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import dist_utils, ops
+from ._lib import MAX_TOPK, AtlasB200Error
+from .passage_store import make_store
+
+EMBEDDINGS_DIM: int = 768  # src/retrievers.py:13
+
+
+class DistributedIndex(object):
+    def __init__(self):
+        self._bank = None  # [N_local, 768] fp16, CUDA
+        self.doc_map = dict()
+        self.is_in_gpu = True
+        self._store = None
+        self._workspace = ops.Workspace()
+        # global id of local row l is _id_base + _id_stride * l
+        self._id_base, self._id_stride = 0, 1
+        self._offsets = None  # contiguous layout (after load_index): first global id of every rank
+
+    # ------------------------------------------------------------------ bank / reference view
+    @property
+    def embeddings(self):
+        """The reference's `[768, N]` tensor (src/index.py:51), as a view of the passage-major bank."""
+        return None if self._bank is None else self._bank.t()
+
+    @embeddings.setter
+    def embeddings(self, value):
+        if value is None:
+            self._bank = None
+            return
+        if value.dim() != 2 or value.shape[0] != EMBEDDINGS_DIM:
+            raise ValueError(f"embeddings must be [{EMBEDDINGS_DIM}, N], got {tuple(value.shape)}")
+        self._bank = value.t().contiguous().to(device=self._device(), dtype=torch.float16)
+
+    @staticmethod
+    def _device():
+        if not torch.cuda.is_available():
+            raise AtlasB200Error("atlas_b200.DistributedIndex needs a CUDA device (no CPU fallback)")
+        return torch.device("cuda", torch.cuda.current_device())
+
+    def init_embeddings(self, passages, dim: Optional[int] = EMBEDDINGS_DIM):
+        """src/index.py:49-53.  Local row l holds global passage line l*W + rank (src/index_io.py:41)."""
+        if dim != EMBEDDINGS_DIM:
+            raise ValueError(f"only dim={EMBEDDINGS_DIM} is supported (src/retrievers.py:13)")
+        if not self.is_in_gpu:
+            raise AtlasB200Error("is_in_gpu=False (CPU-resident bank) is a FAISS-only mode and is not supported")
+        self.doc_map = {i: doc for i, doc in enumerate(passages)}
+        self._bank = torch.zeros(len(passages), dim, dtype=torch.float16, device=self._device())
+        self._id_base, self._id_stride = dist_utils.get_rank(), dist_utils.get_world_size()
+        self._offsets = None
+        self._reset_store()
+
+    def _reset_store(self):
+        if self._store is not None:
+            self._store.close()
+        self._store = None
+
+    def _get_store(self):
+        if self._store is None:
+            self._store = make_store(self.doc_map, dist_utils.get_rank(), dist_utils.get_world_size())
+        return self._store
+
+    # ------------------------------------------------------------------ persistence (reference format)
+    def _get_saved_embedding_path(self, save_dir: str, shard: int) -> str:
+        return os.path.join(save_dir, f"embeddings.{shard}.pt")
+
+    def _get_saved_passages_path(self, save_dir: str, shard: int) -> str:
+        return os.path.join(save_dir, f"passages.{shard}.pt")
+
+    def save_index(self, path: str, total_saved_shards: int, overwrite_saved_passages: bool = False) -> None:
+        """Same files as src/index.py:61-87: `embeddings.{s}.pt` = [768, n_s] fp16, `passages.{s}.pt`."""
+        assert self._bank is not None
+        rank = dist_utils.get_rank()
+        ws = dist_utils.get_world_size()
+        assert total_saved_shards % ws == 0, f"N workers must be a multiple of shards to save"
+        shards_per_worker = total_saved_shards // ws
+        n_embeddings = self._bank.shape[0]
+        embeddings_per_shard = math.ceil(n_embeddings / shards_per_worker)
+        assert n_embeddings == len(self.doc_map), len(self.doc_map)
+        for shard_ind, shard_start in enumerate(range(0, n_embeddings, embeddings_per_shard)):
+            shard_end = min(shard_start + embeddings_per_shard, n_embeddings)
+            shard_id = shard_ind + rank * shards_per_worker
+            passage_shard_path = self._get_saved_passages_path(path, shard_id)
+            if not os.path.exists(passage_shard_path) or overwrite_saved_passages:
+                passage_shard = [self.doc_map[i] for i in range(shard_start, shard_end)]
+                with open(passage_shard_path, "wb") as fobj:
+                    pickle.dump(passage_shard, fobj, protocol=pickle.HIGHEST_PROTOCOL)
+            embeddings_shard = self._bank[shard_start:shard_end].t().contiguous()  # [768, n_s]
+            torch.save(embeddings_shard, self._get_saved_embedding_path(path, shard_id))
+
+    def load_index(self, path: str, total_saved_shards: int):
+        """src/index.py:89-111.  Rank r holds shard files r*S/W .. (r+1)*S/W-1 concatenated; global ids
+        are then contiguous per rank (offsets exchanged once here)."""
+        rank = dist_utils.get_rank()
+        ws = dist_utils.get_world_size()
+        assert total_saved_shards % ws == 0, f"N workers must be a multiple of shards to save"
+        shards_per_worker = total_saved_shards // ws
+        passages, rows = [], []
+        for shard_id in range(rank * shards_per_worker, (rank + 1) * shards_per_worker):
+            with open(self._get_saved_passages_path(path, shard_id), "rb") as fobj:
+                passages.append(pickle.load(fobj))
+            shard = torch.load(self._get_saved_embedding_path(path, shard_id), map_location="cpu")
+            rows.append(shard.t().to(torch.float16))
+        self.doc_map = {}
+        n_passages = 0
+        for chunk in passages:
+            for p in chunk:
+                self.doc_map[n_passages] = p
+                n_passages += 1
+        self._bank = torch.cat(rows, dim=0).contiguous().to(self._device())
+        sizes = dist_utils.get_varsize(self._bank)
+        self._offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        self._id_base, self._id_stride = int(self._offsets[rank]), 1
+        self._reset_store()
+
+    # ------------------------------------------------------------------ search
+    def _compute_scores_and_indices(self, allqueries: torch.Tensor, topk: int):
+        """src/index.py:113-120 semantics (fp16 scores of `allqueries.half() @ embeddings`, row top-k),
+        fused.  Returns (scores [nq, k] fp16 desc, indices [nq, k] int64 LOCAL row numbers)."""
+        return ops.search_shard(self._bank, allqueries, topk, 0, 1, self._workspace)
+
+    def _local_search(self, allqueries, topk):
+        """Local shard scan returning GLOBAL ids."""
+        return ops.search_shard(self._bank, allqueries, topk, self._id_base, self._id_stride, self._workspace)
+
+    def _merge(self, blob_all, ids_off, world, nq_total, topk, q_begin, nq_out):
+        return ops.topk_merge_blob(blob_all, ids_off, world, nq_total, topk, q_begin, nq_out, torch.float16)
+
+    def _owner_local(self, gid, world):
+        if self._offsets is None:
+            return gid % world, gid // world
+        r = int(np.searchsorted(self._offsets, gid, side="right")) - 1
+        return r, gid - int(self._offsets[r])
+
+    @torch.no_grad()
+    def search_knn(self, queries, topk):
+        """Exhaustive k-nearest-neighbour search by inner product (src/index.py:122-157).
+
+        Collective: every rank must call it, also with 0 queries (src/atlas.py:103-106).
+        Returns (docs: List[nq][k] passage dicts, scores: List[nq][k] floats, descending)."""
+        if self._bank is None:
+            raise AtlasB200Error("search_knn before init_embeddings/load_index")
+        if topk > MAX_TOPK:
+            raise AtlasB200Error(f"topk={topk} > {MAX_TOPK}")
+        if topk > self._bank.shape[0]:
+            # torch.topk in the reference raises the same way (src/index.py:118)
+            raise RuntimeError(f"selected index k out of range: topk={topk} > local bank size {self._bank.shape[0]}")
+        world = dist_utils.get_world_size()
+        rank = dist_utils.get_rank()
+        queries = queries.reshape(-1, EMBEDDINGS_DIM)
+        nq_local = queries.shape[0]
+        if world == 1:
+            scores, ids = self._local_search(queries, topk)
+        else:
+            sizes = dist_utils.get_varsize(queries)                                # tiny all_gather (+ sync)
+            q16 = queries.to(self._bank.device).to(torch.float16)                  # `.half()`, src/index.py:117
+            allq = dist_utils.varsize_all_gather(q16, sizes)                       # all_gather #1
+            nq_total = int(sum(sizes))
+            s_loc, i_loc = self._local_search(allq, topk)
+            blob, ids_off = ops.pack_results(s_loc, i_loc)
+            blob_all = dist_utils.all_gather_fixed(blob)                           # all_gather #2
+            q_begin = int(sum(sizes[:rank]))
+            scores, ids = self._merge(blob_all, ids_off, world, nq_total, topk, q_begin, nq_local)
+        scores_host = scores.float().cpu()
+        ids_host = ids.cpu().tolist()
+        flat = [self._owner_local(g, world) for row in ids_host for g in row]
+        docs_flat = self._get_store().lookup(flat)
+        docs = [docs_flat[r * topk:(r + 1) * topk] for r in range(nq_local)]
+        return docs, scores_host.tolist()
+
+    def is_index_trained(self) -> bool:  # src/index.py:159-160
+        return True
+
+    def train_index(self):
+        return None
+
+
+class DistributedFAISSIndex(DistributedIndex):
+    """src/index.py:163-381 wraps faiss-gpu IVF/PQ indices.  Out of scope here (north_star: "No FAISS");
+    the exact flat index above is the supported mode and is what the README recommends."""
+
+    def __init__(self, index_type: str = "flat", code_size: Optional[int] = None):
+        raise AtlasB200Error(
+            "DistributedFAISSIndex is not provided by atlas_b200: use --index_mode flat "
+            "(exact search, atlas_b200.index.DistributedIndex)"
+        )

@@ -121,3 +121,28 @@ def search_host(bank, queries_host, k, id_base=0, id_stride=1, workspace=None):
                                        _ptr(out_i), id_base, id_stride, _ptr(buf), buf.numel(),
                                        current_stream_ptr()))
     return out_s, out_i
+
+
+def pack_results(scores, ids):
+    """One contiguous byte blob [scores (16-bit) | pad to 8 | ids (int64)] so that a SINGLE all-gather
+    ships both (replaces the 2*W gathers of src/index.py:138-141).  Returns (blob uint8, ids offset)."""
+    nbytes_s = scores.numel() * 2
+    ids_off = (nbytes_s + 7) // 8 * 8
+    blob = torch.empty(ids_off + ids.numel() * 8, dtype=torch.uint8, device=scores.device)
+    blob[:nbytes_s].view(scores.dtype).copy_(scores.reshape(-1))
+    blob[ids_off:].view(torch.int64).copy_(ids.reshape(-1))
+    return blob, ids_off
+
+
+def topk_merge_blob(blob_all, ids_off, world, nq_total, k, q_begin, nq_out, dtype):
+    """Merge directly out of the all-gathered blobs `[W, blob_bytes]` (see pack_results)."""
+    require_cuda(blob_all, "blob_all")
+    blob_bytes = blob_all.shape[1]
+    assert blob_bytes % 8 == 0 and blob_all.is_contiguous()
+    out_s = torch.empty((nq_out, k), dtype=dtype, device=blob_all.device)
+    out_i = torch.empty((nq_out, k), dtype=torch.int64, device=blob_all.device)
+    base = blob_all.data_ptr()
+    check(lib().atlas_b200_topk_merge(ctypes.c_void_p(base), ctypes.c_void_p(base + ids_off), blob_bytes // 2,
+                                      blob_bytes // 8, 1 if dtype == torch.bfloat16 else 0, world, nq_total, k,
+                                      q_begin, nq_out, _ptr(out_s), _ptr(out_i), current_stream_ptr()))
+    return out_s, out_i

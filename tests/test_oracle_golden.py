@@ -1,0 +1,60 @@
+"""CPU: the numpy oracle (oracle/mips_oracle.py) against the fixtures produced by running the
+UNMODIFIED reference index (oracle/make_golden.py -> tests/golden/mips_*.npz)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import mips_oracle
+from conftest import GOLDEN_DIR, golden_inputs, load_golden
+
+CASES = sorted(os.path.basename(p)[5:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "mips_*.npz")))
+
+
+def test_goldens_present():
+    assert {"c1_grid", "c1_gauss", "w4_grid_empty_rank"} <= set(CASES)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference(name):
+    g = load_golden(name)
+    bank, q, nq_per_rank = golden_inputs(g)
+    k = int(g["k"])
+    off = np.cumsum([0] + nq_per_rank)
+    res = mips_oracle.search_knn_oracle(bank, [q[off[i]:off[i + 1]] for i in range(len(nq_per_rank))], k)
+    vals = np.concatenate([v for v, _ in res])
+    ids = np.concatenate([i for _, i in res])
+    ref_scores, ref_ids, canon_ids = g["ref_scores"], g["ref_ids"], g["canon_ids"]
+    if str(g["dist"]) == "grid":
+        # exact-grid inputs: accumulation order cannot matter -> bit-exact values, canonical ids
+        assert np.array_equal(vals.view(np.uint16), ref_scores.view(np.uint16))
+        assert np.array_equal(ids, canon_ids)
+    else:
+        # realistic inputs: BLAS accumulation order may flip an fp16 rounding -> <= 1 ulp
+        a = vals.astype(np.float32)
+        b = ref_scores.astype(np.float32)
+        assert np.all(np.abs(a - b) <= np.spacing(np.abs(b).astype(np.float16)).astype(np.float32))
+    # the reference's own pick agrees wherever the tie order / k-boundary cannot matter
+    for r in range(vals.shape[0]):
+        if str(g["dist"]) == "grid":
+            assert mips_oracle.ids_match_tie_aware(ref_scores[r], ref_ids[r], ids[r])
+
+
+def test_canonical_topk_tie_rule():
+    s = np.array([[1.0, 2.0, 2.0, -0.0, 0.0, 2.0]], dtype=np.float16)
+    v, i = mips_oracle.canonical_topk(s, 5)
+    assert i.tolist() == [[1, 2, 5, 0, 3]]
+    with pytest.raises(RuntimeError):
+        mips_oracle.canonical_topk(s, 7)
+
+
+def test_sharded_equals_single():
+    import synth
+
+    bank = synth.make_bank(999, seed=3)
+    q = synth.make_queries(6, seed=4)
+    single = mips_oracle.search_knn_oracle(bank, [q], 11)[0]
+    multi = mips_oracle.search_knn_oracle(bank, [q[:2], q[2:2], q[2:]], 11)
+    assert np.array_equal(np.concatenate([m[1] for m in multi]), single[1])
+    assert np.array_equal(np.concatenate([m[0] for m in multi]).view(np.uint16), single[0].view(np.uint16))
