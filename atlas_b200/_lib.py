@@ -59,6 +59,10 @@ def lib():
     ]
     L.atlas_b200_cast_f32.restype = c.c_int
     L.atlas_b200_cast_f32.argtypes = [c.c_void_p, c.c_void_p, c.c_int64, c.c_int32, c.c_void_p]
+    L.atlas_b200_profile_enable.restype = None
+    L.atlas_b200_profile_enable.argtypes = [c.c_int32]
+    L.atlas_b200_profile_collect.restype = c.c_int
+    L.atlas_b200_profile_collect.argtypes = [c.POINTER(c.c_double), c.POINTER(c.c_int32)]
     _lib = L
     return L
 
@@ -73,6 +77,8 @@ EXPORTED_SYMBOLS = [
     "atlas_b200_topk_merge",
     "atlas_b200_search_host",
     "atlas_b200_cast_f32",
+    "atlas_b200_profile_enable",
+    "atlas_b200_profile_collect",
 ]
 
 

@@ -3,6 +3,9 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <utility>
+#include <vector>
+
 namespace abh {
 
 static thread_local char g_err[512] = "";
@@ -67,9 +70,50 @@ int num_sms() {
     return n;
 }
 
+// ---- profiling of the dominant kernel -------------------------------------------------------
+static bool g_prof_on = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
+static size_t g_prof_used = 0;
+
+void prof_begin(cudaStream_t s) {
+    if (!g_prof_on) return;
+    if (g_prof_used == g_prof_events.size()) {
+        cudaEvent_t a, b;
+        if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+        g_prof_events.emplace_back(a, b);
+    }
+    cudaEventRecord(g_prof_events[g_prof_used].first, s);
+}
+
+void prof_end(cudaStream_t s) {
+    if (!g_prof_on || g_prof_used >= g_prof_events.size()) return;
+    cudaEventRecord(g_prof_events[g_prof_used].second, s);
+    ++g_prof_used;
+}
+
 }  // namespace abh
 
 extern "C" {
+
+void atlas_b200_profile_enable(int32_t on) {
+    abh::g_prof_on = on != 0;
+    abh::g_prof_used = 0;
+}
+
+int atlas_b200_profile_collect(double* total_ms, int32_t* launches) {
+    double tot = 0;
+    for (size_t i = 0; i < abh::g_prof_used; ++i) {
+        float ms = 0;
+        AB_CUDA_CHECK(cudaEventSynchronize(abh::g_prof_events[i].second));
+        AB_CUDA_CHECK(cudaEventElapsedTime(&ms, abh::g_prof_events[i].first, abh::g_prof_events[i].second));
+        tot += ms;
+    }
+    if (total_ms) *total_ms = tot;
+    if (launches) *launches = static_cast<int32_t>(abh::g_prof_used);
+    abh::g_prof_used = 0;
+    return ATLAS_B200_OK;
+}
+
 
 const char* atlas_b200_last_error(void) { return abh::g_err; }
 const char* atlas_b200_version(void) { return "atlas_b200 0.1 (sm_100a)"; }

@@ -43,6 +43,11 @@ int make_tmap_2d_16bit(CUtensorMap* out, const void* base, uint64_t rows, uint64
 
 int num_sms();
 
+// Optional CUDA-event bracketing of the dominant kernel (bench.py's roofline measurement): when
+// enabled, callers wrap that launch with prof_begin/prof_end on the launching stream.
+void prof_begin(cudaStream_t s);
+void prof_end(cudaStream_t s);
+
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 }  // namespace abh

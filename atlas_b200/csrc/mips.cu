@@ -622,7 +622,9 @@ static int topk_impl(const void* bank, int64_t n, int64_t ld, const void* querie
             p.tile_begin = 0;
             p.tile_step = 1;
             p.num_tiles = total_tiles;
+            abh::prof_begin(s);
             rc = launch_scan<kBF16>(tq, tb, p, s);
+            abh::prof_end(s);
             if (rc) return rc;
             mips_select_kernel<kBF16><<<nqb, SEL_THREADS, 0, s>>>(w.cand, w.count, w.capq, k, SEL_EMIT, w.bound, os_b,
                                                                  oi_b, id_base, id_stride, status);

@@ -158,11 +158,9 @@ class DistributedIndex(object):
         return r, gid - int(self._offsets[r])
 
     @torch.no_grad()
-    def search_knn(self, queries, topk):
-        """Exhaustive k-nearest-neighbour search by inner product (src/index.py:122-157).
-
-        Collective: every rank must call it, also with 0 queries (src/atlas.py:103-106).
-        Returns (docs: List[nq][k] passage dicts, scores: List[nq][k] floats, descending)."""
+    def search_device(self, queries, topk):
+        """Device half of `search_knn`: returns (scores [nq_local, k] fp16, global ids [nq_local, k] int64)
+        as CUDA tensors.  Collective (2 all-gathers + one tiny size exchange when world_size > 1)."""
         if self._bank is None:
             raise AtlasB200Error("search_knn before init_embeddings/load_index")
         if topk > MAX_TOPK:
@@ -173,19 +171,27 @@ class DistributedIndex(object):
         world = dist_utils.get_world_size()
         rank = dist_utils.get_rank()
         queries = queries.reshape(-1, EMBEDDINGS_DIM)
-        nq_local = queries.shape[0]
         if world == 1:
-            scores, ids = self._local_search(queries, topk)
-        else:
-            sizes = dist_utils.get_varsize(queries)                                # tiny all_gather (+ sync)
-            q16 = queries.to(self._bank.device).to(torch.float16)                  # `.half()`, src/index.py:117
-            allq = dist_utils.varsize_all_gather(q16, sizes)                       # all_gather #1
-            nq_total = int(sum(sizes))
-            s_loc, i_loc = self._local_search(allq, topk)
-            blob, ids_off = ops.pack_results(s_loc, i_loc)
-            blob_all = dist_utils.all_gather_fixed(blob)                           # all_gather #2
-            q_begin = int(sum(sizes[:rank]))
-            scores, ids = self._merge(blob_all, ids_off, world, nq_total, topk, q_begin, nq_local)
+            return self._local_search(queries, topk)
+        sizes = dist_utils.get_varsize(queries)                                # tiny all_gather (+ sync)
+        q16 = queries.to(self._bank.device).to(torch.float16)                  # `.half()`, src/index.py:117
+        allq = dist_utils.varsize_all_gather(q16, sizes)                       # all_gather #1
+        nq_total = int(sum(sizes))
+        s_loc, i_loc = self._local_search(allq, topk)
+        blob, ids_off = ops.pack_results(s_loc, i_loc)
+        blob_all = dist_utils.all_gather_fixed(blob)                           # all_gather #2
+        q_begin = int(sum(sizes[:rank]))
+        return self._merge(blob_all, ids_off, world, nq_total, topk, q_begin, queries.shape[0])
+
+    @torch.no_grad()
+    def search_knn(self, queries, topk):
+        """Exhaustive k-nearest-neighbour search by inner product (src/index.py:122-157).
+
+        Collective: every rank must call it, also with 0 queries (src/atlas.py:103-106).
+        Returns (docs: List[nq][k] passage dicts, scores: List[nq][k] floats, descending)."""
+        world = dist_utils.get_world_size()
+        nq_local = queries.reshape(-1, EMBEDDINGS_DIM).shape[0]
+        scores, ids = self.search_device(queries, topk)
         scores_host = scores.float().cpu()
         ids_host = ids.cpu().tolist()
         flat = [self._owner_local(g, world) for row in ids_host for g in row]

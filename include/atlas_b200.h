@@ -98,6 +98,13 @@ int atlas_b200_search_host(const void* bank, int64_t n, int64_t ld, int32_t is_b
                            int64_t id_base, int64_t id_stride,
                            void* workspace, size_t workspace_bytes, void* stream);
 
+/* Measurement hook for bench.py's roofline: while enabled, every launch of the DOMINANT kernel (the
+ * main bank sweep of atlas_b200_mips_topk) is bracketed with CUDA events on its launching stream.
+ * atlas_b200_profile_collect() synchronises those events, returns the summed kernel time and the
+ * number of bracketed launches, and resets the list.  Not thread safe; off by default. */
+void atlas_b200_profile_enable(int32_t on);
+int atlas_b200_profile_collect(double* total_ms, int32_t* launches);
+
 /* fp32 -> fp16/bf16 row conversion (`allqueries.half()`), device to device. */
 int atlas_b200_cast_f32(const float* src, void* dst, int64_t count, int32_t to_bf16, void* stream);
 

@@ -58,3 +58,21 @@ def test_sharded_equals_single():
     multi = mips_oracle.search_knn_oracle(bank, [q[:2], q[2:2], q[2:]], 11)
     assert np.array_equal(np.concatenate([m[1] for m in multi]), single[1])
     assert np.array_equal(np.concatenate([m[0] for m in multi]).view(np.uint16), single[0].view(np.uint16))
+
+
+def test_ref_cpu_path_matches_golden():
+    """The torch-CPU restatement used for the timed CPU baseline returns the reference's values."""
+    import torch
+
+    import ref_cpu_path
+    import synth
+
+    g = load_golden("c1_grid")
+    bank, q, _ = golden_inputs(g)
+    docs, scores = ref_cpu_path.reference_search_cpu(
+        torch.from_numpy(bank).T.contiguous(), ref_cpu_path.LazyDocMap(bank.shape[0]), torch.from_numpy(q), int(g["k"]))
+    got = np.array(scores, dtype=np.float32).astype(np.float16)
+    assert np.array_equal(got.view(np.uint16), g["ref_scores"].view(np.uint16))
+    ids = np.array([[int(d["id"]) for d in row] for row in docs])
+    for r in range(ids.shape[0]):
+        assert mips_oracle.ids_match_tie_aware(g["ref_scores"][r], g["ref_ids"][r], ids[r])
