@@ -28,6 +28,7 @@
 #include "host_common.h"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace mips {
 
@@ -273,6 +274,231 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// scan kernel v2 ("TS"): the query block stays resident in TENSOR MEMORY as the tcgen05 A operand,
+// so the only bytes that cross L2 -> SM are the bank rows.
+//
+//   TMEM (512 columns x 128 lanes per SM): columns [0,384) = 128 queries x 768 fp16 (2 per column),
+//   columns [384,448) and [448,512) = double-buffered 128 x 64 fp32 accumulators.
+//   kPair = true : a 2-CTA cluster (cta_group::2, UMMA M=256) covers 256 queries; each CTA owns 128
+//                  query rows in its own TMEM and streams HALF of every 64-passage tile (32 rows) through
+//                  its own shared memory, so each bank byte is fetched once per SM pair.
+//   kPair = false: one CTA (UMMA M=128) for <= 128 queries.
+//   smem: a 192 KB ring of single K-block slabs (rows x 128 B, 128B swizzle) - 24 x 8 KB or 48 x 4 KB.
+// Roles (256 threads): warp 0 TMA producer, warp 1 MMA issuer (leader CTA), warp 2 TMEM allocator,
+// warps 4-7 load the queries into TMEM once (tcgen05.st), then run the threshold-filter epilogue.
+// ---------------------------------------------------------------------------------------------
+constexpr int TS_TILE_N = 64;
+constexpr int TS_A_COLS = DIM / 2;
+constexpr int TS_THREADS = 256;
+
+template <bool kPair>
+struct TsCfg {
+    static constexpr int ROWS_PER_CTA = kPair ? 32 : 64;
+    static constexpr int STAGE_BYTES = ROWS_PER_CTA * 128;
+    static constexpr int STAGES = kPair ? 48 : 24;
+    static constexpr int UMMA_M = kPair ? 256 : 128;
+    static constexpr int CTAS = kPair ? 2 : 1;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
+};
+
+template <bool kBF16, bool kPair>
+__global__ void __launch_bounds__(TS_THREADS, 1)
+mips_scan_ts_kernel(const __grid_constant__ CUtensorMap tmap_bank, const uint16_t* __restrict__ qstage,
+                    const ScanParams p) {
+    using C = TsCfg<kPair>;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[C::STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[C::STAGES];
+    __shared__ __align__(8) uint64_t tmem_full_bar[2];
+    __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+    __shared__ __align__(8) uint64_t a_ready_bar;
+    __shared__ uint32_t tmem_base_smem;
+
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t cta_rank = kPair ? ab::cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;
+    const int group = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int num_groups = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+    const uint32_t smem_base = (ab::smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - ab::smem_u32(smem_raw));
+
+    if (warp == 0 && lane == 0) ab::tma_prefetch_desc(&tmap_bank);
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < C::STAGES; ++s) {
+            ab::mbar_init(&full_bar[s], 1);
+            ab::mbar_init(&empty_bar[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            ab::mbar_init(&tmem_full_bar[b], 1);
+            ab::mbar_init(&tmem_empty_bar[b], 128u * C::CTAS);
+        }
+        ab::mbar_init(&a_ready_bar, 128u * C::CTAS);
+        ab::fence_barrier_init();
+    }
+    if (warp == 2) ab::tmem_alloc<C::CTAS>(&tmem_base_smem, TMEM_COLS);
+    ab::tc_fence_before();
+    if constexpr (kPair) {
+        ab::cluster_sync_all();
+    } else {
+        __syncthreads();
+    }
+    ab::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        // ===================== TMA producer (every CTA streams its own rows) =====================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int i = group; i < p.num_tiles; i += num_groups) {
+                const int tile = p.tile_begin + i * p.tile_step;
+                const int row0 = tile * TS_TILE_N + static_cast<int>(cta_rank) * C::ROWS_PER_CTA;
+                for (int kb = 0; kb < K_BLOCKS; ++kb) {
+                    ab::mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    uint8_t* dst = smem_gen + stage * C::STAGE_BYTES;
+                    if constexpr (kPair) {
+                        // the leader's barrier collects the bytes of BOTH CTAs' loads
+                        if (leader) ab::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+                        ab::tma_load_2d_2sm(&tmap_bank, &full_bar[stage], dst, kb * BLOCK_K, row0, ab::kEvictFirst);
+                    } else {
+                        ab::mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+                        ab::tma_load_2d(&tmap_bank, &full_bar[stage], dst, kb * BLOCK_K, row0, ab::kEvictFirst);
+                    }
+                    if (++stage == C::STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (lane == 0 && leader) {
+            constexpr uint32_t idesc = ab::umma_idesc_f16(C::UMMA_M, TS_TILE_N, kBF16);
+            ab::mbar_wait(&a_ready_bar, 0);
+            ab::tc_fence_after();
+            uint32_t stage = 0, phase = 0;
+            int it = 0;
+            for (int i = group; i < p.num_tiles; i += num_groups, ++it) {
+                const uint32_t buf = it & 1;
+                ab::mbar_wait(&tmem_empty_bar[buf], ((it >> 1) & 1) ^ 1u);
+                ab::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + TS_A_COLS + buf * TS_TILE_N;
+                for (int kb = 0; kb < K_BLOCKS; ++kb) {
+                    ab::mbar_wait(&full_bar[stage], phase);
+                    ab::tc_fence_after();
+                    const uint32_t sb = smem_base + stage * C::STAGE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        const uint64_t bdesc = ab::umma_desc_k_sw128(sb + k * UMMA_K * 2);
+                        ab::umma_ts<C::CTAS>(d_tmem, tmem_base + kb * (BLOCK_K / 2) + k * (UMMA_K / 2), bdesc, idesc,
+                                             (kb | k) != 0 ? 1u : 0u);
+                    }
+                    if constexpr (kPair) {
+                        ab::umma_commit_2sm(&empty_bar[stage], 0x3);
+                    } else {
+                        ab::umma_commit(&empty_bar[stage]);
+                    }
+                    if (++stage == C::STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                if constexpr (kPair) {
+                    ab::umma_commit_2sm(&tmem_full_bar[buf], 0x3);
+                } else {
+                    ab::umma_commit(&tmem_full_bar[buf]);
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== query load into TMEM, then the filter epilogue =====================
+        const uint32_t lg = warp & 3u;
+        const uint32_t q = cta_rank * 128u + lg * 32u + lane;  // row of the staged query block
+        const uint32_t lane_addr = tmem_base + ((lg * 32u) << 16);
+        {
+            const uint4* src = reinterpret_cast<const uint4*>(qstage + static_cast<size_t>(q) * DIM);
+#pragma unroll 1
+            for (int kb = 0; kb < K_BLOCKS; ++kb) {
+                uint32_t r[32];
+#pragma unroll
+                for (int v = 0; v < 8; ++v) {
+                    const uint4 x = __ldg(src + kb * 8 + v);
+                    r[4 * v + 0] = x.x;
+                    r[4 * v + 1] = x.y;
+                    r[4 * v + 2] = x.z;
+                    r[4 * v + 3] = x.w;
+                }
+                ab::tmem_st32(lane_addr + kb * (BLOCK_K / 2), r);
+            }
+            ab::tmem_st_wait();
+            ab::tc_fence_before();
+            if (leader) {
+                ab::mbar_arrive(&a_ready_bar);
+            } else {
+                ab::mbar_arrive_cluster(&a_ready_bar, 0);
+            }
+        }
+        const float bnd = (static_cast<int>(q) < p.nq) ? p.bound[q] : INFINITY;
+        uint64_t* my_cand = p.cand + static_cast<size_t>(q) * p.capq;
+        int it = 0;
+        for (int i = group; i < p.num_tiles; i += num_groups, ++it) {
+            const uint32_t buf = it & 1;
+            const int tile = p.tile_begin + i * p.tile_step;
+            ab::mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1);
+            ab::tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < TS_TILE_N / 32; ++c) {
+                uint32_t r[32];
+                ab::tmem_ld32(lane_addr + TS_A_COLS + buf * TS_TILE_N + c * 32, r);
+                ab::tmem_ld_wait();
+                float m = __uint_as_float(r[0]);
+#pragma unroll
+                for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(r[j]));
+                if (__any_sync(0xffffffffu, m >= bnd)) {
+                    const int id0 = tile * TS_TILE_N + c * 32;
+                    uint32_t npass = 0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        npass += (__uint_as_float(r[j]) >= bnd && id0 + j < p.n_rows) ? 1u : 0u;
+                    if (npass) {
+                        uint32_t pos = atomicAdd(&p.count[q], npass);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float v = __uint_as_float(r[j]);
+                            if (v >= bnd && id0 + j < p.n_rows) {
+                                if (pos < p.capq)
+                                    my_cand[pos] = pack_candidate(bits_to_key(round_to_bits<kBF16>(v)),
+                                                                  static_cast<uint32_t>(id0 + j));
+                                ++pos;
+                            }
+                        }
+                    }
+                }
+            }
+            ab::tc_fence_before();
+            if (leader) {
+                ab::mbar_arrive(&tmem_empty_bar[buf]);
+            } else {
+                ab::mbar_arrive_cluster(&tmem_empty_bar[buf], 0);
+            }
+        }
+    }
+
+    ab::tc_fence_before();
+    if constexpr (kPair) {
+        ab::cluster_sync_all();
+    } else {
+        __syncthreads();
+    }
+    if (warp == 2) {
+        ab::tc_fence_after();
+        ab::tmem_dealloc<C::CTAS>(tmem_base, TMEM_COLS);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // prep: stage one query block (zero padded to QBLOCK rows), reset counters and bounds
 // ---------------------------------------------------------------------------------------------
@@ -337,9 +563,15 @@ mips_select_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ count, ui
             hist[t] = 0;
             __syncthreads();
             const uint64_t prefix = s_prefix;
-            for (uint32_t i = t; i < n; i += SEL_THREADS) {
-                const uint64_t key = c[i];
-                if ((key & mask) == prefix) atomicAdd(&hist[(key >> (8 * b)) & 0xFFu], 1u);
+            // warp-aggregated histogram: scores cluster in a handful of bins, so per-key shared atomics
+            // would serialise; lanes with the same bin elect one leader that adds their population count
+            for (uint32_t i0 = 0; i0 < n; i0 += SEL_THREADS) {
+                const uint32_t i = i0 + t;
+                const uint64_t key = (i < n) ? c[i] : 0;
+                const bool live = (i < n) && ((key & mask) == prefix);
+                const uint32_t bin = live ? static_cast<uint32_t>((key >> (8 * b)) & 0xFFu) : 256u;
+                const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+                if (live && (t & 31) == static_cast<int>(__ffs(peers)) - 1) atomicAdd(&hist[bin], __popc(peers));
             }
             __syncthreads();
             if (t == 0) {
@@ -547,6 +779,45 @@ static int launch_scan(const CUtensorMap& tq, const CUtensorMap& tb, const ScanP
     return ATLAS_B200_OK;
 }
 
+// 0 = SS kernel (queries streamed through smem), 1 = TS kernel (queries resident in TMEM)
+static int g_kernel_mode = -1;
+static int kernel_mode() {
+    if (g_kernel_mode < 0) {
+        const char* e = getenv("ATLAS_B200_MIPS_KERNEL");
+        g_kernel_mode = (e && (e[0] == 's' || e[0] == 'S')) ? 0 : 1;
+    }
+    return g_kernel_mode;
+}
+
+template <bool kBF16, bool kPair>
+static int launch_scan_ts(const CUtensorMap& tb, const uint16_t* qstage, const ScanParams& p, cudaStream_t s) {
+    using C = TsCfg<kPair>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        AB_CUDA_CHECK(cudaFuncSetAttribute(mips_scan_ts_kernel<kBF16, kPair>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        attr_set = true;
+    }
+    if (p.num_tiles <= 0) return ATLAS_B200_OK;
+    const int max_groups = abh::num_sms() / C::CTAS;
+    const int groups = p.num_tiles < max_groups ? p.num_tiles : max_groups;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(groups * C::CTAS));
+    cfg.blockDim = dim3(TS_THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C::CTAS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    AB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mips_scan_ts_kernel<kBF16, kPair>, tb, qstage, p));
+    abh::count_launch();
+    return ATLAS_B200_OK;
+}
+
 static int check_common(const void* bank, int64_t n, int64_t ld, const void* queries, int nq, int k) {
     AB_REQUIRE(nq >= 0 && k >= 1, "nq must be >= 0 and k >= 1 (nq=%d k=%d)", nq, k);
     AB_REQUIRE(k <= ATLAS_B200_MAX_TOPK, "k=%d exceeds ATLAS_B200_MAX_TOPK=%d", k, ATLAS_B200_MAX_TOPK);
@@ -574,14 +845,26 @@ static int topk_impl(const void* bank, int64_t n, int64_t ld, const void* querie
         abh::set_error("workspace too small: have %zu need %zu", workspace_bytes, need);
         return ATLAS_B200_EWORKSPACE;
     }
-    CUtensorMap tq, tb;
-    rc = abh::make_tmap_2d_16bit(&tq, w.qstage, QBLOCK, DIM, DIM, HALF_M, BLOCK_K, kBF16);
-    if (rc) return rc;
-    rc = abh::make_tmap_2d_16bit(&tb, bank, static_cast<uint64_t>(n), DIM, static_cast<uint64_t>(ld), TILE_N,
-                                 BLOCK_K, kBF16);
-    if (rc) return rc;
+    const bool ts = kernel_mode() == 1;
+    const int tile_n = ts ? TS_TILE_N : TILE_N;
+    // tensor maps: SS = query block + 128-row bank boxes; TS = 64-row (single CTA) / 32-row (CTA pair) boxes
+    CUtensorMap tq, tb, tb_pair;
+    if (!ts) {
+        rc = abh::make_tmap_2d_16bit(&tq, w.qstage, QBLOCK, DIM, DIM, HALF_M, BLOCK_K, kBF16);
+        if (rc) return rc;
+        rc = abh::make_tmap_2d_16bit(&tb, bank, static_cast<uint64_t>(n), DIM, static_cast<uint64_t>(ld), TILE_N,
+                                     BLOCK_K, kBF16);
+        if (rc) return rc;
+    } else {
+        rc = abh::make_tmap_2d_16bit(&tb, bank, static_cast<uint64_t>(n), DIM, static_cast<uint64_t>(ld),
+                                     TsCfg<false>::ROWS_PER_CTA, BLOCK_K, kBF16);
+        if (rc) return rc;
+        rc = abh::make_tmap_2d_16bit(&tb_pair, bank, static_cast<uint64_t>(n), DIM, static_cast<uint64_t>(ld),
+                                     TsCfg<true>::ROWS_PER_CTA, BLOCK_K, kBF16);
+        if (rc) return rc;
+    }
 
-    const int total_tiles = static_cast<int>((n + TILE_N - 1) / TILE_N);
+    const int total_tiles = static_cast<int>((n + tile_n - 1) / tile_n);
     const uint16_t* q16 = static_cast<const uint16_t*>(queries);
     uint16_t* os = static_cast<uint16_t*>(out_scores);
 
@@ -599,6 +882,11 @@ static int topk_impl(const void* bank, int64_t n, int64_t ld, const void* querie
         p.capq = w.capq;
         uint16_t* os_b = os + static_cast<size_t>(q0) * k;
         int64_t* oi_b = out_ids + static_cast<size_t>(q0) * k;
+        auto scan = [&](const ScanParams& sp) -> int {
+            if (!ts) return launch_scan<kBF16>(tq, tb, sp, s);
+            if (sp.n_halves == 2) return launch_scan_ts<kBF16, true>(tb_pair, w.qstage, sp, s);
+            return launch_scan_ts<kBF16, false>(tb, w.qstage, sp, s);
+        };
 
         if (!exhaustive) {
             if (n > static_cast<int64_t>(w.capq)) {
@@ -606,13 +894,13 @@ static int topk_impl(const void* bank, int64_t n, int64_t ld, const void* querie
                 double m = 2.0 * sqrt(static_cast<double>(k) * static_cast<double>(n));
                 if (m < 4096) m = 4096;
                 if (m > w.capq / 2) m = w.capq / 2;
-                int sample_tiles = static_cast<int>(m / TILE_N);
+                int sample_tiles = static_cast<int>(m / tile_n);
                 if (sample_tiles < 1) sample_tiles = 1;
                 if (sample_tiles > total_tiles) sample_tiles = total_tiles;
                 p.tile_begin = 0;
                 p.tile_step = total_tiles / sample_tiles;
                 p.num_tiles = sample_tiles;
-                rc = launch_scan<kBF16>(tq, tb, p, s);
+                rc = scan(p);
                 if (rc) return rc;
                 mips_select_kernel<kBF16><<<nqb, SEL_THREADS, 0, s>>>(w.cand, w.count, w.capq, k, SEL_WRITE_BOUND,
                                                                      w.bound, nullptr, nullptr, 0, 0, nullptr);
@@ -623,7 +911,7 @@ static int topk_impl(const void* bank, int64_t n, int64_t ld, const void* querie
             p.tile_step = 1;
             p.num_tiles = total_tiles;
             abh::prof_begin(s);
-            rc = launch_scan<kBF16>(tq, tb, p, s);
+            rc = scan(p);
             abh::prof_end(s);
             if (rc) return rc;
             mips_select_kernel<kBF16><<<nqb, SEL_THREADS, 0, s>>>(w.cand, w.count, w.capq, k, SEL_EMIT, w.bound, os_b,
@@ -631,14 +919,14 @@ static int topk_impl(const void* bank, int64_t n, int64_t ld, const void* querie
             abh::count_launch();
         } else {
             // chunked exact scan: every score of a chunk is a candidate, winners are carried forward
-            int chunk_tiles = static_cast<int>((w.capq - static_cast<uint32_t>(k)) / TILE_N);
+            int chunk_tiles = static_cast<int>((w.capq - static_cast<uint32_t>(k)) / tile_n);
             if (chunk_tiles < 1) chunk_tiles = 1;
             for (int t0 = 0; t0 < total_tiles; t0 += chunk_tiles) {
                 const bool last = t0 + chunk_tiles >= total_tiles;
                 p.tile_begin = t0;
                 p.tile_step = 1;
                 p.num_tiles = last ? total_tiles - t0 : chunk_tiles;
-                rc = launch_scan<kBF16>(tq, tb, p, s);
+                rc = scan(p);
                 if (rc) return rc;
                 mips_select_kernel<kBF16><<<nqb, SEL_THREADS, 0, s>>>(w.cand, w.count, w.capq, k,
                                                                      last ? SEL_EMIT : SEL_CARRY, w.bound, os_b, oi_b,
@@ -654,6 +942,8 @@ static int topk_impl(const void* bank, int64_t n, int64_t ld, const void* querie
 }  // namespace mips
 
 extern "C" {
+
+void atlas_b200_mips_set_kernel(int32_t mode) { mips::g_kernel_mode = mode ? 1 : 0; }
 
 size_t atlas_b200_mips_workspace_bytes(int64_t n, int32_t nq, int32_t k) {
     if (n < 1) n = 1;

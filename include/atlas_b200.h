@@ -68,6 +68,11 @@ int atlas_b200_mips_topk(const void* bank, int64_t n, int64_t ld, int32_t is_bf1
                          void* out_scores, int64_t* out_ids, int64_t id_base, int64_t id_stride,
                          int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Selects the scan kernel: 1 (default) = queries resident in TMEM (tcgen05 A-from-TMEM, CTA pairs);
+ * 0 = queries streamed through shared memory next to the bank tiles (first-generation kernel, kept for
+ * A/B measurements).  Also settable with the environment variable ATLAS_B200_MIPS_KERNEL=ss|ts. */
+void atlas_b200_mips_set_kernel(int32_t mode);
+
 /* Same contract, exact for ANY input (chunked scan, no thresholds); slower.  Used as the fallback
  * when `status` reports overflow.  Synchronous with respect to nothing: enqueued on `stream`. */
 int atlas_b200_mips_topk_exhaustive(const void* bank, int64_t n, int64_t ld, int32_t is_bf16,

@@ -49,8 +49,14 @@ def run_case(n, nq, k, dist="grid", bseed=1, qseed=2, exhaustive=False, verbose=
     return ok_s and ok_i
 
 
+from atlas_b200._lib import lib
+MODE = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+lib().atlas_b200_mips_set_kernel(MODE)
+print("kernel mode", MODE, "(1 = TS/TMEM-resident queries, 0 = SS)", flush=True)
 results = {}
 try:
+    results["single_small"] = run_case(128, 4, 128)
+    results["single_c1"] = run_case(10000, 64, 40)
     results["tiny_full"] = run_case(128, 4, 128)          # whole matrix, single tile
     results["tiny_full_2tiles"] = run_case(256, 130, 256) # two tiles, both query halves
     results["ragged"] = run_case(257, 3, 5)
