@@ -61,6 +61,8 @@ def lib():
     L.atlas_b200_cast_f32.argtypes = [c.c_void_p, c.c_void_p, c.c_int64, c.c_int32, c.c_void_p]
     L.atlas_b200_mips_set_kernel.restype = None
     L.atlas_b200_mips_set_kernel.argtypes = [c.c_int32]
+    L.atlas_b200_mips_set_debug_counters.restype = None
+    L.atlas_b200_mips_set_debug_counters.argtypes = [c.c_void_p]
     L.atlas_b200_profile_enable.restype = None
     L.atlas_b200_profile_enable.argtypes = [c.c_int32]
     L.atlas_b200_profile_collect.restype = c.c_int
@@ -80,6 +82,7 @@ EXPORTED_SYMBOLS = [
     "atlas_b200_search_host",
     "atlas_b200_cast_f32",
     "atlas_b200_mips_set_kernel",
+    "atlas_b200_mips_set_debug_counters",
     "atlas_b200_profile_enable",
     "atlas_b200_profile_collect",
 ]

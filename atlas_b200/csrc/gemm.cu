@@ -1,0 +1,322 @@
+// Dense linear layers of Contriever (BERT) and FiD (T5) on tcgen05:
+//     C[M, N] = epilogue( A[M, K] . W[N, K]^T )        A, W, C 16-bit (fp16 or bf16), fp32 accumulate
+// W is the nn.Linear weight as stored ([out_features, in_features]), i.e. both operands are K-major
+// and stream through TMA boxes with the 128-byte swizzle straight into UMMA shared-memory descriptors.
+//
+// Replaces the cuBLAS GEMM + separate ATen elementwise kernels behind
+//   BertSelfAttention q/k/v, BertSelfOutput.dense, BertIntermediate.dense (+erf-GELU),
+//   BertOutput.dense                                     (src/modeling_bert.py:280-466)
+//   T5Attention q/k/v/o, T5DenseGatedGeluDense wi_0/wi_1 (+gelu_new gate)/wo, lm_head
+//                                                        (src/modeling_t5.py:272-289,418-531,1642-1647)
+// Fused epilogues (runtime-selected, applied to the fp32 accumulator read back from TMEM):
+//   EPI_NONE      C = acc
+//   EPI_BIAS      C = acc + bias[n]
+//   EPI_GELU      C = gelu_erf(acc + bias[n])                      (ACT2FN["gelu"], modeling_bert.py:444)
+//   EPI_RESIDUAL  C = acc + bias[n] + R[m, n]                      (dense + residual, LN follows)
+//   EPI_GATED     C[m, j] = gelu_new(acc[m, 2j]) * acc[m, 2j+1]    (W rows interleaved wi_0/wi_1;
+//                                                                   modeling_t5.py:281-285, fp32 GELU)
+//
+// Persistent, warp-specialised, one CTA per SM (grid = #SMs):
+//   warp 0 TMA producer | warp 1 MMA issuer (UMMA M=128, N=BLOCK_N, K=16) | warp 2 TMEM allocator
+//   warps 4-11 epilogue: TMEM -> registers -> epilogue math -> 16-bit global stores
+// TMEM: 2 accumulator buffers x BLOCK_N columns, so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include "common.cuh"
+#include "host_common.h"
+
+#include <math.h>
+
+namespace gemm {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;
+constexpr int UMMA_K = 16;
+constexpr int THREADS = 384;
+constexpr int EPI_WARPS = 8;
+
+enum Epilogue { EPI_NONE = 0, EPI_BIAS = 1, EPI_GELU = 2, EPI_RESIDUAL = 3, EPI_GATED = 4 };
+
+template <int BLOCK_N>
+struct Cfg {
+    static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+    static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
+    static constexpr int TMEM_COLS = 2 * BLOCK_N;  // 256 or 512 (power of two)
+};
+
+struct Params {
+    int M, N, K;
+    int ldc;              // elements; for EPI_GATED C has N/2 columns
+    int ldr;              // residual row stride
+    int epi;
+    const uint16_t* bias;      // [N] 16-bit or nullptr
+    const uint16_t* residual;  // [M, ldr] 16-bit or nullptr
+    uint16_t* C;
+};
+
+template <bool kBF16>
+__device__ __forceinline__ float to_f32(uint16_t h) {
+    if constexpr (kBF16) return __bfloat162float(__ushort_as_bfloat16(h));
+    return __half2float(__ushort_as_half(h));
+}
+template <bool kBF16>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    if constexpr (kBF16) {
+        return static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16_rn(a))) |
+               (static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16_rn(b))) << 16);
+    }
+    return static_cast<uint32_t>(__half_as_ushort(__float2half_rn(a))) |
+           (static_cast<uint32_t>(__half_as_ushort(__float2half_rn(b))) << 16);
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// transformers' "gelu_new": 0.5*x*(1+tanh(sqrt(2/pi)*(x+0.044715*x^3)))
+__device__ __forceinline__ float gelu_new(float x) {
+    return 0.5f * x * (1.0f + tanhf(0.7978845608028654f * (x + 0.044715f * x * x * x)));
+}
+
+template <bool kBF16, int BLOCK_N>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
+    using C = Cfg<BLOCK_N>;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[C::STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[C::STAGES];
+    __shared__ __align__(8) uint64_t tmem_full_bar[2];
+    __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+    __shared__ uint32_t tmem_base_smem;
+
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t smem_base = (ab::smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - ab::smem_u32(smem_raw));
+
+    const int num_m = (p.M + BLOCK_M - 1) / BLOCK_M;
+    const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+    const int num_tiles = num_m * num_n;
+    const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+
+    if (warp == 0 && lane == 0) {
+        ab::tma_prefetch_desc(&tmap_a);
+        ab::tma_prefetch_desc(&tmap_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < C::STAGES; ++s) {
+            ab::mbar_init(&full_bar[s], 1);
+            ab::mbar_init(&empty_bar[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            ab::mbar_init(&tmem_full_bar[b], 1);
+            ab::mbar_init(&tmem_empty_bar[b], EPI_WARPS);
+        }
+        ab::fence_barrier_init();
+    }
+    if (warp == 2) ab::tmem_alloc<1>(&tmem_base_smem, C::TMEM_COLS);
+    ab::tc_fence_before();
+    __syncthreads();
+    ab::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const int m_blk = t / num_n, n_blk = t % num_n;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    ab::mbar_wait(&empty_bar[stage], phase ^ 1u, 11);
+                    ab::mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+                    uint8_t* st = smem_gen + stage * C::STAGE_BYTES;
+                    ab::tma_load_2d(&tmap_a, &full_bar[stage], st, kb * BLOCK_K, m_blk * BLOCK_M, ab::kEvictNormal);
+                    ab::tma_load_2d(&tmap_b, &full_bar[stage], st + C::A_BYTES, kb * BLOCK_K, n_blk * BLOCK_N,
+                                    ab::kEvictLast);
+                    if (++stage == C::STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = ab::umma_idesc_f16(BLOCK_M, BLOCK_N, kBF16);
+            uint32_t stage = 0, phase = 0;
+            int it = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+                const uint32_t buf = it & 1;
+                ab::mbar_wait(&tmem_empty_bar[buf], ((it >> 1) & 1) ^ 1u, 12);
+                ab::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * BLOCK_N;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    ab::mbar_wait(&full_bar[stage], phase, 13);
+                    ab::tc_fence_after();
+                    const uint64_t adesc0 = ab::umma_desc_k_sw128(smem_base + stage * C::STAGE_BYTES);
+                    const uint64_t bdesc0 = ab::umma_desc_k_sw128(smem_base + stage * C::STAGE_BYTES + C::A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        ab::umma_ss<1>(d_tmem, adesc0 + ((k * UMMA_K * 2) >> 4), bdesc0 + ((k * UMMA_K * 2) >> 4), idesc,
+                                       (kb | k) != 0 ? 1u : 0u);
+                    }
+                    ab::umma_commit(&empty_bar[stage]);
+                    if (++stage == C::STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                ab::umma_commit(&tmem_full_bar[buf]);
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const uint32_t lg = warp & 3u;
+        const uint32_t half = (warp - 4u) >> 2;  // which half of the BLOCK_N columns
+        constexpr int CHUNKS = BLOCK_N / 64;     // 32-column chunks per warp
+        int it = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+            const uint32_t buf = it & 1;
+            const int m_blk = t / num_n, n_blk = t % num_n;
+            const int row = m_blk * BLOCK_M + static_cast<int>(lg * 32 + lane);
+            ab::mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1, 14);
+            ab::tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < CHUNKS; ++c) {
+                const int col_local = static_cast<int>(half) * (BLOCK_N / 2) + c * 32;
+                const int col0 = n_blk * BLOCK_N + col_local;
+                uint32_t r[32];
+                ab::tmem_ld32(tmem_base + ((lg * 32u) << 16) + buf * BLOCK_N + col_local, r);
+                ab::tmem_ld_wait();
+                if (c == CHUNKS - 1) {
+                    // all accumulator columns of this warp are in registers: release the buffer
+                    ab::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ab::mbar_arrive(&tmem_empty_bar[buf]);
+                }
+                if (row >= p.M || col0 >= p.N) continue;
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                if (p.epi != EPI_NONE && p.epi != EPI_GATED && p.bias != nullptr) {
+#pragma unroll
+                    for (int j8 = 0; j8 < 4; ++j8) {
+                        if (col0 + j8 * 8 < p.N) {
+                            const uint4 b = __ldg(reinterpret_cast<const uint4*>(p.bias + col0 + j8 * 8));
+                            const uint32_t w[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                v[j8 * 8 + 2 * e] += to_f32<kBF16>(static_cast<uint16_t>(w[e] & 0xFFFFu));
+                                v[j8 * 8 + 2 * e + 1] += to_f32<kBF16>(static_cast<uint16_t>(w[e] >> 16));
+                            }
+                        }
+                    }
+                }
+                if (p.epi == EPI_GELU) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                } else if (p.epi == EPI_RESIDUAL) {
+                    const uint16_t* rrow = p.residual + static_cast<size_t>(row) * p.ldr + col0;
+#pragma unroll
+                    for (int j8 = 0; j8 < 4; ++j8) {
+                        if (col0 + j8 * 8 < p.N) {
+                            const uint4 b = __ldg(reinterpret_cast<const uint4*>(rrow + j8 * 8));
+                            const uint32_t w[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                v[j8 * 8 + 2 * e] += to_f32<kBF16>(static_cast<uint16_t>(w[e] & 0xFFFFu));
+                                v[j8 * 8 + 2 * e + 1] += to_f32<kBF16>(static_cast<uint16_t>(w[e] >> 16));
+                            }
+                        }
+                    }
+                }
+                if (p.epi == EPI_GATED) {
+                    // columns (2j, 2j+1) = (x.wi_0[j], x.wi_1[j]) -> 16 outputs
+                    uint16_t* crow = p.C + static_cast<size_t>(row) * p.ldc + (col0 >> 1);
+                    uint32_t o[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        o[e] = pack2<kBF16>(gelu_new(v[4 * e]) * v[4 * e + 1], gelu_new(v[4 * e + 2]) * v[4 * e + 3]);
+#pragma unroll
+                    for (int j8 = 0; j8 < 2; ++j8)
+                        if (col0 + j8 * 16 < p.N)
+                            *reinterpret_cast<uint4*>(crow + j8 * 8) =
+                                make_uint4(o[4 * j8], o[4 * j8 + 1], o[4 * j8 + 2], o[4 * j8 + 3]);
+                } else {
+                    uint16_t* crow = p.C + static_cast<size_t>(row) * p.ldc + col0;
+#pragma unroll
+                    for (int j8 = 0; j8 < 4; ++j8) {
+                        if (col0 + j8 * 8 < p.N) {
+                            *reinterpret_cast<uint4*>(crow + j8 * 8) = make_uint4(
+                                pack2<kBF16>(v[j8 * 8 + 0], v[j8 * 8 + 1]), pack2<kBF16>(v[j8 * 8 + 2], v[j8 * 8 + 3]),
+                                pack2<kBF16>(v[j8 * 8 + 4], v[j8 * 8 + 5]), pack2<kBF16>(v[j8 * 8 + 6], v[j8 * 8 + 7]));
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    ab::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        ab::tc_fence_after();
+        ab::tmem_dealloc<1>(tmem_base, C::TMEM_COLS);
+    }
+}
+
+template <bool kBF16, int BLOCK_N>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, cudaStream_t s) {
+    using C = Cfg<BLOCK_N>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        AB_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<kBF16, BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           C::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * ((p.N + BLOCK_N - 1) / BLOCK_N);
+    const int grid = tiles < abh::num_sms() ? tiles : abh::num_sms();
+    gemm_kernel<kBF16, BLOCK_N><<<grid, THREADS, C::SMEM_BYTES, s>>>(ta, tb, p);
+    abh::count_launch();
+    AB_CUDA_CHECK(cudaGetLastError());
+    return ATLAS_B200_OK;
+}
+
+}  // namespace gemm
+
+extern "C" {
+
+int atlas_b200_linear(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, const void* residual,
+                      int64_t ldr, void* C, int64_t ldc, int32_t M, int32_t N, int32_t K, int32_t epilogue,
+                      int32_t is_bf16, void* stream) {
+    using namespace gemm;
+    AB_REQUIRE(M >= 0 && N > 0 && K > 0, "bad GEMM shape M=%d N=%d K=%d", M, N, K);
+    if (M == 0) return ATLAS_B200_OK;
+    AB_REQUIRE(N % 8 == 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldc % 8 == 0,
+               "N, K and the leading dimensions must be multiples of 8 (16-byte rows)");
+    AB_REQUIRE(epilogue >= EPI_NONE && epilogue <= EPI_GATED, "unknown epilogue %d", epilogue);
+    AB_REQUIRE(epilogue != EPI_RESIDUAL || (residual != nullptr && ldr % 8 == 0), "EPI_RESIDUAL needs a residual");
+    AB_REQUIRE(epilogue != EPI_GATED || N % 32 == 0, "EPI_GATED needs N %% 32 == 0");
+    AB_REQUIRE((reinterpret_cast<uintptr_t>(C) & 15u) == 0, "C must be 16-byte aligned");
+    Params p;
+    p.M = M;
+    p.N = N;
+    p.K = K;
+    p.ldc = static_cast<int>(ldc);
+    p.ldr = static_cast<int>(ldr);
+    p.epi = epilogue;
+    p.bias = static_cast<const uint16_t*>(bias);
+    p.residual = static_cast<const uint16_t*>(residual);
+    p.C = static_cast<uint16_t*>(C);
+    const bool wide = N >= 256 && (static_cast<int64_t>((M + 127) / 128) * ((N + 255) / 256) >= abh::num_sms() / 2);
+    const int block_n = wide ? 256 : 128;
+    CUtensorMap ta, tb;
+    int rc = abh::make_tmap_2d_16bit(&ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K),
+                                     static_cast<uint64_t>(lda), BLOCK_M, BLOCK_K, is_bf16 != 0);
+    if (rc) return rc;
+    rc = abh::make_tmap_2d_16bit(&tb, W, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldw),
+                                 static_cast<uint32_t>(block_n), BLOCK_K, is_bf16 != 0);
+    if (rc) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (is_bf16) return wide ? launch<true, 256>(ta, tb, p, s) : launch<true, 128>(ta, tb, p, s);
+    return wide ? launch<false, 256>(ta, tb, p, s) : launch<false, 128>(ta, tb, p, s);
+}
+
+}  // extern "C"

@@ -119,6 +119,7 @@ struct ScanParams {
     uint32_t* count;      // [QBLOCK]
     uint64_t* cand;       // [QBLOCK][capq]
     uint32_t capq;
+    unsigned long long* dbg;  // optional [gridDim.x][8] cycle counters (nullptr = off)
 };
 
 template <bool kBF16>
@@ -169,7 +170,7 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             for (int i = blockIdx.x; i < p.num_tiles; i += gridDim.x) {
                 const int tile = p.tile_begin + i * p.tile_step;
                 for (int kb = 0; kb < K_BLOCKS; ++kb) {
-                    ab::mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    ab::mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
                     ab::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
                     uint8_t* st = smem_gen + stage * STAGE_BYTES;
                     ab::tma_load_2d(&tmap_q, &full_bar[stage], st, kb * BLOCK_K, 0, ab::kEvictLast);
@@ -193,10 +194,10 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             int it = 0;
             for (int i = blockIdx.x; i < p.num_tiles; i += gridDim.x, ++it) {
                 const uint32_t buf = it & 1;
-                ab::mbar_wait(&tmem_empty_bar[buf], ((it >> 1) & 1) ^ 1u);
+                ab::mbar_wait(&tmem_empty_bar[buf], ((it >> 1) & 1) ^ 1u, 2);
                 ab::tc_fence_after();
                 for (int kb = 0; kb < K_BLOCKS; ++kb) {
-                    ab::mbar_wait(&full_bar[stage], phase);
+                    ab::mbar_wait(&full_bar[stage], phase, 3);
                     ab::tc_fence_after();
                     const uint32_t st = smem_base + stage * STAGE_BYTES;
                     for (int h = 0; h < p.n_halves; ++h) {
@@ -229,7 +230,7 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             for (int i = blockIdx.x; i < p.num_tiles; i += gridDim.x, ++it) {
                 const uint32_t buf = it & 1;
                 const int tile = p.tile_begin + i * p.tile_step;
-                ab::mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1);
+                ab::mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1, 4);
                 ab::tc_fence_after();
 #pragma unroll 1
                 for (int c = 0; c < TILE_N / 32; ++c) {
@@ -276,44 +277,131 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
 
 // ---------------------------------------------------------------------------------------------
-// scan kernel v2 ("TS"): the query block stays resident in TENSOR MEMORY as the tcgen05 A operand,
-// so the only bytes that cross L2 -> SM are the bank rows.
+// scan kernel v2 ("TS"): the query block stays RESIDENT ON THE SM as the tcgen05 A operand, so the
+// only bytes that cross L2 -> SM are the bank rows.
 //
-//   TMEM (512 columns x 128 lanes per SM): columns [0,384) = 128 queries x 768 fp16 (2 per column),
-//   columns [384,448) and [448,512) = double-buffered 128 x 64 fp32 accumulators.
+//   128 queries x 768 fp16 = 192 KB per CTA: K-blocks 0..7 (512 K) live in TENSOR MEMORY (256 columns,
+//   A-from-TMEM MMAs), K-blocks 8..11 (256 K) in 64 KB of shared memory (A-from-smem MMAs).  That split
+//   leaves 256 TMEM columns for TWO 128 x 128 fp32 accumulator buffers (MMA of tile i+1 overlaps the
+//   epilogue of tile i) at UMMA N = 128 — measured: below N = 128 tcgen05.mma is issue-bound at ~46-50
+//   cycles per instruction, at N >= 128 it runs at the 64/128-cycle peak (tools/umma_bench.cu).
 //   kPair = true : a 2-CTA cluster (cta_group::2, UMMA M=256) covers 256 queries; each CTA owns 128
-//                  query rows in its own TMEM and streams HALF of every 64-passage tile (32 rows) through
-//                  its own shared memory, so each bank byte is fetched once per SM pair.
-//   kPair = false: one CTA (UMMA M=128) for <= 128 queries.
-//   smem: a 192 KB ring of single K-block slabs (rows x 128 B, 128B swizzle) - 24 x 8 KB or 48 x 4 KB.
-// Roles (256 threads): warp 0 TMA producer, warp 1 MMA issuer (leader CTA), warp 2 TMEM allocator,
-// warps 4-7 load the queries into TMEM once (tcgen05.st), then run the threshold-filter epilogue.
+//                  query rows and streams HALF of every 128-passage tile (64 full rows = 96 KB contiguous
+//                  in HBM, two 3-D TMA boxes of 48 KB) through its own shared memory, so each bank byte is
+//                  fetched once per SM pair.
+//   kPair = false: one CTA (UMMA M=128) for <= 128 queries, four 48 KB boxes per 128-row tile.
+//   smem: 64 KB resident query K-tail + 3 ring stages x 48 KB (K-major slabs [rows][128 B], 128B swizzle).
+// Roles (384 threads): warp 0 TMA producer, warp 1 MMA issuer (leader CTA), warp 2 TMEM allocator,
+// warps 4-11 load the query K-head into TMEM once (tcgen05.st), then run the threshold-filter epilogue
+// (warp w: TMEM lane group w%4, accumulator columns 64*((w-4)/4) .. +63).
 // ---------------------------------------------------------------------------------------------
-constexpr int TS_TILE_N = 64;
-constexpr int TS_A_COLS = DIM / 2;
-constexpr int TS_THREADS = 256;
+constexpr int TS_TILE_N = 128;
+constexpr int TS_KB_TMEM = 8;                        // K-blocks of the queries kept in TMEM
+constexpr int TS_KB_SMEM = K_BLOCKS - TS_KB_TMEM;    // K-blocks of the queries kept in smem
+constexpr int TS_A_COLS = TS_KB_TMEM * (BLOCK_K / 2);  // 256 TMEM columns
+constexpr int TS_A_SMEM_BYTES = TS_KB_SMEM * HALF_M * 128;  // 64 KB
+constexpr int TS_THREADS = 384;
+constexpr int TS_EPI_WARPS = 8;
 
 template <bool kPair>
 struct TsCfg {
-    static constexpr int ROWS_PER_CTA = kPair ? 32 : 64;
-    static constexpr int STAGE_BYTES = ROWS_PER_CTA * 128;
-    static constexpr int STAGES = kPair ? 48 : 24;
+    static constexpr int ROWS_PER_CTA = kPair ? 64 : 128;
+    static constexpr int SLAB_BYTES = ROWS_PER_CTA * 128;
+    static constexpr int KB_PER_STAGE = kPair ? 6 : 3;
+    static constexpr int STAGE_BYTES = KB_PER_STAGE * SLAB_BYTES;  // 48 KB
+    static constexpr int STAGES_PER_TILE = K_BLOCKS / KB_PER_STAGE;
+    static constexpr int STAGES = 3;
     static constexpr int UMMA_M = kPair ? 256 : 128;
     static constexpr int CTAS = kPair ? 2 : 1;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
+    static constexpr int SMEM_BYTES = TS_A_SMEM_BYTES + STAGES * STAGE_BYTES + 1024;
 };
+
+__device__ __forceinline__ float max32(const uint32_t (&r)[32]) {
+    float t[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) t[j] = fmaxf(__uint_as_float(r[j]), __uint_as_float(r[j + 16]));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t[j] = fmaxf(t[j], t[j + 8]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) t[j] = fmaxf(t[j], t[j + 4]);
+    return fmaxf(fmaxf(t[0], t[1]), fmaxf(t[2], t[3]));
+}
+
+// Per-thread slot reservation in a query's candidate list: a thread claims BLOCKS of slots with one
+// atomicAdd (>= 8 at a time) and fills them privately, so the L2 atomic (measured: thousands of cycles
+// of latency while the bank sweep saturates HBM) is paid once or twice per thread per kernel instead of
+// once per hit.  Slots of a block that stay unused are written as 0 = the smallest composite key, which
+// the selection kernel can never pick while k real candidates exist.
+struct SlotBlock {
+    uint32_t pos;
+    uint32_t left;
+};
+
+__device__ __forceinline__ void slots_release(SlotBlock& b, uint32_t capq, uint64_t* my_cand) {
+    while (b.left) {
+        if (b.pos < capq) my_cand[b.pos] = 0ull;
+        ++b.pos;
+        --b.left;
+    }
+}
+
+// r[j] for a run-time j without local memory: a 5-level select tree over the 32 registers.
+__device__ __forceinline__ float mux32(const uint32_t (&r)[32], int j) {
+    uint32_t a[16], b[8], c[4];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = (j & 16) ? r[i + 16] : r[i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) b[i] = (j & 8) ? a[i + 8] : a[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c[i] = (j & 4) ? b[i + 4] : b[i];
+    const uint32_t d0 = (j & 2) ? c[2] : c[0], d1 = (j & 2) ? c[3] : c[1];
+    return __uint_as_float((j & 1) ? d1 : d0);
+}
+
+// Slow path of the threshold filter for one thread (= one query row) that has at least one passing
+// score among 32 accumulator columns: hit bitmask by straight-line compares, then the (few) set bits are
+// walked, each value fetched with the select tree above.  Only lanes with hits run this; there are no
+// warp votes, no chains of dependent branches and no local-memory arrays.
+template <bool kBF16>
+__device__ __forceinline__ void append_hits32(const uint32_t (&r)[32], float bnd, int id0, int n_rows,
+                                              uint32_t* count_q, uint32_t capq, uint64_t* my_cand, SlotBlock& blk) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) m |= (__uint_as_float(r[j]) >= bnd) ? (1u << j) : 0u;
+    // columns past the end of the bank (zero-filled by TMA in the last tile) never count
+    const int valid = n_rows - id0;
+    if (valid < 32) m &= (valid <= 0) ? 0u : ((1u << valid) - 1u);
+    const uint32_t npass = __popc(m);
+    if (npass == 0) return;
+    if (npass > blk.left) {
+        slots_release(blk, capq, my_cand);
+        const uint32_t want = (npass + 7u) & ~7u;
+        blk.pos = atomicAdd(count_q, want);
+        blk.left = want;
+    }
+    while (m) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        const float v = mux32(r, j);
+        if (blk.pos < capq)
+            my_cand[blk.pos] = pack_candidate(bits_to_key(round_to_bits<kBF16>(v)), static_cast<uint32_t>(id0 + j));
+        ++blk.pos;
+        --blk.left;
+    }
+}
 
 template <bool kBF16, bool kPair>
 __global__ void __launch_bounds__(TS_THREADS, 1)
-mips_scan_ts_kernel(const __grid_constant__ CUtensorMap tmap_bank, const uint16_t* __restrict__ qstage,
-                    const ScanParams p) {
+mips_scan_ts_kernel(const __grid_constant__ CUtensorMap tmap_bank, const __grid_constant__ CUtensorMap tmap_q,
+                    const uint16_t* __restrict__ qstage, const ScanParams p) {
     using C = TsCfg<kPair>;
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[C::STAGES];
     __shared__ __align__(8) uint64_t empty_bar[C::STAGES];
     __shared__ __align__(8) uint64_t tmem_full_bar[2];
     __shared__ __align__(8) uint64_t tmem_empty_bar[2];
-    __shared__ __align__(8) uint64_t a_ready_bar;
+    __shared__ __align__(8) uint64_t a_tmem_bar;   // query K-head written to TMEM (all epilogue threads)
+    __shared__ __align__(8) uint64_t a_smem_bar;   // query K-tail landed in smem (TMA)
     __shared__ uint32_t tmem_base_smem;
 
     const uint32_t warp = threadIdx.x >> 5;
@@ -322,10 +410,15 @@ mips_scan_ts_kernel(const __grid_constant__ CUtensorMap tmap_bank, const uint16_
     const bool leader = cta_rank == 0;
     const int group = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
     const int num_groups = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
-    const uint32_t smem_base = (ab::smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t smem_base = (ab::smem_u32(smem_raw) + 1023u) & ~1023u;   // resident query K-tail
+    const uint32_t ring_base = smem_base + TS_A_SMEM_BYTES;
     uint8_t* smem_gen = smem_raw + (smem_base - ab::smem_u32(smem_raw));
+    uint8_t* ring_gen = smem_gen + TS_A_SMEM_BYTES;
 
-    if (warp == 0 && lane == 0) ab::tma_prefetch_desc(&tmap_bank);
+    if (warp == 0 && lane == 0) {
+        ab::tma_prefetch_desc(&tmap_bank);
+        ab::tma_prefetch_desc(&tmap_q);
+    }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
             ab::mbar_init(&full_bar[s], 1);
@@ -333,9 +426,10 @@ mips_scan_ts_kernel(const __grid_constant__ CUtensorMap tmap_bank, const uint16_
         }
         for (int b = 0; b < 2; ++b) {
             ab::mbar_init(&tmem_full_bar[b], 1);
-            ab::mbar_init(&tmem_empty_bar[b], 128u * C::CTAS);
+            ab::mbar_init(&tmem_empty_bar[b], static_cast<uint32_t>(TS_EPI_WARPS * C::CTAS));
         }
-        ab::mbar_init(&a_ready_bar, 128u * C::CTAS);
+        ab::mbar_init(&a_tmem_bar, static_cast<uint32_t>(TS_EPI_WARPS * 32 * C::CTAS));
+        ab::mbar_init(&a_smem_bar, 1);
         ab::fence_barrier_init();
     }
     if (warp == 2) ab::tmem_alloc<C::CTAS>(&tmem_base_smem, TMEM_COLS);
@@ -351,20 +445,36 @@ mips_scan_ts_kernel(const __grid_constant__ CUtensorMap tmap_bank, const uint16_
     if (warp == 0) {
         // ===================== TMA producer (every CTA streams its own rows) =====================
         if (lane == 0) {
+            // resident query K-tail: K-blocks 8..11 of this CTA's 128 query rows
+            if (leader) ab::mbar_arrive_expect_tx(&a_smem_bar, TS_A_SMEM_BYTES * C::CTAS);
+            for (int s = 0; s < TS_KB_SMEM; ++s) {
+                if constexpr (kPair) {
+                    ab::tma_load_2d_2sm(&tmap_q, &a_smem_bar, smem_gen + s * (HALF_M * 128), (TS_KB_TMEM + s) * BLOCK_K,
+                                        static_cast<int>(cta_rank) * HALF_M, ab::kEvictLast);
+                } else {
+                    ab::tma_load_2d(&tmap_q, &a_smem_bar, smem_gen + s * (HALF_M * 128), (TS_KB_TMEM + s) * BLOCK_K, 0,
+                                    ab::kEvictLast);
+                }
+            }
             uint32_t stage = 0, phase = 0;
+            long long w_empty = 0;
             for (int i = group; i < p.num_tiles; i += num_groups) {
                 const int tile = p.tile_begin + i * p.tile_step;
                 const int row0 = tile * TS_TILE_N + static_cast<int>(cta_rank) * C::ROWS_PER_CTA;
-                for (int kb = 0; kb < K_BLOCKS; ++kb) {
-                    ab::mbar_wait(&empty_bar[stage], phase ^ 1u);
-                    uint8_t* dst = smem_gen + stage * C::STAGE_BYTES;
+                for (int st = 0; st < C::STAGES_PER_TILE; ++st) {
+                    const long long t0 = clock64();
+                    ab::mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
+                    w_empty += clock64() - t0;
+                    uint8_t* dst = ring_gen + stage * C::STAGE_BYTES;
                     if constexpr (kPair) {
-                        // the leader's barrier collects the bytes of BOTH CTAs' loads
+                        // the leader's barrier collects the bytes of BOTH CTAs' boxes
                         if (leader) ab::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
-                        ab::tma_load_2d_2sm(&tmap_bank, &full_bar[stage], dst, kb * BLOCK_K, row0, ab::kEvictFirst);
+                        ab::tma_load_3d_2sm(&tmap_bank, &full_bar[stage], dst, 0, row0, st * C::KB_PER_STAGE,
+                                            ab::kEvictFirst);
                     } else {
                         ab::mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-                        ab::tma_load_2d(&tmap_bank, &full_bar[stage], dst, kb * BLOCK_K, row0, ab::kEvictFirst);
+                        ab::tma_load_3d(&tmap_bank, &full_bar[stage], dst, 0, row0, st * C::KB_PER_STAGE,
+                                        ab::kEvictFirst);
                     }
                     if (++stage == C::STAGES) {
                         stage = 0;
@@ -372,29 +482,52 @@ mips_scan_ts_kernel(const __grid_constant__ CUtensorMap tmap_bank, const uint16_
                     }
                 }
             }
+            if (p.dbg) p.dbg[blockIdx.x * 16 + 0] = w_empty;
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA only) =====================
         if (lane == 0 && leader) {
             constexpr uint32_t idesc = ab::umma_idesc_f16(C::UMMA_M, TS_TILE_N, kBF16);
-            ab::mbar_wait(&a_ready_bar, 0);
+            const long long tstart = clock64();
+            long long w_te = 0, w_full = 0;
+            ab::mbar_wait(&a_tmem_bar, 0, 5);
+            ab::mbar_wait(&a_smem_bar, 0, 6);
+            const long long w_a = clock64() - tstart;
             ab::tc_fence_after();
+            const uint64_t adesc0 = ab::umma_desc_k_sw128(smem_base);
             uint32_t stage = 0, phase = 0;
             int it = 0;
             for (int i = group; i < p.num_tiles; i += num_groups, ++it) {
                 const uint32_t buf = it & 1;
-                ab::mbar_wait(&tmem_empty_bar[buf], ((it >> 1) & 1) ^ 1u);
+                const long long t0 = clock64();
+                ab::mbar_wait(&tmem_empty_bar[buf], ((it >> 1) & 1) ^ 1u, 2);
+                w_te += clock64() - t0;
                 ab::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + TS_A_COLS + buf * TS_TILE_N;
-                for (int kb = 0; kb < K_BLOCKS; ++kb) {
-                    ab::mbar_wait(&full_bar[stage], phase);
-                    ab::tc_fence_after();
-                    const uint32_t sb = smem_base + stage * C::STAGE_BYTES;
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                        const uint64_t bdesc = ab::umma_desc_k_sw128(sb + k * UMMA_K * 2);
-                        ab::umma_ts<C::CTAS>(d_tmem, tmem_base + kb * (BLOCK_K / 2) + k * (UMMA_K / 2), bdesc, idesc,
-                                             (kb | k) != 0 ? 1u : 0u);
+                for (int st = 0; st < C::STAGES_PER_TILE; ++st) {
+                    const long long t1 = clock64();
+                    ab::mbar_wait(&full_bar[stage], phase, 3);
+                    w_full += clock64() - t1;
+                    ab::tc_fence_after();
+                    const uint64_t desc0 = ab::umma_desc_k_sw128(ring_base + stage * C::STAGE_BYTES);
+#pragma unroll
+                    for (int kbl = 0; kbl < C::KB_PER_STAGE; ++kbl) {
+                        const int kb = st * C::KB_PER_STAGE + kbl;
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                            const uint64_t bdesc =
+                                desc0 + static_cast<uint64_t>((kbl * C::SLAB_BYTES + k * UMMA_K * 2) >> 4);
+                            if (kb < TS_KB_TMEM) {
+                                ab::umma_ts<C::CTAS>(d_tmem, tmem_base + kb * (BLOCK_K / 2) + k * (UMMA_K / 2), bdesc,
+                                                     idesc, (kb | k) != 0 ? 1u : 0u);
+                            } else {
+                                const uint64_t adesc =
+                                    adesc0 +
+                                    static_cast<uint64_t>(((kb - TS_KB_TMEM) * (HALF_M * 128) + k * UMMA_K * 2) >> 4);
+                                ab::umma_ss<C::CTAS>(d_tmem, adesc, bdesc, idesc, 1u);
+                            }
+                        }
                     }
                     if constexpr (kPair) {
                         ab::umma_commit_2sm(&empty_bar[stage], 0x3);
@@ -412,16 +545,25 @@ mips_scan_ts_kernel(const __grid_constant__ CUtensorMap tmap_bank, const uint16_
                     ab::umma_commit(&tmem_full_bar[buf]);
                 }
             }
+            if (p.dbg) {
+                p.dbg[blockIdx.x * 16 + 1] = w_te;
+                p.dbg[blockIdx.x * 16 + 2] = w_full;
+                p.dbg[blockIdx.x * 16 + 3] = w_a;
+                p.dbg[blockIdx.x * 16 + 4] = clock64() - tstart;
+                p.dbg[blockIdx.x * 16 + 5] = it;
+            }
         }
     } else if (warp >= 4) {
-        // ===================== query load into TMEM, then the filter epilogue =====================
+        // ===================== query K-head into TMEM, then the filter epilogue =====================
         const uint32_t lg = warp & 3u;
-        const uint32_t q = cta_rank * 128u + lg * 32u + lane;  // row of the staged query block
+        const uint32_t half = (warp - 4u) >> 2;                 // which 64 accumulator columns
+        const uint32_t q = cta_rank * 128u + lg * 32u + lane;   // row of the staged query block
         const uint32_t lane_addr = tmem_base + ((lg * 32u) << 16);
         {
             const uint4* src = reinterpret_cast<const uint4*>(qstage + static_cast<size_t>(q) * DIM);
 #pragma unroll 1
-            for (int kb = 0; kb < K_BLOCKS; ++kb) {
+            for (int kb = static_cast<int>(half) * (TS_KB_TMEM / 2); kb < static_cast<int>(half + 1) * (TS_KB_TMEM / 2);
+                 ++kb) {
                 uint32_t r[32];
 #pragma unroll
                 for (int v = 0; v < 8; ++v) {
@@ -436,55 +578,62 @@ mips_scan_ts_kernel(const __grid_constant__ CUtensorMap tmap_bank, const uint16_
             ab::tmem_st_wait();
             ab::tc_fence_before();
             if (leader) {
-                ab::mbar_arrive(&a_ready_bar);
+                ab::mbar_arrive(&a_tmem_bar);
             } else {
-                ab::mbar_arrive_cluster(&a_ready_bar, 0);
+                ab::mbar_arrive_cluster(&a_tmem_bar, 0);
             }
         }
         const float bnd = (static_cast<int>(q) < p.nq) ? p.bound[q] : INFINITY;
         uint64_t* my_cand = p.cand + static_cast<size_t>(q) * p.capq;
         int it = 0;
+        long long w_tf = 0, w_ld = 0, w_arr = 0, w_max = 0, w_slow = 0;
+        SlotBlock blk = {0u, 0u};
         for (int i = group; i < p.num_tiles; i += num_groups, ++it) {
             const uint32_t buf = it & 1;
             const int tile = p.tile_begin + i * p.tile_step;
-            ab::mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1);
+            const long long t0 = clock64();
+            ab::mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1, 4);
+            const long long t1 = clock64();
+            w_tf += t1 - t0;
             ab::tc_fence_after();
-#pragma unroll 1
-            for (int c = 0; c < TS_TILE_N / 32; ++c) {
-                uint32_t r[32];
-                ab::tmem_ld32(lane_addr + TS_A_COLS + buf * TS_TILE_N + c * 32, r);
-                ab::tmem_ld_wait();
-                float m = __uint_as_float(r[0]);
-#pragma unroll
-                for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(r[j]));
-                if (__any_sync(0xffffffffu, m >= bnd)) {
-                    const int id0 = tile * TS_TILE_N + c * 32;
-                    uint32_t npass = 0;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        npass += (__uint_as_float(r[j]) >= bnd && id0 + j < p.n_rows) ? 1u : 0u;
-                    if (npass) {
-                        uint32_t pos = atomicAdd(&p.count[q], npass);
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float v = __uint_as_float(r[j]);
-                            if (v >= bnd && id0 + j < p.n_rows) {
-                                if (pos < p.capq)
-                                    my_cand[pos] = pack_candidate(bits_to_key(round_to_bits<kBF16>(v)),
-                                                                  static_cast<uint32_t>(id0 + j));
-                                ++pos;
-                            }
-                        }
-                    }
+            const uint32_t d_addr = lane_addr + TS_A_COLS + buf * TS_TILE_N + half * 64u;
+            uint32_t r0[32], r1[32];
+            ab::tmem_ld32(d_addr, r0);
+            ab::tmem_ld32(d_addr + 32, r1);
+            ab::tmem_ld_wait();
+            const long long t2 = clock64();
+            w_ld += t2 - t1;
+            // the accumulator columns are in registers: hand the buffer back before filtering
+            ab::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (leader) {
+                    ab::mbar_arrive(&tmem_empty_bar[buf]);
+                } else {
+                    ab::mbar_arrive_cluster(&tmem_empty_bar[buf], 0);
                 }
             }
-            ab::tc_fence_before();
-            if (leader) {
-                ab::mbar_arrive(&tmem_empty_bar[buf]);
-            } else {
-                ab::mbar_arrive_cluster(&tmem_empty_bar[buf], 0);
-            }
+            const long long t3 = clock64();
+            w_arr += t3 - t2;
+            const int id0 = tile * TS_TILE_N + static_cast<int>(half) * 64;
+            // lane-divergent on purpose: only rows with a hit pay for the slow path
+            const float mx0 = max32(r0), mx1 = max32(r1);
+            asm volatile("" ::"f"(mx0), "f"(mx1));
+            const long long t4 = clock64();
+            w_max += t4 - t3;
+            if (mx0 >= bnd) append_hits32<kBF16>(r0, bnd, id0, p.n_rows, &p.count[q], p.capq, my_cand, blk);
+            if (mx1 >= bnd) append_hits32<kBF16>(r1, bnd, id0 + 32, p.n_rows, &p.count[q], p.capq, my_cand, blk);
+            __syncwarp();
+            w_slow += clock64() - t4;
         }
+        slots_release(blk, p.capq, my_cand);
+        if (p.dbg && warp == 4 && lane == 0) {
+            p.dbg[blockIdx.x * 16 + 7] = w_ld;
+            p.dbg[blockIdx.x * 16 + 8] = w_arr;
+            p.dbg[blockIdx.x * 16 + 9] = w_max;
+            p.dbg[blockIdx.x * 16 + 10] = w_slow;
+        }
+        if (p.dbg && warp == 4 && lane == 0) p.dbg[blockIdx.x * 16 + 6] = w_tf;
     }
 
     ab::tc_fence_before();
@@ -637,10 +786,12 @@ mips_select_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ count, ui
     }
     if (mode & SEL_WRITE_BOUND) {
         if (t == 0) {
-            bound[q] = (kk == static_cast<uint32_t>(k) && kk > 0)
-                           ? lower_bound_for_key<kBF16>(static_cast<uint32_t>(win[kk - 1] >> 32))
-                           : -INFINITY;
-            count[q] = 0;
+            if (kk == static_cast<uint32_t>(k) && kk > 0) {
+                bound[q] = lower_bound_for_key<kBF16>(static_cast<uint32_t>(win[kk - 1] >> 32));
+            } else if (!(mode & SEL_CARRY)) {
+                bound[q] = -INFINITY;  // refinement passes keep the previous (still valid) bound instead
+            }
+            if (!(mode & SEL_CARRY)) count[q] = 0;
         }
     }
 }
@@ -781,6 +932,7 @@ static int launch_scan(const CUtensorMap& tq, const CUtensorMap& tb, const ScanP
 
 // 0 = SS kernel (queries streamed through smem), 1 = TS kernel (queries resident in TMEM)
 static int g_kernel_mode = -1;
+static unsigned long long* g_dbg = nullptr;  // device buffer for wait-cycle counters of the main scan
 static int kernel_mode() {
     if (g_kernel_mode < 0) {
         const char* e = getenv("ATLAS_B200_MIPS_KERNEL");
@@ -790,7 +942,8 @@ static int kernel_mode() {
 }
 
 template <bool kBF16, bool kPair>
-static int launch_scan_ts(const CUtensorMap& tb, const uint16_t* qstage, const ScanParams& p, cudaStream_t s) {
+static int launch_scan_ts(const CUtensorMap& tb, const CUtensorMap& tq, const uint16_t* qstage, const ScanParams& p,
+                          cudaStream_t s) {
     using C = TsCfg<kPair>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -813,7 +966,7 @@ static int launch_scan_ts(const CUtensorMap& tb, const uint16_t* qstage, const S
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    AB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mips_scan_ts_kernel<kBF16, kPair>, tb, qstage, p));
+    AB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mips_scan_ts_kernel<kBF16, kPair>, tb, tq, qstage, p));
     abh::count_launch();
     return ATLAS_B200_OK;
 }
@@ -849,18 +1002,18 @@ static int topk_impl(const void* bank, int64_t n, int64_t ld, const void* querie
     const int tile_n = ts ? TS_TILE_N : TILE_N;
     // tensor maps: SS = query block + 128-row bank boxes; TS = 64-row (single CTA) / 32-row (CTA pair) boxes
     CUtensorMap tq, tb, tb_pair;
+    rc = abh::make_tmap_2d_16bit(&tq, w.qstage, QBLOCK, DIM, DIM, HALF_M, BLOCK_K, kBF16);
+    if (rc) return rc;
     if (!ts) {
-        rc = abh::make_tmap_2d_16bit(&tq, w.qstage, QBLOCK, DIM, DIM, HALF_M, BLOCK_K, kBF16);
-        if (rc) return rc;
         rc = abh::make_tmap_2d_16bit(&tb, bank, static_cast<uint64_t>(n), DIM, static_cast<uint64_t>(ld), TILE_N,
                                      BLOCK_K, kBF16);
         if (rc) return rc;
     } else {
-        rc = abh::make_tmap_2d_16bit(&tb, bank, static_cast<uint64_t>(n), DIM, static_cast<uint64_t>(ld),
-                                     TsCfg<false>::ROWS_PER_CTA, BLOCK_K, kBF16);
+        rc = abh::make_tmap_kslabs_16bit(&tb, bank, static_cast<uint64_t>(n), DIM, static_cast<uint64_t>(ld),
+                                         TsCfg<false>::ROWS_PER_CTA, TsCfg<false>::KB_PER_STAGE, kBF16);
         if (rc) return rc;
-        rc = abh::make_tmap_2d_16bit(&tb_pair, bank, static_cast<uint64_t>(n), DIM, static_cast<uint64_t>(ld),
-                                     TsCfg<true>::ROWS_PER_CTA, BLOCK_K, kBF16);
+        rc = abh::make_tmap_kslabs_16bit(&tb_pair, bank, static_cast<uint64_t>(n), DIM, static_cast<uint64_t>(ld),
+                                         TsCfg<true>::ROWS_PER_CTA, TsCfg<true>::KB_PER_STAGE, kBF16);
         if (rc) return rc;
     }
 
@@ -880,17 +1033,19 @@ static int topk_impl(const void* bank, int64_t n, int64_t ld, const void* querie
         p.count = w.count;
         p.cand = w.cand;
         p.capq = w.capq;
+        p.dbg = nullptr;
         uint16_t* os_b = os + static_cast<size_t>(q0) * k;
         int64_t* oi_b = out_ids + static_cast<size_t>(q0) * k;
         auto scan = [&](const ScanParams& sp) -> int {
             if (!ts) return launch_scan<kBF16>(tq, tb, sp, s);
-            if (sp.n_halves == 2) return launch_scan_ts<kBF16, true>(tb_pair, w.qstage, sp, s);
-            return launch_scan_ts<kBF16, false>(tb, w.qstage, sp, s);
+            if (sp.n_halves == 2) return launch_scan_ts<kBF16, true>(tb_pair, tq, w.qstage, sp, s);
+            return launch_scan_ts<kBF16, false>(tb, tq, w.qstage, sp, s);
         };
 
         if (!exhaustive) {
+            int first_tile = 0;
             if (n > static_cast<int64_t>(w.capq)) {
-                // (1)+(2): threshold from a strided sample of ~2*sqrt(k*n) rows
+                // (1)+(2): first bound from a strided sample of ~2*sqrt(k*n) rows (every score kept)
                 double m = 2.0 * sqrt(static_cast<double>(k) * static_cast<double>(n));
                 if (m < 4096) m = 4096;
                 if (m > w.capq / 2) m = w.capq / 2;
@@ -905,14 +1060,34 @@ static int topk_impl(const void* bank, int64_t n, int64_t ld, const void* querie
                 mips_select_kernel<kBF16><<<nqb, SEL_THREADS, 0, s>>>(w.cand, w.count, w.capq, k, SEL_WRITE_BOUND,
                                                                      w.bound, nullptr, nullptr, 0, 0, nullptr);
                 abh::count_launch();
+                // (2b) refinement: sweep the first ~1/10 of the bank with that bound, then tighten the bound to
+                // the k-th best seen so far (its winners stay in the lists) before sweeping the other 9/10.
+                // Expected survivors per query: k*n_A/m in this part, k*n_B/n_A (~9k) in the rest.
+                const int tiles_a = total_tiles / 10;
+                if (tiles_a * static_cast<int64_t>(tile_n) >= 8 * static_cast<int64_t>(m)) {
+                    p.tile_begin = 0;
+                    p.tile_step = 1;
+                    p.num_tiles = tiles_a;
+                    abh::prof_begin(s);
+                    rc = scan(p);
+                    abh::prof_end(s);
+                    if (rc) return rc;
+                    mips_select_kernel<kBF16><<<nqb, SEL_THREADS, 0, s>>>(w.cand, w.count, w.capq, k,
+                                                                         SEL_WRITE_BOUND | SEL_CARRY, w.bound, nullptr,
+                                                                         nullptr, 0, 0, status);
+                    abh::count_launch();
+                    first_tile = tiles_a;
+                }
             }
-            // (3)+(4)
-            p.tile_begin = 0;
+            // (3)+(4): the main sweep and the final selection
+            p.tile_begin = first_tile;
             p.tile_step = 1;
-            p.num_tiles = total_tiles;
+            p.num_tiles = total_tiles - first_tile;
+            p.dbg = g_dbg;
             abh::prof_begin(s);
             rc = scan(p);
             abh::prof_end(s);
+            p.dbg = nullptr;
             if (rc) return rc;
             mips_select_kernel<kBF16><<<nqb, SEL_THREADS, 0, s>>>(w.cand, w.count, w.capq, k, SEL_EMIT, w.bound, os_b,
                                                                  oi_b, id_base, id_stride, status);
@@ -944,6 +1119,9 @@ static int topk_impl(const void* bank, int64_t n, int64_t ld, const void* querie
 extern "C" {
 
 void atlas_b200_mips_set_kernel(int32_t mode) { mips::g_kernel_mode = mode ? 1 : 0; }
+void atlas_b200_mips_set_debug_counters(void* device_u64_buffer) {
+    mips::g_dbg = static_cast<unsigned long long*>(device_u64_buffer);
+}
 
 size_t atlas_b200_mips_workspace_bytes(int64_t n, int32_t nq, int32_t k) {
     if (n < 1) n = 1;

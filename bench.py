@@ -37,8 +37,8 @@ METRIC = "retrieve queries/sec (exact top-40 MIPS search_knn over the 768-d fp16
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=N_LOCAL, help="passages per GPU (default: the BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -54,42 +54,47 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md):
+    one `nvidia-smi -lms 20` process is started before the region and stopped after it."""
 
     QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        self.index, self.samples, self.stop = index, [], False
-        self.thread = threading.Thread(target=self._run, daemon=True)
-
-    def _run(self):
-        while not self.stop:
-            try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) >= 6:
-                    self.samples.append(parts)
-            except Exception:
-                pass
-            time.sleep(0.1)
+        self.index, self.samples, self.proc = index, [], None
 
     def __enter__(self):
-        self.thread.start()
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.15)  # let the first samples land before the region starts
+        except Exception:
+            self.proc = None
         return self
 
     def __exit__(self, *a):
-        self.stop = True
-        self.thread.join(timeout=6)
+        if self.proc is None:
+            return
+        time.sleep(0.05)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        for line in out.strip().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 6:
+                self.samples.append(parts)
 
     def summary(self):
         sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
         mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[j] for s in self.samples for j in range(4) if s[2 + j].lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.samples)}
 
 
 def make_bank(rows, device, seed):
@@ -266,7 +271,10 @@ def run_ours(args):
         return
 
     peak, peak_src = peaks()
-    kernel_ms = kms.value / max(1, kn.value)
+    # the bank sweep is bracketed per launch inside the library (CUDA events on the launching stream);
+    # one search sweeps the bank exactly once, split over `sweeps_per_search` launches of the same kernel
+    sweeps_per_search = max(1, kn.value // args.steps)
+    kernel_ms = kms.value / args.steps                       # all sweep launches of one search
     alg_bytes = args.rows * DIM * 2
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
     line = {
@@ -276,8 +284,10 @@ def run_ours(args):
         "config": workload_config(args),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
-                     "kernel": "mips_scan_kernel (main bank sweep)", "kernel_ms": kernel_ms,
-                     "kernel_launches_timed": kn.value, "algorithmic_bytes_per_launch": alg_bytes,
+                     "kernel": "mips_scan_ts_kernel (bank sweep; one search = %d launches covering the bank once)"
+                               % sweeps_per_search,
+                     "kernel_ms_per_search": kernel_ms, "kernel_launches_timed": kn.value,
+                     "algorithmic_bytes_per_search": alg_bytes,
                      "kernel_share_of_step": kernel_ms / ms_per_step if ms_per_step else None},
         "e2e": {"value": NQ / (e2e_ms * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,

@@ -73,6 +73,10 @@ int atlas_b200_mips_topk(const void* bank, int64_t n, int64_t ld, int32_t is_bf1
  * A/B measurements).  Also settable with the environment variable ATLAS_B200_MIPS_KERNEL=ss|ts. */
 void atlas_b200_mips_set_kernel(int32_t mode);
 
+/* Development aid: when a device buffer of gridDim*8 uint64 is registered, the main TS scan kernel
+ * accumulates per-CTA cycle counters (producer wait, MMA waits, epilogue wait, total).  NULL = off. */
+void atlas_b200_mips_set_debug_counters(void* device_u64_buffer);
+
 /* Same contract, exact for ANY input (chunked scan, no thresholds); slower.  Used as the fallback
  * when `status` reports overflow.  Synchronous with respect to nothing: enqueued on `stream`. */
 int atlas_b200_mips_topk_exhaustive(const void* bank, int64_t n, int64_t ld, int32_t is_bf16,
