@@ -61,6 +61,10 @@ def lib():
     L.atlas_b200_cast_f32.argtypes = [c.c_void_p, c.c_void_p, c.c_int64, c.c_int32, c.c_void_p]
     L.atlas_b200_mips_set_kernel.restype = None
     L.atlas_b200_mips_set_kernel.argtypes = [c.c_int32]
+    L.atlas_b200_linear.restype = c.c_int
+    L.atlas_b200_linear.argtypes = [c.c_void_p, c.c_int64, c.c_void_p, c.c_int64, c.c_void_p, c.c_void_p, c.c_int64,
+                                    c.c_void_p, c.c_int64, c.c_int32, c.c_int32, c.c_int32, c.c_int32, c.c_int32,
+                                    c.c_void_p]
     L.atlas_b200_mips_set_debug_counters.restype = None
     L.atlas_b200_mips_set_debug_counters.argtypes = [c.c_void_p]
     L.atlas_b200_profile_enable.restype = None
@@ -81,6 +85,7 @@ EXPORTED_SYMBOLS = [
     "atlas_b200_topk_merge",
     "atlas_b200_search_host",
     "atlas_b200_cast_f32",
+    "atlas_b200_linear",
     "atlas_b200_mips_set_kernel",
     "atlas_b200_mips_set_debug_counters",
     "atlas_b200_profile_enable",

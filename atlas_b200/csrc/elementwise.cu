@@ -1,0 +1,242 @@
+// Row-wise normalisation, embedding and pooling kernels of the Contriever / FiD forward pass.
+// HBM-bound byte work: one warp per row, 16-byte vector loads/stores, fp32 statistics in registers,
+// warp-shuffle reductions; nothing is re-read.  Rounding points follow the reference exactly:
+//
+//   bert_layernorm   BertLayerNorm.forward, src/modeling_bert.py:104-114 (callers pass `.float()` input,
+//                    :245,386,465):  xn = (x - mean(x)) * rsqrt(mean(x^2) + eps)   [fp32, UNCENTRED 2nd moment]
+//                                    y  = w * half(xn) + b                          [two 16-bit roundings]
+//   t5_rmsnorm       T5LayerNorm.forward, src/modeling_t5.py:244-253:
+//                                    y  = w * half(x * rsqrt(mean(x^2) + eps))
+//   bert_embed_ln    BertEmbeddings.forward, src/modeling_bert.py:213-247: word + token_type (+= position),
+//                    16-bit adds in that order, then BertLayerNorm on the fp32 copy
+//   masked_mean_pool Contriever.forward, src/retrievers.py:50-53: masked_fill(~mask, 0).sum(1) / mask.sum(1)
+//                    (sum accumulated in fp32 and rounded once, then one 16-bit division)
+#include "common.cuh"
+#include "host_common.h"
+
+namespace ew {
+
+constexpr int MAXV = 8;  // 16-byte vectors per lane -> rows of up to 8*32*8 = 2048 elements
+
+template <bool kBF16>
+__device__ __forceinline__ float lo(uint32_t w) {
+    if constexpr (kBF16) return __bfloat162float(__ushort_as_bfloat16(static_cast<unsigned short>(w & 0xFFFFu)));
+    return __half2float(__ushort_as_half(static_cast<unsigned short>(w & 0xFFFFu)));
+}
+template <bool kBF16>
+__device__ __forceinline__ float hi(uint32_t w) {
+    if constexpr (kBF16) return __bfloat162float(__ushort_as_bfloat16(static_cast<unsigned short>(w >> 16)));
+    return __half2float(__ushort_as_half(static_cast<unsigned short>(w >> 16)));
+}
+template <bool kBF16>
+__device__ __forceinline__ uint32_t rnd(float v) {
+    if constexpr (kBF16) return __bfloat16_as_ushort(__float2bfloat16_rn(v));
+    return __half_as_ushort(__float2half_rn(v));
+}
+template <bool kBF16>
+__device__ __forceinline__ float rf(float v) {  // round through the 16-bit type
+    if constexpr (kBF16) return __bfloat162float(__float2bfloat16_rn(v));
+    return __half2float(__float2half_rn(v));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// y = w * r16(norm(x)) (+ b), all products/sums rounded to 16 bits like torch's half kernels
+template <bool kBF16, bool kCentre, bool kBias>
+__device__ __forceinline__ void norm_row(float (&v)[MAXV][8], int nvec, int H, float eps, const uint16_t* w,
+                                         const uint16_t* b, uint16_t* y, int lane) {
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+        if (lane + 32 * i < nvec)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                s1 += v[i][e];
+                s2 += v[i][e] * v[i][e];
+            }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    const float mean = kCentre ? s1 / static_cast<float>(H) : 0.f;
+    const float rstd = rsqrtf(s2 / static_cast<float>(H) + eps);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int vec = lane + 32 * i;
+        if (vec < nvec) {
+            const uint4 wv = __ldg(reinterpret_cast<const uint4*>(w) + vec);
+            const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+            uint32_t bb[4] = {0, 0, 0, 0};
+            if (kBias) {
+                const uint4 bv = __ldg(reinterpret_cast<const uint4*>(b) + vec);
+                bb[0] = bv.x; bb[1] = bv.y; bb[2] = bv.z; bb[3] = bv.w;
+            }
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float n0 = rf<kBF16>((v[i][2 * e] - mean) * rstd);
+                const float n1 = rf<kBF16>((v[i][2 * e + 1] - mean) * rstd);
+                float y0 = rf<kBF16>(lo<kBF16>(ww[e]) * n0);
+                float y1 = rf<kBF16>(hi<kBF16>(ww[e]) * n1);
+                if (kBias) {
+                    y0 = y0 + lo<kBF16>(bb[e]);
+                    y1 = y1 + hi<kBF16>(bb[e]);
+                }
+                o[e] = rnd<kBF16>(y0) | (rnd<kBF16>(y1) << 16);
+            }
+            reinterpret_cast<uint4*>(y)[vec] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
+template <bool kBF16, bool kCentre, bool kBias>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const uint16_t* __restrict__ x, int64_t ldx, const uint16_t* __restrict__ w,
+                 const uint16_t* __restrict__ b, uint16_t* __restrict__ y, int64_t ldy, int rows, int H, float eps) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const int nvec = H >> 3;
+    float v[MAXV][8];
+    const uint4* xr = reinterpret_cast<const uint4*>(x + row * ldx);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        if (lane + 32 * i < nvec) {
+            const uint4 t = __ldg(xr + lane + 32 * i);
+            const uint32_t tw[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                v[i][2 * e] = lo<kBF16>(tw[e]);
+                v[i][2 * e + 1] = hi<kBF16>(tw[e]);
+            }
+        }
+    }
+    norm_row<kBF16, kCentre, kBias>(v, nvec, H, eps, w, b, y + row * ldy, lane);
+}
+
+template <bool kBF16>
+__global__ void __launch_bounds__(256)
+bert_embed_ln_kernel(const int64_t* __restrict__ input_ids, const int64_t* __restrict__ token_type_ids,
+                     const uint16_t* __restrict__ word_emb, const uint16_t* __restrict__ type_emb,
+                     const uint16_t* __restrict__ pos_emb, const uint16_t* __restrict__ w,
+                     const uint16_t* __restrict__ b, uint16_t* __restrict__ y, int rows, int L, int H, float eps) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const int nvec = H >> 3;
+    const int64_t tok = input_ids[row];
+    const int64_t typ = token_type_ids ? token_type_ids[row] : 0;
+    const int pos = row % L;  // position_ids = arange(L) (modeling_bert.py:223-224)
+    const uint4* we = reinterpret_cast<const uint4*>(word_emb + tok * H);
+    const uint4* te = reinterpret_cast<const uint4*>(type_emb + typ * H);
+    const uint4* pe = reinterpret_cast<const uint4*>(pos_emb + static_cast<int64_t>(pos) * H);
+    float v[MAXV][8];
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        if (lane + 32 * i < nvec) {
+            const uint4 a = __ldg(we + lane + 32 * i), c = __ldg(te + lane + 32 * i), d = __ldg(pe + lane + 32 * i);
+            const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, cw[4] = {c.x, c.y, c.z, c.w}, dw[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                // embeddings = inputs_embeds + token_type_embeddings; embeddings += position_embeddings (16-bit)
+                v[i][2 * e] = rf<kBF16>(rf<kBF16>(lo<kBF16>(aw[e]) + lo<kBF16>(cw[e])) + lo<kBF16>(dw[e]));
+                v[i][2 * e + 1] = rf<kBF16>(rf<kBF16>(hi<kBF16>(aw[e]) + hi<kBF16>(cw[e])) + hi<kBF16>(dw[e]));
+            }
+        }
+    }
+    norm_row<kBF16, true, true>(v, nvec, H, eps, w, b, y + static_cast<int64_t>(row) * H, lane);
+}
+
+// out[b, :] = sum_l mask[b,l] * x[b,l,:] / sum_l mask[b,l]; one block per (b, 256-column slab)
+template <bool kBF16>
+__global__ void __launch_bounds__(256)
+masked_mean_pool_kernel(const uint16_t* __restrict__ x, const int64_t* __restrict__ mask, uint16_t* __restrict__ out,
+                        int64_t ld_out, int L, int H) {
+    const int b = blockIdx.x;
+    const int col = blockIdx.y * blockDim.x + threadIdx.x;
+    if (col >= H) return;
+    float acc = 0.f;
+    int64_t cnt = 0;
+    for (int l = 0; l < L; ++l) {
+        const int64_t m = mask[static_cast<int64_t>(b) * L + l];
+        cnt += (m != 0);
+        if (m != 0) {
+            const uint16_t h = x[(static_cast<int64_t>(b) * L + l) * H + col];
+            acc += kBF16 ? __bfloat162float(__ushort_as_bfloat16(h)) : __half2float(__ushort_as_half(h));
+        }
+    }
+    const float s = rf<kBF16>(acc);                                  // last_hidden.sum(dim=1) in 16 bits
+    out[b * ld_out + col] = static_cast<uint16_t>(rnd<kBF16>(s / static_cast<float>(cnt)));
+}
+
+}  // namespace ew
+
+extern "C" {
+
+int atlas_b200_layernorm(const void* x, int64_t ldx, const void* weight, const void* bias, void* y, int64_t ldy,
+                         int32_t rows, int32_t H, float eps, int32_t kind, int32_t is_bf16, void* stream) {
+    AB_REQUIRE(rows >= 0 && H > 0 && H % 8 == 0 && H <= ew::MAXV * 256, "layernorm: H=%d must be a multiple of 8, <= %d",
+               H, ew::MAXV * 256);
+    AB_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0, "layernorm: row strides must be multiples of 8");
+    AB_REQUIRE(kind == 0 || kind == 1, "layernorm: kind must be 0 (BertLayerNorm) or 1 (T5 RMSNorm)");
+    AB_REQUIRE(kind == 1 || bias != nullptr, "BertLayerNorm needs a bias");
+    if (rows == 0) return ATLAS_B200_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int grid = (rows + 7) / 8;
+    const uint16_t *xp = static_cast<const uint16_t*>(x), *wp = static_cast<const uint16_t*>(weight),
+                   *bp = static_cast<const uint16_t*>(bias);
+    uint16_t* yp = static_cast<uint16_t*>(y);
+    if (kind == 0) {
+        if (is_bf16) ew::layernorm_kernel<true, true, true><<<grid, 256, 0, s>>>(xp, ldx, wp, bp, yp, ldy, rows, H, eps);
+        else ew::layernorm_kernel<false, true, true><<<grid, 256, 0, s>>>(xp, ldx, wp, bp, yp, ldy, rows, H, eps);
+    } else {
+        if (is_bf16) ew::layernorm_kernel<true, false, false><<<grid, 256, 0, s>>>(xp, ldx, wp, bp, yp, ldy, rows, H, eps);
+        else ew::layernorm_kernel<false, false, false><<<grid, 256, 0, s>>>(xp, ldx, wp, bp, yp, ldy, rows, H, eps);
+    }
+    abh::count_launch();
+    AB_CUDA_CHECK(cudaGetLastError());
+    return ATLAS_B200_OK;
+}
+
+int atlas_b200_bert_embed_ln(const int64_t* input_ids, const int64_t* token_type_ids, const void* word_emb,
+                             const void* type_emb, const void* pos_emb, const void* ln_weight, const void* ln_bias,
+                             void* y, int32_t batch, int32_t L, int32_t H, float eps, int32_t is_bf16, void* stream) {
+    AB_REQUIRE(batch >= 0 && L > 0 && H % 8 == 0 && H <= ew::MAXV * 256, "bert_embed_ln: bad shape");
+    const int rows = batch * L;
+    if (rows == 0) return ATLAS_B200_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int grid = (rows + 7) / 8;
+    const uint16_t *we = static_cast<const uint16_t*>(word_emb), *te = static_cast<const uint16_t*>(type_emb),
+                   *pe = static_cast<const uint16_t*>(pos_emb), *w = static_cast<const uint16_t*>(ln_weight),
+                   *b = static_cast<const uint16_t*>(ln_bias);
+    if (is_bf16)
+        ew::bert_embed_ln_kernel<true><<<grid, 256, 0, s>>>(input_ids, token_type_ids, we, te, pe, w, b,
+                                                            static_cast<uint16_t*>(y), rows, L, H, eps);
+    else
+        ew::bert_embed_ln_kernel<false><<<grid, 256, 0, s>>>(input_ids, token_type_ids, we, te, pe, w, b,
+                                                             static_cast<uint16_t*>(y), rows, L, H, eps);
+    abh::count_launch();
+    AB_CUDA_CHECK(cudaGetLastError());
+    return ATLAS_B200_OK;
+}
+
+int atlas_b200_masked_mean_pool(const void* x, const int64_t* mask, void* out, int64_t ld_out, int32_t batch, int32_t L,
+                                int32_t H, int32_t is_bf16, void* stream) {
+    AB_REQUIRE(batch >= 0 && L > 0 && H > 0, "masked_mean_pool: bad shape");
+    if (batch == 0) return ATLAS_B200_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    dim3 grid(batch, (H + 255) / 256);
+    if (is_bf16)
+        ew::masked_mean_pool_kernel<true><<<grid, 256, 0, s>>>(static_cast<const uint16_t*>(x), mask,
+                                                               static_cast<uint16_t*>(out), ld_out, L, H);
+    else
+        ew::masked_mean_pool_kernel<false><<<grid, 256, 0, s>>>(static_cast<const uint16_t*>(x), mask,
+                                                                static_cast<uint16_t*>(out), ld_out, L, H);
+    abh::count_launch();
+    AB_CUDA_CHECK(cudaGetLastError());
+    return ATLAS_B200_OK;
+}
+
+}  // extern "C"

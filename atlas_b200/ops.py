@@ -146,3 +146,43 @@ def topk_merge_blob(blob_all, ids_off, world, nq_total, k, q_begin, nq_out, dtyp
                                       blob_bytes // 8, 1 if dtype == torch.bfloat16 else 0, world, nq_total, k,
                                       q_begin, nq_out, _ptr(out_s), _ptr(out_i), current_stream_ptr()))
     return out_s, out_i
+
+
+# ---------------------------------------------------------------------------------------------
+# dense layers (csrc/gemm.cu)
+# ---------------------------------------------------------------------------------------------
+EPI_NONE, EPI_BIAS, EPI_GELU, EPI_RESIDUAL, EPI_GATED = 0, 1, 2, 3, 4
+
+
+def linear(x, weight, bias=None, residual=None, epilogue=None, out=None):
+    """y = epilogue(x @ weight.T) on tcgen05.  x [..., K], weight [N, K] (nn.Linear layout), 16-bit.
+
+    epilogue: EPI_NONE / EPI_BIAS / EPI_GELU / EPI_RESIDUAL / EPI_GATED (see include/atlas_b200.h);
+    default: EPI_RESIDUAL if `residual` is given, else EPI_BIAS if `bias` is given, else EPI_NONE."""
+    require_cuda(x, "x")
+    if x.dtype not in (torch.float16, torch.bfloat16) or weight.dtype != x.dtype:
+        raise AtlasB200Error(f"linear: x and weight must both be fp16 or bf16 (got {x.dtype}, {weight.dtype})")
+    K = x.shape[-1]
+    N = weight.shape[0]
+    if weight.shape[1] != K:
+        raise AtlasB200Error(f"linear: weight {tuple(weight.shape)} does not match K={K}")
+    x2 = x.reshape(-1, K)
+    if x2.stride(-1) != 1:
+        x2 = x2.contiguous()
+    w = weight if weight.stride(-1) == 1 else weight.contiguous()
+    M = x2.shape[0]
+    if epilogue is None:
+        epilogue = EPI_RESIDUAL if residual is not None else (EPI_BIAS if bias is not None else EPI_NONE)
+    n_out = N // 2 if epilogue == EPI_GATED else N
+    if out is None:
+        out = torch.empty((M, n_out), dtype=x.dtype, device=x.device)
+    r2 = None
+    if residual is not None:
+        r2 = residual.reshape(-1, residual.shape[-1])
+        if r2.stride(-1) != 1:
+            r2 = r2.contiguous()
+    check(lib().atlas_b200_linear(
+        _ptr(x2), x2.stride(0), _ptr(w), w.stride(0), _ptr(bias) if bias is not None else None,
+        _ptr(r2) if r2 is not None else None, r2.stride(0) if r2 is not None else 0, _ptr(out), out.stride(0),
+        M, N, K, epilogue, 1 if x.dtype == torch.bfloat16 else 0, current_stream_ptr()))
+    return out.reshape(*x.shape[:-1], n_out)

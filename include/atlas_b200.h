@@ -107,6 +107,22 @@ int atlas_b200_search_host(const void* bank, int64_t n, int64_t ld, int32_t is_b
                            int64_t id_base, int64_t id_stride,
                            void* workspace, size_t workspace_bytes, void* stream);
 
+/* --------------------------------------------------------------------------------------------
+ * Dense linear layer with a fused epilogue on tcgen05 (csrc/gemm.cu):
+ *     C[M, N] = epilogue( A[M, K] . W[N, K]^T )     A, W, C, bias, residual: fp16 (is_bf16 = 0) or bf16
+ * W is the nn.Linear weight as stored by torch ([out_features, in_features]).  fp32 accumulation.
+ * Replaces cuBLAS GEMM + ATen elementwise kernels behind the Linear layers of the Contriever encoder
+ * (src/modeling_bert.py:280-466) and of FiD's T5 blocks (src/modeling_t5.py:272-289,418-531,1642-1647).
+ *   epilogue  0 none | 1 +bias | 2 gelu_erf(+bias) (modeling_bert.py:444)
+ *             | 3 +bias +residual[M, ldr] (dense + residual before LayerNorm)
+ *             | 4 gated: C[m, j] = gelu_new(acc[m, 2j]) * acc[m, 2j+1], C has N/2 columns; W rows are
+ *               wi_0 / wi_1 interleaved (modeling_t5.py:281-285; GELU evaluated in fp32 as at :283)
+ * lda / ldw / ldc / ldr are row strides in elements (multiples of 8); N and K multiples of 8.
+ * bias may be NULL (no bias added) for epilogues 1-3. */
+int atlas_b200_linear(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias,
+                      const void* residual, int64_t ldr, void* C, int64_t ldc,
+                      int32_t M, int32_t N, int32_t K, int32_t epilogue, int32_t is_bf16, void* stream);
+
 /* Measurement hook for bench.py's roofline: while enabled, every launch of the DOMINANT kernel (the
  * main bank sweep of atlas_b200_mips_topk) is bracketed with CUDA events on its launching stream.
  * atlas_b200_profile_collect() synchronises those events, returns the summed kernel time and the

@@ -1,0 +1,98 @@
+"""GPU numerics of the tcgen05 linear layer (csrc/gemm.cu) against a plain PyTorch fp32 reference of the
+same op (inputs rounded to the 16-bit type first, fp32 math, one rounding of the result).  Tolerance:
+the result must be within 1 ulp(16-bit) + 1e-3*|ref| of the correctly rounded fp32 reference — what a
+different fp32 accumulation order can cost — and bit-exact on exact-grid inputs."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    from atlas_b200._lib import lib
+
+    lib()
+    return torch.device("cuda:0")
+
+
+def _ref(x, w, bias, residual, epi):
+    acc = x.float() @ w.float().T
+    if epi in (1, 2, 3) and bias is not None:
+        acc = acc + bias.float()
+    if epi == 2:
+        acc = torch.nn.functional.gelu(acc)                       # erf GELU (modeling_bert.py:444)
+    if epi == 3:
+        acc = acc + residual.float()
+    if epi == 4:
+        a, b = acc[:, 0::2], acc[:, 1::2]
+        acc = torch.nn.functional.gelu(a, approximate="tanh") * b  # gelu_new in fp32 (modeling_t5.py:283)
+    return acc
+
+
+def _close(got, ref, dtype):
+    ref16 = ref.to(dtype).float()
+    ulp = (torch.finfo(dtype).eps * ref16.abs()).clamp_min(torch.finfo(dtype).tiny * 1024)
+    err = (got.float() - ref).abs()
+    return bool((err <= 1.0 * ulp + 1e-3 * ref.abs() + 1e-6).all()), float(err.max())
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (257, 768, 768), (1000, 3072, 768), (333, 768, 3072),
+                                   (4096, 2304, 768), (19200, 768, 768), (64, 32128, 768)])
+@pytest.mark.parametrize("epi", [0, 1, 2, 3])
+def test_linear_matches_fp32_reference(dev, dtype, M, N, K, epi):
+    from atlas_b200 import ops
+
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K + epi)
+    x = (torch.randn(M, K, generator=g) * 0.5).to(dtype).to(dev)
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(dtype).to(dev)
+    bias = (torch.randn(N, generator=g) * 0.1).to(dtype).to(dev)
+    res = (torch.randn(M, N, generator=g)).to(dtype).to(dev)
+    y = ops.linear(x, w, bias if epi else None, res if epi == 3 else None, epilogue=epi)
+    ok, err = _close(y, _ref(x, w, bias, res, epi), dtype)
+    assert ok, f"max abs err {err}"
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_gated_gelu_epilogue(dev, dtype):
+    from atlas_b200 import ops
+
+    g = torch.Generator(device="cpu").manual_seed(5)
+    M, K, F = 777, 768, 2048
+    x = (torch.randn(M, K, generator=g) * 0.5).to(dtype).to(dev)
+    w0 = (torch.randn(F, K, generator=g) / math.sqrt(K)).to(dtype)
+    w1 = (torch.randn(F, K, generator=g) / math.sqrt(K)).to(dtype)
+    w = torch.stack([w0, w1], dim=1).reshape(2 * F, K).contiguous().to(dev)   # rows interleaved wi_0 / wi_1
+    y = ops.linear(x, w, epilogue=ops.EPI_GATED)
+    assert y.shape == (M, F)
+    ok, err = _close(y, _ref(x, w, None, None, 4), dtype)
+    assert ok, f"max abs err {err}"
+
+
+def test_exact_grid_bit_exact(dev):
+    """Inputs on a coarse grid: every partial sum is exact in fp32, so the result must equal the fp32
+    reference bit for bit after the single rounding."""
+    from atlas_b200 import ops
+
+    g = torch.Generator(device="cpu").manual_seed(9)
+    x = (torch.randint(-8, 9, (515, 768), generator=g).float() / 8).half().to(dev)
+    w = (torch.randint(-8, 9, (1536, 768), generator=g).float() / 8).half().to(dev)
+    y = ops.linear(x, w)
+    assert torch.equal(y, (x.float() @ w.float().T).half())
+
+
+def test_strided_input_and_output_view(dev):
+    from atlas_b200 import ops
+
+    g = torch.Generator(device="cpu").manual_seed(11)
+    big = (torch.randn(300, 2304, generator=g) * 0.3).half().to(dev)
+    x = big[:, 768:1536]                                   # row stride 2304, K = 768
+    w = (torch.randn(768, 768, generator=g) / 27.7).half().to(dev)
+    out = torch.zeros(300, 1536, dtype=torch.float16, device=dev)
+    ops.linear(x, w, out=out[:, 768:])
+    ok, err = _close(out[:, 768:], x.float() @ w.float().T, torch.float16)
+    assert ok and float(out[:, :768].abs().max()) == 0.0
