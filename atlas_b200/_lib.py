@@ -65,6 +65,19 @@ def lib():
     L.atlas_b200_linear.argtypes = [c.c_void_p, c.c_int64, c.c_void_p, c.c_int64, c.c_void_p, c.c_void_p, c.c_int64,
                                     c.c_void_p, c.c_int64, c.c_int32, c.c_int32, c.c_int32, c.c_int32, c.c_int32,
                                     c.c_void_p]
+    L.atlas_b200_layernorm.restype = c.c_int
+    L.atlas_b200_layernorm.argtypes = [c.c_void_p, c.c_int64, c.c_void_p, c.c_void_p, c.c_void_p, c.c_int64, c.c_int32,
+                                       c.c_int32, c.c_float, c.c_int32, c.c_int32, c.c_void_p]
+    L.atlas_b200_bert_embed_ln.restype = c.c_int
+    L.atlas_b200_bert_embed_ln.argtypes = [c.c_void_p] * 8 + [c.c_int32, c.c_int32, c.c_int32, c.c_float, c.c_int32,
+                                                              c.c_void_p]
+    L.atlas_b200_masked_mean_pool.restype = c.c_int
+    L.atlas_b200_masked_mean_pool.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_int64, c.c_int32, c.c_int32,
+                                              c.c_int32, c.c_int32, c.c_void_p]
+    L.atlas_b200_attention.restype = c.c_int
+    L.atlas_b200_attention.argtypes = [c.c_void_p, c.c_int64, c.c_int32, c.c_void_p, c.c_int64, c.c_int32, c.c_void_p,
+                                       c.c_int64, c.c_int32, c.c_void_p, c.c_int64, c.c_void_p, c.c_void_p, c.c_int32,
+                                       c.c_int32, c.c_int32, c.c_int32, c.c_float, c.c_float, c.c_int32, c.c_void_p]
     L.atlas_b200_mips_set_debug_counters.restype = None
     L.atlas_b200_mips_set_debug_counters.argtypes = [c.c_void_p]
     L.atlas_b200_profile_enable.restype = None
@@ -86,6 +99,10 @@ EXPORTED_SYMBOLS = [
     "atlas_b200_search_host",
     "atlas_b200_cast_f32",
     "atlas_b200_linear",
+    "atlas_b200_layernorm",
+    "atlas_b200_bert_embed_ln",
+    "atlas_b200_masked_mean_pool",
+    "atlas_b200_attention",
     "atlas_b200_mips_set_kernel",
     "atlas_b200_mips_set_debug_counters",
     "atlas_b200_profile_enable",

@@ -706,21 +706,30 @@ mips_select_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ count, ui
     for (int i = t; i < P; i += SEL_THREADS) win[i] = 0;
     __syncthreads();
 
+    // A bound-only pass (no winners needed) stops after the two score bytes of the 48-bit key.
+    const bool bound_only = (mode & SEL_WRITE_BOUND) && !(mode & (SEL_EMIT | SEL_CARRY));
     if (kk > 0) {
         uint64_t mask = 0;
-        for (int b = 5; b >= 0; --b) {
+        for (int b = 5; b >= (bound_only ? 4 : 0); --b) {
             hist[t] = 0;
             __syncthreads();
             const uint64_t prefix = s_prefix;
-            // warp-aggregated histogram: scores cluster in a handful of bins, so per-key shared atomics
-            // would serialise; lanes with the same bin elect one leader that adds their population count
-            for (uint32_t i0 = 0; i0 < n; i0 += SEL_THREADS) {
-                const uint32_t i = i0 + t;
-                const uint64_t key = (i < n) ? c[i] : 0;
-                const bool live = (i < n) && ((key & mask) == prefix);
-                const uint32_t bin = live ? static_cast<uint32_t>((key >> (8 * b)) & 0xFFu) : 256u;
-                const uint32_t peers = __match_any_sync(0xffffffffu, bin);
-                if (live && (t & 31) == static_cast<int>(__ffs(peers)) - 1) atomicAdd(&hist[bin], __popc(peers));
+            if (b == 5) {
+                // top byte of the score key: scores cluster in a handful of bins, per-key shared atomics would
+                // serialise -> lanes with the same bin elect a leader that adds their population count
+                for (uint32_t i0 = 0; i0 < n; i0 += SEL_THREADS) {
+                    const uint32_t i = i0 + t;
+                    const bool live = i < n;
+                    const uint32_t bin = live ? static_cast<uint32_t>((c[i] >> 40) & 0xFFu) : 256u;
+                    const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+                    if (live && (t & 31) == static_cast<int>(__ffs(peers)) - 1) atomicAdd(&hist[bin], __popc(peers));
+                }
+            } else {
+                // lower bytes are close to uniform over the 256 bins: plain shared atomics, 4 keys in flight
+                for (uint32_t i = t; i < n; i += SEL_THREADS) {
+                    const uint64_t key = c[i];
+                    if ((key & mask) == prefix) atomicAdd(&hist[(key >> (8 * b)) & 0xFFu], 1u);
+                }
             }
             __syncthreads();
             if (t == 0) {
@@ -737,7 +746,7 @@ mips_select_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ count, ui
             __syncthreads();
         }
         const uint64_t kth = s_prefix;  // exact k-th largest key (keys are unique: ids differ)
-        for (uint32_t i = t; i < n; i += SEL_THREADS) {
+        for (uint32_t i = t; i < n && !bound_only; i += SEL_THREADS) {
             const uint64_t key = c[i];
             if (key >= kth) {
                 const uint32_t pos = atomicAdd(&s_nwin, 1u);
@@ -746,7 +755,7 @@ mips_select_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ count, ui
         }
         __syncthreads();
         // bitonic sort, descending
-        for (int size = 2; size <= P; size <<= 1) {
+        for (int size = 2; size <= P && !bound_only; size <<= 1) {
             for (int stride = size >> 1; stride > 0; stride >>= 1) {
                 for (int i = t; i < P / 2; i += SEL_THREADS) {
                     const int lo = 2 * i - (i & (stride - 1));
@@ -787,7 +796,10 @@ mips_select_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ count, ui
     if (mode & SEL_WRITE_BOUND) {
         if (t == 0) {
             if (kk == static_cast<uint32_t>(k) && kk > 0) {
-                bound[q] = lower_bound_for_key<kBF16>(static_cast<uint32_t>(win[kk - 1] >> 32));
+                // bound-only passes resolved just the 16 score bits of the k-th key (s_prefix bits 47..32)
+                const uint32_t kth16 = bound_only ? static_cast<uint32_t>(s_prefix >> 32)
+                                                  : static_cast<uint32_t>(win[kk - 1] >> 32);
+                bound[q] = lower_bound_for_key<kBF16>(kth16);
             } else if (!(mode & SEL_CARRY)) {
                 bound[q] = -INFINITY;  // refinement passes keep the previous (still valid) bound instead
             }

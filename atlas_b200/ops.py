@@ -186,3 +186,66 @@ def linear(x, weight, bias=None, residual=None, epilogue=None, out=None):
         _ptr(r2) if r2 is not None else None, r2.stride(0) if r2 is not None else 0, _ptr(out), out.stride(0),
         M, N, K, epilogue, 1 if x.dtype == torch.bfloat16 else 0, current_stream_ptr()))
     return out.reshape(*x.shape[:-1], n_out)
+
+
+# ---------------------------------------------------------------------------------------------
+# normalisation / embedding / pooling (csrc/elementwise.cu) and attention (csrc/attention.cu)
+# ---------------------------------------------------------------------------------------------
+def _bf(t):
+    return 1 if t.dtype == torch.bfloat16 else 0
+
+
+def layernorm(x, weight, bias=None, eps=1e-12, kind=0, out=None):
+    """kind 0: BertLayerNorm (uncentred 2nd moment, src/modeling_bert.py:104-114); kind 1: T5 RMSNorm."""
+    require_cuda(x, "x")
+    H = x.shape[-1]
+    x2 = x.reshape(-1, H)
+    if x2.stride(-1) != 1:
+        x2 = x2.contiguous()
+    if out is None:
+        out = torch.empty_like(x2)
+    check(lib().atlas_b200_layernorm(_ptr(x2), x2.stride(0), _ptr(weight), _ptr(bias) if bias is not None else None,
+                                     _ptr(out), out.stride(0), x2.shape[0], H, float(eps), kind, _bf(x),
+                                     current_stream_ptr()))
+    return out.reshape(x.shape)
+
+
+def bert_embed_ln(input_ids, token_type_ids, word_emb, type_emb, pos_emb, ln_weight, ln_bias, eps):
+    require_cuda(input_ids, "input_ids")
+    B, L = input_ids.shape
+    H = word_emb.shape[1]
+    y = torch.empty((B, L, H), dtype=word_emb.dtype, device=word_emb.device)
+    ids = input_ids.contiguous()
+    tt = token_type_ids.contiguous() if token_type_ids is not None else None
+    check(lib().atlas_b200_bert_embed_ln(_ptr(ids), _ptr(tt) if tt is not None else None, _ptr(word_emb), _ptr(type_emb),
+                                         _ptr(pos_emb), _ptr(ln_weight), _ptr(ln_bias), _ptr(y), B, L, H, float(eps),
+                                         _bf(word_emb), current_stream_ptr()))
+    return y
+
+
+def masked_mean_pool(x, mask, out=None):
+    """x [B, L, H] 16-bit, mask [B, L] int64 -> [B, H] (optionally written into `out` rows, e.g. the bank)."""
+    require_cuda(x, "x")
+    B, L, H = x.shape
+    xc = x.contiguous()
+    m = mask.to(torch.int64).contiguous()
+    if out is None:
+        out = torch.empty((B, H), dtype=x.dtype, device=x.device)
+    check(lib().atlas_b200_masked_mean_pool(_ptr(xc), _ptr(m), _ptr(out), out.stride(0), B, L, H, _bf(x),
+                                            current_stream_ptr()))
+    return out
+
+
+def attention(q, q_col0, k, k_col0, v, v_col0, B, H, Lq, Lk, add_mask=None, bias_delta=None, scale=1.0,
+              causal_value=0.0, out=None):
+    """Fused attention reading Q/K/V in place from [B*L, ld] projection buffers (head h at col0 + 64h)."""
+    require_cuda(q, "q")
+    if out is None:
+        out = torch.empty((B * Lq, H * 64), dtype=q.dtype, device=q.device)
+    am = add_mask.float().contiguous() if add_mask is not None else None
+    bd = bias_delta.float().contiguous() if bias_delta is not None else None
+    check(lib().atlas_b200_attention(_ptr(q), q.stride(0), q_col0, _ptr(k), k.stride(0), k_col0, _ptr(v), v.stride(0),
+                                     v_col0, _ptr(out), out.stride(0), _ptr(am) if am is not None else None,
+                                     _ptr(bd) if bd is not None else None, B, H, Lq, Lk, float(scale),
+                                     float(causal_value), _bf(q), current_stream_ptr()))
+    return out

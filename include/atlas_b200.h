@@ -123,6 +123,38 @@ int atlas_b200_linear(const void* A, int64_t lda, const void* W, int64_t ldw, co
                       const void* residual, int64_t ldr, void* C, int64_t ldc,
                       int32_t M, int32_t N, int32_t K, int32_t epilogue, int32_t is_bf16, void* stream);
 
+/* Row-wise normalisation of 16-bit activations (csrc/elementwise.cu), one rounding point per torch op:
+ *   kind 0  BertLayerNorm (src/modeling_bert.py:104-114): y = w * r16((x - mean) * rsqrt(mean(x^2) + eps)) + b
+ *           — note the UNCENTRED second moment; callers pass the residual sum already rounded to 16 bits.
+ *   kind 1  T5LayerNorm / RMSNorm (src/modeling_t5.py:244-253): y = w * r16(x * rsqrt(mean(x^2) + eps)) */
+int atlas_b200_layernorm(const void* x, int64_t ldx, const void* weight, const void* bias, void* y, int64_t ldy,
+                         int32_t rows, int32_t H, float eps, int32_t kind, int32_t is_bf16, void* stream);
+
+/* BertEmbeddings.forward (src/modeling_bert.py:213-247): word + token_type + position embeddings
+ * (16-bit adds in that order), BertLayerNorm.  input_ids / token_type_ids [batch, L] int64
+ * (token_type_ids may be NULL = zeros); y [batch*L, H]. */
+int atlas_b200_bert_embed_ln(const int64_t* input_ids, const int64_t* token_type_ids, const void* word_emb,
+                             const void* type_emb, const void* pos_emb, const void* ln_weight, const void* ln_bias,
+                             void* y, int32_t batch, int32_t L, int32_t H, float eps, int32_t is_bf16, void* stream);
+
+/* Contriever average pooling (src/retrievers.py:50-53): out[b] = sum_l mask[b,l]*x[b,l] / sum_l mask[b,l].
+ * `out` rows may be strided (ld_out) so the result can be written straight into the passage bank. */
+int atlas_b200_masked_mean_pool(const void* x, const int64_t* mask, void* out, int64_t ld_out, int32_t batch,
+                                int32_t L, int32_t H, int32_t is_bf16, void* stream);
+
+/* Fused multi-head attention, head_dim 64, Lk <= 512 keys per segment (csrc/attention.cu):
+ *   O[b,i,h,:] = softmax_j( scale*Q[b,i,h].K[b,j,h] + bias_delta[h, j-i+Lq-1] + add_mask[b,j] (+causal) ) V[b,j,h,:]
+ * q / k / v point at row-major [B*L, ld] 16-bit buffers (e.g. the fused QKV projection output); head h
+ * occupies columns [col0 + 64h, col0 + 64h + 64).  add_mask [B, Lk] fp32 additive (NULL = none),
+ * bias_delta [H, Lq+Lk-1] fp32 (NULL = none; T5 relative-position bias by offset), causal_value 0 = off,
+ * otherwise added where j > i (the reference adds -10000, transformers 4.18 get_extended_attention_mask).
+ * Replaces BertSelfAttention.forward (src/modeling_bert.py:328-366, scale 1/8) and T5Attention.forward
+ * (src/modeling_t5.py:478-524, scale 1) incl. the materialised scores / probabilities. */
+int atlas_b200_attention(const void* q, int64_t ldq, int32_t q_col0, const void* k, int64_t ldk, int32_t k_col0,
+                         const void* v, int64_t ldv, int32_t v_col0, void* out, int64_t ldo,
+                         const float* add_mask, const float* bias_delta, int32_t B, int32_t H, int32_t Lq,
+                         int32_t Lk, float scale, float causal_value, int32_t is_bf16, void* stream);
+
 /* Measurement hook for bench.py's roofline: while enabled, every launch of the DOMINANT kernel (the
  * main bank sweep of atlas_b200_mips_topk) is bracketed with CUDA events on its launching stream.
  * atlas_b200_profile_collect() synchronises those events, returns the summed kernel time and the

@@ -1,0 +1,135 @@
+"""GPU numerics of the normalisation / embedding / pooling / attention kernels against plain PyTorch
+fp32 references of the same ops (rounding points restated from the reference model code)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    from atlas_b200._lib import lib
+
+    lib()
+    return torch.device("cuda:0")
+
+
+def _bert_ln_ref(x16, w, b, eps):
+    """BertLayerNorm on `.float()` input then `.type_as` (src/modeling_bert.py:104-114,386)."""
+    x = x16.float()
+    mean = x.mean(-1, keepdim=True)
+    var = x.pow(2).mean(-1, keepdim=True)
+    h = ((x - mean) * torch.rsqrt(var + eps)).to(w.dtype)
+    return w * h + b
+
+
+def _rms_ref(x16, w, eps):
+    var = x16.float().pow(2).mean(-1, keepdim=True)
+    h = (x16 * torch.rsqrt(var + eps)).to(w.dtype)
+    return w * h
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("H", [768, 2048, 64])
+def test_layernorm_kinds(dev, dtype, H):
+    from atlas_b200 import ops
+
+    g = torch.Generator(device="cpu").manual_seed(H)
+    x = (torch.randn(1000, H, generator=g) * 2 + 0.3).to(dtype).to(dev)
+    w = (1 + 0.1 * torch.randn(H, generator=g)).to(dtype).to(dev)
+    b = (0.1 * torch.randn(H, generator=g)).to(dtype).to(dev)
+    y0 = ops.layernorm(x, w, b, eps=1e-12, kind=0)
+    r0 = _bert_ln_ref(x, w, b, 1e-12)
+    y1 = ops.layernorm(x, w, None, eps=1e-6, kind=1)
+    r1 = _rms_ref(x, w, 1e-6)
+    for y, r in ((y0, r0), (y1, r1)):
+        # identical rounding points: allow one 16-bit ulp for fp32 reduction-order effects on the statistics
+        ulp = torch.finfo(dtype).eps * r.float().abs() + 1e-6
+        assert torch.all((y.float() - r.float()).abs() <= 2.0 * ulp), float((y.float() - r.float()).abs().max())
+        assert float((y == r).float().mean()) > 0.97
+
+
+def test_bert_embed_ln(dev):
+    from atlas_b200 import ops
+
+    g = torch.Generator(device="cpu").manual_seed(3)
+    V, L, H, B = 1000, 37, 768, 5
+    we = (torch.randn(V, H, generator=g) * 0.02).half().to(dev)
+    te = (torch.randn(2, H, generator=g) * 0.02).half().to(dev)
+    pe = (torch.randn(512, H, generator=g) * 0.02).half().to(dev)
+    w = (1 + 0.1 * torch.randn(H, generator=g)).half().to(dev)
+    b = (0.1 * torch.randn(H, generator=g)).half().to(dev)
+    ids = torch.randint(0, V, (B, L), generator=g).to(dev)
+    y = ops.bert_embed_ln(ids, None, we, te, pe, w, b, 1e-12)
+    emb = we[ids] + te[torch.zeros_like(ids)]
+    emb += pe[torch.arange(L, device=dev)][None]
+    ref = _bert_ln_ref(emb, w, b, 1e-12)
+    assert torch.all((y.float() - ref.float()).abs() <= 2 * torch.finfo(torch.float16).eps * ref.float().abs() + 1e-6)
+
+
+def test_masked_mean_pool_into_bank_rows(dev):
+    from atlas_b200 import ops
+
+    g = torch.Generator(device="cpu").manual_seed(4)
+    B, L, H = 9, 50, 768
+    x = torch.randn(B, L, H, generator=g).half().to(dev)
+    lens = torch.randint(1, L + 1, (B,), generator=g)
+    mask = (torch.arange(L)[None] < lens[:, None]).long().to(dev)
+    bank = torch.zeros(20, H, dtype=torch.float16, device=dev)
+    ops.masked_mean_pool(x, mask, out=bank[4:4 + B])
+    last = x.masked_fill(~mask[..., None].bool(), 0.0)
+    ref = last.sum(dim=1) / mask.sum(dim=1)[..., None]       # src/retrievers.py:50-53 on a half tensor
+    assert torch.all((bank[4:4 + B].float() - ref.float()).abs() <= torch.finfo(torch.float16).eps * ref.float().abs() + 1e-7)
+    assert float(bank[:4].abs().max()) == 0 and float(bank[4 + B:].abs().max()) == 0
+
+
+def _attn_ref(qkv, B, H, L, add_mask, bias_delta, scale, causal_value):
+    """fp32 reference: scores = scale*QK^T + bias + mask, softmax, PV (inputs are the 16-bit values)."""
+    d = 64
+    q = qkv[:, : H * d].float().view(B, L, H, d).permute(0, 2, 1, 3)
+    k = qkv[:, H * d: 2 * H * d].float().view(B, L, H, d).permute(0, 2, 1, 3)
+    v = qkv[:, 2 * H * d:].float().view(B, L, H, d).permute(0, 2, 1, 3)
+    s = torch.matmul(q, k.transpose(-1, -2)) * scale
+    if bias_delta is not None:
+        i = torch.arange(L, device=qkv.device)
+        idx = i[None, :] - i[:, None] + (L - 1)              # [i, j] -> j - i + L - 1
+        s = s + bias_delta[:, idx][None]
+    if add_mask is not None:
+        s = s + add_mask[:, None, None, :]
+    if causal_value != 0.0:
+        i = torch.arange(L, device=qkv.device)
+        s = s + (i[None, :] > i[:, None]).float() * causal_value
+    p = torch.softmax(s, dim=-1)
+    return torch.matmul(p, v).permute(0, 2, 1, 3).reshape(B * L, H * d)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("B,H,L,mode", [(3, 12, 384, "t5enc"), (2, 12, 128, "bert"), (5, 12, 173, "bert"),
+                                        (2, 12, 512, "bert"), (4, 12, 32, "t5dec"), (1, 32, 384, "t5enc")])
+def test_attention_matches_fp32_reference(dev, dtype, B, H, L, mode):
+    from atlas_b200 import ops
+
+    g = torch.Generator(device="cpu").manual_seed(B * 100 + L)
+    qkv = (torch.randn(B * L, 3 * H * 64, generator=g) * (0.35 if mode == "bert" else 0.12)).to(dtype).to(dev)
+    lens = torch.randint(max(1, L // 3), L + 1, (B,), generator=g)
+    keep = (torch.arange(L)[None] < lens[:, None]).float().to(dev)
+    add_mask = (1.0 - keep) * -10000.0
+    bias = None
+    scale, causal = 1.0, 0.0
+    if mode == "bert":
+        scale = 1.0 / 8.0
+    else:
+        bias = (torch.randn(H, 2 * L - 1, generator=g) * 0.5).to(dev)
+    if mode == "t5dec":
+        causal = -10000.0
+    out = ops.attention(qkv, 0, qkv, H * 64, qkv, 2 * H * 64, B, H, L, L, add_mask=add_mask, bias_delta=bias, scale=scale,
+                        causal_value=causal)
+    ref = _attn_ref(qkv, B, H, L, add_mask, bias, scale, causal)
+    err = (out.float() - ref).abs()
+    tol = 2e-3 if dtype == torch.float16 else 1.2e-2   # P and O are rounded to the 16-bit type (8 / 11 mantissa bits)
+    assert float(err.max()) <= tol * max(1.0, float(ref.abs().max())), float(err.max())
+    # valid rows only matter, but every row must be finite
+    assert torch.isfinite(out.float()).all()
