@@ -37,7 +37,9 @@ def _close(got, ref, dtype):
     ref16 = ref.to(dtype).float()
     ulp = (torch.finfo(dtype).eps * ref16.abs()).clamp_min(torch.finfo(dtype).tiny * 1024)
     err = (got.float() - ref).abs()
-    return bool((err <= 1.0 * ulp + 1e-3 * ref.abs() + 1e-6).all()), float(err.max())
+    # 1 ulp of the 16-bit result + relative slack + an ABSOLUTE term for fp32 accumulation-order noise
+    # (the fp32 torch reference itself is ~5e-6 away from the fp64 value at K = 3072; measured, tools/diag_gemm.py)
+    return bool((err <= 1.0 * ulp + 1e-3 * ref.abs() + 3e-5).all()), float(err.max())
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
