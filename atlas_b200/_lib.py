@@ -77,7 +77,11 @@ def lib():
     L.atlas_b200_attention.restype = c.c_int
     L.atlas_b200_attention.argtypes = [c.c_void_p, c.c_int64, c.c_int32, c.c_void_p, c.c_int64, c.c_int32, c.c_void_p,
                                        c.c_int64, c.c_int32, c.c_void_p, c.c_int64, c.c_void_p, c.c_void_p, c.c_int32,
-                                       c.c_int32, c.c_int32, c.c_int32, c.c_float, c.c_float, c.c_int32, c.c_void_p]
+                                       c.c_int32, c.c_int32, c.c_int32, c.c_float, c.c_float, c.c_int32, c.c_void_p,
+                                       c.c_void_p, c.c_int32, c.c_void_p]
+    L.atlas_b200_attention_combine.restype = c.c_int
+    L.atlas_b200_attention_combine.argtypes = [c.c_void_p, c.c_void_p, c.c_int32, c.c_int32, c.c_int32, c.c_int32,
+                                               c.c_void_p, c.c_int64, c.c_int32, c.c_void_p]
     L.atlas_b200_mips_set_debug_counters.restype = None
     L.atlas_b200_mips_set_debug_counters.argtypes = [c.c_void_p]
     L.atlas_b200_profile_enable.restype = None
@@ -103,6 +107,7 @@ EXPORTED_SYMBOLS = [
     "atlas_b200_bert_embed_ln",
     "atlas_b200_masked_mean_pool",
     "atlas_b200_attention",
+    "atlas_b200_attention_combine",
     "atlas_b200_mips_set_kernel",
     "atlas_b200_mips_set_debug_counters",
     "atlas_b200_profile_enable",

@@ -43,6 +43,11 @@ struct Params {
     const float* bias_delta;  // [H, Lq + Lk - 1]: bias for (j - i) + (Lq - 1), or nullptr
     float scale;
     float causal_value;       // 0 = not causal; otherwise the additive value for j > i (reference: -10000)
+    // split-KV (decoder cross-attention over n_ctx*L keys): segment b reads the queries of batch b / q_div and
+    // writes UN-normalised fp32 partial outputs + (row max, row sum) for combine_splits_kernel
+    int q_div;
+    float* o_partial;         // [B*Lq, H*64] fp32 or nullptr
+    float* ml_partial;        // [B*Lq, H, 2] fp32
 };
 
 __device__ __forceinline__ void tmem_ld32f(uint32_t taddr, float (&v)[32]) {
@@ -148,7 +153,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 for (int qt = 0; qt < n_qt; ++qt, ++qt_it) {
                     ab::mbar_wait(&q_empty, (qt_it & 1) ^ 1u, 22);
                     ab::mbar_arrive_expect_tx(&q_full, Q_BYTES);
-                    ab::tma_load_2d(&tmap_q, &q_full, sQ, p.q_col0 + h * D, b * p.Lq + qt * BLOCK_Q, ab::kEvictFirst);
+                    ab::tma_load_2d(&tmap_q, &q_full, sQ, p.q_col0 + h * D, (b / p.q_div) * p.Lq + qt * BLOCK_Q,
+                                    ab::kEvictFirst);
                 }
             }
         }
@@ -251,6 +257,28 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 // ---- output: O / sum -> 16-bit, 128 contiguous bytes per row ----
                 ab::mbar_wait(&o_full, qt_it & 1, 28);
                 ab::tc_fence_after();
+                if (p.o_partial != nullptr) {
+                    // split-KV: un-normalised partial output in fp32 + (max, sum) of this split
+                    float* dst = p.o_partial + (static_cast<size_t>(b) * p.Lq + i) * (static_cast<size_t>(p.H) * D) + h * D;
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        float v[32];
+                        tmem_ld32f(lane_addr + o_col + c * 32, v);
+                        if (i < p.Lq) {
+#pragma unroll
+                            for (int v4 = 0; v4 < 8; ++v4)
+                                reinterpret_cast<float4*>(dst + c * 32)[v4] =
+                                    make_float4(v[4 * v4], v[4 * v4 + 1], v[4 * v4 + 2], v[4 * v4 + 3]);
+                        }
+                    }
+                    ab::tc_fence_before();
+                    ab::mbar_arrive(&s_free);
+                    if (i < p.Lq) {
+                        float* ml = p.ml_partial + ((static_cast<size_t>(b) * p.Lq + i) * p.H + h) * 2;
+                        ml[0] = mx;
+                        ml[1] = sum;
+                    }
+                } else {
                 const float inv = 1.0f / sum;
                 uint32_t outw[32];
 #pragma unroll
@@ -268,6 +296,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     for (int v4 = 0; v4 < 8; ++v4)
                         dst[v4] = make_uint4(outw[4 * v4], outw[4 * v4 + 1], outw[4 * v4 + 2], outw[4 * v4 + 3]);
                 }
+                }
             }
         }
     }
@@ -280,6 +309,33 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     }
 }
 
+// out[b, i, h, :] = sum_s w_s O_s / sum_s w_s l_s with w_s = exp(m_s - max_s m_s); one warp per (b, i, h)
+template <bool kBF16>
+__global__ void combine_splits_kernel(const float* __restrict__ o_partial, const float* __restrict__ ml, int B, int splits,
+                                      int Lq, int H, uint16_t* __restrict__ out, int64_t ldo) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= B * Lq * H) return;
+    const int h = w % H, i = (w / H) % Lq, b = w / (H * Lq);
+    float M = -INFINITY;
+    for (int s = 0; s < splits; ++s) {
+        const size_t row = (static_cast<size_t>(b) * splits + s) * Lq + i;
+        M = fmaxf(M, ml[(row * H + h) * 2]);
+    }
+    float acc0 = 0.f, acc1 = 0.f, den = 0.f;
+    for (int s = 0; s < splits; ++s) {
+        const size_t row = (static_cast<size_t>(b) * splits + s) * Lq + i;
+        const float wgt = exp2f((ml[(row * H + h) * 2] - M) * LOG2E);
+        den += wgt * ml[(row * H + h) * 2 + 1];
+        const float2 o = reinterpret_cast<const float2*>(o_partial + row * (static_cast<size_t>(H) * D) + h * D)[lane];
+        acc0 += wgt * o.x;
+        acc1 += wgt * o.y;
+    }
+    const float inv = 1.0f / den;
+    reinterpret_cast<uint32_t*>(out + (static_cast<size_t>(b) * Lq + i) * ldo + h * D)[lane] =
+        pack2<kBF16>(acc0 * inv, acc1 * inv);
+}
+
 }  // namespace attn
 
 extern "C" {
@@ -287,8 +343,11 @@ extern "C" {
 int atlas_b200_attention(const void* q, int64_t ldq, int32_t q_col0, const void* k, int64_t ldk, int32_t k_col0,
                          const void* v, int64_t ldv, int32_t v_col0, void* out, int64_t ldo, const float* add_mask,
                          const float* bias_delta, int32_t B, int32_t H, int32_t Lq, int32_t Lk, float scale,
-                         float causal_value, int32_t is_bf16, void* stream) {
+                         float causal_value, int32_t q_div, float* o_partial, float* ml_partial, int32_t is_bf16,
+                         void* stream) {
     using namespace attn;
+    AB_REQUIRE(q_div >= 1 && B % q_div == 0, "attention: q_div must divide the number of key segments");
+    AB_REQUIRE((o_partial == nullptr) == (ml_partial == nullptr), "attention: partial outputs come in pairs");
     AB_REQUIRE(B >= 0 && H > 0 && Lq > 0 && Lk > 0 && Lk <= MAX_LK, "attention: need 0 < Lk <= %d (got Lq=%d Lk=%d)",
                MAX_LK, Lq, Lk);
     AB_REQUIRE(Lq + Lk - 1 <= 2 * MAX_LK, "attention: Lq + Lk too large for the bias table");
@@ -297,7 +356,7 @@ int atlas_b200_attention(const void* q, int64_t ldq, int32_t q_col0, const void*
                "attention: strides and column offsets must be multiples of 8 elements");
     if (B == 0) return ATLAS_B200_OK;
     CUtensorMap tq, tk, tv;
-    int rc = abh::make_tmap_2d_16bit(&tq, q, static_cast<uint64_t>(B) * Lq, static_cast<uint64_t>(q_col0 + H * D),
+    int rc = abh::make_tmap_2d_16bit(&tq, q, static_cast<uint64_t>(B / q_div) * Lq, static_cast<uint64_t>(q_col0 + H * D),
                                      static_cast<uint64_t>(ldq), BLOCK_Q, D, is_bf16 != 0);
     if (rc) return rc;
     rc = abh::make_tmap_2d_16bit(&tk, k, static_cast<uint64_t>(B) * Lk, static_cast<uint64_t>(k_col0 + H * D),
@@ -320,6 +379,9 @@ int atlas_b200_attention(const void* q, int64_t ldq, int32_t q_col0, const void*
     p.bias_delta = bias_delta;
     p.scale = scale;
     p.causal_value = causal_value;
+    p.q_div = q_div;
+    p.o_partial = o_partial;
+    p.ml_partial = ml_partial;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     static bool attr_set[2] = {false, false};
     const int items = B * H;
@@ -339,6 +401,24 @@ int atlas_b200_attention(const void* q, int64_t ldq, int32_t q_col0, const void*
         }
         attention_kernel<false><<<grid, THREADS, SMEM_BYTES, s>>>(tq, tk, tv, p);
     }
+    abh::count_launch();
+    AB_CUDA_CHECK(cudaGetLastError());
+    return ATLAS_B200_OK;
+}
+
+int atlas_b200_attention_combine(const float* o_partial, const float* ml_partial, int32_t B, int32_t splits, int32_t Lq,
+                                 int32_t H, void* out, int64_t ldo, int32_t is_bf16, void* stream) {
+    AB_REQUIRE(B >= 0 && splits >= 1 && Lq > 0 && H > 0 && ldo % 2 == 0, "attention_combine: bad shape");
+    if (B == 0) return ATLAS_B200_OK;
+    const int warps = B * Lq * H;
+    const int grid = (warps * 32 + 255) / 256;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (is_bf16)
+        attn::combine_splits_kernel<true><<<grid, 256, 0, s>>>(o_partial, ml_partial, B, splits, Lq, H,
+                                                               static_cast<uint16_t*>(out), ldo);
+    else
+        attn::combine_splits_kernel<false><<<grid, 256, 0, s>>>(o_partial, ml_partial, B, splits, Lq, H,
+                                                                static_cast<uint16_t*>(out), ldo);
     abh::count_launch();
     AB_CUDA_CHECK(cudaGetLastError());
     return ATLAS_B200_OK;

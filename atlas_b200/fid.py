@@ -1,0 +1,362 @@
+"""Drop-in for `src.fid.FiD` (reference src/fid.py:28-357 over the vendored T5 v1.1, src/modeling_t5.py):
+Fusion-in-Decoder forward on B200 kernels.  FORWARD ONLY in this round (evaluation / scoring / greedy
+generation); backward through the fused kernels is not implemented yet.
+
+Surface kept: `FiD(config)`, `forward(input_ids [B, n*L], attention_mask, decoder_input_ids,
+labels, encoder_outputs=None, use_cache=False)` -> output indexable as `out[0]` = loss, `out[1]` = logits with
+`.logits`, `.loss`, `.encoder_last_hidden_state`; `encoder.config.{n_context,bsz}` are read like the reference's
+`FiDStack` (src/fid.py:47-49,66-76); `_shift_right`; `generate` (greedy); parameter names identical to HF T5
+(`shared`, `encoder.block.N.layer.0.SelfAttention.{q,k,v,o}`, `relative_attention_bias` on block 0,
+`layer.1.EncDecAttention`, `DenseReluDense.{wi_0,wi_1,wo}`, `lm_head`) so reference checkpoints load.
+
+What runs where (all in csrc/): RMSNorm (T5LayerNorm, modeling_t5.py:244-253); q/k/v/o and FF projections on the
+tcgen05 GEMM with fused residual and gated-GELU epilogues (modeling_t5.py:281-289); encoder self-attention as
+B*n independent L-token segments with the relative-position bias added on the fly from a [H, 2L-1] table
+(modeling_t5.py:352-416,478-524) - the [B*n, H, L, L] bias / probability tensors are never materialised;
+decoder cross-attention over the n*L concatenated keys as split-KV + combine (fid.py:298-349).
+Not reproduced: dropout (eval only), the `isinf` clamps and their three host syncs per block
+(modeling_t5.py:657-708), cross-attention score capture (fid.py:126-235).
+"""
+import copy
+import math
+from types import SimpleNamespace
+
+import torch
+from torch import nn
+
+from . import ops
+from ._lib import AtlasB200Error
+from .retrievers import HalfCache
+
+
+class T5ConfigLite(SimpleNamespace):
+    """The T5Config fields this path reads (defaults = google/t5-base-lm-adapt, i.e. T5 v1.1 base)."""
+
+    def __init__(self, **kw):
+        d = dict(vocab_size=32128, d_model=768, d_kv=64, d_ff=2048, num_layers=12, num_decoder_layers=12, num_heads=12,
+                 relative_attention_num_buckets=32, layer_norm_epsilon=1e-6, feed_forward_proj="gated-gelu",
+                 tie_word_embeddings=False, decoder_start_token_id=0, pad_token_id=0, eos_token_id=1)
+        d.update(kw)
+        super().__init__(**d)
+
+
+class _Norm(nn.Module):
+    def __init__(self, d):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(d))
+
+
+class _Attn(nn.Module):
+    def __init__(self, c, has_bias):
+        super().__init__()
+        inner = c.num_heads * c.d_kv
+        self.q = nn.Linear(c.d_model, inner, bias=False)
+        self.k = nn.Linear(c.d_model, inner, bias=False)
+        self.v = nn.Linear(c.d_model, inner, bias=False)
+        self.o = nn.Linear(inner, c.d_model, bias=False)
+        if has_bias:
+            self.relative_attention_bias = nn.Embedding(c.relative_attention_num_buckets, c.num_heads)
+
+
+class _SelfAttnLayer(nn.Module):
+    def __init__(self, c, has_bias):
+        super().__init__()
+        self.SelfAttention = _Attn(c, has_bias)
+        self.layer_norm = _Norm(c.d_model)
+
+
+class _CrossAttnLayer(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.EncDecAttention = _Attn(c, False)
+        self.layer_norm = _Norm(c.d_model)
+
+
+class _FF(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.wi_0 = nn.Linear(c.d_model, c.d_ff, bias=False)
+        self.wi_1 = nn.Linear(c.d_model, c.d_ff, bias=False)
+        self.wo = nn.Linear(c.d_ff, c.d_model, bias=False)
+
+
+class _FFLayer(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.DenseReluDense = _FF(c)
+        self.layer_norm = _Norm(c.d_model)
+
+
+class _Block(nn.Module):
+    def __init__(self, c, is_decoder, has_bias):
+        super().__init__()
+        layers = [_SelfAttnLayer(c, has_bias)]
+        if is_decoder:
+            layers.append(_CrossAttnLayer(c))
+        layers.append(_FFLayer(c))
+        self.layer = nn.ModuleList(layers)
+
+
+class FiDStack(nn.Module):
+    def __init__(self, config, embed_tokens, is_decoder):
+        super().__init__()
+        self.config = copy.copy(config)
+        self.config.is_decoder = is_decoder
+        self.is_decoder = is_decoder
+        self.embed_tokens = embed_tokens
+        n = config.num_decoder_layers if is_decoder else config.num_layers
+        self.block = nn.ModuleList([_Block(config, is_decoder, i == 0) for i in range(n)])
+        self.final_layer_norm = _Norm(config.d_model)
+
+
+def relative_position_bucket(relative_position, bidirectional=True, num_buckets=32, max_distance=128):
+    """T5's bucket function restated with the same torch ops and rounding as src/modeling_t5.py:352-397."""
+    relative_buckets = 0
+    if bidirectional:
+        num_buckets //= 2
+        relative_buckets += (relative_position > 0).to(torch.long) * num_buckets
+        relative_position = torch.abs(relative_position)
+    else:
+        relative_position = -torch.min(relative_position, torch.zeros_like(relative_position))
+    max_exact = num_buckets // 2
+    is_small = relative_position < max_exact
+    if_large = max_exact + (
+        torch.log(relative_position.float() / max_exact) / math.log(max_distance / max_exact) * (num_buckets - max_exact)
+    ).to(torch.long)
+    if_large = torch.min(if_large, torch.full_like(if_large, num_buckets - 1))
+    relative_buckets += torch.where(is_small, relative_position, if_large)
+    return relative_buckets
+
+
+def bias_by_delta(weight, lq, lk, bidirectional, num_buckets):
+    """[H, lq+lk-1] fp32 table: entry (j - i) + (lq - 1) holds the head's bias for key j / query i
+    (`compute_bias`, src/modeling_t5.py:399-416, indexed by offset instead of a [lq, lk] matrix)."""
+    delta = torch.arange(-(lq - 1), lk, device=weight.device, dtype=torch.long)
+    buckets = relative_position_bucket(delta, bidirectional=bidirectional, num_buckets=num_buckets)
+    return weight[buckets].t().float().contiguous()
+
+
+class FiDOutput(tuple):
+    """(loss, logits, encoder_last_hidden_state) with the attribute names Atlas reads (src/atlas.py:292-300,583-590)."""
+
+    def __new__(cls, loss, logits, enc):
+        o = super().__new__(cls, (loss, logits, enc))
+        o.loss, o.logits, o.encoder_last_hidden_state = loss, logits, enc
+        return o
+
+
+class FiD(nn.Module):
+    def __init__(self, config=None):
+        super().__init__()
+        config = config or T5ConfigLite()
+        if config.d_kv != 64:
+            raise AtlasB200Error("atlas_b200 attention kernels need d_kv = 64 (all T5 v1.1 sizes)")
+        if getattr(config, "feed_forward_proj", "gated-gelu") != "gated-gelu":
+            raise AtlasB200Error("only T5 v1.1 (gated-gelu) is implemented")
+        self.config = config
+        self.model_dim = config.d_model
+        self.shared = nn.Embedding(config.vocab_size, config.d_model)
+        self.encoder = FiDStack(config, self.shared, is_decoder=False)
+        self.decoder = FiDStack(config, self.shared, is_decoder=True)
+        self.lm_head = nn.Linear(config.d_model, config.vocab_size, bias=False)
+        self.encoder.config.n_context = 1
+        self.encoder.config.bsz = 1
+        self._half = HalfCache()
+        self._gated = {}
+
+    # ---- reference surface that is configuration only -------------------------------------
+    def set_checkpoint(self, use_checkpoint):
+        pass
+
+    def gradient_checkpointing_enable(self):
+        pass
+
+    def gradient_checkpointing_disable(self):
+        pass
+
+    def reset_score_storage(self):
+        pass
+
+    def overwrite_forward_crossattention(self):
+        pass
+
+    def create_crossattention_storage(self):
+        pass
+
+    def get_crossattention_scores(self, *a, **k):
+        raise AtlasB200Error("cross-attention score capture (gold_score_mode eval*/std*/adist) is not implemented")
+
+    def _shift_right(self, input_ids):  # src/modeling_t5.py:789-813
+        start, pad = self.config.decoder_start_token_id, self.config.pad_token_id
+        shifted = input_ids.new_zeros(input_ids.shape)
+        shifted[..., 1:] = input_ids[..., :-1].clone()
+        shifted[..., 0] = start
+        shifted.masked_fill_(shifted == -100, pad)
+        return shifted
+
+    # ---- weights ---------------------------------------------------------------------------
+    def _dtype(self):
+        d = self.shared.weight.dtype
+        return d if d in (torch.float16, torch.bfloat16) else torch.bfloat16
+
+    def _weights(self):
+        dt = self._dtype()
+        W = self._half.get(self, dt)
+        if self._gated.get("key") is not self._half.key:
+            g = {}
+            for name in list(W.keys()):
+                if name.endswith("DenseReluDense.wi_0.weight"):
+                    w0, w1 = W[name], W[name.replace("wi_0", "wi_1")]
+                    # rows interleaved (wi_0[j], wi_1[j]) for the gated-GELU GEMM epilogue
+                    g[name.replace("wi_0.weight", "wi_01")] = torch.stack([w0, w1], dim=1).reshape(-1, w0.shape[1]).contiguous()
+            self._gated = {"key": self._half.key, "w": g}
+        return W, self._gated["w"], dt
+
+    # ---- encoder ---------------------------------------------------------------------------
+    def _ff(self, W, G, prefix, h, eps):
+        n = ops.layernorm(h, W[prefix + "layer_norm.weight"], None, eps, kind=1)
+        g = ops.linear(n, G[prefix + "DenseReluDense.wi_01"], epilogue=ops.EPI_GATED)
+        return ops.linear(g, W[prefix + "DenseReluDense.wo.weight"], None, residual=h, epilogue=ops.EPI_RESIDUAL)
+
+    @torch.no_grad()
+    def encode(self, input_ids, attention_mask):
+        """FiDStack encoder (src/fid.py:32-78): [B, n*L] -> each passage encoded independently -> [B, n*L, d]."""
+        c = self.config
+        W, G, dt = self._weights()
+        n_ctx, bsz = self.encoder.config.n_context, self.encoder.config.bsz
+        ids = input_ids.reshape(input_ids.size(0) * n_ctx, -1)
+        mask = attention_mask.reshape(attention_mask.size(0) * n_ctx, -1)
+        S, L = ids.shape
+        d, H = c.d_model, c.num_heads
+        h = W["shared.weight"][ids.reshape(-1)]                                  # embedding gather, [S*L, d]
+        add_mask = (1.0 - mask.to(torch.float32)) * -10000.0                      # 4.18 get_extended_attention_mask
+        bias = bias_by_delta(W["encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight"], L, L, True,
+                             c.relative_attention_num_buckets)
+        qkv = torch.empty((S * L, 3 * H * 64), dtype=dt, device=h.device)
+        for i in range(c.num_layers):
+            p = f"encoder.block.{i}.layer.0."
+            n = ops.layernorm(h, W[p + "layer_norm.weight"], None, c.layer_norm_epsilon, kind=1)
+            ops.linear(n, W[p + "SelfAttention.q.weight"], out=qkv[:, : H * 64])
+            ops.linear(n, W[p + "SelfAttention.k.weight"], out=qkv[:, H * 64: 2 * H * 64])
+            ops.linear(n, W[p + "SelfAttention.v.weight"], out=qkv[:, 2 * H * 64:])
+            ctx = ops.attention(qkv, 0, qkv, H * 64, qkv, 2 * H * 64, S, H, L, L, add_mask=add_mask, bias_delta=bias,
+                                scale=1.0)
+            h = ops.linear(ctx, W[p + "SelfAttention.o.weight"], None, residual=h, epilogue=ops.EPI_RESIDUAL)
+            h = self._ff(W, G, f"encoder.block.{i}.layer.1.", h, c.layer_norm_epsilon)
+        h = ops.layernorm(h, W["encoder.final_layer_norm.weight"], None, c.layer_norm_epsilon, kind=1)
+        return h.view(bsz, -1, d)
+
+    # ---- decoder ---------------------------------------------------------------------------
+    @torch.no_grad()
+    def cross_kv(self, enc):
+        """K/V projections of the encoder output for every decoder layer ([B*n*L, 2*H*64] each), computed once
+        per forward / per generation (the reference recomputes them every decoding step without use_cache)."""
+        c = self.config
+        W, _, dt = self._weights()
+        H = c.num_heads
+        flat = enc.reshape(-1, c.d_model)
+        out = []
+        for i in range(c.num_decoder_layers):
+            p = f"decoder.block.{i}.layer.1.EncDecAttention."
+            kv = torch.empty((flat.shape[0], 2 * H * 64), dtype=dt, device=flat.device)
+            ops.linear(flat, W[p + "k.weight"], out=kv[:, : H * 64])
+            ops.linear(flat, W[p + "v.weight"], out=kv[:, H * 64:])
+            out.append(kv)
+        return out
+
+    @torch.no_grad()
+    def decode(self, decoder_input_ids, enc, enc_mask, cross_kv=None):
+        """Decoder stack + LM head: [B, T] -> logits [B, T, vocab] (src/modeling_t5.py:875-1083,1619-1647)."""
+        c = self.config
+        W, G, dt = self._weights()
+        B, T = decoder_input_ids.shape
+        d, H = c.d_model, c.num_heads
+        Lk = enc.shape[1]
+        split = next(s for s in range(min(512, Lk), 0, -1) if Lk % s == 0)   # largest divisor of Lk that fits TMEM
+        if split < 64 and Lk > 512:
+            raise AtlasB200Error(f"n_context*text_maxlength = {Lk} has no divisor in [64, 512] for the split-KV kernel")
+        if cross_kv is None:
+            cross_kv = self.cross_kv(enc)
+        h = W["shared.weight"][decoder_input_ids.reshape(-1)]
+        bias = bias_by_delta(W["decoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight"], T, T, False,
+                             c.relative_attention_num_buckets)
+        # invert_attention_mask (4.18): -1e4 for fp16, -1e9 otherwise (src/modeling_t5.py:950)
+        neg = -1e4 if dt == torch.float16 else -1e9
+        cross_mask = (1.0 - enc_mask.reshape(B, Lk).to(torch.float32)) * neg
+        qkv = torch.empty((B * T, 3 * H * 64), dtype=dt, device=h.device)
+        for i in range(c.num_decoder_layers):
+            p = f"decoder.block.{i}.layer.0."
+            n = ops.layernorm(h, W[p + "layer_norm.weight"], None, c.layer_norm_epsilon, kind=1)
+            ops.linear(n, W[p + "SelfAttention.q.weight"], out=qkv[:, : H * 64])
+            ops.linear(n, W[p + "SelfAttention.k.weight"], out=qkv[:, H * 64: 2 * H * 64])
+            ops.linear(n, W[p + "SelfAttention.v.weight"], out=qkv[:, 2 * H * 64:])
+            ctx = ops.attention(qkv, 0, qkv, H * 64, qkv, 2 * H * 64, B, H, T, T, bias_delta=bias, scale=1.0,
+                                causal_value=-10000.0)
+            h = ops.linear(ctx, W[p + "SelfAttention.o.weight"], None, residual=h, epilogue=ops.EPI_RESIDUAL)
+            p = f"decoder.block.{i}.layer.1."
+            n = ops.layernorm(h, W[p + "layer_norm.weight"], None, c.layer_norm_epsilon, kind=1)
+            q = ops.linear(n, W[p + "EncDecAttention.q.weight"])
+            ctx = ops.cross_attention_split(q, 0, cross_kv[i], 0, H * 64, B, H, T, Lk, add_mask=cross_mask, scale=1.0,
+                                            split=split)
+            h = ops.linear(ctx, W[p + "EncDecAttention.o.weight"], None, residual=h, epilogue=ops.EPI_RESIDUAL)
+            h = self._ff(W, G, f"decoder.block.{i}.layer.2.", h, c.layer_norm_epsilon)
+        h = ops.layernorm(h, W["decoder.final_layer_norm.weight"], None, c.layer_norm_epsilon, kind=1)
+        if getattr(c, "tie_word_embeddings", False):
+            h = (h.float() * (d ** -0.5)).to(dt)                                  # src/modeling_t5.py:1642-1645
+        logits = ops.linear(h, W["lm_head.weight"])
+        return logits.view(B, T, -1)
+
+    # ---- public forward / generate -----------------------------------------------------------
+    def forward(self, input_ids=None, attention_mask=None, decoder_input_ids=None, labels=None, encoder_outputs=None,
+                use_cache=False, **unused):
+        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
+            raise AtlasB200Error("atlas_b200.FiD is forward-only in this round: call it under torch.no_grad()")
+        if encoder_outputs is not None:
+            enc = encoder_outputs[0]
+        else:
+            enc = self.encode(input_ids, attention_mask)
+        if decoder_input_ids is None and labels is not None:
+            decoder_input_ids = self._shift_right(labels)
+        B = enc.shape[0]
+        logits = self.decode(decoder_input_ids, enc, attention_mask.reshape(B, -1))
+        loss = None
+        if labels is not None:
+            # CrossEntropyLoss(ignore_index=-100), src/modeling_t5.py:1650-1652
+            loss = torch.nn.functional.cross_entropy(logits.reshape(-1, logits.size(-1)).float(), labels.reshape(-1),
+                                                     ignore_index=-100).to(logits.dtype)
+        pd = self.shared.weight.dtype
+        if logits.dtype != pd:
+            logits, enc = logits.to(pd), enc.to(pd)
+        return FiDOutput(loss, logits, enc)
+
+    @torch.no_grad()
+    def generate(self, input_ids=None, attention_mask=None, max_length=32, min_length=1, num_beams=1,
+                 num_return_sequences=1, length_penalty=1.0, forced_bos_token_id=None, prefix_allowed_tokens_fn=None,
+                 **unused):
+        """Greedy decoding (what `Atlas.generate` requests with num_beams=1, src/atlas.py:592-619): the encoder
+        and the cross-attention K/V projections run once, every step re-runs the (tiny) decoder prefix."""
+        if num_beams != 1 or num_return_sequences != 1:
+            raise AtlasB200Error("only greedy generation (num_beams=1) is implemented")
+        c = self.config
+        enc = self.encode(input_ids, attention_mask)
+        B = enc.shape[0]
+        kv = self.cross_kv(enc)
+        mask = attention_mask.reshape(B, -1)
+        seq = torch.full((B, 1), c.decoder_start_token_id, dtype=torch.long, device=enc.device)
+        done = torch.zeros(B, dtype=torch.bool, device=enc.device)
+        for step in range(max_length - 1):
+            logits = self.decode(seq, enc, mask, cross_kv=kv)[:, -1].float()
+            if step + 1 < min_length:
+                logits[:, c.eos_token_id] = -float("inf")
+            if prefix_allowed_tokens_fn is not None:
+                allowed = torch.full_like(logits, -float("inf"))
+                for b in range(B):
+                    allowed[b, prefix_allowed_tokens_fn(b, seq[b])] = 0
+                logits = logits + allowed
+            nxt = logits.argmax(dim=-1)
+            nxt = torch.where(done, torch.full_like(nxt, c.pad_token_id), nxt)
+            seq = torch.cat([seq, nxt[:, None]], dim=1)
+            done = done | (nxt == c.eos_token_id)
+            if bool(done.all()):
+                break
+        return seq

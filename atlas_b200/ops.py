@@ -247,5 +247,26 @@ def attention(q, q_col0, k, k_col0, v, v_col0, B, H, Lq, Lk, add_mask=None, bias
     check(lib().atlas_b200_attention(_ptr(q), q.stride(0), q_col0, _ptr(k), k.stride(0), k_col0, _ptr(v), v.stride(0),
                                      v_col0, _ptr(out), out.stride(0), _ptr(am) if am is not None else None,
                                      _ptr(bd) if bd is not None else None, B, H, Lq, Lk, float(scale),
-                                     float(causal_value), _bf(q), current_stream_ptr()))
+                                     float(causal_value), 1, None, None, _bf(q), current_stream_ptr()))
+    return out
+
+
+def cross_attention_split(q, q_col0, kv, k_col0, v_col0, B, H, Lq, Lk_total, add_mask=None, scale=1.0, split=512):
+    """Attention of Lq (<= 128) queries per batch element over Lk_total keys (FiD decoder cross-attention,
+    Lk_total = n_ctx * L): split-KV over segments of `split` keys + combine.  q [B*Lq, ld], kv [B*Lk_total, ld]."""
+    require_cuda(q, "q")
+    if Lk_total % split != 0:
+        raise AtlasB200Error(f"cross_attention_split: Lk_total={Lk_total} must be a multiple of {split}")
+    splits = Lk_total // split
+    o_part = torch.empty((B * splits * Lq, H * 64), dtype=torch.float32, device=q.device)
+    ml = torch.empty((B * splits * Lq, H, 2), dtype=torch.float32, device=q.device)
+    am = add_mask.float().contiguous() if add_mask is not None else None
+    dummy = torch.empty((8,), dtype=q.dtype, device=q.device)
+    check(lib().atlas_b200_attention(_ptr(q), q.stride(0), q_col0, _ptr(kv), kv.stride(0), k_col0, _ptr(kv),
+                                     kv.stride(0), v_col0, _ptr(dummy), 8, _ptr(am) if am is not None else None, None,
+                                     B * splits, H, Lq, split, float(scale), 0.0, splits, _ptr(o_part), _ptr(ml), _bf(q),
+                                     current_stream_ptr()))
+    out = torch.empty((B * Lq, H * 64), dtype=q.dtype, device=q.device)
+    check(lib().atlas_b200_attention_combine(_ptr(o_part), _ptr(ml), B, splits, Lq, H, _ptr(out), out.stride(0), _bf(q),
+                                             current_stream_ptr()))
     return out

@@ -1,0 +1,288 @@
+"""Drop-in for `src.retrievers` (reference src/retrievers.py:16-135): Contriever = BERT encoder + masked
+mean pooling, and the dual-encoder wrappers.  FORWARD ONLY in this round (index build / refresh and query
+embedding under `torch.no_grad`, which is how `Atlas.build_index` / `Atlas._retrieve` call it,
+src/atlas.py:61-88,90-118); the retriever-with-grad path of training is not provided yet.
+
+Parameter names and shapes are those of the reference's `BertModel` (vendored HF 4.18,
+src/modeling_bert.py:190-648,872-1045), so `load_state_dict` of a Contriever checkpoint works:
+    embeddings.{word,position,token_type}_embeddings.weight, embeddings.LayerNorm.{weight,bias},
+    encoder.layer.N.attention.self.{query,key,value}.{weight,bias}, attention.output.dense / LayerNorm,
+    intermediate.dense, output.dense / LayerNorm.
+The arithmetic runs in `csrc/`: tcgen05 GEMMs with fused bias / erf-GELU / residual epilogues, fused attention
+reading Q/K/V in place from one [tokens, 2304] projection buffer, the reference's non-standard BertLayerNorm
+(uncentred second moment, src/modeling_bert.py:104-114), masked mean pooling that can write straight into
+the passage bank rows.  16-bit only on the device: fp32 parameters (the live query encoder without
+`--precision bf16`) are cast to fp16 copies that are refreshed when the parameters change.
+"""
+import copy
+import math
+from types import SimpleNamespace
+
+import torch
+from torch import nn
+
+from . import ops
+from ._lib import AtlasB200Error
+
+EMBEDDINGS_DIM: int = 768
+
+
+class BertConfigLite(SimpleNamespace):
+    """The BertConfig fields this path reads (defaults = bert-base-uncased / facebook/contriever)."""
+
+    def __init__(self, **kw):
+        d = dict(vocab_size=30522, hidden_size=768, num_hidden_layers=12, num_attention_heads=12,
+                 intermediate_size=3072, max_position_embeddings=512, type_vocab_size=2, layer_norm_eps=1e-12,
+                 hidden_act="gelu", pad_token_id=0)
+        d.update(kw)
+        super().__init__(**d)
+
+
+def _cfg(config, name, default=None):
+    return getattr(config, name, default)
+
+
+class _LN(nn.Module):
+    def __init__(self, h):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(h))
+        self.bias = nn.Parameter(torch.zeros(h))
+
+
+class _Embeddings(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.word_embeddings = nn.Embedding(c.vocab_size, c.hidden_size, padding_idx=_cfg(c, "pad_token_id", 0))
+        self.position_embeddings = nn.Embedding(c.max_position_embeddings, c.hidden_size)
+        self.token_type_embeddings = nn.Embedding(c.type_vocab_size, c.hidden_size)
+        self.LayerNorm = _LN(c.hidden_size)
+        self.register_buffer("position_ids", torch.arange(c.max_position_embeddings).expand((1, -1)), persistent=False)
+
+
+class _SelfAttention(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.query = nn.Linear(c.hidden_size, c.hidden_size)
+        self.key = nn.Linear(c.hidden_size, c.hidden_size)
+        self.value = nn.Linear(c.hidden_size, c.hidden_size)
+
+
+class _DenseLN(nn.Module):
+    def __init__(self, fin, fout):
+        super().__init__()
+        self.dense = nn.Linear(fin, fout)
+        self.LayerNorm = _LN(fout)
+
+
+class _Attention(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.self = _SelfAttention(c)
+        self.output = _DenseLN(c.hidden_size, c.hidden_size)
+
+
+class _Intermediate(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.dense = nn.Linear(c.hidden_size, c.intermediate_size)
+
+
+class _Layer(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.attention = _Attention(c)
+        self.intermediate = _Intermediate(c)
+        self.output = _DenseLN(c.intermediate_size, c.hidden_size)
+
+
+class _Encoder(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.layer = nn.ModuleList([_Layer(c) for _ in range(c.num_hidden_layers)])
+
+
+class HalfCache:
+    """16-bit device copies of a module's parameters, rebuilt when any parameter changed (`_version`)."""
+
+    def __init__(self):
+        self.key, self.store = None, {}
+
+    def get(self, module, dtype):
+        params = list(module.named_parameters())
+        key = (dtype, tuple((p.data_ptr(), p._version) for _, p in params))
+        if key != self.key:
+            self.store = {n: (p.detach() if p.dtype == dtype else p.detach().to(dtype)).contiguous() for n, p in params}
+            self.key = key
+        return self.store
+
+
+class Contriever(nn.Module):
+    def __init__(self, config=None, pooling="average", **kwargs):
+        super().__init__()
+        config = config or BertConfigLite()
+        self.config = config
+        if not hasattr(config, "pooling"):
+            self.config.pooling = pooling
+        if config.hidden_size != config.num_attention_heads * 64:
+            raise AtlasB200Error("atlas_b200 attention kernels need head_dim 64")
+        if _cfg(config, "hidden_act", "gelu") != "gelu":
+            raise AtlasB200Error("only the erf GELU of BERT-base / Contriever is implemented")
+        self.embeddings = _Embeddings(config)
+        self.encoder = _Encoder(config)
+        self._half = HalfCache()
+        self.apply(self._init_weights)
+
+    def _init_weights(self, m):  # HF BERT init (src/modeling_bert.py:~850), std 0.02
+        if isinstance(m, nn.Linear):
+            m.weight.data.normal_(mean=0.0, std=0.02)
+            if m.bias is not None:
+                m.bias.data.zero_()
+        elif isinstance(m, nn.Embedding):
+            m.weight.data.normal_(mean=0.0, std=0.02)
+            if m.padding_idx is not None:
+                m.weight.data[m.padding_idx].zero_()
+
+    def gradient_checkpointing_enable(self):
+        pass
+
+    def gradient_checkpointing_disable(self):
+        pass
+
+    def _dtype(self):
+        d = self.embeddings.word_embeddings.weight.dtype
+        return d if d in (torch.float16, torch.bfloat16) else torch.float16
+
+    @torch.no_grad()
+    def encode(self, input_ids, attention_mask, token_type_ids=None, out=None):
+        """last hidden state [B, L, H] in the 16-bit compute dtype (src/modeling_bert.py:929-1045)."""
+        c = self.config
+        dt = self._dtype()
+        W = self._half.get(self, dt)
+        B, L = input_ids.shape
+        H, nh = c.hidden_size, c.num_attention_heads
+        h = ops.bert_embed_ln(input_ids, token_type_ids, W["embeddings.word_embeddings.weight"],
+                              W["embeddings.token_type_embeddings.weight"], W["embeddings.position_embeddings.weight"],
+                              W["embeddings.LayerNorm.weight"], W["embeddings.LayerNorm.bias"], c.layer_norm_eps)
+        h = h.view(B * L, H)
+        # transformers==4.18 get_extended_attention_mask: (1 - mask) * -10000 (src/modeling_bert.py:993)
+        add_mask = (1.0 - attention_mask.to(torch.float32)) * -10000.0
+        qkv = torch.empty((B * L, 3 * H), dtype=dt, device=h.device)
+        for i in range(c.num_hidden_layers):
+            p = f"encoder.layer.{i}."
+            ops.linear(h, W[p + "attention.self.query.weight"], W[p + "attention.self.query.bias"], out=qkv[:, 0:H])
+            ops.linear(h, W[p + "attention.self.key.weight"], W[p + "attention.self.key.bias"], out=qkv[:, H:2 * H])
+            ops.linear(h, W[p + "attention.self.value.weight"], W[p + "attention.self.value.bias"], out=qkv[:, 2 * H:])
+            ctx = ops.attention(qkv, 0, qkv, H, qkv, 2 * H, B, nh, L, L, add_mask=add_mask, scale=1.0 / math.sqrt(64))
+            s1 = ops.linear(ctx, W[p + "attention.output.dense.weight"], W[p + "attention.output.dense.bias"], residual=h)
+            h1 = ops.layernorm(s1, W[p + "attention.output.LayerNorm.weight"], W[p + "attention.output.LayerNorm.bias"],
+                               c.layer_norm_eps, kind=0)
+            inter = ops.linear(h1, W[p + "intermediate.dense.weight"], W[p + "intermediate.dense.bias"],
+                               epilogue=ops.EPI_GELU)
+            s2 = ops.linear(inter, W[p + "output.dense.weight"], W[p + "output.dense.bias"], residual=h1)
+            h = ops.layernorm(s2, W[p + "output.LayerNorm.weight"], W[p + "output.LayerNorm.bias"], c.layer_norm_eps,
+                              kind=0)
+        return h.view(B, L, H)
+
+    def forward(self, input_ids=None, attention_mask=None, token_type_ids=None, position_ids=None, head_mask=None,
+                inputs_embeds=None, encoder_hidden_states=None, encoder_attention_mask=None, output_attentions=None,
+                output_hidden_states=None, normalize=False):
+        """src/retrievers.py:22-60.  Returns [B, 768] embeddings in the parameters' dtype."""
+        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
+            raise AtlasB200Error("atlas_b200.Contriever is forward-only in this round: call it under torch.no_grad() "
+                                 "(index build / query embedding); retriever training is not implemented")
+        if position_ids is not None or inputs_embeds is not None:
+            raise AtlasB200Error("position_ids / inputs_embeds are not used by Atlas and not supported")
+        last_hidden = self.encode(input_ids, attention_mask, token_type_ids)
+        pooling = self.config.pooling
+        if pooling == "average":
+            emb = ops.masked_mean_pool(last_hidden, attention_mask)
+        elif pooling == "cls":
+            emb = last_hidden[:, 0].clone()
+        else:
+            raise AtlasB200Error(f"pooling={pooling!r} is not implemented (Contriever uses 'average')")
+        if normalize:
+            emb = torch.nn.functional.normalize(emb.float(), dim=-1).to(emb.dtype)
+        pd = self.embeddings.word_embeddings.weight.dtype
+        return emb if emb.dtype == pd else emb.to(pd)
+
+    @torch.no_grad()
+    def embed_into(self, input_ids, attention_mask, bank_rows):
+        """Index refresh in place: pooled embeddings written straight into `bank_rows` ([B, 768] slice of
+        the passage bank) - replaces `index.embeddings[:, a:b] = embeddings.T` (src/atlas.py:78-79)."""
+        last_hidden = self.encode(input_ids, attention_mask)
+        if last_hidden.dtype != bank_rows.dtype:
+            raise AtlasB200Error("embed_into: the retriever copy must have the bank dtype (fp16, src/atlas.py:54-59)")
+        ops.masked_mean_pool(last_hidden, attention_mask, out=bank_rows)
+        return bank_rows
+
+
+class BaseRetriever(nn.Module):
+    """src/retrievers.py:63-87."""
+
+    def __init__(self, *args, **kwargs):
+        super(BaseRetriever, self).__init__()
+
+    def embed_queries(self, *args, **kwargs):
+        raise NotImplementedError()
+
+    def embed_passages(self, *args, **kwargs):
+        raise NotImplementedError()
+
+    def forward(self, *args, is_passages=False, **kwargs):
+        if is_passages:
+            return self.embed_passages(*args, **kwargs)
+        else:
+            return self.embed_queries(*args, **kwargs)
+
+    def gradient_checkpointing_enable(self):
+        for m in self.children():
+            m.gradient_checkpointing_enable()
+
+    def gradient_checkpointing_disable(self):
+        for m in self.children():
+            m.gradient_checkpointing_disable()
+
+
+class DualEncoderRetriever(BaseRetriever):
+    """src/retrievers.py:90-105."""
+
+    def __init__(self, opt, contriever):
+        super(DualEncoderRetriever, self).__init__()
+        self.opt = opt
+        self.contriever = contriever
+
+    def _embed(self, *args, **kwargs):
+        return self.contriever(*args, **kwargs)
+
+    def embed_queries(self, *args, **kwargs):
+        return self._embed(*args, **kwargs)
+
+    def embed_passages(self, *args, **kwargs):
+        return self._embed(*args, **kwargs)
+
+
+class UntiedDualEncoderRetriever(BaseRetriever):
+    """src/retrievers.py:108-135."""
+
+    def __init__(self, opt, query_encoder, passage_encoder=None):
+        super(UntiedDualEncoderRetriever, self).__init__()
+        self.opt = opt
+        self.query_contriever = query_encoder
+        if passage_encoder is None:
+            passage_encoder = copy.deepcopy(query_encoder) if hasattr(query_encoder, "module") else query_encoder
+        self.passage_contriever = passage_encoder
+
+    def embed_queries(self, *args, **kwargs):
+        return self.query_contriever(*args, **kwargs)
+
+    def embed_passages(self, *args, **kwargs):
+        if self.opt.query_side_retriever_training:
+            is_train = self.passage_contriever.training
+            self.passage_contriever.eval()
+            with torch.no_grad():
+                passage_emb = self.passage_contriever(*args, **kwargs)
+            if is_train:
+                self.passage_contriever.train()
+        else:
+            passage_emb = self.passage_contriever(*args, **kwargs)
+        return passage_emb

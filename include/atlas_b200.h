@@ -153,7 +153,16 @@ int atlas_b200_masked_mean_pool(const void* x, const int64_t* mask, void* out, i
 int atlas_b200_attention(const void* q, int64_t ldq, int32_t q_col0, const void* k, int64_t ldk, int32_t k_col0,
                          const void* v, int64_t ldv, int32_t v_col0, void* out, int64_t ldo,
                          const float* add_mask, const float* bias_delta, int32_t B, int32_t H, int32_t Lq,
-                         int32_t Lk, float scale, float causal_value, int32_t is_bf16, void* stream);
+                         int32_t Lk, float scale, float causal_value, int32_t q_div, float* o_partial,
+                         float* ml_partial, int32_t is_bf16, void* stream);
+
+/* Split-KV support for the FiD decoder's cross-attention over n_ctx*L (= 15 360) keys
+ * (fid.py:298-349 / src/modeling_t5.py:478-524): call atlas_b200_attention with B = batch*splits key
+ * segments of <= 512 keys, q_div = splits (segment s reads the queries of batch s / splits) and
+ * o_partial [B*Lq, H*64] / ml_partial [B*Lq, H, 2] fp32 (un-normalised output, row max, row sum);
+ * then this merges the splits:  out[b,i,h,:] = sum_s e^(m_s-M) O_s / sum_s e^(m_s-M) l_s. */
+int atlas_b200_attention_combine(const float* o_partial, const float* ml_partial, int32_t B, int32_t splits,
+                                 int32_t Lq, int32_t H, void* out, int64_t ldo, int32_t is_bf16, void* stream);
 
 /* Measurement hook for bench.py's roofline: while enabled, every launch of the DOMINANT kernel (the
  * main bank sweep of atlas_b200_mips_topk) is bracketed with CUDA events on its launching stream.
