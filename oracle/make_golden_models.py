@@ -46,6 +46,9 @@ def fid():
     from src.fid import FiD
 
     cfg = T5Config(**model_synth.T5_CFG)
+    # transformers 5.x drops the kwarg; T5 v1.1 checkpoints (google/t5-*-lm-adapt) have untied heads
+    cfg.tie_word_embeddings = False
+    assert cfg.tie_word_embeddings is False
     ids, mask, labels = model_synth.fid_inputs()
     B, n_ctx = 2, 3
     out = {}
