@@ -27,10 +27,11 @@ namespace attn {
 constexpr int D = 64;            // head dim
 constexpr int BLOCK_Q = 128;
 constexpr int MAX_LK = 512;
-constexpr int THREADS = 256;
-constexpr int Q_BYTES = BLOCK_Q * D * 2;        // 16 KB
+constexpr int THREADS = 384;
+constexpr int SM_THREADS = 256;                 // softmax / output threads (warps 4..11), 2 per query row
+constexpr int Q_BYTES = BLOCK_Q * D * 2;        // 16 KB, double buffered
 constexpr int KV_BYTES = MAX_LK * D * 2;        // 64 KB each
-constexpr int SMEM_BYTES = Q_BYTES + 2 * KV_BYTES + 1024;
+constexpr int SMEM_BYTES = 2 * Q_BYTES + 2 * KV_BYTES + 1024;
 constexpr int TMEM_COLS = 512;
 constexpr float LOG2E = 1.4426950408889634f;
 
@@ -49,14 +50,6 @@ struct Params {
     float* o_partial;         // [B*Lq, H*64] fp32 or nullptr
     float* ml_partial;        // [B*Lq, H, 2] fp32
 };
-
-__device__ __forceinline__ void tmem_ld32f(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
-    ab::tmem_ld32(taddr, r);
-    ab::tmem_ld_wait();
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-}
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
     asm volatile(
@@ -89,24 +82,40 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
            (static_cast<uint32_t>(__half_as_ushort(__float2half_rn(b))) << 16);
 }
 
+__device__ __forceinline__ void sm_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// scores of one 32-key chunk in the log2 domain: t = v*scale2 + (mask2[j] + bias2[j + boff])
+template <bool kBias>
+__device__ __forceinline__ void chunk_scores(const uint32_t (&r)[32], float (&t)[32], float scale2, const float* mask2,
+                                             const float* bias2, int j0, int boff) {
+#pragma unroll
+    for (int jj = 0; jj < 32; ++jj) {
+        float add = mask2[j0 + jj];
+        if (kBias) add += bias2[j0 + jj + boff];
+        t[jj] = fmaf(__uint_as_float(r[jj]), scale2, add);
+    }
+}
+
 template <bool kBF16>
 __global__ void __launch_bounds__(THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                  const __grid_constant__ CUtensorMap tmap_v, const Params p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t kv_full, kv_empty, q_full, q_empty, s_full, p_ready, o_full, s_free;
+    __shared__ __align__(8) uint64_t k_full, k_empty, v_full, v_empty, q_full[2], q_empty[2], s_full, p_ready, o_full, s_free;
     __shared__ uint32_t tmem_base_smem;
-    __shared__ float s_bias[2 * MAX_LK];  // bias by (j - i) + (Lq - 1), this head
-    __shared__ float s_mask[MAX_LK];      // additive key mask, this segment
+    __shared__ float s_bias[2 * MAX_LK];  // (bias by (j - i) + (Lq - 1) [+ causal]) * log2e, this head
+    __shared__ float s_mask[MAX_LK];      // additive key mask * log2e (-inf beyond Lk), this segment
+    __shared__ float s_red[2][BLOCK_Q];   // per-row partial max of the two key halves
+    __shared__ float s_sum[2][BLOCK_Q];   // per-row partial sums
 
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t smem_base = (ab::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - ab::smem_u32(smem_raw));
     uint8_t* sQ = smem_gen;
-    uint8_t* sK = smem_gen + Q_BYTES;
+    uint8_t* sK = smem_gen + 2 * Q_BYTES;
     uint8_t* sV = sK + KV_BYTES;
-    const uint32_t aQ = smem_base, aK = smem_base + Q_BYTES, aV = aK + KV_BYTES;
+    const uint32_t aQ = smem_base, aK = smem_base + 2 * Q_BYTES, aV = aK + KV_BYTES;
 
     const int n_chunks = (p.Lk + 127) / 128;   // 128-key chunks (TMA boxes / S column blocks)
     const int lk_pad = n_chunks * 128;
@@ -120,14 +129,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         ab::tma_prefetch_desc(&tmap_v);
     }
     if (warp == 1 && lane == 0) {
-        ab::mbar_init(&kv_full, 1);
-        ab::mbar_init(&kv_empty, 1);
-        ab::mbar_init(&q_full, 1);
-        ab::mbar_init(&q_empty, 1);
+        ab::mbar_init(&k_full, 1);
+        ab::mbar_init(&k_empty, 1);
+        ab::mbar_init(&v_full, 1);
+        ab::mbar_init(&v_empty, 1);
+        for (int i = 0; i < 2; ++i) {
+            ab::mbar_init(&q_full[i], 1);
+            ab::mbar_init(&q_empty[i], 1);
+        }
         ab::mbar_init(&s_full, 1);
-        ab::mbar_init(&p_ready, 128);
+        ab::mbar_init(&p_ready, SM_THREADS);
         ab::mbar_init(&o_full, 1);
-        ab::mbar_init(&s_free, 128);
+        ab::mbar_init(&s_free, SM_THREADS);
         ab::fence_barrier_init();
     }
     if (warp == 2) ab::tmem_alloc<1>(&tmem_base_smem, TMEM_COLS);
@@ -138,24 +151,33 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
     if (warp == 0) {
         // ===================== TMA producer =====================
+        // K and V have separate barriers: the next (segment, head)'s K streams in while the current one's last
+        // query tile is still in its softmax / P.V phase, its V while the next S = Q.K^T and softmax run.
         if (lane == 0) {
             int item_it = 0, qt_it = 0;
+            const uint32_t kv_bytes = static_cast<uint32_t>(n_chunks * 128 * D * 2);
+            auto load_q = [&](int b, int h, int qt) {
+                const int qb = qt_it & 1;
+                ab::mbar_wait(&q_empty[qb], ((qt_it >> 1) & 1) ^ 1u, 22);
+                ab::mbar_arrive_expect_tx(&q_full[qb], Q_BYTES);
+                ab::tma_load_2d(&tmap_q, &q_full[qb], sQ + qb * Q_BYTES, p.q_col0 + h * D,
+                                (b / p.q_div) * p.Lq + qt * BLOCK_Q, ab::kEvictFirst);
+                ++qt_it;
+            };
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_it) {
                 const int b = item / p.H, h = item % p.H;
-                ab::mbar_wait(&kv_empty, (item_it & 1) ^ 1u, 21);
-                ab::mbar_arrive_expect_tx(&kv_full, static_cast<uint32_t>(2 * n_chunks * 128 * D * 2));
-                for (int c = 0; c < n_chunks; ++c) {
-                    ab::tma_load_2d(&tmap_k, &kv_full, sK + c * (128 * D * 2), p.k_col0 + h * D, b * p.Lk + c * 128,
+                ab::mbar_wait(&k_empty, (item_it & 1) ^ 1u, 21);
+                ab::mbar_arrive_expect_tx(&k_full, kv_bytes);
+                for (int c = 0; c < n_chunks; ++c)
+                    ab::tma_load_2d(&tmap_k, &k_full, sK + c * (128 * D * 2), p.k_col0 + h * D, b * p.Lk + c * 128,
                                     ab::kEvictNormal);
-                    ab::tma_load_2d(&tmap_v, &kv_full, sV + c * (128 * D * 2), p.v_col0 + h * D, b * p.Lk + c * 128,
+                load_q(b, h, 0);
+                ab::mbar_wait(&v_empty, (item_it & 1) ^ 1u, 29);
+                ab::mbar_arrive_expect_tx(&v_full, kv_bytes);
+                for (int c = 0; c < n_chunks; ++c)
+                    ab::tma_load_2d(&tmap_v, &v_full, sV + c * (128 * D * 2), p.v_col0 + h * D, b * p.Lk + c * 128,
                                     ab::kEvictNormal);
-                }
-                for (int qt = 0; qt < n_qt; ++qt, ++qt_it) {
-                    ab::mbar_wait(&q_empty, (qt_it & 1) ^ 1u, 22);
-                    ab::mbar_arrive_expect_tx(&q_full, Q_BYTES);
-                    ab::tma_load_2d(&tmap_q, &q_full, sQ, p.q_col0 + h * D, (b / p.q_div) * p.Lq + qt * BLOCK_Q,
-                                    ab::kEvictFirst);
-                }
+                for (int qt = 1; qt < n_qt; ++qt) load_q(b, h, qt);
             }
         }
     } else if (warp == 1) {
@@ -166,12 +188,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             constexpr uint32_t idesc_o = ab::umma_idesc_f16(BLOCK_Q, D, kBF16) | (1u << 16);
             int item_it = 0, qt_it = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_it) {
-                ab::mbar_wait(&kv_full, item_it & 1, 23);
+                ab::mbar_wait(&k_full, item_it & 1, 23);
                 for (int qt = 0; qt < n_qt; ++qt, ++qt_it) {
-                    ab::mbar_wait(&q_full, qt_it & 1, 24);
+                    const int qb = qt_it & 1;
+                    ab::mbar_wait(&q_full[qb], (qt_it >> 1) & 1, 24);
                     ab::mbar_wait(&s_free, (qt_it & 1) ^ 1u, 25);
                     ab::tc_fence_after();
-                    const uint64_t qdesc = ab::umma_desc_k_sw128(aQ);
+                    const uint64_t qdesc = ab::umma_desc_k_sw128(aQ + qb * Q_BYTES);
                     for (int c = 0; c < n_chunks; ++c) {
                         const uint64_t kdesc = ab::umma_desc_k_sw128(aK + c * (128 * D * 2));
 #pragma unroll
@@ -179,123 +202,143 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                             ab::umma_ss<1>(tmem_base + c * 128, qdesc + ((k * 32) >> 4), kdesc + ((k * 32) >> 4), idesc_s,
                                            k != 0 ? 1u : 0u);
                     }
-                    ab::umma_commit(&q_empty);  // Q tile consumed once the S MMAs retire
+                    ab::umma_commit(&q_empty[qb]);  // Q tile consumed once the S MMAs retire
+                    if (qt == n_qt - 1) ab::umma_commit(&k_empty);
                     ab::umma_commit(&s_full);
+                    if (qt == 0) ab::mbar_wait(&v_full, item_it & 1, 30);
                     ab::mbar_wait(&p_ready, qt_it & 1, 26);
                     ab::tc_fence_after();
                     const uint64_t vdesc = umma_desc_mn_sw128(aV);
                     for (int k = 0; k < lk_pad / 16; ++k)
                         ab::umma_ts<1>(tmem_base + o_col, tmem_base + k * 8, vdesc + static_cast<uint64_t>((k * 2048) >> 4),
                                        idesc_o, k != 0 ? 1u : 0u);
-                    if (qt == n_qt - 1) ab::umma_commit(&kv_empty);  // last use of this (segment, head)'s K / V
+                    if (qt == n_qt - 1) ab::umma_commit(&v_empty);  // last use of this (segment, head)'s V
                     ab::umma_commit(&o_full);
                 }
             }
         }
     } else if (warp >= 4) {
-        // ===================== softmax + output =====================
+        // ===================== softmax + output: two threads per query row =====================
         const uint32_t lg = warp & 3u;
-        const int row_in_tile = static_cast<int>(lg * 32 + lane);
+        const uint32_t half = (warp - 4u) >> 2;                    // key chunks half, half+2, ... ; O columns 32*half..
+        const int row = static_cast<int>(lg * 32 + lane);
         const uint32_t lane_addr = tmem_base + ((lg * 32u) << 16);
         const int tid = static_cast<int>(threadIdx.x) - 128;
+        const float scale2 = p.scale * LOG2E;
+        const bool has_bias = (p.bias_delta != nullptr) || (p.causal_value != 0.f);
+        const int n32 = lk_pad / 32;
         int qt_it = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int b = item / p.H, h = item % p.H;
-            // per-(segment, head) tables; the previous item's softmax is finished (all 128 threads passed its o_full)
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            for (int j = tid; j < lk_pad; j += 128)
-                s_mask[j] = (j < p.Lk) ? (p.add_mask ? p.add_mask[static_cast<size_t>(b) * p.Lk + j] : 0.f) : -INFINITY;
-            if (p.bias_delta)
-                for (int d = tid; d < p.Lq + p.Lk - 1; d += 128)
-                    s_bias[d] = p.bias_delta[static_cast<size_t>(h) * (p.Lq + p.Lk - 1) + d];
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            sm_bar();  // the previous item's softmax passes are over for all 256 threads
+            for (int j = tid; j < lk_pad; j += SM_THREADS)
+                s_mask[j] = (j < p.Lk) ? (p.add_mask ? p.add_mask[static_cast<size_t>(b) * p.Lk + j] * LOG2E : 0.f)
+                                       : -INFINITY;
+            if (has_bias)
+                for (int d = tid; d < 2 * MAX_LK; d += SM_THREADS) {   // entries past the valid offsets stay finite (0)
+                    float v = 0.f;
+                    if (d < p.Lq + p.Lk - 1) {
+                        v = p.bias_delta ? p.bias_delta[static_cast<size_t>(h) * (p.Lq + p.Lk - 1) + d] : 0.f;
+                        if (p.causal_value != 0.f && d > p.Lq - 1) v += p.causal_value;   // j > i
+                    }
+                    s_bias[d] = v * LOG2E;
+                }
+            sm_bar();
             for (int qt = 0; qt < n_qt; ++qt, ++qt_it) {
-                const int i = qt * BLOCK_Q + row_in_tile;       // query position inside the segment
-                const int boff = p.Lq - 1 - i;                  // bias index = j + boff
+                const int i = qt * BLOCK_Q + row;                   // query position inside the segment
+                const int boff = min(p.Lq - 1 - i, 2 * MAX_LK - 1 - lk_pad);  // bias index = j + boff (clamped for pad rows)
+                const int boffc = max(boff, 0);
                 ab::mbar_wait(&s_full, qt_it & 1, 27);
                 ab::tc_fence_after();
-                // ---- pass 1: row max of scale*s + bias + mask ----
+                // ---- pass 1: partial row max over this thread's chunks (loads software-pipelined) ----
                 float mx = -INFINITY;
-                for (int c = 0; c < lk_pad / 32; ++c) {
-                    float v[32];
-                    tmem_ld32f(lane_addr + c * 32, v);
+                {
+                    uint32_t ra[32], rb[32];
+                    float t[32];
+                    int c = static_cast<int>(half);
+                    ab::tmem_ld32(lane_addr + c * 32, ra);
+                    while (c < n32) {
+                        ab::tmem_ld_wait();
+                        if (c + 2 < n32) ab::tmem_ld32(lane_addr + (c + 2) * 32, rb);
+                        if (has_bias) chunk_scores<true>(ra, t, scale2, s_mask, s_bias, c * 32, boffc);
+                        else chunk_scores<false>(ra, t, scale2, s_mask, s_bias, c * 32, boffc);
 #pragma unroll
-                    for (int jj = 0; jj < 32; ++jj) {
-                        const int j = c * 32 + jj;
-                        float s = v[jj] * p.scale + s_mask[j];
-                        if (p.bias_delta) s += s_bias[min(max(j + boff, 0), 2 * MAX_LK - 1)];
-                        if (p.causal_value != 0.f && j > i) s += p.causal_value;
-                        mx = fmaxf(mx, s);
+                        for (int jj = 0; jj < 32; ++jj) mx = fmaxf(mx, t[jj]);
+                        c += 2;
+                        if (c >= n32) break;
+                        ab::tmem_ld_wait();
+                        if (c + 2 < n32) ab::tmem_ld32(lane_addr + (c + 2) * 32, ra);
+                        if (has_bias) chunk_scores<true>(rb, t, scale2, s_mask, s_bias, c * 32, boffc);
+                        else chunk_scores<false>(rb, t, scale2, s_mask, s_bias, c * 32, boffc);
+#pragma unroll
+                        for (int jj = 0; jj < 32; ++jj) mx = fmaxf(mx, t[jj]);
+                        c += 2;
                     }
                 }
-                // ---- pass 2: p = exp(s - max), row sum, P (16-bit) written over the S columns it replaces ----
+                s_red[half][row] = mx;
+                sm_bar();
+                mx = fmaxf(s_red[0][row], s_red[1][row]);
+                // ---- pass 2: p = 2^(t - max), partial row sum, P (16-bit) written over the S columns it replaces ----
                 float sum = 0.f;
-                const float mxl = mx * LOG2E;
-                for (int c = 0; c < lk_pad / 32; ++c) {
-                    float v[32];
-                    tmem_ld32f(lane_addr + c * 32, v);
-                    uint32_t pk[16];
+                {
+                    uint32_t ra[32];
+                    float t[32];
+                    for (int c = static_cast<int>(half); c < n32; c += 2) {
+                        ab::tmem_ld32(lane_addr + c * 32, ra);
+                        ab::tmem_ld_wait();
+                        if (has_bias) chunk_scores<true>(ra, t, scale2, s_mask, s_bias, c * 32, boffc);
+                        else chunk_scores<false>(ra, t, scale2, s_mask, s_bias, c * 32, boffc);
+                        uint32_t pk[16];
 #pragma unroll
-                    for (int jj = 0; jj < 32; jj += 2) {
-                        float e[2];
-#pragma unroll
-                        for (int u = 0; u < 2; ++u) {
-                            const int j = c * 32 + jj + u;
-                            float s = v[jj + u] * p.scale + s_mask[j];
-                            if (p.bias_delta) s += s_bias[min(max(j + boff, 0), 2 * MAX_LK - 1)];
-                            if (p.causal_value != 0.f && j > i) s += p.causal_value;
-                            e[u] = exp2f(s * LOG2E - mxl);
-                            sum += e[u];
+                        for (int jj = 0; jj < 32; jj += 2) {
+                            const float e0 = exp2f(t[jj] - mx), e1 = exp2f(t[jj + 1] - mx);
+                            sum += e0 + e1;
+                            pk[jj >> 1] = pack2<kBF16>(e0, e1);
                         }
-                        pk[jj >> 1] = pack2<kBF16>(e[0], e[1]);
+                        tmem_st16(lane_addr + c * 16, pk);
                     }
-                    tmem_st16(lane_addr + c * 16, pk);
                 }
+                s_sum[half][row] = sum;
                 ab::tmem_st_wait();
                 ab::tc_fence_before();
+                sm_bar();  // both halves' sums are in smem; all P columns of this warp pair are written
                 ab::mbar_arrive(&p_ready);
-                // ---- output: O / sum -> 16-bit, 128 contiguous bytes per row ----
+                sum = s_sum[0][row] + s_sum[1][row];
+                // ---- output: this thread's 32 of the 64 O columns ----
                 ab::mbar_wait(&o_full, qt_it & 1, 28);
                 ab::tc_fence_after();
-                if (p.o_partial != nullptr) {
-                    // split-KV: un-normalised partial output in fp32 + (max, sum) of this split
-                    float* dst = p.o_partial + (static_cast<size_t>(b) * p.Lq + i) * (static_cast<size_t>(p.H) * D) + h * D;
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        float v[32];
-                        tmem_ld32f(lane_addr + o_col + c * 32, v);
-                        if (i < p.Lq) {
-#pragma unroll
-                            for (int v4 = 0; v4 < 8; ++v4)
-                                reinterpret_cast<float4*>(dst + c * 32)[v4] =
-                                    make_float4(v[4 * v4], v[4 * v4 + 1], v[4 * v4 + 2], v[4 * v4 + 3]);
-                        }
-                    }
-                    ab::tc_fence_before();
-                    ab::mbar_arrive(&s_free);
-                    if (i < p.Lq) {
-                        float* ml = p.ml_partial + ((static_cast<size_t>(b) * p.Lq + i) * p.H + h) * 2;
-                        ml[0] = mx;
-                        ml[1] = sum;
-                    }
-                } else {
-                const float inv = 1.0f / sum;
-                uint32_t outw[32];
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    float v[32];
-                    tmem_ld32f(lane_addr + o_col + c * 32, v);
-#pragma unroll
-                    for (int jj = 0; jj < 32; jj += 2) outw[c * 16 + (jj >> 1)] = pack2<kBF16>(v[jj] * inv, v[jj + 1] * inv);
-                }
+                uint32_t ro[32];
+                ab::tmem_ld32(lane_addr + o_col + half * 32, ro);
+                ab::tmem_ld_wait();
                 ab::tc_fence_before();
                 ab::mbar_arrive(&s_free);  // S / P / O columns may be overwritten by the next query tile
                 if (i < p.Lq) {
-                    uint4* dst = reinterpret_cast<uint4*>(p.O + (static_cast<size_t>(b) * p.Lq + i) * p.ldo + h * D);
+                    if (p.o_partial != nullptr) {
+                        // split-KV: un-normalised partial output in fp32 + (max, sum) of this split (natural log units)
+                        float* dst = p.o_partial + (static_cast<size_t>(b) * p.Lq + i) * (static_cast<size_t>(p.H) * D) +
+                                     h * D + half * 32;
 #pragma unroll
-                    for (int v4 = 0; v4 < 8; ++v4)
-                        dst[v4] = make_uint4(outw[4 * v4], outw[4 * v4 + 1], outw[4 * v4 + 2], outw[4 * v4 + 3]);
-                }
+                        for (int v4 = 0; v4 < 8; ++v4)
+                            reinterpret_cast<float4*>(dst)[v4] =
+                                make_float4(__uint_as_float(ro[4 * v4]), __uint_as_float(ro[4 * v4 + 1]),
+                                            __uint_as_float(ro[4 * v4 + 2]), __uint_as_float(ro[4 * v4 + 3]));
+                        if (half == 0) {
+                            float* ml = p.ml_partial + ((static_cast<size_t>(b) * p.Lq + i) * p.H + h) * 2;
+                            ml[0] = mx * (1.0f / LOG2E);
+                            ml[1] = sum;
+                        }
+                    } else {
+                        const float inv = 1.0f / sum;
+                        uint4* dst = reinterpret_cast<uint4*>(p.O + (static_cast<size_t>(b) * p.Lq + i) * p.ldo + h * D +
+                                                              half * 32);
+#pragma unroll
+                        for (int v4 = 0; v4 < 4; ++v4)
+                            dst[v4] = make_uint4(
+                                pack2<kBF16>(__uint_as_float(ro[8 * v4]) * inv, __uint_as_float(ro[8 * v4 + 1]) * inv),
+                                pack2<kBF16>(__uint_as_float(ro[8 * v4 + 2]) * inv, __uint_as_float(ro[8 * v4 + 3]) * inv),
+                                pack2<kBF16>(__uint_as_float(ro[8 * v4 + 4]) * inv, __uint_as_float(ro[8 * v4 + 5]) * inv),
+                                pack2<kBF16>(__uint_as_float(ro[8 * v4 + 6]) * inv, __uint_as_float(ro[8 * v4 + 7]) * inv));
+                    }
                 }
             }
         }

@@ -209,6 +209,12 @@ class FiD(nn.Module):
                     w0, w1 = W[name], W[name.replace("wi_0", "wi_1")]
                     # rows interleaved (wi_0[j], wi_1[j]) for the gated-GELU GEMM epilogue
                     g[name.replace("wi_0.weight", "wi_01")] = torch.stack([w0, w1], dim=1).reshape(-1, w0.shape[1]).contiguous()
+                elif name.endswith("SelfAttention.q.weight"):
+                    # one [3*H*64, d] projection: a single GEMM writes the [tokens, q|k|v] buffer the attention reads
+                    g[name.replace("q.weight", "qkv")] = torch.cat(
+                        [W[name], W[name.replace("q.weight", "k.weight")], W[name.replace("q.weight", "v.weight")]], 0)
+                elif name.endswith("EncDecAttention.k.weight"):
+                    g[name.replace("k.weight", "kv")] = torch.cat([W[name], W[name.replace("k.weight", "v.weight")]], 0)
             self._gated = {"key": self._half.key, "w": g}
         return W, self._gated["w"], dt
 
@@ -236,9 +242,7 @@ class FiD(nn.Module):
         for i in range(c.num_layers):
             p = f"encoder.block.{i}.layer.0."
             n = ops.layernorm(h, W[p + "layer_norm.weight"], None, c.layer_norm_epsilon, kind=1)
-            ops.linear(n, W[p + "SelfAttention.q.weight"], out=qkv[:, : H * 64])
-            ops.linear(n, W[p + "SelfAttention.k.weight"], out=qkv[:, H * 64: 2 * H * 64])
-            ops.linear(n, W[p + "SelfAttention.v.weight"], out=qkv[:, 2 * H * 64:])
+            ops.linear(n, G[p + "SelfAttention.qkv"], out=qkv)
             ctx = ops.attention(qkv, 0, qkv, H * 64, qkv, 2 * H * 64, S, H, L, L, add_mask=add_mask, bias_delta=bias,
                                 scale=1.0)
             h = ops.linear(ctx, W[p + "SelfAttention.o.weight"], None, residual=h, epilogue=ops.EPI_RESIDUAL)
@@ -252,17 +256,12 @@ class FiD(nn.Module):
         """K/V projections of the encoder output for every decoder layer ([B*n*L, 2*H*64] each), computed once
         per forward / per generation (the reference recomputes them every decoding step without use_cache)."""
         c = self.config
-        W, _, dt = self._weights()
-        H = c.num_heads
+        W, G, dt = self._weights()
         flat = enc.reshape(-1, c.d_model)
-        out = []
-        for i in range(c.num_decoder_layers):
-            p = f"decoder.block.{i}.layer.1.EncDecAttention."
-            kv = torch.empty((flat.shape[0], 2 * H * 64), dtype=dt, device=flat.device)
-            ops.linear(flat, W[p + "k.weight"], out=kv[:, : H * 64])
-            ops.linear(flat, W[p + "v.weight"], out=kv[:, H * 64:])
-            out.append(kv)
-        return out
+        if flat.dtype != dt:
+            flat = flat.to(dt)
+        return [ops.linear(flat, G[f"decoder.block.{i}.layer.1.EncDecAttention.kv"])
+                for i in range(c.num_decoder_layers)]
 
     @torch.no_grad()
     def decode(self, decoder_input_ids, enc, enc_mask, cross_kv=None):
@@ -287,9 +286,7 @@ class FiD(nn.Module):
         for i in range(c.num_decoder_layers):
             p = f"decoder.block.{i}.layer.0."
             n = ops.layernorm(h, W[p + "layer_norm.weight"], None, c.layer_norm_epsilon, kind=1)
-            ops.linear(n, W[p + "SelfAttention.q.weight"], out=qkv[:, : H * 64])
-            ops.linear(n, W[p + "SelfAttention.k.weight"], out=qkv[:, H * 64: 2 * H * 64])
-            ops.linear(n, W[p + "SelfAttention.v.weight"], out=qkv[:, 2 * H * 64:])
+            ops.linear(n, G[p + "SelfAttention.qkv"], out=qkv)
             ctx = ops.attention(qkv, 0, qkv, H * 64, qkv, 2 * H * 64, B, H, T, T, bias_delta=bias, scale=1.0,
                                 causal_value=-10000.0)
             h = ops.linear(ctx, W[p + "SelfAttention.o.weight"], None, residual=h, epilogue=ops.EPI_RESIDUAL)

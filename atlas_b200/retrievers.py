@@ -130,6 +130,7 @@ class Contriever(nn.Module):
         self.embeddings = _Embeddings(config)
         self.encoder = _Encoder(config)
         self._half = HalfCache()
+        self._fused = {}
         self.apply(self._init_weights)
 
     def _init_weights(self, m):  # HF BERT init (src/modeling_bert.py:~850), std 0.02
@@ -158,6 +159,14 @@ class Contriever(nn.Module):
         c = self.config
         dt = self._dtype()
         W = self._half.get(self, dt)
+        if self._fused.get("key") is not self._half.key:   # one [2304, 768] projection per layer: q | k | v
+            f = {}
+            for i in range(c.num_hidden_layers):
+                p = f"encoder.layer.{i}.attention.self."
+                f[p + "qkv.weight"] = torch.cat([W[p + "query.weight"], W[p + "key.weight"], W[p + "value.weight"]], 0)
+                f[p + "qkv.bias"] = torch.cat([W[p + "query.bias"], W[p + "key.bias"], W[p + "value.bias"]], 0)
+            self._fused = {"key": self._half.key, "w": f}
+        F = self._fused["w"]
         B, L = input_ids.shape
         H, nh = c.hidden_size, c.num_attention_heads
         h = ops.bert_embed_ln(input_ids, token_type_ids, W["embeddings.word_embeddings.weight"],
@@ -169,9 +178,7 @@ class Contriever(nn.Module):
         qkv = torch.empty((B * L, 3 * H), dtype=dt, device=h.device)
         for i in range(c.num_hidden_layers):
             p = f"encoder.layer.{i}."
-            ops.linear(h, W[p + "attention.self.query.weight"], W[p + "attention.self.query.bias"], out=qkv[:, 0:H])
-            ops.linear(h, W[p + "attention.self.key.weight"], W[p + "attention.self.key.bias"], out=qkv[:, H:2 * H])
-            ops.linear(h, W[p + "attention.self.value.weight"], W[p + "attention.self.value.bias"], out=qkv[:, 2 * H:])
+            ops.linear(h, F[p + "attention.self.qkv.weight"], F[p + "attention.self.qkv.bias"], out=qkv)
             ctx = ops.attention(qkv, 0, qkv, H, qkv, 2 * H, B, nh, L, L, add_mask=add_mask, scale=1.0 / math.sqrt(64))
             s1 = ops.linear(ctx, W[p + "attention.output.dense.weight"], W[p + "attention.output.dense.bias"], residual=h)
             h1 = ops.layernorm(s1, W[p + "attention.output.LayerNorm.weight"], W[p + "attention.output.LayerNorm.bias"],
