@@ -162,7 +162,6 @@ class FiD(nn.Module):
         self.encoder.config.n_context = 1
         self.encoder.config.bsz = 1
         self._half = HalfCache()
-        self._gated = {}
 
     # ---- reference surface that is configuration only -------------------------------------
     def set_checkpoint(self, use_checkpoint):
@@ -202,21 +201,24 @@ class FiD(nn.Module):
     def _weights(self):
         dt = self._dtype()
         W = self._half.get(self, dt)
-        if self._gated.get("key") is not self._half.key:
-            g = {}
-            for name in list(W.keys()):
-                if name.endswith("DenseReluDense.wi_0.weight"):
-                    w0, w1 = W[name], W[name.replace("wi_0", "wi_1")]
-                    # rows interleaved (wi_0[j], wi_1[j]) for the gated-GELU GEMM epilogue
-                    g[name.replace("wi_0.weight", "wi_01")] = torch.stack([w0, w1], dim=1).reshape(-1, w0.shape[1]).contiguous()
-                elif name.endswith("SelfAttention.q.weight"):
-                    # one [3*H*64, d] projection: a single GEMM writes the [tokens, q|k|v] buffer the attention reads
-                    g[name.replace("q.weight", "qkv")] = torch.cat(
-                        [W[name], W[name.replace("q.weight", "k.weight")], W[name.replace("q.weight", "v.weight")]], 0)
-                elif name.endswith("EncDecAttention.k.weight"):
-                    g[name.replace("k.weight", "kv")] = torch.cat([W[name], W[name.replace("k.weight", "v.weight")]], 0)
-            self._gated = {"key": self._half.key, "w": g}
-        return W, self._gated["w"], dt
+        return W, self._half.derived(dt, self._fuse), dt
+
+    @staticmethod
+    def _fuse(W):
+        """Weights derived once per parameter version: interleaved wi_0/wi_1, fused q|k|v and cross k|v."""
+        g = {}
+        for name in list(W.keys()):
+            if name.endswith("DenseReluDense.wi_0.weight"):
+                w0, w1 = W[name], W[name.replace("wi_0", "wi_1")]
+                # rows interleaved (wi_0[j], wi_1[j]) for the gated-GELU GEMM epilogue
+                g[name.replace("wi_0.weight", "wi_01")] = torch.stack([w0, w1], dim=1).reshape(-1, w0.shape[1]).contiguous()
+            elif name.endswith("SelfAttention.q.weight"):
+                # one [3*H*64, d] projection: a single GEMM writes the [tokens, q|k|v] buffer the attention reads
+                g[name.replace("q.weight", "qkv")] = torch.cat(
+                    [W[name], W[name.replace("q.weight", "k.weight")], W[name.replace("q.weight", "v.weight")]], 0)
+            elif name.endswith("EncDecAttention.k.weight"):
+                g[name.replace("k.weight", "kv")] = torch.cat([W[name], W[name.replace("k.weight", "v.weight")]], 0)
+        return g
 
     # ---- encoder ---------------------------------------------------------------------------
     def _ff(self, W, G, prefix, h, eps):

@@ -102,18 +102,28 @@ class _Encoder(nn.Module):
 
 
 class HalfCache:
-    """16-bit device copies of a module's parameters, rebuilt when any parameter changed (`_version`)."""
+    """16-bit device copies of a module's parameters, one set per compute dtype (the live query encoder may run
+    in bf16 while index refresh embeds passages in fp16, src/atlas.py:54-59), each rebuilt when any parameter
+    changed (`_version`).  `derived(dtype, build)` caches tensors computed from a set (fused QKV weights ...)."""
 
     def __init__(self):
-        self.key, self.store = None, {}
+        self.sets = {}
 
     def get(self, module, dtype):
         params = list(module.named_parameters())
         key = (dtype, tuple((p.data_ptr(), p._version) for _, p in params))
-        if key != self.key:
-            self.store = {n: (p.detach() if p.dtype == dtype else p.detach().to(dtype)).contiguous() for n, p in params}
-            self.key = key
-        return self.store
+        ent = self.sets.get(dtype)
+        if ent is None or ent["key"] != key:
+            store = {n: (p.detach() if p.dtype == dtype else p.detach().to(dtype)).contiguous() for n, p in params}
+            ent = {"key": key, "store": store, "derived": None}
+            self.sets[dtype] = ent
+        return ent["store"]
+
+    def derived(self, dtype, build):
+        ent = self.sets[dtype]
+        if ent["derived"] is None:
+            ent["derived"] = build(ent["store"])
+        return ent["derived"]
 
 
 class Contriever(nn.Module):
@@ -130,7 +140,6 @@ class Contriever(nn.Module):
         self.embeddings = _Embeddings(config)
         self.encoder = _Encoder(config)
         self._half = HalfCache()
-        self._fused = {}
         self.apply(self._init_weights)
 
     def _init_weights(self, m):  # HF BERT init (src/modeling_bert.py:~850), std 0.02
@@ -153,20 +162,23 @@ class Contriever(nn.Module):
         d = self.embeddings.word_embeddings.weight.dtype
         return d if d in (torch.float16, torch.bfloat16) else torch.float16
 
+    def _fuse(self, W):
+        """one [2304, 768] projection per layer: q | k | v"""
+        f = {}
+        for i in range(self.config.num_hidden_layers):
+            p = f"encoder.layer.{i}.attention.self."
+            f[p + "qkv.weight"] = torch.cat([W[p + "query.weight"], W[p + "key.weight"], W[p + "value.weight"]], 0)
+            f[p + "qkv.bias"] = torch.cat([W[p + "query.bias"], W[p + "key.bias"], W[p + "value.bias"]], 0)
+        return f
+
     @torch.no_grad()
-    def encode(self, input_ids, attention_mask, token_type_ids=None, out=None):
-        """last hidden state [B, L, H] in the 16-bit compute dtype (src/modeling_bert.py:929-1045)."""
+    def encode(self, input_ids, attention_mask, token_type_ids=None, dtype=None):
+        """last hidden state [B, L, H] in the 16-bit compute dtype (src/modeling_bert.py:929-1045).
+        `dtype` overrides the compute dtype (fp16 for passages whatever the live parameters are)."""
         c = self.config
-        dt = self._dtype()
+        dt = dtype or self._dtype()
         W = self._half.get(self, dt)
-        if self._fused.get("key") is not self._half.key:   # one [2304, 768] projection per layer: q | k | v
-            f = {}
-            for i in range(c.num_hidden_layers):
-                p = f"encoder.layer.{i}.attention.self."
-                f[p + "qkv.weight"] = torch.cat([W[p + "query.weight"], W[p + "key.weight"], W[p + "value.weight"]], 0)
-                f[p + "qkv.bias"] = torch.cat([W[p + "query.bias"], W[p + "key.bias"], W[p + "value.bias"]], 0)
-            self._fused = {"key": self._half.key, "w": f}
-        F = self._fused["w"]
+        F = self._half.derived(dt, self._fuse)
         B, L = input_ids.shape
         H, nh = c.hidden_size, c.num_attention_heads
         h = ops.bert_embed_ln(input_ids, token_type_ids, W["embeddings.word_embeddings.weight"],
@@ -213,10 +225,18 @@ class Contriever(nn.Module):
         return emb if emb.dtype == pd else emb.to(pd)
 
     @torch.no_grad()
-    def embed_into(self, input_ids, attention_mask, bank_rows):
+    def embed_fp16(self, input_ids, attention_mask):
+        """Passage embeddings computed with fp16 copies of the weights, whatever the live dtype is: what the
+        reference gets from `copy.deepcopy(retriever).half().eval()` (src/atlas.py:54-59)."""
+        if self.config.pooling != "average":
+            raise AtlasB200Error("embed_fp16: only average pooling is implemented")
+        return ops.masked_mean_pool(self.encode(input_ids, attention_mask, dtype=torch.float16), attention_mask)
+
+    @torch.no_grad()
+    def embed_into(self, input_ids, attention_mask, bank_rows, dtype=None):
         """Index refresh in place: pooled embeddings written straight into `bank_rows` ([B, 768] slice of
         the passage bank) - replaces `index.embeddings[:, a:b] = embeddings.T` (src/atlas.py:78-79)."""
-        last_hidden = self.encode(input_ids, attention_mask)
+        last_hidden = self.encode(input_ids, attention_mask, dtype=dtype)
         if last_hidden.dtype != bank_rows.dtype:
             raise AtlasB200Error("embed_into: the retriever copy must have the bank dtype (fp16, src/atlas.py:54-59)")
         ops.masked_mean_pool(last_hidden, attention_mask, out=bank_rows)

@@ -76,3 +76,30 @@ def test_ref_cpu_path_matches_golden():
     ids = np.array([[int(d["id"]) for d in row] for row in docs])
     for r in range(ids.shape[0]):
         assert mips_oracle.ids_match_tie_aware(g["ref_scores"][r], g["ref_ids"][r], ids[r])
+
+
+def test_atlas_golden_retrieval_is_the_oracle_topk():
+    """The Atlas-level golden (reference `Atlas.retrieve` on the reference `DistributedIndex`, oracle/make_golden_atlas.py)
+    pins the oracle once more: its returned scores are the canonical top-k of its own fp16 score matrix."""
+    g = np.load(os.path.join(GOLDEN_DIR, "atlas_tiny.npz"))
+    full = g["all_scores_fp16"].astype(np.float16)
+    vals, ids = mips_oracle.canonical_topk(full, g["ret_ids"].shape[1])
+    assert np.array_equal(vals.astype(np.float32), g["ret_scores"])
+    for r in range(ids.shape[0]):
+        uniq = np.array([np.sum(full[r] == v) == 1 for v in vals[r]])
+        assert np.array_equal(ids[r][uniq], g["ret_ids"][r][uniq])
+    # and the reference bank is the fp16 rounding of embeddings close to the fp32 retriever's
+    assert np.abs(g["bank_fp16"].astype(np.float32) - g["bank_fp32"]).max() < 1e-2
+
+
+def test_fake_tokenizer_surface():
+    import atlas_synth
+
+    rt, bt = atlas_synth.tokenizers()
+    enc = bt(["a b c", "d"], padding="longest", return_tensors="pt", max_length=8, truncation=True)
+    assert enc["input_ids"].shape == (2, 5) and enc["attention_mask"].sum().item() == 8
+    assert enc["input_ids"][0, 0].item() == bt.cls_token_id and enc["input_ids"][1, 2].item() == bt.sep_token_id
+    enc = rt(["x y </s>"], padding="max_length", max_length=6, truncation=True, return_tensors="pt", add_special_tokens=False)
+    assert enc["input_ids"].shape == (1, 6) and enc["input_ids"][0, 2].item() == rt.eos_token_id
+    assert rt(["p q r s t u v"], max_length=4, truncation=True, return_tensors="pt")["input_ids"][0, -1].item() == 1
+    assert len(rt.vocab) == atlas_synth.READER_VOCAB
