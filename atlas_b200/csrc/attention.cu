@@ -84,16 +84,49 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 
 __device__ __forceinline__ void sm_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-// scores of one 32-key chunk in the log2 domain: t = v*scale2 + (mask2[j] + bias2[j + boff])
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Pass 1 on one 32-key chunk, IN PLACE: r[jj] <- t = S*scale2 + (mask2[j] + bias2[j + boff]) (log2 domain); returns
+// the chunk maximum.  The key mask is the same for every row: read with 128-bit broadcast loads (8 per chunk); the
+// relative-position bias is one 4-byte load per element (lanes of a warp read 32 consecutive floats).
 template <bool kBias>
-__device__ __forceinline__ void chunk_scores(const uint32_t (&r)[32], float (&t)[32], float scale2, const float* mask2,
-                                             const float* bias2, int j0, int boff) {
+__device__ __forceinline__ float chunk_scores(uint32_t (&r)[32], float scale2, const float* mask2, const float* bias2,
+                                              int j0, int boff) {
+    float mx = -INFINITY;
+    const float4* m4 = reinterpret_cast<const float4*>(mask2 + j0);
 #pragma unroll
-    for (int jj = 0; jj < 32; ++jj) {
-        float add = mask2[j0 + jj];
-        if (kBias) add += bias2[j0 + jj + boff];
-        t[jj] = fmaf(__uint_as_float(r[jj]), scale2, add);
+    for (int q = 0; q < 8; ++q) {
+        const float4 m = m4[q];
+        const float add[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int jj = 4 * q + e;
+            float a = add[e];
+            if (kBias) a += bias2[j0 + jj + boff];
+            const float t = fmaf(__uint_as_float(r[jj]), scale2, a);
+            r[jj] = __float_as_uint(t);
+            mx = fmaxf(mx, t);
+        }
     }
+    return mx;
+}
+
+// Pass 2 on one chunk: p = 2^(t - max), returns the partial row sum, packs P to 16 bits.
+template <bool kBF16>
+__device__ __forceinline__ float chunk_probs(const uint32_t (&r)[32], uint32_t (&pk)[16], float mx) {
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < 32; jj += 2) {
+        const float e0 = ex2_approx(__uint_as_float(r[jj]) - mx), e1 = ex2_approx(__uint_as_float(r[jj + 1]) - mx);
+        s0 += e0;
+        s1 += e1;
+        pk[jj >> 1] = pack2<kBF16>(e0, e1);
+    }
+    return s0 + s1;
 }
 
 template <bool kBF16>
@@ -104,7 +137,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     __shared__ __align__(8) uint64_t k_full, k_empty, v_full, v_empty, q_full[2], q_empty[2], s_full, p_ready, o_full, s_free;
     __shared__ uint32_t tmem_base_smem;
     __shared__ float s_bias[2 * MAX_LK];  // (bias by (j - i) + (Lq - 1) [+ causal]) * log2e, this head
-    __shared__ float s_mask[MAX_LK];      // additive key mask * log2e (-inf beyond Lk), this segment
+    __shared__ __align__(16) float s_mask[MAX_LK];      // additive key mask * log2e (-inf beyond Lk), this segment
     __shared__ float s_red[2][BLOCK_Q];   // per-row partial max of the two key halves
     __shared__ float s_sum[2][BLOCK_Q];   // per-row partial sums
 
@@ -250,52 +283,50 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 const int boffc = max(boff, 0);
                 ab::mbar_wait(&s_full, qt_it & 1, 27);
                 ab::tc_fence_after();
-                // ---- pass 1: partial row max over this thread's chunks (loads software-pipelined) ----
+                // ---- pass 1: t = scaled score + mask + bias written back over S; partial row max (loads pipelined) ----
                 float mx = -INFINITY;
                 {
                     uint32_t ra[32], rb[32];
-                    float t[32];
                     int c = static_cast<int>(half);
                     ab::tmem_ld32(lane_addr + c * 32, ra);
                     while (c < n32) {
                         ab::tmem_ld_wait();
                         if (c + 2 < n32) ab::tmem_ld32(lane_addr + (c + 2) * 32, rb);
-                        if (has_bias) chunk_scores<true>(ra, t, scale2, s_mask, s_bias, c * 32, boffc);
-                        else chunk_scores<false>(ra, t, scale2, s_mask, s_bias, c * 32, boffc);
-#pragma unroll
-                        for (int jj = 0; jj < 32; ++jj) mx = fmaxf(mx, t[jj]);
+                        mx = fmaxf(mx, has_bias ? chunk_scores<true>(ra, scale2, s_mask, s_bias, c * 32, boffc)
+                                                : chunk_scores<false>(ra, scale2, s_mask, s_bias, c * 32, boffc));
+                        ab::tmem_st32(lane_addr + c * 32, ra);
                         c += 2;
                         if (c >= n32) break;
                         ab::tmem_ld_wait();
                         if (c + 2 < n32) ab::tmem_ld32(lane_addr + (c + 2) * 32, ra);
-                        if (has_bias) chunk_scores<true>(rb, t, scale2, s_mask, s_bias, c * 32, boffc);
-                        else chunk_scores<false>(rb, t, scale2, s_mask, s_bias, c * 32, boffc);
-#pragma unroll
-                        for (int jj = 0; jj < 32; ++jj) mx = fmaxf(mx, t[jj]);
+                        mx = fmaxf(mx, has_bias ? chunk_scores<true>(rb, scale2, s_mask, s_bias, c * 32, boffc)
+                                                : chunk_scores<false>(rb, scale2, s_mask, s_bias, c * 32, boffc));
+                        ab::tmem_st32(lane_addr + c * 32, rb);
                         c += 2;
                     }
                 }
                 s_red[half][row] = mx;
+                ab::tmem_st_wait();   // this thread re-reads its own t columns in pass 2
                 sm_bar();
                 mx = fmaxf(s_red[0][row], s_red[1][row]);
                 // ---- pass 2: p = 2^(t - max), partial row sum, P (16-bit) written over the S columns it replaces ----
                 float sum = 0.f;
                 {
-                    uint32_t ra[32];
-                    float t[32];
-                    for (int c = static_cast<int>(half); c < n32; c += 2) {
-                        ab::tmem_ld32(lane_addr + c * 32, ra);
+                    uint32_t ra[32], rb[32], pk[16];
+                    int c = static_cast<int>(half);
+                    ab::tmem_ld32(lane_addr + c * 32, ra);
+                    while (c < n32) {
                         ab::tmem_ld_wait();
-                        if (has_bias) chunk_scores<true>(ra, t, scale2, s_mask, s_bias, c * 32, boffc);
-                        else chunk_scores<false>(ra, t, scale2, s_mask, s_bias, c * 32, boffc);
-                        uint32_t pk[16];
-#pragma unroll
-                        for (int jj = 0; jj < 32; jj += 2) {
-                            const float e0 = exp2f(t[jj] - mx), e1 = exp2f(t[jj + 1] - mx);
-                            sum += e0 + e1;
-                            pk[jj >> 1] = pack2<kBF16>(e0, e1);
-                        }
+                        if (c + 2 < n32) ab::tmem_ld32(lane_addr + (c + 2) * 32, rb);
+                        sum += chunk_probs<kBF16>(ra, pk, mx);
                         tmem_st16(lane_addr + c * 16, pk);
+                        c += 2;
+                        if (c >= n32) break;
+                        ab::tmem_ld_wait();
+                        if (c + 2 < n32) ab::tmem_ld32(lane_addr + (c + 2) * 32, ra);
+                        sum += chunk_probs<kBF16>(rb, pk, mx);
+                        tmem_st16(lane_addr + c * 16, pk);
+                        c += 2;
                     }
                 }
                 s_sum[half][row] = sum;
