@@ -15,8 +15,9 @@
 // exp / sum) with no online rescaling.  One CTA works on one (segment, head) at a time: K and V are loaded once
 // and reused by all of its 128-row query tiles.
 //
-// Roles (256 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator,
-// warps 4-7 softmax + output (thread <-> query row = TMEM lane).
+// Roles (384 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-3 TMEM allocator + per-item mask / bias
+// tables (double buffered, one item ahead), warps 4-11 softmax + output (two threads per query row = TMEM lane).
+// With <= 384 keys the output of query tile t-1 is written while the tensor pipe runs P.V(t) and S(t+1).
 #include "common.cuh"
 #include "host_common.h"
 
@@ -29,6 +30,7 @@ constexpr int BLOCK_Q = 128;
 constexpr int MAX_LK = 512;
 constexpr int THREADS = 384;
 constexpr int SM_THREADS = 256;                 // softmax / output threads (warps 4..11), 2 per query row
+constexpr int AUX_THREADS = 64;                 // warps 2, 3: per-item mask / bias tables, one item ahead
 constexpr int Q_BYTES = BLOCK_Q * D * 2;        // 16 KB, double buffered
 constexpr int KV_BYTES = MAX_LK * D * 2;        // 64 KB each
 constexpr int SMEM_BYTES = 2 * Q_BYTES + 2 * KV_BYTES + 1024;
@@ -74,15 +76,12 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
 
 template <bool kBF16>
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
-    if constexpr (kBF16) {
-        return static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16_rn(a))) |
-               (static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16_rn(b))) << 16);
-    }
-    return static_cast<uint32_t>(__half_as_ushort(__float2half_rn(a))) |
-           (static_cast<uint32_t>(__half_as_ushort(__float2half_rn(b))) << 16);
+    return ab::pack2_rn<kBF16>(a, b);
 }
 
 __device__ __forceinline__ void sm_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// the two warps that share query rows 32*lg .. 32*lg+31 (key halves 0 and 1)
+__device__ __forceinline__ void pair_bar(uint32_t lg) { asm volatile("bar.sync %0, 64;" ::"r"(2u + lg) : "memory"); }
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -135,9 +134,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                  const __grid_constant__ CUtensorMap tmap_v, const Params p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t k_full, k_empty, v_full, v_empty, q_full[2], q_empty[2], s_full, p_ready, o_full, s_free;
+    __shared__ __align__(8) uint64_t aux_full[2], aux_empty[2];
     __shared__ uint32_t tmem_base_smem;
-    __shared__ float s_bias[2 * MAX_LK];  // (bias by (j - i) + (Lq - 1) [+ causal]) * log2e, this head
-    __shared__ __align__(16) float s_mask[MAX_LK];      // additive key mask * log2e (-inf beyond Lk), this segment
+    // per-(segment, head) tables, double buffered: filled by the two auxiliary warps one item ahead of the softmax warps
+    __shared__ float s_bias[2][2 * MAX_LK];               // (bias by (j - i) + (Lq - 1) [+ causal]) * log2e
+    __shared__ __align__(16) float s_mask[2][MAX_LK];     // additive key mask * log2e (-inf beyond Lk)
     __shared__ float s_red[2][BLOCK_Q];   // per-row partial max of the two key halves
     __shared__ float s_sum[2][BLOCK_Q];   // per-row partial sums
 
@@ -154,7 +155,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const int lk_pad = n_chunks * 128;
     const int n_qt = (p.Lq + BLOCK_Q - 1) / BLOCK_Q;
     const int n_items = p.B * p.H;
-    const uint32_t o_col = static_cast<uint32_t>(lk_pad / 2);  // O accumulator: right after the packed P columns
+    // TMEM columns: S (fp32, one column per key) at [0, lk_pad); P (16-bit) overwrites [0, lk_pad/2).
+    //   lk_pad <= 384 ("pipelined"): two O accumulators at 384 and 448, outside the S columns.  The S = Q.K^T of the
+    //       next query tile is issued as soon as this tile's P.V has retired, and the softmax warps write tile t-1's
+    //       output while the tensor pipe runs P.V(t) and S(t+1).
+    //   lk_pad == 512: one O accumulator at lk_pad/2 (inside the S columns, free once P is packed); the next S waits
+    //       until the softmax warps have read O (s_free).
+    const bool pipelined = lk_pad <= 384;
+    auto o_col_of = [&](int qt_it) -> uint32_t {
+        return pipelined ? static_cast<uint32_t>(384 + 64 * (qt_it & 1)) : static_cast<uint32_t>(lk_pad / 2);
+    };
 
     if (warp == 0 && lane == 0) {
         ab::tma_prefetch_desc(&tmap_q);
@@ -169,6 +179,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         for (int i = 0; i < 2; ++i) {
             ab::mbar_init(&q_full[i], 1);
             ab::mbar_init(&q_empty[i], 1);
+            ab::mbar_init(&aux_full[i], AUX_THREADS);
+            ab::mbar_init(&aux_empty[i], SM_THREADS);
         }
         ab::mbar_init(&s_full, 1);
         ab::mbar_init(&p_ready, SM_THREADS);
@@ -225,7 +237,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 for (int qt = 0; qt < n_qt; ++qt, ++qt_it) {
                     const int qb = qt_it & 1;
                     ab::mbar_wait(&q_full[qb], (qt_it >> 1) & 1, 24);
-                    ab::mbar_wait(&s_free, (qt_it & 1) ^ 1u, 25);
+                    if (pipelined) {
+                        // S(t) overwrites the columns P(t-1) occupies: wait until P.V(t-1) has retired
+                        if (qt_it > 0) ab::mbar_wait(&o_full, (qt_it - 1) & 1, 31);
+                    } else {
+                        ab::mbar_wait(&s_free, (qt_it & 1) ^ 1u, 25);
+                    }
                     ab::tc_fence_after();
                     const uint64_t qdesc = ab::umma_desc_k_sw128(aQ + qb * Q_BYTES);
                     for (int c = 0; c < n_chunks; ++c) {
@@ -242,41 +259,92 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     ab::mbar_wait(&p_ready, qt_it & 1, 26);
                     ab::tc_fence_after();
                     const uint64_t vdesc = umma_desc_mn_sw128(aV);
+                    const uint32_t o_tmem = tmem_base + o_col_of(qt_it);
                     for (int k = 0; k < lk_pad / 16; ++k)
-                        ab::umma_ts<1>(tmem_base + o_col, tmem_base + k * 8, vdesc + static_cast<uint64_t>((k * 2048) >> 4),
-                                       idesc_o, k != 0 ? 1u : 0u);
+                        ab::umma_ts<1>(o_tmem, tmem_base + k * 8, vdesc + static_cast<uint64_t>((k * 2048) >> 4), idesc_o,
+                                       k != 0 ? 1u : 0u);
                     if (qt == n_qt - 1) ab::umma_commit(&v_empty);  // last use of this (segment, head)'s V
                     ab::umma_commit(&o_full);
                 }
             }
         }
-    } else if (warp >= 4) {
-        // ===================== softmax + output: two threads per query row =====================
-        const uint32_t lg = warp & 3u;
-        const uint32_t half = (warp - 4u) >> 2;                    // key chunks half, half+2, ... ; O columns 32*half..
-        const int row = static_cast<int>(lg * 32 + lane);
-        const uint32_t lane_addr = tmem_base + ((lg * 32u) << 16);
-        const int tid = static_cast<int>(threadIdx.x) - 128;
-        const float scale2 = p.scale * LOG2E;
+    } else if (warp < 4) {
+        // ===================== auxiliary warps 2, 3: mask / bias tables of the NEXT item =====================
+        const int tid = static_cast<int>(threadIdx.x) - 64;
         const bool has_bias = (p.bias_delta != nullptr) || (p.causal_value != 0.f);
-        const int n32 = lk_pad / 32;
-        int qt_it = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int item_it = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_it) {
             const int b = item / p.H, h = item % p.H;
-            sm_bar();  // the previous item's softmax passes are over for all 256 threads
-            for (int j = tid; j < lk_pad; j += SM_THREADS)
-                s_mask[j] = (j < p.Lk) ? (p.add_mask ? p.add_mask[static_cast<size_t>(b) * p.Lk + j] * LOG2E : 0.f)
-                                       : -INFINITY;
+            const int buf = item_it & 1;
+            ab::mbar_wait(&aux_empty[buf], ((item_it >> 1) & 1) ^ 1u, 32);
+            for (int j = tid; j < lk_pad; j += AUX_THREADS)
+                s_mask[buf][j] = (j < p.Lk) ? (p.add_mask ? p.add_mask[static_cast<size_t>(b) * p.Lk + j] * LOG2E : 0.f)
+                                            : -INFINITY;
             if (has_bias)
-                for (int d = tid; d < 2 * MAX_LK; d += SM_THREADS) {   // entries past the valid offsets stay finite (0)
+                for (int d = tid; d < 2 * MAX_LK; d += AUX_THREADS) {   // entries past the valid offsets stay finite (0)
                     float v = 0.f;
                     if (d < p.Lq + p.Lk - 1) {
                         v = p.bias_delta ? p.bias_delta[static_cast<size_t>(h) * (p.Lq + p.Lk - 1) + d] : 0.f;
                         if (p.causal_value != 0.f && d > p.Lq - 1) v += p.causal_value;   // j > i
                     }
-                    s_bias[d] = v * LOG2E;
+                    s_bias[buf][d] = v * LOG2E;
                 }
-            sm_bar();
+            ab::mbar_arrive(&aux_full[buf]);
+        }
+    } else {
+        // ===================== softmax + output: two threads per query row =====================
+        const uint32_t lg = warp & 3u;
+        const uint32_t half = (warp - 4u) >> 2;                    // key chunks half, half+2, ... ; O columns 32*half..
+        const int row = static_cast<int>(lg * 32 + lane);
+        const uint32_t lane_addr = tmem_base + ((lg * 32u) << 16);
+        const float scale2 = p.scale * LOG2E;
+        const bool has_bias = (p.bias_delta != nullptr) || (p.causal_value != 0.f);
+        const int n32 = lk_pad / 32;
+
+        // one finished tile's output: O (fp32, TMEM) -> normalised 16-bit rows, or split-KV partials
+        auto emit = [&](int b, int h, int i, float mx, float sum, uint32_t ocol) {
+            uint32_t ro[32];
+            ab::tmem_ld32(lane_addr + ocol + half * 32, ro);
+            ab::tmem_ld_wait();
+            if (i >= p.Lq) return;
+            if (p.o_partial != nullptr) {
+                // split-KV: un-normalised partial output in fp32 + (max, sum) of this split (natural log units)
+                float* dst = p.o_partial + (static_cast<size_t>(b) * p.Lq + i) * (static_cast<size_t>(p.H) * D) + h * D +
+                             half * 32;
+#pragma unroll
+                for (int v4 = 0; v4 < 8; ++v4)
+                    reinterpret_cast<float4*>(dst)[v4] =
+                        make_float4(__uint_as_float(ro[4 * v4]), __uint_as_float(ro[4 * v4 + 1]),
+                                    __uint_as_float(ro[4 * v4 + 2]), __uint_as_float(ro[4 * v4 + 3]));
+                if (half == 0) {
+                    float* ml = p.ml_partial + ((static_cast<size_t>(b) * p.Lq + i) * p.H + h) * 2;
+                    ml[0] = mx * (1.0f / LOG2E);
+                    ml[1] = sum;
+                }
+            } else {
+                const float inv = 1.0f / sum;
+                uint4* dst = reinterpret_cast<uint4*>(p.O + (static_cast<size_t>(b) * p.Lq + i) * p.ldo + h * D + half * 32);
+#pragma unroll
+                for (int v4 = 0; v4 < 4; ++v4)
+                    dst[v4] = make_uint4(
+                        pack2<kBF16>(__uint_as_float(ro[8 * v4]) * inv, __uint_as_float(ro[8 * v4 + 1]) * inv),
+                        pack2<kBF16>(__uint_as_float(ro[8 * v4 + 2]) * inv, __uint_as_float(ro[8 * v4 + 3]) * inv),
+                        pack2<kBF16>(__uint_as_float(ro[8 * v4 + 4]) * inv, __uint_as_float(ro[8 * v4 + 5]) * inv),
+                        pack2<kBF16>(__uint_as_float(ro[8 * v4 + 6]) * inv, __uint_as_float(ro[8 * v4 + 7]) * inv));
+            }
+        };
+
+        int qt_it = 0, item_it = 0;
+        // pipelined mode: the previous tile, whose output is written while the tensor pipe works on this one
+        bool pend = false;
+        int pend_b = 0, pend_h = 0, pend_i = 0, pend_it = 0;
+        float pend_mx = 0.f, pend_sum = 1.f;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_it) {
+            const int b = item / p.H, h = item % p.H;
+            const int buf = item_it & 1;
+            ab::mbar_wait(&aux_full[buf], (item_it >> 1) & 1, 33);
+            const float* mask2 = s_mask[buf];
+            const float* bias2 = s_bias[buf];
             for (int qt = 0; qt < n_qt; ++qt, ++qt_it) {
                 const int i = qt * BLOCK_Q + row;                   // query position inside the segment
                 const int boff = min(p.Lq - 1 - i, 2 * MAX_LK - 1 - lk_pad);  // bias index = j + boff (clamped for pad rows)
@@ -292,19 +360,20 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     while (c < n32) {
                         ab::tmem_ld_wait();
                         if (c + 2 < n32) ab::tmem_ld32(lane_addr + (c + 2) * 32, rb);
-                        mx = fmaxf(mx, has_bias ? chunk_scores<true>(ra, scale2, s_mask, s_bias, c * 32, boffc)
-                                                : chunk_scores<false>(ra, scale2, s_mask, s_bias, c * 32, boffc));
+                        mx = fmaxf(mx, has_bias ? chunk_scores<true>(ra, scale2, mask2, bias2, c * 32, boffc)
+                                                : chunk_scores<false>(ra, scale2, mask2, bias2, c * 32, boffc));
                         ab::tmem_st32(lane_addr + c * 32, ra);
                         c += 2;
                         if (c >= n32) break;
                         ab::tmem_ld_wait();
                         if (c + 2 < n32) ab::tmem_ld32(lane_addr + (c + 2) * 32, ra);
-                        mx = fmaxf(mx, has_bias ? chunk_scores<true>(rb, scale2, s_mask, s_bias, c * 32, boffc)
-                                                : chunk_scores<false>(rb, scale2, s_mask, s_bias, c * 32, boffc));
+                        mx = fmaxf(mx, has_bias ? chunk_scores<true>(rb, scale2, mask2, bias2, c * 32, boffc)
+                                                : chunk_scores<false>(rb, scale2, mask2, bias2, c * 32, boffc));
                         ab::tmem_st32(lane_addr + c * 32, rb);
                         c += 2;
                     }
                 }
+                if (qt == n_qt - 1) ab::mbar_arrive(&aux_empty[buf]);   // last read of this item's tables
                 s_red[half][row] = mx;
                 ab::tmem_st_wait();   // this thread re-reads its own t columns in pass 2
                 sm_bar();
@@ -312,21 +381,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 // ---- pass 2: p = 2^(t - max), partial row sum, P (16-bit) written over the S columns it replaces ----
                 float sum = 0.f;
                 {
-                    uint32_t ra[32], rb[32], pk[16];
-                    int c = static_cast<int>(half);
-                    ab::tmem_ld32(lane_addr + c * 32, ra);
-                    while (c < n32) {
+                    uint32_t ra[32], pk[16];
+                    for (int c = static_cast<int>(half); c < n32; c += 2) {
+                        ab::tmem_ld32(lane_addr + c * 32, ra);
                         ab::tmem_ld_wait();
-                        if (c + 2 < n32) ab::tmem_ld32(lane_addr + (c + 2) * 32, rb);
+                        // P of chunks 2k, 2k+1 lands on the columns of S chunk k: both threads of a row must have
+                        // loaded their chunk of this iteration (hence every chunk <= 2k+1) before either stores P
+                        pair_bar(lg);
                         sum += chunk_probs<kBF16>(ra, pk, mx);
                         tmem_st16(lane_addr + c * 16, pk);
-                        c += 2;
-                        if (c >= n32) break;
-                        ab::tmem_ld_wait();
-                        if (c + 2 < n32) ab::tmem_ld32(lane_addr + (c + 2) * 32, ra);
-                        sum += chunk_probs<kBF16>(rb, pk, mx);
-                        tmem_st16(lane_addr + c * 16, pk);
-                        c += 2;
                     }
                 }
                 s_sum[half][row] = sum;
@@ -335,43 +398,25 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 sm_bar();  // both halves' sums are in smem; all P columns of this warp pair are written
                 ab::mbar_arrive(&p_ready);
                 sum = s_sum[0][row] + s_sum[1][row];
-                // ---- output: this thread's 32 of the 64 O columns ----
-                ab::mbar_wait(&o_full, qt_it & 1, 28);
-                ab::tc_fence_after();
-                uint32_t ro[32];
-                ab::tmem_ld32(lane_addr + o_col + half * 32, ro);
-                ab::tmem_ld_wait();
-                ab::tc_fence_before();
-                ab::mbar_arrive(&s_free);  // S / P / O columns may be overwritten by the next query tile
-                if (i < p.Lq) {
-                    if (p.o_partial != nullptr) {
-                        // split-KV: un-normalised partial output in fp32 + (max, sum) of this split (natural log units)
-                        float* dst = p.o_partial + (static_cast<size_t>(b) * p.Lq + i) * (static_cast<size_t>(p.H) * D) +
-                                     h * D + half * 32;
-#pragma unroll
-                        for (int v4 = 0; v4 < 8; ++v4)
-                            reinterpret_cast<float4*>(dst)[v4] =
-                                make_float4(__uint_as_float(ro[4 * v4]), __uint_as_float(ro[4 * v4 + 1]),
-                                            __uint_as_float(ro[4 * v4 + 2]), __uint_as_float(ro[4 * v4 + 3]));
-                        if (half == 0) {
-                            float* ml = p.ml_partial + ((static_cast<size_t>(b) * p.Lq + i) * p.H + h) * 2;
-                            ml[0] = mx * (1.0f / LOG2E);
-                            ml[1] = sum;
-                        }
-                    } else {
-                        const float inv = 1.0f / sum;
-                        uint4* dst = reinterpret_cast<uint4*>(p.O + (static_cast<size_t>(b) * p.Lq + i) * p.ldo + h * D +
-                                                              half * 32);
-#pragma unroll
-                        for (int v4 = 0; v4 < 4; ++v4)
-                            dst[v4] = make_uint4(
-                                pack2<kBF16>(__uint_as_float(ro[8 * v4]) * inv, __uint_as_float(ro[8 * v4 + 1]) * inv),
-                                pack2<kBF16>(__uint_as_float(ro[8 * v4 + 2]) * inv, __uint_as_float(ro[8 * v4 + 3]) * inv),
-                                pack2<kBF16>(__uint_as_float(ro[8 * v4 + 4]) * inv, __uint_as_float(ro[8 * v4 + 5]) * inv),
-                                pack2<kBF16>(__uint_as_float(ro[8 * v4 + 6]) * inv, __uint_as_float(ro[8 * v4 + 7]) * inv));
-                    }
+                if (pipelined) {
+                    // P.V(t-1) retired before S(t) was issued (MMA warp), and S(t) was observed above: O(t-1) is final
+                    if (pend) emit(pend_b, pend_h, pend_i, pend_mx, pend_sum, o_col_of(pend_it));
+                    ab::tc_fence_before();
+                    pend = true;
+                    pend_b = b, pend_h = h, pend_i = i, pend_it = qt_it, pend_mx = mx, pend_sum = sum;
+                } else {
+                    ab::mbar_wait(&o_full, qt_it & 1, 28);
+                    ab::tc_fence_after();
+                    emit(b, h, i, mx, sum, o_col_of(qt_it));
+                    ab::tc_fence_before();
+                    ab::mbar_arrive(&s_free);  // S / P / O columns may be overwritten by the next query tile
                 }
             }
+        }
+        if (pend) {
+            ab::mbar_wait(&o_full, pend_it & 1, 34);
+            ab::tc_fence_after();
+            emit(pend_b, pend_h, pend_i, pend_mx, pend_sum, o_col_of(pend_it));
         }
     }
 

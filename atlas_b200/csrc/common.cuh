@@ -34,6 +34,19 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// Two fp32 -> packed 16-bit (lo = a, hi = b), round-to-nearest-even.  One F2FP instruction on the ALU pipe; the
+// scalar __float2bfloat16_rn / __float2half_rn compile to F2F on the (16 lanes/clk) XU pipe that MUFU.EX2 also needs.
+template <bool kBF16>
+__device__ __forceinline__ uint32_t pack2_rn(float a, float b) {
+    uint32_t d;
+    if constexpr (kBF16) {
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+    } else {
+        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+    }
+    return d;
+}
+
 // ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------

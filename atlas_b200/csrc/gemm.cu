@@ -62,12 +62,7 @@ __device__ __forceinline__ float to_f32(uint16_t h) {
 }
 template <bool kBF16>
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
-    if constexpr (kBF16) {
-        return static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16_rn(a))) |
-               (static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16_rn(b))) << 16);
-    }
-    return static_cast<uint32_t>(__half_as_ushort(__float2half_rn(a))) |
-           (static_cast<uint32_t>(__half_as_ushort(__float2half_rn(b))) << 16);
+    return ab::pack2_rn<kBF16>(a, b);
 }
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }

@@ -1,0 +1,35 @@
+"""Single-op drivers for ncu captures: python tools/prof_ops.py attention|gemm|contriever|fid [reps]."""
+import os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from atlas_b200 import ops
+dev = torch.device("cuda:0")
+torch.manual_seed(0)
+what = sys.argv[1] if len(sys.argv) > 1 else "attention"
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+
+def timed(fn, n=10, warm=3):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+if what == "attention":
+    S, H, L = 160, 12, 384      # FiD-base encoder, 4 queries x 40 passages
+    qkv = torch.randn(S * L, 3 * H * 64, device=dev).bfloat16() * 0.2
+    bias = torch.randn(H, 2 * L - 1, device=dev)
+    am = torch.zeros(S, L, device=dev)
+    fn = lambda: ops.attention(qkv, 0, qkv, H * 64, qkv, 2 * H * 64, S, H, L, L, add_mask=am, bias_delta=bias)
+    ms = timed(fn, reps)
+    print(f"attention S={S} H={H} L={L}: {ms:.3f} ms = {4 * S * H * L * L * 64 / ms / 1e9:.0f} TFLOP/s")
+elif what == "gemm":
+    M, N, K = 61440, 4096, 768  # FiD-base wi_0|wi_1 gated projection, 4 queries
+    x = torch.randn(M, K, device=dev).bfloat16() * 0.1
+    w = torch.randn(N, K, device=dev).bfloat16() * 0.03
+    fn = lambda: ops.linear(x, w, epilogue=ops.EPI_GATED)
+    ms = timed(fn, reps)
+    print(f"gemm M={M} N={N} K={K} gated: {ms:.3f} ms = {2 * M * N * K / ms / 1e9:.0f} TFLOP/s")
