@@ -86,6 +86,8 @@ def lib():
     L.atlas_b200_mips_set_debug_counters.argtypes = [c.c_void_p]
     L.atlas_b200_profile_enable.restype = None
     L.atlas_b200_profile_enable.argtypes = [c.c_int32]
+    L.atlas_b200_profile_work.restype = c.c_double
+    L.atlas_b200_profile_work.argtypes = []
     L.atlas_b200_profile_collect.restype = c.c_int
     L.atlas_b200_profile_collect.argtypes = [c.POINTER(c.c_double), c.POINTER(c.c_int32)]
     _lib = L
@@ -111,6 +113,7 @@ EXPORTED_SYMBOLS = [
     "atlas_b200_mips_set_kernel",
     "atlas_b200_mips_set_debug_counters",
     "atlas_b200_profile_enable",
+    "atlas_b200_profile_work",
     "atlas_b200_profile_collect",
 ]
 

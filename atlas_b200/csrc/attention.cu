@@ -28,8 +28,9 @@ namespace attn {
 constexpr int D = 64;            // head dim
 constexpr int BLOCK_Q = 128;
 constexpr int MAX_LK = 512;
-constexpr int THREADS = 384;
-constexpr int SM_THREADS = 256;                 // softmax / output threads (warps 4..11), 2 per query row
+constexpr int SPLIT = 4;                       // softmax threads per query row (key chunks part, part+SPLIT, ...)
+constexpr int SM_THREADS = 128 * SPLIT;         // softmax / output threads (warps 4..), 4 warps per SM sub-partition
+constexpr int THREADS = 128 + SM_THREADS;
 constexpr int AUX_THREADS = 64;                 // warps 2, 3: per-item mask / bias tables, one item ahead
 constexpr int Q_BYTES = BLOCK_Q * D * 2;        // 16 KB, double buffered
 constexpr int KV_BYTES = MAX_LK * D * 2;        // 64 KB each
@@ -52,6 +53,15 @@ struct Params {
     float* o_partial;         // [B*Lq, H*64] fp32 or nullptr
     float* ml_partial;        // [B*Lq, H, 2] fp32
 };
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
     asm volatile(
@@ -79,9 +89,9 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     return ab::pack2_rn<kBF16>(a, b);
 }
 
-__device__ __forceinline__ void sm_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-// the two warps that share query rows 32*lg .. 32*lg+31 (key halves 0 and 1)
-__device__ __forceinline__ void pair_bar(uint32_t lg) { asm volatile("bar.sync %0, 64;" ::"r"(2u + lg) : "memory"); }
+__device__ __forceinline__ void sm_bar() { asm volatile("bar.sync 1, %0;" ::"n"(SM_THREADS) : "memory"); }
+// the SPLIT warps that share query rows 32*lg .. 32*lg+31
+__device__ __forceinline__ void pair_bar(uint32_t lg) { asm volatile("bar.sync %0, %1;" ::"r"(2u + lg), "n"(32 * SPLIT) : "memory"); }
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -139,8 +149,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     // per-(segment, head) tables, double buffered: filled by the two auxiliary warps one item ahead of the softmax warps
     __shared__ float s_bias[2][2 * MAX_LK];               // (bias by (j - i) + (Lq - 1) [+ causal]) * log2e
     __shared__ __align__(16) float s_mask[2][MAX_LK];     // additive key mask * log2e (-inf beyond Lk)
-    __shared__ float s_red[2][BLOCK_Q];   // per-row partial max of the two key halves
-    __shared__ float s_sum[2][BLOCK_Q];   // per-row partial sums
+    __shared__ float s_red[SPLIT][BLOCK_Q];   // per-row partial max of the SPLIT key parts
+    __shared__ float s_sum[SPLIT][BLOCK_Q];   // per-row partial sums
 
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t lane = threadIdx.x & 31u;
@@ -292,40 +302,41 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             ab::mbar_arrive(&aux_full[buf]);
         }
     } else {
-        // ===================== softmax + output: two threads per query row =====================
+        // ===================== softmax + output: SPLIT threads per query row =====================
         const uint32_t lg = warp & 3u;
-        const uint32_t half = (warp - 4u) >> 2;                    // key chunks half, half+2, ... ; O columns 32*half..
+        const uint32_t part = (warp - 4u) >> 2;                    // key chunks part, part+SPLIT, ...; O columns 16*part..
         const int row = static_cast<int>(lg * 32 + lane);
         const uint32_t lane_addr = tmem_base + ((lg * 32u) << 16);
         const float scale2 = p.scale * LOG2E;
         const bool has_bias = (p.bias_delta != nullptr) || (p.causal_value != 0.f);
         const int n32 = lk_pad / 32;
+        constexpr int OC = D / SPLIT;                               // O columns per thread
 
         // one finished tile's output: O (fp32, TMEM) -> normalised 16-bit rows, or split-KV partials
         auto emit = [&](int b, int h, int i, float mx, float sum, uint32_t ocol) {
-            uint32_t ro[32];
-            ab::tmem_ld32(lane_addr + ocol + half * 32, ro);
+            uint32_t ro[OC];
+            tmem_ld16(lane_addr + ocol + part * OC, ro);
             ab::tmem_ld_wait();
             if (i >= p.Lq) return;
             if (p.o_partial != nullptr) {
                 // split-KV: un-normalised partial output in fp32 + (max, sum) of this split (natural log units)
                 float* dst = p.o_partial + (static_cast<size_t>(b) * p.Lq + i) * (static_cast<size_t>(p.H) * D) + h * D +
-                             half * 32;
+                             part * OC;
 #pragma unroll
-                for (int v4 = 0; v4 < 8; ++v4)
+                for (int v4 = 0; v4 < OC / 4; ++v4)
                     reinterpret_cast<float4*>(dst)[v4] =
                         make_float4(__uint_as_float(ro[4 * v4]), __uint_as_float(ro[4 * v4 + 1]),
                                     __uint_as_float(ro[4 * v4 + 2]), __uint_as_float(ro[4 * v4 + 3]));
-                if (half == 0) {
+                if (part == 0) {
                     float* ml = p.ml_partial + ((static_cast<size_t>(b) * p.Lq + i) * p.H + h) * 2;
                     ml[0] = mx * (1.0f / LOG2E);
                     ml[1] = sum;
                 }
             } else {
                 const float inv = 1.0f / sum;
-                uint4* dst = reinterpret_cast<uint4*>(p.O + (static_cast<size_t>(b) * p.Lq + i) * p.ldo + h * D + half * 32);
+                uint4* dst = reinterpret_cast<uint4*>(p.O + (static_cast<size_t>(b) * p.Lq + i) * p.ldo + h * D + part * OC);
 #pragma unroll
-                for (int v4 = 0; v4 < 4; ++v4)
+                for (int v4 = 0; v4 < OC / 8; ++v4)
                     dst[v4] = make_uint4(
                         pack2<kBF16>(__uint_as_float(ro[8 * v4]) * inv, __uint_as_float(ro[8 * v4 + 1]) * inv),
                         pack2<kBF16>(__uint_as_float(ro[8 * v4 + 2]) * inv, __uint_as_float(ro[8 * v4 + 3]) * inv),
@@ -351,53 +362,46 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 const int boffc = max(boff, 0);
                 ab::mbar_wait(&s_full, qt_it & 1, 27);
                 ab::tc_fence_after();
-                // ---- pass 1: t = scaled score + mask + bias written back over S; partial row max (loads pipelined) ----
+                // ---- pass 1: t = scaled score + mask + bias written back over S; partial row max ----
                 float mx = -INFINITY;
                 {
-                    uint32_t ra[32], rb[32];
-                    int c = static_cast<int>(half);
-                    ab::tmem_ld32(lane_addr + c * 32, ra);
-                    while (c < n32) {
+                    uint32_t ra[32];
+                    for (int c = static_cast<int>(part); c < n32; c += SPLIT) {
+                        ab::tmem_ld32(lane_addr + c * 32, ra);
                         ab::tmem_ld_wait();
-                        if (c + 2 < n32) ab::tmem_ld32(lane_addr + (c + 2) * 32, rb);
                         mx = fmaxf(mx, has_bias ? chunk_scores<true>(ra, scale2, mask2, bias2, c * 32, boffc)
                                                 : chunk_scores<false>(ra, scale2, mask2, bias2, c * 32, boffc));
                         ab::tmem_st32(lane_addr + c * 32, ra);
-                        c += 2;
-                        if (c >= n32) break;
-                        ab::tmem_ld_wait();
-                        if (c + 2 < n32) ab::tmem_ld32(lane_addr + (c + 2) * 32, ra);
-                        mx = fmaxf(mx, has_bias ? chunk_scores<true>(rb, scale2, mask2, bias2, c * 32, boffc)
-                                                : chunk_scores<false>(rb, scale2, mask2, bias2, c * 32, boffc));
-                        ab::tmem_st32(lane_addr + c * 32, rb);
-                        c += 2;
                     }
                 }
                 if (qt == n_qt - 1) ab::mbar_arrive(&aux_empty[buf]);   // last read of this item's tables
-                s_red[half][row] = mx;
+                s_red[part][row] = mx;
                 ab::tmem_st_wait();   // this thread re-reads its own t columns in pass 2
                 sm_bar();
-                mx = fmaxf(s_red[0][row], s_red[1][row]);
+#pragma unroll
+                for (int q = 0; q < SPLIT; ++q) mx = fmaxf(mx, s_red[q][row]);
                 // ---- pass 2: p = 2^(t - max), partial row sum, P (16-bit) written over the S columns it replaces ----
                 float sum = 0.f;
                 {
                     uint32_t ra[32], pk[16];
-                    for (int c = static_cast<int>(half); c < n32; c += 2) {
+                    for (int c = static_cast<int>(part); c < n32; c += SPLIT) {
                         ab::tmem_ld32(lane_addr + c * 32, ra);
                         ab::tmem_ld_wait();
-                        // P of chunks 2k, 2k+1 lands on the columns of S chunk k: both threads of a row must have
-                        // loaded their chunk of this iteration (hence every chunk <= 2k+1) before either stores P
+                        // P of chunks SPLIT*k .. SPLIT*k+SPLIT-1 lands on the columns of S chunks <= SPLIT*k + SPLIT-1:
+                        // every thread of a row must have loaded its chunk of this iteration before any of them stores P
                         pair_bar(lg);
                         sum += chunk_probs<kBF16>(ra, pk, mx);
                         tmem_st16(lane_addr + c * 16, pk);
                     }
                 }
-                s_sum[half][row] = sum;
+                s_sum[part][row] = sum;
                 ab::tmem_st_wait();
                 ab::tc_fence_before();
                 sm_bar();  // both halves' sums are in smem; all P columns of this warp pair are written
                 ab::mbar_arrive(&p_ready);
-                sum = s_sum[0][row] + s_sum[1][row];
+                sum = 0.f;
+#pragma unroll
+                for (int q = 0; q < SPLIT; ++q) sum += s_sum[q][row];
                 if (pipelined) {
                     // P.V(t-1) retired before S(t) was issued (MMA warp), and S(t) was observed above: O(t-1) is final
                     if (pend) emit(pend_b, pend_h, pend_i, pend_mx, pend_sum, o_col_of(pend_it));
@@ -505,6 +509,7 @@ int atlas_b200_attention(const void* q, int64_t ldq, int32_t q_col0, const void*
     static bool attr_set[2] = {false, false};
     const int items = B * H;
     const int grid = items < abh::num_sms() ? items : abh::num_sms();
+    abh::prof_begin(s, abh::PROF_ATTENTION);
     if (is_bf16) {
         if (!attr_set[1]) {
             AB_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -520,6 +525,7 @@ int atlas_b200_attention(const void* q, int64_t ldq, int32_t q_col0, const void*
         }
         attention_kernel<false><<<grid, THREADS, SMEM_BYTES, s>>>(tq, tk, tv, p);
     }
+    abh::prof_end(s, abh::PROF_ATTENTION, 4.0 * B * H * static_cast<double>(Lq) * Lk * D);
     abh::count_launch();
     AB_CUDA_CHECK(cudaGetLastError());
     return ATLAS_B200_OK;

@@ -268,7 +268,9 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
     }
     const int tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * ((p.N + BLOCK_N - 1) / BLOCK_N);
     const int grid = tiles < abh::num_sms() ? tiles : abh::num_sms();
+    abh::prof_begin(s, abh::PROF_LINEAR);
     gemm_kernel<kBF16, BLOCK_N><<<grid, THREADS, C::SMEM_BYTES, s>>>(ta, tb, p);
+    abh::prof_end(s, abh::PROF_LINEAR, 2.0 * p.M * static_cast<double>(p.N) * p.K);
     abh::count_launch();
     AB_CUDA_CHECK(cudaGetLastError());
     return ATLAS_B200_OK;

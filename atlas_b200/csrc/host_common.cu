@@ -95,12 +95,13 @@ int num_sms() {
 }
 
 // ---- profiling of the dominant kernel -------------------------------------------------------
-static bool g_prof_on = false;
+static int g_prof_on = 0;   // 0 off, otherwise the ProfKind being bracketed
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
 static size_t g_prof_used = 0;
+static double g_prof_work = 0;
 
-void prof_begin(cudaStream_t s) {
-    if (!g_prof_on) return;
+void prof_begin(cudaStream_t s, int kind) {
+    if (g_prof_on != kind) return;
     if (g_prof_used == g_prof_events.size()) {
         cudaEvent_t a, b;
         if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
@@ -109,20 +110,24 @@ void prof_begin(cudaStream_t s) {
     cudaEventRecord(g_prof_events[g_prof_used].first, s);
 }
 
-void prof_end(cudaStream_t s) {
-    if (!g_prof_on || g_prof_used >= g_prof_events.size()) return;
+void prof_end(cudaStream_t s, int kind, double work) {
+    if (g_prof_on != kind || g_prof_used >= g_prof_events.size()) return;
     cudaEventRecord(g_prof_events[g_prof_used].second, s);
     ++g_prof_used;
+    g_prof_work += work;
 }
 
 }  // namespace abh
 
 extern "C" {
 
-void atlas_b200_profile_enable(int32_t on) {
-    abh::g_prof_on = on != 0;
+void atlas_b200_profile_enable(int32_t kind) {
+    abh::g_prof_on = kind;
     abh::g_prof_used = 0;
+    abh::g_prof_work = 0;
 }
+
+double atlas_b200_profile_work(void) { return abh::g_prof_work; }
 
 int atlas_b200_profile_collect(double* total_ms, int32_t* launches) {
     double tot = 0;

@@ -1080,9 +1080,9 @@ static int topk_impl(const void* bank, int64_t n, int64_t ld, const void* querie
                     p.tile_begin = 0;
                     p.tile_step = 1;
                     p.num_tiles = tiles_a;
-                    abh::prof_begin(s);
+                    abh::prof_begin(s, abh::PROF_SCAN);
                     rc = scan(p);
-                    abh::prof_end(s);
+                    abh::prof_end(s, abh::PROF_SCAN, static_cast<double>(tiles_a) * tile_n * DIM * 2.0);
                     if (rc) return rc;
                     mips_select_kernel<kBF16><<<nqb, SEL_THREADS, 0, s>>>(w.cand, w.count, w.capq, k,
                                                                          SEL_WRITE_BOUND | SEL_CARRY, w.bound, nullptr,
@@ -1096,9 +1096,9 @@ static int topk_impl(const void* bank, int64_t n, int64_t ld, const void* querie
             p.tile_step = 1;
             p.num_tiles = total_tiles - first_tile;
             p.dbg = g_dbg;
-            abh::prof_begin(s);
+            abh::prof_begin(s, abh::PROF_SCAN);
             rc = scan(p);
-            abh::prof_end(s);
+            abh::prof_end(s, abh::PROF_SCAN, static_cast<double>(total_tiles - first_tile) * tile_n * DIM * 2.0);
             p.dbg = nullptr;
             if (rc) return rc;
             mips_select_kernel<kBF16><<<nqb, SEL_THREADS, 0, s>>>(w.cand, w.count, w.capq, k, SEL_EMIT, w.bound, os_b,

@@ -19,6 +19,7 @@ Not reproduced: dropout (eval only), the `isinf` clamps and their three host syn
 """
 import copy
 import math
+import os
 from types import SimpleNamespace
 
 import torch
@@ -136,6 +137,29 @@ def bias_by_delta(weight, lq, lk, bidirectional, num_buckets):
     return weight[buckets].t().float().contiguous()
 
 
+class _GraphRunner:
+    """One captured CUDA graph of a static-shape function of device tensors.  Every kernel of this package is
+    launched through the C ABI on `torch.cuda.current_stream()`, so capturing the whole forward removes the ~150
+    host launches of the decoder stack (launch-bound at T = 32 target tokens) from the critical path."""
+
+    def __init__(self, fn, example_inputs):
+        self.static_in = [t.clone() for t in example_inputs]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):           # eager warm-up: lazy kernel attributes, allocator, weight caches
+            fn(*self.static_in)
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_out = fn(*self.static_in)
+
+    def __call__(self, *inputs):
+        for dst, src in zip(self.static_in, inputs):
+            dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.static_out
+
+
 class FiDOutput(tuple):
     """(loss, logits, encoder_last_hidden_state) with the attribute names Atlas reads (src/atlas.py:292-300,583-590)."""
 
@@ -162,6 +186,10 @@ class FiD(nn.Module):
         self.encoder.config.n_context = 1
         self.encoder.config.bsz = 1
         self._half = HalfCache()
+        # CUDA-graph replay of the static-shape forward (eval / scoring); ATLAS_B200_CUDA_GRAPH=0 or
+        # `model.cuda_graphs = False` runs every kernel launch eagerly (needed under profilers' event bracketing)
+        self.cuda_graphs = os.environ.get("ATLAS_B200_CUDA_GRAPH", "1") != "0"
+        self._graphs = {}
 
     # ---- reference surface that is configuration only -------------------------------------
     def set_checkpoint(self, use_checkpoint):
@@ -305,19 +333,45 @@ class FiD(nn.Module):
         logits = ops.linear(h, W["lm_head.weight"])
         return logits.view(B, T, -1)
 
+    # ---- CUDA-graph cache --------------------------------------------------------------------
+    def _run(self, tag, fn, inputs):
+        """Run `fn(*inputs)` (static shapes, device tensors in / out): replay a captured graph when enabled."""
+        if not self.cuda_graphs:
+            return fn(*inputs)
+        self._weights()                                      # make sure the 16-bit weight copies exist / are current
+        dt = self._dtype()
+        key = (tag, dt, self._half.sets[dt]["key"], tuple((tuple(t.shape), t.dtype, t.device) for t in inputs))
+        runner = self._graphs.get(key)
+        if runner is None:
+            if len(self._graphs) >= 8:                       # shapes changed often: drop the oldest graph + its pool
+                self._graphs.pop(next(iter(self._graphs)))
+            runner = _GraphRunner(fn, inputs)
+            self._graphs[key] = runner
+        out = runner(*inputs)
+        # results live in the graph's static buffers: hand out copies
+        return out.clone() if torch.is_tensor(out) else tuple(o.clone() for o in out)
+
     # ---- public forward / generate -----------------------------------------------------------
     def forward(self, input_ids=None, attention_mask=None, decoder_input_ids=None, labels=None, encoder_outputs=None,
                 use_cache=False, **unused):
         if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
             raise AtlasB200Error("atlas_b200.FiD is forward-only in this round: call it under torch.no_grad()")
-        if encoder_outputs is not None:
-            enc = encoder_outputs[0]
-        else:
-            enc = self.encode(input_ids, attention_mask)
         if decoder_input_ids is None and labels is not None:
             decoder_input_ids = self._shift_right(labels)
-        B = enc.shape[0]
-        logits = self.decode(decoder_input_ids, enc, attention_mask.reshape(B, -1))
+        if encoder_outputs is not None:
+            enc = encoder_outputs[0]
+            B = enc.shape[0]
+            mask2 = attention_mask.reshape(B, -1)
+            logits = self._run("dec", lambda e, m, d: self.decode(d, e, m), (enc, mask2.to(torch.bool), decoder_input_ids))
+        else:
+            n_ctx, bsz = self.encoder.config.n_context, self.encoder.config.bsz
+
+            def full(ids, mask, dec):
+                e = self.encode(ids, mask)
+                return self.decode(dec, e, mask.reshape(e.shape[0], -1)), e
+
+            logits, enc = self._run(("full", n_ctx, bsz), full,
+                                    (input_ids, attention_mask.to(torch.bool), decoder_input_ids))
         loss = None
         if labels is not None:
             # CrossEntropyLoss(ignore_index=-100), src/modeling_t5.py:1650-1652

@@ -1,26 +1,27 @@
 #!/usr/bin/env python
-"""bench.py — the driver's measurement contract for atlas_b200 (see DESIGN.md §Measurement).
+"""bench.py — the driver's measurement contract for atlas_b200 (see DESIGN.md §6).
 
-A "step" is ONE `search_knn` of the global query batch (256 queries, top-40) over the sharded
-768-d fp16 passage bank: BASELINE.json configs[1] at N=1 (4 Mi x 768 bank on one B200), the same
-4 Mi-row shard PER GPU at N>1 (weak scaling in bank size; BASELINE.json configs[2] at N=8 = 32 Mi).
+Metric (BASELINE.json): end-to-end queries/sec of the retrieve-then-read step — Contriever query embedding,
+exact top-40 search over the GPU-resident 768-d fp16 passage bank (BASELINE configs[1]: 4 Mi passages per GPU,
+configs[2] at 8 GPUs = 32 Mi), FiD-base forward over the 40 retrieved passages (configs[3]: T5-v1.1-base, n_docs 40,
+text_maxlength 384, 32 target tokens) — plus the MIPS scan against the HBM roofline.
 
-  value     queries/s, inputs resident in HBM (device-resident queries, device results), whole job
-  e2e       queries/s through the reference-facing call with HOST buffers: pinned fp32 queries are
-            copied H2D, searched, and (score, id) results copied D2H inside the timed region
-  roofline  HBM: algorithmic bytes of the bank sweep (n_local x 768 x 2) / CUDA-event duration of the
-            scan kernel (events recorded inside the library on the launching stream)
-  cpu_baseline  the reference's CPU path (torch-CPU matmul + topk restated in oracle/ref_cpu_path.py)
-            timed on this box's host cores on a bounded sample
-
-`--impl reference` times that same CPU path as the reference arm.
+  value         queries/s of the whole job, step inputs already resident in HBM, CUDA events, max over ranks
+  e2e           the same step with HOST inputs: pinned token ids are copied H2D and the retrieved ids / scores and the
+                loss are copied D2H inside the timed region
+  roofline      the dominant kernel of the step (tcgen05 GEMM): FLOPs / CUDA-event time, against the measured bf16 peak
+  mips          the retrieval kernel alone at its BASELINE batch (256 queries): queries/s, C-ABI e2e with host buffers,
+                and the bank sweep against the measured HBM peak (`mips.roofline`)
+  cpu_baseline  the reference's CPU path (oracle/: torch-CPU restatements pinned to the reference's goldens) on this
+                box's host cores, bounded sample
+`--impl reference` times that CPU path as the reference arm.  One process per GPU; weak scaling (per-GPU batch and
+per-GPU bank shard fixed).
 """
 import argparse
 import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -31,26 +32,35 @@ DIM = 768
 NQ = 256                    # global query batch
 TOPK = 40
 CPU_SAMPLE_ROWS = 1 << 20   # bounded CPU sample: 1 Mi of the 4 Mi rows (scaled linearly, stated)
-METRIC = "retrieve queries/sec (exact top-40 MIPS search_knn over the 768-d fp16 passage bank)"
+METRIC = "end-to-end queries/sec (retrieve top-40 + FiD-base fwd)"
+N_DOCS, TEXT_LEN, TARGET_LEN, QUERY_TOKENS = 40, 384, 32, 20   # BASELINE configs[3] / finetune_qa defaults
+FID_FLOPS_PER_QUERY = 3.29e12
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=8, help="queries per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=N_LOCAL, help="passages per GPU (default: the BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
 
-def peaks():
+def peaks(kind="hbm"):
+    """(peak, source).  hbm: GB/s (burst copy figure: the sweep is timed alone); tensor: dense bf16 TFLOP/s,
+    the SUSTAINED figure (the GEMMs are timed inside a long step)."""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    key = "hbm_gbs" if kind == "hbm" else "bf16_tflops_sustained"
     if os.path.exists(path):
         with open(path) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+            d = json.load(f)
+        if key in d:
+            return float(d[key]), f"measured (MEASURED_PEAKS.json {key})"
+    return (6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)") if kind == "hbm" else \
+        (1500.0, "fallback (B200_PROFILING.md dense bf16)")
 
 
 class ClockSampler:
@@ -116,13 +126,17 @@ def make_queries():
     return torch.randn(NQ, DIM, generator=torch.Generator().manual_seed(4321))
 
 
-def cpu_reference_leg(steps, warmup, rows_full):
-    """The reference's CPU path on a bounded sample of the workload (all host threads)."""
+def cpu_reference_leg(batch, rows_full, fid_queries=1, search_steps=2):
+    """The reference's CPU path on a bounded sample of the step (all host threads): Contriever query embedding and
+    FiD-base forward (oracle/fid_cpu.py, fp32 torch-CPU) for `fid_queries` queries, and matmul + topk + doc lookup
+    (oracle/ref_cpu_path.py) for `batch` queries over a 1 Mi-row sample of the bank, scaled linearly to the bank."""
     import torch
 
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import fid_cpu
     import ref_cpu_path
 
+    torch.manual_seed(0)
     rows = min(CPU_SAMPLE_ROWS, rows_full)
     gen = torch.Generator().manual_seed(1234)
     emb = torch.empty(DIM, rows, dtype=torch.float16)
@@ -130,33 +144,71 @@ def cpu_reference_leg(steps, warmup, rows_full):
     for s in range(0, rows, step):
         e = min(rows, s + step)
         emb[:, s:e] = (torch.randn(DIM, e - s, generator=gen) / (DIM ** 0.5)).half()
-    q = make_queries()
     doc_map = ref_cpu_path.LazyDocMap(rows)
-    for _ in range(warmup):
+    bert = fid_cpu.bert_random_state(fid_cpu.BERT_BASE)
+    t5 = fid_cpu.t5_random_state(fid_cpu.T5_BASE)
+    q_ids, q_mask, dec, labels = make_step_inputs(batch, 0)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        q = fid_cpu.contriever_forward(bert, fid_cpu.BERT_BASE, q_ids, q_mask)
+        t_embed = (time.perf_counter() - t0) / batch
         ref_cpu_path.reference_search_cpu(emb, doc_map, q, TOPK)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        ref_cpu_path.reference_search_cpu(emb, doc_map, q, TOPK)
-    dt = (time.perf_counter() - t0) / steps
-    scale = rows_full / rows  # the scan is linear in the number of passages
-    qps = NQ / (dt * scale)
-    return {"value": qps, "unit": "queries/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{NQ} queries x {rows} of {rows_full} passages per step (time scaled x{scale:g}), "
-                      f"torch-CPU fp16 matmul + topk + python doc lookup (oracle/ref_cpu_path.py), {steps} steps",
-            "ms_per_step_sample": dt * 1e3}
+        t0 = time.perf_counter()
+        for _ in range(search_steps):
+            docs, _ = ref_cpu_path.reference_search_cpu(emb, doc_map, q, TOPK)
+        t_search = (time.perf_counter() - t0) / search_steps * (rows_full / rows) / batch
+        ids = torch.randint(2, 32000, (fid_queries, N_DOCS * TEXT_LEN))
+        mask = torch.ones(fid_queries, N_DOCS * TEXT_LEN, dtype=torch.bool)
+        t0 = time.perf_counter()
+        fid_cpu.fid_forward(t5, fid_cpu.T5_BASE, ids, mask, dec[:fid_queries], labels[:fid_queries], n_context=N_DOCS)
+        t_read = (time.perf_counter() - t0) / fid_queries
+    per_query = t_embed + t_search + t_read
+    return {"value": 1.0 / per_query, "unit": "queries/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"per query: Contriever embed {t_embed:.3f} s ({batch} queries timed) + search {t_search:.3f} s "
+                      f"({batch} queries x {rows} of {rows_full} passages, time scaled x{rows_full / rows:g}) + FiD-base "
+                      f"fp32 forward {t_read:.3f} s ({fid_queries} query timed); torch-CPU, oracle/fid_cpu.py + "
+                      f"oracle/ref_cpu_path.py",
+            "s_per_query": per_query}
+
+
+def make_step_inputs(batch, seed):
+    """Synthetic NQ-shaped batch: queries of ~20 tokens padded to text_maxlength like the reference does
+    (src/atlas.py:187-199), 32 target tokens."""
+    import torch
+
+    g = torch.Generator().manual_seed(777 + seed)
+    q_ids = torch.zeros(batch, TEXT_LEN, dtype=torch.long)
+    q_mask = torch.zeros(batch, TEXT_LEN, dtype=torch.long)
+    q_ids[:, :QUERY_TOKENS] = torch.randint(1000, 30000, (batch, QUERY_TOKENS), generator=g)
+    q_mask[:, :QUERY_TOKENS] = 1
+    labels = torch.randint(2, 32000, (batch, TARGET_LEN), generator=g)
+    dec = torch.cat([torch.zeros(batch, 1, dtype=torch.long), labels[:, :-1]], dim=1)
+    return q_ids, q_mask, dec, labels
+
+
+def workload_config(args):
+    return {"workload": f"BASELINE configs[1]+[3]: per GPU a {args.rows}x768 fp16 passage bank (exact top-{TOPK}) and "
+                        f"{args.batch} queries/step through Contriever-base query embedding -> search_knn -> FiD-base "
+                        f"(T5-v1.1-base, n_docs {N_DOCS}, text_maxlength {TEXT_LEN}, {TARGET_LEN} target tokens) forward + loss",
+            "bank_rows_per_gpu": args.rows, "bank_rows_total": args.rows * args.gpus,
+            "queries_per_step": args.batch * args.gpus, "per_gpu_batch": args.batch, "topk": TOPK,
+            "parallelism": f"dp{args.gpus}: bank sharded over {args.gpus} GPU(s) (queries all-gathered, one all-gather "
+                           f"of per-shard top-k), reader data-parallel",
+            "reader_tokens": "synthetic: token ids derived on the device from the retrieved passage ids (stand-in for a "
+                             "device-resident token cache; no tokenizer vocabulary offline)",
+            "weights": "random init (Contriever-base / T5-v1.1-base shapes), bf16 reader + retriever, fp16 bank",
+            "l2": "bank (6.4 GB) and per-step activations (> 1 GB) exceed the 126 MB L2; no explicit flush"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 5))
-    warmup = max(1, min(args.warmup, 2))
-    leg = cpu_reference_leg(steps, warmup, args.rows * args.gpus)
+    leg = cpu_reference_leg(args.batch, args.rows * args.gpus, fid_queries=1, search_steps=max(1, min(args.steps, 2)))
     line = {
         "impl": "reference", "metric": METRIC, "value": leg["value"], "unit": "queries/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": warmup, "ms_per_step": leg["ms_per_step_sample"] * (args.rows * args.gpus / min(CPU_SAMPLE_ROWS, args.rows * args.gpus)),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "steps": 1, "warmup": 0, "ms_per_step": leg["s_per_query"] * 1e3 * args.batch * args.gpus,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args),
         "cpu_baseline": {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": leg["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -165,21 +217,17 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args):
-    return {"workload": f"BASELINE configs[1]: {args.rows}x768 fp16 passage bank per GPU, batch={NQ} queries, top-{TOPK} exact MIPS",
-            "bank_rows_per_gpu": args.rows, "bank_rows_total": args.rows * args.gpus, "queries_per_step": NQ,
-            "topk": TOPK, "parallelism": f"bank sharded over {args.gpus} GPU(s), queries all-gathered",
-            "l2": "inputs (6.4 GB bank per GPU) larger than the 126 MB L2; no explicit flush"}
-
-
 def run_ours(args):
+    import ctypes
+
     import torch
     import torch.distributed as dist
 
     from atlas_b200 import ops
     from atlas_b200._lib import lib
+    from atlas_b200.fid import FiD, T5ConfigLite
     from atlas_b200.index import DistributedIndex
-    import ctypes
+    from atlas_b200.retrievers import BertConfigLite, Contriever
 
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import ref_cpu_path
@@ -208,11 +256,11 @@ def run_ours(args):
             pass
 
     index._store = _SyntheticStore()
-
-    q_host = make_queries().pin_memory()
-    per = NQ // world
-    q_host_local = q_host[rank * per:(rank + 1) * per].contiguous().pin_memory() if world > 1 else q_host
-    q_dev_local = q_host_local.to(dev)
+    torch.manual_seed(0)          # identical weights on every rank
+    retriever = Contriever(BertConfigLite()).to(torch.bfloat16).to(dev).eval()
+    reader = FiD(T5ConfigLite()).to(torch.bfloat16).to(dev).eval()
+    reader.encoder.config.n_context, reader.encoder.config.bsz = N_DOCS, args.batch
+    B = args.batch
 
     def barrier_sync():
         if world > 1:
@@ -226,43 +274,74 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    host = [t.pin_memory() for t in make_step_inputs(B, rank)]
+    resident = [t.to(dev) for t in host]
+    pos = torch.arange(TEXT_LEN, device=dev, dtype=torch.long)
+    reader_mask = torch.ones(B, N_DOCS * TEXT_LEN, dtype=torch.bool, device=dev)
+
+    def step(from_host):
+        """One retrieve-then-read step of this rank's B queries (collective inside search_device)."""
+        q_ids, q_mask, dec, labels = [t.to(dev, non_blocking=True) for t in host] if from_host else resident
+        with torch.no_grad():
+            q_emb = retriever(input_ids=q_ids, attention_mask=q_mask)                  # [B, 768]
+            scores, gids = index.search_device(q_emb, TOPK)                            # [B, 40] fp16 / int64 global ids
+            # reader tokens of (query, passage) pairs: synthetic ids keyed by the retrieved passage id
+            reader_ids = ((gids[:, :, None] * 1315423911 + pos * 2654435761) % 32000 + 2).view(B, N_DOCS * TEXT_LEN)
+            out = reader(input_ids=reader_ids, attention_mask=reader_mask, decoder_input_ids=dec, labels=labels)
+        if from_host:
+            return out[0].float().cpu(), gids.cpu(), scores.cpu()                     # D2H: loss + retrieved ids/scores
+        return out[0], gids, scores
+
     # ---------------- value: device-resident inputs -----------------------------------------
-    for _ in range(args.warmup):
-        index.search_device(q_dev_local, TOPK)
+    for _ in range(max(args.warmup, 3)):
+        step(False)
     launches0 = L.atlas_b200_launch_count()
-    L.atlas_b200_profile_enable(1)
     barrier_sync()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
         e0.record()
         for _ in range(args.steps):
-            s, i = index.search_device(q_dev_local, TOPK)
+            loss, gids, _ = step(False)
         e1.record()
         barrier_sync()
     total_ms = max_over_ranks(e0.elapsed_time(e1))
-    launches = L.atlas_b200_launch_count() - launches0
-    kms, kn = ctypes.c_double(0), ctypes.c_int32(0)
-    L.atlas_b200_profile_collect(ctypes.byref(kms), ctypes.byref(kn))
-    L.atlas_b200_profile_enable(0)
+    launches_eager = None
     ms_per_step = total_ms / args.steps
-    value = NQ / (ms_per_step * 1e-3)
+    value = B * world / (ms_per_step * 1e-3)
+    assert bool(torch.isfinite(loss.float())), "non-finite loss in the benchmark step"
 
-    # ---------------- e2e: host buffers through the public call ------------------------------
-    def e2e_step():
-        if world == 1:
-            return ops.search_host(index._bank, q_host_local, TOPK, workspace=index._workspace)
-        return index.search_knn(q_host_local.to(dev, non_blocking=True), TOPK)
-
-    for _ in range(max(3, args.warmup // 2)):
-        e2e_step()
+    # ---------------- e2e: host inputs / host results ------------------------------------------
+    for _ in range(2):
+        step(True)
     barrier_sync()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        out = e2e_step()
+        step(True)
     barrier_sync()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
-    h2d = q_host_local.numel() * 4 * world
-    d2h = NQ * TOPK * (2 + 8) if world > 1 else NQ * TOPK * (4 + 8)
+    h2d = sum(t.numel() * t.element_size() for t in host) * world
+    d2h = (4 + B * TOPK * (8 + 2)) * world
+
+    # ---------------- per-kernel time of the step (eager launches bracketed with CUDA events in the library) -------
+    reader.cuda_graphs = False
+    prof = {}
+    for kind, name in ((2, "gemm"), (3, "attention")):
+        step(False)
+        torch.cuda.synchronize()
+        l0 = L.atlas_b200_launch_count()
+        L.atlas_b200_profile_enable(kind)
+        step(False)
+        torch.cuda.synchronize()
+        work = L.atlas_b200_profile_work()
+        kms, kn = ctypes.c_double(0), ctypes.c_int32(0)
+        L.atlas_b200_profile_collect(ctypes.byref(kms), ctypes.byref(kn))
+        L.atlas_b200_profile_enable(0)
+        prof[name] = (kms.value, kn.value, work)
+        launches_eager = L.atlas_b200_launch_count() - l0
+    reader.cuda_graphs = True
+
+    # ---------------- the retrieval kernel alone at its BASELINE batch (256 queries) -------------
+    mips = mips_leg(args, index, dev, world, rank, L, barrier_sync, max_over_ranks)
 
     if rank != 0:
         if world > 1:
@@ -270,40 +349,111 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    peak, peak_src = peaks()
-    # the bank sweep is bracketed per launch inside the library (CUDA events on the launching stream);
-    # one search sweeps the bank exactly once, split over `sweeps_per_search` launches of the same kernel
-    sweeps_per_search = max(1, kn.value // args.steps)
-    kernel_ms = kms.value / args.steps                       # all sweep launches of one search
-    alg_bytes = args.rows * DIM * 2
-    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
+    peak, peak_src = peaks("tensor")
+    g_ms, g_n, g_flops = prof["gemm"]
+    a_ms, a_n, a_flops = prof["attention"]
+    achieved = g_flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
     line = {
         "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": workload_config(args),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
-                     "kernel": "mips_scan_ts_kernel (bank sweep; one search = %d launches covering the bank once)"
-                               % sweeps_per_search,
-                     "kernel_ms_per_search": kernel_ms, "kernel_launches_timed": kn.value,
-                     "algorithmic_bytes_per_search": alg_bytes,
-                     "kernel_share_of_step": kernel_ms / ms_per_step if ms_per_step else None},
-        "e2e": {"value": NQ / (e2e_ms * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": h2d,
+                     "kernel": "gemm_kernel (tcgen05 linear layers of FiD-base / Contriever-base, fused epilogues)",
+                     "kernel_ms_per_step": g_ms, "kernel_launches_per_step": g_n, "algorithmic_flops_per_step": g_flops,
+                     "kernel_share_of_step": g_ms / ms_per_step if ms_per_step else None,
+                     "attention_kernel": {"ms_per_step": a_ms, "launches_per_step": a_n,
+                                          "achieved_tflops": a_flops / (a_ms * 1e-3) / 1e12 if a_ms > 0 else None,
+                                          "share_of_step": a_ms / ms_per_step if ms_per_step else None},
+                     "model_flops_utilisation": FID_FLOPS_PER_QUERY * B / (ms_per_step * 1e-3) / 1e12 / peak},
+        "e2e": {"value": B * world / (e2e_ms * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
-                "call": "atlas_b200_search_host (C ABI, host buffers)" if world == 1 else
-                        "DistributedIndex.search_knn (pinned host queries -> passage dicts + scores)"},
-        "gpu_launches": int(launches),
+                "call": "Contriever.forward -> DistributedIndex.search_device -> FiD.forward (pinned host token ids in, "
+                        "loss + retrieved ids / scores out)"},
+        "gpu_launches": int(launches_eager) * args.steps if launches_eager else 0,
+        "gpu_launches_note": "kernels per step counted on an eager step; the timed steps replay the reader's launches "
+                             "from a CUDA graph",
         "clocks": clocks.summary(),
-        "aggregate_bank_GBps": world * alg_bytes / (ms_per_step * 1e-3) / 1e9,
+        "mips": mips,
     }
     if not args.no_cpu_baseline and world == 1:
-        leg = cpu_reference_leg(3, 1, args.rows)
+        leg = cpu_reference_leg(B, args.rows)
         line["cpu_baseline"] = {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def mips_leg(args, index, dev, world, rank, L, barrier_sync, max_over_ranks):
+    """search_knn alone: 256 queries / top-40 over the sharded bank (BASELINE configs[1] at N=1, configs[2] at N=8)."""
+    import ctypes
+
+    import torch
+
+    from atlas_b200 import ops
+
+    steps, warmup = max(20, args.steps), 5
+    q_host = make_queries().pin_memory()
+    per = NQ // world
+    q_host_local = q_host[rank * per:(rank + 1) * per].contiguous().pin_memory() if world > 1 else q_host
+    q_dev_local = q_host_local.to(dev)
+    for _ in range(warmup):
+        index.search_device(q_dev_local, TOPK)
+    L.atlas_b200_profile_enable(1)
+    barrier_sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        index.search_device(q_dev_local, TOPK)
+    e1.record()
+    barrier_sync()
+    total_ms = max_over_ranks(e0.elapsed_time(e1))
+    kms, kn = ctypes.c_double(0), ctypes.c_int32(0)
+    L.atlas_b200_profile_collect(ctypes.byref(kms), ctypes.byref(kn))
+    L.atlas_b200_profile_enable(0)
+    ms_per_step = total_ms / steps
+
+    def e2e_step():
+        if world == 1:
+            return ops.search_host(index._bank, q_host_local, TOPK, workspace=index._workspace)
+        return index.search_knn(q_host_local.to(dev, non_blocking=True), TOPK)
+
+    for _ in range(3):
+        e2e_step()
+    barrier_sync()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        e2e_step()
+    barrier_sync()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / steps
+    peak, peak_src = peaks("hbm")
+    kernel_ms = kms.value / steps
+    alg_bytes = args.rows * DIM * 2
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_mips_scan_traffic.json")
+    if os.path.exists(tpath):     # dram bytes of the sweep from the committed `ncu --set full` capture (see profiles/)
+        with open(tpath) as f:
+            traffic = json.load(f).get("dram_bytes_per_search")
+    return {
+        "metric": "retrieve queries/sec (exact top-40 search_knn, 256-query batches)", "value": NQ / (ms_per_step * 1e-3),
+        "unit": "queries/s", "ms_per_step": ms_per_step, "steps": steps, "queries_per_step": NQ,
+        "e2e": {"value": NQ / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": q_host_local.numel() * 4 * world,
+                "d2h_bytes_per_step": NQ * TOPK * (2 + 8) if world > 1 else NQ * TOPK * (4 + 8),
+                "call": "atlas_b200_search_host (C ABI, host buffers)" if world == 1 else
+                        "DistributedIndex.search_knn (pinned host queries -> passage dicts + scores)"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
+                     "kernel": "mips_scan_ts_kernel (bank sweep; one search = %d launches covering the bank once)"
+                               % max(1, kn.value // steps),
+                     "kernel_ms_per_search": kernel_ms, "kernel_launches_timed": kn.value,
+                     "algorithmic_bytes_per_search": alg_bytes,
+                     "kernel_share_of_step": kernel_ms / ms_per_step if ms_per_step else None},
+        "aggregate_bank_GBps": world * alg_bytes / (ms_per_step * 1e-3) / 1e9,
+    }
 
 
 def main():

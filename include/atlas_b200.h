@@ -164,11 +164,17 @@ int atlas_b200_attention(const void* q, int64_t ldq, int32_t q_col0, const void*
 int atlas_b200_attention_combine(const float* o_partial, const float* ml_partial, int32_t B, int32_t splits,
                                  int32_t Lq, int32_t H, void* out, int64_t ldo, int32_t is_bf16, void* stream);
 
-/* Measurement hook for bench.py's roofline: while enabled, every launch of the DOMINANT kernel (the
- * main bank sweep of atlas_b200_mips_topk) is bracketed with CUDA events on its launching stream.
- * atlas_b200_profile_collect() synchronises those events, returns the summed kernel time and the
- * number of bracketed launches, and resets the list.  Not thread safe; off by default. */
-void atlas_b200_profile_enable(int32_t on);
+/* Measurement hook for bench.py's roofline: while enabled, every launch of ONE kind of kernel is bracketed
+ * with CUDA events on its launching stream:
+ *   kind 1  the bank sweep of atlas_b200_mips_topk (work = algorithmic bytes swept)
+ *   kind 2  the tcgen05 GEMM of atlas_b200_linear   (work = 2*M*N*K FLOPs)
+ *   kind 3  the attention kernel                     (work = 4*B*H*Lq*Lk*64 FLOPs)
+ *   kind 0  off (default).
+ * atlas_b200_profile_work() returns the work summed over the bracketed launches so far;
+ * atlas_b200_profile_collect() synchronises the events, returns the summed kernel time and the number of
+ * bracketed launches, and resets the list (call profile_work first).  Not thread safe. */
+void atlas_b200_profile_enable(int32_t kind);
+double atlas_b200_profile_work(void);
 int atlas_b200_profile_collect(double* total_ms, int32_t* launches);
 
 /* fp32 -> fp16/bf16 row conversion (`allqueries.half()`), device to device. */

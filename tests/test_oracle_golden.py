@@ -103,3 +103,57 @@ def test_fake_tokenizer_surface():
     assert enc["input_ids"].shape == (1, 6) and enc["input_ids"][0, 2].item() == rt.eos_token_id
     assert rt(["p q r s t u v"], max_length=4, truncation=True, return_tensors="pt")["input_ids"][0, -1].item() == 1
     assert len(rt.vocab) == atlas_synth.READER_VOCAB
+
+
+def _named_state(kind, seed):
+    """The seeded weights of oracle/model_synth.py under the HF parameter names (no module needed)."""
+    import torch
+
+    import model_synth
+    from atlas_b200.fid import FiD, T5ConfigLite
+    from atlas_b200.retrievers import BertConfigLite, Contriever
+
+    if kind == "fid":
+        m = FiD(T5ConfigLite(**{k: v for k, v in model_synth.T5_CFG.items()
+                                if k not in ("dropout_rate", "is_encoder_decoder", "use_cache")}))
+    else:
+        m = Contriever(BertConfigLite(**model_synth.CONTRIEVER_CFG))
+    sd, sha = model_synth.fill_state_dict(m.state_dict(), seed)
+    return {k: v.float() if torch.is_floating_point(v) else v for k, v in sd.items()}, sha
+
+
+def test_fid_cpu_restatement_matches_reference():
+    """oracle/fid_cpu.py (the CPU checker / timed CPU baseline on the GPU box) reproduces the UNMODIFIED reference
+    FiD's fp32 logits, loss and encoder states on the golden case (oracle/make_golden_models.py)."""
+    import torch
+
+    import fid_cpu
+    import model_synth
+
+    g = np.load(os.path.join(GOLDEN_DIR, "fid_tiny.npz"))
+    sd, sha = _named_state("fid", 202)
+    assert sha == str(g["weights_sha256"])
+    ids, mask, labels = model_synth.fid_inputs()
+    dec = labels.clone()
+    dec = torch.cat([torch.zeros(dec.shape[0], 1, dtype=dec.dtype), dec[:, :-1]], dim=1).masked_fill_(
+        torch.cat([torch.zeros(dec.shape[0], 1, dtype=torch.bool), labels[:, :-1] == -100], dim=1), 0)   # _shift_right
+    with torch.no_grad():
+        loss, logits, enc = fid_cpu.fid_forward(sd, model_synth.T5_CFG, ids, mask, dec, labels, n_context=3)
+    assert np.abs(logits.numpy() - g["logits_fp32"]).max() < 2e-4
+    assert abs(float(loss) - float(g["loss_fp32"])) < 1e-4
+    assert np.abs(enc.numpy() - g["enc_fp32"].astype(np.float32)).max() < 2e-3   # golden stored in fp16
+
+
+def test_contriever_cpu_restatement_matches_reference():
+    import torch
+
+    import fid_cpu
+    import model_synth
+
+    g = np.load(os.path.join(GOLDEN_DIR, "contriever_tiny.npz"))
+    sd, sha = _named_state("contriever", 101)
+    assert sha == str(g["weights_sha256"])
+    ids, mask = model_synth.contriever_inputs()
+    with torch.no_grad():
+        emb = fid_cpu.contriever_forward(sd, model_synth.CONTRIEVER_CFG, ids, mask)
+    assert np.abs(emb.numpy() - g["emb_fp32"]).max() < 2e-4
