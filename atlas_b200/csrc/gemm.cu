@@ -17,13 +17,21 @@
 //                                                                   modeling_t5.py:281-285, fp32 GELU)
 //
 // Persistent, warp-specialised, one CTA per SM (grid = #SMs):
-//   warp 0 TMA producer | warp 1 MMA issuer (UMMA M=128, N=BLOCK_N, K=16) | warp 2 TMEM allocator
+//   warp 0 TMA producer | warp 1 MMA issuer (UMMA K=16) | warp 2 TMEM allocator
 //   warps 4-11 epilogue: TMEM -> registers -> epilogue math -> 16-bit global stores
 // TMEM: 2 accumulator buffers x BLOCK_N columns, so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Two tile shapes:
+//   kPair = true  (large M): a 2-CTA cluster computes a 256 x 256 tile with cta_group::2 MMAs (UMMA M=256, N=256).
+//       Each CTA streams its own 128 rows of A and HALF of the W tile (128 rows) -> 32 KB per 64-wide K block and
+//       CTA instead of 48 KB, which buys a 6-stage ring: the mainloop of the 1-CTA shape was starved by L2 latency
+//       (4 stages x 48 KB in flight ~ latency x bandwidth; tensor pipe 61 % busy, profiles/r01_gemm_v1.md).
+//       The leader CTA issues the MMAs; tcgen05.commit multicasts ring / accumulator barriers to both CTAs.
+//   kPair = false: one CTA, 128 x BLOCK_N tiles (small M: decoder, tails).
 #include "common.cuh"
 #include "host_common.h"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace gemm {
 
@@ -35,14 +43,17 @@ constexpr int EPI_WARPS = 8;
 
 enum Epilogue { EPI_NONE = 0, EPI_BIAS = 1, EPI_GELU = 2, EPI_RESIDUAL = 3, EPI_GATED = 4 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool kPair>
 struct Cfg {
-    static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-    static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+    static constexpr int CTAS = kPair ? 2 : 1;
+    static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;                 // this CTA's 128 rows of A
+    static constexpr int B_ROWS = BLOCK_N / CTAS;                         // W rows this CTA streams
+    static constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
     static constexpr int TMEM_COLS = 2 * BLOCK_N;  // 256 or 512 (power of two)
+    static constexpr int UMMA_M = BLOCK_M * CTAS;
 };
 
 struct Params {
@@ -67,14 +78,21 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 // transformers' "gelu_new": 0.5*x*(1+tanh(sqrt(2/pi)*(x+0.044715*x^3)))
+// = x * sigmoid(2u), u = sqrt(2/pi) (x + 0.044715 x^3): 1 + tanh(u) = 2 / (1 + e^(-2u)).  One MUFU.EX2 and one
+// MUFU.RCP (both ~1e-7 relative) instead of tanhf's ~30-instruction path: the 128 x 256 gated epilogue (16 k GELUs
+// per tile) was longer than the tile's MMAs.  e^(-2u) = inf for very negative x gives x / inf = -0 (true value ~0).
 __device__ __forceinline__ float gelu_new(float x) {
-    return 0.5f * x * (1.0f + tanhf(0.7978845608028654f * (x + 0.044715f * x * x * x)));
+    const float u2 = x * (1.5957691216057308f + 0.07135481627260025f * x * x);    // 2u
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * u2));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return x * r;
 }
 
-template <bool kBF16, int BLOCK_N>
+template <bool kBF16, int BLOCK_N, bool kPair>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
-    using C = Cfg<BLOCK_N>;
+    using C = Cfg<BLOCK_N, kPair>;
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[C::STAGES];
     __shared__ __align__(8) uint64_t empty_bar[C::STAGES];
@@ -87,7 +105,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const uint32_t smem_base = (ab::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - ab::smem_u32(smem_raw));
 
-    const int num_m = (p.M + BLOCK_M - 1) / BLOCK_M;
+    const uint32_t cta_rank = kPair ? ab::cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;
+    const int group = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int num_groups = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+    constexpr int TILE_M = BLOCK_M * C::CTAS;
+    const int num_m = (p.M + TILE_M - 1) / TILE_M;
     const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
     const int num_tiles = num_m * num_n;
     const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
@@ -103,28 +126,42 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
         for (int b = 0; b < 2; ++b) {
             ab::mbar_init(&tmem_full_bar[b], 1);
-            ab::mbar_init(&tmem_empty_bar[b], EPI_WARPS);
+            ab::mbar_init(&tmem_empty_bar[b], EPI_WARPS * C::CTAS);
         }
         ab::fence_barrier_init();
     }
-    if (warp == 2) ab::tmem_alloc<1>(&tmem_base_smem, C::TMEM_COLS);
+    if (warp == 2) ab::tmem_alloc<C::CTAS>(&tmem_base_smem, C::TMEM_COLS);
     ab::tc_fence_before();
-    __syncthreads();
+    if constexpr (kPair) {
+        ab::cluster_sync_all();
+    } else {
+        __syncthreads();
+    }
     ab::tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
 
     if (warp == 0) {
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            for (int t = group; t < num_tiles; t += num_groups) {
                 const int m_blk = t / num_n, n_blk = t % num_n;
+                const int a_row = m_blk * TILE_M + static_cast<int>(cta_rank) * BLOCK_M;
+                const int b_row = n_blk * BLOCK_N + static_cast<int>(cta_rank) * C::B_ROWS;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     ab::mbar_wait(&empty_bar[stage], phase ^ 1u, 11);
-                    ab::mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
                     uint8_t* st = smem_gen + stage * C::STAGE_BYTES;
-                    ab::tma_load_2d(&tmap_a, &full_bar[stage], st, kb * BLOCK_K, m_blk * BLOCK_M, ab::kEvictNormal);
-                    ab::tma_load_2d(&tmap_b, &full_bar[stage], st + C::A_BYTES, kb * BLOCK_K, n_blk * BLOCK_N,
-                                    ab::kEvictLast);
+                    if constexpr (kPair) {
+                        // the leader's barrier collects the bytes of BOTH CTAs' boxes
+                        if (leader) ab::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+                        ab::tma_load_2d_2sm(&tmap_a, &full_bar[stage], st, kb * BLOCK_K, a_row, ab::kEvictNormal);
+                        ab::tma_load_2d_2sm(&tmap_b, &full_bar[stage], st + C::A_BYTES, kb * BLOCK_K, b_row,
+                                            ab::kEvictLast);
+                    } else {
+                        ab::mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+                        ab::tma_load_2d(&tmap_a, &full_bar[stage], st, kb * BLOCK_K, a_row, ab::kEvictNormal);
+                        ab::tma_load_2d(&tmap_b, &full_bar[stage], st + C::A_BYTES, kb * BLOCK_K, b_row,
+                                        ab::kEvictLast);
+                    }
                     if (++stage == C::STAGES) {
                         stage = 0;
                         phase ^= 1u;
@@ -133,11 +170,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = ab::umma_idesc_f16(BLOCK_M, BLOCK_N, kBF16);
+        // MMA issuer (leader CTA of a pair only)
+        if (lane == 0 && leader) {
+            constexpr uint32_t idesc = ab::umma_idesc_f16(C::UMMA_M, BLOCK_N, kBF16);
             uint32_t stage = 0, phase = 0;
             int it = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+            for (int t = group; t < num_tiles; t += num_groups, ++it) {
                 const uint32_t buf = it & 1;
                 ab::mbar_wait(&tmem_empty_bar[buf], ((it >> 1) & 1) ^ 1u, 12);
                 ab::tc_fence_after();
@@ -149,16 +187,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                     const uint64_t bdesc0 = ab::umma_desc_k_sw128(smem_base + stage * C::STAGE_BYTES + C::A_BYTES);
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                        ab::umma_ss<1>(d_tmem, adesc0 + ((k * UMMA_K * 2) >> 4), bdesc0 + ((k * UMMA_K * 2) >> 4), idesc,
-                                       (kb | k) != 0 ? 1u : 0u);
+                        ab::umma_ss<C::CTAS>(d_tmem, adesc0 + ((k * UMMA_K * 2) >> 4), bdesc0 + ((k * UMMA_K * 2) >> 4),
+                                             idesc, (kb | k) != 0 ? 1u : 0u);
                     }
-                    ab::umma_commit(&empty_bar[stage]);
+                    if constexpr (kPair) {
+                        ab::umma_commit_2sm(&empty_bar[stage], 0x3);
+                    } else {
+                        ab::umma_commit(&empty_bar[stage]);
+                    }
                     if (++stage == C::STAGES) {
                         stage = 0;
                         phase ^= 1u;
                     }
                 }
-                ab::umma_commit(&tmem_full_bar[buf]);
+                if constexpr (kPair) {
+                    ab::umma_commit_2sm(&tmem_full_bar[buf], 0x3);
+                } else {
+                    ab::umma_commit(&tmem_full_bar[buf]);
+                }
             }
         }
     } else if (warp >= 4) {
@@ -167,10 +213,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const uint32_t half = (warp - 4u) >> 2;  // which half of the BLOCK_N columns
         constexpr int CHUNKS = BLOCK_N / 64;     // 32-column chunks per warp
         int it = 0;
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        for (int t = group; t < num_tiles; t += num_groups, ++it) {
             const uint32_t buf = it & 1;
             const int m_blk = t / num_n, n_blk = t % num_n;
-            const int row = m_blk * BLOCK_M + static_cast<int>(lg * 32 + lane);
+            const int row = m_blk * TILE_M + static_cast<int>(cta_rank) * BLOCK_M + static_cast<int>(lg * 32 + lane);
             ab::mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1, 14);
             ab::tc_fence_after();
 #pragma unroll 1
@@ -184,7 +230,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                     // all accumulator columns of this warp are in registers: release the buffer
                     ab::tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) ab::mbar_arrive(&tmem_empty_bar[buf]);
+                    if (lane == 0) {
+                        if (leader) ab::mbar_arrive(&tmem_empty_bar[buf]);
+                        else ab::mbar_arrive_cluster(&tmem_empty_bar[buf], 0);   // the leader issues the next MMAs
+                    }
                 }
                 if (row >= p.M || col0 >= p.N) continue;
                 float v[32];
@@ -250,26 +299,48 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
 
     ab::tc_fence_before();
-    __syncthreads();
+    if constexpr (kPair) {
+        ab::cluster_sync_all();   // the peer's MMAs / multicast commits may still target this CTA's smem and barriers
+    } else {
+        __syncthreads();
+    }
     if (warp == 2) {
         ab::tc_fence_after();
-        ab::tmem_dealloc<1>(tmem_base, C::TMEM_COLS);
+        ab::tmem_dealloc<C::CTAS>(tmem_base, C::TMEM_COLS);
     }
 }
 
-template <bool kBF16, int BLOCK_N>
+template <bool kBF16, int BLOCK_N, bool kPair>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, cudaStream_t s) {
-    using C = Cfg<BLOCK_N>;
+    using C = Cfg<BLOCK_N, kPair>;
     static bool attr_set = false;
     if (!attr_set) {
-        AB_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<kBF16, BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           C::SMEM_BYTES));
+        AB_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<kBF16, BLOCK_N, kPair>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         attr_set = true;
     }
-    const int tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * ((p.N + BLOCK_N - 1) / BLOCK_N);
-    const int grid = tiles < abh::num_sms() ? tiles : abh::num_sms();
+    const int tile_m = BLOCK_M * C::CTAS;
+    const int tiles = ((p.M + tile_m - 1) / tile_m) * ((p.N + BLOCK_N - 1) / BLOCK_N);
+    const int groups_max = abh::num_sms() / C::CTAS;
+    const int grid = (tiles < groups_max ? tiles : groups_max) * C::CTAS;
     abh::prof_begin(s, abh::PROF_LINEAR);
-    gemm_kernel<kBF16, BLOCK_N><<<grid, THREADS, C::SMEM_BYTES, s>>>(ta, tb, p);
+    if constexpr (kPair) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(static_cast<unsigned>(grid));
+        cfg.blockDim = dim3(THREADS);
+        cfg.dynamicSmemBytes = C::SMEM_BYTES;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        AB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<kBF16, BLOCK_N, kPair>, ta, tb, p));
+    } else {
+        gemm_kernel<kBF16, BLOCK_N, kPair><<<grid, THREADS, C::SMEM_BYTES, s>>>(ta, tb, p);
+    }
     abh::prof_end(s, abh::PROF_LINEAR, 2.0 * p.M * static_cast<double>(p.N) * p.K);
     abh::count_launch();
     AB_CUDA_CHECK(cudaGetLastError());
@@ -303,17 +374,29 @@ int atlas_b200_linear(const void* A, int64_t lda, const void* W, int64_t ldw, co
     p.residual = static_cast<const uint16_t*>(residual);
     p.C = static_cast<uint16_t*>(C);
     const bool wide = N >= 256 && (static_cast<int64_t>((M + 127) / 128) * ((N + 255) / 256) >= abh::num_sms() / 2);
-    const int block_n = wide ? 256 : 128;
+    // 256 x 256 pair tiles once there are enough of them to fill the 74 CTA pairs (encoder-sized M)
+    const bool pair = N >= 256 && M >= 256 &&
+                      (static_cast<int64_t>((M + 255) / 256) * ((N + 255) / 256) >= abh::num_sms() / 2);
+    const int block_n = (wide || pair) ? 256 : 128;
+    const int b_box_rows = pair ? 128 : block_n;
     CUtensorMap ta, tb;
     int rc = abh::make_tmap_2d_16bit(&ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K),
                                      static_cast<uint64_t>(lda), BLOCK_M, BLOCK_K, is_bf16 != 0);
     if (rc) return rc;
     rc = abh::make_tmap_2d_16bit(&tb, W, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldw),
-                                 static_cast<uint32_t>(block_n), BLOCK_K, is_bf16 != 0);
+                                 static_cast<uint32_t>(b_box_rows), BLOCK_K, is_bf16 != 0);
     if (rc) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (is_bf16) return wide ? launch<true, 256>(ta, tb, p, s) : launch<true, 128>(ta, tb, p, s);
-    return wide ? launch<false, 256>(ta, tb, p, s) : launch<false, 128>(ta, tb, p, s);
+    static const bool no_pair = getenv("ATLAS_B200_GEMM_NO_PAIR") != nullptr;   // A/B measurements
+    if (pair && !no_pair) return is_bf16 ? launch<true, 256, true>(ta, tb, p, s) : launch<false, 256, true>(ta, tb, p, s);
+    if (pair && no_pair) {   // the 1-CTA kernel needs the full-height W box
+        rc = abh::make_tmap_2d_16bit(&tb, W, static_cast<uint64_t>(N), static_cast<uint64_t>(K),
+                                     static_cast<uint64_t>(ldw), 256, BLOCK_K, is_bf16 != 0);
+        if (rc) return rc;
+        return is_bf16 ? launch<true, 256, false>(ta, tb, p, s) : launch<false, 256, false>(ta, tb, p, s);
+    }
+    if (is_bf16) return wide ? launch<true, 256, false>(ta, tb, p, s) : launch<true, 128, false>(ta, tb, p, s);
+    return wide ? launch<false, 256, false>(ta, tb, p, s) : launch<false, 128, false>(ta, tb, p, s);
 }
 
 }  // extern "C"

@@ -44,7 +44,8 @@ def _close(got, ref, dtype):
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (257, 768, 768), (1000, 3072, 768), (333, 768, 3072),
-                                   (4096, 2304, 768), (19200, 768, 768), (64, 32128, 768)])
+                                   (4096, 2304, 768), (19200, 768, 768), (64, 32128, 768),
+                                   (9999, 1032, 520)])   # 256 x 256 CTA-pair tiles with ragged M / N / K tails
 @pytest.mark.parametrize("epi", [0, 1, 2, 3])
 def test_linear_matches_fp32_reference(dev, dtype, M, N, K, epi):
     from atlas_b200 import ops
@@ -60,11 +61,12 @@ def test_linear_matches_fp32_reference(dev, dtype, M, N, K, epi):
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
-def test_gated_gelu_epilogue(dev, dtype):
+@pytest.mark.parametrize("M", [777, 5000])      # 1-CTA tiles / 2-CTA pair tiles
+def test_gated_gelu_epilogue(dev, dtype, M):
     from atlas_b200 import ops
 
     g = torch.Generator(device="cpu").manual_seed(5)
-    M, K, F = 777, 768, 2048
+    K, F = 768, 2048
     x = (torch.randn(M, K, generator=g) * 0.5).to(dtype).to(dev)
     w0 = (torch.randn(F, K, generator=g) / math.sqrt(K)).to(dtype)
     w1 = (torch.randn(F, K, generator=g) / math.sqrt(K)).to(dtype)
