@@ -15,13 +15,14 @@
 // exp / sum) with no online rescaling.  One CTA works on one (segment, head) at a time: K and V are loaded once
 // and reused by all of its 128-row query tiles.
 //
-// Roles (384 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-3 TMEM allocator + per-item mask / bias
-// tables (double buffered, one item ahead), warps 4-11 softmax + output (two threads per query row = TMEM lane).
+// Roles (608 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator + per-item mask / bias
+// tables (double buffered, one item ahead), warps 3-18 softmax + output (four threads per query row = TMEM lane).
 // With <= 384 keys the output of query tile t-1 is written while the tensor pipe runs P.V(t) and S(t+1).
 #include "common.cuh"
 #include "host_common.h"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace attn {
 
@@ -30,8 +31,13 @@ constexpr int BLOCK_Q = 128;
 constexpr int MAX_LK = 512;
 constexpr int SPLIT = 4;                       // softmax threads per query row (key chunks part, part+SPLIT, ...)
 constexpr int SM_THREADS = 128 * SPLIT;         // softmax / output threads (warps 4..), 4 warps per SM sub-partition
-constexpr int THREADS = 128 + SM_THREADS;
-constexpr int AUX_THREADS = 64;                 // warps 2, 3: per-item mask / bias tables, one item ahead
+constexpr int THREADS = 96 + SM_THREADS;           // 19 warps -> 104 registers per thread
+// attention_split_kernel: 2 softmax threads per query row, each keeping its <= 96 score columns of a key half in
+// registers between the two softmax passes (register files are allocated per 4 warps: 20 warps cap at 96 registers)
+constexpr int SPLIT2 = 2;
+constexpr int SM_THREADS2 = 128 * SPLIT2;
+constexpr int THREADS_SPLIT = 64 + SM_THREADS2;    // producer/aux warp, MMA warp, 8 softmax warps
+constexpr int AUX_THREADS = 32;                 // warp 2: per-item mask / bias tables, one item ahead
 constexpr int Q_BYTES = BLOCK_Q * D * 2;        // 16 KB, double buffered
 constexpr int KV_BYTES = MAX_LK * D * 2;        // 64 KB each
 constexpr int SMEM_BYTES = 2 * Q_BYTES + 2 * KV_BYTES + 1024;
@@ -89,6 +95,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     return ab::pack2_rn<kBF16>(a, b);
 }
 
+__device__ __forceinline__ void sm_bar2() { asm volatile("bar.sync 1, %0;" ::"n"(SM_THREADS2) : "memory"); }
 __device__ __forceinline__ void sm_bar() { asm volatile("bar.sync 1, %0;" ::"n"(SM_THREADS) : "memory"); }
 // the SPLIT warps that share query rows 32*lg .. 32*lg+31
 __device__ __forceinline__ void pair_bar(uint32_t lg) { asm volatile("bar.sync %0, %1;" ::"r"(2u + lg), "n"(32 * SPLIT) : "memory"); }
@@ -278,8 +285,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 }
             }
         }
-    } else if (warp < 4) {
-        // ===================== auxiliary warps 2, 3: mask / bias tables of the NEXT item =====================
+    } else if (warp == 2) {
+        // ===================== auxiliary warp 2: mask / bias tables of the NEXT item =====================
         const int tid = static_cast<int>(threadIdx.x) - 64;
         const bool has_bias = (p.bias_delta != nullptr) || (p.causal_value != 0.f);
         int item_it = 0;
@@ -287,10 +294,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             const int b = item / p.H, h = item % p.H;
             const int buf = item_it & 1;
             ab::mbar_wait(&aux_empty[buf], ((item_it >> 1) & 1) ^ 1u, 32);
+#pragma unroll 4
             for (int j = tid; j < lk_pad; j += AUX_THREADS)
                 s_mask[buf][j] = (j < p.Lk) ? (p.add_mask ? p.add_mask[static_cast<size_t>(b) * p.Lk + j] * LOG2E : 0.f)
                                             : -INFINITY;
             if (has_bias)
+#pragma unroll 4
                 for (int d = tid; d < 2 * MAX_LK; d += AUX_THREADS) {   // entries past the valid offsets stay finite (0)
                     float v = 0.f;
                     if (d < p.Lq + p.Lk - 1) {
@@ -304,7 +313,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     } else {
         // ===================== softmax + output: SPLIT threads per query row =====================
         const uint32_t lg = warp & 3u;
-        const uint32_t part = (warp - 4u) >> 2;                    // key chunks part, part+SPLIT, ...; O columns 16*part..
+        const uint32_t part = (warp - 3u) >> 2;                    // key chunks part, part+SPLIT, ...; O columns 16*part..
         const int row = static_cast<int>(lg * 32 + lane);
         const uint32_t lane_addr = tmem_base + ((lg * 32u) << 16);
         const float scale2 = p.scale * LOG2E;
@@ -432,6 +441,375 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// attention_split_kernel: the <= 384-key kernel.  Every 128-query tile is processed as TWO independent key halves
+// (a = keys [0, lk_pad/2), b = the rest), each with its own exact two-pass softmax (row max m_h, row sum l_h) and its
+// own un-normalised accumulator O_h = P_h.V_h; the halves are merged in registers when the tile's output is written:
+//     out = (w_a O_a + w_b O_b) / (w_a l_a + w_b l_b),   w_h = 2^(m_h - max(m_a, m_b))
+// (the split-KV identity, src/fid.py:298-349 semantics unchanged).  This makes the tensor pipe and the softmax warps
+// overlap: while the softmax warps work on half b of tile t the MMA warp runs P_a.V_a(t) and S_a(t+1), and vice versa.
+// TMEM columns: S_a [0, half) | S_b [half, 2*half) (P_h packed over the first half of S_h) | O_a 384 | O_b 448.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+                 "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+
+// pass 1 on one 16-key unit, in place: r <- t = S*scale2 + mask2[j] + bias2[j + boff]; returns the unit maximum
+template <bool kBias>
+__device__ __forceinline__ float unit_scores(uint32_t (&r)[16], float scale2, const float* mask2, const float* bias2,
+                                             int j0, int boff) {
+    float mx = -INFINITY;
+    const float4* m4 = reinterpret_cast<const float4*>(mask2 + j0);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float4 m = m4[q];
+        const float add[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int jj = 4 * q + e;
+            float a = add[e];
+            if (kBias) a += bias2[j0 + jj + boff];
+            const float t = fmaf(__uint_as_float(r[jj]), scale2, a);
+            r[jj] = __float_as_uint(t);
+            mx = fmaxf(mx, t);
+        }
+    }
+    return mx;
+}
+
+template <bool kBF16>
+__device__ __forceinline__ float unit_probs(const uint32_t (&r)[16], uint32_t (&pk)[8], float mx) {
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < 16; jj += 2) {
+        const float e0 = ex2_approx(__uint_as_float(r[jj]) - mx), e1 = ex2_approx(__uint_as_float(r[jj + 1]) - mx);
+        s0 += e0;
+        s1 += e1;
+        pk[jj >> 1] = pack2<kBF16>(e0, e1);
+    }
+    return s0 + s1;
+}
+
+template <bool kBF16>
+__global__ void __launch_bounds__(THREADS_SPLIT, 1)   // 10 warps (allocated as 12): up to 168 registers per thread
+attention_split_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                       const __grid_constant__ CUtensorMap tmap_v, const Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t k_full, k_empty, v_full, v_empty, q_full[2], q_empty[2];
+    __shared__ __align__(8) uint64_t s_full[2], p_ready[2], o_full[2], aux_full[2], aux_empty[2];
+    __shared__ uint32_t tmem_base_smem;
+    __shared__ float s_bias[2][2 * MAX_LK];
+    __shared__ __align__(16) float s_mask[2][MAX_LK];
+    __shared__ float s_red[SPLIT2][BLOCK_Q];
+    __shared__ float s_sum[SPLIT2][BLOCK_Q];
+    __shared__ float s_stat[2][4][BLOCK_Q];   // per tile parity: (m_a, l_a, m_b, l_b) of every row, kept until the output
+
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t smem_base = (ab::smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - ab::smem_u32(smem_raw));
+    uint8_t* sQ = smem_gen;
+    uint8_t* sK = smem_gen + 2 * Q_BYTES;
+    uint8_t* sV = sK + KV_BYTES;
+    const uint32_t aQ = smem_base, aK = smem_base + 2 * Q_BYTES, aV = aK + KV_BYTES;
+
+    const int n_chunks = (p.Lk + 127) / 128;
+    const int lk_pad = n_chunks * 128;          // <= 384 (host dispatch)
+    const int half = lk_pad / 2;                // keys per half: 64, 128 or 192
+    const int n_qt = (p.Lq + BLOCK_Q - 1) / BLOCK_Q;
+    const int n_items = p.B * p.H;
+    const int my_items = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    const int n_tiles = my_items * n_qt;        // 128-query tiles this CTA processes, in order (item-major)
+    constexpr uint32_t O_COL0 = 384;
+
+    if (warp == 0 && lane == 0) {
+        ab::tma_prefetch_desc(&tmap_q);
+        ab::tma_prefetch_desc(&tmap_k);
+        ab::tma_prefetch_desc(&tmap_v);
+    }
+    if (warp == 1 && lane == 0) {
+        ab::mbar_init(&k_full, 1);
+        ab::mbar_init(&k_empty, 1);
+        ab::mbar_init(&v_full, 1);
+        ab::mbar_init(&v_empty, 1);
+        for (int i = 0; i < 2; ++i) {
+            ab::mbar_init(&q_full[i], 1);
+            ab::mbar_init(&q_empty[i], 1);
+            ab::mbar_init(&s_full[i], 1);
+            ab::mbar_init(&p_ready[i], SM_THREADS2);
+            ab::mbar_init(&o_full[i], 1);
+            ab::mbar_init(&aux_full[i], AUX_THREADS);
+            ab::mbar_init(&aux_empty[i], SM_THREADS2);
+        }
+        ab::fence_barrier_init();
+    }
+    if (warp == 0) ab::tmem_alloc<1>(&tmem_base_smem, TMEM_COLS);
+    ab::tc_fence_before();
+    __syncthreads();
+    ab::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        // ===================== warp 0: mask / bias tables (all lanes) + TMA producer (lane 0), one item ahead ========
+        // The tables of item n+1 are filled BEFORE its loads are issued: the fill only waits for item n-1's softmax
+        // (aux_empty), while a Q load can wait on this item's own MMAs.
+        const bool has_bias = (p.bias_delta != nullptr) || (p.causal_value != 0.f);
+        const int tid = static_cast<int>(lane);
+        int item_it = 0, qt_it = 0;
+        const uint32_t kv_bytes = static_cast<uint32_t>(n_chunks * 128 * D * 2);
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_it) {
+            const int b = item / p.H, h = item % p.H;
+            const int buf = item_it & 1;
+            ab::mbar_wait(&aux_empty[buf], ((item_it >> 1) & 1) ^ 1u, 52);
+#pragma unroll 4
+            for (int j = tid; j < lk_pad; j += AUX_THREADS)
+                s_mask[buf][j] = (j < p.Lk) ? (p.add_mask ? p.add_mask[static_cast<size_t>(b) * p.Lk + j] * LOG2E : 0.f)
+                                            : -INFINITY;
+            if (has_bias) {
+#pragma unroll 4
+                for (int d = tid; d < 2 * MAX_LK; d += AUX_THREADS) {
+                    float v = 0.f;
+                    if (d < p.Lq + p.Lk - 1) {
+                        v = p.bias_delta ? p.bias_delta[static_cast<size_t>(h) * (p.Lq + p.Lk - 1) + d] : 0.f;
+                        if (p.causal_value != 0.f && d > p.Lq - 1) v += p.causal_value;   // j > i
+                    }
+                    s_bias[buf][d] = v * LOG2E;
+                }
+            }
+            ab::mbar_arrive(&aux_full[buf]);
+            if (lane == 0) {
+                auto load_q = [&](int qt) {
+                    const int qb = qt_it & 1;
+                    ab::mbar_wait(&q_empty[qb], ((qt_it >> 1) & 1) ^ 1u, 42);
+                    ab::mbar_arrive_expect_tx(&q_full[qb], Q_BYTES);
+                    ab::tma_load_2d(&tmap_q, &q_full[qb], sQ + qb * Q_BYTES, p.q_col0 + h * D,
+                                    (b / p.q_div) * p.Lq + qt * BLOCK_Q, ab::kEvictFirst);
+                    ++qt_it;
+                };
+                ab::mbar_wait(&k_empty, (item_it & 1) ^ 1u, 41);
+                ab::mbar_arrive_expect_tx(&k_full, kv_bytes);
+                for (int c = 0; c < n_chunks; ++c)
+                    ab::tma_load_2d(&tmap_k, &k_full, sK + c * (128 * D * 2), p.k_col0 + h * D, b * p.Lk + c * 128,
+                                    ab::kEvictNormal);
+                load_q(0);
+                ab::mbar_wait(&v_empty, (item_it & 1) ^ 1u, 49);
+                ab::mbar_arrive_expect_tx(&v_full, kv_bytes);
+                for (int c = 0; c < n_chunks; ++c)
+                    ab::tma_load_2d(&tmap_v, &v_full, sV + c * (128 * D * 2), p.v_col0 + h * D, b * p.Lk + c * 128,
+                                    ab::kEvictNormal);
+                for (int qt = 1; qt < n_qt; ++qt) load_q(qt);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer: P_a.V_a(t), S_a(t+1), P_b.V_b(t), S_b(t+1), ... =====================
+        if (lane == 0 && n_tiles > 0) {
+            const uint32_t idesc_s = ab::umma_idesc_f16(BLOCK_Q, half, kBF16);
+            constexpr uint32_t idesc_o = ab::umma_idesc_f16(BLOCK_Q, D, kBF16) | (1u << 16);   // B = V rows, MN-major
+            // S_h(g) = Q(g) . K_h^T  -> columns [h*half, h*half + half)
+            auto issue_s = [&](int hh, int g) {
+                const uint64_t qdesc = ab::umma_desc_k_sw128(aQ + (g & 1) * Q_BYTES);
+                const uint64_t kdesc = ab::umma_desc_k_sw128(aK + hh * half * (D * 2));
+#pragma unroll
+                for (int k = 0; k < D / 16; ++k)
+                    ab::umma_ss<1>(tmem_base + hh * half, qdesc + ((k * 32) >> 4), kdesc + ((k * 32) >> 4), idesc_s,
+                                   k != 0 ? 1u : 0u);
+            };
+            // O_h(g) = P_h . V_h : A = packed P in TMEM, B = V rows of this half
+            auto issue_pv = [&](int hh) {
+                const uint64_t vdesc = umma_desc_mn_sw128(aV + hh * half * (D * 2));
+                for (int k = 0; k < half / 16; ++k)
+                    ab::umma_ts<1>(tmem_base + O_COL0 + 64 * hh, tmem_base + hh * half + k * 8,
+                                   vdesc + static_cast<uint64_t>((k * 2048) >> 4), idesc_o, k != 0 ? 1u : 0u);
+            };
+            // prologue: both halves of tile 0
+            ab::mbar_wait(&k_full, 0, 43);
+            ab::mbar_wait(&q_full[0], 0, 44);
+            ab::tc_fence_after();
+            issue_s(0, 0);
+            ab::umma_commit(&s_full[0]);
+            issue_s(1, 0);
+            ab::umma_commit(&q_empty[0]);
+            if (n_qt == 1) ab::umma_commit(&k_empty);
+            ab::umma_commit(&s_full[1]);
+            for (int g = 0; g < n_tiles; ++g) {
+                const int item_it = g / n_qt, qt = g % n_qt;
+                const bool has_next = g + 1 < n_tiles;
+                const int nitem_it = (g + 1) / n_qt, nqt = (g + 1) % n_qt;
+                if (qt == 0) ab::mbar_wait(&v_full, item_it & 1, 50);
+                // ---- half a ----
+                ab::mbar_wait(&p_ready[0], g & 1, 46);
+                ab::tc_fence_after();
+                issue_pv(0);
+                ab::umma_commit(&o_full[0]);
+                if (has_next) {
+                    if (nqt == 0) ab::mbar_wait(&k_full, nitem_it & 1, 43);
+                    ab::mbar_wait(&q_full[(g + 1) & 1], ((g + 1) >> 1) & 1, 44);
+                    ab::mbar_wait(&o_full[0], g & 1, 51);     // P_a(g) consumed: its columns may take S_a(g+1)
+                    ab::tc_fence_after();
+                    issue_s(0, g + 1);
+                    ab::umma_commit(&s_full[0]);
+                }
+                // ---- half b ----
+                ab::mbar_wait(&p_ready[1], g & 1, 47);
+                ab::tc_fence_after();
+                issue_pv(1);
+                if (qt == n_qt - 1) ab::umma_commit(&v_empty);   // last use of this (segment, head)'s V
+                ab::umma_commit(&o_full[1]);
+                if (has_next) {
+                    ab::mbar_wait(&o_full[1], g & 1, 52);
+                    ab::tc_fence_after();
+                    issue_s(1, g + 1);
+                    ab::umma_commit(&q_empty[(g + 1) & 1]);
+                    if (nqt == n_qt - 1) ab::umma_commit(&k_empty);
+                    ab::umma_commit(&s_full[1]);
+                }
+            }
+        }
+    } else {
+        // ===================== softmax + output: SPLIT threads per query row =====================
+        const uint32_t lg = warp & 3u;
+        const uint32_t part = (warp - 2u) >> 2;
+        const int row = static_cast<int>(lg * 32 + lane);
+        const uint32_t lane_addr = tmem_base + ((lg * 32u) << 16);
+        const float scale2 = p.scale * LOG2E;
+        const bool has_bias = (p.bias_delta != nullptr) || (p.causal_value != 0.f);
+        constexpr int MAXU = 6;                                      // 16-key units per thread and half (half <= 192)
+        const int upp = half / 16 / SPLIT2;                          // 2, 4 or 6
+        constexpr int OC = D / SPLIT2;                               // 32 output columns per thread
+
+        // merge the two halves of a finished tile and write its rows
+        auto emit = [&](int gp) {
+            const int item = static_cast<int>(blockIdx.x) + (gp / n_qt) * static_cast<int>(gridDim.x);
+            const int b = item / p.H, h = item % p.H;
+            const int i = (gp % n_qt) * BLOCK_Q + row;
+            const float m0 = s_stat[gp & 1][0][row], l0 = s_stat[gp & 1][1][row];
+            const float m1 = s_stat[gp & 1][2][row], l1 = s_stat[gp & 1][3][row];
+            const float M = fmaxf(m0, m1);
+            const float w0 = ex2_approx(m0 - M), w1 = ex2_approx(m1 - M);
+            const float den = w0 * l0 + w1 * l1;
+            const bool partial = p.o_partial != nullptr;
+            const float c0 = partial ? w0 : w0 / den, c1 = partial ? w1 : w1 / den;
+#pragma unroll 1
+            for (int cc = 0; cc < OC / 16; ++cc) {          // 16 output columns at a time (register pressure)
+                const int col = static_cast<int>(part) * OC + cc * 16;
+                uint32_t ra[16], rb[16];
+                tmem_ld16(lane_addr + O_COL0 + col, ra);
+                tmem_ld16(lane_addr + O_COL0 + 64 + col, rb);
+                ab::tmem_ld_wait();
+                if (i >= p.Lq) continue;
+                float o[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) o[e] = c0 * __uint_as_float(ra[e]) + c1 * __uint_as_float(rb[e]);
+                if (partial) {
+                    float* dst = p.o_partial + (static_cast<size_t>(b) * p.Lq + i) * (static_cast<size_t>(p.H) * D) +
+                                 h * D + col;
+#pragma unroll
+                    for (int v4 = 0; v4 < 4; ++v4)
+                        reinterpret_cast<float4*>(dst)[v4] = make_float4(o[4 * v4], o[4 * v4 + 1], o[4 * v4 + 2], o[4 * v4 + 3]);
+                } else {
+                    uint4* dst = reinterpret_cast<uint4*>(p.O + (static_cast<size_t>(b) * p.Lq + i) * p.ldo + h * D + col);
+#pragma unroll
+                    for (int v4 = 0; v4 < 2; ++v4)
+                        dst[v4] = make_uint4(pack2<kBF16>(o[8 * v4], o[8 * v4 + 1]), pack2<kBF16>(o[8 * v4 + 2], o[8 * v4 + 3]),
+                                             pack2<kBF16>(o[8 * v4 + 4], o[8 * v4 + 5]), pack2<kBF16>(o[8 * v4 + 6], o[8 * v4 + 7]));
+                }
+            }
+            if (partial && part == 0 && i < p.Lq) {
+                float* ml = p.ml_partial + ((static_cast<size_t>(b) * p.Lq + i) * p.H + h) * 2;
+                ml[0] = M * (1.0f / LOG2E);
+                ml[1] = den;
+            }
+        };
+
+        int g = 0, item_it = 0;
+        bool pend = false;   // tile g-1 still has to be written out
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_it) {
+            const int buf = item_it & 1;
+            ab::mbar_wait(&aux_full[buf], (item_it >> 1) & 1, 53);
+            const float* mask2 = s_mask[buf];
+            const float* bias2 = s_bias[buf];
+            for (int qt = 0; qt < n_qt; ++qt, ++g) {
+                const int i = qt * BLOCK_Q + row;
+                const int boff = min(p.Lq - 1 - i, 2 * MAX_LK - 1 - lk_pad);
+                const int boffc = max(boff, 0);
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const uint32_t s_addr = lane_addr + static_cast<uint32_t>(hh * half);
+                    const int key0 = hh * half;
+                    ab::mbar_wait(&s_full[hh], g & 1, 47 + hh);
+                    ab::tc_fence_after();
+                    // ---- pass 1: this thread's (<= 48) score columns are read from TMEM ONCE and stay in registers ----
+                    uint32_t r[MAXU][16];
+#pragma unroll
+                    for (int k = 0; k < MAXU; ++k)
+                        if (k < upp) tmem_ld16(s_addr + (part + k * SPLIT2) * 16, r[k]);
+                    ab::tmem_ld_wait();
+                    float mx = -INFINITY;
+#pragma unroll
+                    for (int k = 0; k < MAXU; ++k)
+                        if (k < upp) {
+                            const int j0 = key0 + static_cast<int>(part + k * SPLIT2) * 16;
+                            mx = fmaxf(mx, has_bias ? unit_scores<true>(r[k], scale2, mask2, bias2, j0, boffc)
+                                                    : unit_scores<false>(r[k], scale2, mask2, bias2, j0, boffc));
+                        }
+                    if (hh == 1 && qt == n_qt - 1) ab::mbar_arrive(&aux_empty[buf]);   // last read of the tables
+                    s_red[part][row] = mx;
+                    sm_bar2();   // also: every thread has finished LOADING S_h, so P may overwrite its columns
+#pragma unroll
+                    for (int q = 0; q < SPLIT2; ++q) mx = fmaxf(mx, s_red[q][row]);
+                    const float mx_use = (mx == -INFINITY) ? 0.f : mx;      // a half made of padding keys only: P = 0
+                    // ---- pass 2: p = 2^(t - max) from registers, packed P over the first half of S_h ----
+                    float sum = 0.f;
+#pragma unroll
+                    for (int k = 0; k < MAXU; ++k)
+                        if (k < upp) {
+                            uint32_t pk[8];
+                            sum += unit_probs<kBF16>(r[k], pk, mx_use);
+                            tmem_st8(s_addr + (part + k * SPLIT2) * 8, pk);
+                        }
+                    s_sum[part][row] = sum;
+                    ab::tmem_st_wait();
+                    if (hh == 0 && pend) {
+                        // O_a(g-1) retired before S_a(g) was issued; O_b(g-1) has its own barrier
+                        ab::mbar_wait(&o_full[1], (g - 1) & 1, 54);
+                        ab::tc_fence_after();
+                        emit(g - 1);
+                        pend = false;
+                    }
+                    ab::tc_fence_before();
+                    sm_bar2();
+                    ab::mbar_arrive(&p_ready[hh]);
+                    sum = 0.f;
+#pragma unroll
+                    for (int q = 0; q < SPLIT2; ++q) sum += s_sum[q][row];
+                    if (part == 0) {
+                        s_stat[g & 1][2 * hh][row] = mx;
+                        s_stat[g & 1][2 * hh + 1][row] = sum;
+                    }
+                }
+                pend = true;
+            }
+        }
+        if (pend) {
+            sm_bar2();   // the last tile's row statistics (written by the part-0 threads) are visible
+            ab::mbar_wait(&o_full[0], (g - 1) & 1, 55);
+            ab::mbar_wait(&o_full[1], (g - 1) & 1, 56);
+            ab::tc_fence_after();
+            emit(g - 1);
+        }
+    }
+
+    ab::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        ab::tc_fence_after();
+        ab::tmem_dealloc<1>(tmem_base, TMEM_COLS);
+    }
+}
+
 // out[b, i, h, :] = sum_s w_s O_s / sum_s w_s l_s with w_s = exp(m_s - max_s m_s); one warp per (b, i, h)
 template <bool kBF16>
 __global__ void combine_splits_kernel(const float* __restrict__ o_partial, const float* __restrict__ ml, int B, int splits,
@@ -506,25 +884,25 @@ int atlas_b200_attention(const void* q, int64_t ldq, int32_t q_col0, const void*
     p.o_partial = o_partial;
     p.ml_partial = ml_partial;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    static bool attr_set[2] = {false, false};
     const int items = B * H;
     const int grid = items < abh::num_sms() ? items : abh::num_sms();
     abh::prof_begin(s, abh::PROF_ATTENTION);
-    if (is_bf16) {
-        if (!attr_set[1]) {
-            AB_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               SMEM_BYTES));
-            attr_set[1] = true;
+    static const bool no_split = getenv("ATLAS_B200_ATTN_NO_SPLIT") != nullptr;   // A/B measurements
+    const bool split = ((Lk + 127) / 128) * 128 <= 384 && !no_split;
+    const int threads = split ? THREADS_SPLIT : THREADS;
+    auto launch = [&](auto kernel, bool& attr_done) -> int {
+        if (!attr_done) {
+            AB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+            attr_done = true;
         }
-        attention_kernel<true><<<grid, THREADS, SMEM_BYTES, s>>>(tq, tk, tv, p);
-    } else {
-        if (!attr_set[0]) {
-            AB_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               SMEM_BYTES));
-            attr_set[0] = true;
-        }
-        attention_kernel<false><<<grid, THREADS, SMEM_BYTES, s>>>(tq, tk, tv, p);
-    }
+        kernel<<<grid, threads, SMEM_BYTES, s>>>(tq, tk, tv, p);
+        return ATLAS_B200_OK;
+    };
+    static bool attr_set[4] = {false, false, false, false};
+    int lrc;
+    if (split) lrc = is_bf16 ? launch(attention_split_kernel<true>, attr_set[0]) : launch(attention_split_kernel<false>, attr_set[1]);
+    else lrc = is_bf16 ? launch(attention_kernel<true>, attr_set[2]) : launch(attention_kernel<false>, attr_set[3]);
+    if (lrc) return lrc;
     abh::prof_end(s, abh::PROF_ATTENTION, 4.0 * B * H * static_cast<double>(Lq) * Lk * D);
     abh::count_launch();
     AB_CUDA_CHECK(cudaGetLastError());
