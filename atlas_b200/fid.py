@@ -191,6 +191,13 @@ class FiD(nn.Module):
         self.cuda_graphs = os.environ.get("ATLAS_B200_CUDA_GRAPH", "1") != "0"
         self._graphs = {}
 
+    @classmethod
+    def from_pretrained(cls, path, **kw):
+        """Local HF-layout directory (config.json + weights) of a T5 v1.1 checkpoint, src/model_io.py:77."""
+        from ._pretrained import load_pretrained
+
+        return load_pretrained(cls, T5ConfigLite, path, **kw)
+
     # ---- reference surface that is configuration only -------------------------------------
     def set_checkpoint(self, use_checkpoint):
         pass

@@ -152,6 +152,13 @@ class Contriever(nn.Module):
             if m.padding_idx is not None:
                 m.weight.data[m.padding_idx].zero_()
 
+    @classmethod
+    def from_pretrained(cls, path, **kw):
+        """Local HF-layout directory (config.json + weights), src/model_io.py:45."""
+        from ._pretrained import load_pretrained
+
+        return load_pretrained(cls, BertConfigLite, path, **kw)
+
     def gradient_checkpointing_enable(self):
         pass
 
