@@ -39,6 +39,37 @@ __device__ __forceinline__ float rf(float v) {  // round through the 16-bit type
     return __half2float(__float2half_rn(v));
 }
 
+template <bool kBF16>
+__device__ __forceinline__ uint32_t pack2_rn(float a, float b) {   // lo = a, hi = b
+    uint32_t d;
+    if constexpr (kBF16) {
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+    } else {
+        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+    }
+    return d;
+}
+template <bool kBF16>
+__device__ __forceinline__ uint32_t mul2(uint32_t a, uint32_t b) {
+    uint32_t d;
+    if constexpr (kBF16) {
+        asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    } else {
+        asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    }
+    return d;
+}
+template <bool kBF16>
+__device__ __forceinline__ uint32_t add2(uint32_t a, uint32_t b) {
+    uint32_t d;
+    if constexpr (kBF16) {
+        asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    } else {
+        asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    }
+    return d;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -76,15 +107,13 @@ __device__ __forceinline__ void norm_row(float (&v)[MAXV][8], int nvec, int H, f
             uint32_t o[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const float n0 = rf<kBF16>((v[i][2 * e] - mean) * rstd);
-                const float n1 = rf<kBF16>((v[i][2 * e + 1] - mean) * rstd);
-                float y0 = rf<kBF16>(lo<kBF16>(ww[e]) * n0);
-                float y1 = rf<kBF16>(hi<kBF16>(ww[e]) * n1);
-                if (kBias) {
-                    y0 = y0 + lo<kBF16>(bb[e]);
-                    y1 = y1 + hi<kBF16>(bb[e]);
-                }
-                o[e] = rnd<kBF16>(y0) | (rnd<kBF16>(y1) << 16);
+                // r16(norm) for two elements with one packed conversion (F2FP, ALU pipe), then the 16-bit multiply /
+                // add of the reference's half kernels as native x2 instructions (products of two 16-bit values are
+                // exact in fp32, so HMUL2's single rounding equals round16(fp32 product))
+                const uint32_t n2 = pack2_rn<kBF16>((v[i][2 * e] - mean) * rstd, (v[i][2 * e + 1] - mean) * rstd);
+                uint32_t y2 = mul2<kBF16>(ww[e], n2);
+                if (kBias) y2 = add2<kBF16>(y2, bb[e]);
+                o[e] = y2;
             }
             reinterpret_cast<uint4*>(y)[vec] = make_uint4(o[0], o[1], o[2], o[3]);
         }

@@ -308,7 +308,10 @@ class FiD(nn.Module):
         B, T = decoder_input_ids.shape
         d, H = c.d_model, c.num_heads
         Lk = enc.shape[1]
-        split = next(s for s in range(min(512, Lk), 0, -1) if Lk % s == 0)   # largest divisor of Lk that fits TMEM
+        # key segments of the split-KV cross-attention: the largest divisor of Lk up to 384 keys (the two-half kernel,
+        # attention_split_kernel), else up to 512 (single-accumulator kernel)
+        split = next((s for s in range(min(384, Lk), 63, -1) if Lk % s == 0), None) or \
+            next(s for s in range(min(512, Lk), 0, -1) if Lk % s == 0)
         if split < 64 and Lk > 512:
             raise AtlasB200Error(f"n_context*text_maxlength = {Lk} has no divisor in [64, 512] for the split-KV kernel")
         if cross_kv is None:

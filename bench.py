@@ -46,6 +46,9 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=N_LOCAL, help="passages per GPU (default: the BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="run warm-up + the timed steps inside an NVTX range 'atlas_b200_timed' and exit (for ncu "
+                         "--nvtx --nvtx-include 'atlas_b200_timed/'; no JSON line is printed)")
     return ap.parse_args()
 
 
@@ -299,11 +302,17 @@ def run_ours(args):
     barrier_sync()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
+        torch.cuda.nvtx.range_push("atlas_b200_timed")
         e0.record()
         for _ in range(args.steps):
             loss, gids, _ = step(False)
         e1.record()
         barrier_sync()
+        torch.cuda.nvtx.range_pop()
+    if args.profile_step:
+        if world > 1:
+            dist.destroy_process_group()
+        return
     total_ms = max_over_ranks(e0.elapsed_time(e1))
     launches_eager = None
     ms_per_step = total_ms / args.steps

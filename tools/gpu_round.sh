@@ -1,13 +1,14 @@
 #!/bin/bash
-# One GPU visit: parity tests, smoke, bench, ncu launch list + full capture of the scan kernel.
+# One GPU visit for the round's evidence: launch list of one bench step + full captures of the dominant kernels.
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -15
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
-python bench.py --steps 20 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 3000 gpurun_out/bench.json; tail -3 gpurun_out/bench.err
-if [ "$1" != "noprof" ]; then
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'mips_|topk_merge|cast_f32|widen' -c 40 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1
-tail -25 gpurun_out/launches.csv
-ncu --set full --clock-control none --import-source on -k regex:mips_scan -s 2 -c 2 -o gpurun_out/prof_scan -f python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
-tail -3 gpurun_out/ncu_full.log
+# (1) launch list (per-kernel gpu__time_duration, serialised / cold-cache: shares, not absolutes); eager launches so that
+#     every kernel of the step appears as its own row
+ATLAS_B200_CUDA_GRAPH=0 ncu --metrics gpu__time_duration.sum --clock-control none --nvtx --nvtx-include "atlas_b200_timed/" \
+    --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --profile-step > gpurun_out/ncu_launch.log 2>&1
+tail -2 gpurun_out/ncu_launch.log | cut -c1-300
+wc -l gpurun_out/launches.csv
+# (2) full capture of the CTA-pair GEMM
+ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 2 -c 1 -o gpurun_out/prof_gemm2 -f \
+    python tools/prof_ops.py gemm 3 > gpurun_out/ncu_gemm.log 2>&1
+tail -2 gpurun_out/ncu_gemm.log
 ls -la gpurun_out
-fi
