@@ -64,6 +64,14 @@ struct Params {
     const uint16_t* bias;      // [N] 16-bit or nullptr
     const uint16_t* residual;  // [M, ldr] 16-bit or nullptr
     uint16_t* C;
+    // fused T5 RMSNorm (src/modeling_t5.py:244-253) around the GEMM:
+    //   row_ss  [M] fp32 sum of squares of the A rows (or nullptr): acc[m, :] *= rsqrt(row_ss[m] / K + rs_eps) before the
+    //           epilogue, i.e. the GEMM consumes the UN-normalised rows with the norm weight folded into W
+    //   out_ss  [M] fp32 (or nullptr): += sum over this launch's columns of (16-bit rounded output)^2, the statistic the
+    //           next RMSNorm needs, accumulated with one atomicAdd per thread and tile
+    const float* row_ss;
+    float* out_ss;
+    float rs_eps;
 };
 
 template <bool kBF16>
@@ -76,7 +84,22 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     return ab::pack2_rn<kBF16>(a, b);
 }
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// erf-GELU (ACT2FN["gelu"]): 0.5 x (1 + erf(x / sqrt 2)).  erf by Abramowitz-Stegun 7.1.26 (|abs error| <= 1.5e-7, i.e.
+// fp32-level on 1 + erf): t = 1 / (1 + p|z|), erf|z| = 1 - (a1 t + ... + a5 t^5) e^(-z^2) -- one MUFU.RCP, one MUFU.EX2 and
+// six FMAs instead of erff's ~25-instruction two-branch polynomial (the 128 x 256 GELU epilogue was as long as the MMAs).
+__device__ __forceinline__ float gelu_erf(float x) {
+    const float z = fabsf(x) * 0.70710678118654752f;
+    float t, e;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z * z));
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float erfc_abs = poly * t * e;                       // 1 - erf(|z|)
+    const float one_plus_erf = x >= 0.f ? 2.0f - erfc_abs : erfc_abs;
+    return 0.5f * x * one_plus_erf;
+}
 // transformers' "gelu_new": 0.5*x*(1+tanh(sqrt(2/pi)*(x+0.044715*x^3)))
 // = x * sigmoid(2u), u = sqrt(2/pi) (x + 0.044715 x^3): 1 + tanh(u) = 2 / (1 + e^(-2u)).  One MUFU.EX2 and one
 // MUFU.RCP (both ~1e-7 relative) instead of tanhf's ~30-instruction path: the 128 x 256 gated epilogue (16 k GELUs
@@ -217,6 +240,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             const uint32_t buf = it & 1;
             const int m_blk = t / num_n, n_blk = t % num_n;
             const int row = m_blk * TILE_M + static_cast<int>(cta_rank) * BLOCK_M + static_cast<int>(lg * 32 + lane);
+            // fused RMSNorm of the A rows: a per-row scale of the accumulator (loaded while the MMAs run)
+            const float rscale = (p.row_ss != nullptr && row < p.M)
+                                     ? rsqrtf(__ldg(p.row_ss + row) / static_cast<float>(p.K) + p.rs_eps) : 1.0f;
+            float ss_out = 0.f;
             ab::mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1, 14);
             ab::tc_fence_after();
 #pragma unroll 1
@@ -238,7 +265,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 if (row >= p.M || col0 >= p.N) continue;
                 float v[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * rscale;
                 if (p.epi != EPI_NONE && p.epi != EPI_GATED && p.bias != nullptr) {
 #pragma unroll
                     for (int j8 = 0; j8 < 4; ++j8) {
@@ -288,13 +315,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 #pragma unroll
                     for (int j8 = 0; j8 < 4; ++j8) {
                         if (col0 + j8 * 8 < p.N) {
-                            *reinterpret_cast<uint4*>(crow + j8 * 8) = make_uint4(
+                            const uint4 o = make_uint4(
                                 pack2<kBF16>(v[j8 * 8 + 0], v[j8 * 8 + 1]), pack2<kBF16>(v[j8 * 8 + 2], v[j8 * 8 + 3]),
                                 pack2<kBF16>(v[j8 * 8 + 4], v[j8 * 8 + 5]), pack2<kBF16>(v[j8 * 8 + 6], v[j8 * 8 + 7]));
+                            *reinterpret_cast<uint4*>(crow + j8 * 8) = o;
+                            if (p.out_ss != nullptr) {   // squares of the values as STORED (what a separate norm would read)
+                                const uint32_t w[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float a = to_f32<kBF16>(static_cast<uint16_t>(w[e] & 0xFFFFu));
+                                    const float b = to_f32<kBF16>(static_cast<uint16_t>(w[e] >> 16));
+                                    ss_out = fmaf(a, a, fmaf(b, b, ss_out));
+                                }
+                            }
                         }
                     }
                 }
             }
+            if (p.out_ss != nullptr && row < p.M) atomicAdd(p.out_ss + row, ss_out);
         }
     }
 
@@ -351,9 +389,20 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
 
 extern "C" {
 
+int atlas_b200_linear_ex(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, const void* residual,
+                         int64_t ldr, void* C, int64_t ldc, int32_t M, int32_t N, int32_t K, int32_t epilogue,
+                         int32_t is_bf16, const float* row_ss, float* out_ss, float rs_eps, void* stream);
+
 int atlas_b200_linear(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, const void* residual,
                       int64_t ldr, void* C, int64_t ldc, int32_t M, int32_t N, int32_t K, int32_t epilogue,
                       int32_t is_bf16, void* stream) {
+    return atlas_b200_linear_ex(A, lda, W, ldw, bias, residual, ldr, C, ldc, M, N, K, epilogue, is_bf16, nullptr, nullptr,
+                                0.f, stream);
+}
+
+int atlas_b200_linear_ex(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, const void* residual,
+                         int64_t ldr, void* C, int64_t ldc, int32_t M, int32_t N, int32_t K, int32_t epilogue,
+                         int32_t is_bf16, const float* row_ss, float* out_ss, float rs_eps, void* stream) {
     using namespace gemm;
     AB_REQUIRE(M >= 0 && N > 0 && K > 0, "bad GEMM shape M=%d N=%d K=%d", M, N, K);
     if (M == 0) return ATLAS_B200_OK;
@@ -363,7 +412,11 @@ int atlas_b200_linear(const void* A, int64_t lda, const void* W, int64_t ldw, co
     AB_REQUIRE(epilogue != EPI_RESIDUAL || (residual != nullptr && ldr % 8 == 0), "EPI_RESIDUAL needs a residual");
     AB_REQUIRE(epilogue != EPI_GATED || N % 32 == 0, "EPI_GATED needs N %% 32 == 0");
     AB_REQUIRE((reinterpret_cast<uintptr_t>(C) & 15u) == 0, "C must be 16-byte aligned");
+    AB_REQUIRE(out_ss == nullptr || epilogue != EPI_GATED, "out_ss is not available with the gated epilogue");
     Params p;
+    p.row_ss = row_ss;
+    p.out_ss = out_ss;
+    p.rs_eps = rs_eps;
     p.M = M;
     p.N = N;
     p.K = K;

@@ -189,6 +189,7 @@ class FiD(nn.Module):
         # CUDA-graph replay of the static-shape forward (eval / scoring); ATLAS_B200_CUDA_GRAPH=0 or
         # `model.cuda_graphs = False` runs every kernel launch eagerly (needed under profilers' event bracketing)
         self.cuda_graphs = os.environ.get("ATLAS_B200_CUDA_GRAPH", "1") != "0"
+        self.fuse_norm = os.environ.get("ATLAS_B200_FUSE_NORM", "1") != "0"   # RMSNorm folded into the encoder GEMMs
         self._graphs = {}
 
     @classmethod
@@ -253,6 +254,15 @@ class FiD(nn.Module):
                     [W[name], W[name.replace("q.weight", "k.weight")], W[name.replace("q.weight", "v.weight")]], 0)
             elif name.endswith("EncDecAttention.k.weight"):
                 g[name.replace("k.weight", "kv")] = torch.cat([W[name], W[name.replace("k.weight", "v.weight")]], 0)
+        # encoder projections with the preceding RMSNorm weight folded in (W'[n, k] = W[n, k] * ln[k]) for the fused norm
+        for name in [n for n in g if n.startswith("encoder.")]:
+            if name.endswith("SelfAttention.qkv"):
+                ln = W[name.replace("SelfAttention.qkv", "layer_norm.weight")]
+            elif name.endswith("DenseReluDense.wi_01"):
+                ln = W[name.replace("DenseReluDense.wi_01", "layer_norm.weight")]
+            else:
+                continue
+            g[name + "_n"] = (g[name].float() * ln.float()[None, :]).to(g[name].dtype).contiguous()
         return g
 
     # ---- encoder ---------------------------------------------------------------------------
@@ -276,14 +286,37 @@ class FiD(nn.Module):
         bias = bias_by_delta(W["encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight"], L, L, True,
                              c.relative_attention_num_buckets)
         qkv = torch.empty((S * L, 3 * H * 64), dtype=dt, device=h.device)
-        for i in range(c.num_layers):
-            p = f"encoder.block.{i}.layer.0."
-            n = ops.layernorm(h, W[p + "layer_norm.weight"], None, c.layer_norm_epsilon, kind=1)
-            ops.linear(n, G[p + "SelfAttention.qkv"], out=qkv)
-            ctx = ops.attention(qkv, 0, qkv, H * 64, qkv, 2 * H * 64, S, H, L, L, add_mask=add_mask, bias_delta=bias,
-                                scale=1.0)
-            h = ops.linear(ctx, W[p + "SelfAttention.o.weight"], None, residual=h, epilogue=ops.EPI_RESIDUAL)
-            h = self._ff(W, G, f"encoder.block.{i}.layer.1.", h, c.layer_norm_epsilon)
+        eps = c.layer_norm_epsilon
+        if self.fuse_norm:
+            # RMSNorm fused around the GEMMs (atlas_b200_linear_ex): the residual GEMMs emit each row's sum of squares,
+            # the consuming projection reads the UN-normalised hidden state with the norm weight folded into its matrix
+            # and scales its accumulator rows by rsqrt(ss / d + eps).  Only the very first and the final norm run as
+            # kernels; 2 x num_layers normalised [tokens, d] tensors are never written or read.
+            ss = torch.zeros((2 * c.num_layers, S * L), dtype=torch.float32, device=h.device)
+            for i in range(c.num_layers):
+                p = f"encoder.block.{i}.layer.0."
+                if i == 0:
+                    n = ops.layernorm(h, W[p + "layer_norm.weight"], None, eps, kind=1)
+                    ops.linear(n, G[p + "SelfAttention.qkv"], out=qkv)
+                else:
+                    ops.linear(h, G[p + "SelfAttention.qkv_n"], out=qkv, row_ss=ss[2 * i - 1], rs_eps=eps)
+                ctx = ops.attention(qkv, 0, qkv, H * 64, qkv, 2 * H * 64, S, H, L, L, add_mask=add_mask, bias_delta=bias,
+                                    scale=1.0)
+                h = ops.linear(ctx, W[p + "SelfAttention.o.weight"], None, residual=h, epilogue=ops.EPI_RESIDUAL,
+                               out_ss=ss[2 * i])
+                p = f"encoder.block.{i}.layer.1."
+                g = ops.linear(h, G[p + "DenseReluDense.wi_01_n"], epilogue=ops.EPI_GATED, row_ss=ss[2 * i], rs_eps=eps)
+                h = ops.linear(g, W[p + "DenseReluDense.wo.weight"], None, residual=h, epilogue=ops.EPI_RESIDUAL,
+                               out_ss=ss[2 * i + 1])
+        else:
+            for i in range(c.num_layers):
+                p = f"encoder.block.{i}.layer.0."
+                n = ops.layernorm(h, W[p + "layer_norm.weight"], None, eps, kind=1)
+                ops.linear(n, G[p + "SelfAttention.qkv"], out=qkv)
+                ctx = ops.attention(qkv, 0, qkv, H * 64, qkv, 2 * H * 64, S, H, L, L, add_mask=add_mask, bias_delta=bias,
+                                    scale=1.0)
+                h = ops.linear(ctx, W[p + "SelfAttention.o.weight"], None, residual=h, epilogue=ops.EPI_RESIDUAL)
+                h = self._ff(W, G, f"encoder.block.{i}.layer.1.", h, eps)
         h = ops.layernorm(h, W["encoder.final_layer_norm.weight"], None, c.layer_norm_epsilon, kind=1)
         return h.view(bsz, -1, d)
 
@@ -350,7 +383,8 @@ class FiD(nn.Module):
             return fn(*inputs)
         self._weights()                                      # make sure the 16-bit weight copies exist / are current
         dt = self._dtype()
-        key = (tag, dt, self._half.sets[dt]["key"], tuple((tuple(t.shape), t.dtype, t.device) for t in inputs))
+        key = (tag, dt, self.fuse_norm, self._half.sets[dt]["key"],
+               tuple((tuple(t.shape), t.dtype, t.device) for t in inputs))
         runner = self._graphs.get(key)
         if runner is None:
             if len(self._graphs) >= 8:                       # shapes changed often: drop the oldest graph + its pool

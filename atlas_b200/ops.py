@@ -154,11 +154,14 @@ def topk_merge_blob(blob_all, ids_off, world, nq_total, k, q_begin, nq_out, dtyp
 EPI_NONE, EPI_BIAS, EPI_GELU, EPI_RESIDUAL, EPI_GATED = 0, 1, 2, 3, 4
 
 
-def linear(x, weight, bias=None, residual=None, epilogue=None, out=None):
+def linear(x, weight, bias=None, residual=None, epilogue=None, out=None, row_ss=None, out_ss=None, rs_eps=1e-6):
     """y = epilogue(x @ weight.T) on tcgen05.  x [..., K], weight [N, K] (nn.Linear layout), 16-bit.
 
     epilogue: EPI_NONE / EPI_BIAS / EPI_GELU / EPI_RESIDUAL / EPI_GATED (see include/atlas_b200.h);
-    default: EPI_RESIDUAL if `residual` is given, else EPI_BIAS if `bias` is given, else EPI_NONE."""
+    default: EPI_RESIDUAL if `residual` is given, else EPI_BIAS if `bias` is given, else EPI_NONE.
+    Fused T5 RMSNorm (atlas_b200_linear_ex): `row_ss` fp32 [M] = sum of squares of the rows of x -> accumulator rows are
+    scaled by rsqrt(row_ss / K + rs_eps) (x is the UN-normalised hidden state, the norm weight is folded into `weight`);
+    `out_ss` fp32 [M] (pre-zeroed) receives the sum of squares of the stored output rows."""
     require_cuda(x, "x")
     if x.dtype not in (torch.float16, torch.bfloat16) or weight.dtype != x.dtype:
         raise AtlasB200Error(f"linear: x and weight must both be fp16 or bf16 (got {x.dtype}, {weight.dtype})")
@@ -181,10 +184,14 @@ def linear(x, weight, bias=None, residual=None, epilogue=None, out=None):
         r2 = residual.reshape(-1, residual.shape[-1])
         if r2.stride(-1) != 1:
             r2 = r2.contiguous()
-    check(lib().atlas_b200_linear(
+    for t in (row_ss, out_ss):
+        if t is not None and (t.dtype != torch.float32 or t.numel() != M or not t.is_contiguous() or not t.is_cuda):
+            raise AtlasB200Error("linear: row_ss / out_ss must be contiguous CUDA fp32 tensors with one element per row")
+    check(lib().atlas_b200_linear_ex(
         _ptr(x2), x2.stride(0), _ptr(w), w.stride(0), _ptr(bias) if bias is not None else None,
         _ptr(r2) if r2 is not None else None, r2.stride(0) if r2 is not None else 0, _ptr(out), out.stride(0),
-        M, N, K, epilogue, 1 if x.dtype == torch.bfloat16 else 0, current_stream_ptr()))
+        M, N, K, epilogue, 1 if x.dtype == torch.bfloat16 else 0, _ptr(row_ss) if row_ss is not None else None,
+        _ptr(out_ss) if out_ss is not None else None, float(rs_eps), current_stream_ptr()))
     return out.reshape(*x.shape[:-1], n_out)
 
 

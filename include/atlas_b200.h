@@ -123,6 +123,18 @@ int atlas_b200_linear(const void* A, int64_t lda, const void* W, int64_t ldw, co
                       const void* residual, int64_t ldr, void* C, int64_t ldc,
                       int32_t M, int32_t N, int32_t K, int32_t epilogue, int32_t is_bf16, void* stream);
 
+/* atlas_b200_linear with T5's RMSNorm (src/modeling_t5.py:244-253) fused around it, so the normalised activations never
+ * exist in memory:
+ *   row_ss  device fp32 [M] = sum of squares of every A row, or NULL.  The accumulator row m is multiplied by
+ *           rsqrt(row_ss[m] / K + rs_eps) before the epilogue: A holds the UN-normalised hidden states and the caller
+ *           folds the norm weight into W (W'[n, k] = W[n, k] * ln_weight[k]).
+ *   out_ss  device fp32 [M] or NULL (not with the gated epilogue): incremented by the sum of squares of the 16-bit values
+ *           this launch stores in each row (zero it first) - the statistic of the NEXT norm, produced by the residual GEMM. */
+int atlas_b200_linear_ex(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias,
+                         const void* residual, int64_t ldr, void* C, int64_t ldc, int32_t M, int32_t N, int32_t K,
+                         int32_t epilogue, int32_t is_bf16, const float* row_ss, float* out_ss, float rs_eps,
+                         void* stream);
+
 /* Row-wise normalisation of 16-bit activations (csrc/elementwise.cu), one rounding point per torch op:
  *   kind 0  BertLayerNorm (src/modeling_bert.py:104-114): y = w * r16((x - mean) * rsqrt(mean(x^2) + eps)) + b
  *           — note the UNCENTRED second moment; callers pass the residual sum already rounded to 16 bits.

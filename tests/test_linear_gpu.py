@@ -100,3 +100,37 @@ def test_strided_input_and_output_view(dev):
     ops.linear(x, w, out=out[:, 768:])
     ok, err = _close(out[:, 768:], x.float() @ w.float().T, torch.float16)
     assert ok and float(out[:, :768].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("M", [300, 6000])      # 1-CTA tiles / 2-CTA pair tiles
+def test_fused_rmsnorm_around_the_gemm(dev, dtype, M):
+    """atlas_b200_linear_ex: (a) `out_ss` = sum of squares of the stored residual output rows, (b) `row_ss` scales the
+    accumulator rows by rsqrt(ss / K + eps) - together T5's RMSNorm (src/modeling_t5.py:244-253) with the norm weight
+    folded into the consumer's matrix.  Reference: fp32 torch of the same folded computation, and the un-fused
+    layernorm + linear path of this library (same result up to the 16-bit rounding of the normalised activations)."""
+    from atlas_b200 import ops
+
+    g = torch.Generator(device="cpu").manual_seed(11 + M)
+    d, F = 768, 1024
+    ctx = (torch.randn(M, d, generator=g) * 0.5).to(dtype).to(dev)
+    wo = (torch.randn(d, d, generator=g) / math.sqrt(d)).to(dtype).to(dev)
+    res = (torch.randn(M, d, generator=g) * 3.0).to(dtype).to(dev)
+    ln = (1.0 + 0.1 * torch.randn(d, generator=g)).to(dtype).to(dev)
+    wi = (torch.randn(F, d, generator=g) / math.sqrt(d)).to(dtype).to(dev)
+    eps = 1e-6
+    ss = torch.zeros(M, dtype=torch.float32, device=dev)
+    h = ops.linear(ctx, wo, None, residual=res, epilogue=ops.EPI_RESIDUAL, out_ss=ss)
+    h_plain = ops.linear(ctx, wo, None, residual=res, epilogue=ops.EPI_RESIDUAL)
+    assert torch.equal(h, h_plain)
+    ss_ref = h.float().pow(2).sum(-1)
+    assert torch.allclose(ss, ss_ref, rtol=2e-5, atol=1e-4), float((ss - ss_ref).abs().max())
+    wi_n = (wi.float() * ln.float()[None, :]).to(dtype)
+    y = ops.linear(h, wi_n, row_ss=ss, rs_eps=eps)
+    ref = (h.float() @ wi_n.float().T) * torch.rsqrt(ss_ref / d + eps)[:, None]
+    ok, err = _close(y, ref, dtype)
+    assert ok, f"max abs err {err}"
+    # against the un-fused path (normalised activations rounded to 16 bits in between): same up to that rounding
+    y2 = ops.linear(ops.layernorm(h, ln, None, eps, kind=1), wi)
+    tol = 4 * torch.finfo(dtype).eps
+    assert float((y.float() - y2.float()).abs().max()) <= tol * float(y2.float().abs().max()) + 1e-3
