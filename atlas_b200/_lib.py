@@ -94,6 +94,31 @@ def lib():
     L.atlas_b200_profile_work.argtypes = []
     L.atlas_b200_profile_collect.restype = c.c_int
     L.atlas_b200_profile_collect.argtypes = [c.POINTER(c.c_double), c.POINTER(c.c_int32)]
+    i32, i64, vp, f32 = c.c_int32, c.c_int64, c.c_void_p, c.c_float
+    L.atlas_b200_attention_bwd.restype = c.c_int
+    L.atlas_b200_attention_bwd.argtypes = [vp, i64, i32, vp, i64, i32, vp, i64, i32, vp, i64, vp, i64, vp, i64, i32, vp,
+                                           i64, i32, vp, i64, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, f32, i32,
+                                           vp]
+    L.atlas_b200_transpose.restype = c.c_int
+    L.atlas_b200_transpose.argtypes = [vp, i64, vp, i64, i32, i32, i32, vp]
+    L.atlas_b200_colsum.restype = c.c_int
+    L.atlas_b200_colsum.argtypes = [vp, i64, vp, i32, i32, i32, vp]
+    L.atlas_b200_layernorm_bwd.restype = c.c_int
+    L.atlas_b200_layernorm_bwd.argtypes = [vp, i64, vp, i64, vp, vp, i64, vp, i64, vp, vp, i32, i32, f32, i32, i32, vp]
+    L.atlas_b200_gated_gelu.restype = c.c_int
+    L.atlas_b200_gated_gelu.argtypes = [vp, i64, vp, i64, vp, i64, i64, i32, i32, vp]
+    L.atlas_b200_gelu_erf.restype = c.c_int
+    L.atlas_b200_gelu_erf.argtypes = [vp, i64, vp, i64, vp, i64, i64, i32, i32, vp]
+    L.atlas_b200_bert_embed_sum.restype = c.c_int
+    L.atlas_b200_bert_embed_sum.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
+    L.atlas_b200_scatter_add_rows.restype = c.c_int
+    L.atlas_b200_scatter_add_rows.argtypes = [vp, i32, vp, i64, vp, i64, i32, i64, i64, i32, vp]
+    L.atlas_b200_masked_mean_pool_bwd.restype = c.c_int
+    L.atlas_b200_masked_mean_pool_bwd.argtypes = [vp, i64, vp, vp, i32, i32, i32, i32, vp]
+    L.atlas_b200_cross_entropy_fwd.restype = c.c_int
+    L.atlas_b200_cross_entropy_fwd.argtypes = [vp, i64, vp, vp, vp, i32, i32, i32, vp]
+    L.atlas_b200_cross_entropy_bwd.restype = c.c_int
+    L.atlas_b200_cross_entropy_bwd.argtypes = [vp, i64, vp, vp, vp, vp, i64, i32, i32, i32, vp]
     _lib = L
     return L
 
@@ -120,6 +145,17 @@ EXPORTED_SYMBOLS = [
     "atlas_b200_profile_enable",
     "atlas_b200_profile_work",
     "atlas_b200_profile_collect",
+    "atlas_b200_attention_bwd",
+    "atlas_b200_transpose",
+    "atlas_b200_colsum",
+    "atlas_b200_layernorm_bwd",
+    "atlas_b200_gated_gelu",
+    "atlas_b200_gelu_erf",
+    "atlas_b200_bert_embed_sum",
+    "atlas_b200_scatter_add_rows",
+    "atlas_b200_masked_mean_pool_bwd",
+    "atlas_b200_cross_entropy_fwd",
+    "atlas_b200_cross_entropy_bwd",
 ]
 
 

@@ -1,0 +1,483 @@
+// Backward of the fused attention (csrc/attention.cu), head_dim 64, any Lq / Lk:
+//     S = scale * Q K^T + bias_delta[h, j - i + Lq - 1] + add_mask[b, j] (+ causal_value where j > i)
+//     P = softmax_j(S)   (fp32),   O = P V
+// given dO:   dV = P^T dO,   dP = dO V^T,   dS = P o (dP - D),  D_i = sum_d dO_id O_id,
+//             dQ = scale * dS K,   dK = scale * dS^T Q,   dbias_delta[h, j - i + Lq - 1] += dS_ij.
+// This is what autograd derives for `BertSelfAttention.forward` (src/modeling_bert.py:328-366), `T5Attention.forward`
+// (src/modeling_t5.py:478-524) and FiD's `cross_attention_forward` (src/fid.py:298-349) in the reference's training
+// step (train.py -> Atlas.forward -> loss.backward()); the [B, H, Lq, Lk] score / probability tensors the reference
+// keeps alive for autograd are recomputed tile by tile instead (the forward saves only O).
+//
+// Round-1 implementation: warp-level `mma.sync.m16n8k16` tiles (64 queries x 64 keys per CTA step, 4 warps, operands
+// through swizzled shared memory + ldmatrix), two kernels so that no output needs atomics:
+//   attn_bwd_dq_kernel   CTA = (b, h, 64-query block): pass 1 over the keys recomputes the row log-sum-exp (written to
+//                        `lse` for the second kernel, with D to `dsum`), pass 2 accumulates dQ (and dbias).
+//   attn_bwd_dkv_kernel  CTA = (b, h, 64-key block): loops over the query blocks, accumulates dK and dV.
+// Bound: tensor (legacy warp-MMA path; the tcgen05 port with S/dP in tensor memory is the next step).
+// FLOPs per call = 2 * B*H*Lq*Lk*64 * 8 (S twice + dP + dQ in the first kernel, S + dP + dV + dK in the second).
+#include "common.cuh"
+#include "host_common.h"
+
+#include <math.h>
+
+namespace attnb {
+
+constexpr int D = 64;
+constexpr int BM = 64;        // rows of the CTA's resident operand (queries in dq, keys in dkv)
+constexpr int BN = 64;        // rows of the streamed operand tile
+constexpr int THREADS = 128;  // 4 warps x 16 rows
+constexpr int TILE_BYTES = 64 * 128;
+
+struct Params {
+    const uint16_t *q, *k, *v, *o, *dout;
+    int64_t ldq, ldk, ldv, ldo, lddo;
+    int q_col0, k_col0, v_col0;
+    uint16_t *dq, *dk, *dv;
+    int64_t lddq, lddk, lddv;
+    int dq_col0, dk_col0, dv_col0;
+    const float* add_mask;    // [B, Lk] or nullptr
+    const float* bias_delta;  // [H, Lq + Lk - 1] or nullptr
+    float* dbias;             // [H, Lq + Lk - 1] (+=, atomics) or nullptr
+    float* lse;               // [B, H, Lq]
+    float* dsum;              // [B, H, Lq]
+    int B, H, Lq, Lk;
+    float scale, causal_value;
+};
+
+// ---- shared-memory tiles: 64 rows x 128 bytes, 16-byte chunks XOR-swizzled by the row ------------------------------
+__device__ __forceinline__ uint32_t tile_off(int row, int chunk) {
+    return static_cast<uint32_t>(row * 128 + ((chunk ^ (row & 7)) << 4));
+}
+
+// rows [r0, r0 + 64) of a [nrows, ld] matrix (columns col .. col + 63) -> tile; rows >= nrows are zero-filled
+__device__ __forceinline__ void load_tile(uint8_t* tile, const uint16_t* base, int64_t ld, int col, int64_t row_base,
+                                          int r0, int nrows) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int idx = it * THREADS + static_cast<int>(threadIdx.x);
+        const int row = idx >> 3, chunk = idx & 7;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (r0 + row < nrows)
+            v = __ldg(reinterpret_cast<const uint4*>(base + (row_base + r0 + row) * ld + col + chunk * 8));
+        *reinterpret_cast<uint4*>(tile + tile_off(row, chunk)) = v;
+    }
+}
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+
+template <bool kBF16>
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    if constexpr (kBF16) {
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+                     "{%0, %1, %2, %3};"
+                     : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    } else {
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+                     "{%0, %1, %2, %3};"
+                     : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    }
+}
+
+// A fragments (16 rows x 64 k, four k-steps) of the warp's rows [row0, row0 + 16) of a tile
+__device__ __forceinline__ void load_a_frags(uint32_t (&a)[4][4], uint32_t tile, int row0, int lane) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) ldsm_x4(a[ks], tile + tile_off(row0 + (lane & 15), ks * 2 + (lane >> 4)));
+}
+
+// acc[nt][.] (16 x 64, eight n-tiles) += A(16 x 64 over d) . T^T, T = tile of 64 rows x 64 d: B[k = d][n = tile row]
+template <bool kBF16>
+__device__ __forceinline__ void mma_a_tileT(float (&acc)[8][4], const uint32_t (&a)[4][4], uint32_t tile, int lane) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+            uint32_t b[4];
+            ldsm_x4(b, tile + tile_off(np * 16 + (lane & 7) + ((lane >> 4) << 3), ks * 2 + ((lane >> 3) & 1)));
+            mma16816<kBF16>(acc[2 * np], a[ks], b[0], b[1]);
+            mma16816<kBF16>(acc[2 * np + 1], a[ks], b[2], b[3]);
+        }
+    }
+}
+
+// acc[nt][.] (16 x 64 over d) += P(16 x 64 over the tile rows, as accumulator-layout fp32 values) . T,
+// T = tile of 64 rows x 64 d: B[k = tile row][n = d] (transposing ldmatrix)
+template <bool kBF16>
+__device__ __forceinline__ void mma_p_tile(float (&acc)[8][4], const float (&p)[8][4], uint32_t tile, int lane) {
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        uint32_t a[4];
+        a[0] = ab::pack2_rn<kBF16>(p[2 * kk][0], p[2 * kk][1]);
+        a[1] = ab::pack2_rn<kBF16>(p[2 * kk][2], p[2 * kk][3]);
+        a[2] = ab::pack2_rn<kBF16>(p[2 * kk + 1][0], p[2 * kk + 1][1]);
+        a[3] = ab::pack2_rn<kBF16>(p[2 * kk + 1][2], p[2 * kk + 1][3]);
+#pragma unroll
+        for (int dp = 0; dp < 4; ++dp) {
+            uint32_t b[4];
+            ldsm_x4_t(b, tile + tile_off(kk * 16 + (lane & 7) + (((lane >> 3) & 1) << 3), dp * 2 + (lane >> 4)));
+            mma16816<kBF16>(acc[2 * dp], a, b[0], b[1]);
+            mma16816<kBF16>(acc[2 * dp + 1], a, b[2], b[3]);
+        }
+    }
+}
+
+// the score of (query i, key j) from the raw dot product; identical in both kernels and both passes
+__device__ __forceinline__ float score(float dot, int i, int j, const Params& p, const float* bias_s,
+                                       const float* mask_row) {
+    if (j >= p.Lk) return -INFINITY;
+    const int ic = i < p.Lq ? i : p.Lq - 1;
+    float s = dot * p.scale;
+    if (bias_s != nullptr) s += bias_s[j - ic + p.Lq - 1];
+    if (mask_row != nullptr) s += __ldg(mask_row + j);
+    if (p.causal_value != 0.f && j > ic) s += p.causal_value;
+    return s;
+}
+
+template <bool kBF16>
+__device__ __forceinline__ float to_f32(uint32_t h) {
+    if constexpr (kBF16) return __bfloat162float(__ushort_as_bfloat16(static_cast<unsigned short>(h)));
+    return __half2float(__ushort_as_half(static_cast<unsigned short>(h)));
+}
+
+// 16 x 64 fp32 accumulator (rows g / g + 8 of the warp's 16) -> 16-bit global rows
+template <bool kBF16>
+__device__ __forceinline__ void store_acc(const float (&acc)[8][4], float mul, uint16_t* base, int64_t ld, int col,
+                                          int64_t row_base, int r_lo, int nrows, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int r = r_lo + g + half * 8;
+        if (r >= nrows) continue;
+        uint16_t* row = base + (row_base + r) * ld + col;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+            *reinterpret_cast<uint32_t*>(row + nt * 8 + 2 * t) =
+                ab::pack2_rn<kBF16>(acc[nt][2 * half] * mul, acc[nt][2 * half + 1] * mul);
+    }
+}
+
+// ======================================================================================================================
+// dQ kernel (+ log-sum-exp, D, dbias)
+// ======================================================================================================================
+template <bool kBF16>
+__global__ void __launch_bounds__(THREADS)
+attn_bwd_dq_kernel(const Params p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sQ = smem;
+    uint8_t* sdO = smem + TILE_BYTES;
+    uint8_t* sK = smem + 2 * TILE_BYTES;
+    uint8_t* sV = smem + 3 * TILE_BYTES;
+    const int ntab = p.Lq + p.Lk - 1;
+    float* bias_s = p.bias_delta ? reinterpret_cast<float*>(smem + 4 * TILE_BYTES) : nullptr;
+    float* dbias_s = p.dbias ? reinterpret_cast<float*>(smem + 4 * TILE_BYTES) + (p.bias_delta ? ntab : 0) : nullptr;
+
+    const int nqb = (p.Lq + BM - 1) / BM;
+    const int qb = static_cast<int>(blockIdx.x) % nqb;
+    const int h = (static_cast<int>(blockIdx.x) / nqb) % p.H;
+    const int b = static_cast<int>(blockIdx.x) / (nqb * p.H);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int q0 = qb * BM;
+    const int64_t qrow_base = static_cast<int64_t>(b) * p.Lq, krow_base = static_cast<int64_t>(b) * p.Lk;
+    const float* mask_row = p.add_mask ? p.add_mask + static_cast<int64_t>(b) * p.Lk : nullptr;
+
+    for (int x = threadIdx.x; x < ntab; x += THREADS) {
+        if (bias_s) bias_s[x] = __ldg(p.bias_delta + static_cast<int64_t>(h) * ntab + x);
+        if (dbias_s) dbias_s[x] = 0.f;
+    }
+    load_tile(sQ, p.q, p.ldq, p.q_col0 + h * D, qrow_base, q0, p.Lq);
+    load_tile(sdO, p.dout, p.lddo, h * D, qrow_base, q0, p.Lq);
+
+    // D_i = sum_d dO[i, d] * O[i, d]: two lanes per row, 32 columns each, straight from global memory
+    float drow[2];
+    {
+        const int r = q0 + warp * 16 + (lane >> 1);
+        float acc = 0.f;
+        if (r < p.Lq) {
+            const uint16_t* po = p.o + (qrow_base + r) * p.ldo + h * D + (lane & 1) * 32;
+            const uint16_t* pd = p.dout + (qrow_base + r) * p.lddo + h * D + (lane & 1) * 32;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint4 a = __ldg(reinterpret_cast<const uint4*>(po) + c);
+                const uint4 d = __ldg(reinterpret_cast<const uint4*>(pd) + c);
+                const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, dw[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    acc = fmaf(to_f32<kBF16>(aw[e] & 0xFFFFu), to_f32<kBF16>(dw[e] & 0xFFFFu), acc);
+                    acc = fmaf(to_f32<kBF16>(aw[e] >> 16), to_f32<kBF16>(dw[e] >> 16), acc);
+                }
+            }
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        // the row (lane >> 1) total now sits in lanes 2r and 2r + 1; this thread needs rows g and g + 8
+        drow[0] = __shfl_sync(0xffffffffu, acc, 2 * g);
+        drow[1] = __shfl_sync(0xffffffffu, acc, 2 * (g + 8));
+        if ((lane & 1) == 0 && r < p.Lq) p.dsum[(static_cast<int64_t>(b) * p.H + h) * p.Lq + r] = acc;
+    }
+    __syncthreads();
+
+    const uint32_t sQ_a = ab::smem_u32(sQ), sdO_a = ab::smem_u32(sdO), sK_a = ab::smem_u32(sK), sV_a = ab::smem_u32(sV);
+    uint32_t qa[4][4], doa[4][4];
+    load_a_frags(qa, sQ_a, warp * 16, lane);
+    load_a_frags(doa, sdO_a, warp * 16, lane);
+
+    const int nkb = (p.Lk + BN - 1) / BN;
+    const int i_lo = q0 + warp * 16 + g;   // this thread's rows: i_lo and i_lo + 8
+
+    // ---- pass 1: row max / sum of exp -> log-sum-exp -----------------------------------------------------------------
+    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+    for (int kb = 0; kb < nkb; ++kb) {
+        __syncthreads();
+        load_tile(sK, p.k, p.ldk, p.k_col0 + h * D, krow_base, kb * BN, p.Lk);
+        __syncthreads();
+        float acc[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+        mma_a_tileT<kBF16>(acc, qa, sK_a, lane);
+        float tmax[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float s = score(acc[nt][e], i_lo + (e >> 1) * 8, kb * BN + nt * 8 + 2 * t + (e & 1), p, bias_s, mask_row);
+                acc[nt][e] = s;
+                tmax[e >> 1] = fmaxf(tmax[e >> 1], s);
+            }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            tmax[r] = fmaxf(tmax[r], __shfl_xor_sync(0xffffffffu, tmax[r], 1));
+            tmax[r] = fmaxf(tmax[r], __shfl_xor_sync(0xffffffffu, tmax[r], 2));
+        }
+        float m_new[2], tsum[2] = {0.f, 0.f};
+#pragma unroll
+        for (int r = 0; r < 2; ++r) m_new[r] = fmaxf(m_run[r], tmax[r]);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) tsum[e >> 1] += __expf(acc[nt][e] - m_new[e >> 1]);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            tsum[r] += __shfl_xor_sync(0xffffffffu, tsum[r], 1);
+            tsum[r] += __shfl_xor_sync(0xffffffffu, tsum[r], 2);
+            l_run[r] = l_run[r] * __expf(m_run[r] - m_new[r]) + tsum[r];
+            m_run[r] = m_new[r];
+        }
+    }
+    float lse[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        lse[r] = m_run[r] + __logf(l_run[r]);
+        const int i = i_lo + r * 8;
+        if (t == 0 && i < p.Lq) p.lse[(static_cast<int64_t>(b) * p.H + h) * p.Lq + i] = lse[r];
+    }
+
+    // ---- pass 2: dQ = scale * (P o (dO V^T - D)) K --------------------------------------------------------------------
+    float dqacc[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dqacc[nt][e] = 0.f;
+    for (int kb = 0; kb < nkb; ++kb) {
+        __syncthreads();
+        load_tile(sK, p.k, p.ldk, p.k_col0 + h * D, krow_base, kb * BN, p.Lk);
+        load_tile(sV, p.v, p.ldv, p.v_col0 + h * D, krow_base, kb * BN, p.Lk);
+        __syncthreads();
+        float acc[8][4], dp[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                acc[nt][e] = 0.f;
+                dp[nt][e] = 0.f;
+            }
+        mma_a_tileT<kBF16>(acc, qa, sK_a, lane);
+        mma_a_tileT<kBF16>(dp, doa, sV_a, lane);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int i = i_lo + (e >> 1) * 8, j = kb * BN + nt * 8 + 2 * t + (e & 1);
+                const float s = score(acc[nt][e], i, j, p, bias_s, mask_row);
+                const float pr = __expf(s - lse[e >> 1]);
+                const float ds = pr * (dp[nt][e] - drow[e >> 1]);
+                acc[nt][e] = ds;
+                if (dbias_s != nullptr && i < p.Lq && j < p.Lk) atomicAdd(&dbias_s[j - i + p.Lq - 1], ds);
+            }
+        mma_p_tile<kBF16>(dqacc, acc, sK_a, lane);
+    }
+    store_acc<kBF16>(dqacc, p.scale, p.dq, p.lddq, p.dq_col0 + h * D, qrow_base, q0 + warp * 16, p.Lq, lane);
+    if (dbias_s != nullptr) {
+        __syncthreads();
+        for (int x = threadIdx.x; x < ntab; x += THREADS) {
+            const float v = dbias_s[x];
+            if (v != 0.f) atomicAdd(p.dbias + static_cast<int64_t>(h) * ntab + x, v);
+        }
+    }
+}
+
+// ======================================================================================================================
+// dK / dV kernel: everything transposed (rows = keys, columns = queries)
+// ======================================================================================================================
+template <bool kBF16>
+__global__ void __launch_bounds__(THREADS)
+attn_bwd_dkv_kernel(const Params p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sK = smem;
+    uint8_t* sV = smem + TILE_BYTES;
+    uint8_t* sQ = smem + 2 * TILE_BYTES;
+    uint8_t* sdO = smem + 3 * TILE_BYTES;
+    float* lse_s = reinterpret_cast<float*>(smem + 4 * TILE_BYTES);
+    float* d_s = lse_s + BN;
+    const int ntab = p.Lq + p.Lk - 1;
+    float* bias_s = p.bias_delta ? d_s + BN : nullptr;
+
+    const int nkb = (p.Lk + BM - 1) / BM;
+    const int kb = static_cast<int>(blockIdx.x) % nkb;
+    const int h = (static_cast<int>(blockIdx.x) / nkb) % p.H;
+    const int b = static_cast<int>(blockIdx.x) / (nkb * p.H);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int k0 = kb * BM;
+    const int64_t qrow_base = static_cast<int64_t>(b) * p.Lq, krow_base = static_cast<int64_t>(b) * p.Lk;
+    const float* mask_row = p.add_mask ? p.add_mask + static_cast<int64_t>(b) * p.Lk : nullptr;
+
+    if (bias_s)
+        for (int x = threadIdx.x; x < ntab; x += THREADS) bias_s[x] = __ldg(p.bias_delta + static_cast<int64_t>(h) * ntab + x);
+    load_tile(sK, p.k, p.ldk, p.k_col0 + h * D, krow_base, k0, p.Lk);
+    load_tile(sV, p.v, p.ldv, p.v_col0 + h * D, krow_base, k0, p.Lk);
+    __syncthreads();
+    const uint32_t sQ_a = ab::smem_u32(sQ), sdO_a = ab::smem_u32(sdO), sK_a = ab::smem_u32(sK), sV_a = ab::smem_u32(sV);
+    uint32_t ka[4][4], va[4][4];
+    load_a_frags(ka, sK_a, warp * 16, lane);
+    load_a_frags(va, sV_a, warp * 16, lane);
+
+    float dkacc[8][4], dvacc[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            dkacc[nt][e] = 0.f;
+            dvacc[nt][e] = 0.f;
+        }
+    const int j_lo = k0 + warp * 16 + g;   // this thread's keys: j_lo and j_lo + 8
+    const int nqb = (p.Lq + BN - 1) / BN;
+    const float* lse_g = p.lse + (static_cast<int64_t>(b) * p.H + h) * p.Lq;
+    const float* d_g = p.dsum + (static_cast<int64_t>(b) * p.H + h) * p.Lq;
+    for (int qb = 0; qb < nqb; ++qb) {
+        __syncthreads();
+        load_tile(sQ, p.q, p.ldq, p.q_col0 + h * D, qrow_base, qb * BN, p.Lq);
+        load_tile(sdO, p.dout, p.lddo, h * D, qrow_base, qb * BN, p.Lq);
+        if (threadIdx.x < BN) {
+            const int i = qb * BN + static_cast<int>(threadIdx.x);
+            lse_s[threadIdx.x] = i < p.Lq ? lse_g[i] : INFINITY;   // exp(s - inf) = 0 for the padding queries
+            d_s[threadIdx.x] = i < p.Lq ? d_g[i] : 0.f;
+        }
+        __syncthreads();
+        float acc[8][4], dp[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                acc[nt][e] = 0.f;
+                dp[nt][e] = 0.f;
+            }
+        mma_a_tileT<kBF16>(acc, ka, sQ_a, lane);     // S^T  = K Q^T
+        mma_a_tileT<kBF16>(dp, va, sdO_a, lane);     // dP^T = V dO^T
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int il = nt * 8 + 2 * t + (e & 1);
+                const float s = score(acc[nt][e], qb * BN + il, j_lo + (e >> 1) * 8, p, bias_s, mask_row);
+                const float pr = __expf(s - lse_s[il]);
+                acc[nt][e] = pr;
+                dp[nt][e] = pr * (dp[nt][e] - d_s[il]);
+            }
+        mma_p_tile<kBF16>(dvacc, acc, sdO_a, lane);  // dV += P^T dO
+        mma_p_tile<kBF16>(dkacc, dp, sQ_a, lane);    // dK += dS^T Q
+    }
+    store_acc<kBF16>(dkacc, p.scale, p.dk, p.lddk, p.dk_col0 + h * D, krow_base, k0 + warp * 16, p.Lk, lane);
+    store_acc<kBF16>(dvacc, 1.0f, p.dv, p.lddv, p.dv_col0 + h * D, krow_base, k0 + warp * 16, p.Lk, lane);
+}
+
+}  // namespace attnb
+
+extern "C" {
+
+int atlas_b200_attention_bwd(const void* q, int64_t ldq, int32_t q_col0, const void* k, int64_t ldk, int32_t k_col0,
+                             const void* v, int64_t ldv, int32_t v_col0, const void* out, int64_t ldo, const void* dout,
+                             int64_t lddo, void* dq, int64_t lddq, int32_t dq_col0, void* dk, int64_t lddk,
+                             int32_t dk_col0, void* dv, int64_t lddv, int32_t dv_col0, const float* add_mask,
+                             const float* bias_delta, float* dbias_delta, float* lse, float* dsum, int32_t B, int32_t H,
+                             int32_t Lq, int32_t Lk, float scale, float causal_value, int32_t is_bf16, void* stream) {
+    using namespace attnb;
+    AB_REQUIRE(B >= 0 && H > 0 && Lq > 0 && Lk > 0, "attention_bwd: bad shape B=%d H=%d Lq=%d Lk=%d", B, H, Lq, Lk);
+    AB_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && lddo % 8 == 0 && lddq % 8 == 0 &&
+                   lddk % 8 == 0 && lddv % 8 == 0 && q_col0 % 8 == 0 && k_col0 % 8 == 0 && v_col0 % 8 == 0 &&
+                   dq_col0 % 8 == 0 && dk_col0 % 8 == 0 && dv_col0 % 8 == 0,
+               "attention_bwd: strides and column offsets must be multiples of 8 elements");
+    AB_REQUIRE(lse != nullptr && dsum != nullptr, "attention_bwd: lse / dsum scratch ([B, H, Lq] fp32 each) is required");
+    AB_REQUIRE(dbias_delta == nullptr || bias_delta != nullptr, "attention_bwd: dbias_delta without bias_delta");
+    const int64_t ntab = static_cast<int64_t>(Lq) + Lk - 1;
+    AB_REQUIRE(bias_delta == nullptr || ntab <= 8192, "attention_bwd: Lq + Lk - 1 = %lld exceeds the bias table (8192)",
+               static_cast<long long>(ntab));
+    if (B == 0) return ATLAS_B200_OK;
+    const int64_t nq_ctas = static_cast<int64_t>(B) * H * ((Lq + BM - 1) / BM);
+    const int64_t nk_ctas = static_cast<int64_t>(B) * H * ((Lk + BM - 1) / BM);
+    AB_REQUIRE(nq_ctas < (1ll << 31) && nk_ctas < (1ll << 31), "attention_bwd: grid too large");
+    Params p;
+    p.q = static_cast<const uint16_t*>(q);
+    p.k = static_cast<const uint16_t*>(k);
+    p.v = static_cast<const uint16_t*>(v);
+    p.o = static_cast<const uint16_t*>(out);
+    p.dout = static_cast<const uint16_t*>(dout);
+    p.ldq = ldq; p.ldk = ldk; p.ldv = ldv; p.ldo = ldo; p.lddo = lddo;
+    p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
+    p.dq = static_cast<uint16_t*>(dq);
+    p.dk = static_cast<uint16_t*>(dk);
+    p.dv = static_cast<uint16_t*>(dv);
+    p.lddq = lddq; p.lddk = lddk; p.lddv = lddv;
+    p.dq_col0 = dq_col0; p.dk_col0 = dk_col0; p.dv_col0 = dv_col0;
+    p.add_mask = add_mask;
+    p.bias_delta = bias_delta;
+    p.dbias = dbias_delta;
+    p.lse = lse;
+    p.dsum = dsum;
+    p.B = B; p.H = H; p.Lq = Lq; p.Lk = Lk;
+    p.scale = scale;
+    p.causal_value = causal_value;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int smem_dq = 4 * TILE_BYTES + static_cast<int>(((bias_delta ? ntab : 0) + (dbias_delta ? ntab : 0)) * 4);
+    const int smem_dkv = 4 * TILE_BYTES + 2 * BN * 4 + static_cast<int>((bias_delta ? ntab : 0) * 4);
+    constexpr int SMEM_MAX = 4 * TILE_BYTES + 2 * BN * 4 + 2 * 8192 * 4;
+    static bool attr_set = false;
+    if (!attr_set) {
+        AB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+        AB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+        AB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dkv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+        AB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dkv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+        attr_set = true;
+    }
+    abh::prof_begin(s, abh::PROF_ATTENTION_BWD);
+    if (is_bf16) {
+        attn_bwd_dq_kernel<true><<<static_cast<unsigned>(nq_ctas), THREADS, smem_dq, s>>>(p);
+        attn_bwd_dkv_kernel<true><<<static_cast<unsigned>(nk_ctas), THREADS, smem_dkv, s>>>(p);
+    } else {
+        attn_bwd_dq_kernel<false><<<static_cast<unsigned>(nq_ctas), THREADS, smem_dq, s>>>(p);
+        attn_bwd_dkv_kernel<false><<<static_cast<unsigned>(nk_ctas), THREADS, smem_dkv, s>>>(p);
+    }
+    abh::prof_end(s, abh::PROF_ATTENTION_BWD, 16.0 * B * H * static_cast<double>(Lq) * Lk * D);
+    abh::count_launch(2);
+    AB_CUDA_CHECK(cudaGetLastError());
+    return ATLAS_B200_OK;
+}
+
+}  // extern "C"

@@ -25,9 +25,9 @@ from types import SimpleNamespace
 import torch
 from torch import nn
 
-from . import ops
+from . import grad_ops, ops
 from ._lib import AtlasB200Error
-from .retrievers import HalfCache
+from .retrievers import HalfCache, _warn_no_dropout
 
 
 class T5ConfigLite(SimpleNamespace):
@@ -204,10 +204,12 @@ class FiD(nn.Module):
         pass
 
     def gradient_checkpointing_enable(self):
-        pass
+        """Recompute each block in the backward instead of keeping its activations (torch.utils.checkpoint around the
+        autograd Functions of grad_ops.py), `--use_gradient_checkpoint_reader` (src/model_io.py:86-87)."""
+        self._grad_ckpt = True
 
     def gradient_checkpointing_disable(self):
-        pass
+        self._grad_ckpt = False
 
     def reset_score_storage(self):
         pass
@@ -376,6 +378,130 @@ class FiD(nn.Module):
         logits = ops.linear(h, W["lm_head.weight"])
         return logits.view(B, T, -1)
 
+    # ---- training path (autograd through the kernels, grad_ops.py) ---------------------------------------
+    def _train_weights(self):
+        """16-bit views of the live parameters built with DIFFERENTIABLE casts / concatenations, so that autograd routes
+        the kernels' weight gradients back to the reference-named parameters (q / k / v, wi_0 / wi_1 ...)."""
+        dt = self._dtype()
+        W = {n: (p if p.dtype == dt else p.to(dt)) for n, p in self.named_parameters()}
+        G = {}
+        for name in list(W.keys()):
+            if name.endswith("DenseReluDense.wi_0.weight"):
+                w0, w1 = W[name], W[name.replace("wi_0", "wi_1")]
+                G[name.replace("wi_0.weight", "wi_01")] = torch.stack([w0, w1], dim=1).reshape(-1, w0.shape[1])
+            elif name.endswith("SelfAttention.q.weight"):
+                G[name.replace("q.weight", "qkv")] = torch.cat(
+                    [W[name], W[name.replace("q.weight", "k.weight")], W[name.replace("q.weight", "v.weight")]], 0)
+            elif name.endswith("EncDecAttention.k.weight"):
+                G[name.replace("k.weight", "kv")] = torch.cat([W[name], W[name.replace("k.weight", "v.weight")]], 0)
+        return W, G, dt
+
+    def _check_trainable(self):
+        if self.training and float(getattr(self.config, "dropout_rate", 0.0) or 0.0) > 0.0:
+            _warn_no_dropout("FiD")
+
+    def _maybe_ckpt(self, fn, *args):
+        if getattr(self, "_grad_ckpt", False):
+            from torch.utils.checkpoint import checkpoint
+
+            return checkpoint(fn, *args, use_reentrant=False)
+        return fn(*args)
+
+    def _encode_train(self, WG, input_ids, attention_mask):
+        """`encode` with autograd (same kernels forward, un-fused norms; backward = grad_ops)."""
+        g = grad_ops
+        c = self.config
+        W, G, dt = WG
+        n_ctx, bsz = self.encoder.config.n_context, self.encoder.config.bsz
+        ids = input_ids.reshape(input_ids.size(0) * n_ctx, -1)
+        mask = attention_mask.reshape(attention_mask.size(0) * n_ctx, -1)
+        S, L = ids.shape
+        d, H = c.d_model, c.num_heads
+        eps = c.layer_norm_epsilon
+        h = g.embedding(W["shared.weight"], ids)
+        add_mask = (1.0 - mask.to(torch.float32)) * -10000.0
+        bias = bias_by_delta(W["encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight"], L, L, True,
+                             c.relative_attention_num_buckets)
+
+        def block(i, h, bias):
+            p = f"encoder.block.{i}.layer.0."
+            n = g.layernorm(h, W[p + "layer_norm.weight"], None, eps, kind=1)
+            qkv = g.linear(n, G[p + "SelfAttention.qkv"])
+            ctx = g.self_attention(qkv, S, H, L, add_mask=add_mask, bias_delta=bias, scale=1.0)
+            h = g.linear(ctx, W[p + "SelfAttention.o.weight"], None, residual=h)
+            p = f"encoder.block.{i}.layer.1."
+            n = g.layernorm(h, W[p + "layer_norm.weight"], None, eps, kind=1)
+            u = g.linear(n, G[p + "DenseReluDense.wi_01"])
+            return g.linear(g.gated_gelu(u), W[p + "DenseReluDense.wo.weight"], None, residual=h)
+
+        for i in range(c.num_layers):
+            h = self._maybe_ckpt(block, i, h, bias)
+        h = g.layernorm(h, W["encoder.final_layer_norm.weight"], None, eps, kind=1)
+        return h.view(bsz, -1, d)
+
+    def _decode_train(self, WG, decoder_input_ids, enc, enc_mask):
+        g = grad_ops
+        c = self.config
+        W, G, dt = WG
+        B, T = decoder_input_ids.shape
+        d, H = c.d_model, c.num_heads
+        Lk = enc.shape[1]
+        eps = c.layer_norm_epsilon
+        split = next((s for s in range(min(384, Lk), 63, -1) if Lk % s == 0), None) or \
+            next(s for s in range(min(512, Lk), 0, -1) if Lk % s == 0)
+        if split < 64 and Lk > 512:
+            raise AtlasB200Error(f"n_context*text_maxlength = {Lk} has no divisor in [64, 512] for the split-KV kernel")
+        flat = enc.reshape(-1, d)
+        if flat.dtype != dt:
+            flat = flat.to(dt)
+        h = g.embedding(W["shared.weight"], decoder_input_ids)
+        bias = bias_by_delta(W["decoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight"], T, T, False,
+                             c.relative_attention_num_buckets)
+        neg = -1e4 if dt == torch.float16 else -1e9
+        cross_mask = (1.0 - enc_mask.reshape(B, Lk).to(torch.float32)) * neg
+
+        def block(i, h, bias, flat):
+            p = f"decoder.block.{i}.layer.0."
+            n = g.layernorm(h, W[p + "layer_norm.weight"], None, eps, kind=1)
+            qkv = g.linear(n, G[p + "SelfAttention.qkv"])
+            ctx = g.self_attention(qkv, B, H, T, bias_delta=bias, scale=1.0, causal_value=-10000.0)
+            h = g.linear(ctx, W[p + "SelfAttention.o.weight"], None, residual=h)
+            p = f"decoder.block.{i}.layer.1."
+            n = g.layernorm(h, W[p + "layer_norm.weight"], None, eps, kind=1)
+            q = g.linear(n, W[p + "EncDecAttention.q.weight"])
+            kv = g.linear(flat, G[p + "EncDecAttention.kv"])
+            ctx = g.cross_attention(q, kv, B, H, T, Lk, add_mask=cross_mask, scale=1.0, split=split)
+            h = g.linear(ctx, W[p + "EncDecAttention.o.weight"], None, residual=h)
+            p = f"decoder.block.{i}.layer.2."
+            n = g.layernorm(h, W[p + "layer_norm.weight"], None, eps, kind=1)
+            u = g.linear(n, G[p + "DenseReluDense.wi_01"])
+            return g.linear(g.gated_gelu(u), W[p + "DenseReluDense.wo.weight"], None, residual=h)
+
+        for i in range(c.num_decoder_layers):
+            h = self._maybe_ckpt(block, i, h, bias, flat)
+        h = g.layernorm(h, W["decoder.final_layer_norm.weight"], None, eps, kind=1)
+        if getattr(c, "tie_word_embeddings", False):
+            raise AtlasB200Error("tied LM head (T5 v1.0) is not supported on the training path (T5 v1.1 is untied)")
+        logits = g.linear(h, W["lm_head.weight"])
+        return logits.view(B, T, -1)
+
+    def _forward_train(self, input_ids, attention_mask, decoder_input_ids, labels, encoder_outputs):
+        self._check_trainable()
+        WG = self._train_weights()
+        if encoder_outputs is not None:
+            enc = encoder_outputs[0]
+        else:
+            enc = self._encode_train(WG, input_ids, attention_mask.to(torch.bool))
+        B = enc.shape[0]
+        logits = self._decode_train(WG, decoder_input_ids, enc, attention_mask.reshape(B, -1).to(torch.bool))
+        loss = None
+        pd = self.shared.weight.dtype
+        if labels is not None:
+            loss = grad_ops.cross_entropy(logits, labels).to(pd)      # CrossEntropyLoss(ignore_index=-100)
+        if logits.dtype != pd:
+            logits, enc = logits.to(pd), enc.to(pd)
+        return FiDOutput(loss, logits, enc)
+
     # ---- CUDA-graph cache --------------------------------------------------------------------
     def _run(self, tag, fn, inputs):
         """Run `fn(*inputs)` (static shapes, device tensors in / out): replay a captured graph when enabled."""
@@ -398,10 +524,11 @@ class FiD(nn.Module):
     # ---- public forward / generate -----------------------------------------------------------
     def forward(self, input_ids=None, attention_mask=None, decoder_input_ids=None, labels=None, encoder_outputs=None,
                 use_cache=False, **unused):
-        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
-            raise AtlasB200Error("atlas_b200.FiD is forward-only in this round: call it under torch.no_grad()")
         if decoder_input_ids is None and labels is not None:
             decoder_input_ids = self._shift_right(labels)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # training step (train.py): the same kernels forward, autograd through grad_ops.py backward
+            return self._forward_train(input_ids, attention_mask, decoder_input_ids, labels, encoder_outputs)
         if encoder_outputs is not None:
             enc = encoder_outputs[0]
             B = enc.shape[0]

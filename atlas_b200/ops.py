@@ -277,3 +277,169 @@ def cross_attention_split(q, q_col0, kv, k_col0, v_col0, B, H, Lq, Lk_total, add
     check(lib().atlas_b200_attention_combine(_ptr(o_part), _ptr(ml), B, splits, Lq, H, _ptr(out), out.stride(0), _bf(q),
                                              current_stream_ptr()))
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# backward pass (csrc/backward.cu, csrc/attention_bwd.cu): raw kernel wrappers; the autograd wiring is grad_ops.py
+# ---------------------------------------------------------------------------------------------
+def _rows2d(t):
+    t2 = t.reshape(-1, t.shape[-1])
+    return t2 if t2.stride(-1) == 1 else t2.contiguous()
+
+
+def transpose(x, pad_to=8):
+    """[R, C] 16-bit -> [C, Rpad] with Rpad = R rounded up to `pad_to` and the pad columns zero."""
+    require_cuda(x, "x")
+    x2 = _rows2d(x)
+    R, C = x2.shape
+    Rpad = (R + pad_to - 1) // pad_to * pad_to
+    out = torch.empty((C, Rpad), dtype=x.dtype, device=x.device)
+    check(lib().atlas_b200_transpose(_ptr(x2), x2.stride(0), _ptr(out), out.stride(0), R, C, Rpad, current_stream_ptr()))
+    return out
+
+
+def colsum(x):
+    """fp32 [N] column sums of a 16-bit [M, N] matrix (bias gradient)."""
+    require_cuda(x, "x")
+    x2 = _rows2d(x)
+    out = torch.zeros(x2.shape[1], dtype=torch.float32, device=x.device)
+    check(lib().atlas_b200_colsum(_ptr(x2), x2.stride(0), _ptr(out), x2.shape[0], x2.shape[1], _bf(x), current_stream_ptr()))
+    return out
+
+
+def linear_dgrad(dy, weight):
+    """dX [M, K] = dY [M, N] . W [N, K]: the same tcgen05 GEMM on W^T (a weight-sized transpose per call)."""
+    return linear(dy, transpose(weight))
+
+
+def linear_wgrad(dy, x):
+    """dW [N, K] = dY^T [N, M] . X [M, K] (contraction over the M tokens, fp32 accumulation, 16-bit result)."""
+    dyT, xT = transpose(dy), transpose(x)
+    return linear(dyT, xT)
+
+
+def layernorm_bwd(x, dy, weight, eps, kind, dres=None, need_bias=False):
+    """-> (dx like x, dweight fp32 [H], dbias fp32 [H] or None)."""
+    require_cuda(x, "x")
+    H = x.shape[-1]
+    x2, dy2 = _rows2d(x), _rows2d(dy)
+    r2 = _rows2d(dres) if dres is not None else None
+    dx = torch.empty_like(x2)
+    dw = torch.zeros(H, dtype=torch.float32, device=x.device)
+    db = torch.zeros(H, dtype=torch.float32, device=x.device) if (need_bias or kind == 0) else None
+    check(lib().atlas_b200_layernorm_bwd(_ptr(x2), x2.stride(0), _ptr(dy2), dy2.stride(0), _ptr(weight),
+                                         _ptr(r2) if r2 is not None else None, r2.stride(0) if r2 is not None else 0,
+                                         _ptr(dx), dx.stride(0), _ptr(dw), _ptr(db) if db is not None else None,
+                                         x2.shape[0], H, float(eps), kind, _bf(x), current_stream_ptr()))
+    return dx.reshape(x.shape), dw, db
+
+
+def gated_gelu(u, dg=None):
+    """u [M, 2F] interleaved (wi_0 | wi_1) pre-activations -> g [M, F]; with dg [M, F] -> du [M, 2F]."""
+    require_cuda(u, "u")
+    u2 = _rows2d(u)
+    M, F2 = u2.shape
+    F = F2 // 2
+    if dg is None:
+        out = torch.empty((M, F), dtype=u.dtype, device=u.device)
+        check(lib().atlas_b200_gated_gelu(_ptr(u2), u2.stride(0), None, 0, _ptr(out), out.stride(0), M, F, _bf(u),
+                                          current_stream_ptr()))
+        return out.reshape(*u.shape[:-1], F)
+    d2 = _rows2d(dg)
+    out = torch.empty((M, F2), dtype=u.dtype, device=u.device)
+    check(lib().atlas_b200_gated_gelu(_ptr(u2), u2.stride(0), _ptr(d2), d2.stride(0), _ptr(out), out.stride(0), M, F,
+                                      _bf(u), current_stream_ptr()))
+    return out.reshape(u.shape)
+
+
+def gelu_erf(z, dy=None):
+    """erf GELU of z (dy None) or its backward dy * gelu'(z)."""
+    require_cuda(z, "z")
+    z2 = _rows2d(z)
+    d2 = _rows2d(dy) if dy is not None else None
+    out = torch.empty_like(z2)
+    check(lib().atlas_b200_gelu_erf(_ptr(z2), z2.stride(0), _ptr(d2) if d2 is not None else None,
+                                    d2.stride(0) if d2 is not None else 0, _ptr(out), out.stride(0), z2.shape[0],
+                                    z2.shape[1], _bf(z), current_stream_ptr()))
+    return out.reshape(z.shape)
+
+
+def bert_embed_sum(input_ids, token_type_ids, word_emb, type_emb, pos_emb):
+    require_cuda(input_ids, "input_ids")
+    B, L = input_ids.shape
+    H = word_emb.shape[1]
+    y = torch.empty((B, L, H), dtype=word_emb.dtype, device=word_emb.device)
+    ids = input_ids.contiguous()
+    tt = token_type_ids.contiguous() if token_type_ids is not None else None
+    check(lib().atlas_b200_bert_embed_sum(_ptr(ids), _ptr(tt) if tt is not None else None, _ptr(word_emb), _ptr(type_emb),
+                                          _ptr(pos_emb), _ptr(y), B, L, H, _bf(word_emb), current_stream_ptr()))
+    return y
+
+
+def scatter_add_rows(src, table_rows, index=None, modulo=0, skip_index=-1):
+    """fp32 [table_rows, H] with dst[index[r]] += src[r] (index None: r % modulo)."""
+    require_cuda(src, "src")
+    s2 = _rows2d(src)
+    H = s2.shape[1]
+    dst = torch.zeros((table_rows, H), dtype=torch.float32, device=src.device)
+    idx = index.reshape(-1).contiguous() if index is not None else None
+    check(lib().atlas_b200_scatter_add_rows(_ptr(idx) if idx is not None else None, int(modulo), _ptr(s2), s2.stride(0),
+                                            _ptr(dst), s2.shape[0], H, int(skip_index), int(table_rows), _bf(src),
+                                            current_stream_ptr()))
+    return dst
+
+
+def masked_mean_pool_bwd(demb, mask, L, H):
+    require_cuda(demb, "demb")
+    d2 = demb if demb.stride(-1) == 1 else demb.contiguous()
+    B = d2.shape[0]
+    m = mask.to(torch.int64).contiguous()
+    dx = torch.empty((B, L, H), dtype=demb.dtype, device=demb.device)
+    check(lib().atlas_b200_masked_mean_pool_bwd(_ptr(d2), d2.stride(0), _ptr(m), _ptr(dx), B, L, H, _bf(demb),
+                                                current_stream_ptr()))
+    return dx
+
+
+def cross_entropy_fwd(logits, labels):
+    """-> (lse fp32 [rows], per-row loss fp32 [rows], 0 where label == -100)."""
+    require_cuda(logits, "logits")
+    l2 = _rows2d(logits)
+    rows, V = l2.shape
+    y = labels.reshape(-1).to(torch.int64).contiguous()
+    lse = torch.empty(rows, dtype=torch.float32, device=logits.device)
+    loss = torch.empty(rows, dtype=torch.float32, device=logits.device)
+    check(lib().atlas_b200_cross_entropy_fwd(_ptr(l2), l2.stride(0), _ptr(y), _ptr(lse), _ptr(loss), rows, V, _bf(logits),
+                                             current_stream_ptr()))
+    return lse, loss
+
+
+def cross_entropy_bwd(logits, labels, lse, gscale):
+    """dlogits = (softmax - onehot) * gscale[0] for the valid rows (gscale: fp32 device scalar)."""
+    l2 = _rows2d(logits)
+    rows, V = l2.shape
+    y = labels.reshape(-1).to(torch.int64).contiguous()
+    out = torch.empty_like(l2)
+    gs = gscale.reshape(1).to(torch.float32).contiguous()
+    check(lib().atlas_b200_cross_entropy_bwd(_ptr(l2), l2.stride(0), _ptr(y), _ptr(lse), _ptr(gs), _ptr(out),
+                                             out.stride(0), rows, V, _bf(logits), current_stream_ptr()))
+    return out.reshape(logits.shape)
+
+
+def attention_bwd(q, q_col0, k, k_col0, v, v_col0, out, dout, dq, dq_col0, dk, dk_col0, dv, dv_col0, B, H, Lq, Lk,
+                  add_mask=None, bias_delta=None, need_dbias=False, scale=1.0, causal_value=0.0):
+    """Backward of `attention` / `cross_attention_split` (un-split key range).  dq / dk / dv are written in place at
+    their column offsets; returns dbias_delta fp32 [H, Lq+Lk-1] (or None)."""
+    require_cuda(q, "q")
+    am = add_mask.float().contiguous() if add_mask is not None else None
+    bd = bias_delta.float().contiguous() if bias_delta is not None else None
+    dbias = torch.zeros((H, Lq + Lk - 1), dtype=torch.float32, device=q.device) if (need_dbias and bd is not None) else None
+    scratch = torch.empty((2, B, H, Lq), dtype=torch.float32, device=q.device)
+    o2 = out if out.stride(-1) == 1 else out.contiguous()
+    do2 = _rows2d(dout)
+    check(lib().atlas_b200_attention_bwd(
+        _ptr(q), q.stride(0), q_col0, _ptr(k), k.stride(0), k_col0, _ptr(v), v.stride(0), v_col0, _ptr(o2), o2.stride(0),
+        _ptr(do2), do2.stride(0), _ptr(dq), dq.stride(0), dq_col0, _ptr(dk), dk.stride(0), dk_col0, _ptr(dv),
+        dv.stride(0), dv_col0, _ptr(am) if am is not None else None, _ptr(bd) if bd is not None else None,
+        _ptr(dbias) if dbias is not None else None, _ptr(scratch[0]), _ptr(scratch[1]), B, H, Lq, Lk, float(scale),
+        float(causal_value), _bf(q), current_stream_ptr()))
+    return dbias

@@ -21,7 +21,7 @@ from types import SimpleNamespace
 import torch
 from torch import nn
 
-from . import ops
+from . import grad_ops, ops
 from ._lib import AtlasB200Error
 
 EMBEDDINGS_DIM: int = 768
@@ -99,6 +99,19 @@ class _Encoder(nn.Module):
     def __init__(self, c):
         super().__init__()
         self.layer = nn.ModuleList([_Layer(c) for _ in range(c.num_hidden_layers)])
+
+
+_warned = set()
+
+
+def _warn_no_dropout(who):
+    """The training path has no dropout kernels yet: say so once instead of silently diverging from the reference."""
+    if who not in _warned:
+        _warned.add(who)
+        import warnings
+
+        warnings.warn(f"atlas_b200.{who}: dropout > 0 is configured but the B200 training path runs WITHOUT dropout "
+                      "(not implemented yet); use --dropout 0 for exact agreement with the reference")
 
 
 class HalfCache:
@@ -209,19 +222,59 @@ class Contriever(nn.Module):
                               kind=0)
         return h.view(B, L, H)
 
+    # ---- training path (autograd through the kernels, grad_ops.py) ---------------------------------------
+    def _encode_train(self, input_ids, attention_mask, token_type_ids=None):
+        """`encode` with autograd: the same GEMM / attention / LayerNorm kernels forward (bias + GELU un-fused so the
+        pre-activations are kept), hand-written backward kernels behind torch.autograd (src/modeling_bert.py:929-1045
+        under `loss.backward()`).  16-bit views of the parameters are made with differentiable casts / concatenations."""
+        g = grad_ops
+        c = self.config
+        pd = self.embeddings.word_embeddings.weight.dtype
+        # fp32 master parameters train through bf16 activations / gradients (fp16 gradients would need loss scaling)
+        dt = pd if pd in (torch.float16, torch.bfloat16) else torch.bfloat16
+        if self.training and max(float(_cfg(c, "hidden_dropout_prob", 0.0) or 0.0),
+                                 float(_cfg(c, "attention_probs_dropout_prob", 0.0) or 0.0)) > 0.0:
+            _warn_no_dropout("Contriever")
+        W = {n: (p if p.dtype == dt else p.to(dt)) for n, p in self.named_parameters()}
+        B, L = input_ids.shape
+        H, nh = c.hidden_size, c.num_attention_heads
+        pad = self.embeddings.word_embeddings.padding_idx
+        x = g.bert_embed_sum(input_ids, token_type_ids, W["embeddings.word_embeddings.weight"],
+                             W["embeddings.token_type_embeddings.weight"], W["embeddings.position_embeddings.weight"],
+                             -1 if pad is None else int(pad))
+        h = g.layernorm(x.view(B * L, H), W["embeddings.LayerNorm.weight"], W["embeddings.LayerNorm.bias"],
+                        c.layer_norm_eps, kind=0)
+        add_mask = (1.0 - attention_mask.to(torch.float32)) * -10000.0
+        for i in range(c.num_hidden_layers):
+            p = f"encoder.layer.{i}."
+            a = p + "attention.self."
+            wqkv = torch.cat([W[a + "query.weight"], W[a + "key.weight"], W[a + "value.weight"]], 0)
+            bqkv = torch.cat([W[a + "query.bias"], W[a + "key.bias"], W[a + "value.bias"]], 0)
+            qkv = g.linear(h, wqkv, bqkv)
+            ctx = g.self_attention(qkv, B, nh, L, add_mask=add_mask, scale=1.0 / math.sqrt(64))
+            s1 = g.linear(ctx, W[p + "attention.output.dense.weight"], W[p + "attention.output.dense.bias"], residual=h)
+            h1 = g.layernorm(s1, W[p + "attention.output.LayerNorm.weight"], W[p + "attention.output.LayerNorm.bias"],
+                             c.layer_norm_eps, kind=0)
+            z = g.linear(h1, W[p + "intermediate.dense.weight"], W[p + "intermediate.dense.bias"])
+            s2 = g.linear(g.gelu_erf(z), W[p + "output.dense.weight"], W[p + "output.dense.bias"], residual=h1)
+            h = g.layernorm(s2, W[p + "output.LayerNorm.weight"], W[p + "output.LayerNorm.bias"], c.layer_norm_eps,
+                            kind=0)
+        return h.view(B, L, H)
+
     def forward(self, input_ids=None, attention_mask=None, token_type_ids=None, position_ids=None, head_mask=None,
                 inputs_embeds=None, encoder_hidden_states=None, encoder_attention_mask=None, output_attentions=None,
                 output_hidden_states=None, normalize=False):
         """src/retrievers.py:22-60.  Returns [B, 768] embeddings in the parameters' dtype."""
-        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
-            raise AtlasB200Error("atlas_b200.Contriever is forward-only in this round: call it under torch.no_grad() "
-                                 "(index build / query embedding); retriever training is not implemented")
         if position_ids is not None or inputs_embeds is not None:
             raise AtlasB200Error("position_ids / inputs_embeds are not used by Atlas and not supported")
-        last_hidden = self.encode(input_ids, attention_mask, token_type_ids)
+        with_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if with_grad:   # retriever training (src/atlas.py:457-465): autograd through the kernels
+            last_hidden = self._encode_train(input_ids, attention_mask, token_type_ids)
+        else:
+            last_hidden = self.encode(input_ids, attention_mask, token_type_ids)
         pooling = self.config.pooling
         if pooling == "average":
-            emb = ops.masked_mean_pool(last_hidden, attention_mask)
+            emb = (grad_ops.masked_mean_pool if with_grad else ops.masked_mean_pool)(last_hidden, attention_mask)
         elif pooling == "cls":
             emb = last_hidden[:, 0].clone()
         else:

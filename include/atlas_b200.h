@@ -176,11 +176,84 @@ int atlas_b200_attention(const void* q, int64_t ldq, int32_t q_col0, const void*
 int atlas_b200_attention_combine(const float* o_partial, const float* ml_partial, int32_t B, int32_t splits,
                                  int32_t Lq, int32_t H, void* out, int64_t ldo, int32_t is_bf16, void* stream);
 
+/* --------------------------------------------------------------------------------------------
+ * Backward pass (training): what autograd derives in the reference's train.py step
+ * (`Atlas.forward` -> `loss.backward()`, src/atlas.py:399-550) for the kernels above.  Weight and
+ * input gradients of the linear layers are atlas_b200_linear calls on transposed operands
+ * (dX = dY . W via W^T, dW = dY^T . X via atlas_b200_transpose); the entry points below are the rest.
+ * -------------------------------------------------------------------------------------------- */
+
+/* Backward of atlas_b200_attention (any Lq / Lk, head_dim 64; csrc/attention_bwd.cu).  q / k / v / out as in the
+ * forward (out = the forward's result [B*Lq, H*64]); dout [B*Lq, H*64]; dq / dk / dv are written at column offsets
+ * d?_col0 + 64h of [B*L, ld] buffers (so one [tokens, 3*H*64] buffer can receive dQ | dK | dV for a fused projection).
+ * dbias_delta [H, Lq+Lk-1] fp32 is INCREMENTED (zero it first; NULL = not needed); lse / dsum are [B, H, Lq] fp32
+ * scratch.  For FiD's cross-attention (src/fid.py:298-349) pass the un-split key range: B = batch, Lk = n_ctx * L.
+ * Replaces autograd through BertSelfAttention.forward (src/modeling_bert.py:328-366) and T5Attention.forward
+ * (src/modeling_t5.py:478-524). */
+int atlas_b200_attention_bwd(const void* q, int64_t ldq, int32_t q_col0, const void* k, int64_t ldk, int32_t k_col0,
+                             const void* v, int64_t ldv, int32_t v_col0, const void* out, int64_t ldo, const void* dout,
+                             int64_t lddo, void* dq, int64_t lddq, int32_t dq_col0, void* dk, int64_t lddk,
+                             int32_t dk_col0, void* dv, int64_t lddv, int32_t dv_col0, const float* add_mask,
+                             const float* bias_delta, float* dbias_delta, float* lse, float* dsum, int32_t B, int32_t H,
+                             int32_t Lq, int32_t Lk, float scale, float causal_value, int32_t is_bf16, void* stream);
+
+/* dst[c, r] = src[r, c] (16-bit elements) for r < R and 0 for R <= r < Rpad: the K-major operands of the weight-gradient
+ * GEMM dW[N, K] = dY^T[N, M] . X[M, K] (contraction over the M tokens, padded to a multiple of 8). */
+int atlas_b200_transpose(const void* src, int64_t lds, void* dst, int64_t ldd, int32_t R, int32_t C, int32_t Rpad,
+                         void* stream);
+
+/* out[n] += sum_m x[m, n]  (fp32; bias gradients of the Linear layers). */
+int atlas_b200_colsum(const void* x, int64_t ld, float* out, int32_t M, int32_t N, int32_t is_bf16, void* stream);
+
+/* Backward of atlas_b200_layernorm (same `kind`): dx = d(norm)/dx . (dy * w) (+ dres when given: the residual
+ * branch's gradient, fused), dweight / dbias fp32 [H] INCREMENTED (dbias only for kind 0). */
+int atlas_b200_layernorm_bwd(const void* x, int64_t ldx, const void* dy, int64_t lddy, const void* weight,
+                             const void* dres, int64_t lddres, void* dx, int64_t lddx, float* dweight, float* dbias,
+                             int32_t rows, int32_t H, float eps, int32_t kind, int32_t is_bf16, void* stream);
+
+/* T5DenseGatedGeluDense (src/modeling_t5.py:281-285) on u [M, 2F] whose columns (2j, 2j+1) hold (x.wi_0[j], x.wi_1[j]):
+ *   dg == NULL: out [M, F]  = r16(gelu_new(u0)) * u1        (training forward: the pre-activations are kept)
+ *   dg != NULL: out [M, 2F] = (dg * u1 * gelu_new'(u0), dg * gelu_new(u0)) interleaved like u. */
+int atlas_b200_gated_gelu(const void* u, int64_t ldu, const void* dg, int64_t lddg, void* out, int64_t ldo, int64_t M,
+                          int32_t F, int32_t is_bf16, void* stream);
+
+/* erf GELU (src/modeling_bert.py:444) on z [M, N]: dy == NULL: out = gelu(z); else out = dy * gelu'(z). */
+int atlas_b200_gelu_erf(const void* z, int64_t ldz, const void* dy, int64_t lddy, void* out, int64_t ldo, int64_t M,
+                        int32_t N, int32_t is_bf16, void* stream);
+
+/* word + token_type + position embeddings WITHOUT the LayerNorm (src/modeling_bert.py:236-243): the training forward
+ * keeps the sum for the LayerNorm backward. */
+int atlas_b200_bert_embed_sum(const int64_t* input_ids, const int64_t* token_type_ids, const void* word_emb,
+                              const void* type_emb, const void* pos_emb, void* y, int32_t batch, int32_t L, int32_t H,
+                              int32_t is_bf16, void* stream);
+
+/* Embedding gradient: dst[index[row], :] += src[row, :] in fp32 (index == NULL: row % modulo, the position ids);
+ * rows whose index equals skip_index (nn.Embedding padding_idx; -1 = none) or lies outside [0, table_rows) are dropped. */
+int atlas_b200_scatter_add_rows(const int64_t* index, int32_t modulo, const void* src, int64_t lds, float* dst,
+                                int64_t rows, int32_t H, int64_t skip_index, int64_t table_rows, int32_t is_bf16,
+                                void* stream);
+
+/* Backward of atlas_b200_masked_mean_pool: dx[b, l, :] = mask[b, l] ? demb[b, :] / sum_l mask[b, l] : 0. */
+int atlas_b200_masked_mean_pool_bwd(const void* demb, int64_t ld_demb, const int64_t* mask, void* dx, int32_t batch,
+                                    int32_t L, int32_t H, int32_t is_bf16, void* stream);
+
+/* CrossEntropyLoss(ignore_index=-100) over 16-bit logits [rows, V] (src/modeling_t5.py:1650-1652):
+ *   fwd: lse[row] = logsumexp(logits[row]), loss[row] = lse - logits[row, label] (0 for ignored rows); the caller
+ *        divides the sum by the number of valid rows.
+ *   bwd: dlogits[row, c] = (softmax(logits[row])[c] - [c == label]) * gscale[0] (0 for ignored rows); gscale is a
+ *        device scalar (upstream gradient / number of valid rows), so no host synchronisation is needed. */
+int atlas_b200_cross_entropy_fwd(const void* logits, int64_t ld, const int64_t* labels, float* lse, float* loss,
+                                 int32_t rows, int32_t V, int32_t is_bf16, void* stream);
+int atlas_b200_cross_entropy_bwd(const void* logits, int64_t ld, const int64_t* labels, const float* lse,
+                                 const float* gscale, void* dlogits, int64_t ldd, int32_t rows, int32_t V, int32_t is_bf16,
+                                 void* stream);
+
 /* Measurement hook for bench.py's roofline: while enabled, every launch of ONE kind of kernel is bracketed
  * with CUDA events on its launching stream:
  *   kind 1  the bank sweep of atlas_b200_mips_topk (work = algorithmic bytes swept)
  *   kind 2  the tcgen05 GEMM of atlas_b200_linear   (work = 2*M*N*K FLOPs)
  *   kind 3  the attention kernel                     (work = 4*B*H*Lq*Lk*64 FLOPs)
+ *   kind 4  the attention backward kernels           (work = 16*B*H*Lq*Lk*64 FLOPs)
  *   kind 0  off (default).
  * atlas_b200_profile_work() returns the work summed over the bracketed launches so far;
  * atlas_b200_profile_collect() synchronises the events, returns the summed kernel time and the number of

@@ -157,3 +157,54 @@ def test_contriever_cpu_restatement_matches_reference():
     with torch.no_grad():
         emb = fid_cpu.contriever_forward(sd, model_synth.CONTRIEVER_CFG, ids, mask)
     assert np.abs(emb.numpy() - g["emb_fp32"]).max() < 2e-4
+
+
+# ---- gradients: the autograd of the CPU restatements against the reference's own loss.backward() -------------------
+def _shift_right(labels):
+    import torch
+
+    s = labels.new_zeros(labels.shape)
+    s[..., 1:] = labels[..., :-1].clone()
+    s[..., 0] = 0
+    return s.masked_fill(s == -100, 0)
+
+
+@pytest.mark.parametrize("which", ["fid", "contriever"])
+def test_gradient_oracle_matches_reference(which):
+    import torch
+
+    import fid_cpu
+    import grad_oracle
+    import model_synth
+
+    g = np.load(os.path.join(GOLDEN_DIR, "grads_tiny.npz"))
+    if which == "fid":
+        from atlas_b200.fid import FiD, T5ConfigLite
+
+        cfg = {k: v for k, v in model_synth.T5_CFG.items() if k not in ("dropout_rate", "is_encoder_decoder", "use_cache")}
+        sd, sha = model_synth.fill_state_dict(FiD(T5ConfigLite(**cfg)).state_dict(), 202)
+        ids, mask, labels = model_synth.fid_inputs()
+        loss, grads = grad_oracle.fid_grads(sd, model_synth.T5_CFG, ids, mask, labels, 3, _shift_right)
+    else:
+        from atlas_b200.retrievers import BertConfigLite, Contriever
+
+        sd, sha = model_synth.fill_state_dict(Contriever(BertConfigLite(**model_synth.CONTRIEVER_CFG)).state_dict(), 101)
+        ids, mask = model_synth.contriever_inputs()
+        loss, grads = grad_oracle.contriever_grads(sd, model_synth.CONTRIEVER_CFG, ids, mask)
+    assert sha == str(g[f"{which}/weights_sha256"])
+    assert abs(loss - float(g[f"{which}_fp32/loss"])) <= 2e-5 * abs(loss)
+    names = [n[len(which) + 11:] for n in g.files if n.startswith(f"{which}_fp32/norm/")]
+    assert len(names) >= 30 and set(names) <= set(grads)
+    top = max(float(g[f"{which}_fp32/norm/{n}"]) for n in names)
+    for n in names:
+        gr = grads[n].numpy()
+        ref_norm = float(g[f"{which}_fp32/norm/{n}"])
+        if ref_norm < 1e-6 * top:            # mathematically zero gradients (BERT key bias): noise in the reference too
+            assert np.linalg.norm(gr) < 1e-5 * top
+            continue
+        assert abs(np.linalg.norm(gr) - ref_norm) <= 2e-4 * ref_norm, n
+        proj = float((gr * grad_oracle.direction(n, gr.shape)).sum())
+        assert abs(proj - float(g[f"{which}_fp32/proj/{n}"])) <= 2e-3 * ref_norm, n
+        key = f"{which}_fp32/full/{n}"
+        if key in g.files:
+            assert np.abs(gr - g[key]).max() <= 2e-4 * np.abs(g[key]).max() + 1e-7, n
