@@ -97,8 +97,15 @@ def lib():
     i32, i64, vp, f32 = c.c_int32, c.c_int64, c.c_void_p, c.c_float
     L.atlas_b200_attention_bwd.restype = c.c_int
     L.atlas_b200_attention_bwd.argtypes = [vp, i64, i32, vp, i64, i32, vp, i64, i32, vp, i64, vp, i64, vp, i64, i32, vp,
-                                           i64, i32, vp, i64, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, f32, i32,
-                                           vp]
+                                           i64, i32, vp, i64, i32, vp, vp, vp, vp, i32, vp, vp, i32, i32, i32, i32, f32,
+                                           f32, i32, vp]
+    L.atlas_b200_attention_ex.restype = c.c_int
+    L.atlas_b200_attention_ex.argtypes = [vp, i64, i32, vp, i64, i32, vp, i64, i32, vp, i64, vp, vp, i32, i32, i32, i32,
+                                          f32, f32, i32, vp, vp, vp, i32, vp]
+    L.atlas_b200_attention_combine_ex.restype = c.c_int
+    L.atlas_b200_attention_combine_ex.argtypes = [vp, vp, i32, i32, i32, i32, vp, i64, vp, i32, vp]
+    L.atlas_b200_linear_wgrad.restype = c.c_int
+    L.atlas_b200_linear_wgrad.argtypes = [vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, vp]
     L.atlas_b200_transpose.restype = c.c_int
     L.atlas_b200_transpose.argtypes = [vp, i64, vp, i64, i32, i32, i32, vp]
     L.atlas_b200_colsum.restype = c.c_int
@@ -146,6 +153,9 @@ EXPORTED_SYMBOLS = [
     "atlas_b200_profile_work",
     "atlas_b200_profile_collect",
     "atlas_b200_attention_bwd",
+    "atlas_b200_attention_ex",
+    "atlas_b200_attention_combine_ex",
+    "atlas_b200_linear_wgrad",
     "atlas_b200_transpose",
     "atlas_b200_colsum",
     "atlas_b200_layernorm_bwd",

@@ -58,6 +58,7 @@ struct Params {
     int q_div;
     float* o_partial;         // [B*Lq, H*64] fp32 or nullptr
     float* ml_partial;        // [B*Lq, H, 2] fp32
+    float* lse_out;           // [B, H, Lq] fp32 row log-sum-exp (natural log) for the backward pass, or nullptr
 };
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
@@ -343,6 +344,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 }
             } else {
                 const float inv = 1.0f / sum;
+                if (p.lse_out != nullptr && part == 0)
+                    p.lse_out[(static_cast<size_t>(b) * p.H + h) * p.Lq + i] = mx * (1.0f / LOG2E) + __logf(sum);
                 uint4* dst = reinterpret_cast<uint4*>(p.O + (static_cast<size_t>(b) * p.Lq + i) * p.ldo + h * D + part * OC);
 #pragma unroll
                 for (int v4 = 0; v4 < OC / 8; ++v4)
@@ -722,6 +725,8 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                 ml[0] = M * (1.0f / LOG2E);
                 ml[1] = den;
             }
+            if (!partial && p.lse_out != nullptr && part == 0 && i < p.Lq)
+                p.lse_out[(static_cast<size_t>(b) * p.H + h) * p.Lq + i] = M * (1.0f / LOG2E) + __logf(den);
         };
 
         int g = 0, item_it = 0;
@@ -813,7 +818,7 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
 // out[b, i, h, :] = sum_s w_s O_s / sum_s w_s l_s with w_s = exp(m_s - max_s m_s); one warp per (b, i, h)
 template <bool kBF16>
 __global__ void combine_splits_kernel(const float* __restrict__ o_partial, const float* __restrict__ ml, int B, int splits,
-                                      int Lq, int H, uint16_t* __restrict__ out, int64_t ldo) {
+                                      int Lq, int H, uint16_t* __restrict__ out, int64_t ldo, float* __restrict__ lse_out) {
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (w >= B * Lq * H) return;
@@ -833,6 +838,7 @@ __global__ void combine_splits_kernel(const float* __restrict__ o_partial, const
         acc1 += wgt * o.y;
     }
     const float inv = 1.0f / den;
+    if (lse_out != nullptr && lane == 0) lse_out[(static_cast<size_t>(b) * H + h) * Lq + i] = M + __logf(den);
     reinterpret_cast<uint32_t*>(out + (static_cast<size_t>(b) * Lq + i) * ldo + h * D)[lane] =
         pack2<kBF16>(acc0 * inv, acc1 * inv);
 }
@@ -846,7 +852,17 @@ int atlas_b200_attention(const void* q, int64_t ldq, int32_t q_col0, const void*
                          const float* bias_delta, int32_t B, int32_t H, int32_t Lq, int32_t Lk, float scale,
                          float causal_value, int32_t q_div, float* o_partial, float* ml_partial, int32_t is_bf16,
                          void* stream) {
+    return atlas_b200_attention_ex(q, ldq, q_col0, k, ldk, k_col0, v, ldv, v_col0, out, ldo, add_mask, bias_delta, B, H, Lq,
+                                   Lk, scale, causal_value, q_div, o_partial, ml_partial, nullptr, is_bf16, stream);
+}
+
+int atlas_b200_attention_ex(const void* q, int64_t ldq, int32_t q_col0, const void* k, int64_t ldk, int32_t k_col0,
+                            const void* v, int64_t ldv, int32_t v_col0, void* out, int64_t ldo, const float* add_mask,
+                            const float* bias_delta, int32_t B, int32_t H, int32_t Lq, int32_t Lk, float scale,
+                            float causal_value, int32_t q_div, float* o_partial, float* ml_partial, float* lse_out,
+                            int32_t is_bf16, void* stream) {
     using namespace attn;
+    AB_REQUIRE(lse_out == nullptr || o_partial == nullptr, "attention: lse_out is produced by attention_combine in split mode");
     AB_REQUIRE(q_div >= 1 && B % q_div == 0, "attention: q_div must divide the number of key segments");
     AB_REQUIRE((o_partial == nullptr) == (ml_partial == nullptr), "attention: partial outputs come in pairs");
     AB_REQUIRE(B >= 0 && H > 0 && Lq > 0 && Lk > 0 && Lk <= MAX_LK, "attention: need 0 < Lk <= %d (got Lq=%d Lk=%d)",
@@ -883,6 +899,7 @@ int atlas_b200_attention(const void* q, int64_t ldq, int32_t q_col0, const void*
     p.q_div = q_div;
     p.o_partial = o_partial;
     p.ml_partial = ml_partial;
+    p.lse_out = lse_out;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int items = B * H;
     const int grid = items < abh::num_sms() ? items : abh::num_sms();
@@ -911,6 +928,11 @@ int atlas_b200_attention(const void* q, int64_t ldq, int32_t q_col0, const void*
 
 int atlas_b200_attention_combine(const float* o_partial, const float* ml_partial, int32_t B, int32_t splits, int32_t Lq,
                                  int32_t H, void* out, int64_t ldo, int32_t is_bf16, void* stream) {
+    return atlas_b200_attention_combine_ex(o_partial, ml_partial, B, splits, Lq, H, out, ldo, nullptr, is_bf16, stream);
+}
+
+int atlas_b200_attention_combine_ex(const float* o_partial, const float* ml_partial, int32_t B, int32_t splits, int32_t Lq,
+                                    int32_t H, void* out, int64_t ldo, float* lse_out, int32_t is_bf16, void* stream) {
     AB_REQUIRE(B >= 0 && splits >= 1 && Lq > 0 && H > 0 && ldo % 2 == 0, "attention_combine: bad shape");
     if (B == 0) return ATLAS_B200_OK;
     const int warps = B * Lq * H;
@@ -918,10 +940,10 @@ int atlas_b200_attention_combine(const float* o_partial, const float* ml_partial
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (is_bf16)
         attn::combine_splits_kernel<true><<<grid, 256, 0, s>>>(o_partial, ml_partial, B, splits, Lq, H,
-                                                               static_cast<uint16_t*>(out), ldo);
+                                                               static_cast<uint16_t*>(out), ldo, lse_out);
     else
         attn::combine_splits_kernel<false><<<grid, 256, 0, s>>>(o_partial, ml_partial, B, splits, Lq, H,
-                                                                static_cast<uint16_t*>(out), ldo);
+                                                                static_cast<uint16_t*>(out), ldo, lse_out);
     abh::count_launch();
     AB_CUDA_CHECK(cudaGetLastError());
     return ATLAS_B200_OK;

@@ -38,8 +38,10 @@ struct Params {
     const float* add_mask;    // [B, Lk] or nullptr
     const float* bias_delta;  // [H, Lq + Lk - 1] or nullptr
     float* dbias;             // [H, Lq + Lk - 1] (+=, atomics) or nullptr
-    float* lse;               // [B, H, Lq]
+    float* lse;               // [B, H, Lq]  (input when lse_given: written by the forward kernels)
     float* dsum;              // [B, H, Lq]
+    float* dq_accum;          // [B*Lq, H*64] fp32 (+=, atomics) when the keys are split over `key_chunks` CTAs, else nullptr
+    int lse_given, key_chunks;
     int B, H, Lq, Lk;
     float scale, causal_value;
 };
@@ -180,9 +182,11 @@ attn_bwd_dq_kernel(const Params p) {
     float* dbias_s = p.dbias ? reinterpret_cast<float*>(smem + 4 * TILE_BYTES) + (p.bias_delta ? ntab : 0) : nullptr;
 
     const int nqb = (p.Lq + BM - 1) / BM;
-    const int qb = static_cast<int>(blockIdx.x) % nqb;
-    const int h = (static_cast<int>(blockIdx.x) / nqb) % p.H;
-    const int b = static_cast<int>(blockIdx.x) / (nqb * p.H);
+    const int chunk = static_cast<int>(blockIdx.x) % p.key_chunks;     // this CTA's share of the keys (cross-attention)
+    const int item = static_cast<int>(blockIdx.x) / p.key_chunks;
+    const int qb = item % nqb;
+    const int h = (item / nqb) % p.H;
+    const int b = item / (nqb * p.H);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int q0 = qb * BM;
     const int64_t qrow_base = static_cast<int64_t>(b) * p.Lq, krow_base = static_cast<int64_t>(b) * p.Lk;
@@ -231,9 +235,9 @@ attn_bwd_dq_kernel(const Params p) {
     const int nkb = (p.Lk + BN - 1) / BN;
     const int i_lo = q0 + warp * 16 + g;   // this thread's rows: i_lo and i_lo + 8
 
-    // ---- pass 1: row max / sum of exp -> log-sum-exp -----------------------------------------------------------------
+    // ---- pass 1: row max / sum of exp -> log-sum-exp (skipped when the forward kernel saved it) ----------------------
     float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
-    for (int kb = 0; kb < nkb; ++kb) {
+    for (int kb = 0; kb < (p.lse_given ? 0 : nkb); ++kb) {
         __syncthreads();
         load_tile(sK, p.k, p.ldk, p.k_col0 + h * D, krow_base, kb * BN, p.Lk);
         __syncthreads();
@@ -275,10 +279,18 @@ attn_bwd_dq_kernel(const Params p) {
     float lse[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
-        lse[r] = m_run[r] + __logf(l_run[r]);
         const int i = i_lo + r * 8;
-        if (t == 0 && i < p.Lq) p.lse[(static_cast<int64_t>(b) * p.H + h) * p.Lq + i] = lse[r];
+        if (p.lse_given) {
+            // padding rows: +inf makes every probability 0 (their dO rows are zero as well)
+            lse[r] = i < p.Lq ? __ldg(p.lse + (static_cast<int64_t>(b) * p.H + h) * p.Lq + i) : INFINITY;
+        } else {
+            lse[r] = m_run[r] + __logf(l_run[r]);
+            if (t == 0 && i < p.Lq) p.lse[(static_cast<int64_t>(b) * p.H + h) * p.Lq + i] = lse[r];
+        }
     }
+    const int per_chunk = (nkb + p.key_chunks - 1) / p.key_chunks;
+    const int kb_begin = chunk * per_chunk;
+    const int kb_end = min(nkb, kb_begin + per_chunk);
 
     // ---- pass 2: dQ = scale * (P o (dO V^T - D)) K --------------------------------------------------------------------
     float dqacc[8][4];
@@ -286,7 +298,7 @@ attn_bwd_dq_kernel(const Params p) {
     for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
         for (int e = 0; e < 4; ++e) dqacc[nt][e] = 0.f;
-    for (int kb = 0; kb < nkb; ++kb) {
+    for (int kb = kb_begin; kb < kb_end; ++kb) {
         __syncthreads();
         load_tile(sK, p.k, p.ldk, p.k_col0 + h * D, krow_base, kb * BN, p.Lk);
         load_tile(sV, p.v, p.ldv, p.v_col0 + h * D, krow_base, kb * BN, p.Lk);
@@ -314,7 +326,22 @@ attn_bwd_dq_kernel(const Params p) {
             }
         mma_p_tile<kBF16>(dqacc, acc, sK_a, lane);
     }
-    store_acc<kBF16>(dqacc, p.scale, p.dq, p.lddq, p.dq_col0 + h * D, qrow_base, q0 + warp * 16, p.Lq, lane);
+    if (p.dq_accum != nullptr) {
+        // keys split over several CTAs: fp32 partial sums, converted to 16 bits by the caller afterwards
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int i = i_lo + half * 8;
+            if (i >= p.Lq) continue;
+            float* row = p.dq_accum + (qrow_base + i) * (static_cast<int64_t>(p.H) * D) + h * D;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                atomicAdd(row + nt * 8 + 2 * t, dqacc[nt][2 * half] * p.scale);
+                atomicAdd(row + nt * 8 + 2 * t + 1, dqacc[nt][2 * half + 1] * p.scale);
+            }
+        }
+    } else {
+        store_acc<kBF16>(dqacc, p.scale, p.dq, p.lddq, p.dq_col0 + h * D, qrow_base, q0 + warp * 16, p.Lq, lane);
+    }
     if (dbias_s != nullptr) {
         __syncthreads();
         for (int x = threadIdx.x; x < ntab; x += THREADS) {
@@ -416,9 +443,12 @@ int atlas_b200_attention_bwd(const void* q, int64_t ldq, int32_t q_col0, const v
                              const void* v, int64_t ldv, int32_t v_col0, const void* out, int64_t ldo, const void* dout,
                              int64_t lddo, void* dq, int64_t lddq, int32_t dq_col0, void* dk, int64_t lddk,
                              int32_t dk_col0, void* dv, int64_t lddv, int32_t dv_col0, const float* add_mask,
-                             const float* bias_delta, float* dbias_delta, float* lse, float* dsum, int32_t B, int32_t H,
-                             int32_t Lq, int32_t Lk, float scale, float causal_value, int32_t is_bf16, void* stream) {
+                             const float* bias_delta, float* dbias_delta, float* lse, int32_t lse_given, float* dsum,
+                             float* dq_accum, int32_t B, int32_t H, int32_t Lq, int32_t Lk, float scale,
+                             float causal_value, int32_t is_bf16, void* stream) {
     using namespace attnb;
+    AB_REQUIRE(dq_accum == nullptr || (lse_given != 0 && dbias_delta == nullptr),
+               "attention_bwd: dq_accum (keys split over CTAs) needs the forward's lse and no dbias");
     AB_REQUIRE(B >= 0 && H > 0 && Lq > 0 && Lk > 0, "attention_bwd: bad shape B=%d H=%d Lq=%d Lk=%d", B, H, Lq, Lk);
     AB_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && lddo % 8 == 0 && lddq % 8 == 0 &&
                    lddk % 8 == 0 && lddv % 8 == 0 && q_col0 % 8 == 0 && k_col0 % 8 == 0 && v_col0 % 8 == 0 &&
@@ -430,7 +460,17 @@ int atlas_b200_attention_bwd(const void* q, int64_t ldq, int32_t q_col0, const v
     AB_REQUIRE(bias_delta == nullptr || ntab <= 8192, "attention_bwd: Lq + Lk - 1 = %lld exceeds the bias table (8192)",
                static_cast<long long>(ntab));
     if (B == 0) return ATLAS_B200_OK;
-    const int64_t nq_ctas = static_cast<int64_t>(B) * H * ((Lq + BM - 1) / BM);
+    // split the keys of a long, few-query attention (FiD cross-attention: 32 queries x 15 360 keys) over enough CTAs to
+    // fill the GPU; each CTA keeps >= 4 key blocks so the atomics stay a small part of its work
+    int key_chunks = 1;
+    if (dq_accum != nullptr) {
+        const int nkb = (Lk + BN - 1) / BN;
+        const int64_t base = static_cast<int64_t>(B) * H * ((Lq + BM - 1) / BM);
+        const int64_t want = (2ll * abh::num_sms() + base - 1) / base;
+        key_chunks = static_cast<int>(want < 1 ? 1 : (want > (nkb + 3) / 4 ? (nkb + 3) / 4 : want));
+        if (key_chunks < 1) key_chunks = 1;
+    }
+    const int64_t nq_ctas = static_cast<int64_t>(B) * H * ((Lq + BM - 1) / BM) * key_chunks;
     const int64_t nk_ctas = static_cast<int64_t>(B) * H * ((Lk + BM - 1) / BM);
     AB_REQUIRE(nq_ctas < (1ll << 31) && nk_ctas < (1ll << 31), "attention_bwd: grid too large");
     Params p;
@@ -451,6 +491,9 @@ int atlas_b200_attention_bwd(const void* q, int64_t ldq, int32_t q_col0, const v
     p.dbias = dbias_delta;
     p.lse = lse;
     p.dsum = dsum;
+    p.dq_accum = dq_accum;
+    p.lse_given = lse_given;
+    p.key_chunks = key_chunks;
     p.B = B; p.H = H; p.Lq = Lq; p.Lk = Lk;
     p.scale = scale;
     p.causal_value = causal_value;

@@ -112,7 +112,24 @@ __device__ __forceinline__ float gelu_new(float x) {
     return x * r;
 }
 
-template <bool kBF16, int BLOCK_N, bool kPair>
+// smem descriptor of an MN-major operand tile: 64-element (128-byte) MN blocks, each [BLOCK_K rows][128 B] with the 128B
+// swizzle exactly as a TMA box {64, BLOCK_K} writes it, consecutive MN blocks `lbo_bytes` apart (LBO), 8-row K groups
+// 1024 bytes apart (SBO); one UMMA_K = 16 step advances the start address by 16 rows = 2048 bytes.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
+// kTN = false: C = A[M, K] . W[N, K]^T, both operands K-major (activations x nn.Linear weight).
+// kTN = true : C[M, N] = A[K, M]^T . W[K, N]: both operands MN-major, i.e. the contraction runs over the ROWS of two
+//              row-major matrices - the weight gradient dW[N_out, K_in] = dY[tokens, N_out]^T . X[tokens, K_in] without
+//              transposing either activation matrix (rows past K are zero-filled by TMA: no padding needed).
+template <bool kBF16, int BLOCK_N, bool kPair, bool kTN>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
     using C = Cfg<BLOCK_N, kPair>;
@@ -173,7 +190,32 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 for (int kb = 0; kb < num_kb; ++kb) {
                     ab::mbar_wait(&empty_bar[stage], phase ^ 1u, 11);
                     uint8_t* st = smem_gen + stage * C::STAGE_BYTES;
-                    if constexpr (kPair) {
+                    if constexpr (kTN) {
+                        // boxes of {64 columns (one swizzle atom along MN), 64 contraction rows}
+                        if constexpr (kPair) {
+                            if (leader) ab::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+                        } else {
+                            ab::mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+                        }
+#pragma unroll
+                        for (int j = 0; j < BLOCK_M / 64; ++j) {
+                            if constexpr (kPair)
+                                ab::tma_load_2d_2sm(&tmap_a, &full_bar[stage], st + j * 8192, a_row + 64 * j, kb * BLOCK_K,
+                                                    ab::kEvictNormal);
+                            else
+                                ab::tma_load_2d(&tmap_a, &full_bar[stage], st + j * 8192, a_row + 64 * j, kb * BLOCK_K,
+                                                ab::kEvictNormal);
+                        }
+#pragma unroll
+                        for (int j = 0; j < C::B_ROWS / 64; ++j) {
+                            if constexpr (kPair)
+                                ab::tma_load_2d_2sm(&tmap_b, &full_bar[stage], st + C::A_BYTES + j * 8192, b_row + 64 * j,
+                                                    kb * BLOCK_K, ab::kEvictNormal);
+                            else
+                                ab::tma_load_2d(&tmap_b, &full_bar[stage], st + C::A_BYTES + j * 8192, b_row + 64 * j,
+                                                kb * BLOCK_K, ab::kEvictNormal);
+                        }
+                    } else if constexpr (kPair) {
                         // the leader's barrier collects the bytes of BOTH CTAs' boxes
                         if (leader) ab::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
                         ab::tma_load_2d_2sm(&tmap_a, &full_bar[stage], st, kb * BLOCK_K, a_row, ab::kEvictNormal);
@@ -195,7 +237,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     } else if (warp == 1) {
         // MMA issuer (leader CTA of a pair only)
         if (lane == 0 && leader) {
-            constexpr uint32_t idesc = ab::umma_idesc_f16(C::UMMA_M, BLOCK_N, kBF16);
+            // bits 15 / 16: A / B operand is MN-major
+            constexpr uint32_t idesc = ab::umma_idesc_f16(C::UMMA_M, BLOCK_N, kBF16) | (kTN ? ((1u << 15) | (1u << 16)) : 0u);
             uint32_t stage = 0, phase = 0;
             int it = 0;
             for (int t = group; t < num_tiles; t += num_groups, ++it) {
@@ -206,12 +249,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 for (int kb = 0; kb < num_kb; ++kb) {
                     ab::mbar_wait(&full_bar[stage], phase, 13);
                     ab::tc_fence_after();
-                    const uint64_t adesc0 = ab::umma_desc_k_sw128(smem_base + stage * C::STAGE_BYTES);
-                    const uint64_t bdesc0 = ab::umma_desc_k_sw128(smem_base + stage * C::STAGE_BYTES + C::A_BYTES);
+                    if constexpr (kTN) {
+                        const uint64_t adesc0 = umma_desc_mn_sw128(smem_base + stage * C::STAGE_BYTES, 8192);
+                        const uint64_t bdesc0 = umma_desc_mn_sw128(smem_base + stage * C::STAGE_BYTES + C::A_BYTES, 8192);
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                        ab::umma_ss<C::CTAS>(d_tmem, adesc0 + ((k * UMMA_K * 2) >> 4), bdesc0 + ((k * UMMA_K * 2) >> 4),
-                                             idesc, (kb | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                            ab::umma_ss<C::CTAS>(d_tmem, adesc0 + ((k * UMMA_K * 128) >> 4),
+                                                 bdesc0 + ((k * UMMA_K * 128) >> 4), idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
+                    } else {
+                        const uint64_t adesc0 = ab::umma_desc_k_sw128(smem_base + stage * C::STAGE_BYTES);
+                        const uint64_t bdesc0 = ab::umma_desc_k_sw128(smem_base + stage * C::STAGE_BYTES + C::A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                            ab::umma_ss<C::CTAS>(d_tmem, adesc0 + ((k * UMMA_K * 2) >> 4),
+                                                 bdesc0 + ((k * UMMA_K * 2) >> 4), idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
                     }
                     if constexpr (kPair) {
                         ab::umma_commit_2sm(&empty_bar[stage], 0x3);
@@ -348,12 +401,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
 }
 
-template <bool kBF16, int BLOCK_N, bool kPair>
+template <bool kBF16, int BLOCK_N, bool kPair, bool kTN = false>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, cudaStream_t s) {
     using C = Cfg<BLOCK_N, kPair>;
     static bool attr_set = false;
     if (!attr_set) {
-        AB_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<kBF16, BLOCK_N, kPair>,
+        AB_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<kBF16, BLOCK_N, kPair, kTN>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         attr_set = true;
     }
@@ -375,9 +428,9 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        AB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<kBF16, BLOCK_N, kPair>, ta, tb, p));
+        AB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<kBF16, BLOCK_N, kPair, kTN>, ta, tb, p));
     } else {
-        gemm_kernel<kBF16, BLOCK_N, kPair><<<grid, THREADS, C::SMEM_BYTES, s>>>(ta, tb, p);
+        gemm_kernel<kBF16, BLOCK_N, kPair, kTN><<<grid, THREADS, C::SMEM_BYTES, s>>>(ta, tb, p);
     }
     abh::prof_end(s, abh::PROF_LINEAR, 2.0 * p.M * static_cast<double>(p.N) * p.K);
     abh::count_launch();
@@ -450,6 +503,46 @@ int atlas_b200_linear_ex(const void* A, int64_t lda, const void* W, int64_t ldw,
     }
     if (is_bf16) return wide ? launch<true, 256, false>(ta, tb, p, s) : launch<true, 128, false>(ta, tb, p, s);
     return wide ? launch<false, 256, false>(ta, tb, p, s) : launch<false, 128, false>(ta, tb, p, s);
+}
+
+int atlas_b200_linear_wgrad(const void* dY, int64_t lddy, const void* X, int64_t ldx, void* dW, int64_t lddw, int32_t tokens,
+                            int32_t N, int32_t K, int32_t is_bf16, void* stream) {
+    using namespace gemm;
+    AB_REQUIRE(tokens >= 0 && N > 0 && K > 0, "bad wgrad shape tokens=%d N=%d K=%d", tokens, N, K);
+    AB_REQUIRE(N % 8 == 0 && K % 8 == 0 && lddy % 8 == 0 && ldx % 8 == 0 && lddw % 8 == 0,
+               "wgrad: N, K and the leading dimensions must be multiples of 8 (16-byte rows)");
+    AB_REQUIRE((reinterpret_cast<uintptr_t>(dW) & 15u) == 0, "dW must be 16-byte aligned");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (tokens == 0) {
+        AB_CUDA_CHECK(cudaMemset2DAsync(dW, static_cast<size_t>(lddw) * 2, 0, static_cast<size_t>(K) * 2, N, s));
+        return ATLAS_B200_OK;
+    }
+    Params p;
+    p.row_ss = nullptr;
+    p.out_ss = nullptr;
+    p.rs_eps = 0.f;
+    p.M = N;            // output rows  = out_features
+    p.N = K;            // output cols  = in_features
+    p.K = tokens;       // contraction  = tokens
+    p.ldc = static_cast<int>(lddw);
+    p.ldr = 0;
+    p.epi = EPI_NONE;
+    p.bias = nullptr;
+    p.residual = nullptr;
+    p.C = static_cast<uint16_t*>(dW);
+    const bool wide = K >= 256;
+    const bool pair = K >= 256 && N >= 256;
+    CUtensorMap ta, tb;
+    // both maps: rows = tokens, box = {64 columns, 64 tokens}
+    int rc = abh::make_tmap_2d_16bit(&ta, dY, static_cast<uint64_t>(tokens), static_cast<uint64_t>(N),
+                                     static_cast<uint64_t>(lddy), BLOCK_K, 64, is_bf16 != 0);
+    if (rc) return rc;
+    rc = abh::make_tmap_2d_16bit(&tb, X, static_cast<uint64_t>(tokens), static_cast<uint64_t>(K), static_cast<uint64_t>(ldx),
+                                 BLOCK_K, 64, is_bf16 != 0);
+    if (rc) return rc;
+    if (pair) return is_bf16 ? launch<true, 256, true, true>(ta, tb, p, s) : launch<false, 256, true, true>(ta, tb, p, s);
+    if (is_bf16) return wide ? launch<true, 256, false, true>(ta, tb, p, s) : launch<true, 128, false, true>(ta, tb, p, s);
+    return wide ? launch<false, 256, false, true>(ta, tb, p, s) : launch<false, 128, false, true>(ta, tb, p, s);
 }
 
 }  // extern "C"

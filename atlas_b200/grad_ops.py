@@ -79,21 +79,21 @@ class _SelfAttention(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, qkv, bias_delta, add_mask, B, H, L, scale, causal_value):
-        out = ops.attention(qkv, 0, qkv, H * 64, qkv, 2 * H * 64, B, H, L, L, add_mask=add_mask, bias_delta=bias_delta,
-                            scale=scale, causal_value=causal_value)
-        ctx.save_for_backward(qkv, out, bias_delta, add_mask)
+        out, lse = ops.attention(qkv, 0, qkv, H * 64, qkv, 2 * H * 64, B, H, L, L, add_mask=add_mask,
+                                 bias_delta=bias_delta, scale=scale, causal_value=causal_value, return_lse=True)
+        ctx.save_for_backward(qkv, out, bias_delta, add_mask, lse)
         ctx.dims = (B, H, L, scale, causal_value)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        qkv, out, bias_delta, add_mask = ctx.saved_tensors
+        qkv, out, bias_delta, add_mask, lse = ctx.saved_tensors
         B, H, L, scale, causal_value = ctx.dims
         dqkv = torch.empty_like(qkv)
         dbias = ops.attention_bwd(qkv, 0, qkv, H * 64, qkv, 2 * H * 64, out, dout.contiguous(), dqkv, 0, dqkv, H * 64,
                                   dqkv, 2 * H * 64, B, H, L, L, add_mask=add_mask, bias_delta=bias_delta,
                                   need_dbias=bias_delta is not None and _need(ctx, 1), scale=scale,
-                                  causal_value=causal_value)
+                                  causal_value=causal_value, lse=lse)
         return dqkv, dbias, None, None, None, None, None, None
 
 
@@ -106,19 +106,20 @@ class _CrossAttention(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, q, kv, add_mask, B, H, T, Lk, scale, split):
-        out = ops.cross_attention_split(q, 0, kv, 0, H * 64, B, H, T, Lk, add_mask=add_mask, scale=scale, split=split)
-        ctx.save_for_backward(q, kv, out, add_mask)
+        out, lse = ops.cross_attention_split(q, 0, kv, 0, H * 64, B, H, T, Lk, add_mask=add_mask, scale=scale,
+                                             split=split, return_lse=True)
+        ctx.save_for_backward(q, kv, out, add_mask, lse)
         ctx.dims = (B, H, T, Lk, scale)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        q, kv, out, add_mask = ctx.saved_tensors
+        q, kv, out, add_mask, lse = ctx.saved_tensors
         B, H, T, Lk, scale = ctx.dims
-        dq = torch.empty_like(q)
+        dq = torch.empty((B * T, H * 64), dtype=q.dtype, device=q.device)
         dkv = torch.empty_like(kv)
         ops.attention_bwd(q, 0, kv, 0, kv, H * 64, out, dout.contiguous(), dq, 0, dkv, 0, dkv, H * 64, B, H, T, Lk,
-                          add_mask=add_mask, scale=scale)
+                          add_mask=add_mask, scale=scale, lse=lse, split_keys=Lk > 1024)
         return dq, dkv, None, None, None, None, None, None, None
 
 

@@ -4,6 +4,7 @@ torch owns the device memory and the stream; the arithmetic happens in `lib/liba
 Nothing here falls back to torch ops: a missing library or a CPU tensor raises.
 """
 import ctypes
+import os
 
 import torch
 
@@ -244,21 +245,25 @@ def masked_mean_pool(x, mask, out=None):
 
 
 def attention(q, q_col0, k, k_col0, v, v_col0, B, H, Lq, Lk, add_mask=None, bias_delta=None, scale=1.0,
-              causal_value=0.0, out=None):
-    """Fused attention reading Q/K/V in place from [B*L, ld] projection buffers (head h at col0 + 64h)."""
+              causal_value=0.0, out=None, return_lse=False):
+    """Fused attention reading Q/K/V in place from [B*L, ld] projection buffers (head h at col0 + 64h).
+    return_lse: also return the row log-sum-exp [B, H, Lq] fp32 (saved for the backward pass)."""
     require_cuda(q, "q")
     if out is None:
         out = torch.empty((B * Lq, H * 64), dtype=q.dtype, device=q.device)
     am = add_mask.float().contiguous() if add_mask is not None else None
     bd = bias_delta.float().contiguous() if bias_delta is not None else None
-    check(lib().atlas_b200_attention(_ptr(q), q.stride(0), q_col0, _ptr(k), k.stride(0), k_col0, _ptr(v), v.stride(0),
-                                     v_col0, _ptr(out), out.stride(0), _ptr(am) if am is not None else None,
-                                     _ptr(bd) if bd is not None else None, B, H, Lq, Lk, float(scale),
-                                     float(causal_value), 1, None, None, _bf(q), current_stream_ptr()))
-    return out
+    lse = torch.empty((B, H, Lq), dtype=torch.float32, device=q.device) if return_lse else None
+    check(lib().atlas_b200_attention_ex(_ptr(q), q.stride(0), q_col0, _ptr(k), k.stride(0), k_col0, _ptr(v), v.stride(0),
+                                        v_col0, _ptr(out), out.stride(0), _ptr(am) if am is not None else None,
+                                        _ptr(bd) if bd is not None else None, B, H, Lq, Lk, float(scale),
+                                        float(causal_value), 1, None, None, _ptr(lse) if lse is not None else None,
+                                        _bf(q), current_stream_ptr()))
+    return (out, lse) if return_lse else out
 
 
-def cross_attention_split(q, q_col0, kv, k_col0, v_col0, B, H, Lq, Lk_total, add_mask=None, scale=1.0, split=512):
+def cross_attention_split(q, q_col0, kv, k_col0, v_col0, B, H, Lq, Lk_total, add_mask=None, scale=1.0, split=512,
+                          return_lse=False):
     """Attention of Lq (<= 128) queries per batch element over Lk_total keys (FiD decoder cross-attention,
     Lk_total = n_ctx * L): split-KV over segments of `split` keys + combine.  q [B*Lq, ld], kv [B*Lk_total, ld]."""
     require_cuda(q, "q")
@@ -274,9 +279,10 @@ def cross_attention_split(q, q_col0, kv, k_col0, v_col0, B, H, Lq, Lk_total, add
                                      B * splits, H, Lq, split, float(scale), 0.0, splits, _ptr(o_part), _ptr(ml), _bf(q),
                                      current_stream_ptr()))
     out = torch.empty((B * Lq, H * 64), dtype=q.dtype, device=q.device)
-    check(lib().atlas_b200_attention_combine(_ptr(o_part), _ptr(ml), B, splits, Lq, H, _ptr(out), out.stride(0), _bf(q),
-                                             current_stream_ptr()))
-    return out
+    lse = torch.empty((B, H, Lq), dtype=torch.float32, device=q.device) if return_lse else None
+    check(lib().atlas_b200_attention_combine_ex(_ptr(o_part), _ptr(ml), B, splits, Lq, H, _ptr(out), out.stride(0),
+                                                _ptr(lse) if lse is not None else None, _bf(q), current_stream_ptr()))
+    return (out, lse) if return_lse else out
 
 
 # ---------------------------------------------------------------------------------------------
@@ -313,9 +319,21 @@ def linear_dgrad(dy, weight):
 
 
 def linear_wgrad(dy, x):
-    """dW [N, K] = dY^T [N, M] . X [M, K] (contraction over the M tokens, fp32 accumulation, 16-bit result)."""
-    dyT, xT = transpose(dy), transpose(x)
-    return linear(dyT, xT)
+    """dW [N, K] = dY^T [N, M] . X [M, K] (contraction over the M tokens, fp32 accumulation, 16-bit result): the tcgen05
+    GEMM with both operands MN-major (no transposes).  ATLAS_B200_WGRAD_TRANSPOSE=1 selects the first-generation path
+    (two explicit transposes + the K-major GEMM), kept for A/B measurements."""
+    require_cuda(dy, "dy")
+    if os.environ.get("ATLAS_B200_WGRAD_TRANSPOSE") == "1":
+        return linear(transpose(dy), transpose(x))
+    dy2, x2 = _rows2d(dy), _rows2d(x)
+    if dy2.shape[0] != x2.shape[0] or dy2.dtype != x2.dtype:
+        raise AtlasB200Error(f"linear_wgrad: dy {tuple(dy2.shape)} and x {tuple(x2.shape)} do not match")
+    M, N = dy2.shape
+    K = x2.shape[1]
+    dw = torch.empty((N, K), dtype=dy.dtype, device=dy.device)
+    check(lib().atlas_b200_linear_wgrad(_ptr(dy2), dy2.stride(0), _ptr(x2), x2.stride(0), _ptr(dw), dw.stride(0), M, N, K,
+                                        _bf(dy), current_stream_ptr()))
+    return dw
 
 
 def layernorm_bwd(x, dy, weight, eps, kind, dres=None, need_bias=False):
@@ -426,20 +444,32 @@ def cross_entropy_bwd(logits, labels, lse, gscale):
 
 
 def attention_bwd(q, q_col0, k, k_col0, v, v_col0, out, dout, dq, dq_col0, dk, dk_col0, dv, dv_col0, B, H, Lq, Lk,
-                  add_mask=None, bias_delta=None, need_dbias=False, scale=1.0, causal_value=0.0):
+                  add_mask=None, bias_delta=None, need_dbias=False, scale=1.0, causal_value=0.0, lse=None,
+                  split_keys=False):
     """Backward of `attention` / `cross_attention_split` (un-split key range).  dq / dk / dv are written in place at
-    their column offsets; returns dbias_delta fp32 [H, Lq+Lk-1] (or None)."""
+    their column offsets; returns dbias_delta fp32 [H, Lq+Lk-1] (or None).  `lse` = the forward's log-sum-exp
+    (return_lse=True) saves the recomputation pass; split_keys (needs lse, no dbias; dq must be a whole contiguous
+    [B*Lq, H*64] tensor) spreads a long key range over many CTAs (FiD cross-attention)."""
     require_cuda(q, "q")
     am = add_mask.float().contiguous() if add_mask is not None else None
     bd = bias_delta.float().contiguous() if bias_delta is not None else None
     dbias = torch.zeros((H, Lq + Lk - 1), dtype=torch.float32, device=q.device) if (need_dbias and bd is not None) else None
-    scratch = torch.empty((2, B, H, Lq), dtype=torch.float32, device=q.device)
+    dsum = torch.empty((B, H, Lq), dtype=torch.float32, device=q.device)
+    lse_buf = lse.contiguous() if lse is not None else torch.empty((B, H, Lq), dtype=torch.float32, device=q.device)
     o2 = out if out.stride(-1) == 1 else out.contiguous()
     do2 = _rows2d(dout)
+    accum = None
+    if split_keys:
+        if lse is None or dbias is not None or dq_col0 != 0 or not dq.is_contiguous() or dq.shape[1] != H * 64:
+            raise AtlasB200Error("attention_bwd: split_keys needs the forward's lse, no dbias and a contiguous dq")
+        accum = torch.zeros((B * Lq, H * 64), dtype=torch.float32, device=q.device)
     check(lib().atlas_b200_attention_bwd(
         _ptr(q), q.stride(0), q_col0, _ptr(k), k.stride(0), k_col0, _ptr(v), v.stride(0), v_col0, _ptr(o2), o2.stride(0),
         _ptr(do2), do2.stride(0), _ptr(dq), dq.stride(0), dq_col0, _ptr(dk), dk.stride(0), dk_col0, _ptr(dv),
         dv.stride(0), dv_col0, _ptr(am) if am is not None else None, _ptr(bd) if bd is not None else None,
-        _ptr(dbias) if dbias is not None else None, _ptr(scratch[0]), _ptr(scratch[1]), B, H, Lq, Lk, float(scale),
-        float(causal_value), _bf(q), current_stream_ptr()))
+        _ptr(dbias) if dbias is not None else None, _ptr(lse_buf), 1 if lse is not None else 0, _ptr(dsum),
+        _ptr(accum) if accum is not None else None, B, H, Lq, Lk, float(scale), float(causal_value), _bf(q),
+        current_stream_ptr()))
+    if accum is not None:
+        check(lib().atlas_b200_cast_f32(_ptr(accum), _ptr(dq), accum.numel(), _bf(q), current_stream_ptr()))
     return dbias

@@ -168,6 +168,14 @@ int atlas_b200_attention(const void* q, int64_t ldq, int32_t q_col0, const void*
                          int32_t Lk, float scale, float causal_value, int32_t q_div, float* o_partial,
                          float* ml_partial, int32_t is_bf16, void* stream);
 
+/* atlas_b200_attention that also writes the row log-sum-exp of the scores, lse_out [B, H, Lq] fp32 (natural log; NULL =
+ * not needed, not available together with o_partial): all the backward pass needs besides the output itself. */
+int atlas_b200_attention_ex(const void* q, int64_t ldq, int32_t q_col0, const void* k, int64_t ldk, int32_t k_col0,
+                            const void* v, int64_t ldv, int32_t v_col0, void* out, int64_t ldo, const float* add_mask,
+                            const float* bias_delta, int32_t B, int32_t H, int32_t Lq, int32_t Lk, float scale,
+                            float causal_value, int32_t q_div, float* o_partial, float* ml_partial, float* lse_out,
+                            int32_t is_bf16, void* stream);
+
 /* Split-KV support for the FiD decoder's cross-attention over n_ctx*L (= 15 360) keys
  * (fid.py:298-349 / src/modeling_t5.py:478-524): call atlas_b200_attention with B = batch*splits key
  * segments of <= 512 keys, q_div = splits (segment s reads the queries of batch s / splits) and
@@ -175,6 +183,10 @@ int atlas_b200_attention(const void* q, int64_t ldq, int32_t q_col0, const void*
  * then this merges the splits:  out[b,i,h,:] = sum_s e^(m_s-M) O_s / sum_s e^(m_s-M) l_s. */
 int atlas_b200_attention_combine(const float* o_partial, const float* ml_partial, int32_t B, int32_t splits,
                                  int32_t Lq, int32_t H, void* out, int64_t ldo, int32_t is_bf16, void* stream);
+/* ... and the log-sum-exp over ALL splits, lse_out [B, H, Lq] fp32 (NULL = not needed). */
+int atlas_b200_attention_combine_ex(const float* o_partial, const float* ml_partial, int32_t B, int32_t splits,
+                                    int32_t Lq, int32_t H, void* out, int64_t ldo, float* lse_out, int32_t is_bf16,
+                                    void* stream);
 
 /* --------------------------------------------------------------------------------------------
  * Backward pass (training): what autograd derives in the reference's train.py step
@@ -186,16 +198,28 @@ int atlas_b200_attention_combine(const float* o_partial, const float* ml_partial
 /* Backward of atlas_b200_attention (any Lq / Lk, head_dim 64; csrc/attention_bwd.cu).  q / k / v / out as in the
  * forward (out = the forward's result [B*Lq, H*64]); dout [B*Lq, H*64]; dq / dk / dv are written at column offsets
  * d?_col0 + 64h of [B*L, ld] buffers (so one [tokens, 3*H*64] buffer can receive dQ | dK | dV for a fused projection).
- * dbias_delta [H, Lq+Lk-1] fp32 is INCREMENTED (zero it first; NULL = not needed); lse / dsum are [B, H, Lq] fp32
- * scratch.  For FiD's cross-attention (src/fid.py:298-349) pass the un-split key range: B = batch, Lk = n_ctx * L.
+ * dbias_delta [H, Lq+Lk-1] fp32 is INCREMENTED (zero it first; NULL = not needed); lse / dsum are [B, H, Lq] fp32:
+ * with lse_given != 0, `lse` holds the forward's log-sum-exp (atlas_b200_attention_ex / _combine_ex) and is only read,
+ * otherwise it is recomputed (one more pass over the keys) and written.  For FiD's cross-attention
+ * (src/fid.py:298-349) pass the un-split key range: B = batch, Lk = n_ctx * L; with dq_accum [B*Lq, H*64] fp32 (zeroed,
+ * needs lse_given, no dbias) the keys are split over several CTAs that add their partial dQ into dq_accum instead of
+ * writing `dq` - the caller converts it to 16 bits (atlas_b200_cast_f32).
  * Replaces autograd through BertSelfAttention.forward (src/modeling_bert.py:328-366) and T5Attention.forward
  * (src/modeling_t5.py:478-524). */
 int atlas_b200_attention_bwd(const void* q, int64_t ldq, int32_t q_col0, const void* k, int64_t ldk, int32_t k_col0,
                              const void* v, int64_t ldv, int32_t v_col0, const void* out, int64_t ldo, const void* dout,
                              int64_t lddo, void* dq, int64_t lddq, int32_t dq_col0, void* dk, int64_t lddk,
                              int32_t dk_col0, void* dv, int64_t lddv, int32_t dv_col0, const float* add_mask,
-                             const float* bias_delta, float* dbias_delta, float* lse, float* dsum, int32_t B, int32_t H,
-                             int32_t Lq, int32_t Lk, float scale, float causal_value, int32_t is_bf16, void* stream);
+                             const float* bias_delta, float* dbias_delta, float* lse, int32_t lse_given, float* dsum,
+                             float* dq_accum, int32_t B, int32_t H, int32_t Lq, int32_t Lk, float scale,
+                             float causal_value, int32_t is_bf16, void* stream);
+
+/* Weight gradient of a Linear layer on tcgen05 (csrc/gemm.cu, MN-major operand descriptors):
+ *     dW[N, K] = dY[tokens, N]^T . X[tokens, K]        16-bit operands, fp32 accumulation over the tokens
+ * Both activations are read as they lie in memory (no transposes); dW is written in 16 bits like the reference's
+ * bf16 gradients (`--precision bf16`, src/model_io.py:94-98). */
+int atlas_b200_linear_wgrad(const void* dY, int64_t lddy, const void* X, int64_t ldx, void* dW, int64_t lddw,
+                            int32_t tokens, int32_t N, int32_t K, int32_t is_bf16, void* stream);
 
 /* dst[c, r] = src[r, c] (16-bit elements) for r < R and 0 for R <= r < Rpad: the K-major operands of the weight-gradient
  * GEMM dW[N, K] = dY^T[N, M] . X[M, K] (contraction over the M tokens, padded to a multiple of 8). */

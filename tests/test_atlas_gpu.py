@@ -183,9 +183,13 @@ def test_generate_greedy_matches_stepwise_argmax(setup, G):
         seq = out[:, :1]
         for t in range(1, out.shape[1]):
             logits = m.reader(input_ids=ids, attention_mask=mask, decoder_input_ids=seq).logits[:, -1].float()
-            nxt = logits.argmax(-1)
             alive = ~((seq == 1).any(dim=1))
-            assert (out[alive, t] == nxt[alive]).all(), t
+            # the generated token is the argmax of the re-computed logits, up to near-ties of the 16-bit logits: the
+            # fused RMSNorm statistics are accumulated with fp32 atomics (order varies run to run), which can move a
+            # bf16 logit by one ulp (2^-7 relative) between the two computations
+            top = logits.max(-1).values
+            chosen = logits.gather(1, out[:, t:t + 1]).squeeze(1)
+            assert (chosen[alive] >= top[alive] - 2.0 ** -6 * top[alive].abs().clamp_min(1.0)).all(), t
             seq = out[:, :t + 1]
 
 

@@ -307,3 +307,33 @@ def test_cross_attention_backward(dev, dtype, B, H, T, Lk, split):
     # masked keys receive exactly zero gradient (their probability underflows to 0 like in the reference)
     dead = (~valid).to(dev).reshape(B * Lk)
     assert float(kv.grad[dead].abs().max()) == 0.0 if dead.any() else True
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("tokens,N,K", [(1000, 768, 768), (77, 128, 64), (4096, 512, 2048), (30720, 2304, 768),
+                                        (5, 64, 256), (129, 2048, 768)])
+def test_wgrad_mn_major_gemm_exact(dev, dtype, tokens, N, K):
+    """dW = dY^T X on the MN-major tcgen05 path: exact-grid inputs (multiples of 1/8 in [-2, 2]) make every partial sum
+    exact in fp32 whatever the accumulation order, so the result must equal the fp32 product rounded once - bit for bit,
+    and so must the first-generation path (explicit transposes + K-major GEMM)."""
+    import os
+
+    from atlas_b200 import ops
+
+    g = torch.Generator(device="cpu").manual_seed(31 + tokens)
+    dy = (torch.randint(-16, 17, (tokens, N), generator=g).float() / 8).to(dtype).to(dev)
+    x = (torch.randint(-16, 17, (tokens, K), generator=g).float() / 8).to(dtype).to(dev)
+    want = (dy.float().t() @ x.float()).to(dtype)
+    got = ops.linear_wgrad(dy, x)
+    assert got.shape == (N, K)
+    assert torch.equal(got, want), float((got.float() - want.float()).abs().max())
+    os.environ["ATLAS_B200_WGRAD_TRANSPOSE"] = "1"
+    try:
+        old = ops.linear_wgrad(dy, x)
+    finally:
+        del os.environ["ATLAS_B200_WGRAD_TRANSPOSE"]
+    assert torch.equal(old, want)
+    # strided views (a column slice of a wider activation buffer)
+    wide = torch.zeros(tokens, N + 64, dtype=dtype, device=dev)
+    wide[:, 32:32 + N] = dy
+    assert torch.equal(ops.linear_wgrad(wide[:, 32:32 + N], x), want)
