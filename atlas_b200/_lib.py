@@ -104,6 +104,9 @@ def lib():
                                           f32, f32, i32, vp, vp, vp, i32, vp]
     L.atlas_b200_attention_combine_ex.restype = c.c_int
     L.atlas_b200_attention_combine_ex.argtypes = [vp, vp, i32, i32, i32, i32, vp, i64, vp, i32, vp]
+    L.atlas_b200_cross_attention_stats.restype = c.c_int
+    L.atlas_b200_cross_attention_stats.argtypes = [vp, i64, i32, vp, i64, i32, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32,
+                                                   f32, i32, vp]
     L.atlas_b200_linear_wgrad.restype = c.c_int
     L.atlas_b200_linear_wgrad.argtypes = [vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, vp]
     L.atlas_b200_transpose.restype = c.c_int
@@ -155,6 +158,7 @@ EXPORTED_SYMBOLS = [
     "atlas_b200_attention_bwd",
     "atlas_b200_attention_ex",
     "atlas_b200_attention_combine_ex",
+    "atlas_b200_cross_attention_stats",
     "atlas_b200_linear_wgrad",
     "atlas_b200_transpose",
     "atlas_b200_colsum",

@@ -211,17 +211,83 @@ class FiD(nn.Module):
     def gradient_checkpointing_disable(self):
         self._grad_ckpt = False
 
+    # ---- cross-attention score capture (src/fid.py:126-235,333-343) -------------------------------------
     def reset_score_storage(self):
-        pass
+        self._xattn = []
 
     def overwrite_forward_crossattention(self):
-        pass
+        """From now on every forward also records, per decoder layer, the head-means of the cross-attention logits,
+        probabilities and ||V||-weighted probabilities (src/model_io.py:79-81 calls this for the eval* / std* gold score
+        modes and `compute_crossattention_stats`).  The recording forward runs eagerly (no CUDA graph)."""
+        self._capture = True
 
     def create_crossattention_storage(self):
-        pass
+        self._xattn = []
 
-    def get_crossattention_scores(self, *a, **k):
-        raise AtlasB200Error("cross-attention score capture (gold_score_mode eval*/std*/adist) is not implemented")
+    def _record_xattn(self, q, kv, B, H, T, Lk, lse, mask):
+        if getattr(self, "_capture", False):
+            if not hasattr(self, "_xattn"):
+                self._xattn = []
+            self._xattn.append(ops.cross_attention_stats(q.detach(), 0, kv.detach(), 0, H * 64, B, H, T, Lk, lse,
+                                                         add_mask=mask, scale=1.0))
+
+    @torch.no_grad()
+    def get_crossattention_scores(self, n_passages, mask, labels, ids, mode="all", mask_query=None):
+        """One scalar per (query, passage) from the recorded cross-attention maps: `FiD.get_crossattention_scores`
+        (src/fid.py:136-164) -> dict of [B, n_passages] tensors named {scores,probs,norms}{top5,top10,top20,nosep,first,
+        sum,avg,woquery}."""
+        rec = getattr(self, "_xattn", None)
+        if not rec or len(rec) < self.config.num_decoder_layers:
+            raise AtlasB200Error("get_crossattention_scores: no recorded forward (call overwrite_forward_crossattention() "
+                                 "and run a forward first)")
+        rec = rec[-self.config.num_decoder_layers:]
+        output = {}
+        for idx, prefix in ((0, "scores"), (2, "norms"), (1, "probs")):
+            if prefix in mode or "all" in mode:
+                self.aggregate_value(torch.stack([r[idx] for r in rec]), mask, labels, n_passages, ids, mask_query, output,
+                                     prefix=prefix)
+        return output
+
+    def aggregate_value(self, scores, mask, labels, n_passages, ids, mask_query=None, output=None, prefix=""):
+        """src/fid.py:166-203, same reductions and the same (hard-coded 256) normalisers."""
+        output = {} if output is None else output
+        n_layers, bsz, n_tokens, _ = scores.size()
+        ids = ids.view(bsz, n_passages, -1)
+        scores = scores.view(n_layers, bsz, n_tokens, n_passages, -1)
+        mask = mask.view(bsz, n_passages, -1).bool()
+        scores = scores.masked_fill(~mask[None, :, None], 0.0)
+        valid = ~(labels == -100)
+        ntokens_sum = 256 * n_layers * valid.sum(dim=[1])[:, None]
+        ntokens_wquery = mask.sum(dim=[2]) * n_layers * valid.sum(dim=[1])[:, None]
+        ntokens_first = mask.sum(dim=[2]) * n_layers
+        scores = scores.sum(dim=[0])
+        for k in (5, 10, 20):
+            output[f"{prefix}top{k}"] = self.get_topk_score(k, scores, mask, labels, n_layers)
+        scores = scores.masked_fill((labels == -100)[:, :, None, None], 0.0)
+        scores_wquery = scores.sum(dim=[1, 3])
+        output[f"{prefix}nosep"] = scores.masked_fill(~(ids == 1)[:, None], 0).sum(dim=[1, 3]) / ntokens_sum
+        output[f"{prefix}first"] = scores[:, 0].sum(dim=[2]) / ntokens_first
+        output[f"{prefix}sum"] = scores_wquery / ntokens_sum
+        output[f"{prefix}avg"] = scores_wquery / ntokens_wquery
+        if mask_query is not None:
+            output[f"{prefix}woquery"] = self.get_woquery_score(scores, mask_query, mask, labels, n_layers)
+        return output
+
+    def get_topk_score(self, topk, scores, mask, labels, n_layers):   # src/fid.py:205-210
+        top = torch.topk(scores, k=topk, dim=-1)[0].sum(dim=[3])
+        top = top.masked_fill((labels == -100)[:, :, None], 0.0)
+        ntokens_top = n_layers * (~(labels == -100)).sum(dim=[1])[:, None]
+        return top.sum(dim=1) / (topk * ntokens_top)
+
+    def get_woquery_score(self, scores, mask_query, mask, labels, n_layers):   # src/fid.py:212-224
+        if scores.size(-1) > mask_query.size(-1):
+            pad = torch.zeros([mask_query.size(0), scores.size(-1) - mask_query.size(-1)], device=mask_query.device,
+                              dtype=torch.bool)
+            mask_query = torch.cat([mask_query, pad], dim=-1)
+        mq = mask * (~mask_query[:, None])
+        woq = scores.masked_fill(~mq[:, None], 0.0)
+        ntokens_woquery = 256 * n_layers * (~(labels == -100)).sum(dim=[1])[:, None]
+        return woq.sum(dim=[1, 3]) / ntokens_woquery
 
     def _shift_right(self, input_ids):  # src/modeling_t5.py:789-813
         start, pad = self.config.decoder_start_token_id, self.config.pad_token_id
@@ -358,6 +424,7 @@ class FiD(nn.Module):
         neg = -1e4 if dt == torch.float16 else -1e9
         cross_mask = (1.0 - enc_mask.reshape(B, Lk).to(torch.float32)) * neg
         qkv = torch.empty((B * T, 3 * H * 64), dtype=dt, device=h.device)
+        capture = getattr(self, "_capture", False)
         for i in range(c.num_decoder_layers):
             p = f"decoder.block.{i}.layer.0."
             n = ops.layernorm(h, W[p + "layer_norm.weight"], None, c.layer_norm_epsilon, kind=1)
@@ -368,8 +435,13 @@ class FiD(nn.Module):
             p = f"decoder.block.{i}.layer.1."
             n = ops.layernorm(h, W[p + "layer_norm.weight"], None, c.layer_norm_epsilon, kind=1)
             q = ops.linear(n, W[p + "EncDecAttention.q.weight"])
-            ctx = ops.cross_attention_split(q, 0, cross_kv[i], 0, H * 64, B, H, T, Lk, add_mask=cross_mask, scale=1.0,
-                                            split=split)
+            if capture:
+                ctx, lse = ops.cross_attention_split(q, 0, cross_kv[i], 0, H * 64, B, H, T, Lk, add_mask=cross_mask,
+                                                     scale=1.0, split=split, return_lse=True)
+                self._record_xattn(q, cross_kv[i], B, H, T, Lk, lse, cross_mask)
+            else:
+                ctx = ops.cross_attention_split(q, 0, cross_kv[i], 0, H * 64, B, H, T, Lk, add_mask=cross_mask,
+                                                scale=1.0, split=split)
             h = ops.linear(ctx, W[p + "EncDecAttention.o.weight"], None, residual=h, epilogue=ops.EPI_RESIDUAL)
             h = self._ff(W, G, f"decoder.block.{i}.layer.2.", h, c.layer_norm_epsilon)
         h = ops.layernorm(h, W["decoder.final_layer_norm.weight"], None, c.layer_norm_epsilon, kind=1)
@@ -470,7 +542,8 @@ class FiD(nn.Module):
             n = g.layernorm(h, W[p + "layer_norm.weight"], None, eps, kind=1)
             q = g.linear(n, W[p + "EncDecAttention.q.weight"])
             kv = g.linear(flat, G[p + "EncDecAttention.kv"])
-            ctx = g.cross_attention(q, kv, B, H, T, Lk, add_mask=cross_mask, scale=1.0, split=split)
+            ctx, lse = g.cross_attention(q, kv, B, H, T, Lk, add_mask=cross_mask, scale=1.0, split=split, return_lse=True)
+            self._record_xattn(q, kv, B, H, T, Lk, lse, cross_mask)
             h = g.linear(ctx, W[p + "EncDecAttention.o.weight"], None, residual=h)
             p = f"decoder.block.{i}.layer.2."
             n = g.layernorm(h, W[p + "layer_norm.weight"], None, eps, kind=1)
@@ -505,7 +578,7 @@ class FiD(nn.Module):
     # ---- CUDA-graph cache --------------------------------------------------------------------
     def _run(self, tag, fn, inputs):
         """Run `fn(*inputs)` (static shapes, device tensors in / out): replay a captured graph when enabled."""
-        if not self.cuda_graphs:
+        if not self.cuda_graphs or getattr(self, "_capture", False):   # recording forwards append to a python list
             return fn(*inputs)
         self._weights()                                      # make sure the 16-bit weight copies exist / are current
         dt = self._dtype()

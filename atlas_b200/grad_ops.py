@@ -110,10 +110,11 @@ class _CrossAttention(torch.autograd.Function):
                                              split=split, return_lse=True)
         ctx.save_for_backward(q, kv, out, add_mask, lse)
         ctx.dims = (B, H, T, Lk, scale)
-        return out
+        ctx.mark_non_differentiable(lse)
+        return out, lse
 
     @staticmethod
-    def backward(ctx, dout):
+    def backward(ctx, dout, _dlse):
         q, kv, out, add_mask, lse = ctx.saved_tensors
         B, H, T, Lk, scale = ctx.dims
         dq = torch.empty((B * T, H * 64), dtype=q.dtype, device=q.device)
@@ -123,8 +124,9 @@ class _CrossAttention(torch.autograd.Function):
         return dq, dkv, None, None, None, None, None, None, None
 
 
-def cross_attention(q, kv, B, H, T, Lk, add_mask=None, scale=1.0, split=384):
-    return _CrossAttention.apply(q, kv, add_mask, B, H, T, Lk, scale, split)
+def cross_attention(q, kv, B, H, T, Lk, add_mask=None, scale=1.0, split=384, return_lse=False):
+    out, lse = _CrossAttention.apply(q, kv, add_mask, B, H, T, Lk, scale, split)
+    return (out, lse) if return_lse else out
 
 
 class _GatedGelu(torch.autograd.Function):

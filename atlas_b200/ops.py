@@ -473,3 +473,16 @@ def attention_bwd(q, q_col0, k, k_col0, v, v_col0, out, dout, dq, dq_col0, dk, d
     if accum is not None:
         check(lib().atlas_b200_cast_f32(_ptr(accum), _ptr(dq), accum.numel(), _bf(q), current_stream_ptr()))
     return dbias
+
+
+def cross_attention_stats(q, q_col0, kv, k_col0, v_col0, B, H, T, Lk, lse, add_mask=None, scale=1.0):
+    """Means over heads of the cross-attention logits, probabilities and ||V||-weighted probabilities -> three fp32
+    [B, T, Lk] tensors (`score_storage`, `prob_storage`, `normalized_score_storage` of src/fid.py:333-343)."""
+    require_cuda(q, "q")
+    am = add_mask.float().contiguous() if add_mask is not None else None
+    out = torch.empty((3, B, T, Lk), dtype=torch.float32, device=q.device)
+    l2 = lse.contiguous()
+    check(lib().atlas_b200_cross_attention_stats(_ptr(q), q.stride(0), q_col0, _ptr(kv), kv.stride(0), k_col0, v_col0,
+                                                 _ptr(am) if am is not None else None, _ptr(l2), _ptr(out[0]), _ptr(out[1]),
+                                                 _ptr(out[2]), B, H, T, Lk, float(scale), _bf(q), current_stream_ptr()))
+    return out[0], out[1], out[2]

@@ -12,6 +12,7 @@ text_maxlength 384, 32 target tokens) — plus the MIPS scan against the HBM roo
   roofline      the dominant kernel of the step (tcgen05 GEMM): FLOPs / CUDA-event time, against the measured bf16 peak
   mips          the retrieval kernel alone at its BASELINE batch (256 queries): queries/s, C-ABI e2e with host buffers,
                 and the bank sweep against the measured HBM peak (`mips.roofline`)
+  train         supplementary: FiD-base forward + BACKWARD step (the training path's kernels), reader tokens/s
   cpu_baseline  the reference's CPU path (oracle/: torch-CPU restatements pinned to the reference's goldens) on this
                 box's host cores, bounded sample
 `--impl reference` times that CPU path as the reference arm.  One process per GPU; weak scaling (per-GPU batch and
@@ -352,6 +353,12 @@ def run_ours(args):
     # ---------------- the retrieval kernel alone at its BASELINE batch (256 queries) -------------
     mips = mips_leg(args, index, dev, world, rank, L, barrier_sync, max_over_ranks)
 
+    # ---------------- the reader's TRAINING step (forward + backward kernels), BASELINE configs[3] shapes -------------
+    try:
+        train = train_leg(args, reader, dev, world, L, barrier_sync, max_over_ranks)
+    except Exception as e:   # the headline line must survive a failure of this supplementary leg
+        train = {"error": repr(e)[:300]}
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -385,6 +392,7 @@ def run_ours(args):
                              "from a CUDA graph",
         "clocks": clocks.summary(),
         "mips": mips,
+        "train": train,
     }
     if not args.no_cpu_baseline and world == 1:
         leg = cpu_reference_leg(B, args.rows)
@@ -393,6 +401,71 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def train_leg(args, reader, dev, world, L, barrier_sync, max_over_ranks, steps=3, warmup=2):
+    """FiD-base forward + backward (`loss.backward()` through grad_ops.py's kernels; at N > 1 followed by one NCCL
+    all-reduce of the flattened gradients, what DDP does in train.py) on `train_batch` queries x 40 passages x 384 tokens
+    per GPU: reader tokens/s (B * n_docs * text_maxlength per step, SURVEY.md §8d C5's unit) and the share of the GEMM /
+    attention-backward kernels.  Supplementary to the headline metric (which is the forward step)."""
+    import ctypes
+
+    import torch
+    import torch.distributed as dist
+
+    tb = min(args.batch, 2)
+    reader.train()
+    cfg = reader.encoder.config
+    old = (cfg.n_context, cfg.bsz)
+    cfg.n_context, cfg.bsz = N_DOCS, tb
+    g = torch.Generator().manual_seed(99)
+    ids = torch.randint(2, 32000, (tb, N_DOCS * TEXT_LEN), generator=g).to(dev)
+    mask = torch.ones(tb, N_DOCS * TEXT_LEN, dtype=torch.bool, device=dev)
+    labels = torch.randint(2, 32000, (tb, TARGET_LEN), generator=g).to(dev)
+
+    def step():
+        reader.zero_grad(set_to_none=True)
+        out = reader(input_ids=ids, attention_mask=mask, labels=labels)
+        out[0].backward()
+        if world > 1:
+            flat = torch.cat([p.grad.reshape(-1) for p in reader.parameters() if p.grad is not None])
+            dist.all_reduce(flat)
+        return out[0]
+
+    try:
+        for _ in range(warmup):
+            loss = step()
+        barrier_sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = step()
+        e1.record()
+        barrier_sync()
+        ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+        assert bool(torch.isfinite(loss.float())), "non-finite training loss"
+        shares = {}
+        for kind, name in ((2, "gemm"), (4, "attention_bwd")):
+            L.atlas_b200_profile_enable(kind)
+            step()
+            torch.cuda.synchronize()
+            work = L.atlas_b200_profile_work()
+            kms, kn = ctypes.c_double(0), ctypes.c_int32(0)
+            L.atlas_b200_profile_collect(ctypes.byref(kms), ctypes.byref(kn))
+            L.atlas_b200_profile_enable(0)
+            shares[name] = {"ms_per_step": kms.value, "launches_per_step": kn.value,
+                            "achieved_tflops": work / (kms.value * 1e-3) / 1e12 if kms.value > 0 else None,
+                            "share_of_step": kms.value / ms if ms else None}
+    finally:
+        reader.zero_grad(set_to_none=True)
+        reader.eval()
+        cfg.n_context, cfg.bsz = old
+    tokens = tb * N_DOCS * TEXT_LEN * world
+    return {"metric": "reader training tokens/sec (FiD-base forward + backward, bf16, dropout 0)",
+            "value": tokens / (ms * 1e-3), "unit": "tokens/s", "ms_per_step": ms, "steps": steps,
+            "queries_per_step": tb * world, "reader_tokens_per_step": tokens,
+            "gradient_allreduce": "one NCCL all-reduce of the flattened bf16 gradients" if world > 1 else "none (1 GPU)",
+            "kernels": shares}
 
 
 def mips_leg(args, index, dev, world, rank, L, barrier_sync, max_over_ranks):

@@ -214,6 +214,16 @@ int atlas_b200_attention_bwd(const void* q, int64_t ldq, int32_t q_col0, const v
                              float* dq_accum, int32_t B, int32_t H, int32_t Lq, int32_t Lk, float scale,
                              float causal_value, int32_t is_bf16, void* stream);
 
+/* Cross-attention statistics for retriever distillation (`cross_attention_forward`, src/fid.py:333-343): with
+ * S = scale * Q K^T + add_mask and P = softmax over the Lk = n_ctx * L keys (lse = the forward's log-sum-exp [B, H, T],
+ * atlas_b200_attention_combine_ex), the means over heads of S, P and ||V[b, j, h, :]|| * P -> three [B, T, Lk] fp32 maps
+ * (`score_storage`, `prob_storage`, `normalized_score_storage`).  q [B*T, ldq], kv [B*Lk, ldkv] with K / V of head h at
+ * columns k_col0 + 64h / v_col0 + 64h.  T <= 128.  (csrc/xattn_stats.cu) */
+int atlas_b200_cross_attention_stats(const void* q, int64_t ldq, int32_t q_col0, const void* kv, int64_t ldkv,
+                                     int32_t k_col0, int32_t v_col0, const float* add_mask, const float* lse,
+                                     float* out_scores, float* out_probs, float* out_norms, int32_t B, int32_t H, int32_t T,
+                                     int32_t Lk, float scale, int32_t is_bf16, void* stream);
+
 /* Weight gradient of a Linear layer on tcgen05 (csrc/gemm.cu, MN-major operand descriptors):
  *     dW[N, K] = dY[tokens, N]^T . X[tokens, K]        16-bit operands, fp32 accumulation over the tokens
  * Both activations are read as they lie in memory (no transposes); dW is written in 16 bits like the reference's

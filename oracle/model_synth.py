@@ -83,3 +83,16 @@ def fid_inputs(seed=33, B=2, n_ctx=3, L=64, T=8, vocab=512):
     return (torch.from_numpy(ids.reshape(B, n_ctx * L).astype(np.int64)),
             torch.from_numpy(mask.reshape(B, n_ctx * L)),
             torch.from_numpy(labels.astype(np.int64)))
+
+
+def fid_inputs_with_sep(seed=33, B=2, n_ctx=3, L=64, T=8, vocab=512, n_query=5):
+    """`fid_inputs` with an EOS (id 1) closing every passage, plus the reader's query mask (first `n_query` tokens of a
+    passage are the question, src/atlas.py:407-413): inputs of the cross-attention score goldens."""
+    ids, mask, labels = fid_inputs(seed, B, n_ctx, L, T, vocab)
+    ids = ids.clone().view(B, n_ctx, L)
+    m = mask.view(B, n_ctx, L)
+    last = m.sum(-1) - 1
+    ids.scatter_(2, last[..., None], 1)
+    mask_query = torch.zeros(B, n_query + 3, dtype=torch.bool)
+    mask_query[:, :n_query] = True
+    return ids.view(B, n_ctx * L), mask, labels, mask_query

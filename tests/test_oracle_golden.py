@@ -208,3 +208,26 @@ def test_gradient_oracle_matches_reference(which):
         key = f"{which}_fp32/full/{n}"
         if key in g.files:
             assert np.abs(gr - g[key]).max() <= 2e-4 * np.abs(g[key]).max() + 1e-7, n
+
+
+def test_crossattention_aggregates_match_reference():
+    """Host logic of `FiD.get_crossattention_scores` / `aggregate_value` / `get_topk_score` / `get_woquery_score`
+    (atlas_b200/fid.py, pure tensor reductions) fed with the maps the UNMODIFIED reference recorded
+    (tests/golden/xattn_tiny.npz, oracle/make_golden_xattn.py): all 24 aggregates."""
+    import torch
+
+    import model_synth
+    from atlas_b200.fid import FiD, T5ConfigLite
+
+    g = np.load(os.path.join(GOLDEN_DIR, "xattn_tiny.npz"))
+    cfg = {k: v for k, v in model_synth.T5_CFG.items() if k not in ("dropout_rate", "is_encoder_decoder", "use_cache")}
+    model = FiD(T5ConfigLite(**cfg))
+    ids, mask, labels, mask_query = model_synth.fid_inputs_with_sep()
+    model._xattn = [tuple(torch.from_numpy(g[f"fp32/layer{li}/{k}"]) for k in ("scores", "probs", "norms"))
+                    for li in range(cfg["num_decoder_layers"])]
+    agg = model.get_crossattention_scores(3, mask, labels=labels, ids=ids, mode="all", mask_query=mask_query)
+    keys = [k[9:] for k in g.files if k.startswith("fp32/agg/")]
+    assert len(keys) == 24 and set(keys) == set(agg)
+    for k in keys:
+        ref = g[f"fp32/agg/{k}"]
+        assert np.abs(agg[k].numpy() - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max()), k

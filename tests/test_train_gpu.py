@@ -220,3 +220,77 @@ def test_atlas_training_step_matches_reference(dev):
         assert abs(proj - float(G[f"fp32/proj/{n}"])) <= tol_proj * ref_norm, (n, proj, float(G[f"fp32/proj/{n}"]))
         checked += 1
     assert checked >= 80
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_crossattention_score_capture_matches_reference(dev, dtype):
+    """`overwrite_forward_crossattention` + `get_crossattention_scores` (src/fid.py:126-235,333-343): the recorded
+    head-mean maps of every decoder layer (csrc/xattn_stats.cu) and all 24 aggregates against the reference's fp32 run
+    (tests/golden/xattn_tiny.npz); budget = 3 x the reference's own bf16 drift of each aggregate, floor 2 %."""
+    from atlas_b200.fid import FiD, T5ConfigLite
+
+    G = np.load(os.path.join(GOLDEN_DIR, "xattn_tiny.npz"))
+    model = FiD(T5ConfigLite(**T5_KW))
+    sd, _ = model_synth.fill_state_dict(model.state_dict(), 202)
+    model.load_state_dict(sd)
+    model = model.to(dtype).to(dev).eval()
+    model.overwrite_forward_crossattention()
+    model.create_crossattention_storage()
+    model.encoder.config.n_context, model.encoder.config.bsz = 3, 2
+    ids, mask, labels, mask_query = model_synth.fid_inputs_with_sep()
+    with torch.no_grad():
+        model(input_ids=ids.to(dev), attention_mask=mask.to(dev), decoder_input_ids=model._shift_right(labels.to(dev)),
+              labels=labels.to(dev), use_cache=False)
+        agg = model.get_crossattention_scores(3, mask.to(dev), labels=labels.to(dev), ids=ids.to(dev), mode="all",
+                                              mask_query=mask_query.to(dev))
+    assert len(model._xattn) == 2
+    live = mask[:, None, :].expand(-1, labels.shape[1], -1).numpy()
+    for li in range(2):
+        for idx, name in ((0, "scores"), (1, "probs"), (2, "norms")):
+            got = model._xattn[li][idx].float().cpu().numpy()
+            ref = G[f"fp32/layer{li}/{name}"]
+            scale = np.abs(ref[live]).max()
+            assert np.abs(got - ref)[live].max() <= (6e-2 if dtype == torch.bfloat16 else 1e-2) * scale, (li, name)
+            if name != "scores":     # masked keys carry no probability
+                assert np.abs(got[~live]).max() <= 1e-6
+    for k in [k[9:] for k in G.files if k.startswith("fp32/agg/")]:
+        ref, ref16 = G[f"fp32/agg/{k}"], G[f"bf16/agg/{k}"]
+        budget = max(3.0 * np.abs(ref16 - ref).max(), 2e-2 * np.abs(ref).max()) + 1e-6
+        assert np.abs(agg[k].float().cpu().numpy() - ref).max() <= budget, k
+    model.reset_score_storage()
+    assert model._xattn == []
+
+
+def test_atlas_step_with_crossattention_gold_scores(dev):
+    """gold_score_mode `stdnormsum` (scores recorded during the training forward) and `evalnormsum` (a separate no-grad
+    pass, `Atlas.eval_score` src/atlas.py:310-340) drive the retriever loss; compute_crossattention_stats fills corr/*."""
+    import atlas_synth
+    from atlas_b200.atlas import Atlas
+    from atlas_b200.fid import FiD, T5ConfigLite
+    from atlas_b200.retrievers import BertConfigLite, Contriever, DualEncoderRetriever
+
+    ret_ids = np.load(os.path.join(GOLDEN_DIR, "atlas_tiny.npz"))["ret_ids"]
+    reader_tok, retriever_tok = atlas_synth.tokenizers()
+    corpus = atlas_synth.make_corpus()
+    passages = [[corpus[int(i)] for i in row] for row in ret_ids]
+    query, target = atlas_synth.make_batch()
+    for mode in ("stdnormsum", "evalnormsum"):
+        opt = atlas_synth.make_opt(gold_score_mode=mode, temperature_gold=0.1, temperature_score=0.1,
+                                   compute_crossattention_stats=(mode == "stdnormsum"))
+        reader = FiD(T5ConfigLite(**T5_KW))
+        sd, _ = model_synth.fill_state_dict(reader.state_dict(), seed=202)
+        reader.load_state_dict(sd)
+        reader.overwrite_forward_crossattention()          # what src/model_io.py:79-81 does for these modes
+        reader.create_crossattention_storage()
+        contriever = Contriever(BertConfigLite(**model_synth.CONTRIEVER_CFG))
+        sd, _ = model_synth.fill_state_dict(contriever.state_dict(), seed=101)
+        contriever.load_state_dict(sd)
+        model = Atlas(opt, reader.to(dev), DualEncoderRetriever(opt, contriever.to(dev)), reader_tok, retriever_tok).eval()
+        model.retrieve = lambda *a, **k: (passages, None)
+        stats = {}
+        reader_loss, retriever_loss = model(None, query, target, train_retriever=True, iter_stats=stats)
+        assert torch.isfinite(reader_loss) and torch.isfinite(retriever_loss) and retriever_loss.requires_grad
+        (reader_loss + retriever_loss).backward()
+        assert contriever.encoder.layer[0].attention.self.query.weight.grad is not None
+        if mode == "stdnormsum":
+            assert any(k.startswith("corr/") for k in stats)
