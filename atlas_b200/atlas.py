@@ -64,7 +64,13 @@ def select_crossattention_scores(scores, mode):
     """Pick the aggregate named after the `eval` / `std` prefix of gold_score_mode (src/atlas.py:639-643)."""
     for prefix in ("eval", "std"):
         if prefix in mode:
-            return scores[mode[len(prefix):]]
+            key = mode[len(prefix):]
+            if key not in scores and key.startswith("norm") and "norms" + key[4:] in scores:
+                # `--gold_score_mode evalnormsum` (= the paper's `adist`, the only eval* choice of src/options.py:244) asks for
+                # "normsum", but `aggregate_value(..., prefix="norms")` names the aggregate "normssum" (src/fid.py:162,198):
+                # the reference raises KeyError here.  The intended aggregate is served instead.
+                key = "norms" + key[4:]
+            return scores[key]
     return None
 
 
