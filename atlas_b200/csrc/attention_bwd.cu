@@ -19,6 +19,7 @@
 #include "host_common.h"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace attnb {
 
@@ -435,6 +436,295 @@ attn_bwd_dkv_kernel(const Params p) {
     store_acc<kBF16>(dvacc, 1.0f, p.dv, p.lddv, p.dv_col0 + h * D, krow_base, k0 + warp * 16, p.Lk, lane);
 }
 
+
+// ======================================================================================================================
+// Second-generation kernels (default when the forward's log-sum-exp is available): same arithmetic, but
+//   - the streamed tiles are double-buffered with cp.async (the next key / query block lands while this one is computed),
+//   - the resident operand's A fragments are re-read from shared memory per k-step instead of living in 32 registers and
+//     the additive mask / bias come from (padded) shared-memory tables, so three CTAs (12 warps) fit per SM instead of two.
+// ======================================================================================================================
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// asynchronous version of load_tile (rows >= nrows are zero-filled through src-size 0)
+__device__ __forceinline__ void load_tile_async(uint32_t tile, const uint16_t* base, int64_t ld, int col, int64_t row_base,
+                                                int r0, int nrows) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int idx = it * THREADS + static_cast<int>(threadIdx.x);
+        const int row = idx >> 3, chunk = idx & 7;
+        const bool ok = r0 + row < nrows;
+        const uint16_t* src = base + (row_base + (ok ? r0 + row : 0)) * ld + col + chunk * 8;
+        cp_async16(tile + tile_off(row, chunk), src, ok ? 16 : 0);
+    }
+}
+
+// acc (16 x 64) += A(rows row0.. of a_tile, 16 x 64 over d) . T^T with the A fragments read per k-step
+template <bool kBF16>
+__device__ __forceinline__ void mma_rows_tileT(float (&acc)[8][4], uint32_t a_tile, int row0, uint32_t b_tile, int lane) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        uint32_t a[4];
+        ldsm_x4(a, a_tile + tile_off(row0 + (lane & 15), ks * 2 + (lane >> 4)));
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+            uint32_t b[4];
+            ldsm_x4(b, b_tile + tile_off(np * 16 + (lane & 7) + ((lane >> 4) << 3), ks * 2 + ((lane >> 3) & 1)));
+            mma16816<kBF16>(acc[2 * np], a, b[0], b[1]);
+            mma16816<kBF16>(acc[2 * np + 1], a, b[2], b[3]);
+        }
+    }
+}
+
+constexpr int BIAS_PAD = 64;   // zero entries on both sides of the shared bias table: offsets of padding rows / keys stay in range
+
+template <bool kBF16>
+__global__ void __launch_bounds__(THREADS, 3)
+attn_bwd_dq2_kernel(const Params p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int ntab = p.Lq + p.Lk - 1;
+    float* mask_s = reinterpret_cast<float*>(smem + 6 * TILE_BYTES);                       // [2][64]
+    float* bias_s = p.bias_delta ? mask_s + 2 * BN : nullptr;                              // [ntab + 2 * BIAS_PAD]
+    float* dbias_s = p.dbias ? mask_s + 2 * BN + (p.bias_delta ? ntab + 2 * BIAS_PAD : 0) : nullptr;
+
+    const int nqb = (p.Lq + BM - 1) / BM;
+    const int chunk = static_cast<int>(blockIdx.x) % p.key_chunks;
+    const int item = static_cast<int>(blockIdx.x) / p.key_chunks;
+    const int qb = item % nqb;
+    const int h = (item / nqb) % p.H;
+    const int b = item / (nqb * p.H);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int q0 = qb * BM;
+    const int64_t qrow_base = static_cast<int64_t>(b) * p.Lq, krow_base = static_cast<int64_t>(b) * p.Lk;
+    const float* mask_row = p.add_mask ? p.add_mask + static_cast<int64_t>(b) * p.Lk : nullptr;
+
+    if (bias_s)
+        for (int x = threadIdx.x; x < ntab + 2 * BIAS_PAD; x += THREADS) {
+            const int d = x - BIAS_PAD;
+            bias_s[x] = (d >= 0 && d < ntab) ? __ldg(p.bias_delta + static_cast<int64_t>(h) * ntab + d) : 0.f;
+        }
+    if (dbias_s)
+        for (int x = threadIdx.x; x < ntab; x += THREADS) dbias_s[x] = 0.f;
+    const uint32_t smem_a = ab::smem_u32(smem);
+    const uint32_t sQ_a = smem_a, sdO_a = smem_a + TILE_BYTES;
+    load_tile(smem, p.q, p.ldq, p.q_col0 + h * D, qrow_base, q0, p.Lq);
+    load_tile(smem + TILE_BYTES, p.dout, p.lddo, h * D, qrow_base, q0, p.Lq);
+
+    float drow[2];
+    {
+        const int r = q0 + warp * 16 + (lane >> 1);
+        float acc = 0.f;
+        if (r < p.Lq) {
+            const uint16_t* po = p.o + (qrow_base + r) * p.ldo + h * D + (lane & 1) * 32;
+            const uint16_t* pd = p.dout + (qrow_base + r) * p.lddo + h * D + (lane & 1) * 32;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint4 a = __ldg(reinterpret_cast<const uint4*>(po) + c);
+                const uint4 d = __ldg(reinterpret_cast<const uint4*>(pd) + c);
+                const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, dw[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    acc = fmaf(to_f32<kBF16>(aw[e] & 0xFFFFu), to_f32<kBF16>(dw[e] & 0xFFFFu), acc);
+                    acc = fmaf(to_f32<kBF16>(aw[e] >> 16), to_f32<kBF16>(dw[e] >> 16), acc);
+                }
+            }
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        drow[0] = __shfl_sync(0xffffffffu, acc, 2 * g);
+        drow[1] = __shfl_sync(0xffffffffu, acc, 2 * (g + 8));
+        if ((lane & 1) == 0 && r < p.Lq) p.dsum[(static_cast<int64_t>(b) * p.H + h) * p.Lq + r] = acc;
+    }
+    const int i_lo = q0 + warp * 16 + g;
+    float lse[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int i = i_lo + r * 8;
+        lse[r] = i < p.Lq ? __ldg(p.lse + (static_cast<int64_t>(b) * p.H + h) * p.Lq + i) : INFINITY;
+    }
+    const int nkb = (p.Lk + BN - 1) / BN;
+    const int per_chunk = (nkb + p.key_chunks - 1) / p.key_chunks;
+    const int kb_begin = chunk * per_chunk;
+    const int kb_end = min(nkb, kb_begin + per_chunk);
+
+    auto prefetch = [&](int kb, int buf) {
+        load_tile_async(smem_a + (2 + buf) * TILE_BYTES, p.k, p.ldk, p.k_col0 + h * D, krow_base, kb * BN, p.Lk);
+        load_tile_async(smem_a + (4 + buf) * TILE_BYTES, p.v, p.ldv, p.v_col0 + h * D, krow_base, kb * BN, p.Lk);
+        if (threadIdx.x < BN) {
+            const int j = kb * BN + static_cast<int>(threadIdx.x);
+            mask_s[buf * BN + threadIdx.x] = (mask_row != nullptr && j < p.Lk) ? __ldg(mask_row + j) : 0.f;
+        }
+        cp_async_commit();
+    };
+    if (kb_begin < kb_end) prefetch(kb_begin, 0);
+
+    float dqacc[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dqacc[nt][e] = 0.f;
+    const float* bias_c = bias_s ? bias_s + BIAS_PAD : nullptr;
+    for (int kb = kb_begin; kb < kb_end; ++kb) {
+        const int buf = (kb - kb_begin) & 1;
+        cp_async_wait_all();
+        __syncthreads();                       // this block's tiles are visible; everyone is done with the other buffer
+        if (kb + 1 < kb_end) prefetch(kb + 1, buf ^ 1);
+        const uint32_t sK_a = smem_a + (2 + buf) * TILE_BYTES, sV_a = smem_a + (4 + buf) * TILE_BYTES;
+        float acc[8][4], dp[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                acc[nt][e] = 0.f;
+                dp[nt][e] = 0.f;
+            }
+        mma_rows_tileT<kBF16>(acc, sQ_a, warp * 16, sK_a, lane);
+        mma_rows_tileT<kBF16>(dp, sdO_a, warp * 16, sV_a, lane);
+        const int base = kb * BN + 2 * t - i_lo + p.Lq - 1;      // table offset of (row i_lo, column 2t of this block)
+        const float* mk = mask_s + buf * BN + 2 * t;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int half = e >> 1, e2 = e & 1;
+                const int i = i_lo + half * 8, j = kb * BN + nt * 8 + 2 * t + e2;
+                const int off = base + 8 * (nt - half) + e2;
+                float sc = acc[nt][e] * p.scale + mk[nt * 8 + e2];
+                if (bias_c != nullptr) sc += bias_c[off];
+                if (p.causal_value != 0.f && j > min(i, p.Lq - 1)) sc += p.causal_value;
+                if (j >= p.Lk) sc = -INFINITY;
+                const float pr = __expf(sc - lse[half]);
+                const float ds = pr * (dp[nt][e] - drow[half]);
+                acc[nt][e] = ds;
+                if (dbias_s != nullptr && i < p.Lq && j < p.Lk) atomicAdd(&dbias_s[off], ds);
+            }
+        mma_p_tile<kBF16>(dqacc, acc, sK_a, lane);
+    }
+    if (p.dq_accum != nullptr) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int i = i_lo + half * 8;
+            if (i >= p.Lq) continue;
+            float* row = p.dq_accum + (qrow_base + i) * (static_cast<int64_t>(p.H) * D) + h * D;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                atomicAdd(row + nt * 8 + 2 * t, dqacc[nt][2 * half] * p.scale);
+                atomicAdd(row + nt * 8 + 2 * t + 1, dqacc[nt][2 * half + 1] * p.scale);
+            }
+        }
+    } else {
+        store_acc<kBF16>(dqacc, p.scale, p.dq, p.lddq, p.dq_col0 + h * D, qrow_base, q0 + warp * 16, p.Lq, lane);
+    }
+    if (dbias_s != nullptr) {
+        __syncthreads();
+        for (int x = threadIdx.x; x < ntab; x += THREADS) {
+            const float v = dbias_s[x];
+            if (v != 0.f) atomicAdd(p.dbias + static_cast<int64_t>(h) * ntab + x, v);
+        }
+    }
+}
+
+template <bool kBF16>
+__global__ void __launch_bounds__(THREADS, 3)
+attn_bwd_dkv2_kernel(const Params p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    // sK | sV | sQ[2] | sdO[2] | lse_s[2][64] | d_s[2][64] | bias (padded)
+    const int ntab = p.Lq + p.Lk - 1;
+    float* lse_s = reinterpret_cast<float*>(smem + 6 * TILE_BYTES);
+    float* d_s = lse_s + 2 * BN;
+    float* bias_s = p.bias_delta ? d_s + 2 * BN : nullptr;
+
+    const int nkb = (p.Lk + BM - 1) / BM;
+    const int kb = static_cast<int>(blockIdx.x) % nkb;
+    const int h = (static_cast<int>(blockIdx.x) / nkb) % p.H;
+    const int b = static_cast<int>(blockIdx.x) / (nkb * p.H);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int k0 = kb * BM;
+    const int64_t qrow_base = static_cast<int64_t>(b) * p.Lq, krow_base = static_cast<int64_t>(b) * p.Lk;
+    const float* lse_g = p.lse + (static_cast<int64_t>(b) * p.H + h) * p.Lq;
+    const float* d_g = p.dsum + (static_cast<int64_t>(b) * p.H + h) * p.Lq;
+
+    if (bias_s)
+        for (int x = threadIdx.x; x < ntab + 2 * BIAS_PAD; x += THREADS) {
+            const int d = x - BIAS_PAD;
+            bias_s[x] = (d >= 0 && d < ntab) ? __ldg(p.bias_delta + static_cast<int64_t>(h) * ntab + d) : 0.f;
+        }
+    const uint32_t smem_a = ab::smem_u32(smem);
+    const uint32_t sK_a = smem_a, sV_a = smem_a + TILE_BYTES;
+    load_tile(smem, p.k, p.ldk, p.k_col0 + h * D, krow_base, k0, p.Lk);
+    load_tile(smem + TILE_BYTES, p.v, p.ldv, p.v_col0 + h * D, krow_base, k0, p.Lk);
+
+    const int j_lo = k0 + warp * 16 + g;
+    float mk[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int j = j_lo + r * 8;
+        mk[r] = (p.add_mask != nullptr && j < p.Lk) ? __ldg(p.add_mask + static_cast<int64_t>(b) * p.Lk + j) : 0.f;
+    }
+    const int nqb = (p.Lq + BN - 1) / BN;
+    auto prefetch = [&](int qb, int buf) {
+        load_tile_async(smem_a + (2 + buf) * TILE_BYTES, p.q, p.ldq, p.q_col0 + h * D, qrow_base, qb * BN, p.Lq);
+        load_tile_async(smem_a + (4 + buf) * TILE_BYTES, p.dout, p.lddo, h * D, qrow_base, qb * BN, p.Lq);
+        if (threadIdx.x < BN) {
+            const int i = qb * BN + static_cast<int>(threadIdx.x);
+            lse_s[buf * BN + threadIdx.x] = i < p.Lq ? __ldg(lse_g + i) : INFINITY;
+            d_s[buf * BN + threadIdx.x] = i < p.Lq ? __ldg(d_g + i) : 0.f;
+        }
+        cp_async_commit();
+    };
+    prefetch(0, 0);
+
+    float dkacc[8][4], dvacc[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            dkacc[nt][e] = 0.f;
+            dvacc[nt][e] = 0.f;
+        }
+    const float* bias_c = bias_s ? bias_s + BIAS_PAD : nullptr;
+    for (int qb = 0; qb < nqb; ++qb) {
+        const int buf = qb & 1;
+        cp_async_wait_all();
+        __syncthreads();
+        if (qb + 1 < nqb) prefetch(qb + 1, buf ^ 1);
+        const uint32_t sQ_a = smem_a + (2 + buf) * TILE_BYTES, sdO_a = smem_a + (4 + buf) * TILE_BYTES;
+        float acc[8][4], dp[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                acc[nt][e] = 0.f;
+                dp[nt][e] = 0.f;
+            }
+        mma_rows_tileT<kBF16>(acc, sK_a, warp * 16, sQ_a, lane);      // S^T  = K Q^T
+        mma_rows_tileT<kBF16>(dp, sV_a, warp * 16, sdO_a, lane);      // dP^T = V dO^T
+        const int base = j_lo - (qb * BN + 2 * t) + p.Lq - 1;         // table offset of (key j_lo, query column 2t)
+        const float* ls = lse_s + buf * BN + 2 * t;
+        const float* dd = d_s + buf * BN + 2 * t;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int half = e >> 1, e2 = e & 1;
+                const int j = j_lo + half * 8, i = qb * BN + nt * 8 + 2 * t + e2;
+                float sc = acc[nt][e] * p.scale + mk[half];
+                if (bias_c != nullptr) sc += bias_c[base + 8 * (half - nt) - e2];
+                if (p.causal_value != 0.f && j > min(i, p.Lq - 1)) sc += p.causal_value;
+                if (j >= p.Lk) sc = -INFINITY;
+                const float pr = __expf(sc - ls[nt * 8 + e2]);
+                acc[nt][e] = pr;
+                dp[nt][e] = pr * (dp[nt][e] - dd[nt * 8 + e2]);
+            }
+        mma_p_tile<kBF16>(dvacc, acc, sdO_a, lane);   // dV += P^T dO
+        mma_p_tile<kBF16>(dkacc, dp, sQ_a, lane);     // dK += dS^T Q
+    }
+    store_acc<kBF16>(dkacc, p.scale, p.dk, p.lddk, p.dk_col0 + h * D, krow_base, k0 + warp * 16, p.Lk, lane);
+    store_acc<kBF16>(dvacc, 1.0f, p.dv, p.lddv, p.dv_col0 + h * D, krow_base, k0 + warp * 16, p.Lk, lane);
+}
+
 }  // namespace attnb
 
 extern "C" {
@@ -498,11 +788,20 @@ int atlas_b200_attention_bwd(const void* q, int64_t ldq, int32_t q_col0, const v
     p.scale = scale;
     p.causal_value = causal_value;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const int smem_dq = 4 * TILE_BYTES + static_cast<int>(((bias_delta ? ntab : 0) + (dbias_delta ? ntab : 0)) * 4);
-    const int smem_dkv = 4 * TILE_BYTES + 2 * BN * 4 + static_cast<int>((bias_delta ? ntab : 0) * 4);
-    constexpr int SMEM_MAX = 4 * TILE_BYTES + 2 * BN * 4 + 2 * 8192 * 4;
+    static const bool force_v1 = getenv("ATLAS_B200_ATTN_BWD_V1") != nullptr;   // A/B measurements
+    const bool v2 = lse_given != 0 && !force_v1;
+    const int smem_dq = v2 ? 6 * TILE_BYTES + 2 * BN * 4 +
+                                 static_cast<int>(((bias_delta ? ntab + 2 * BIAS_PAD : 0) + (dbias_delta ? ntab : 0)) * 4)
+                           : 4 * TILE_BYTES + static_cast<int>(((bias_delta ? ntab : 0) + (dbias_delta ? ntab : 0)) * 4);
+    const int smem_dkv = v2 ? 6 * TILE_BYTES + 4 * BN * 4 + static_cast<int>((bias_delta ? ntab + 2 * BIAS_PAD : 0) * 4)
+                            : 4 * TILE_BYTES + 2 * BN * 4 + static_cast<int>((bias_delta ? ntab : 0) * 4);
+    constexpr int SMEM_MAX = 6 * TILE_BYTES + 4 * BN * 4 + 2 * (8192 + 2 * BIAS_PAD) * 4;
     static bool attr_set = false;
     if (!attr_set) {
+        AB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dq2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+        AB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dq2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+        AB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dkv2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+        AB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dkv2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
         AB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
         AB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
         AB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dkv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
@@ -510,7 +809,15 @@ int atlas_b200_attention_bwd(const void* q, int64_t ldq, int32_t q_col0, const v
         attr_set = true;
     }
     abh::prof_begin(s, abh::PROF_ATTENTION_BWD);
-    if (is_bf16) {
+    if (v2) {
+        if (is_bf16) {
+            attn_bwd_dq2_kernel<true><<<static_cast<unsigned>(nq_ctas), THREADS, smem_dq, s>>>(p);
+            attn_bwd_dkv2_kernel<true><<<static_cast<unsigned>(nk_ctas), THREADS, smem_dkv, s>>>(p);
+        } else {
+            attn_bwd_dq2_kernel<false><<<static_cast<unsigned>(nq_ctas), THREADS, smem_dq, s>>>(p);
+            attn_bwd_dkv2_kernel<false><<<static_cast<unsigned>(nk_ctas), THREADS, smem_dkv, s>>>(p);
+        }
+    } else if (is_bf16) {
         attn_bwd_dq_kernel<true><<<static_cast<unsigned>(nq_ctas), THREADS, smem_dq, s>>>(p);
         attn_bwd_dkv_kernel<true><<<static_cast<unsigned>(nk_ctas), THREADS, smem_dkv, s>>>(p);
     } else {

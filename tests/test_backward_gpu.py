@@ -337,3 +337,33 @@ def test_wgrad_mn_major_gemm_exact(dev, dtype, tokens, N, K):
     wide = torch.zeros(tokens, N + 64, dtype=dtype, device=dev)
     wide[:, 32:32 + N] = dy
     assert torch.equal(ops.linear_wgrad(wide[:, 32:32 + N], x), want)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_attention_backward_recompute_path_matches(dev, dtype):
+    """atlas_b200_attention_bwd without the forward's log-sum-exp (first-generation kernels: one more pass over the keys
+    recomputes it) agrees with the default path that reads the lse written by the forward kernel."""
+    from atlas_b200 import ops
+
+    g = torch.Generator(device="cpu").manual_seed(41)
+    B, H, L = 3, 4, 200
+    qkv = (torch.randn(B * L, 3 * H * 64, generator=g) * 0.35).to(dtype).to(dev)
+    bias = (0.5 * torch.randn(H, 2 * L - 1, generator=g)).to(dev)
+    mask = ((torch.arange(L)[None, :] >= torch.tensor([L, 150, 77])[:, None]).float() * -10000.0).to(dev)
+    out, lse = ops.attention(qkv, 0, qkv, H * 64, qkv, 2 * H * 64, B, H, L, L, add_mask=mask, bias_delta=bias,
+                             return_lse=True)
+    dout = torch.randn(B * L, H * 64, generator=g).to(dtype).to(dev)
+    res = []
+    for use_lse in (True, False):
+        dqkv = torch.empty_like(qkv)
+        db = ops.attention_bwd(qkv, 0, qkv, H * 64, qkv, 2 * H * 64, out, dout, dqkv, 0, dqkv, H * 64, dqkv, 2 * H * 64,
+                               B, H, L, L, add_mask=mask, bias_delta=bias, need_dbias=True, lse=lse if use_lse else None)
+        res.append((dqkv, db))
+    close(res[1][0], res[0][0], REL[dtype] / 4, "dqkv v1 vs v2")
+    close(res[1][1], res[0][1], REL[dtype] / 4, "dbias v1 vs v2")
+    # the forward's lse is the log-sum-exp of the scores
+    q, k, _ = (t.reshape(B, L, H, 64) for t in qkv.float().split(H * 64, dim=1))
+    i = torch.arange(L, device=dev)[:, None]
+    j = torch.arange(L, device=dev)[None, :]
+    s = torch.einsum("bihd,bjhd->bhij", q, k) + bias[:, (j - i + L - 1)][None] + mask[:, None, None, :]
+    assert float((torch.logsumexp(s, -1) - lse).abs().max()) <= 2e-3

@@ -98,6 +98,23 @@ if "step" in what:
             print(f"    {k:14s} {ms:8.2f} ms in {n:4d} launches = {tf:7.1f} TFLOP/s  ({100 * ms / t_step:.0f} % of the step)")
         sys.stdout.flush()
 
+if "launchlist" in what:
+    # one FiD-base training step (1 query) inside an NVTX range, for `ncu --nvtx --nvtx-include "atlas_b200_train/"`
+    model = FiD(T5ConfigLite()).to(torch.bfloat16).to(dev).train()
+    n_ctx, L, T, B = 40, 384, 32, 1
+    model.encoder.config.n_context, model.encoder.config.bsz = n_ctx, B
+    ids = torch.randint(2, 32000, (B, n_ctx * L), device=dev)
+    mask = torch.ones(B, n_ctx * L, dtype=torch.bool, device=dev)
+    labels = torch.randint(2, 32000, (B, T), device=dev)
+    for i in range(3):
+        if i == 2:
+            torch.cuda.synchronize()
+            torch.cuda.nvtx.range_push("atlas_b200_train")
+        model.zero_grad(set_to_none=True)
+        model(input_ids=ids, attention_mask=mask, labels=labels)[0].backward()
+    torch.cuda.synchronize()
+    torch.cuda.nvtx.range_pop()
+
 if "ops" in what:
     M, d, dff, H, S, L = 30720, 768, 2048, 12, 80, 384
     x = torch.randn(M, d, device=dev).bfloat16() * 0.1

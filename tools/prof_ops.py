@@ -33,3 +33,23 @@ elif what == "gemm":
     fn = lambda: ops.linear(x, w, epilogue=ops.EPI_GATED)
     ms = timed(fn, reps)
     print(f"gemm M={M} N={N} K={K} gated: {ms:.3f} ms = {2 * M * N * K / ms / 1e9:.0f} TFLOP/s")
+elif what == "attn_bwd":
+    S, H, L = 80, 12, 384       # FiD-base encoder, 2 queries x 40 passages (the bench's training leg)
+    qkv = torch.randn(S * L, 3 * H * 64, device=dev).bfloat16() * 0.2
+    bias = torch.randn(H, 2 * L - 1, device=dev)
+    am = torch.zeros(S, L, device=dev)
+    out, lse = ops.attention(qkv, 0, qkv, H * 64, qkv, 2 * H * 64, S, H, L, L, add_mask=am, bias_delta=bias, return_lse=True)
+    do = torch.randn_like(out)
+    dqkv = torch.empty_like(qkv)
+    fn = lambda: ops.attention_bwd(qkv, 0, qkv, H * 64, qkv, 2 * H * 64, out, do, dqkv, 0, dqkv, H * 64, dqkv, 2 * H * 64,
+                                   S, H, L, L, add_mask=am, bias_delta=bias, need_dbias=True, lse=lse)
+    ms = timed(fn, reps)
+    print(f"attention bwd S={S} H={H} L={L} (lse from the forward, dbias): {ms:.3f} ms = "
+          f"{14 * S * H * L * L * 64 / ms / 1e9:.0f} TFLOP/s executed (7 tile GEMMs), {10 * S * H * L * L * 64 / ms / 1e9:.0f} useful")
+elif what == "wgrad":
+    M, N, K = 30720, 4096, 768  # dW of the interleaved wi_0|wi_1 projection, 2 queries
+    x = torch.randn(M, K, device=dev).bfloat16() * 0.1
+    dy = torch.randn(M, N, device=dev).bfloat16() * 0.1
+    fn = lambda: ops.linear_wgrad(dy, x)
+    ms = timed(fn, reps)
+    print(f"wgrad tokens={M} N={N} K={K} (MN-major tcgen05): {ms:.3f} ms = {2 * M * N * K / ms / 1e9:.0f} TFLOP/s")
