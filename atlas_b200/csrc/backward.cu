@@ -87,7 +87,9 @@ colsum_kernel(const uint16_t* __restrict__ x, int64_t ld, float* __restrict__ ou
 //                           dw += dy * r16(xn),  db += dy
 // One warp per row (grid-stride over rows); dw / db accumulate in shared memory, flushed once per block.
 constexpr int MAXV = 8;
-template <bool kBF16, bool kCentre>
+// NV = 16-byte vectors per lane (H <= NV * 256).  kRegAcc: dw / db partial sums live in registers across the rows a warp
+// processes and reach shared memory once per warp (NV <= 4: H <= 1024); otherwise one shared atomic per element and row.
+template <bool kBF16, bool kCentre, int NV, bool kRegAcc>
 __global__ void __launch_bounds__(256)
 norm_bwd_kernel(const uint16_t* __restrict__ x, int64_t ldx, const uint16_t* __restrict__ dy, int64_t lddy,
                 const uint16_t* __restrict__ w, const uint16_t* __restrict__ dres, int64_t lddres,
@@ -100,11 +102,25 @@ norm_bwd_kernel(const uint16_t* __restrict__ x, int64_t ldx, const uint16_t* __r
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const int nvec = H >> 3;
+    float wv[NV][8];                              // the norm weight of this lane's columns
+    float rdw[kRegAcc ? NV : 1][8], rdb[kRegAcc ? NV : 1][8];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int vec = lane + 32 * i;
+        uint4 ww = make_uint4(0, 0, 0, 0);
+        if (vec < nvec) ww = __ldg(reinterpret_cast<const uint4*>(w) + vec);
+        const uint32_t w4[4] = {ww.x, ww.y, ww.z, ww.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            wv[i][e] = f32<kBF16>(w4[e >> 1] >> ((e & 1) * 16));
+            if (kRegAcc) rdw[i][e] = rdb[i][e] = 0.f;
+        }
+    }
     for (int row = blockIdx.x * nwarp + warp; row < rows; row += gridDim.x * nwarp) {
-        float xv[MAXV][8], gv[MAXV][8];
+        float xv[NV][8], gv[NV][8];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int i = 0; i < MAXV; ++i) {
+        for (int i = 0; i < NV; ++i) {
             const int vec = lane + 32 * i;
             if (vec < nvec) {
                 const uint4 a = __ldg(reinterpret_cast<const uint4*>(x + row * ldx) + vec);
@@ -114,8 +130,7 @@ norm_bwd_kernel(const uint16_t* __restrict__ x, int64_t ldx, const uint16_t* __r
                 for (int e = 0; e < 4; ++e) {
                     xv[i][2 * e] = f32<kBF16>(aw[e]);
                     xv[i][2 * e + 1] = f32<kBF16>(aw[e] >> 16);
-                    // gv holds dy for now; the weight is applied below
-                    gv[i][2 * e] = f32<kBF16>(dw4[e]);
+                    gv[i][2 * e] = f32<kBF16>(dw4[e]);          // dy for now; the weight is applied below
                     gv[i][2 * e + 1] = f32<kBF16>(dw4[e] >> 16);
                     s1 += xv[i][2 * e] + xv[i][2 * e + 1];
                     s2 += xv[i][2 * e] * xv[i][2 * e] + xv[i][2 * e + 1] * xv[i][2 * e + 1];
@@ -128,20 +143,21 @@ norm_bwd_kernel(const uint16_t* __restrict__ x, int64_t ldx, const uint16_t* __r
         const float rs = rsqrtf(s2 / static_cast<float>(H) + eps);
         float m1 = 0.f, m2 = 0.f;
 #pragma unroll
-        for (int i = 0; i < MAXV; ++i) {
+        for (int i = 0; i < NV; ++i) {
             const int vec = lane + 32 * i;
             if (vec < nvec) {
-                const uint4 ww = __ldg(reinterpret_cast<const uint4*>(w) + vec);
-                const uint32_t w4[4] = {ww.x, ww.y, ww.z, ww.w};
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    const float wt = f32<kBF16>(w4[e >> 1] >> ((e & 1) * 16));
                     const float xn = (xv[i][e] - mean) * rs;
                     const float dyv = gv[i][e];
-                    const int col = vec * 8 + e;
-                    atomicAdd(&dw_s[col], dyv * rf<kBF16>(xn));
-                    if (db != nullptr) atomicAdd(&db_s[col], dyv);
-                    const float dxn = dyv * wt;
+                    if (kRegAcc) {
+                        rdw[i][e] = fmaf(dyv, rf<kBF16>(xn), rdw[i][e]);
+                        rdb[i][e] += dyv;
+                    } else {
+                        atomicAdd(&dw_s[vec * 8 + e], dyv * rf<kBF16>(xn));
+                        if (db != nullptr) atomicAdd(&db_s[vec * 8 + e], dyv);
+                    }
+                    const float dxn = dyv * wv[i][e];
                     gv[i][e] = dxn;
                     m1 += dxn;
                     m2 += dxn * xn;
@@ -151,7 +167,7 @@ norm_bwd_kernel(const uint16_t* __restrict__ x, int64_t ldx, const uint16_t* __r
         m1 = kCentre ? warp_sum(m1) / static_cast<float>(H) : 0.f;
         m2 = warp_sum(m2) / static_cast<float>(H);
 #pragma unroll
-        for (int i = 0; i < MAXV; ++i) {
+        for (int i = 0; i < NV; ++i) {
             const int vec = lane + 32 * i;
             if (vec < nvec) {
                 float o[8];
@@ -169,6 +185,19 @@ norm_bwd_kernel(const uint16_t* __restrict__ x, int64_t ldx, const uint16_t* __r
                 out.z = ab::pack2_rn<kBF16>(o[4], o[5]);
                 out.w = ab::pack2_rn<kBF16>(o[6], o[7]);
                 reinterpret_cast<uint4*>(dx + row * lddx)[vec] = out;
+            }
+        }
+    }
+    if (kRegAcc) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int vec = lane + 32 * i;
+            if (vec < nvec) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    atomicAdd(&dw_s[vec * 8 + e], rdw[i][e]);
+                    if (db != nullptr) atomicAdd(&db_s[vec * 8 + e], rdb[i][e]);
+                }
             }
         }
     }
@@ -436,13 +465,21 @@ int atlas_b200_layernorm_bwd(const void* x, int64_t ldx, const void* dy, int64_t
                    *wp = static_cast<const uint16_t*>(weight), *rp = static_cast<const uint16_t*>(dres);
     uint16_t* dxp = static_cast<uint16_t*>(dx);
     float* dbp = kind == 0 ? dbias : nullptr;
-    if (kind == 0) {
-        if (is_bf16) bw::norm_bwd_kernel<true, true><<<grid, 256, smem, s>>>(xp, ldx, dyp, lddy, wp, rp, lddres, dxp, lddx, dweight, dbp, rows, H, eps);
-        else bw::norm_bwd_kernel<false, true><<<grid, 256, smem, s>>>(xp, ldx, dyp, lddy, wp, rp, lddres, dxp, lddx, dweight, dbp, rows, H, eps);
-    } else {
-        if (is_bf16) bw::norm_bwd_kernel<true, false><<<grid, 256, smem, s>>>(xp, ldx, dyp, lddy, wp, rp, lddres, dxp, lddx, dweight, dbp, rows, H, eps);
-        else bw::norm_bwd_kernel<false, false><<<grid, 256, smem, s>>>(xp, ldx, dyp, lddy, wp, rp, lddres, dxp, lddx, dweight, dbp, rows, H, eps);
-    }
+    auto go = [&](auto kern) { kern<<<grid, 256, smem, s>>>(xp, ldx, dyp, lddy, wp, rp, lddres, dxp, lddx, dweight, dbp, rows, H, eps); };
+#define AB_NORM_BWD(NV, REG)                                                                      \
+    do {                                                                                          \
+        if (kind == 0) {                                                                          \
+            if (is_bf16) go(bw::norm_bwd_kernel<true, true, NV, REG>);                            \
+            else go(bw::norm_bwd_kernel<false, true, NV, REG>);                                   \
+        } else {                                                                                  \
+            if (is_bf16) go(bw::norm_bwd_kernel<true, false, NV, REG>);                           \
+            else go(bw::norm_bwd_kernel<false, false, NV, REG>);                                  \
+        }                                                                                         \
+    } while (0)
+    if (H <= 768) AB_NORM_BWD(3, true);
+    else if (H <= 1024) AB_NORM_BWD(4, true);
+    else AB_NORM_BWD(8, false);
+#undef AB_NORM_BWD
     abh::count_launch();
     AB_CUDA_CHECK(cudaGetLastError());
     return ATLAS_B200_OK;

@@ -1,6 +1,7 @@
 """Drop-in for `src.fid.FiD` (reference src/fid.py:28-357 over the vendored T5 v1.1, src/modeling_t5.py):
-Fusion-in-Decoder forward on B200 kernels.  FORWARD ONLY in this round (evaluation / scoring / greedy
-generation); backward through the fused kernels is not implemented yet.
+Fusion-in-Decoder on B200 kernels: the no-grad forward (evaluation / scoring / greedy generation, replayed from a
+CUDA graph), the with-grad forward + hand-written backward kernels of the training step (`_forward_train`, grad_ops.py),
+and the cross-attention score capture used for retriever distillation (src/fid.py:126-235,333-343).
 
 Surface kept: `FiD(config)`, `forward(input_ids [B, n*L], attention_mask, decoder_input_ids,
 labels, encoder_outputs=None, use_cache=False)` -> output indexable as `out[0]` = loss, `out[1]` = logits with
@@ -14,8 +15,8 @@ tcgen05 GEMM with fused residual and gated-GELU epilogues (modeling_t5.py:281-28
 B*n independent L-token segments with the relative-position bias added on the fly from a [H, 2L-1] table
 (modeling_t5.py:352-416,478-524) - the [B*n, H, L, L] bias / probability tensors are never materialised;
 decoder cross-attention over the n*L concatenated keys as split-KV + combine (fid.py:298-349).
-Not reproduced: dropout (eval only), the `isinf` clamps and their three host syncs per block
-(modeling_t5.py:657-708), cross-attention score capture (fid.py:126-235).
+Not reproduced: dropout (the training path runs without it and warns once), the `isinf` clamps and their three host
+syncs per block (modeling_t5.py:657-708).
 """
 import copy
 import math

@@ -1,7 +1,8 @@
 """Drop-in for `src.retrievers` (reference src/retrievers.py:16-135): Contriever = BERT encoder + masked
-mean pooling, and the dual-encoder wrappers.  FORWARD ONLY in this round (index build / refresh and query
-embedding under `torch.no_grad`, which is how `Atlas.build_index` / `Atlas._retrieve` call it,
-src/atlas.py:61-88,90-118); the retriever-with-grad path of training is not provided yet.
+mean pooling, and the dual-encoder wrappers.  Under `torch.no_grad` (index build / refresh, query embedding:
+`Atlas.build_index` / `Atlas._retrieve`, src/atlas.py:61-88,90-118) the fused forward runs; with gradients enabled
+(retriever training, src/atlas.py:457-465) the same kernels run forward with the hand-written backward kernels behind
+torch.autograd (`_encode_train`, grad_ops.py).
 
 Parameter names and shapes are those of the reference's `BertModel` (vendored HF 4.18,
 src/modeling_bert.py:190-648,872-1045), so `load_state_dict` of a Contriever checkpoint works:
