@@ -108,7 +108,9 @@ def lib():
     L.atlas_b200_cross_attention_stats.argtypes = [vp, i64, i32, vp, i64, i32, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32,
                                                    f32, i32, vp]
     L.atlas_b200_linear_wgrad.restype = c.c_int
-    L.atlas_b200_linear_wgrad.argtypes = [vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, vp]
+    L.atlas_b200_linear_wgrad.argtypes = [vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, vp, c.c_size_t, vp]
+    L.atlas_b200_linear_wgrad_workspace_bytes.restype = c.c_size_t
+    L.atlas_b200_linear_wgrad_workspace_bytes.argtypes = [i32, i32, i32]
     L.atlas_b200_transpose.restype = c.c_int
     L.atlas_b200_transpose.argtypes = [vp, i64, vp, i64, i32, i32, i32, vp]
     L.atlas_b200_colsum.restype = c.c_int
@@ -160,6 +162,7 @@ EXPORTED_SYMBOLS = [
     "atlas_b200_attention_combine_ex",
     "atlas_b200_cross_attention_stats",
     "atlas_b200_linear_wgrad",
+    "atlas_b200_linear_wgrad_workspace_bytes",
     "atlas_b200_transpose",
     "atlas_b200_colsum",
     "atlas_b200_layernorm_bwd",

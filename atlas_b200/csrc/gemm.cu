@@ -72,6 +72,11 @@ struct Params {
     const float* row_ss;
     float* out_ss;
     float rs_eps;
+    // split-K (weight gradients: few output tiles, very long contraction): work item = (tile, split); split s covers the
+    // k-blocks [s * kb_per_split, (s + 1) * kb_per_split) and stores its fp32 partial tile to C32 + s * M * N (row stride N);
+    // splitk_reduce_kernel sums the partials and rounds once.  splits == 1 / C32 == nullptr: the ordinary epilogues.
+    int splits, kb_per_split;
+    float* C32;
 };
 
 template <bool kBF16>
@@ -152,7 +157,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     constexpr int TILE_M = BLOCK_M * C::CTAS;
     const int num_m = (p.M + TILE_M - 1) / TILE_M;
     const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
-    const int num_tiles = num_m * num_n;
+    const int num_tiles = num_m * num_n * p.splits;     // work items: (tile, split), split fastest
     const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
 
     if (warp == 0 && lane == 0) {
@@ -184,10 +189,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             for (int t = group; t < num_tiles; t += num_groups) {
-                const int m_blk = t / num_n, n_blk = t % num_n;
+                const int tile = t / p.splits, split = t % p.splits;
+                const int m_blk = tile / num_n, n_blk = tile % num_n;
                 const int a_row = m_blk * TILE_M + static_cast<int>(cta_rank) * BLOCK_M;
                 const int b_row = n_blk * BLOCK_N + static_cast<int>(cta_rank) * C::B_ROWS;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                const int kb0 = split * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     ab::mbar_wait(&empty_bar[stage], phase ^ 1u, 11);
                     uint8_t* st = smem_gen + stage * C::STAGE_BYTES;
                     if constexpr (kTN) {
@@ -246,7 +253,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 ab::mbar_wait(&tmem_empty_bar[buf], ((it >> 1) & 1) ^ 1u, 12);
                 ab::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * BLOCK_N;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                const int kb0 = (t % p.splits) * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     ab::mbar_wait(&full_bar[stage], phase, 13);
                     ab::tc_fence_after();
                     if constexpr (kTN) {
@@ -255,7 +263,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 #pragma unroll
                         for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                             ab::umma_ss<C::CTAS>(d_tmem, adesc0 + ((k * UMMA_K * 128) >> 4),
-                                                 bdesc0 + ((k * UMMA_K * 128) >> 4), idesc, (kb | k) != 0 ? 1u : 0u);
+                                                 bdesc0 + ((k * UMMA_K * 128) >> 4), idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
                         }
                     } else {
                         const uint64_t adesc0 = ab::umma_desc_k_sw128(smem_base + stage * C::STAGE_BYTES);
@@ -263,7 +271,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 #pragma unroll
                         for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                             ab::umma_ss<C::CTAS>(d_tmem, adesc0 + ((k * UMMA_K * 2) >> 4),
-                                                 bdesc0 + ((k * UMMA_K * 2) >> 4), idesc, (kb | k) != 0 ? 1u : 0u);
+                                                 bdesc0 + ((k * UMMA_K * 2) >> 4), idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
                         }
                     }
                     if constexpr (kPair) {
@@ -291,7 +299,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         int it = 0;
         for (int t = group; t < num_tiles; t += num_groups, ++it) {
             const uint32_t buf = it & 1;
-            const int m_blk = t / num_n, n_blk = t % num_n;
+            const int tile = t / p.splits, split = t % p.splits;
+            const int m_blk = tile / num_n, n_blk = tile % num_n;
             const int row = m_blk * TILE_M + static_cast<int>(cta_rank) * BLOCK_M + static_cast<int>(lg * 32 + lane);
             // fused RMSNorm of the A rows: a per-row scale of the accumulator (loaded while the MMAs run)
             const float rscale = (p.row_ss != nullptr && row < p.M)
@@ -316,6 +325,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                     }
                 }
                 if (row >= p.M || col0 >= p.N) continue;
+                if (p.C32 != nullptr) {   // split-K partial: raw fp32 accumulator
+                    float* crow = p.C32 + (static_cast<size_t>(split) * p.M + row) * p.N + col0;
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4)
+                        if (col0 + j4 * 4 < p.N)
+                            *reinterpret_cast<uint4*>(crow + j4 * 4) = make_uint4(r[4 * j4], r[4 * j4 + 1], r[4 * j4 + 2], r[4 * j4 + 3]);
+                    continue;
+                }
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * rscale;
@@ -411,7 +428,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
         attr_set = true;
     }
     const int tile_m = BLOCK_M * C::CTAS;
-    const int tiles = ((p.M + tile_m - 1) / tile_m) * ((p.N + BLOCK_N - 1) / BLOCK_N);
+    const int tiles = ((p.M + tile_m - 1) / tile_m) * ((p.N + BLOCK_N - 1) / BLOCK_N) * p.splits;
     const int groups_max = abh::num_sms() / C::CTAS;
     const int grid = (tiles < groups_max ? tiles : groups_max) * C::CTAS;
     abh::prof_begin(s, abh::PROF_LINEAR);
@@ -436,6 +453,26 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
     abh::count_launch();
     AB_CUDA_CHECK(cudaGetLastError());
     return ATLAS_B200_OK;
+}
+
+// out[i] = round16(sum_s part[s][i]) for the M*N outputs of a split-K GEMM (8 outputs per thread)
+template <bool kBF16>
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ part, uint16_t* __restrict__ out, int64_t ldc, int M, int N, int splits) {
+    const int64_t vecs = static_cast<int64_t>(M) * (N / 8);
+    for (int64_t idx = blockIdx.x * 256ll + threadIdx.x; idx < vecs; idx += gridDim.x * 256ll) {
+        const int64_t row = idx / (N / 8);
+        const int col = static_cast<int>(idx % (N / 8)) * 8;
+        float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int sidx = 0; sidx < splits; ++sidx) {
+            const float4* src = reinterpret_cast<const float4*>(part + (static_cast<size_t>(sidx) * M + row) * N + col);
+            const float4 x = __ldg(src), y = __ldg(src + 1);
+            a[0] += x.x; a[1] += x.y; a[2] += x.z; a[3] += x.w;
+            a[4] += y.x; a[5] += y.y; a[6] += y.z; a[7] += y.w;
+        }
+        *reinterpret_cast<uint4*>(out + row * ldc + col) =
+            make_uint4(pack2<kBF16>(a[0], a[1]), pack2<kBF16>(a[2], a[3]), pack2<kBF16>(a[4], a[5]), pack2<kBF16>(a[6], a[7]));
+    }
 }
 
 }  // namespace gemm
@@ -467,6 +504,9 @@ int atlas_b200_linear_ex(const void* A, int64_t lda, const void* W, int64_t ldw,
     AB_REQUIRE((reinterpret_cast<uintptr_t>(C) & 15u) == 0, "C must be 16-byte aligned");
     AB_REQUIRE(out_ss == nullptr || epilogue != EPI_GATED, "out_ss is not available with the gated epilogue");
     Params p;
+    p.splits = 1;
+    p.kb_per_split = (K + BLOCK_K - 1) / BLOCK_K;
+    p.C32 = nullptr;
     p.row_ss = row_ss;
     p.out_ss = out_ss;
     p.rs_eps = rs_eps;
@@ -505,8 +545,39 @@ int atlas_b200_linear_ex(const void* A, int64_t lda, const void* W, int64_t ldw,
     return wide ? launch<false, 256, false>(ta, tb, p, s) : launch<false, 128, false>(ta, tb, p, s);
 }
 
+// (tile shape, number of K splits) of a weight-gradient GEMM: minimise the number of waves of work items per split
+static void wgrad_plan(int32_t tokens, int32_t N, int32_t K, bool* pair, int* block_n, int* splits, int* kb_per_split) {
+    using namespace gemm;
+    *pair = K >= 256 && N >= 256;
+    *block_n = K >= 256 ? 256 : 128;
+    const int tile_m = *pair ? 256 : 128;
+    const int64_t tiles = static_cast<int64_t>((N + tile_m - 1) / tile_m) * ((K + *block_n - 1) / *block_n);
+    const int groups = abh::num_sms() / (*pair ? 2 : 1);
+    const int num_kb = (tokens + BLOCK_K - 1) / BLOCK_K;
+    int best = 1;
+    double best_t = 1e30;
+    for (int sp = 1; sp <= 16 && sp * 8 <= num_kb; ++sp) {     // every split keeps >= 8 k-blocks (512 tokens)
+        const int64_t waves = (tiles * sp + groups - 1) / groups;
+        const double t = static_cast<double>(waves) / sp + 0.02 * sp;   // + the partial-tile store / reduce cost
+        if (t < best_t - 1e-9) {
+            best_t = t;
+            best = sp;
+        }
+    }
+    const int per = (num_kb + best - 1) / best;
+    *kb_per_split = per > 0 ? per : 1;
+    *splits = num_kb > 0 ? (num_kb + *kb_per_split - 1) / *kb_per_split : 1;   // no empty split
+}
+
+size_t atlas_b200_linear_wgrad_workspace_bytes(int32_t tokens, int32_t N, int32_t K) {
+    bool pair;
+    int block_n, splits, per;
+    wgrad_plan(tokens, N, K, &pair, &block_n, &splits, &per);
+    return splits > 1 ? static_cast<size_t>(splits) * N * K * sizeof(float) : 0;
+}
+
 int atlas_b200_linear_wgrad(const void* dY, int64_t lddy, const void* X, int64_t ldx, void* dW, int64_t lddw, int32_t tokens,
-                            int32_t N, int32_t K, int32_t is_bf16, void* stream) {
+                            int32_t N, int32_t K, int32_t is_bf16, void* workspace, size_t workspace_bytes, void* stream) {
     using namespace gemm;
     AB_REQUIRE(tokens >= 0 && N > 0 && K > 0, "bad wgrad shape tokens=%d N=%d K=%d", tokens, N, K);
     AB_REQUIRE(N % 8 == 0 && K % 8 == 0 && lddy % 8 == 0 && ldx % 8 == 0 && lddw % 8 == 0,
@@ -530,8 +601,20 @@ int atlas_b200_linear_wgrad(const void* dY, int64_t lddy, const void* X, int64_t
     p.bias = nullptr;
     p.residual = nullptr;
     p.C = static_cast<uint16_t*>(dW);
-    const bool wide = K >= 256;
-    const bool pair = K >= 256 && N >= 256;
+    bool pair;
+    int block_n, splits, per;
+    wgrad_plan(tokens, N, K, &pair, &block_n, &splits, &per);
+    const bool wide = block_n == 256;
+    static const bool no_splitk = getenv("ATLAS_B200_WGRAD_NO_SPLITK") != nullptr;   // A/B measurements
+    const size_t need = static_cast<size_t>(splits) * N * K * sizeof(float);
+    if (splits > 1 && (no_splitk || workspace == nullptr || workspace_bytes < need ||
+                       (reinterpret_cast<uintptr_t>(workspace) & 15u) != 0)) {
+        splits = 1;                                      // no (usable) scratch: one CTA group walks the whole contraction
+        per = (tokens + BLOCK_K - 1) / BLOCK_K;
+    }
+    p.splits = splits;
+    p.kb_per_split = per;
+    p.C32 = splits > 1 ? static_cast<float*>(workspace) : nullptr;
     CUtensorMap ta, tb;
     // both maps: rows = tokens, box = {64 columns, 64 tokens}
     int rc = abh::make_tmap_2d_16bit(&ta, dY, static_cast<uint64_t>(tokens), static_cast<uint64_t>(N),
@@ -540,9 +623,18 @@ int atlas_b200_linear_wgrad(const void* dY, int64_t lddy, const void* X, int64_t
     rc = abh::make_tmap_2d_16bit(&tb, X, static_cast<uint64_t>(tokens), static_cast<uint64_t>(K), static_cast<uint64_t>(ldx),
                                  BLOCK_K, 64, is_bf16 != 0);
     if (rc) return rc;
-    if (pair) return is_bf16 ? launch<true, 256, true, true>(ta, tb, p, s) : launch<false, 256, true, true>(ta, tb, p, s);
-    if (is_bf16) return wide ? launch<true, 256, false, true>(ta, tb, p, s) : launch<true, 128, false, true>(ta, tb, p, s);
-    return wide ? launch<false, 256, false, true>(ta, tb, p, s) : launch<false, 128, false, true>(ta, tb, p, s);
+    if (pair) rc = is_bf16 ? launch<true, 256, true, true>(ta, tb, p, s) : launch<false, 256, true, true>(ta, tb, p, s);
+    else if (is_bf16) rc = wide ? launch<true, 256, false, true>(ta, tb, p, s) : launch<true, 128, false, true>(ta, tb, p, s);
+    else rc = wide ? launch<false, 256, false, true>(ta, tb, p, s) : launch<false, 128, false, true>(ta, tb, p, s);
+    if (rc || splits == 1) return rc;
+    const int64_t vecs = static_cast<int64_t>(N) * (K / 8);
+    const int64_t blocks = (vecs + 255) / 256, cap = static_cast<int64_t>(abh::num_sms()) * 8;
+    const int grid = static_cast<int>(blocks < cap ? blocks : cap);
+    if (is_bf16) splitk_reduce_kernel<true><<<grid, 256, 0, s>>>(p.C32, p.C, p.ldc, N, K, splits);
+    else splitk_reduce_kernel<false><<<grid, 256, 0, s>>>(p.C32, p.C, p.ldc, N, K, splits);
+    abh::count_launch();
+    AB_CUDA_CHECK(cudaGetLastError());
+    return ATLAS_B200_OK;
 }
 
 }  // extern "C"

@@ -31,6 +31,7 @@ class Workspace:
 
 
 _default_ws = Workspace()
+_wgrad_ws = Workspace()
 
 
 def _check_bank(bank):
@@ -331,8 +332,11 @@ def linear_wgrad(dy, x):
     M, N = dy2.shape
     K = x2.shape[1]
     dw = torch.empty((N, K), dtype=dy.dtype, device=dy.device)
+    nbytes = lib().atlas_b200_linear_wgrad_workspace_bytes(M, N, K)        # split-K partial tiles (0 = un-split)
+    ws = _wgrad_ws.get(nbytes, dy.device) if nbytes else None
     check(lib().atlas_b200_linear_wgrad(_ptr(dy2), dy2.stride(0), _ptr(x2), x2.stride(0), _ptr(dw), dw.stride(0), M, N, K,
-                                        _bf(dy), current_stream_ptr()))
+                                        _bf(dy), _ptr(ws) if ws is not None else None, ws.numel() if ws is not None else 0,
+                                        current_stream_ptr()))
     return dw
 
 

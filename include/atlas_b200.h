@@ -227,9 +227,15 @@ int atlas_b200_cross_attention_stats(const void* q, int64_t ldq, int32_t q_col0,
 /* Weight gradient of a Linear layer on tcgen05 (csrc/gemm.cu, MN-major operand descriptors):
  *     dW[N, K] = dY[tokens, N]^T . X[tokens, K]        16-bit operands, fp32 accumulation over the tokens
  * Both activations are read as they lie in memory (no transposes); dW is written in 16 bits like the reference's
- * bf16 gradients (`--precision bf16`, src/model_io.py:94-98). */
+ * bf16 gradients (`--precision bf16`, src/model_io.py:94-98).
+ * Split-K: output tiles are few (N x K weights) and the contraction long (all tokens), so with `workspace` of at least
+ * atlas_b200_linear_wgrad_workspace_bytes(tokens, N, K) bytes (device, 16-byte aligned) the token range is split over
+ * several CTA groups whose fp32 partial tiles are summed and rounded once by a second kernel; workspace == NULL (or too
+ * small) runs the un-split kernel. */
+size_t atlas_b200_linear_wgrad_workspace_bytes(int32_t tokens, int32_t N, int32_t K);
 int atlas_b200_linear_wgrad(const void* dY, int64_t lddy, const void* X, int64_t ldx, void* dW, int64_t lddw,
-                            int32_t tokens, int32_t N, int32_t K, int32_t is_bf16, void* stream);
+                            int32_t tokens, int32_t N, int32_t K, int32_t is_bf16, void* workspace,
+                            size_t workspace_bytes, void* stream);
 
 /* dst[c, r] = src[r, c] (16-bit elements) for r < R and 0 for R <= r < Rpad: the K-major operands of the weight-gradient
  * GEMM dW[N, K] = dY^T[N, M] . X[M, K] (contraction over the M tokens, padded to a multiple of 8). */
