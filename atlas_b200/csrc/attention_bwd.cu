@@ -486,7 +486,9 @@ __global__ void __launch_bounds__(THREADS, 3)
 attn_bwd_dq2_kernel(const Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int ntab = p.Lq + p.Lk - 1;
-    float* mask_s = reinterpret_cast<float*>(smem + 6 * TILE_BYTES);                       // [2][64]
+    // sQ | sdO | sK[2] | sV[2] | dS staging tile (dbias only) | mask_s[2][64] | bias (padded) | dbias
+    uint32_t* stage = reinterpret_cast<uint32_t*>(smem + 6 * TILE_BYTES);                  // [64][32] packed 16-bit pairs
+    float* mask_s = reinterpret_cast<float*>(smem + 7 * TILE_BYTES);                       // [2][64]
     float* bias_s = p.bias_delta ? mask_s + 2 * BN : nullptr;                              // [ntab + 2 * BIAS_PAD]
     float* dbias_s = p.dbias ? mask_s + 2 * BN + (p.bias_delta ? ntab + 2 * BIAS_PAD : 0) : nullptr;
 
@@ -596,10 +598,33 @@ attn_bwd_dq2_kernel(const Params p) {
                 if (p.causal_value != 0.f && j > min(i, p.Lq - 1)) sc += p.causal_value;
                 if (j >= p.Lk) sc = -INFINITY;
                 const float pr = __expf(sc - lse[half]);
-                const float ds = pr * (dp[nt][e] - drow[half]);
-                acc[nt][e] = ds;
-                if (dbias_s != nullptr && i < p.Lq && j < p.Lk) atomicAdd(&dbias_s[off], ds);
+                acc[nt][e] = pr * (dp[nt][e] - drow[half]);      // dS (0 for padding rows / keys: pr = 0)
             }
+        if (dbias_s != nullptr) {
+            // dbias[h, j - i] += dS[i, j]: the 64 x 64 dS tile (16-bit, as the MMAs below consume it) goes through a
+            // rotated shared tile, then thread d sums diagonal d - 63 and owns one table entry - no atomics.
+            // word(r, c / 2) = r * 32 + ((c / 2 + 4 r) & 31): conflict-free for the fragment stores and the diagonal reads
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int r = warp * 16 + g + half * 8;
+                    stage[r * 32 + ((nt * 4 + t + 4 * r) & 31)] = ab::pack2_rn<kBF16>(acc[nt][2 * half], acc[nt][2 * half + 1]);
+                }
+            __syncthreads();
+            const int dl = static_cast<int>(threadIdx.x) - 63;          // diagonal c - r in [-63, 63]
+            if (dl <= 63) {
+                float sum = 0.f;
+                const int r_lo = dl < 0 ? -dl : 0, r_hi = dl > 0 ? 63 - dl : 63;
+                for (int r = r_lo; r <= r_hi; ++r) {
+                    const int c = r + dl;
+                    const uint32_t w = stage[r * 32 + (((c >> 1) + 4 * r) & 31)];
+                    sum += to_f32<kBF16>((c & 1) ? (w >> 16) : (w & 0xFFFFu));
+                }
+                const int idx = kb * BN - q0 + dl + p.Lq - 1;
+                if (idx >= 0 && idx < ntab) dbias_s[idx] += sum;       // one owner per entry within a tile
+            }
+        }
         mma_p_tile<kBF16>(dqacc, acc, sK_a, lane);
     }
     if (p.dq_accum != nullptr) {
@@ -790,12 +815,12 @@ int atlas_b200_attention_bwd(const void* q, int64_t ldq, int32_t q_col0, const v
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     static const bool force_v1 = getenv("ATLAS_B200_ATTN_BWD_V1") != nullptr;   // A/B measurements
     const bool v2 = lse_given != 0 && !force_v1;
-    const int smem_dq = v2 ? 6 * TILE_BYTES + 2 * BN * 4 +
+    const int smem_dq = v2 ? 7 * TILE_BYTES + 2 * BN * 4 +
                                  static_cast<int>(((bias_delta ? ntab + 2 * BIAS_PAD : 0) + (dbias_delta ? ntab : 0)) * 4)
                            : 4 * TILE_BYTES + static_cast<int>(((bias_delta ? ntab : 0) + (dbias_delta ? ntab : 0)) * 4);
     const int smem_dkv = v2 ? 6 * TILE_BYTES + 4 * BN * 4 + static_cast<int>((bias_delta ? ntab + 2 * BIAS_PAD : 0) * 4)
                             : 4 * TILE_BYTES + 2 * BN * 4 + static_cast<int>((bias_delta ? ntab : 0) * 4);
-    constexpr int SMEM_MAX = 6 * TILE_BYTES + 4 * BN * 4 + 2 * (8192 + 2 * BIAS_PAD) * 4;
+    constexpr int SMEM_MAX = 7 * TILE_BYTES + 4 * BN * 4 + 2 * (8192 + 2 * BIAS_PAD) * 4;
     static bool attr_set = false;
     if (!attr_set) {
         AB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dq2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
