@@ -25,7 +25,7 @@ import numpy as np
 import torch
 from torch import nn
 
-from . import dist_utils
+from . import dist_utils, token_cache
 from ._lib import AtlasB200Error
 from .retrievers import EMBEDDINGS_DIM
 
@@ -87,6 +87,7 @@ class Atlas(nn.Module):
         self.retriever_tokenizer = retriever_tokenizer
         self.opt = opt
         self.READER_ALL_TOKENS = list(self.reader_tokenizer.vocab.values())
+        self._token_cache, self._token_cache_key = None, None     # retriever-side passage tokens, kept across refreshes
 
     # ------------------------------------------------------------------------------------------
     # passage side of the retriever: index build / refresh
@@ -125,16 +126,35 @@ class Atlas(nn.Module):
         max_len = min(self.opt.text_maxlength, gpu_embedder_batch_size)
         total = 0
         n_batch = math.ceil(len(passages) / gpu_embedder_batch_size)
+        # token cache (atlas_b200/token_cache.py): the first build tokenises like the reference and records the ids; later
+        # refreshes of the SAME passage shard slice identical batches out of the record instead of re-tokenising
+        use_cache = bool(getattr(self.opt, "cache_retriever_tokens", True)) and len(passages) > 0 and token_cache.fits(
+            len(passages), max_len, int(getattr(self.opt, "token_cache_max_bytes", 8 << 30)))
+        key = token_cache.cache_key(passages, max_len, fmt)
+        cache = self._token_cache if (use_cache and self._token_cache_key == key and self._token_cache is not None
+                                      and self._token_cache.complete) else None
+        record = None
+        if use_cache and cache is None:
+            record = token_cache.RetrieverTokenCache(len(passages), max_len, device=getattr(self.opt, "token_cache_device", "cpu"))
         for i in range(n_batch):
-            chunk = passages[i * gpu_embedder_batch_size:(i + 1) * gpu_embedder_batch_size]
-            enc = self.retriever_tokenizer([fmt.format(**p) for p in chunk], padding="longest", return_tensors="pt",
-                                           max_length=max_len, truncation=True)
-            enc = _to_cuda(enc)
-            rows = bank[total:total + len(chunk)]
+            a, b = i * gpu_embedder_batch_size, min(len(passages), (i + 1) * gpu_embedder_batch_size)
+            if cache is not None:
+                ids, mask = cache.batch(a, b, device=_device())
+                enc = {"input_ids": ids, "attention_mask": mask}
+            else:
+                chunk = passages[a:b]
+                enc = self.retriever_tokenizer([fmt.format(**p) for p in chunk], padding="longest", return_tensors="pt",
+                                               max_length=max_len, truncation=True)
+                if record is not None:
+                    record.append(enc["input_ids"], enc["attention_mask"])
+                enc = _to_cuda(enc)
+            rows = bank[total:total + (b - a)]
             tower.embed_into(enc["input_ids"], enc["attention_mask"], rows, dtype=torch.float16)
-            total += len(chunk)
+            total += b - a
             if logger is not None and i % 500 == 0 and i > 0:
                 logger.info(f"Number of passages encoded: {total}")
+        if record is not None and record.complete:
+            self._token_cache, self._token_cache_key = record, key
         dist_utils.barrier()
         if logger is not None:
             logger.info(f"{total} passages encoded on process: {dist_utils.get_rank()}")
