@@ -174,10 +174,11 @@ class Contriever(nn.Module):
         return load_pretrained(cls, BertConfigLite, path, **kw)
 
     def gradient_checkpointing_enable(self):
-        pass
+        """`--use_gradient_checkpoint_retriever` (src/atlas.py:454-455): recompute each BERT layer in the backward."""
+        self._grad_ckpt = True
 
     def gradient_checkpointing_disable(self):
-        pass
+        self._grad_ckpt = False
 
     def _dtype(self):
         d = self.embeddings.word_embeddings.weight.dtype
@@ -246,7 +247,8 @@ class Contriever(nn.Module):
         h = g.layernorm(x.view(B * L, H), W["embeddings.LayerNorm.weight"], W["embeddings.LayerNorm.bias"],
                         c.layer_norm_eps, kind=0)
         add_mask = (1.0 - attention_mask.to(torch.float32)) * -10000.0
-        for i in range(c.num_hidden_layers):
+
+        def layer(i, h):
             p = f"encoder.layer.{i}."
             a = p + "attention.self."
             wqkv = torch.cat([W[a + "query.weight"], W[a + "key.weight"], W[a + "value.weight"]], 0)
@@ -258,8 +260,16 @@ class Contriever(nn.Module):
                              c.layer_norm_eps, kind=0)
             z = g.linear(h1, W[p + "intermediate.dense.weight"], W[p + "intermediate.dense.bias"])
             s2 = g.linear(g.gelu_erf(z), W[p + "output.dense.weight"], W[p + "output.dense.bias"], residual=h1)
-            h = g.layernorm(s2, W[p + "output.LayerNorm.weight"], W[p + "output.LayerNorm.bias"], c.layer_norm_eps,
-                            kind=0)
+            return g.layernorm(s2, W[p + "output.LayerNorm.weight"], W[p + "output.LayerNorm.bias"], c.layer_norm_eps,
+                               kind=0)
+
+        for i in range(c.num_hidden_layers):
+            if getattr(self, "_grad_ckpt", False):
+                from torch.utils.checkpoint import checkpoint
+
+                h = checkpoint(layer, i, h, use_reentrant=False)
+            else:
+                h = layer(i, h)
         return h.view(B, L, H)
 
     def forward(self, input_ids=None, attention_mask=None, token_type_ids=None, position_ids=None, head_mask=None,
