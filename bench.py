@@ -218,7 +218,7 @@ def run_reference(args):
         "e2e": {"value": leg["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args):
@@ -397,7 +397,7 @@ def run_ours(args):
     if not args.no_cpu_baseline and world == 1:
         leg = cpu_reference_leg(B, args.rows)
         line["cpu_baseline"] = {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -538,8 +538,26 @@ def mips_leg(args, index, dev, world, rank, L, barrier_sync, max_over_ranks):
     }
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract goes to the process's original stdout; everything else that writes to fd 1
+    during the run (NCCL prints its version there when NCCL_DEBUG=VERSION) has been pointed at stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
     args = parse()
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
