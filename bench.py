@@ -366,6 +366,13 @@ def run_ours(args):
         return
 
     peak, peak_src = peaks("tensor")
+    gemm_traffic, gemm_traffic_note = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    if os.path.exists(tpath):     # dram bytes of ONE representative launch from the committed `ncu --set full` capture
+        with open(tpath) as f:
+            tj = json.load(f)
+        gemm_traffic = tj.get("dram_bytes_per_launch")
+        gemm_traffic_note = f"{tj.get('launch')}: algorithmic {tj.get('algorithmic_bytes_per_launch')} B; {tj.get('source')}"
     g_ms, g_n, g_flops = prof["gemm"]
     a_ms, a_n, a_flops = prof["attention"]
     achieved = g_flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
@@ -375,7 +382,8 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": workload_config(args),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                     "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak if peak else None, "traffic": gemm_traffic, "traffic_note": gemm_traffic_note,
+                     "peak_source": peak_src,
                      "kernel": "gemm_kernel (tcgen05 linear layers of FiD-base / Contriever-base, fused epilogues)",
                      "kernel_ms_per_step": g_ms, "kernel_launches_per_step": g_n, "algorithmic_flops_per_step": g_flops,
                      "kernel_share_of_step": g_ms / ms_per_step if ms_per_step else None,
