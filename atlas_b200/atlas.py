@@ -88,6 +88,7 @@ class Atlas(nn.Module):
         self.opt = opt
         self.READER_ALL_TOKENS = list(self.reader_tokenizer.vocab.values())
         self._token_cache, self._token_cache_key = None, None     # retriever-side passage tokens, kept across refreshes
+        self._reader_cache = None                                 # reader-side passage-part tokens (opt.cache_reader_tokens)
 
     # ------------------------------------------------------------------------------------------
     # passage side of the retriever: index build / refresh
@@ -279,7 +280,17 @@ class Atlas(nn.Module):
             retriever_text = [[fmt.format(**p) for p in ps] for ps in passages]
             retriever_tok = _to_cuda(encode_passages(retriever_text, self.retriever_tokenizer,
                                                      min(self.opt.text_maxlength, BERT_MAX_SEQ_LENGTH)))
-        reader_tok = _to_cuda(encode_passages(reader_text, self.reader_tokenizer, self.opt.text_maxlength))
+        reader_tok = None
+        if getattr(self.opt, "cache_reader_tokens", False):
+            # opt-in: passage parts tokenised once per passage id, spliced behind the query part (token_cache.py)
+            rc = self._reader_cache
+            if rc is None or rc.max_length != self.opt.text_maxlength:
+                rc = self._reader_cache = token_cache.ReaderTokenCache(self.reader_tokenizer, self.opt.encoder_format,
+                                                                       self.opt.text_maxlength)
+            if rc.usable:
+                reader_tok = _to_cuda(rc.encode(query, passages))
+        if reader_tok is None:
+            reader_tok = _to_cuda(encode_passages(reader_text, self.reader_tokenizer, self.opt.text_maxlength))
         return reader_tok, retriever_tok
 
     # ------------------------------------------------------------------------------------------

@@ -80,3 +80,36 @@ def test_build_index_refresh_uses_the_record(monkeypatch):
     # another shard (or cache_retriever_tokens = False) goes back to the tokenizer
     model.build_index(index, passages[:40], 32)
     assert calls["tok"] == n_tok + 2
+
+
+@pytest.mark.parametrize("fmt,max_len", [("{query} title: {title} context: {text}", 64),
+                                         ("{query} title: {title} context: {text}", 20),
+                                         ("question: {query} passage: {text}", 48)])
+def test_reader_rows_equal_full_tokenisation(monkeypatch, fmt, max_len):
+    """`Atlas.tokenize_passages` with `cache_reader_tokens`: the spliced rows are tensor-equal to tokenising the
+    concatenated "query + passage" strings (src/atlas.py:261-280), incl. ragged passage counts (EOS-only padding
+    examples), truncation, and repeated retrieval of the same passages."""
+    import atlas_b200.atlas as A
+
+    monkeypatch.setattr(A, "_to_cuda", lambda d: d)
+    reader_tok, retr_tok = atlas_synth.tokenizers()
+    corpus = atlas_synth.make_corpus()
+    query, _ = atlas_synth.make_batch()
+    passages = [corpus[0:4], corpus[2:5], corpus[10:11]]
+    plain = A.Atlas(atlas_synth.make_opt(encoder_format=fmt, text_maxlength=max_len), torch.nn.Linear(1, 1), None,
+                    reader_tok, retr_tok)
+    cached = A.Atlas(atlas_synth.make_opt(encoder_format=fmt, text_maxlength=max_len, cache_reader_tokens=True),
+                     torch.nn.Linear(1, 1), None, reader_tok, retr_tok)
+    for _ in range(2):                                         # second round: every passage part comes from the cache
+        want, _ = plain.tokenize_passages(query, passages)
+        got, _ = cached.tokenize_passages(query, passages)
+        assert torch.equal(got["input_ids"], want["input_ids"]) and torch.equal(got["attention_mask"], want["attention_mask"])
+    rc = cached._reader_cache
+    assert rc.usable and rc.hits >= rc.misses > 0
+
+
+def test_encoder_format_split():
+    assert token_cache.split_encoder_format("{query} title: {title} context: {text}") == ("{query} title: ", "{title} context: {text}")
+    assert token_cache.split_encoder_format("{title} {query} {text}") is None          # query after a passage field
+    assert token_cache.split_encoder_format("{query}:{text}") is None                   # cut not on white space
+    assert token_cache.split_encoder_format("{query}") is None
