@@ -752,6 +752,14 @@ attn_bwd_dkv2_kernel(const Params p) {
 
 }  // namespace attnb
 
+// experimental tcgen05 dQ kernel (attention_bwd_tc.cu), selected with ATLAS_B200_ATTN_BWD_TC=1
+int atlas_b200_attn_bwd_dq_tc(const void* q, int64_t ldq, int32_t q_col0, const void* k, int64_t ldk, int32_t k_col0,
+                              const void* v, int64_t ldv, int32_t v_col0, const void* out, int64_t ldo, const void* dout,
+                              int64_t lddo, void* dq, int64_t lddq, int32_t dq_col0, const float* add_mask,
+                              const float* bias_delta, float* dbias_delta, const float* lse, float* dsum, int32_t B,
+                              int32_t H, int32_t Lq, int32_t Lk, float scale, float causal_value, int32_t is_bf16,
+                              cudaStream_t s);
+
 extern "C" {
 
 int atlas_b200_attention_bwd(const void* q, int64_t ldq, int32_t q_col0, const void* k, int64_t ldk, int32_t k_col0,
@@ -834,12 +842,21 @@ int atlas_b200_attention_bwd(const void* q, int64_t ldq, int32_t q_col0, const v
         attr_set = true;
     }
     abh::prof_begin(s, abh::PROF_ATTENTION_BWD);
+    static const bool use_tc = getenv("ATLAS_B200_ATTN_BWD_TC") != nullptr;   // experimental tcgen05 dQ kernel
+    bool dq_done = false;
+    if (v2 && use_tc && dq_accum == nullptr) {
+        const int rc = atlas_b200_attn_bwd_dq_tc(q, ldq, q_col0, k, ldk, k_col0, v, ldv, v_col0, out, ldo, dout, lddo, dq, lddq,
+                                                 dq_col0, add_mask, bias_delta, dbias_delta, lse, dsum, B, H, Lq, Lk, scale,
+                                                 causal_value, is_bf16, s);
+        if (rc == ATLAS_B200_OK) dq_done = true;
+        else if (rc != ATLAS_B200_EUNSUPPORTED) return rc;
+    }
     if (v2) {
         if (is_bf16) {
-            attn_bwd_dq2_kernel<true><<<static_cast<unsigned>(nq_ctas), THREADS, smem_dq, s>>>(p);
+            if (!dq_done) attn_bwd_dq2_kernel<true><<<static_cast<unsigned>(nq_ctas), THREADS, smem_dq, s>>>(p);
             attn_bwd_dkv2_kernel<true><<<static_cast<unsigned>(nk_ctas), THREADS, smem_dkv, s>>>(p);
         } else {
-            attn_bwd_dq2_kernel<false><<<static_cast<unsigned>(nq_ctas), THREADS, smem_dq, s>>>(p);
+            if (!dq_done) attn_bwd_dq2_kernel<false><<<static_cast<unsigned>(nq_ctas), THREADS, smem_dq, s>>>(p);
             attn_bwd_dkv2_kernel<false><<<static_cast<unsigned>(nk_ctas), THREADS, smem_dkv, s>>>(p);
         }
     } else if (is_bf16) {
