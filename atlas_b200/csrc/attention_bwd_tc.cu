@@ -10,8 +10,9 @@
 //              packed to 16 bits and written to its own 64 columns with tcgen05.st
 //       dQ  += dS_c . K_c      TS MMA: A from tensor memory, B = the K rows as they lie in shared memory (MN-major)
 //   TMEM columns: S0 [0,128) | S1 [128,256) | dP [256,384) | dQ [384,448) | dS [448,512).
-//   dbias[h, j - i] += dS[i, j]: thread = query row, so at a fixed key the 32 lanes of a warp hit 32 consecutive table
-//   entries - conflict-free shared reductions; the table is flushed to global memory once per item.
+//   dbias[h, j - i] += dS[i, j]: each warp stages its 32 x 32 piece of dS in shared memory and sums its 63 diagonals (one
+//   shared fp32 atomic per element was 20 k cycles per chunk: `atomicAdd(float)` on shared memory is a CAS loop); the
+//   per-item table is flushed to global memory once per item.
 // Also writes D_i = sum_d dO[i, d] O[i, d] (`dsum`) for the dK / dV kernel.
 // Roles (352 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator + per-item mask / bias tables,
 // warps 3-10 dS + output (warp w owns TMEM lanes 32 (w % 4) .., column half (w - 3) / 4).
@@ -100,6 +101,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     __shared__ float s_bias[2][2 * MAX_LK];             // (bias by (j - i) + (Lq - 1) [+ causal]) * log2e
     __shared__ __align__(16) float s_mask[2][MAX_LK];   // additive key mask * log2e (-inf beyond Lk)
     __shared__ float s_dbias[2 * MAX_LK];               // per-item dbias by (j - i) + (Lq - 1)
+    __shared__ uint32_t s_stage[8][32 * 16];            // per softmax warp: one 32 x 32 dS piece, packed 16-bit pairs
 
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t lane = threadIdx.x & 31u;
@@ -321,11 +323,36 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                                 if (has_bias) a += bias2[j0 + jj + boffc];
                                 const float t = fmaf(__uint_as_float(rs[jj]), scale2, a);
                                 const float pr = ex2_approx(t - lse2);
-                                ds[e] = pr * (__uint_as_float(rd[jj]) - drow);
-                                if (want_dbias && live && j0 + jj < p.Lk) atomicAdd(&s_dbias[j0 + jj + boff], ds[e]);
+                                ds[e] = pr * (__uint_as_float(rd[jj]) - drow);      // 0 for padding rows / keys (pr = 0)
                             }
                             pk[piece][2 * q4] = ab::pack2_rn<kBF16>(ds[0], ds[1]);
                             pk[piece][2 * q4 + 1] = ab::pack2_rn<kBF16>(ds[2], ds[3]);
+                        }
+                        if (want_dbias) {
+                            // dbias[h, j - i] += dS[i, j] over this warp's 32 x 32 piece (rows = lanes): the packed piece goes
+                            // through a per-warp shared tile rotated by the row (word(l, w) = 16 l + ((w + l) & 15): stores and
+                            // diagonal reads are conflict free), lane d sums diagonals d and d - 32, then two shared
+                            // reductions per lane instead of 32
+                            uint32_t* st = s_stage[warp - 3u];
+#pragma unroll
+                            for (int w = 0; w < 16; ++w) st[lane * 16 + ((w + lane) & 15)] = pk[piece][w];
+                            __syncwarp();
+                            const int i0 = qt * BLOCK_Q + static_cast<int>(lg) * 32;
+                            const int base = j0 - i0 + p.Lq - 1;        // table index of (row i0, column j0)
+#pragma unroll
+                            for (int sgn = 0; sgn < 2; ++sgn) {
+                                const int dl = static_cast<int>(lane) - 32 * sgn;       // diagonal c - r
+                                const int r_lo = dl < 0 ? -dl : 0, r_hi = dl > 0 ? 31 - dl : 31;
+                                float sum = 0.f;
+                                for (int r = r_lo; r <= r_hi; ++r) {
+                                    const int c = r + dl;
+                                    const uint32_t wv = st[r * 16 + (((c >> 1) + r) & 15)];
+                                    sum += to_f32<kBF16>((c & 1) ? (wv >> 16) : wv);
+                                }
+                                const int idx = base + dl;
+                                if (sum != 0.f && idx >= 0 && idx < ntab) atomicAdd(&s_dbias[idx], sum);
+                            }
+                            __syncwarp();
                         }
                     }
                     ab::mbar_wait(&ds_free, (ch & 1) ^ 1u, 72);      // the dQ MMAs of the previous chunk have read dS
