@@ -1,6 +1,11 @@
-// EXPERIMENTAL (round-2 work item, selected only with ATLAS_B200_ATTN_BWD_TC=1; the default backward is the validated
-// warp-MMA path of attention_bwd.cu): the dQ half of the attention backward on tcgen05, structured like the forward
-// kernel of attention.cu.
+// EXPERIMENTAL (selected only with ATLAS_B200_ATTN_BWD_TC=1; the default backward is the warp-MMA path of
+// attention_bwd.cu): the dQ half of the attention backward on tcgen05, structured like the forward kernel of attention.cu
+// (DESIGN.md §8 item 1).  Status at the end of round 1 (1 x B200): CORRECT - all 69 backward / training parity tests pass
+// with it enabled, dQ / dbias within one 16-bit ulp of the warp-MMA kernels (tools/try_tc_bwd.py) - but not yet faster:
+// 0.57 ms vs 0.52 ms for `attn_bwd_dq2_kernel` at 80 x 12 x 384 x 384, i.e. ~17 k cycles per 128 x 128 chunk against
+// ~0.8 k cycles of MMA work: the chunk loop is a serial chain of four hand-offs (dP commit -> TMEM loads -> dS store ->
+// dQ MMA) with only S prefetched.  Next: double-buffer dP and dS so the dS math of chunk c+1 overlaps the dQ MMAs of
+// chunk c, 16 dS warps (4 threads per row), K / V of the next item prefetched, then the dK / dV twin.
 //
 //   CTA = persistent over (segment b, head h) items; K and V of the item resident in shared memory (TMA, K-major, 128B
 //   swizzle); per 128-query tile Q and dO stream in (double buffered).  Per 128-key chunk c:
