@@ -13,6 +13,7 @@ text_maxlength 384, 32 target tokens) — plus the MIPS scan against the HBM roo
   mips          the retrieval kernel alone at its BASELINE batch (256 queries): queries/s, C-ABI e2e with host buffers,
                 and the bank sweep against the measured HBM peak (`mips.roofline`)
   train         supplementary: FiD-base forward + BACKWARD step (the training path's kernels), reader tokens/s
+  refresh       supplementary: index refresh in place (Contriever-base passage embedding into bank rows), passages/s
   cpu_baseline  the reference's CPU path (oracle/: torch-CPU restatements pinned to the reference's goldens) on this
                 box's host cores, bounded sample
 `--impl reference` times that CPU path as the reference arm.  One process per GPU; weak scaling (per-GPU batch and
@@ -359,6 +360,12 @@ def run_ours(args):
     except Exception as e:   # the headline line must survive a failure of this supplementary leg
         train = {"error": repr(e)[:300]}
 
+    # ---------------- index refresh in place (BASELINE configs[2]: re-embed the local shard), one embedder batch -------
+    try:
+        refresh = refresh_leg(args, retriever, index, dev, world, L, barrier_sync, max_over_ranks)
+    except Exception as e:
+        refresh = {"error": repr(e)[:300]}
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -401,6 +408,7 @@ def run_ours(args):
         "clocks": clocks.summary(),
         "mips": mips,
         "train": train,
+        "refresh": refresh,
     }
     if not args.no_cpu_baseline and world == 1:
         leg = cpu_reference_leg(B, args.rows)
@@ -409,6 +417,50 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def refresh_leg(args, retriever, index, dev, world, L, barrier_sync, max_over_ranks, steps=5, warmup=2):
+    """Index refresh (`Atlas.build_index`, src/atlas.py:61-88): one embedder batch of 512 synthetic passages (lengths
+    U[64, 192] tokens, padded to the longest like the reference's tokenizer call) through Contriever-base with fp16
+    weight copies, pooled rows written straight into bank rows (`Contriever.embed_into`).  Passages/s over all ranks (no
+    communication: every rank rewrites its own shard) and the tensor-roofline fraction with SURVEY.md §8(d)'s FLOPs per
+    token (169.9 MFLOP + 36 864 L).  Runs last: it overwrites the first 512 rows of the synthetic bank."""
+    import torch
+
+    nb, lmax = 512, 192
+    g = torch.Generator().manual_seed(4242)
+    lens = torch.randint(64, lmax + 1, (nb,), generator=g)
+    lens[0] = lmax
+    ids = torch.randint(1000, 30000, (nb, lmax), generator=g)
+    mask = (torch.arange(lmax)[None, :] < lens[:, None]).to(torch.int64)
+    ids = (ids * mask).to(dev)
+    mask = mask.to(dev)
+    rows = index._bank[:nb]
+
+    def step():
+        retriever.embed_into(ids, mask, rows, dtype=torch.float16)
+
+    for _ in range(warmup):
+        step()
+    barrier_sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    barrier_sync()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+    assert bool(torch.isfinite(rows.float()).all()), "non-finite embeddings in the refresh leg"
+    flops = nb * lmax * (169.9e6 + 36864.0 * lmax)
+    peak, peak_src = peaks("tensor")
+    achieved = flops / (ms * 1e-3) / 1e12
+    return {"metric": "index refresh passages/sec (Contriever-base fp16 embed of 512-passage batches into bank rows)",
+            "value": nb * world / (ms * 1e-3), "unit": "passages/s", "ms_per_batch": ms, "steps": steps,
+            "passages_per_batch": nb, "padded_tokens": lmax, "tokens_per_s": nb * lmax * world / (ms * 1e-3),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak if peak else None, "peak_source": peak_src,
+                         "algorithmic_flops_per_batch": flops},
+            "shard_refresh_estimate_s": args.rows / (nb / (ms * 1e-3))}
 
 
 def train_leg(args, reader, dev, world, L, barrier_sync, max_over_ranks, steps=3, warmup=2):
