@@ -8,13 +8,19 @@
 // step (train.py -> Atlas.forward -> loss.backward()); the [B, H, Lq, Lk] score / probability tensors the reference
 // keeps alive for autograd are recomputed tile by tile instead (the forward saves only O).
 //
-// Round-1 implementation: warp-level `mma.sync.m16n8k16` tiles (64 queries x 64 keys per CTA step, 4 warps, operands
-// through swizzled shared memory + ldmatrix), two kernels so that no output needs atomics:
-//   attn_bwd_dq_kernel   CTA = (b, h, 64-query block): pass 1 over the keys recomputes the row log-sum-exp (written to
-//                        `lse` for the second kernel, with D to `dsum`), pass 2 accumulates dQ (and dbias).
-//   attn_bwd_dkv_kernel  CTA = (b, h, 64-key block): loops over the query blocks, accumulates dK and dV.
-// Bound: tensor (legacy warp-MMA path; the tcgen05 port with S/dP in tensor memory is the next step).
-// FLOPs per call = 2 * B*H*Lq*Lk*64 * 8 (S twice + dP + dQ in the first kernel, S + dP + dV + dK in the second).
+// Warp-level `mma.sync.m16n8k16` tiles (64 queries x 64 keys per CTA step, 4 warps, operands through XOR-swizzled shared
+// memory + ldmatrix), two kernels so that no output needs atomics:
+//   attn_bwd_dq2_kernel   CTA = (b, h, 64-query block [, key chunk]): reads the row log-sum-exp the forward kernel wrote
+//                         (atlas_b200_attention_ex), writes D_i = sum_d dO O to `dsum`, accumulates dQ over the key blocks
+//                         (cp.async double-buffered K / V tiles); dbias through a staged dS tile + diagonal sums.  A long
+//                         few-query key range (FiD cross-attention) is split over key chunks with fp32 dQ atomics.
+//   attn_bwd_dkv2_kernel  CTA = (b, h, 64-key block): the transposed problem, loops over the query blocks, accumulates dK, dV.
+//   attn_bwd_dq_kernel / attn_bwd_dkv_kernel: first-generation kernels, used when no forward lse is passed (pass 1 over
+//                         the keys recomputes it) and for A/B runs (ATLAS_B200_ATTN_BWD_V1).
+// Bound: tensor (legacy warp-MMA path; profile: profiles/r01_train_step_and_backward_kernels.md).  The tcgen05 version of
+// the dQ kernel (attention_bwd_tc.cu, ATLAS_B200_ATTN_BWD_TC=1) is validated but not yet faster, DESIGN.md §8.
+// FLOPs per call = 2 * B*H*Lq*Lk*64 * 7 with the forward's lse (S + dP + dQ in the first kernel, S + dP + dV + dK in the
+// second), 8 when it is recomputed.
 #include "common.cuh"
 #include "host_common.h"
 

@@ -3,8 +3,9 @@
 (ops.py); torch.autograd only chains them and accumulates into the parameters' `.grad`.
 
 What autograd would derive through the reference's modules is implemented by hand:
-  Linear           y = x W^T (+ b) (+ residual)      dX = dY W (tcgen05 GEMM on W^T), dW = dY^T X (GEMM on transposed
-                                                     operands, fp32 accumulation over the tokens), db = column sums
+  Linear           y = x W^T (+ b) (+ residual)      dX = dY W (tcgen05 GEMM on W^T), dW = dY^T X (tcgen05 GEMM with both
+                                                     operands MN-major: no transposes; split-K, fp32 accumulation over
+                                                     the tokens), db = column sums
   Norm             BertLayerNorm / T5 RMSNorm        src/modeling_bert.py:104-114, src/modeling_t5.py:244-253
   Attention        fused attention, saved O only     src/modeling_bert.py:328-366, src/modeling_t5.py:478-524
   CrossAttention   FiD decoder over n*L keys         src/fid.py:298-349
@@ -12,7 +13,7 @@ What autograd would derive through the reference's modules is implemented by han
   Embedding, BertEmbedSum, MaskedMeanPool, CrossEntropy
 Weights arrive as 16-bit tensors that require grad (the caller derives them from the fp32 / bf16 parameters with
 differentiable casts / concatenations, so autograd routes dW back to the reference-named parameters).
-Dropout is not implemented: the training path requires dropout 0 (callers check).
+Dropout is not implemented: the training path computes without it (callers warn once when dropout > 0 is configured).
 """
 import torch
 
