@@ -766,6 +766,13 @@ int atlas_b200_attn_bwd_dq_tc(const void* q, int64_t ldq, int32_t q_col0, const 
                               int32_t H, int32_t Lq, int32_t Lk, float scale, float causal_value, int32_t is_bf16,
                               cudaStream_t s);
 
+// ... and its dK / dV twin (attention_bwd_tc_dkv.cu), UNTESTED, selected with ATLAS_B200_ATTN_BWD_TC=2
+int atlas_b200_attn_bwd_dkv_tc(const void* q, int64_t ldq, int32_t q_col0, const void* k, int64_t ldk, int32_t k_col0,
+                               const void* v, int64_t ldv, int32_t v_col0, const void* dout, int64_t lddo, void* dk,
+                               int64_t lddk, int32_t dk_col0, void* dv, int64_t lddv, int32_t dv_col0, const float* add_mask,
+                               const float* bias_delta, const float* lse, const float* dsum, int32_t B, int32_t H, int32_t Lq,
+                               int32_t Lk, float scale, float causal_value, int32_t is_bf16, cudaStream_t s);
+
 extern "C" {
 
 int atlas_b200_attention_bwd(const void* q, int64_t ldq, int32_t q_col0, const void* k, int64_t ldk, int32_t k_col0,
@@ -848,22 +855,31 @@ int atlas_b200_attention_bwd(const void* q, int64_t ldq, int32_t q_col0, const v
         attr_set = true;
     }
     abh::prof_begin(s, abh::PROF_ATTENTION_BWD);
-    static const bool use_tc = getenv("ATLAS_B200_ATTN_BWD_TC") != nullptr;   // experimental tcgen05 dQ kernel
-    bool dq_done = false;
+    // experimental tcgen05 kernels: 1 = dQ kernel (validated), 2 = dQ + dK/dV kernels (the latter untested)
+    static const int tc_level = getenv("ATLAS_B200_ATTN_BWD_TC") ? atoi(getenv("ATLAS_B200_ATTN_BWD_TC")) : 0;
+    const bool use_tc = tc_level >= 1;
+    bool dq_done = false, dkv_done = false;
     if (v2 && use_tc && dq_accum == nullptr) {
         const int rc = atlas_b200_attn_bwd_dq_tc(q, ldq, q_col0, k, ldk, k_col0, v, ldv, v_col0, out, ldo, dout, lddo, dq, lddq,
                                                  dq_col0, add_mask, bias_delta, dbias_delta, lse, dsum, B, H, Lq, Lk, scale,
                                                  causal_value, is_bf16, s);
         if (rc == ATLAS_B200_OK) dq_done = true;
         else if (rc != ATLAS_B200_EUNSUPPORTED) return rc;
+        if (dq_done && tc_level >= 2) {
+            const int rc2 = atlas_b200_attn_bwd_dkv_tc(q, ldq, q_col0, k, ldk, k_col0, v, ldv, v_col0, dout, lddo, dk, lddk,
+                                                       dk_col0, dv, lddv, dv_col0, add_mask, bias_delta, lse, dsum, B, H, Lq, Lk,
+                                                       scale, causal_value, is_bf16, s);
+            if (rc2 == ATLAS_B200_OK) dkv_done = true;
+            else if (rc2 != ATLAS_B200_EUNSUPPORTED) return rc2;
+        }
     }
     if (v2) {
         if (is_bf16) {
             if (!dq_done) attn_bwd_dq2_kernel<true><<<static_cast<unsigned>(nq_ctas), THREADS, smem_dq, s>>>(p);
-            attn_bwd_dkv2_kernel<true><<<static_cast<unsigned>(nk_ctas), THREADS, smem_dkv, s>>>(p);
+            if (!dkv_done) attn_bwd_dkv2_kernel<true><<<static_cast<unsigned>(nk_ctas), THREADS, smem_dkv, s>>>(p);
         } else {
             if (!dq_done) attn_bwd_dq2_kernel<false><<<static_cast<unsigned>(nq_ctas), THREADS, smem_dq, s>>>(p);
-            attn_bwd_dkv2_kernel<false><<<static_cast<unsigned>(nk_ctas), THREADS, smem_dkv, s>>>(p);
+            if (!dkv_done) attn_bwd_dkv2_kernel<false><<<static_cast<unsigned>(nk_ctas), THREADS, smem_dkv, s>>>(p);
         }
     } else if (is_bf16) {
         attn_bwd_dq_kernel<true><<<static_cast<unsigned>(nq_ctas), THREADS, smem_dq, s>>>(p);
