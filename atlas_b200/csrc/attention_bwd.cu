@@ -766,7 +766,7 @@ int atlas_b200_attn_bwd_dq_tc(const void* q, int64_t ldq, int32_t q_col0, const 
                               int32_t H, int32_t Lq, int32_t Lk, float scale, float causal_value, int32_t is_bf16,
                               cudaStream_t s);
 
-// ... and its dK / dV twin (attention_bwd_tc_dkv.cu), UNTESTED, selected with ATLAS_B200_ATTN_BWD_TC=2
+// ... and its dK / dV twin (attention_bwd_tc_dkv.cu), selected with ATLAS_B200_ATTN_BWD_TC=2
 int atlas_b200_attn_bwd_dkv_tc(const void* q, int64_t ldq, int32_t q_col0, const void* k, int64_t ldk, int32_t k_col0,
                                const void* v, int64_t ldv, int32_t v_col0, const void* dout, int64_t lddo, void* dk,
                                int64_t lddk, int32_t dk_col0, void* dv, int64_t lddv, int32_t dv_col0, const float* add_mask,
@@ -855,7 +855,7 @@ int atlas_b200_attention_bwd(const void* q, int64_t ldq, int32_t q_col0, const v
         attr_set = true;
     }
     abh::prof_begin(s, abh::PROF_ATTENTION_BWD);
-    // experimental tcgen05 kernels: 1 = dQ kernel (validated), 2 = dQ + dK/dV kernels (the latter untested)
+    // experimental tcgen05 kernels: 1 = dQ kernel, 2 = dQ + dK/dV kernels (see the status notes in attention_bwd_tc*.cu)
     static const int tc_level = getenv("ATLAS_B200_ATTN_BWD_TC") ? atoi(getenv("ATLAS_B200_ATTN_BWD_TC")) : 0;
     const bool use_tc = tc_level >= 1;
     bool dq_done = false, dkv_done = false;

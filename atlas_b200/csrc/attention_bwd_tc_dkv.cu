@@ -1,7 +1,11 @@
-// EXPERIMENTAL AND UNTESTED ON HARDWARE (written at the end of round 1 after the GPU budget was spent; selected only with
-// ATLAS_B200_ATTN_BWD_TC=2; it compiles, nothing else is claimed): the dK / dV half of the attention backward on tcgen05,
-// the transposed twin of attn_bwd_dq_tc_kernel (attention_bwd_tc.cu, which IS validated).  Round 2 starts by running
-// tools/try_tc_bwd.py with ATLAS_B200_ATTN_BWD_TC=2.
+// EXPERIMENTAL (selected only with ATLAS_B200_ATTN_BWD_TC=2; the default backward is the warp-MMA path of attention_bwd.cu):
+// the dK / dV half of the attention backward on tcgen05, the transposed twin of attn_bwd_dq_tc_kernel
+// (attention_bwd_tc.cu).  Status at the end of round 1 (1 x B200, the last seconds of the round's GPU budget): numerically
+// right on the four shapes of tools/try_tc_bwd.py (bf16 / fp16, L = 64 / 200 / 384, with mask and relative-position bias):
+// dK and dV within one 16-bit ulp of the warp-MMA kernels, and ~0.23 ms against 0.33 ms for `attn_bwd_dkv2_kernel` at
+// 80 x 12 x 384 x 384 (total backward with both tcgen05 kernels 0.80 ms vs 0.85 ms).  NOT yet run under the full parity
+// suite (causal, L = 7 / 100 / 130 cases) - round 2 starts with
+// `ATLAS_B200_ATTN_BWD_TC=2 python -m pytest tests/test_backward_gpu.py tests/test_train_gpu.py -m gpu`.
 //
 //   CTA = persistent over (segment b, head h) items; Q and dO of the item resident in shared memory (128-row chunks, TMA,
 //   K-major, 128B swizzle); per 128-key tile K_t and V_t stream in (double buffered).  Per 128-query chunk c:

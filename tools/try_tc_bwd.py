@@ -1,7 +1,7 @@
 """One-shot check of the experimental tcgen05 dQ kernel (ATLAS_B200_ATTN_BWD_TC=1) against the validated warp-MMA path.
     python tools/try_tc_bwd.py ref   -> runs the default path, saves results to /tmp/tc_bwd_ref.pt
     ATLAS_B200_ATTN_BWD_TC=1 python tools/try_tc_bwd.py tc -> runs the tcgen05 dQ kernel, compares, times all shapes
-    ATLAS_B200_ATTN_BWD_TC=2 python tools/try_tc_bwd.py tc -> also the (so far untested) tcgen05 dK / dV kernel.
+    ATLAS_B200_ATTN_BWD_TC=2 python tools/try_tc_bwd.py tc -> also the tcgen05 dK / dV kernel.
 Run under `timeout 60`: a protocol bug in an mbarrier pipeline traps through the watchdog of common.cuh."""
 import os
 import sys
