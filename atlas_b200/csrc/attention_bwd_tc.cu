@@ -4,8 +4,12 @@
 // with it enabled, dQ / dbias within one 16-bit ulp of the warp-MMA kernels (tools/try_tc_bwd.py) - but not yet faster:
 // 0.57 ms vs 0.52 ms for `attn_bwd_dq2_kernel` at 80 x 12 x 384 x 384, i.e. ~17 k cycles per 128 x 128 chunk against
 // ~0.8 k cycles of MMA work: the chunk loop is a serial chain of four hand-offs (dP commit -> TMEM loads -> dS store ->
-// dQ MMA) with only S prefetched.  Next: double-buffer dP and dS so the dS math of chunk c+1 overlaps the dQ MMAs of
-// chunk c, 16 dS warps (4 threads per row), K / V of the next item prefetched, then the dK / dV twin.
+// dQ MMA) with only S prefetched.  Hint from the dK / dV twin (attention_bwd_tc_dkv.cu: same serial structure, TWO TS
+// products and four tcgen05.st per chunk, yet ~0.23 ms): what this kernel has and the twin has not is (a) the per-tile
+// D_i = dO . O dot products read from global memory by every dS thread, (b) the dbias staging + shared reductions, (c) the
+// dsum stores - look there first (D as a per-item table filled by the auxiliary warp, dbias in a separate pass over a
+// stored dS).  Then: double-buffer dP and dS so the dS math of chunk c+1 overlaps the dQ MMAs of chunk c, 16 dS warps
+// (4 threads per row), K / V of the next item prefetched.
 //
 //   CTA = persistent over (segment b, head h) items; K and V of the item resident in shared memory (TMA, K-major, 128B
 //   swizzle); per 128-query tile Q and dO stream in (double buffered).  Per 128-key chunk c:
