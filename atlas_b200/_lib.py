@@ -131,6 +131,14 @@ def lib():
     L.atlas_b200_cross_entropy_fwd.argtypes = [vp, i64, vp, vp, vp, i32, i32, i32, vp]
     L.atlas_b200_cross_entropy_bwd.restype = c.c_int
     L.atlas_b200_cross_entropy_bwd.argtypes = [vp, i64, vp, vp, vp, vp, i64, i32, i32, i32, vp]
+    L.atlas_b200_decode_cross_attention.restype = c.c_int
+    L.atlas_b200_decode_cross_attention.argtypes = [vp, i64, vp, i64, i32, i32, vp, i32, i32, i32, i32, f32, vp, vp, i32, vp]
+    L.atlas_b200_decode_self_attention.restype = c.c_int
+    L.atlas_b200_decode_self_attention.argtypes = [vp, i64, vp, i32, vp, vp, f32, vp, i64, i32, i32, i32, vp]
+    L.atlas_b200_decode_argmax.restype = c.c_int
+    L.atlas_b200_decode_argmax.argtypes = [vp, i64, i32, vp, i64, vp, vp, vp, i32, i32, i32, i32, i32, vp]
+    L.atlas_b200_splice_tokens.restype = c.c_int
+    L.atlas_b200_splice_tokens.argtypes = [vp, vp, i64, i64, vp, vp, vp, i64, i32, i32, i32, i32, i32, vp, vp, vp]
     _lib = L
     return L
 
@@ -173,6 +181,10 @@ EXPORTED_SYMBOLS = [
     "atlas_b200_masked_mean_pool_bwd",
     "atlas_b200_cross_entropy_fwd",
     "atlas_b200_cross_entropy_bwd",
+    "atlas_b200_splice_tokens",
+    "atlas_b200_decode_cross_attention",
+    "atlas_b200_decode_self_attention",
+    "atlas_b200_decode_argmax",
 ]
 
 

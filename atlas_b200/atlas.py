@@ -89,6 +89,7 @@ class Atlas(nn.Module):
         self.READER_ALL_TOKENS = list(self.reader_tokenizer.vocab.values())
         self._token_cache, self._token_cache_key = None, None     # retriever-side passage tokens, kept across refreshes
         self._reader_cache = None                                 # reader-side passage-part tokens (opt.cache_reader_tokens)
+        self._token_bank = None                                   # device-resident reader token bank (set_token_bank)
 
     # ------------------------------------------------------------------------------------------
     # passage side of the retriever: index build / refresh
@@ -178,6 +179,11 @@ class Atlas(nn.Module):
         if self.training:
             self.retriever.train()
         t0 = time.time()
+        cap = getattr(self.opt, "per_gpu_batch_size", None)
+        if cap and getattr(index, "max_queries_per_rank", 0) is None and len(query) <= cap:
+            # every rank runs the same options: the per-GPU batch size bounds the queries of any rank, which lets the
+            # distributed search skip its size exchange (index.py: `max_queries_per_rank`)
+            index.max_queries_per_rank = int(cap)
         if filtering_fun is not None:
             passages, scores = index.search_knn(query_emb, topk * self.opt.filtering_overretrieve_ratio)
             passages, scores = filtering_fun(batch_metadata, passages, scores, topk, training=self.training)
@@ -268,20 +274,18 @@ class Atlas(nn.Module):
         labels, decoder_input_ids = self.reader_tokenize(query, target, target_tokens)
         return query_enc, labels, decoder_input_ids
 
-    def tokenize_passages(self, query, passages):
-        """Reader tokens of "query + passage" ([bsz, n, text_maxlength]) and retriever tokens of the passages
-        ([bsz, n, min(text_maxlength, 512)]) (src/atlas.py:261-280)."""
-        if len(query) == 0:
-            return None, None
-        reader_text = [self.append_query(q, ps) for q, ps in zip(query, passages)]
-        retriever_tok = None
-        if self.retriever_tokenizer:
-            fmt = self.opt.retriever_format
-            retriever_text = [[fmt.format(**p) for p in ps] for ps in passages]
-            retriever_tok = _to_cuda(encode_passages(retriever_text, self.retriever_tokenizer,
-                                                     min(self.opt.text_maxlength, BERT_MAX_SEQ_LENGTH)))
+    def reader_passage_tokens(self, query, passages):
+        """Reader tokens of "query + passage", [bsz, n, text_maxlength] ids + mask on the device (the first half of
+        `tokenize_passages`, src/atlas.py:261-270).  With a device token bank attached (`set_token_bank`) the rows are
+        assembled on the GPU from the passage ids; otherwise the reference's host tokenisation runs."""
         reader_tok = None
-        if getattr(self.opt, "cache_reader_tokens", False):
+        bank = getattr(self, "_token_bank", None)
+        if bank is not None and getattr(self.opt, "device_token_bank", True):
+            n = max(len(ps) for ps in passages)
+            gids = torch.tensor([[int(p["id"]) for p in ps] + [-1] * (n - len(ps)) for ps in passages], dtype=torch.int64)
+            q_ids, q_lens = bank.query_tokens(self.reader_tokenizer, query, _device())
+            reader_tok = bank.splice(gids.to(_device(), non_blocking=True), self.opt.text_maxlength, q_ids, q_lens)
+        if reader_tok is None and getattr(self.opt, "cache_reader_tokens", False):
             # opt-in: passage parts tokenised once per passage id, spliced behind the query part (token_cache.py)
             rc = self._reader_cache
             if rc is None or rc.max_length != self.opt.text_maxlength:
@@ -290,8 +294,28 @@ class Atlas(nn.Module):
             if rc.usable:
                 reader_tok = _to_cuda(rc.encode(query, passages))
         if reader_tok is None:
+            reader_text = [self.append_query(q, ps) for q, ps in zip(query, passages)]
             reader_tok = _to_cuda(encode_passages(reader_text, self.reader_tokenizer, self.opt.text_maxlength))
-        return reader_tok, retriever_tok
+        return reader_tok
+
+    def tokenize_passages(self, query, passages):
+        """Reader tokens of "query + passage" ([bsz, n, text_maxlength]) and retriever tokens of the passages
+        ([bsz, n, min(text_maxlength, 512)]) (src/atlas.py:261-280)."""
+        if len(query) == 0:
+            return None, None
+        retriever_tok = None
+        if self.retriever_tokenizer:
+            fmt = self.opt.retriever_format
+            retriever_text = [[fmt.format(**p) for p in ps] for ps in passages]
+            retriever_tok = _to_cuda(encode_passages(retriever_text, self.retriever_tokenizer,
+                                                     min(self.opt.text_maxlength, BERT_MAX_SEQ_LENGTH)))
+        return self.reader_passage_tokens(query, passages), retriever_tok
+
+    def set_token_bank(self, bank):
+        """Attach a `token_bank.DeviceTokenBank` (reader-side passage tokens on the GPU, keyed by the passages' integer
+        "id"): `tokenize_passages` then assembles the reader input on the device instead of tokenising
+        bsz x n_context strings per step (src/atlas.py:261-280).  None detaches it."""
+        self._token_bank = bank
 
     # ------------------------------------------------------------------------------------------
     # gold scores for retriever distillation

@@ -1,20 +1,23 @@
 """In-tree build of `lib/libatlas_b200.so` with nvcc for sm_100a (no JIT cache: the built .so
-travels to the GPU box with the repo snapshot)."""
+travels to the GPU box with the repo snapshot).  Every .cu under csrc/ is compiled to an object file in
+parallel (only the stale ones), then linked into one shared library."""
 import glob
 import os
 import shutil
 import subprocess
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
+OBJ_DIR = os.path.join(LIB_DIR, "obj")
 LIB = os.path.join(LIB_DIR, "libatlas_b200.so")
 
 NVCC_FLAGS = [
-    "-shared", "-Xcompiler", "-fPIC", "-std=c++17", "-O3", "-lineinfo",
+    "-Xcompiler", "-fPIC", "-std=c++17", "-O3", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-cudart", "static",
 ]
+LINK_FLAGS = ["-shared", "-Xcompiler", "-fPIC", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a"]
 
 
 def _nvcc():
@@ -25,26 +28,48 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
-def _stale():
-    if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "*.cuh"))
+def _headers():
+    deps = glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "*.cuh"))
     deps.append(os.path.join(os.path.dirname(HERE), "include", "atlas_b200.h"))
+    return deps
+
+
+def _obj(src):
+    return os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
     return any(os.path.getmtime(d) > t for d in deps)
 
 
 def build_library(force=False, verbose=False):
     """Compile every .cu under csrc/ into one shared library.  Returns the library path."""
-    if not force and not _stale():
-        return LIB
-    os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    hdrs = _headers()
+    todo = [s for s in sources() if force or _stale(_obj(s), [s] + hdrs)]
+    logs = []
+
+    def compile_one(src):
+        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", _obj(src), src]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+        return res.stderr
+
+    if todo:
+        with ThreadPoolExecutor(max_workers=min(len(todo), os.cpu_count() or 4)) as pool:
+            logs = list(pool.map(compile_one, todo))
+    objs = [_obj(s) for s in sources()]
+    if todo or _stale(LIB, objs):
+        cmd = [_nvcc()] + LINK_FLAGS + ["-o", LIB] + objs
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("link failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
     if verbose:
-        print(res.stderr)
+        print("\n".join(logs))
     return LIB
 
 

@@ -200,6 +200,46 @@ masked_mean_pool_kernel(const uint16_t* __restrict__ x, const int64_t* __restric
     out[b * ld_out + col] = static_cast<uint16_t>(rnd<kBF16>(s / static_cast<float>(cnt)));
 }
 
+
+// Reader-input assembly from the device-resident passage token bank (replaces the per-step host work of
+// Atlas.tokenize_passages, src/atlas.py:261-280: bsz x n_context string formats + tokenizer calls):
+//   row (b, j) = (query_ids[b, :qlen[b]] ++ bank_ids[rows[b, j], :bank_lens[...]])[: L - 1] ++ [eos], padded with `pad`
+// and the attention mask of the same shape.  rows[b, j] < 0 is the "" padding passage: EOS only (src/atlas.py:26-39).
+// One block per output row; 4-byte reads, 8-byte id + 1-byte mask writes (pure HBM byte work: L * 13 B per row).
+__global__ void splice_tokens_kernel(const int32_t* __restrict__ bank_ids, const int32_t* __restrict__ bank_lens,
+                                     int64_t bank_ld, int64_t bank_rows, const int64_t* __restrict__ rows,
+                                     const int64_t* __restrict__ query_ids, const int32_t* __restrict__ query_lens,
+                                     int64_t ldq, int n_ctx, int L, int eos, int pad, int64_t* __restrict__ out_ids,
+                                     uint8_t* __restrict__ out_mask) {
+    const int r = blockIdx.x;                 // output row = b * n_ctx + j
+    const int b = r / n_ctx;
+    int64_t row = rows[r];
+    if (row >= bank_rows) row = -1;           // unknown passage id: treated like the padding passage
+    int qlen = 0, plen = 0;
+    if (row >= 0) {
+        qlen = query_lens ? query_lens[b] : 0;
+        plen = bank_lens[row];
+    }
+    const int body = min(qlen + plen, L - 1);  // tokens before the closing EOS
+    const int32_t* prow = bank_ids + (row >= 0 ? row : 0) * bank_ld;
+    const int64_t* qrow = query_ids ? query_ids + static_cast<int64_t>(b) * ldq : nullptr;
+    int64_t* o = out_ids + static_cast<int64_t>(r) * L;
+    uint8_t* m = out_mask + static_cast<int64_t>(r) * L;
+    for (int t = threadIdx.x; t < L; t += blockDim.x) {
+        int64_t v = pad;
+        uint8_t on = 0;
+        if (t < body) {
+            v = t < qlen ? qrow[t] : static_cast<int64_t>(prow[t - qlen]);
+            on = 1;
+        } else if (t == body) {
+            v = eos;
+            on = 1;
+        }
+        o[t] = v;
+        m[t] = on;
+    }
+}
+
 }  // namespace ew
 
 extern "C" {
@@ -263,6 +303,21 @@ int atlas_b200_masked_mean_pool(const void* x, const int64_t* mask, void* out, i
     else
         ew::masked_mean_pool_kernel<false><<<grid, 256, 0, s>>>(static_cast<const uint16_t*>(x), mask,
                                                                 static_cast<uint16_t*>(out), ld_out, L, H);
+    abh::count_launch();
+    AB_CUDA_CHECK(cudaGetLastError());
+    return ATLAS_B200_OK;
+}
+
+int atlas_b200_splice_tokens(const int32_t* bank_ids, const int32_t* bank_lens, int64_t bank_ld, int64_t bank_rows,
+                             const int64_t* rows, const int64_t* query_ids, const int32_t* query_lens, int64_t ldq,
+                             int32_t batch, int32_t n_ctx, int32_t L, int32_t eos_id, int32_t pad_id, int64_t* out_ids,
+                             uint8_t* out_mask, void* stream) {
+    AB_REQUIRE(batch >= 0 && n_ctx > 0 && L > 1 && bank_ld > 0 && bank_rows >= 0, "splice_tokens: bad shape");
+    AB_REQUIRE((query_ids == nullptr) == (query_lens == nullptr), "splice_tokens: query ids and lengths come together");
+    if (batch == 0) return ATLAS_B200_OK;
+    ew::splice_tokens_kernel<<<batch * n_ctx, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        bank_ids, bank_lens, bank_ld, bank_rows, rows, query_ids, query_lens, ldq, n_ctx, L, eos_id, pad_id, out_ids,
+        out_mask);
     abh::count_launch();
     AB_CUDA_CHECK(cudaGetLastError());
     return ATLAS_B200_OK;

@@ -225,12 +225,22 @@ class FiD(nn.Module):
     def create_crossattention_storage(self):
         self._xattn = []
 
-    def _record_xattn(self, q, kv, B, H, T, Lk, lse, mask):
+    def _record_xattn(self, q, kv, B, H, T, Lk, lse, mask, layer=None):
+        """Keep ONE record per decoder layer, overwritten by every forward (the reference keeps one buffer per attention
+        module, src/fid.py:333-343): constant memory however many forwards run between two `reset_score_storage()` calls."""
         if getattr(self, "_capture", False):
-            if not hasattr(self, "_xattn"):
+            n = self.config.num_decoder_layers
+            if not isinstance(getattr(self, "_xattn", None), list):
                 self._xattn = []
-            self._xattn.append(ops.cross_attention_stats(q.detach(), 0, kv.detach(), 0, H * 64, B, H, T, Lk, lse,
-                                                         add_mask=mask, scale=1.0))
+            rec = ops.cross_attention_stats(q.detach(), 0, kv.detach(), 0, H * 64, B, H, T, Lk, lse, add_mask=mask, scale=1.0)
+            if layer is None:                       # sequential recording: a new forward starts after n records
+                if len(self._xattn) >= n:
+                    self._xattn = []
+                self._xattn.append(rec)
+            else:
+                if len(self._xattn) != n:
+                    self._xattn = [None] * n
+                self._xattn[layer] = rec
 
     @torch.no_grad()
     def get_crossattention_scores(self, n_passages, mask, labels, ids, mode="all", mask_query=None):
@@ -238,7 +248,7 @@ class FiD(nn.Module):
         (src/fid.py:136-164) -> dict of [B, n_passages] tensors named {scores,probs,norms}{top5,top10,top20,nosep,first,
         sum,avg,woquery}."""
         rec = getattr(self, "_xattn", None)
-        if not rec or len(rec) < self.config.num_decoder_layers:
+        if not rec or len(rec) < self.config.num_decoder_layers or any(r is None for r in rec):
             raise AtlasB200Error("get_crossattention_scores: no recorded forward (call overwrite_forward_crossattention() "
                                  "and run a forward first)")
         rec = rec[-self.config.num_decoder_layers:]
@@ -391,15 +401,16 @@ class FiD(nn.Module):
 
     # ---- decoder ---------------------------------------------------------------------------
     @torch.no_grad()
-    def cross_kv(self, enc):
+    def cross_kv(self, enc, out=None):
         """K/V projections of the encoder output for every decoder layer ([B*n*L, 2*H*64] each), computed once
-        per forward / per generation (the reference recomputes them every decoding step without use_cache)."""
+        per forward / per generation (the reference recomputes them every decoding step without use_cache).
+        `out`: list of pre-allocated buffers (the static cross K|V cache of the decode graph)."""
         c = self.config
         W, G, dt = self._weights()
         flat = enc.reshape(-1, c.d_model)
         if flat.dtype != dt:
             flat = flat.to(dt)
-        return [ops.linear(flat, G[f"decoder.block.{i}.layer.1.EncDecAttention.kv"])
+        return [ops.linear(flat, G[f"decoder.block.{i}.layer.1.EncDecAttention.kv"], out=None if out is None else out[i])
                 for i in range(c.num_decoder_layers)]
 
     @torch.no_grad()
@@ -439,7 +450,7 @@ class FiD(nn.Module):
             if capture:
                 ctx, lse = ops.cross_attention_split(q, 0, cross_kv[i], 0, H * 64, B, H, T, Lk, add_mask=cross_mask,
                                                      scale=1.0, split=split, return_lse=True)
-                self._record_xattn(q, cross_kv[i], B, H, T, Lk, lse, cross_mask)
+                self._record_xattn(q, cross_kv[i], B, H, T, Lk, lse, cross_mask, layer=i)
             else:
                 ctx = ops.cross_attention_split(q, 0, cross_kv[i], 0, H * 64, B, H, T, Lk, add_mask=cross_mask,
                                                 scale=1.0, split=split)
@@ -544,7 +555,7 @@ class FiD(nn.Module):
             q = g.linear(n, W[p + "EncDecAttention.q.weight"])
             kv = g.linear(flat, G[p + "EncDecAttention.kv"])
             ctx, lse = g.cross_attention(q, kv, B, H, T, Lk, add_mask=cross_mask, scale=1.0, split=split, return_lse=True)
-            self._record_xattn(q, kv, B, H, T, Lk, lse, cross_mask)
+            self._record_xattn(q, kv, B, H, T, Lk, lse, cross_mask, layer=i)
             h = g.linear(ctx, W[p + "EncDecAttention.o.weight"], None, residual=h)
             p = f"decoder.block.{i}.layer.2."
             n = g.layernorm(h, W[p + "layer_norm.weight"], None, eps, kind=1)
@@ -583,7 +594,8 @@ class FiD(nn.Module):
             return fn(*inputs)
         self._weights()                                      # make sure the 16-bit weight copies exist / are current
         dt = self._dtype()
-        key = (tag, dt, self.fuse_norm, self._half.sets[dt]["key"],
+        # the 16-bit weight buffers are refreshed in place (HalfCache): the graph key only holds their allocation generation
+        key = (tag, dt, self.fuse_norm, self._half.sets[dt]["gen"],
                tuple((tuple(t.shape), t.dtype, t.device) for t in inputs))
         runner = self._graphs.get(key)
         if runner is None:
@@ -627,14 +639,158 @@ class FiD(nn.Module):
             logits, enc = logits.to(pd), enc.to(pd)
         return FiDOutput(loss, logits, enc)
 
+    # ---- greedy generation: KV-cached single-token decode (csrc/decode.cu) ----------------------------------------
+    class _DecodeState:
+        """Static buffers of one (batch, keys, max_length, dtype) generation shape: per-layer self K|V caches, the cross
+        K|V cache, the token / sequence / done / step tensors the step reads and writes on the device, and (optionally)
+        the captured CUDA graph of ONE decode step that every step replays (the step index lives in device memory)."""
+
+        def __init__(self, model, B, Lk, Tmax, dt, dev):
+            c = model.config
+            H, d = c.num_heads, c.d_model
+            nl = c.num_decoder_layers
+            self.B, self.Lk, self.Tmax = B, Lk, Tmax
+            self.self_kv = [torch.zeros((B, Tmax, 2 * H * 64), dtype=dt, device=dev) for _ in range(nl)]
+            self.cross_kv = [torch.empty((B * Lk, 2 * H * 64), dtype=dt, device=dev) for _ in range(nl)]
+            self.cross_mask = torch.zeros((B, Lk), dtype=torch.float32, device=dev)
+            self.tok_in = torch.zeros(B, dtype=torch.int64, device=dev)
+            self.seq = torch.zeros((B, Tmax), dtype=torch.int64, device=dev)
+            self.done = torch.zeros(B, dtype=torch.uint8, device=dev)
+            self.t_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+            self.logits = None
+            self.graph = None
+
+    @torch.no_grad()
+    def _decode_step_logits(self, st):
+        """Decoder stack for ONE new token per sequence (`st.tok_in`, position `st.t_dev`) -> logits [B, vocab].
+        Self-attention appends to / reads the per-layer K|V cache; cross-attention streams the cached cross K|V once."""
+        c = self.config
+        W, G, dt = self._weights()
+        H = c.num_heads
+        eps = c.layer_norm_epsilon
+        B, Lk = st.B, st.Lk
+        h = W["shared.weight"][st.tok_in]                                          # [B, d]
+        for i in range(c.num_decoder_layers):
+            p = f"decoder.block.{i}.layer.0."
+            n = ops.layernorm(h, W[p + "layer_norm.weight"], None, eps, kind=1)
+            qkv = ops.linear(n, G[p + "SelfAttention.qkv"])
+            ctx = ops.decode_self_attention(qkv, st.self_kv[i], st.t_dev, H, bias_delta=st.bias, scale=1.0)
+            h = ops.linear(ctx, W[p + "SelfAttention.o.weight"], None, residual=h, epilogue=ops.EPI_RESIDUAL)
+            p = f"decoder.block.{i}.layer.1."
+            n = ops.layernorm(h, W[p + "layer_norm.weight"], None, eps, kind=1)
+            q = ops.linear(n, W[p + "EncDecAttention.q.weight"])
+            ctx = ops.decode_cross_attention(q, st.cross_kv[i], B, H, Lk, add_mask=st.cross_mask, scale=1.0,
+                                             chunk=st.chunk)
+            h = ops.linear(ctx, W[p + "EncDecAttention.o.weight"], None, residual=h, epilogue=ops.EPI_RESIDUAL)
+            h = self._ff(W, G, f"decoder.block.{i}.layer.2.", h, eps)
+        h = ops.layernorm(h, W["decoder.final_layer_norm.weight"], None, eps, kind=1)
+        if getattr(c, "tie_word_embeddings", False):
+            h = (h.float() * (c.d_model ** -0.5)).to(dt)
+        return ops.linear(h, W["lm_head.weight"])
+
+    def _decode_state(self, B, Lk, Tmax, dt, dev):
+        key = (B, Lk, Tmax, dt, dev)
+        states = self.__dict__.setdefault("_decode_states", {})
+        st = states.get(key)
+        if st is None:
+            if len(states) >= 2:
+                states.pop(next(iter(states)))
+            st = FiD._DecodeState(self, B, Lk, Tmax, dt, dev)
+            # keys per block of the cross-attention sweep: ~4 blocks per SM keep every SM streaming
+            st.chunk = 256 if Lk >= 2048 else 64
+            states[key] = st
+        return st
+
     @torch.no_grad()
     def generate(self, input_ids=None, attention_mask=None, max_length=32, min_length=1, num_beams=1,
                  num_return_sequences=1, length_penalty=1.0, forced_bos_token_id=None, prefix_allowed_tokens_fn=None,
-                 **unused):
-        """Greedy decoding (what `Atlas.generate` requests with num_beams=1, src/atlas.py:592-619): the encoder
-        and the cross-attention K/V projections run once, every step re-runs the (tiny) decoder prefix."""
+                 use_cache=True, **unused):
+        """Greedy decoding (what `Atlas.generate` requests with num_beams=1, src/atlas.py:592-619; transformers 4.18
+        `greedy_search` with `use_cache`): the encoder and the cross-attention K|V projections run once; every step
+        decodes ONE token per sequence against the per-layer self K|V cache and the cached cross K|V (csrc/decode.cu),
+        picks the next token on the device and - without a `prefix_allowed_tokens_fn` - is replayed from a single CUDA
+        graph with no host synchronisation except an all-done poll every 8 steps.  use_cache=False runs the
+        first-generation path (the decoder prefix re-run every step), kept as the parity reference of the tests."""
         if num_beams != 1 or num_return_sequences != 1:
             raise AtlasB200Error("only greedy generation (num_beams=1) is implemented")
+        if not use_cache:
+            return self._generate_prefix_rerun(input_ids, attention_mask, max_length, min_length, prefix_allowed_tokens_fn)
+        c = self.config
+        enc = self.encode(input_ids, attention_mask)
+        B, Lk = enc.shape[0], enc.shape[1]
+        W, G, dt = self._weights()
+        st = self._decode_state(B, Lk, int(max_length), dt, enc.device)
+        self.cross_kv(enc, out=st.cross_kv)
+        neg = -1e4 if dt == torch.float16 else -1e9                                 # invert_attention_mask (4.18)
+        st.cross_mask.copy_((1.0 - attention_mask.reshape(B, Lk).to(torch.float32)) * neg)
+        wkey = (self._half.sets[dt]["gen"], self._half.sets[dt]["key"])
+        if getattr(st, "wkey", None) != wkey:                                       # weights changed: the bias table is stale
+            fresh = bias_by_delta(W["decoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight"], st.Tmax,
+                                  st.Tmax, False, c.relative_attention_num_buckets)
+            if getattr(st, "bias", None) is None:
+                st.bias = fresh
+            else:
+                st.bias.copy_(fresh)            # in place: the captured step graph reads this buffer
+            if getattr(st, "wgen", None) != wkey[0]:                                # buffers re-allocated: re-capture
+                st.graph, st.wgen = None, wkey[0]
+            st.wkey = wkey
+        st.seq.fill_(c.pad_token_id)
+        st.seq[:, 0] = c.decoder_start_token_id
+        st.tok_in.fill_(c.decoder_start_token_id)
+        st.done.zero_()
+        st.t_dev.zero_()
+        n_steps = int(max_length) - 1
+
+        def step():
+            logits = self._decode_step_logits(st)
+            ops.decode_argmax(logits, st.seq, st.tok_in, st.done, st.t_dev, c.eos_token_id, c.pad_token_id, int(min_length))
+
+        use_graph = self.cuda_graphs and prefix_allowed_tokens_fn is None and n_steps > 0
+        if use_graph and (st.graph is None or getattr(st, "min_length", None) != int(min_length)):
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                    # eager warm-up step on scratch state (then reset below)
+                step()
+            torch.cuda.current_stream().wait_stream(side)
+            st.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(st.graph):
+                step()
+            st.min_length = int(min_length)
+            st.seq.fill_(c.pad_token_id)
+            st.seq[:, 0] = c.decoder_start_token_id
+            st.tok_in.fill_(c.decoder_start_token_id)
+            st.done.zero_()
+            st.t_dev.zero_()
+        ran = 0
+        for s_i in range(n_steps):
+            if use_graph:
+                st.graph.replay()
+            elif prefix_allowed_tokens_fn is None:
+                step()
+            else:
+                logits = self._decode_step_logits(st).float()
+                seq_now = st.seq[:, : s_i + 1]
+                allowed = torch.full_like(logits, -float("inf"))
+                for b in range(B):
+                    allowed[b, prefix_allowed_tokens_fn(b, seq_now[b])] = 0
+                logits = (logits + allowed).to(dt)
+                ops.decode_argmax(logits, st.seq, st.tok_in, st.done, st.t_dev, c.eos_token_id, c.pad_token_id,
+                                  int(min_length))
+            ran = s_i + 1
+            if (s_i % 8 == 7 or s_i == n_steps - 1) and bool(st.done.all()):      # the only host synchronisation
+                break
+        seq = st.seq[:, : ran + 1].clone()
+        # transformers stops right after the step in which the last sequence finished: drop all-pad trailing columns
+        is_eos = seq[:, 1:] == c.eos_token_id
+        if bool(is_eos.any(dim=1).all()):
+            first = is_eos.float().argmax(dim=1) + 1
+            seq = seq[:, : int(first.max()) + 1]
+        return seq
+
+    @torch.no_grad()
+    def _generate_prefix_rerun(self, input_ids, attention_mask, max_length, min_length, prefix_allowed_tokens_fn):
+        """First-generation greedy loop: the encoder and the cross-attention K/V projections run once, every step
+        re-runs the whole decoder prefix (no self-attention cache).  Parity reference for the cached path."""
         c = self.config
         enc = self.encode(input_ids, attention_mask)
         B = enc.shape[0]

@@ -41,6 +41,10 @@ class DistributedIndex(object):
         # global id of local row l is _id_base + _id_stride * l
         self._id_base, self._id_stride = 0, 1
         self._offsets = None  # contiguous layout (after load_index): first global id of every rank
+        # Upper bound of the queries ANY rank passes to one search (e.g. --per_gpu_batch_size, identical on all ranks).
+        # When set, a distributed search pads every rank's block to this many rows: no size exchange, no host
+        # synchronisation in front of the query all-gather (src/index.py:127-129 does a var-size gather + a size gather).
+        self.max_queries_per_rank = None
 
     # ------------------------------------------------------------------ bank / reference view
     @property
@@ -144,10 +148,6 @@ class DistributedIndex(object):
         fused.  Returns (scores [nq, k] fp16 desc, indices [nq, k] int64 LOCAL row numbers)."""
         return ops.search_shard(self._bank, allqueries, topk, 0, 1, self._workspace)
 
-    def _local_search(self, allqueries, topk):
-        """Local shard scan returning GLOBAL ids."""
-        return ops.search_shard(self._bank, allqueries, topk, self._id_base, self._id_stride, self._workspace)
-
     def _merge(self, blob_all, ids_off, world, nq_total, topk, q_begin, nq_out):
         return ops.topk_merge_blob(blob_all, ids_off, world, nq_total, topk, q_begin, nq_out, torch.float16)
 
@@ -157,10 +157,23 @@ class DistributedIndex(object):
         r = int(np.searchsorted(self._offsets, gid, side="right")) - 1
         return r, gid - int(self._offsets[r])
 
+    def _local_search(self, allqueries, topk, exhaustive=False):
+        """Local shard scan returning GLOBAL ids + the device status word (no host synchronisation)."""
+        return ops.mips_topk(self._bank, allqueries, topk, self._id_base, self._id_stride, self._workspace,
+                             exhaustive=exhaustive)
+
     @torch.no_grad()
-    def search_device(self, queries, topk):
-        """Device half of `search_knn`: returns (scores [nq_local, k] fp16, global ids [nq_local, k] int64)
-        as CUDA tensors.  Collective (2 all-gathers + one tiny size exchange when world_size > 1)."""
+    def search_device(self, queries, topk, return_status=False, exhaustive=False):
+        """Device half of `search_knn`: (scores [nq_local, k] fp16, global ids [nq_local, k] int64) as CUDA tensors.
+
+        Collective when world_size > 1: ONE all-gather of the query rows + ONE all-gather of the packed per-shard
+        (scores | ids | status) blobs (the reference: 3 + 4*W collectives with pickled passages, src/index.py:127-143).
+        With `max_queries_per_rank` set there is no host synchronisation at all; otherwise one scalar size exchange.
+
+        return_status=False: the overflow flag of the fast path is read here (one host sync) and the exhaustive path is
+        re-run if needed, so the result is final.  return_status=True: nothing synchronises; the third return value is a
+        device int64 scalar (max over shards) that the caller checks at its own synchronisation point
+        (`search_knn` folds it into the D2H copy it needs anyway) and, if non-zero, calls again with exhaustive=True."""
         if self._bank is None:
             raise AtlasB200Error("search_knn before init_embeddings/load_index")
         if topk > MAX_TOPK:
@@ -171,17 +184,35 @@ class DistributedIndex(object):
         world = dist_utils.get_world_size()
         rank = dist_utils.get_rank()
         queries = queries.reshape(-1, EMBEDDINGS_DIM)
+        nq_local = queries.shape[0]
         if world == 1:
-            return self._local_search(queries, topk)
-        sizes = dist_utils.get_varsize(queries)                                # tiny all_gather (+ sync)
-        q16 = queries.to(self._bank.device).to(torch.float16)                  # `.half()`, src/index.py:117
-        allq = dist_utils.varsize_all_gather(q16, sizes)                       # all_gather #1
-        nq_total = int(sum(sizes))
-        s_loc, i_loc = self._local_search(allq, topk)
-        blob, ids_off = ops.pack_results(s_loc, i_loc)
-        blob_all = dist_utils.all_gather_fixed(blob)                           # all_gather #2
-        q_begin = int(sum(sizes[:rank]))
-        return self._merge(blob_all, ids_off, world, nq_total, topk, q_begin, queries.shape[0])
+            s, i, status = self._local_search(queries, topk, exhaustive)
+            status = status.to(torch.int64).reshape(())
+        else:
+            q16 = queries.to(self._bank.device).to(torch.float16)                  # `.half()`, src/index.py:117
+            cap = self.max_queries_per_rank
+            if cap:
+                if nq_local > cap:
+                    raise AtlasB200Error(f"search_knn: {nq_local} queries on this rank but max_queries_per_rank={cap} "
+                                         "(set it to the per-GPU batch size, identical on every rank, or to None)")
+                if nq_local < cap:
+                    q16 = torch.cat([q16, q16.new_zeros((cap - nq_local, EMBEDDINGS_DIM))], dim=0)
+                allq = dist_utils.all_gather_fixed(q16).reshape(world * cap, EMBEDDINGS_DIM)     # all_gather #1, no sync
+                nq_total, q_begin = world * cap, rank * cap
+            else:
+                sizes = dist_utils.get_varsize(queries)                            # tiny all_gather (+ host sync)
+                allq = dist_utils.varsize_all_gather(q16, sizes)                   # all_gather #1
+                nq_total, q_begin = int(sum(sizes)), int(sum(sizes[:rank]))
+            s_loc, i_loc, st_loc = self._local_search(allq, topk, exhaustive)
+            blob, ids_off, st_off = ops.pack_results(s_loc, i_loc, st_loc.to(torch.int64))
+            blob_all = dist_utils.all_gather_fixed(blob)                           # all_gather #2
+            s, i = self._merge(blob_all, ids_off, world, nq_total, topk, q_begin, nq_local)
+            status = blob_all[:, st_off:].contiguous().view(torch.int64).max()
+        if return_status:
+            return s, i, status
+        if not exhaustive and int(status.item()) != 0:      # identical on every rank (max over shards): collective retry
+            return self.search_device(queries, topk, exhaustive=True)
+        return s, i
 
     @torch.no_grad()
     def search_knn(self, queries, topk):
@@ -191,9 +222,14 @@ class DistributedIndex(object):
         Returns (docs: List[nq][k] passage dicts, scores: List[nq][k] floats, descending)."""
         world = dist_utils.get_world_size()
         nq_local = queries.reshape(-1, EMBEDDINGS_DIM).shape[0]
-        scores, ids = self.search_device(queries, topk)
+        scores, ids, status = self.search_device(queries, topk, return_status=True)
+        # the overflow flag (max over shards, identical on every rank) is read at the host sync the results need anyway
         scores_host = scores.float().cpu()
-        ids_host = ids.cpu().tolist()
+        ids_host = ids.cpu()
+        if int(status.item()) != 0:                         # massive ties (e.g. an all-zero bank): exact chunked path
+            scores, ids, _ = self.search_device(queries, topk, return_status=True, exhaustive=True)
+            scores_host, ids_host = scores.float().cpu(), ids.cpu()
+        ids_host = ids_host.tolist()
         flat = [self._owner_local(g, world) for row in ids_host for g in row]
         docs_flat = self._get_store().lookup(flat)
         docs = [docs_flat[r * topk:(r + 1) * topk] for r in range(nq_local)]

@@ -125,15 +125,22 @@ def search_host(bank, queries_host, k, id_base=0, id_stride=1, workspace=None):
     return out_s, out_i
 
 
-def pack_results(scores, ids):
-    """One contiguous byte blob [scores (16-bit) | pad to 8 | ids (int64)] so that a SINGLE all-gather
-    ships both (replaces the 2*W gathers of src/index.py:138-141).  Returns (blob uint8, ids offset)."""
+def pack_results(scores, ids, status=None):
+    """One contiguous byte blob [scores (16-bit) | pad to 8 | ids (int64) | status (int64)] so that a SINGLE all-gather
+    ships both lists AND the shard's overflow flag (replaces the 2*W gathers of src/index.py:138-141; the flag lets every
+    rank learn, at the host sync it has anyway, whether any shard must be re-run exhaustively).
+    Returns (blob uint8, ids offset, status offset)."""
     nbytes_s = scores.numel() * 2
     ids_off = (nbytes_s + 7) // 8 * 8
-    blob = torch.empty(ids_off + ids.numel() * 8, dtype=torch.uint8, device=scores.device)
+    st_off = ids_off + ids.numel() * 8
+    blob = torch.empty(st_off + 8, dtype=torch.uint8, device=scores.device)
     blob[:nbytes_s].view(scores.dtype).copy_(scores.reshape(-1))
-    blob[ids_off:].view(torch.int64).copy_(ids.reshape(-1))
-    return blob, ids_off
+    blob[ids_off:st_off].view(torch.int64).copy_(ids.reshape(-1))
+    if status is None:
+        blob[st_off:].zero_()
+    else:
+        blob[st_off:].view(torch.int64).copy_(status.reshape(1))
+    return blob, ids_off, st_off
 
 
 def topk_merge_blob(blob_all, ids_off, world, nq_total, k, q_begin, nq_out, dtype):
@@ -490,3 +497,45 @@ def cross_attention_stats(q, q_col0, kv, k_col0, v_col0, B, H, T, Lk, lse, add_m
                                                  _ptr(am) if am is not None else None, _ptr(l2), _ptr(out[0]), _ptr(out[1]),
                                                  _ptr(out[2]), B, H, T, Lk, float(scale), _bf(q), current_stream_ptr()))
     return out[0], out[1], out[2]
+
+
+# ---------------------------------------------------------------------------------------------
+# single-token decode (csrc/decode.cu): KV-cached greedy generation
+# ---------------------------------------------------------------------------------------------
+def decode_self_attention(qkv, cache, t_dev, H, bias_delta=None, scale=1.0, out=None):
+    """qkv [B, 3*H*64] of the new token; cache [B, Tmax, 2*H*64] (k | v) updated in place at row t_dev[0]; -> ctx [B, H*64]."""
+    require_cuda(qkv, "qkv")
+    B, Tmax = cache.shape[0], cache.shape[1]
+    if out is None:
+        out = torch.empty((B, H * 64), dtype=qkv.dtype, device=qkv.device)
+    bd = bias_delta.float().contiguous() if bias_delta is not None else None
+    check(lib().atlas_b200_decode_self_attention(_ptr(qkv), qkv.stride(0), _ptr(cache), Tmax, _ptr(t_dev),
+                                                 _ptr(bd) if bd is not None else None, float(scale), _ptr(out),
+                                                 out.stride(0), B, H, _bf(qkv), current_stream_ptr()))
+    return out
+
+
+def decode_cross_attention(q, kv, B, H, Lk, add_mask=None, scale=1.0, chunk=256, out=None):
+    """q [B, H*64] against kv [B*Lk, 2*H*64] (k | v): chunked partials + the split-KV combine -> ctx [B, H*64]."""
+    require_cuda(q, "q")
+    chunks = (Lk + chunk - 1) // chunk
+    o_part = torch.empty((B * chunks, H * 64), dtype=torch.float32, device=q.device)
+    ml = torch.empty((B * chunks, H, 2), dtype=torch.float32, device=q.device)
+    am = add_mask.float().contiguous() if add_mask is not None else None
+    check(lib().atlas_b200_decode_cross_attention(_ptr(q), q.stride(0), _ptr(kv), kv.stride(0), 0, H * 64,
+                                                  _ptr(am) if am is not None else None, B, H, Lk, chunk, float(scale),
+                                                  _ptr(o_part), _ptr(ml), _bf(q), current_stream_ptr()))
+    if out is None:
+        out = torch.empty((B, H * 64), dtype=q.dtype, device=q.device)
+    check(lib().atlas_b200_attention_combine_ex(_ptr(o_part), _ptr(ml), B, chunks, 1, H, _ptr(out), out.stride(0), None,
+                                                _bf(q), current_stream_ptr()))
+    return out
+
+
+def decode_argmax(logits, seq, tok_in, done, t_dev, eos_id, pad_id, min_length):
+    """Greedy pick on the device (see include/atlas_b200.h); advances t_dev."""
+    require_cuda(logits, "logits")
+    B, V = logits.shape
+    check(lib().atlas_b200_decode_argmax(_ptr(logits), logits.stride(0), V, _ptr(seq), seq.stride(0), _ptr(tok_in),
+                                         _ptr(done), _ptr(t_dev), int(eos_id), int(pad_id), int(min_length), B, _bf(logits),
+                                         current_stream_ptr()))

@@ -55,6 +55,10 @@ class SharedPassageStore:
         self._maps = {}
         self._offs = {}
         self._files = {}
+        if rank == 0:       # the directory must not outlive the job when a process exits without close()
+            import atexit
+
+            atexit.register(shutil.rmtree, self.dir, True)
 
     def _data_path(self, r):
         return os.path.join(self.dir, f"passages.{r}.bin")
@@ -115,8 +119,19 @@ class ExchangePassageStore:
 
 
 def single_node(world):
+    """True when every rank of the process group runs on this host.  Decided by exchanging host names (collective):
+    LOCAL_WORLD_SIZE is only set by torchrun - the reference's own SLURM launcher (src/slurm.py) never sets it, and a
+    multi-node job must not pick the /dev/shm store."""
     local = os.environ.get("LOCAL_WORLD_SIZE")
-    return local is None or int(local) == world
+    if local is not None and int(local) != world:
+        return False
+    if not (dist.is_available() and dist.is_initialized()):
+        return True
+    import socket
+
+    names = [None] * world
+    dist.all_gather_object(names, socket.gethostname())
+    return len(set(names)) == 1
 
 
 def make_store(doc_map, rank, world):

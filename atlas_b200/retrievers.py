@@ -115,28 +115,71 @@ def _warn_no_dropout(who):
                       "(not implemented yet); use --dropout 0 for exact agreement with the reference")
 
 
+_WEIGHTS_EPOCH = [0]
+
+
+def _bump_weights_epoch(*_args, **_kw):
+    _WEIGHTS_EPOCH[0] += 1
+
+
+try:    # every optimizer.step() anywhere in the process (AdamWFP32Copy, fairscale OSS ...) marks the 16-bit copies stale:
+    # some optimizers write through `param.data`, which does not bump the parameter's version counter
+    from torch.optim.optimizer import register_optimizer_step_post_hook as _reg_hook
+
+    _reg_hook(_bump_weights_epoch)
+except Exception:       # older torch: version counters + explicit invalidate() only
+    pass
+
+
 class HalfCache:
     """16-bit device copies of a module's parameters, one set per compute dtype (the live query encoder may run
-    in bf16 while index refresh embeds passages in fp16, src/atlas.py:54-59), each rebuilt when any parameter
-    changed (`_version`).  `derived(dtype, build)` caches tensors computed from a set (fused QKV weights ...)."""
+    in bf16 while index refresh embeds passages in fp32-master / fp16 like src/atlas.py:54-59).
+
+    The copies live in FIXED buffers that are refreshed IN PLACE, so CUDA graphs that read them stay valid when the
+    weights change (no re-capture per optimizer step).  A refresh happens on the next `get()` after
+      * any parameter's autograd version or storage changed (in-place ops, `load_state_dict`, `.to()`),
+      * any `optimizer.step()` in the process (global post-step hook: covers optimizers that write through `param.data`),
+      * an explicit `invalidate()` (callers that write `param.data` by hand).
+    `derived(dtype, build)` caches tensors computed from a set (fused QKV weights ...), refreshed in place with it.
+    `gen` changes only when buffers are re-allocated (parameter set / shapes / device changed): the CUDA-graph key."""
 
     def __init__(self):
         self.sets = {}
+        self._dirty = False
+
+    def invalidate(self):
+        self._dirty = True
 
     def get(self, module, dtype):
         params = list(module.named_parameters())
-        key = (dtype, tuple((p.data_ptr(), p._version) for _, p in params))
+        struct = tuple((n, p.data_ptr(), tuple(p.shape), p.dtype, p.device) for n, p in params)
+        key = (tuple(p._version for _, p in params), _WEIGHTS_EPOCH[0])
         ent = self.sets.get(dtype)
-        if ent is None or ent["key"] != key:
+        if ent is None or ent["struct"] != struct:
             store = {n: (p.detach() if p.dtype == dtype else p.detach().to(dtype)).contiguous() for n, p in params}
-            ent = {"key": key, "store": store, "derived": None}
+            gen = 0 if ent is None else ent["gen"] + 1
+            ent = {"struct": struct, "key": key, "store": store, "derived": None, "derived_stale": False, "gen": gen}
             self.sets[dtype] = ent
+            self._dirty = False
+        elif (ent["key"] != key or self._dirty) and not torch.cuda.is_current_stream_capturing():
+            for n, p in params:
+                dst = ent["store"][n]
+                if dst.data_ptr() != p.data_ptr():          # a converted copy (an alias of the live tensor needs nothing)
+                    dst.copy_(p.detach())
+            ent["key"] = key
+            ent["derived_stale"] = ent["derived"] is not None
+            self._dirty = False
         return ent["store"]
 
     def derived(self, dtype, build):
         ent = self.sets[dtype]
         if ent["derived"] is None:
             ent["derived"] = build(ent["store"])
+        elif ent["derived_stale"] and not torch.cuda.is_current_stream_capturing():
+            fresh = build(ent["store"])
+            for k, v in fresh.items():
+                ent["derived"][k].copy_(v)
+            ent["derived_stale"] = False
         return ent["derived"]
 
 

@@ -16,7 +16,13 @@ text_maxlength 384, 32 target tokens) — plus the MIPS scan against the HBM roo
   refresh       supplementary: index refresh in place (Contriever-base passage embedding into bank rows), passages/s
   cpu_baseline  the reference's CPU path (oracle/: torch-CPU restatements pinned to the reference's goldens) on this
                 box's host cores, bounded sample
-`--impl reference` times that CPU path as the reference arm.  One process per GPU; weak scaling (per-GPU batch and
+  gpu_reference the UNMODIFIED reference modules (oracle/_ref/src, staged by oracle/make_ref.py) on cuda:0 in bf16 eager
+                PyTorch (`--index_mode flat`: matmul + topk; eager FiD / Contriever) on the same step: the comparator of
+                north_star's ">= 10x" target, plus the fp32 matmul + topk stand-in for FAISS-GPU flat (faiss is absent)
+  parity_check  before timing: the distributed search's ids / scores against torch `matmul(q.half(), E)` + `topk`
+                (src/index.py:117-118) recomputed on every shard and merged (runs at every N)
+`--impl reference` times the reference's own CPU path (the same unmodified modules, all host threads; one query per
+step, real steps - nothing stitched or extrapolated at N = 1).  One process per GPU; weak scaling (per-GPU batch and
 per-GPU bank shard fixed).
 """
 import argparse
@@ -37,6 +43,7 @@ CPU_SAMPLE_ROWS = 1 << 20   # bounded CPU sample: 1 Mi of the 4 Mi rows (scaled 
 METRIC = "end-to-end queries/sec (retrieve top-40 + FiD-base fwd)"
 N_DOCS, TEXT_LEN, TARGET_LEN, QUERY_TOKENS = 40, 384, 32, 20   # BASELINE configs[3] / finetune_qa defaults
 FID_FLOPS_PER_QUERY = 3.29e12
+PASSAGE_TOKENS = 256                                            # token-bank row width (passage part of the reader input)
 
 
 def parse():
@@ -48,6 +55,9 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=N_LOCAL, help="passages per GPU (default: the BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true")
+    ap.add_argument("--ref-budget-s", type=float, default=150.0,
+                    help="--impl reference: wall-clock budget of the timed CPU steps (each step = one query)")
     ap.add_argument("--profile-step", action="store_true",
                     help="run warm-up + the timed steps inside an NVTX range 'atlas_b200_timed' and exit (for ncu "
                          "--nvtx --nvtx-include 'atlas_b200_timed/'; no JSON line is printed)")
@@ -131,24 +141,86 @@ def make_queries():
     return torch.randn(NQ, DIM, generator=torch.Generator().manual_seed(4321))
 
 
-def cpu_reference_leg(batch, rows_full, fid_queries=1, search_steps=2):
-    """The reference's CPU path on a bounded sample of the step (all host threads): Contriever query embedding and
-    FiD-base forward (oracle/fid_cpu.py, fp32 torch-CPU) for `fid_queries` queries, and matmul + topk + doc lookup
-    (oracle/ref_cpu_path.py) for `batch` queries over a 1 Mi-row sample of the bank, scaled linearly to the bank."""
+def _all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1: the CPU arm must still use every host core."""
+    import torch
+
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
+def cpu_reference_leg(rows_total, budget_s=40.0, max_steps=1, warmup=0):
+    """The reference's CPU path, REAL steps: the unmodified reference `Contriever` -> `DistributedIndex.search_knn`
+    (matmul + topk over the whole `rows_total` x 768 fp16 bank, CPU-resident) -> `FiD` fp32 forward + loss
+    (oracle/ref_runner.py over oracle/_ref/src), ONE query per step (the bounded sample), all host threads.  Falls back
+    to the torch-CPU restatements (oracle/fid_cpu.py, kind "port") only when the reference sources are not staged."""
     import torch
 
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    cores = _all_host_threads()
+    import ref_runner
+
+    if ref_runner.reference_root() is None:
+        return _cpu_port_leg(rows_total, cores)
+    # bank: a 256 Ki-column Gaussian block tiled to the full width (the arithmetic cost does not depend on the values);
+    # capped by the host's free memory (stated) - the reference keeps the bank as ONE [768, N] fp16 tensor
+    rows = rows_total
+    try:
+        import psutil
+
+        free = psutil.virtual_memory().available
+        while rows * DIM * 2 * 2.5 > free and rows > (1 << 20):
+            rows //= 2
+    except Exception:
+        pass
+    block = min(rows, 1 << 18)
+    gen = torch.Generator().manual_seed(1234)
+    blk = (torch.randn(DIM, block, generator=gen) / (DIM ** 0.5)).half()
+    emb = torch.empty(DIM, rows, dtype=torch.float16)          # the reference layout, src/index.py:51
+    for s in range(0, rows, block):
+        e = min(rows, s + block)
+        emb[:, s:e] = blk[:, :e - s]
+    t_build = time.perf_counter()
+    ref = ref_runner.ReferenceStep(rows, "cpu", torch.float32, N_DOCS, TEXT_LEN, embeddings=emb)
+    del emb
+    t_build = time.perf_counter() - t_build
+    q_ids, q_mask, dec, labels = make_step_inputs(1, 0)
+    for _ in range(warmup):
+        ref.step(q_ids, q_mask, dec, labels, TOPK)
+    times, phases = [], []
+    t_start = time.perf_counter()
+    while len(times) < max_steps and (not times or time.perf_counter() - t_start + times[-1] < budget_s):
+        t0 = time.perf_counter()
+        loss, _, ph = ref.step(q_ids, q_mask, dec, labels, TOPK)
+        times.append(time.perf_counter() - t0)
+        phases.append(ph)
+    assert loss == loss, "non-finite reference loss"
+    per_query = sum(times) / len(times)
+    ph = [sum(p[i] for p in phases) / len(phases) for i in range(3)]
+    scale_note = "" if rows == rows_total else f"; bank capped at {rows} of {rows_total} rows by host memory (search time NOT scaled)"
+    return {"value": 1.0 / per_query, "unit": "queries/s", "cores": cores, "kind": "reference",
+            "sample": f"{len(times)} timed step(s) of 1 query each (+{warmup} warm-up) through the UNMODIFIED reference "
+                      f"(oracle/_ref/src: Contriever-base fp32 embed {ph[0]:.3f} s, DistributedIndex.search_knn over "
+                      f"{rows} x 768 fp16 CPU bank {ph[1]:.3f} s, FiD-base fp32 forward n_docs {N_DOCS} x {TEXT_LEN} "
+                      f"tokens {ph[2]:.3f} s); torch-CPU {torch.get_num_threads()} threads{scale_note}",
+            "s_per_query": per_query, "steps": len(times), "model_build_s": t_build}
+
+
+def _cpu_port_leg(rows_full, cores, batch=1):
+    """Fallback when oracle/_ref is absent: the torch-CPU restatements (pinned to the reference's goldens)."""
+    import torch
+
     import fid_cpu
     import ref_cpu_path
 
-    torch.manual_seed(0)
     rows = min(CPU_SAMPLE_ROWS, rows_full)
     gen = torch.Generator().manual_seed(1234)
-    emb = torch.empty(DIM, rows, dtype=torch.float16)
-    step = 1 << 16
-    for s in range(0, rows, step):
-        e = min(rows, s + step)
-        emb[:, s:e] = (torch.randn(DIM, e - s, generator=gen) / (DIM ** 0.5)).half()
+    emb = (torch.randn(DIM, rows, generator=gen) / (DIM ** 0.5)).half()
     doc_map = ref_cpu_path.LazyDocMap(rows)
     bert = fid_cpu.bert_random_state(fid_cpu.BERT_BASE)
     t5 = fid_cpu.t5_random_state(fid_cpu.T5_BASE)
@@ -157,23 +229,20 @@ def cpu_reference_leg(batch, rows_full, fid_queries=1, search_steps=2):
         t0 = time.perf_counter()
         q = fid_cpu.contriever_forward(bert, fid_cpu.BERT_BASE, q_ids, q_mask)
         t_embed = (time.perf_counter() - t0) / batch
+        t0 = time.perf_counter()
         ref_cpu_path.reference_search_cpu(emb, doc_map, q, TOPK)
+        t_search = (time.perf_counter() - t0) * (rows_full / rows) / batch
+        ids = torch.randint(2, 32000, (1, N_DOCS * TEXT_LEN))
+        mask = torch.ones(1, N_DOCS * TEXT_LEN, dtype=torch.bool)
         t0 = time.perf_counter()
-        for _ in range(search_steps):
-            docs, _ = ref_cpu_path.reference_search_cpu(emb, doc_map, q, TOPK)
-        t_search = (time.perf_counter() - t0) / search_steps * (rows_full / rows) / batch
-        ids = torch.randint(2, 32000, (fid_queries, N_DOCS * TEXT_LEN))
-        mask = torch.ones(fid_queries, N_DOCS * TEXT_LEN, dtype=torch.bool)
-        t0 = time.perf_counter()
-        fid_cpu.fid_forward(t5, fid_cpu.T5_BASE, ids, mask, dec[:fid_queries], labels[:fid_queries], n_context=N_DOCS)
-        t_read = (time.perf_counter() - t0) / fid_queries
+        fid_cpu.fid_forward(t5, fid_cpu.T5_BASE, ids, mask, dec[:1], labels[:1], n_context=N_DOCS)
+        t_read = time.perf_counter() - t0
     per_query = t_embed + t_search + t_read
-    return {"value": 1.0 / per_query, "unit": "queries/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"per query: Contriever embed {t_embed:.3f} s ({batch} queries timed) + search {t_search:.3f} s "
-                      f"({batch} queries x {rows} of {rows_full} passages, time scaled x{rows_full / rows:g}) + FiD-base "
-                      f"fp32 forward {t_read:.3f} s ({fid_queries} query timed); torch-CPU, oracle/fid_cpu.py + "
-                      f"oracle/ref_cpu_path.py",
-            "s_per_query": per_query}
+    return {"value": 1.0 / per_query, "unit": "queries/s", "cores": cores, "kind": "port",
+            "sample": f"reference sources not staged: torch-CPU restatements (oracle/fid_cpu.py, oracle/ref_cpu_path.py), "
+                      f"1 query: embed {t_embed:.3f} s + search {t_search:.3f} s ({rows} of {rows_full} rows, scaled) + "
+                      f"FiD-base fp32 forward {t_read:.3f} s",
+            "s_per_query": per_query, "steps": 1, "model_build_s": 0.0}
 
 
 def make_step_inputs(batch, seed):
@@ -199,27 +268,259 @@ def workload_config(args):
             "queries_per_step": args.batch * args.gpus, "per_gpu_batch": args.batch, "topk": TOPK,
             "parallelism": f"dp{args.gpus}: bank sharded over {args.gpus} GPU(s) (queries all-gathered, one all-gather "
                            f"of per-shard top-k), reader data-parallel",
-            "reader_tokens": "synthetic: token ids derived on the device from the retrieved passage ids (stand-in for a "
-                             "device-resident token cache; no tokenizer vocabulary offline)",
+            "reader_tokens": f"synthetic device-resident token bank: {PASSAGE_TOKENS}-token rows keyed by global passage "
+                             f"id (lengths U[{PASSAGE_TOKENS // 2}, {PASSAGE_TOKENS}]), spliced behind the query tokens "
+                             "on the GPU (atlas_b200_splice_tokens); no tokenizer vocabulary offline",
             "weights": "random init (Contriever-base / T5-v1.1-base shapes), bf16 reader + retriever, fp16 bank",
             "l2": "bank (6.4 GB) and per-step activations (> 1 GB) exceed the 126 MB L2; no explicit flush"}
 
 
 def run_reference(args):
+    """Reference arm: the reference's own CPU implementation of the step on this box's host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    leg = cpu_reference_leg(args.batch, args.rows * args.gpus, fid_queries=1, search_steps=max(1, min(args.steps, 2)))
+    leg = cpu_reference_leg(args.rows * args.gpus, budget_s=args.ref_budget_s, max_steps=max(1, args.steps),
+                            warmup=1 if args.warmup > 0 else 0)
     line = {
         "impl": "reference", "metric": METRIC, "value": leg["value"], "unit": "queries/s", "n_gpus": args.gpus,
-        "steps": 1, "warmup": 0, "ms_per_step": leg["s_per_query"] * 1e3 * args.batch * args.gpus,
+        "steps": leg["steps"], "warmup": 1 if args.warmup > 0 else 0, "ms_per_step": leg["s_per_query"] * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args),
+        "config": dict(workload_config(args), reference_step="1 query per step (bounded sample of the "
+                       f"{args.batch * args.gpus}-query step); steps capped by --ref-budget-s {args.ref_budget_s:g}"),
         "cpu_baseline": {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": leg["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
+
+
+class HashTokenizer:
+    """Deterministic word-hash tokenizer with the call surface Atlas uses (no vocabulary files offline): the bench's
+    stand-in for BertTokenizer / T5Tokenizer, used identically by the product arm and the gpu_reference leg."""
+
+    def __init__(self, kind, vocab_size):
+        import zlib
+
+        self.kind, self.vocab_size, self._crc = kind, vocab_size, zlib.crc32
+        self.pad_token_id, self.eos_token_id, self.cls_token_id, self.sep_token_id = 0, 1, 2, 3
+        self.vocab = {f"tok{i}": i for i in range(vocab_size)}
+
+    def _encode(self, text, special):
+        ids = [self.eos_token_id if w == "</s>" else 10 + self._crc(w.lower().encode()) % (self.vocab_size - 10)
+               for w in text.replace("</s>", " </s> ").split()]
+        if special:
+            ids = [self.cls_token_id] + ids + [self.sep_token_id] if self.kind == "bert" else ids + [self.eos_token_id]
+        return ids
+
+    def __call__(self, texts, padding=False, max_length=None, truncation=False, return_tensors=None,
+                 add_special_tokens=True):
+        import torch
+
+        single = isinstance(texts, str)
+        rows = [self._encode(t, add_special_tokens) for t in ([texts] if single else texts)]
+        if truncation and max_length is not None:
+            last = self.sep_token_id if self.kind == "bert" else self.eos_token_id
+            rows = [r if len(r) <= max_length else (r[:max_length - 1] + [last] if add_special_tokens else r[:max_length])
+                    for r in rows]
+        if return_tensors is None:
+            masks = [[1] * len(r) for r in rows]
+            return {"input_ids": rows[0] if single else rows, "attention_mask": masks[0] if single else masks}
+        width = max_length if padding == "max_length" else max((len(r) for r in rows), default=0)
+        ids = torch.full((len(rows), width), self.pad_token_id, dtype=torch.long)
+        mask = torch.zeros((len(rows), width), dtype=torch.long)
+        for i, r in enumerate(rows):
+            ids[i, :len(r)] = torch.tensor(r, dtype=torch.long)
+            mask[i, :len(r)] = 1
+        return {"input_ids": ids, "attention_mask": mask}
+
+    def batch_encode_plus(self, texts, **kw):
+        return self(texts, **kw)
+
+
+class LazyDocs:
+    """doc_map stand-in: local row -> synthetic passage dict, generated on demand (no 32 M python dicts)."""
+
+    def __init__(self, n, base=0, stride=1):
+        self.n, self.base, self.stride = n, base, stride
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        g = self.base + self.stride * int(i)
+        return {"id": str(g), "title": f"t{g}", "text": f"passage {g}"}
+
+
+def bench_opt(batch):
+    """The option fields `Atlas` reads on the measured path (defaults of src/options.py at BASELINE configs[3])."""
+    from types import SimpleNamespace
+
+    return SimpleNamespace(
+        retriever_format="{title} {text}", encoder_format="{query} title: {title} context: {text}",
+        text_maxlength=TEXT_LEN, target_maxlength=TARGET_LEN, retriever_n_context=N_DOCS, n_context=N_DOCS,
+        filtering_overretrieve_ratio=2, retrieve_with_rerank=False, n_to_rerank_with_retrieve_with_rerank=128,
+        per_gpu_embedder_batch_size=512, per_gpu_batch_size=batch, decoder_prompt_format=None, decoder_format=None,
+        use_file_passages=False, gold_score_mode="ppmean", use_gradient_checkpoint_retriever=False,
+        use_gradient_checkpoint_reader=False, compute_crossattention_stats=False, temperature_gold=0.01,
+        temperature_score=0.01, generation_max_length=TARGET_LEN, generation_min_length=1, generation_num_beams=1,
+        generation_length_penalty=1.0, query_side_retriever_training=False, device_token_bank=True)
+
+
+def make_token_bank(rows_total, dev):
+    """Synthetic device-resident reader token bank: int32 [rows_total, PASSAGE_TOKENS] rows keyed by global passage id,
+    lengths U[PASSAGE_TOKENS/2, PASSAGE_TOKENS] (replicated on every rank, atlas_b200/token_bank.py)."""
+    import torch
+
+    from atlas_b200.token_bank import DeviceTokenBank
+
+    gen = torch.Generator(device=dev).manual_seed(4242)
+    ids = torch.empty(rows_total, PASSAGE_TOKENS, dtype=torch.int32, device=dev)
+    step = 1 << 20
+    for s in range(0, rows_total, step):
+        e = min(rows_total, s + step)
+        ids[s:e] = torch.randint(10, 32000, (e - s, PASSAGE_TOKENS), device=dev, generator=gen, dtype=torch.int32)
+    lens = torch.randint(PASSAGE_TOKENS // 2, PASSAGE_TOKENS + 1, (rows_total,), device=dev, generator=gen,
+                         dtype=torch.int32)
+    return DeviceTokenBank(ids, lens, eos_id=1, pad_id=0, parts=("{query} ", "title: {title} context: {text}"))
+
+
+def make_query_strings(batch, seed):
+    import random
+
+    rnd = random.Random(9000 + seed)
+    queries = [" ".join(f"q{rnd.randrange(50000)}" for _ in range(QUERY_TOKENS - 2)) for _ in range(batch)]
+    targets = [" ".join(f"a{rnd.randrange(50000)}" for _ in range(TARGET_LEN - 1)) for _ in range(batch)]
+    return queries, targets
+
+
+def parity_check(index, q_local, dev, world, rank):
+    """Before timing, at every N: the (distributed) search against the reference computation recomputed with torch on
+    every shard - `torch.matmul(allqueries.half(), embeddings)` + `torch.topk` (src/index.py:117-118), per-shard lists
+    merged with a second top-k (src/index.py:144-151).  Checks: returned scores == merged reference scores (<= 1 fp16
+    ulp: cuBLAS and tcgen05 accumulate fp32 in different orders on Gaussian inputs), sorted descending, and every
+    returned id's own score recomputed by its OWNER shard equals the returned score (<= 1 ulp).  Returns a dict."""
+    import torch
+    import torch.distributed as dist
+
+    k = TOPK
+    B = q_local.shape[0]
+    scores, gids = index.search_device(q_local, k)
+    q16 = q_local.half()
+    if world > 1:
+        allq = torch.empty(world * B, DIM, dtype=torch.float16, device=dev)
+        dist.all_gather_into_tensor(allq, q16.contiguous())
+    else:
+        allq = q16
+    S = torch.matmul(allq, index._bank.t())                                  # [W*B, N_local] fp16, the reference's product
+    ref_s, _ = torch.topk(S, k, dim=1)
+    if world > 1:
+        ref_all = torch.empty(world, world * B, k, dtype=torch.float16, device=dev)
+        dist.all_gather_into_tensor(ref_all, ref_s.contiguous())
+        merged = torch.topk(ref_all.permute(1, 0, 2).reshape(world * B, world * k).float(), k, dim=1)[0]
+        g_all = torch.empty(world, B, k, dtype=torch.int64, device=dev)
+        s_all = torch.empty(world, B, k, dtype=torch.float16, device=dev)
+        dist.all_gather_into_tensor(g_all, gids.contiguous())
+        dist.all_gather_into_tensor(s_all, scores.contiguous())
+    else:
+        merged = ref_s.float()
+        g_all, s_all = gids[None], scores[None]
+    mine = merged[rank * B:(rank + 1) * B]
+    got = scores.float()
+    ulp = torch.maximum(mine.abs(), got.abs()).clamp_min(2.0 ** -14) * 2.0 ** -10
+    bad_scores = int(((got - mine).abs() > ulp).sum())
+    bad_sorted = int((got[:, 1:] > got[:, :-1]).sum())
+    # owner check of the ids: rank r owns gid with gid % W == r at local row gid // W
+    own = (g_all % world) == rank
+    rows = torch.where(own, g_all // world, torch.zeros_like(g_all))
+    qidx = (torch.arange(world, device=dev)[:, None, None] * B + torch.arange(B, device=dev)[None, :, None]).expand_as(g_all)
+    mine_s = S[qidx, rows].float()
+    ret_s = s_all.float()
+    ulp2 = torch.maximum(mine_s.abs(), ret_s.abs()).clamp_min(2.0 ** -14) * 2.0 ** -10
+    bad_ids = ((mine_s - ret_s).abs() > ulp2) & own
+    dup = int(sum(len(set(r)) != k for r in gids.tolist()))
+    fails = torch.tensor([bad_scores, bad_sorted, int(bad_ids.sum()), dup], device=dev, dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(fails)
+    f = fails.tolist()
+    del S
+    return {"status": "ok" if sum(f) == 0 else "FAIL", "queries": world * B, "topk": k,
+            "score_mismatches": f[0], "unsorted": f[1], "id_score_mismatches": f[2], "rows_with_duplicate_ids": f[3],
+            "method": "scores vs torch.matmul(q.half(), E)+topk per shard merged by a second topk (src/index.py:117-151), "
+                      "<= 1 fp16 ulp; every returned id re-scored by its owner shard"}
+
+
+def gpu_reference_leg(args, bank, dev, steps=3, warmup=1):
+    """The UNMODIFIED reference modules on cuda:0 (oracle/ref_runner.py over oracle/_ref/src): reference Contriever-base
+    + `DistributedIndex` in `--index_mode flat` (matmul + topk, src/index.py:113-157) + eager FiD-base, bf16 parameters
+    (`--precision bf16`, src/model_io.py:94-98), the same 8-query step on the same bank.  This is the comparator of
+    north_star's ">= 10x the reference's GPU path"; FAISS is absent from the image, so next to it the fp32
+    `matmul` + `topk` over an fp32 copy of the bank is timed as the stand-in for faiss GpuIndexFlatIP (labelled)."""
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_runner
+
+    if ref_runner.reference_root() is None:
+        return {"unavailable": "reference sources not staged (oracle/make_ref.py)"}
+    B = args.batch
+    ref = ref_runner.ReferenceStep(args.rows, dev, torch.bfloat16, N_DOCS, TEXT_LEN, bank=bank)
+    inputs = make_step_inputs(B, 0)
+    for _ in range(warmup):
+        ref.step(*inputs, TOPK)
+    torch.cuda.synchronize()
+    times, phases = [], []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        loss, _, ph = ref.step(*inputs, TOPK)          # ends with float(loss): synchronised
+        times.append(time.perf_counter() - t0)
+        phases.append(ph)
+    assert loss == loss, "non-finite reference loss"
+    ms = 1e3 * sum(times) / len(times)
+    ph = [1e3 * sum(p[i] for p in phases) / len(phases) for i in range(3)]
+    out = {"value": B / (ms * 1e-3), "unit": "queries/s", "ms_per_step": ms, "steps": steps, "queries_per_step": B,
+           "phases_ms": {"contriever": ph[0], "search_knn": ph[1], "fid_forward_loss": ph[2]},
+           "what": "unmodified reference (oracle/_ref/src) on cuda:0, bf16 eager PyTorch + cuBLAS, --index_mode flat; "
+                   "host token ids in, loss out (wall clock, synchronised)"}
+    # search alone at the MIPS batch: reference flat index (fp16 matmul + topk) and the FAISS-flat stand-in (fp32)
+    q = make_queries().to(dev)
+    E = ref.index.embeddings
+
+    def timed(fn, n=5):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    with torch.no_grad():
+        ms_flat = timed(lambda: ref.index._compute_scores_and_indices(q, TOPK))
+        out["search_256q_flat_fp16"] = {"ms": ms_flat, "queries_per_s": NQ / (ms_flat * 1e-3),
+                                        "what": "reference DistributedIndex._compute_scores_and_indices, 256 queries"}
+        try:
+            chunk = 1 << 20
+            E32 = E[:, :chunk].float()
+
+            def faiss_standin():
+                best = None
+                for _ in range(args.rows // chunk):        # same fp32 block re-used: arithmetic and traffic of a full sweep
+                    s_, i_ = torch.topk(torch.matmul(q, E32), TOPK, dim=1)
+                    best = s_ if best is None else torch.maximum(best, s_)
+                return best
+
+            ms32 = timed(faiss_standin, 3)
+            out["search_256q_fp32_standin"] = {"ms": ms32, "queries_per_s": NQ / (ms32 * 1e-3),
+                                               "what": "STAND-IN for faiss GpuIndexFlatIP (faiss absent): fp32 matmul + "
+                                                       "topk over 1 Mi-column fp32 blocks, full-bank arithmetic"}
+        except Exception as e:
+            out["search_256q_fp32_standin"] = {"error": repr(e)[:200]}
+    del ref
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_ours(args):
@@ -230,12 +531,10 @@ def run_ours(args):
 
     from atlas_b200 import ops
     from atlas_b200._lib import lib
+    from atlas_b200.atlas import Atlas
     from atlas_b200.fid import FiD, T5ConfigLite
     from atlas_b200.index import DistributedIndex
-    from atlas_b200.retrievers import BertConfigLite, Contriever
-
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import ref_cpu_path
+    from atlas_b200.retrievers import BertConfigLite, Contriever, DualEncoderRetriever
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -247,10 +546,12 @@ def run_ours(args):
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
     L = lib()
+    B = args.batch
     index = DistributedIndex()
     index._bank = make_bank(args.rows, dev, 1234 + rank)
-    index.doc_map = ref_cpu_path.LazyDocMap(args.rows, rank, world)
+    index.doc_map = LazyDocs(args.rows, rank, world)
     index._id_base, index._id_stride = rank, world
+    index.max_queries_per_rank = B          # every rank searches B queries per step: no size exchange, no host sync
 
     class _SyntheticStore:  # passage text by global id, generated on the fly (no 32M python dicts)
         def lookup(self, owners_locals):
@@ -262,10 +563,14 @@ def run_ours(args):
 
     index._store = _SyntheticStore()
     torch.manual_seed(0)          # identical weights on every rank
-    retriever = Contriever(BertConfigLite()).to(torch.bfloat16).to(dev).eval()
+    contriever = Contriever(BertConfigLite()).to(torch.bfloat16).to(dev).eval()
     reader = FiD(T5ConfigLite()).to(torch.bfloat16).to(dev).eval()
-    reader.encoder.config.n_context, reader.encoder.config.bsz = N_DOCS, args.batch
-    B = args.batch
+    reader.encoder.config.n_context, reader.encoder.config.bsz = N_DOCS, B
+    opt = bench_opt(B)
+    atlas = Atlas(opt, reader, DualEncoderRetriever(opt, contriever), HashTokenizer("t5", 32128),
+                  HashTokenizer("bert", 30522)).eval()
+    bank_tokens = make_token_bank(args.rows * world, dev)
+    atlas.set_token_bank(bank_tokens)
 
     def barrier_sync():
         if world > 1:
@@ -279,27 +584,47 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    host = [t.pin_memory() for t in make_step_inputs(B, rank)]
-    resident = [t.to(dev) for t in host]
-    pos = torch.arange(TEXT_LEN, device=dev, dtype=torch.long)
-    reader_mask = torch.ones(B, N_DOCS * TEXT_LEN, dtype=torch.bool, device=dev)
+    # ---------------- device-resident step inputs (the `value` loop) -------------------------------------------
+    queries, targets = make_query_strings(B, rank)
+    q_enc = atlas.retriever_tokenize(queries)                                   # [B, 384] ids / mask on the device
+    labels, dec = atlas.reader_tokenize(queries, targets, None)
+    rq_ids, rq_lens = bank_tokens.query_tokens(atlas.reader_tokenizer, queries, dev)
+    status_acc = torch.zeros((), dtype=torch.int64, device=dev)
 
-    def step(from_host):
-        """One retrieve-then-read step of this rank's B queries (collective inside search_device)."""
-        q_ids, q_mask, dec, labels = [t.to(dev, non_blocking=True) for t in host] if from_host else resident
+    def step_device():
+        """One retrieve-then-read step of this rank's B queries, inputs resident, NO host synchronisation:
+        Contriever -> sharded scan + (at N > 1) 2 all-gathers + merge -> token-bank splice -> FiD forward + loss."""
         with torch.no_grad():
-            q_emb = retriever(input_ids=q_ids, attention_mask=q_mask)                  # [B, 768]
-            scores, gids = index.search_device(q_emb, TOPK)                            # [B, 40] fp16 / int64 global ids
-            # reader tokens of (query, passage) pairs: synthetic ids keyed by the retrieved passage id
-            reader_ids = ((gids[:, :, None] * 1315423911 + pos * 2654435761) % 32000 + 2).view(B, N_DOCS * TEXT_LEN)
-            out = reader(input_ids=reader_ids, attention_mask=reader_mask, decoder_input_ids=dec, labels=labels)
-        if from_host:
-            return out[0].float().cpu(), gids.cpu(), scores.cpu()                     # D2H: loss + retrieved ids/scores
+            q_emb = contriever(input_ids=q_enc["input_ids"], attention_mask=q_enc["attention_mask"])
+            scores, gids, status = index.search_device(q_emb, TOPK, return_status=True)
+            status_acc.copy_(torch.maximum(status_acc, status))
+            tok = bank_tokens.splice(gids, TEXT_LEN, rq_ids, rq_lens)
+            out = reader(input_ids=tok["input_ids"].view(B, -1), attention_mask=tok["attention_mask"].view(B, -1),
+                         decoder_input_ids=dec, labels=labels)
         return out[0], gids, scores
 
+    def step_api():
+        """The same step through the module surface train.py / evaluate.py call, HOST inputs and outputs: query strings
+        -> Atlas.retriever_tokenize / reader_tokenize (host tokenisation + H2D) -> Atlas.retrieve (query embedding,
+        DistributedIndex.search_knn: ids + scores D2H, passage dicts from the store) -> Atlas.reader_passage_tokens
+        (device token bank) -> Atlas.compute_reader_loss_and_logits (loss D2H)."""
+        enc = atlas.retriever_tokenize(queries)
+        lab, dec_ids = atlas.reader_tokenize(queries, targets, None)
+        passages, scores = atlas.retrieve(index, TOPK, queries, enc["input_ids"], enc["attention_mask"])
+        tok = atlas.reader_passage_tokens(queries, passages)
+        loss, _ = atlas.compute_reader_loss_and_logits(tok, dec_ids, lab)
+        return loss, passages, scores
+
+    # ---------------- parity of the (distributed) search against the reference computation, before timing ----------
+    with torch.no_grad():
+        q_par = contriever(input_ids=q_enc["input_ids"], attention_mask=q_enc["attention_mask"])
+        parity = parity_check(index, q_par, dev, world, rank)
+    assert parity["status"] == "ok", f"search parity check failed: {parity}"
+
     # ---------------- value: device-resident inputs -----------------------------------------
-    for _ in range(max(args.warmup, 3)):
-        step(False)
+    n_warm = max(args.warmup, 3 if world == 1 else 10)     # NCCL connections / graph capture settle before timing
+    for _ in range(n_warm):
+        step_device()
     launches0 = L.atlas_b200_launch_count()
     barrier_sync()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -307,7 +632,7 @@ def run_ours(args):
         torch.cuda.nvtx.range_push("atlas_b200_timed")
         e0.record()
         for _ in range(args.steps):
-            loss, gids, _ = step(False)
+            loss, gids, _ = step_device()
         e1.record()
         barrier_sync()
         torch.cuda.nvtx.range_pop()
@@ -320,28 +645,31 @@ def run_ours(args):
     ms_per_step = total_ms / args.steps
     value = B * world / (ms_per_step * 1e-3)
     assert bool(torch.isfinite(loss.float())), "non-finite loss in the benchmark step"
+    assert int(status_acc.item()) == 0, "the fast search path overflowed during the timed steps (exhaustive path needed)"
 
-    # ---------------- e2e: host inputs / host results ------------------------------------------
-    for _ in range(2):
-        step(True)
+    # ---------------- e2e: host inputs / host results through the Atlas module surface --------------------------
+    for _ in range(3):
+        step_api()
     barrier_sync()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        step(True)
+        loss_host, passages, _ = step_api()
     barrier_sync()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
-    h2d = sum(t.numel() * t.element_size() for t in host) * world
-    d2h = (4 + B * TOPK * (8 + 2)) * world
+    assert loss_host == loss_host and len(passages) == B and len(passages[0]) == TOPK
+    h2d = (sum(t.numel() * t.element_size() for t in q_enc.values()) + labels.numel() * 8 + dec.numel() * 8
+           + rq_ids.numel() * 8 + rq_lens.numel() * 4 + B * N_DOCS * 8) * world
+    d2h = (4 + B * TOPK * (8 + 4) + 8) * world
 
     # ---------------- per-kernel time of the step (eager launches bracketed with CUDA events in the library) -------
     reader.cuda_graphs = False
     prof = {}
     for kind, name in ((2, "gemm"), (3, "attention")):
-        step(False)
+        step_device()
         torch.cuda.synchronize()
         l0 = L.atlas_b200_launch_count()
         L.atlas_b200_profile_enable(kind)
-        step(False)
+        step_device()
         torch.cuda.synchronize()
         work = L.atlas_b200_profile_work()
         kms, kn = ctypes.c_double(0), ctypes.c_int32(0)
@@ -352,7 +680,16 @@ def run_ours(args):
     reader.cuda_graphs = True
 
     # ---------------- the retrieval kernel alone at its BASELINE batch (256 queries) -------------
+    index.max_queries_per_rank = NQ // world
     mips = mips_leg(args, index, dev, world, rank, L, barrier_sync, max_over_ranks)
+    index.max_queries_per_rank = B
+
+    # ---------------- greedy generation with the KV-cached decode path (supplementary) -----------------------------
+    try:
+        generate = generate_leg(args, atlas, bank_tokens, index, q_enc, rq_ids, rq_lens, dev, world, L, barrier_sync,
+                                max_over_ranks)
+    except Exception as e:
+        generate = {"error": repr(e)[:300]}
 
     # ---------------- the reader's TRAINING step (forward + backward kernels), BASELINE configs[3] shapes -------------
     try:
@@ -362,7 +699,7 @@ def run_ours(args):
 
     # ---------------- index refresh in place (BASELINE configs[2]: re-embed the local shard), one embedder batch -------
     try:
-        refresh = refresh_leg(args, retriever, index, dev, world, L, barrier_sync, max_over_ranks)
+        refresh = refresh_leg(args, contriever, index, dev, world, L, barrier_sync, max_over_ranks)
     except Exception as e:
         refresh = {"error": repr(e)[:300]}
 
@@ -383,9 +720,10 @@ def run_ours(args):
     g_ms, g_n, g_flops = prof["gemm"]
     a_ms, a_n, a_flops = prof["attention"]
     achieved = g_flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+    a_tflops = a_flops / (a_ms * 1e-3) / 1e12 if a_ms > 0 else None
     line = {
         "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": n_warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": workload_config(args),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
@@ -394,24 +732,41 @@ def run_ours(args):
                      "kernel": "gemm_kernel (tcgen05 linear layers of FiD-base / Contriever-base, fused epilogues)",
                      "kernel_ms_per_step": g_ms, "kernel_launches_per_step": g_n, "algorithmic_flops_per_step": g_flops,
                      "kernel_share_of_step": g_ms / ms_per_step if ms_per_step else None,
-                     "attention_kernel": {"ms_per_step": a_ms, "launches_per_step": a_n,
-                                          "achieved_tflops": a_flops / (a_ms * 1e-3) / 1e12 if a_ms > 0 else None,
+                     "attention_kernel": {"ms_per_step": a_ms, "launches_per_step": a_n, "achieved_tflops": a_tflops,
+                                          "frac_of_tensor_peak": a_tflops / peak if (a_tflops and peak) else None,
                                           "share_of_step": a_ms / ms_per_step if ms_per_step else None},
+                     "mips_scan": mips.get("roofline"),
                      "model_flops_utilisation": FID_FLOPS_PER_QUERY * B / (ms_per_step * 1e-3) / 1e12 / peak},
         "e2e": {"value": B * world / (e2e_ms * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
-                "call": "Contriever.forward -> DistributedIndex.search_device -> FiD.forward (pinned host token ids in, "
-                        "loss + retrieved ids / scores out)"},
+                "call": "query strings -> Atlas.retriever_tokenize / reader_tokenize -> Atlas.retrieve (Contriever.forward + "
+                        "DistributedIndex.search_knn incl. passage dicts) -> Atlas.reader_passage_tokens (device token "
+                        "bank) -> Atlas.compute_reader_loss_and_logits (loss.item())"},
+        "parity_check": parity,
         "gpu_launches": int(launches_eager) * args.steps if launches_eager else 0,
         "gpu_launches_note": "kernels per step counted on an eager step; the timed steps replay the reader's launches "
                              "from a CUDA graph",
         "clocks": clocks.summary(),
         "mips": mips,
+        "generate": generate,
         "train": train,
         "refresh": refresh,
     }
+    if not args.no_gpu_reference and world == 1:
+        try:
+            gref = gpu_reference_leg(args, index._bank, dev)
+            if "value" in gref:
+                gref["ours_over_reference_e2e"] = line["e2e"]["value"] / gref["value"]
+                m = gref.get("search_256q_flat_fp16")
+                if m and mips.get("value"):
+                    m["ours_over_reference"] = mips["value"] / m["queries_per_s"]
+            line["gpu_reference"] = gref
+        except Exception as e:
+            line["gpu_reference"] = {"error": repr(e)[:300]}
     if not args.no_cpu_baseline and world == 1:
-        leg = cpu_reference_leg(B, args.rows)
+        del index._bank
+        torch.cuda.empty_cache()
+        leg = cpu_reference_leg(args.rows, budget_s=30.0, max_steps=1, warmup=0)
         line["cpu_baseline"] = {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")}
     emit(line)
     if world > 1:

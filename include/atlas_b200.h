@@ -154,6 +154,40 @@ int atlas_b200_bert_embed_ln(const int64_t* input_ids, const int64_t* token_type
 int atlas_b200_masked_mean_pool(const void* x, const int64_t* mask, void* out, int64_t ld_out, int32_t batch,
                                 int32_t L, int32_t H, int32_t is_bf16, void* stream);
 
+/* Single-token decode attention of FiD.generate (csrc/decode.cu; reference: transformers 4.18 `generate` with use_cache
+ * through src/atlas.py:592-619, T5Attention.forward with past_key_value src/modeling_t5.py:418-531):
+ *  decode_cross_attention  q [B, H*64] (one new token per sequence) against the cross K | V rows kv [B*Lk, ldkv] projected once
+ *      per generation; grid = (ceil(Lk / chunk), H, B); writes un-normalised fp32 partials o_partial [B*chunks, H*64] and
+ *      (max, sum) ml_partial [B*chunks, H, 2] for atlas_b200_attention_combine(_ex) with Lq = 1, splits = chunks.
+ *      HBM-bound: every K / V byte is read once per step (Lk * 2 * H*64 * 2 B per query and layer).
+ *  decode_self_attention   appends the new token's K | V (columns H*64.. of qkv [B, 3*H*64]) to cache [B, Tmax, 2*H*64] at
+ *      row *t_dev and attends over keys 0..*t_dev with bias_delta [H, 2*Tmax-1] (T5 relative bias by offset, NULL = none).
+ *      The step index lives in DEVICE memory so that one captured CUDA graph serves every step.
+ *  decode_argmax           greedy pick (lowest index among ties, EOS banned while *t_dev + 1 < min_length, finished rows
+ *      emit pad_id): seq[b, *t_dev + 1] = tok_in[b] = next; done[b] |= next == eos; then *t_dev += 1. */
+int atlas_b200_decode_cross_attention(const void* q, int64_t ldq, const void* kv, int64_t ldkv, int32_t k_col0,
+                                      int32_t v_col0, const float* add_mask, int32_t B, int32_t H, int32_t Lk,
+                                      int32_t chunk, float scale, float* o_partial, float* ml_partial, int32_t is_bf16,
+                                      void* stream);
+int atlas_b200_decode_self_attention(const void* qkv, int64_t ldqkv, void* cache, int32_t Tmax, const int32_t* t_dev,
+                                     const float* bias_delta, float scale, void* out, int64_t ldo, int32_t B, int32_t H,
+                                     int32_t is_bf16, void* stream);
+int atlas_b200_decode_argmax(const void* logits, int64_t ld, int32_t V, int64_t* seq, int64_t ld_seq, int64_t* tok_in,
+                             uint8_t* done, int32_t* t_dev, int32_t eos_id, int32_t pad_id, int32_t min_length, int32_t B,
+                             int32_t is_bf16, void* stream);
+
+/* Reader-input assembly from a device-resident passage token bank.  Replaces the per-step host work of
+ * Atlas.tokenize_passages (src/atlas.py:261-280: bsz * n_context string formats + tokenizer calls, then H2D of
+ * [bsz, n, L] int64 ids + mask):
+ *   out_ids[b, j, :]  = (query_ids[b, :query_lens[b]] ++ bank_ids[rows[b*n + j], :bank_lens[..]])[: L-1] ++ [eos_id],
+ *                       padded with pad_id;  out_mask[b, j, t] = 1 on the token positions (bool bytes).
+ * rows[.] < 0 is the "" padding passage of encode_passages (src/atlas.py:26-39): EOS only.  bank_ids int32
+ * [bank_rows, bank_ld], bank_lens int32 [bank_rows]; query_ids int64 [batch, ldq] (NULL = no query part). */
+int atlas_b200_splice_tokens(const int32_t* bank_ids, const int32_t* bank_lens, int64_t bank_ld, int64_t bank_rows,
+                             const int64_t* rows, const int64_t* query_ids, const int32_t* query_lens, int64_t ldq,
+                             int32_t batch, int32_t n_ctx, int32_t L, int32_t eos_id, int32_t pad_id, int64_t* out_ids,
+                             uint8_t* out_mask, void* stream);
+
 /* Fused multi-head attention, head_dim 64, Lk <= 512 keys per segment (csrc/attention.cu):
  *   O[b,i,h,:] = softmax_j( scale*Q[b,i,h].K[b,j,h] + bias_delta[h, j-i+Lq-1] + add_mask[b,j] (+causal) ) V[b,j,h,:]
  * q / k / v point at row-major [B*L, ld] 16-bit buffers (e.g. the fused QKV projection output); head h

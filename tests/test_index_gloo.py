@@ -29,16 +29,18 @@ def _make_cpu_index_class():
         def _device():
             return torch.device("cpu")
 
-        def _local_search(self, allqueries, topk):
+        def _local_search(self, allqueries, topk, exhaustive=False):
             bank = self._bank.numpy()
             s = mips_oracle.scores_fp16(allqueries.float().numpy(), bank)
             v, local = mips_oracle.canonical_topk(s, topk)
-            return torch.from_numpy(v), torch.from_numpy(self._id_base + self._id_stride * local)
+            status = torch.zeros(1, dtype=torch.int32)     # the device overflow flag of the fast path (never set here)
+            return torch.from_numpy(v), torch.from_numpy(self._id_base + self._id_stride * local), status
 
         def _merge(self, blob_all, ids_off, world, nq_total, topk, q_begin, nq_out):
             nb = nq_total * topk
             vs = torch.stack([blob_all[w, : nb * 2].view(torch.float16).view(nq_total, topk) for w in range(world)])
-            ids = torch.stack([blob_all[w, ids_off:].view(torch.int64).view(nq_total, topk) for w in range(world)])
+            ids = torch.stack([blob_all[w, ids_off:ids_off + nb * 8].view(torch.int64).view(nq_total, topk)
+                               for w in range(world)])
             out_v = np.empty((nq_out, topk), np.float16)
             out_i = np.empty((nq_out, topk), np.int64)
             for j in range(nq_out):
@@ -51,7 +53,7 @@ def _make_cpu_index_class():
     return OracleBackedIndex
 
 
-def _worker(rank, world, name, port, tmpdir, store_mode):
+def _worker(rank, world, name, port, tmpdir, store_mode, capacity=None):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -69,6 +71,7 @@ def _worker(rank, world, name, port, tmpdir, store_mode):
         off = np.cumsum([0] + nq_per_rank)
         Index = _make_cpu_index_class()
         index = Index()
+        index.max_queries_per_rank = capacity        # fixed per-rank capacity: no size exchange in front of the gather
         index.init_embeddings(synth.make_passages(n, rank, world))
         rows = mips_oracle.shard_rows(n, rank, world)
         # the reference's write pattern: index.embeddings[:, a:b] = emb.T   (src/atlas.py:79)
@@ -108,12 +111,32 @@ def _worker(rank, world, name, port, tmpdir, store_mode):
         torch.distributed.destroy_process_group()
 
 
-@pytest.mark.parametrize("name,world,store", [("w2_grid", 2, "shm"), ("w4_grid_empty_rank", 4, "shm"),
-                                              ("w2_grid", 2, "exchange")])
-def test_search_knn_host_logic_gloo(name, world, store):
-    port = 29710 + world + (7 if store == "exchange" else 0)
+@pytest.mark.parametrize("name,world,store,capacity", [("w2_grid", 2, "shm", None), ("w4_grid_empty_rank", 4, "shm", None),
+                                                       ("w2_grid", 2, "exchange", None),
+                                                       ("w4_grid_empty_rank", 4, "shm", 64), ("w2_grid", 2, "shm", 64)])
+def test_search_knn_host_logic_gloo(name, world, store, capacity):
+    port = 29710 + world + (7 if store == "exchange" else 0) + (11 if capacity else 0)
     with tempfile.TemporaryDirectory() as tmp:
-        mp.spawn(_worker, args=(world, name, port, tmp, store), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, name, port, tmp, store, capacity), nprocs=world, join=True)
+
+
+def test_capacity_overflow_raises():
+    """More local queries than `max_queries_per_rank` is a configuration error, not a silent truncation."""
+    from atlas_b200._lib import AtlasB200Error
+
+    Index = _make_cpu_index_class()
+    index = Index()
+    index.max_queries_per_rank = 2
+    index._bank = torch.zeros(8, 768, dtype=torch.float16)
+    import atlas_b200.dist_utils as du
+
+    old = du.get_world_size
+    du.get_world_size = lambda: 2
+    try:
+        with pytest.raises(AtlasB200Error):
+            index.search_device(torch.zeros(3, 768), 4)
+    finally:
+        du.get_world_size = old
 
 
 def test_single_rank_host_logic():
