@@ -112,6 +112,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
     }
 }
 
+// Call-free variant for kernels that re-partition registers with setmaxnreg: a function call (the printf diagnostic
+// above) makes ptxas allocate EVERY region of such a kernel under the smallest setmaxnreg value.  Same bounded spin,
+// the trap carries no message.
+__device__ __forceinline__ void mbar_wait_nocall(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins == AB_WATCHDOG_SPINS) __trap();
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // TMA
 // ---------------------------------------------------------------------------------------------

@@ -250,7 +250,7 @@ int atlas_b200_decode_cross_attention(const void* q, int64_t ldq, const void* kv
     AB_REQUIRE(chunks <= 65535 && H <= 65535 && B <= 65535, "decode_cross_attention: grid too large");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     dim3 grid(chunks, H, B);
-    abh::prof_begin(s, abh::PROF_ATTENTION);
+    abh::prof_begin(s, abh::PROF_DECODE_CROSS);
     if (is_bf16)
         dec::decode_cross_attention_kernel<true><<<grid, dec::CROSS_THREADS, 0, s>>>(
             static_cast<const uint16_t*>(q), ldq, static_cast<const uint16_t*>(kv), ldkv, k_col0, v_col0, add_mask, Lk, chunk,
@@ -259,7 +259,7 @@ int atlas_b200_decode_cross_attention(const void* q, int64_t ldq, const void* kv
         dec::decode_cross_attention_kernel<false><<<grid, dec::CROSS_THREADS, 0, s>>>(
             static_cast<const uint16_t*>(q), ldq, static_cast<const uint16_t*>(kv), ldkv, k_col0, v_col0, add_mask, Lk, chunk,
             scale, o_partial, ml_partial, H);
-    abh::prof_end(s, abh::PROF_ATTENTION, 4.0 * B * H * static_cast<double>(Lk) * dec::D);
+    abh::prof_end(s, abh::PROF_DECODE_CROSS, 4.0 * B * H * static_cast<double>(Lk) * dec::D);   // = K | V bytes read
     abh::count_launch();
     AB_CUDA_CHECK(cudaGetLastError());
     return ATLAS_B200_OK;

@@ -774,6 +774,75 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def generate_leg(args, atlas, bank_tokens, index, q_enc, rq_ids, rq_lens, dev, world, L, barrier_sync, max_over_ranks,
+                 reps=3):
+    """Greedy generation (`Atlas.generate` path, src/atlas.py:592-619) with the KV-cached decode (csrc/decode.cu): per GPU
+    `batch` queries x 40 retrieved passages, `TARGET_LEN` tokens (min_length = max_length so every run decodes the same
+    number of steps).  Reports generated tokens/s over all ranks, the time of one decode step (graph replay) and the
+    cross-attention decode kernel against the HBM roofline: bytes = batch * 15 360 keys * (K + V) 2 * 768 * 2 B * 12 layers
+    per step, every byte read once."""
+    import ctypes
+
+    import torch
+
+    B = args.batch
+    reader = atlas.reader
+    with torch.no_grad():
+        q_emb = atlas.retriever(q_enc["input_ids"], q_enc["attention_mask"], is_passages=False)
+        _, gids, _ = index.search_device(q_emb, TOPK, return_status=True)
+        tok = bank_tokens.splice(gids, TEXT_LEN, rq_ids, rq_lens)
+    ids, mask = tok["input_ids"].view(B, -1), tok["attention_mask"].view(B, -1)
+    reader.encoder.config.n_context, reader.encoder.config.bsz = N_DOCS, B
+
+    def run(n_tokens):
+        return reader.generate(input_ids=ids, attention_mask=mask, max_length=n_tokens, min_length=n_tokens)
+
+    def timed(n_tokens):
+        run(n_tokens)
+        barrier_sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            seq = run(n_tokens)
+        e1.record()
+        barrier_sync()
+        return max_over_ranks(e0.elapsed_time(e1)) / reps, seq
+
+    ms_full, seq = timed(TARGET_LEN)
+    ms_short, _ = timed(2)
+    assert seq.shape == (B, TARGET_LEN)
+    step_ms = (ms_full - ms_short) / (TARGET_LEN - 2)
+    # the cross-attention decode kernel alone (eager steps bracketed with CUDA events inside the library)
+    reader.cuda_graphs = False
+    try:
+        run(4)
+        torch.cuda.synchronize()
+        L.atlas_b200_profile_enable(5)
+        run(4)
+        torch.cuda.synchronize()
+        kms, kn = ctypes.c_double(0), ctypes.c_int32(0)
+        L.atlas_b200_profile_collect(ctypes.byref(kms), ctypes.byref(kn))
+        L.atlas_b200_profile_enable(0)
+    finally:
+        reader.cuda_graphs = True
+    peak, peak_src = peaks("hbm")
+    c = reader.config
+    bytes_per_launch = B * N_DOCS * TEXT_LEN * 2 * c.num_heads * 64 * 2
+    k_ms = kms.value / max(1, kn.value)
+    achieved = bytes_per_launch / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    return {"metric": "greedy generation tokens/sec (FiD-base, n_docs 40, KV-cached decode, encoder + cross K|V once)",
+            "value": B * world * (TARGET_LEN - 1) / (ms_full * 1e-3), "unit": "tokens/s", "ms_per_generate": ms_full,
+            "queries_per_generate": B * world, "tokens_per_query": TARGET_LEN - 1, "ms_encoder_and_first_step": ms_short,
+            "ms_per_decode_step": step_ms, "decode_steps_per_s": 1e3 / step_ms if step_ms > 0 else None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak if peak else None, "peak_source": peak_src,
+                         "kernel": "decode_cross_attention_kernel (one new token against the cached cross K|V)",
+                         "kernel_ms_per_launch": k_ms, "launches_timed": kn.value,
+                         "algorithmic_bytes_per_launch": bytes_per_launch,
+                         "step_bytes_all_layers": bytes_per_launch * c.num_decoder_layers,
+                         "step_level_GBps": bytes_per_launch * c.num_decoder_layers / (step_ms * 1e-3) / 1e9 if step_ms > 0 else None}}
+
+
 def refresh_leg(args, retriever, index, dev, world, L, barrier_sync, max_over_ranks, steps=5, warmup=2):
     """Index refresh (`Atlas.build_index`, src/atlas.py:61-88): one embedder batch of 512 synthetic passages (lengths
     U[64, 192] tokens, padded to the longest like the reference's tokenizer call) through Contriever-base with fp16
@@ -897,15 +966,16 @@ def mips_leg(args, index, dev, world, rank, L, barrier_sync, max_over_ranks):
     q_host_local = q_host[rank * per:(rank + 1) * per].contiguous().pin_memory() if world > 1 else q_host
     q_dev_local = q_host_local.to(dev)
     for _ in range(warmup):
-        index.search_device(q_dev_local, TOPK)
+        index.search_device(q_dev_local, TOPK, return_status=True)
     L.atlas_b200_profile_enable(1)
     barrier_sync()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        index.search_device(q_dev_local, TOPK)
+        _, _, st = index.search_device(q_dev_local, TOPK, return_status=True)     # no host synchronisation
     e1.record()
     barrier_sync()
+    assert int(st.item()) == 0, "fast search path overflowed in the MIPS leg"
     total_ms = max_over_ranks(e0.elapsed_time(e1))
     kms, kn = ctypes.c_double(0), ctypes.c_int32(0)
     L.atlas_b200_profile_collect(ctypes.byref(kms), ctypes.byref(kn))

@@ -28,12 +28,14 @@ def main():
     index.init_embeddings(synth.make_passages(n, rank, world))
     rows = mips_oracle.shard_rows(n, rank, world)
     index.embeddings[:, :] = torch.from_numpy(bank[rows]).T.cuda()
-    for _ in range(2):
-        docs, scores = index.search_knn(torch.from_numpy(qs[rank]).cuda(), k)
-    ids = np.array([[int(d["id"]) for d in row] for row in docs], dtype=np.int64).reshape(-1, k)
-    vals = np.array(scores, dtype=np.float32).reshape(-1, k).astype(np.float16)
-    assert np.array_equal(ids, want[rank][1]), f"rank {rank}: ids differ"
-    assert np.array_equal(vals.view(np.uint16), want[rank][0].view(np.uint16)), f"rank {rank}: scores differ"
+    for capacity in (None, 16):          # size-exchange protocol, then the fixed per-rank capacity (no host sync)
+        index.max_queries_per_rank = capacity
+        for _ in range(2):
+            docs, scores = index.search_knn(torch.from_numpy(qs[rank]).cuda(), k)
+        ids = np.array([[int(d["id"]) for d in row] for row in docs], dtype=np.int64).reshape(-1, k)
+        vals = np.array(scores, dtype=np.float32).reshape(-1, k).astype(np.float16)
+        assert np.array_equal(ids, want[rank][1]), f"rank {rank}: ids differ (capacity {capacity})"
+        assert np.array_equal(vals.view(np.uint16), want[rank][0].view(np.uint16)), f"rank {rank}: scores differ"
     index._reset_store()
     dist.barrier()
     dist.destroy_process_group()

@@ -137,3 +137,52 @@ def test_attention_matches_fp32_reference(dev, dtype, B, H, L, mode):
     assert float(err.max()) <= tol * max(1.0, float(ref.abs().max())), float(err.max())
     # valid rows only matter, but every row must be finite
     assert torch.isfinite(out.float()).all()
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("B,H,L,mode", [(3, 12, 384, "nomask"), (2, 4, 200, "causal"), (2, 12, 384, "ramp"),
+                                        (3, 12, 256, "bert_nomask"), (37, 12, 384, "t5enc"), (2, 12, 480, "t5enc")])
+def test_attention_lanes_kernel_cases(dev, dtype, B, H, L, mode):
+    """The three-lane kernel (csrc/attention_lanes.cu, >= 2 query tiles per segment) on the cases the generic test does not
+    reach: no key mask at all (the bench's shape), causal + bias with several query tiles, a bias RAMP that makes every
+    later key block exceed the lazy reference maximum by more than 2^8 (the in-place rescale of O runs on every block),
+    more (segment, head) items than SMs x 3 with the bias table changing inside a CTA's item range, and 5 key blocks."""
+    from atlas_b200 import ops
+
+    g = torch.Generator(device="cpu").manual_seed(B * 1000 + L + len(mode))
+    bert = mode.startswith("bert")
+    qkv = (torch.randn(B * L, 3 * H * 64, generator=g) * (0.35 if bert else 0.12)).to(dtype).to(dev)
+    add_mask, bias, scale, causal = None, None, 1.0, 0.0
+    if mode in ("t5enc", "ramp", "causal"):
+        lens = torch.randint(max(1, L // 3), L + 1, (B,), generator=g)
+        add_mask = ((1.0 - (torch.arange(L)[None] < lens[:, None]).float()) * -10000.0).to(dev)
+    if bert:
+        scale = 1.0 / 8.0
+    else:
+        bias = (torch.randn(H, 2 * L - 1, generator=g) * 0.5)
+        if mode == "ramp":
+            bias = bias + 0.15 * torch.arange(2 * L - 1)[None, :].float()      # +14 (natural log units) per 96-key block
+        bias = bias.to(dev)
+    if mode == "causal":
+        causal = -10000.0
+    out, lse = ops.attention(qkv, 0, qkv, H * 64, qkv, 2 * H * 64, B, H, L, L, add_mask=add_mask, bias_delta=bias,
+                             scale=scale, causal_value=causal, return_lse=True)
+    ref = _attn_ref(qkv, B, H, L, add_mask, bias, scale, causal)
+    err = (out.float() - ref).abs()
+    tol = 2e-3 if dtype == torch.float16 else 1.2e-2
+    assert torch.isfinite(out.float()).all()
+    assert float(err.max()) <= tol * max(1.0, float(ref.abs().max())), float(err.max())
+    # the saved log-sum-exp (backward pass input) against the fp32 scores
+    d = 64
+    q = qkv[:, : H * d].float().view(B, L, H, d).permute(0, 2, 1, 3)
+    k = qkv[:, H * d: 2 * H * d].float().view(B, L, H, d).permute(0, 2, 1, 3)
+    s = torch.matmul(q, k.transpose(-1, -2)) * scale
+    if bias is not None:
+        idx = torch.arange(L, device=dev)[None, :] - torch.arange(L, device=dev)[:, None] + (L - 1)
+        s = s + bias[:, idx][None]
+    if add_mask is not None:
+        s = s + add_mask[:, None, None, :]
+    if causal != 0.0:
+        i = torch.arange(L, device=dev)
+        s = s + (i[None, :] > i[:, None]).float() * causal
+    assert float((lse - torch.logsumexp(s, dim=-1)).abs().max()) <= 2e-3
