@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--rows", type=int, default=N_LOCAL, help="passages per GPU (default: the BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true")
+    ap.add_argument("--no-xl", action="store_true", help="skip the Atlas-xl training leg (BASELINE configs[4])")
     ap.add_argument("--ref-budget-s", type=float, default=150.0,
                     help="--impl reference: wall-clock budget of the timed CPU steps (each step = one query)")
     ap.add_argument("--profile-step", action="store_true",
@@ -697,6 +698,16 @@ def run_ours(args):
     except Exception as e:   # the headline line must survive a failure of this supplementary leg
         train = {"error": repr(e)[:300]}
 
+    # ---------------- BASELINE configs[4]: Atlas-xl retrieve + forward + backward + distillation loss ----------------
+    if args.no_xl:
+        xl = {"skipped": "--no-xl"}
+    else:
+        try:
+            xl = xl_train_leg(args, atlas, index, bank_tokens, dev, world, rank, L, barrier_sync, max_over_ranks)
+        except Exception as e:
+            xl = {"error": repr(e)[:300]}
+        index.max_queries_per_rank = B
+
     # ---------------- index refresh in place (BASELINE configs[2]: re-embed the local shard), one embedder batch -------
     try:
         refresh = refresh_leg(args, contriever, index, dev, world, L, barrier_sync, max_over_ranks)
@@ -750,6 +761,7 @@ def run_ours(args):
         "mips": mips,
         "generate": generate,
         "train": train,
+        "train_xl": xl,
         "refresh": refresh,
     }
     if not args.no_gpu_reference and world == 1:
@@ -841,6 +853,88 @@ def generate_leg(args, atlas, bank_tokens, index, q_enc, rq_ids, rq_lens, dev, w
                          "algorithmic_bytes_per_launch": bytes_per_launch,
                          "step_bytes_all_layers": bytes_per_launch * c.num_decoder_layers,
                          "step_level_GBps": bytes_per_launch * c.num_decoder_layers / (step_ms * 1e-3) / 1e9 if step_ms > 0 else None}}
+
+
+def xl_train_leg(args, atlas_base, index, bank_tokens, dev, world, rank, L, barrier_sync, max_over_ranks, steps=2, warmup=1):
+    """BASELINE configs[4]: Atlas-xl (T5-v1.1-xl dims: d 2048, 32 heads, d_ff 5120, 24 + 24 layers, n_docs 40, text_maxlength
+    384) retrieve + reader forward + backward + retriever distillation (`Atlas.forward(train_retriever=True)`,
+    gold_score_mode ppmean, src/atlas.py:399-550, dropout 0), per GPU 1 query per step, gradient checkpointing on both
+    models, followed at N > 1 by one NCCL all-reduce of the flattened gradients (what DDP does in train.py).  Reader input
+    tokens/s (B * n_docs * text_maxlength per step, SURVEY.md §8d C5's unit) over all ranks."""
+    import ctypes
+
+    import torch
+    import torch.distributed as dist
+
+    from atlas_b200.atlas import Atlas
+    from atlas_b200.fid import FiD, T5ConfigLite
+    from atlas_b200.retrievers import BertConfigLite, Contriever, DualEncoderRetriever
+
+    torch.manual_seed(1)
+    with torch.device(dev):
+        reader = FiD(T5ConfigLite(d_model=2048, d_ff=5120, num_layers=24, num_decoder_layers=24, num_heads=32))
+        contriever = Contriever(BertConfigLite())
+    reader = reader.to(torch.bfloat16).train()
+    contriever = contriever.to(torch.bfloat16).train()
+    opt = bench_opt(1)
+    opt.use_gradient_checkpoint_reader = True
+    opt.use_gradient_checkpoint_retriever = True
+    atlas = Atlas(opt, reader, DualEncoderRetriever(opt, contriever), atlas_base.reader_tokenizer,
+                  atlas_base.retriever_tokenizer).train()
+    atlas.set_token_bank(bank_tokens)
+    index.max_queries_per_rank = 1
+    queries, targets = make_query_strings(1, 100 + rank)
+    params = [p for p in atlas.parameters() if p.requires_grad]
+
+    def step():
+        for p in params:
+            p.grad = None
+        reader_loss, retriever_loss = atlas(index, queries, targets, train_retriever=True, iter_stats={})
+        (reader_loss + retriever_loss).backward()
+        if world > 1:
+            flat = torch.cat([p.grad.reshape(-1) for p in params if p.grad is not None])
+            dist.all_reduce(flat)
+        return reader_loss, retriever_loss
+
+    try:
+        for _ in range(warmup):
+            rl, tl = step()
+        barrier_sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            rl, tl = step()
+        e1.record()
+        barrier_sync()
+        ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+        assert bool(torch.isfinite(rl.float())) and bool(torch.isfinite(tl.float())), "non-finite xl training losses"
+        shares = {}
+        for kind, name in ((2, "gemm"), (3, "attention_fwd"), (4, "attention_bwd")):
+            L.atlas_b200_profile_enable(kind)
+            step()
+            torch.cuda.synchronize()
+            work = L.atlas_b200_profile_work()
+            kms, kn = ctypes.c_double(0), ctypes.c_int32(0)
+            L.atlas_b200_profile_collect(ctypes.byref(kms), ctypes.byref(kn))
+            L.atlas_b200_profile_enable(0)
+            shares[name] = {"ms_per_step": kms.value, "launches_per_step": kn.value,
+                            "achieved_tflops": work / (kms.value * 1e-3) / 1e12 if kms.value > 0 else None,
+                            "share_of_step": kms.value / ms if ms else None}
+        peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
+    finally:
+        for p in params:
+            p.grad = None
+        del atlas, reader, contriever, params
+        torch.cuda.empty_cache()
+    tokens = N_DOCS * TEXT_LEN * world
+    n_reader = 2849.8e6
+    return {"metric": "Atlas-xl training tokens/sec (retrieve + T5-xl FiD forward + backward + ppmean retriever distillation, "
+                      "bf16, dropout 0, checkpointing on)",
+            "value": tokens / (ms * 1e-3), "unit": "tokens/s", "ms_per_step": ms, "steps": steps, "queries_per_step": world,
+            "reader_tokens_per_step": tokens, "reader_loss": float(rl), "retriever_loss": float(tl),
+            "reader_parameters": n_reader, "peak_memory_GiB": peak_mem,
+            "gradient_allreduce": "one NCCL all-reduce of the flattened bf16 gradients" if world > 1 else "none (1 GPU)",
+            "kernels": shares}
 
 
 def refresh_leg(args, retriever, index, dev, world, L, barrier_sync, max_over_ranks, steps=5, warmup=2):

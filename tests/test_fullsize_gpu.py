@@ -136,7 +136,9 @@ def test_untied_dual_encoder_matches_reference(dev, qside):
         assert err <= 3e-2 * max(1.0, np.abs(ref).max()), (name, err)
     loss = (q.float() * p.float()).sum()
     loss.backward()
-    assert abs(float(loss) - float(g[f"loss_{tag}"])) <= 2e-2 * max(1.0, abs(float(g[f"loss_{tag}"])))
+    # sum of 6 x 768 signed products: the budget scales with sum |q . p| (the terms cancel), bf16 activations
+    scale = float(np.abs(g[f"q_emb_{tag}"] * g[f"p_emb_{tag}"]).sum())
+    assert abs(float(loss) - float(g[f"loss_{tag}"])) <= 1e-2 * scale, (float(loss), float(g[f"loss_{tag}"]), scale)
     for tower, mod in (("query", r.query_contriever), ("passage", r.passage_contriever)):
         names = [str(n) for n in g[f"grad_names_{tower}"]]
         norms = g[f"grad_norms_{tower}_{tag}"]
