@@ -139,6 +139,20 @@ def lib():
     L.atlas_b200_decode_argmax.argtypes = [vp, i64, i32, vp, i64, vp, vp, vp, i32, i32, i32, i32, i32, vp]
     L.atlas_b200_splice_tokens.restype = c.c_int
     L.atlas_b200_splice_tokens.argtypes = [vp, vp, i64, i64, vp, vp, vp, i64, i32, i32, i32, i32, i32, vp, vp, vp]
+    u64 = c.c_uint64
+    L.atlas_b200_dropout.restype = c.c_int
+    L.atlas_b200_dropout.argtypes = [vp, i64, vp, i64, vp, i64, i64, i32, f32, u64, u64, i32, vp]
+    L.atlas_b200_dropout_mask.restype = c.c_int
+    L.atlas_b200_dropout_mask.argtypes = [vp, i64, i32, f32, u64, u64, vp]
+    L.atlas_b200_attention_train.restype = c.c_int
+    L.atlas_b200_attention_train.argtypes = [vp, i64, i32, vp, i64, i32, vp, i64, i32, vp, i64, vp, vp, i32, i32, i32, i32,
+                                             f32, f32, i32, vp, vp, vp, f32, u64, u64, i32, vp]
+    L.atlas_b200_attention_bwd_train.restype = c.c_int
+    L.atlas_b200_attention_bwd_train.argtypes = [vp, i64, i32, vp, i64, i32, vp, i64, i32, vp, i64, vp, i64, vp, i64, i32,
+                                                 vp, i64, i32, vp, i64, i32, vp, vp, vp, vp, i32, vp, vp, i32, i32, i32,
+                                                 i32, f32, f32, f32, u64, u64, i32, vp]
+    L.atlas_b200_attention_dropout_mask.restype = c.c_int
+    L.atlas_b200_attention_dropout_mask.argtypes = [vp, i64, i32, f32, u64, u64, vp]
     _lib = L
     return L
 
@@ -185,6 +199,11 @@ EXPORTED_SYMBOLS = [
     "atlas_b200_decode_cross_attention",
     "atlas_b200_decode_self_attention",
     "atlas_b200_decode_argmax",
+    "atlas_b200_dropout",
+    "atlas_b200_dropout_mask",
+    "atlas_b200_attention_dropout_mask",
+    "atlas_b200_attention_train",
+    "atlas_b200_attention_bwd_train",
 ]
 
 

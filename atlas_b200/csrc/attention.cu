@@ -19,6 +19,7 @@
 // tables (double buffered, one item ahead), warps 3-18 softmax + output (four threads per query row = TMEM lane).
 // With <= 384 keys the output of query tile t-1 is written while the tensor pipe runs P.V(t) and S(t+1).
 #include "common.cuh"
+#include "dropout.cuh"
 #include "host_common.h"
 
 #include <math.h>
@@ -59,6 +60,7 @@ struct Params {
     float* o_partial;         // [B*Lq, H*64] fp32 or nullptr
     float* ml_partial;        // [B*Lq, H, 2] fp32
     float* lse_out;           // [B, H, Lq] fp32 row log-sum-exp (natural log) for the backward pass, or nullptr
+    abdrop::Key drop;         // attention-probability dropout (training path, attention_kernel only); thr16 == 0: off
 };
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
@@ -142,6 +144,29 @@ __device__ __forceinline__ float chunk_probs(const uint32_t (&r)[32], uint32_t (
         s0 += e0;
         s1 += e1;
         pk[jj >> 1] = pack2<kBF16>(e0, e1);
+    }
+    return s0 + s1;
+}
+
+// Pass 2 with attention-probability dropout (src/modeling_t5.py:515-516, src/modeling_bert.py:354): the row sum takes every
+// probability, the packed P tile only the kept ones (the 1 / (1 - p) scale is folded into the output normalisation).
+// `R` = (batch * H + h) * Lq + i, `G` = global key column of the chunk / 32 (csrc/dropout.cuh).
+template <bool kBF16>
+__device__ __forceinline__ float chunk_probs_drop(const uint32_t (&r)[32], uint32_t (&pk)[16], float mx, const abdrop::Key& key,
+                                                  uint64_t R, uint32_t G) {
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint32_t w[4];
+        abdrop::attn_words(key, R, G, q, w);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int jj = 8 * t + 2 * q;
+            const float e0 = ex2_approx(__uint_as_float(r[jj]) - mx), e1 = ex2_approx(__uint_as_float(r[jj + 1]) - mx);
+            s0 += e0;
+            s1 += e1;
+            pk[jj >> 1] = pack2<kBF16>(abdrop::keep_lo(key, w[t]) ? e0 : 0.f, abdrop::keep_hi(key, w[t]) ? e1 : 0.f);
+        }
     }
     return s0 + s1;
 }
@@ -333,17 +358,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 float* dst = p.o_partial + (static_cast<size_t>(b) * p.Lq + i) * (static_cast<size_t>(p.H) * D) + h * D +
                              part * OC;
 #pragma unroll
+                const float ik = p.drop.inv_keep;
                 for (int v4 = 0; v4 < OC / 4; ++v4)
                     reinterpret_cast<float4*>(dst)[v4] =
-                        make_float4(__uint_as_float(ro[4 * v4]), __uint_as_float(ro[4 * v4 + 1]),
-                                    __uint_as_float(ro[4 * v4 + 2]), __uint_as_float(ro[4 * v4 + 3]));
+                        make_float4(__uint_as_float(ro[4 * v4]) * ik, __uint_as_float(ro[4 * v4 + 1]) * ik,
+                                    __uint_as_float(ro[4 * v4 + 2]) * ik, __uint_as_float(ro[4 * v4 + 3]) * ik);
                 if (part == 0) {
                     float* ml = p.ml_partial + ((static_cast<size_t>(b) * p.Lq + i) * p.H + h) * 2;
                     ml[0] = mx * (1.0f / LOG2E);
                     ml[1] = sum;
                 }
             } else {
-                const float inv = 1.0f / sum;
+                const float inv = p.drop.inv_keep / sum;
                 if (p.lse_out != nullptr && part == 0)
                     p.lse_out[(static_cast<size_t>(b) * p.H + h) * p.Lq + i] = mx * (1.0f / LOG2E) + __logf(sum);
                 uint4* dst = reinterpret_cast<uint4*>(p.O + (static_cast<size_t>(b) * p.Lq + i) * p.ldo + h * D + part * OC);
@@ -402,7 +428,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                         // P of chunks SPLIT*k .. SPLIT*k+SPLIT-1 lands on the columns of S chunks <= SPLIT*k + SPLIT-1:
                         // every thread of a row must have loaded its chunk of this iteration before any of them stores P
                         pair_bar(lg);
-                        sum += chunk_probs<kBF16>(ra, pk, mx);
+                        if (p.drop.thr16 != 0u) {
+                            const uint64_t R = (static_cast<uint64_t>(b / p.q_div) * p.H + h) * p.Lq + min(i, p.Lq - 1);
+                            const uint32_t G = static_cast<uint32_t>(((b % p.q_div) * p.Lk + c * 32) >> 5);
+                            sum += chunk_probs_drop<kBF16>(ra, pk, mx, p.drop, R, G);
+                        } else {
+                            sum += chunk_probs<kBF16>(ra, pk, mx);
+                        }
                         tmem_st16(lane_addr + c * 16, pk);
                     }
                 }
@@ -874,7 +906,22 @@ int atlas_b200_attention_ex(const void* q, int64_t ldq, int32_t q_col0, const vo
                             const float* bias_delta, int32_t B, int32_t H, int32_t Lq, int32_t Lk, float scale,
                             float causal_value, int32_t q_div, float* o_partial, float* ml_partial, float* lse_out,
                             int32_t is_bf16, void* stream) {
+    return atlas_b200_attention_train(q, ldq, q_col0, k, ldk, k_col0, v, ldv, v_col0, out, ldo, add_mask, bias_delta, B, H, Lq,
+                                      Lk, scale, causal_value, q_div, o_partial, ml_partial, lse_out, 0.f, 0, 0, is_bf16,
+                                      stream);
+}
+
+int atlas_b200_attention_train(const void* q, int64_t ldq, int32_t q_col0, const void* k, int64_t ldk, int32_t k_col0,
+                               const void* v, int64_t ldv, int32_t v_col0, void* out, int64_t ldo, const float* add_mask,
+                               const float* bias_delta, int32_t B, int32_t H, int32_t Lq, int32_t Lk, float scale,
+                               float causal_value, int32_t q_div, float* o_partial, float* ml_partial, float* lse_out,
+                               float dropout_p, uint64_t seed, uint64_t offset, int32_t is_bf16, void* stream) {
     using namespace attn;
+    AB_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "attention: need 0 <= dropout_p < 1 (got %f)", dropout_p);
+    const abdrop::Key drop = abdrop::make_key(dropout_p, seed, offset);
+    const bool dropping = drop.thr16 != 0u;
+    AB_REQUIRE(!dropping || q_div == 1 || Lk % 32 == 0,
+               "attention: dropout over split keys needs a split length that is a multiple of 32 (got %d)", Lk);
     AB_REQUIRE(lse_out == nullptr || o_partial == nullptr, "attention: lse_out is produced by attention_combine in split mode");
     AB_REQUIRE(q_div >= 1 && B % q_div == 0, "attention: q_div must divide the number of key segments");
     AB_REQUIRE((o_partial == nullptr) == (ml_partial == nullptr), "attention: partial outputs come in pairs");
@@ -888,7 +935,7 @@ int atlas_b200_attention_ex(const void* q, int64_t ldq, int32_t q_col0, const vo
     // >= 2 query tiles per (segment, head) (encoder self-attention of FiD / Contriever): the three-lane kernel.
     // ATLAS_B200_ATTN_LANES=0 selects the first-generation kernels for A/B measurements.
     static const int lanes_sel = getenv("ATLAS_B200_ATTN_LANES") != nullptr ? atoi(getenv("ATLAS_B200_ATTN_LANES")) : 1;
-    if (lanes_sel != 0 && o_partial == nullptr && q_div == 1 && Lq > 128 && Lq <= 512 && Lk <= 576) {
+    if (lanes_sel != 0 && !dropping && o_partial == nullptr && q_div == 1 && Lq > 128 && Lq <= 512 && Lk <= 576) {
         cudaStream_t ls = static_cast<cudaStream_t>(stream);
         abh::prof_begin(ls, abh::PROF_ATTENTION);
         int lrc = (lanes_sel == 2 ? atlas_b200_attention_lanes2_launch : atlas_b200_attention_lanes_launch)(
@@ -927,12 +974,14 @@ int atlas_b200_attention_ex(const void* q, int64_t ldq, int32_t q_col0, const vo
     p.o_partial = o_partial;
     p.ml_partial = ml_partial;
     p.lse_out = lse_out;
+    p.drop = drop;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int items = B * H;
     const int grid = items < abh::num_sms() ? items : abh::num_sms();
     abh::prof_begin(s, abh::PROF_ATTENTION);
     static const bool no_split = getenv("ATLAS_B200_ATTN_NO_SPLIT") != nullptr;   // A/B measurements
-    const bool split = ((Lk + 127) / 128) * 128 <= 384 && !no_split;
+    // dropout on the probabilities (training) is implemented in attention_kernel only
+    const bool split = ((Lk + 127) / 128) * 128 <= 384 && !no_split && !dropping;
     const int threads = split ? THREADS_SPLIT : THREADS;
     auto launch = [&](auto kernel, bool& attr_done) -> int {
         if (!attr_done) {

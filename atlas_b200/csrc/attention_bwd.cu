@@ -22,6 +22,7 @@
 // FLOPs per call = 2 * B*H*Lq*Lk*64 * 7 with the forward's lse (S + dP + dQ in the first kernel, S + dP + dV + dK in the
 // second), 8 when it is recomputed.
 #include "common.cuh"
+#include "dropout.cuh"
 #include "host_common.h"
 
 #include <math.h>
@@ -51,6 +52,7 @@ struct Params {
     int lse_given, key_chunks;
     int B, H, Lq, Lk;
     float scale, causal_value;
+    abdrop::Key drop;         // attention-probability dropout of the forward (second-generation kernels only); thr16 == 0: off
 };
 
 // ---- shared-memory tiles: 64 rows x 128 bytes, 16-byte chunks XOR-swizzled by the row ------------------------------
@@ -604,8 +606,31 @@ attn_bwd_dq2_kernel(const Params p) {
                 if (p.causal_value != 0.f && j > min(i, p.Lq - 1)) sc += p.causal_value;
                 if (j >= p.Lk) sc = -INFINITY;
                 const float pr = __expf(sc - lse[half]);
-                acc[nt][e] = pr * (dp[nt][e] - drow[half]);      // dS (0 for padding rows / keys: pr = 0)
+                acc[nt][e] = pr;
             }
+        if (p.drop.thr16 != 0u) {
+            // dropout of the forward: dP reaches the softmax only through the kept probabilities, scaled by 1 / (1 - p).
+            // One Philox call = this thread's eight elements of one row and 32-key group (csrc/dropout.cuh).
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const uint64_t R = (static_cast<uint64_t>(b) * p.H + h) * p.Lq + min(i_lo + half * 8, p.Lq - 1);
+#pragma unroll
+                for (int grp = 0; grp < 2; ++grp) {
+                    uint32_t w[4];
+                    abdrop::attn_words(p.drop, R, static_cast<uint32_t>(kb * 2 + grp), static_cast<uint32_t>(t), w);
+#pragma unroll
+                    for (int tw = 0; tw < 4; ++tw) {
+                        const int nt = grp * 4 + tw;
+                        dp[nt][2 * half] = abdrop::keep_lo(p.drop, w[tw]) ? dp[nt][2 * half] * p.drop.inv_keep : 0.f;
+                        dp[nt][2 * half + 1] = abdrop::keep_hi(p.drop, w[tw]) ? dp[nt][2 * half + 1] * p.drop.inv_keep : 0.f;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[nt][e] *= dp[nt][e] - drow[e >> 1];   // dS (0 for padding rows / keys: pr = 0)
         if (dbias_s != nullptr) {
             // dbias[h, j - i] += dS[i, j]: the 64 x 64 dS tile (16-bit, as the MMAs below consume it) goes through a
             // rotated shared tile, then thread d sums diagonal d - 63 and owns one table entry - no atomics.
@@ -735,8 +760,24 @@ attn_bwd_dkv2_kernel(const Params p) {
         const int base = j_lo - (qb * BN + 2 * t) + p.Lq - 1;         // table offset of (key j_lo, query column 2t)
         const float* ls = lse_s + buf * BN + 2 * t;
         const float* dd = d_s + buf * BN + 2 * t;
+        const bool hi_word = ((j_lo & 31) >> 3) != 0;                 // j_lo % 32 in [0, 8) or [16, 24): words (0, 1) or (2, 3)
+        const uint32_t jsh = static_cast<uint32_t>(j_lo & 1) * 16u;
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt)
+        for (int nt = 0; nt < 8; ++nt) {
+            // the forward's dropout mask at (query i, key j): word (j % 32) / 8 of call (R(i), j / 32, (j % 8) / 2); the two
+            // key rows of this thread (j_lo, j_lo + 8) share the call, the two query columns (e2) need one call each
+            uint32_t u16[2][2] = {{0xFFFFu, 0xFFFFu}, {0xFFFFu, 0xFFFFu}};   // [half][e2]
+            if (p.drop.thr16 != 0u) {
+#pragma unroll
+                for (int e2 = 0; e2 < 2; ++e2) {
+                    const int i = qb * BN + nt * 8 + 2 * t + e2;
+                    const uint64_t R = (static_cast<uint64_t>(b) * p.H + h) * p.Lq + min(i, p.Lq - 1);
+                    uint32_t w[4];
+                    abdrop::attn_words(p.drop, R, static_cast<uint32_t>(j_lo >> 5), static_cast<uint32_t>((j_lo & 7) >> 1), w);
+                    u16[0][e2] = ((hi_word ? w[2] : w[0]) >> jsh) & 0xFFFFu;
+                    u16[1][e2] = ((hi_word ? w[3] : w[1]) >> jsh) & 0xFFFFu;
+                }
+            }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int half = e >> 1, e2 = e & 1;
@@ -746,9 +787,11 @@ attn_bwd_dkv2_kernel(const Params p) {
                 if (p.causal_value != 0.f && j > min(i, p.Lq - 1)) sc += p.causal_value;
                 if (j >= p.Lk) sc = -INFINITY;
                 const float pr = __expf(sc - ls[nt * 8 + e2]);
-                acc[nt][e] = pr;
-                dp[nt][e] = pr * (dp[nt][e] - dd[nt * 8 + e2]);
+                const float km = (u16[half][e2] >= p.drop.thr16) ? p.drop.inv_keep : 0.f;   // thr16 == 0: always 1
+                acc[nt][e] = pr * km;                              // dropped probabilities: dV = Pd^T dO
+                dp[nt][e] = pr * (dp[nt][e] * km - dd[nt * 8 + e2]);
             }
+        }
         mma_p_tile<kBF16>(dvacc, acc, sdO_a, lane);   // dV += P^T dO
         mma_p_tile<kBF16>(dkacc, dp, sQ_a, lane);     // dK += dS^T Q
     }
@@ -782,7 +825,24 @@ int atlas_b200_attention_bwd(const void* q, int64_t ldq, int32_t q_col0, const v
                              const float* bias_delta, float* dbias_delta, float* lse, int32_t lse_given, float* dsum,
                              float* dq_accum, int32_t B, int32_t H, int32_t Lq, int32_t Lk, float scale,
                              float causal_value, int32_t is_bf16, void* stream) {
+    return atlas_b200_attention_bwd_train(q, ldq, q_col0, k, ldk, k_col0, v, ldv, v_col0, out, ldo, dout, lddo, dq, lddq,
+                                          dq_col0, dk, lddk, dk_col0, dv, lddv, dv_col0, add_mask, bias_delta, dbias_delta,
+                                          lse, lse_given, dsum, dq_accum, B, H, Lq, Lk, scale, causal_value, 0.f, 0, 0,
+                                          is_bf16, stream);
+}
+
+int atlas_b200_attention_bwd_train(const void* q, int64_t ldq, int32_t q_col0, const void* k, int64_t ldk, int32_t k_col0,
+                                   const void* v, int64_t ldv, int32_t v_col0, const void* out, int64_t ldo,
+                                   const void* dout, int64_t lddo, void* dq, int64_t lddq, int32_t dq_col0, void* dk,
+                                   int64_t lddk, int32_t dk_col0, void* dv, int64_t lddv, int32_t dv_col0,
+                                   const float* add_mask, const float* bias_delta, float* dbias_delta, float* lse,
+                                   int32_t lse_given, float* dsum, float* dq_accum, int32_t B, int32_t H, int32_t Lq,
+                                   int32_t Lk, float scale, float causal_value, float dropout_p, uint64_t seed,
+                                   uint64_t offset, int32_t is_bf16, void* stream) {
     using namespace attnb;
+    AB_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "attention_bwd: need 0 <= dropout_p < 1 (got %f)", dropout_p);
+    const abdrop::Key drop = abdrop::make_key(dropout_p, seed, offset);
+    AB_REQUIRE(drop.thr16 == 0u || lse_given != 0, "attention_bwd: dropout needs the forward's log-sum-exp (lse_given)");
     AB_REQUIRE(dq_accum == nullptr || (lse_given != 0 && dbias_delta == nullptr),
                "attention_bwd: dq_accum (keys split over CTAs) needs the forward's lse and no dbias");
     AB_REQUIRE(B >= 0 && H > 0 && Lq > 0 && Lk > 0, "attention_bwd: bad shape B=%d H=%d Lq=%d Lk=%d", B, H, Lq, Lk);
@@ -833,9 +893,10 @@ int atlas_b200_attention_bwd(const void* q, int64_t ldq, int32_t q_col0, const v
     p.B = B; p.H = H; p.Lq = Lq; p.Lk = Lk;
     p.scale = scale;
     p.causal_value = causal_value;
+    p.drop = drop;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     static const bool force_v1 = getenv("ATLAS_B200_ATTN_BWD_V1") != nullptr;   // A/B measurements
-    const bool v2 = lse_given != 0 && !force_v1;
+    const bool v2 = lse_given != 0 && (!force_v1 || drop.thr16 != 0u);
     const int smem_dq = v2 ? 7 * TILE_BYTES + 2 * BN * 4 +
                                  static_cast<int>(((bias_delta ? ntab + 2 * BIAS_PAD : 0) + (dbias_delta ? ntab : 0)) * 4)
                            : 4 * TILE_BYTES + static_cast<int>(((bias_delta ? ntab : 0) + (dbias_delta ? ntab : 0)) * 4);
@@ -857,7 +918,7 @@ int atlas_b200_attention_bwd(const void* q, int64_t ldq, int32_t q_col0, const v
     abh::prof_begin(s, abh::PROF_ATTENTION_BWD);
     // experimental tcgen05 kernels: 1 = dQ kernel, 2 = dQ + dK/dV kernels (see the status notes in attention_bwd_tc*.cu)
     static const int tc_level = getenv("ATLAS_B200_ATTN_BWD_TC") ? atoi(getenv("ATLAS_B200_ATTN_BWD_TC")) : 0;
-    const bool use_tc = tc_level >= 1;
+    const bool use_tc = tc_level >= 1 && drop.thr16 == 0u;     // the tcgen05 kernels do not implement dropout
     bool dq_done = false, dkv_done = false;
     if (v2 && use_tc && dq_accum == nullptr) {
         const int rc = atlas_b200_attn_bwd_dq_tc(q, ldq, q_col0, k, ldk, k_col0, v, ldv, v_col0, out, ldo, dout, lddo, dq, lddq,

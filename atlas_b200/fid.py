@@ -15,7 +15,7 @@ tcgen05 GEMM with fused residual and gated-GELU epilogues (modeling_t5.py:281-28
 B*n independent L-token segments with the relative-position bias added on the fly from a [H, 2L-1] table
 (modeling_t5.py:352-416,478-524) - the [B*n, H, L, L] bias / probability tensors are never materialised;
 decoder cross-attention over the n*L concatenated keys as split-KV + combine (fid.py:298-349).
-Not reproduced: dropout (the training path runs without it and warns once), the `isinf` clamps and their three host
+Dropout: counter-based masks inside the kernels (csrc/dropout.cuh).  Not reproduced: the `isinf` clamps and their three host
 syncs per block (modeling_t5.py:657-708).
 """
 import copy
@@ -28,7 +28,7 @@ from torch import nn
 
 from . import grad_ops, ops
 from ._lib import AtlasB200Error
-from .retrievers import HalfCache, _warn_no_dropout
+from .retrievers import HalfCache
 
 
 class T5ConfigLite(SimpleNamespace):
@@ -481,8 +481,12 @@ class FiD(nn.Module):
         return W, G, dt
 
     def _check_trainable(self):
-        if self.training and float(getattr(self.config, "dropout_rate", 0.0) or 0.0) > 0.0:
-            _warn_no_dropout("FiD")
+        return None
+
+    def _dropout_p(self):
+        """config.dropout_rate in training mode (nn.Dropout / F.dropout of src/modeling_t5.py:266,286,310,515,561,597,
+        964,1059), else 0: masks are generated inside the kernels and re-derived in the backward (csrc/dropout.cuh)."""
+        return float(getattr(self.config, "dropout_rate", 0.0) or 0.0) if self.training else 0.0
 
     def _maybe_ckpt(self, fn, *args):
         if getattr(self, "_grad_ckpt", False):
@@ -502,8 +506,16 @@ class FiD(nn.Module):
         S, L = ids.shape
         d, H = c.d_model, c.num_heads
         eps = c.layer_norm_epsilon
-        h = g.embedding(W["shared.weight"], ids)
+        pdrop = self._dropout_p()
+        h = g.dropout(g.embedding(W["shared.weight"], ids), pdrop)
         add_mask = (1.0 - mask.to(torch.float32)) * -10000.0
+
+        def lin_res(x, w, res):
+            # h + dropout(linear(x)) (T5LayerSelfAttention / T5LayerFF); without dropout the add is the GEMM's epilogue
+            if pdrop:
+                return g.dropout(g.linear(x, w), pdrop, residual=res)
+            return g.linear(x, w, None, residual=res)
+
         bias = bias_by_delta(W["encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight"], L, L, True,
                              c.relative_attention_num_buckets)
 
@@ -511,16 +523,16 @@ class FiD(nn.Module):
             p = f"encoder.block.{i}.layer.0."
             n = g.layernorm(h, W[p + "layer_norm.weight"], None, eps, kind=1)
             qkv = g.linear(n, G[p + "SelfAttention.qkv"])
-            ctx = g.self_attention(qkv, S, H, L, add_mask=add_mask, bias_delta=bias, scale=1.0)
-            h = g.linear(ctx, W[p + "SelfAttention.o.weight"], None, residual=h)
+            ctx = g.self_attention(qkv, S, H, L, add_mask=add_mask, bias_delta=bias, scale=1.0, dropout_p=pdrop)
+            h = lin_res(ctx, W[p + "SelfAttention.o.weight"], h)
             p = f"encoder.block.{i}.layer.1."
             n = g.layernorm(h, W[p + "layer_norm.weight"], None, eps, kind=1)
             u = g.linear(n, G[p + "DenseReluDense.wi_01"])
-            return g.linear(g.gated_gelu(u), W[p + "DenseReluDense.wo.weight"], None, residual=h)
+            return lin_res(g.dropout(g.gated_gelu(u), pdrop), W[p + "DenseReluDense.wo.weight"], h)
 
         for i in range(c.num_layers):
             h = self._maybe_ckpt(block, i, h, bias)
-        h = g.layernorm(h, W["encoder.final_layer_norm.weight"], None, eps, kind=1)
+        h = g.dropout(g.layernorm(h, W["encoder.final_layer_norm.weight"], None, eps, kind=1), pdrop)
         return h.view(bsz, -1, d)
 
     def _decode_train(self, WG, decoder_input_ids, enc, enc_mask):
@@ -531,14 +543,27 @@ class FiD(nn.Module):
         d, H = c.d_model, c.num_heads
         Lk = enc.shape[1]
         eps = c.layer_norm_epsilon
-        split = next((s for s in range(min(384, Lk), 63, -1) if Lk % s == 0), None) or \
+        pdrop = self._dropout_p()
+        split = None
+        if pdrop:    # the dropout mask is addressed in 32-key groups over the whole key range (csrc/dropout.cuh)
+            split = next((s for s in range(min(512, Lk) // 32 * 32, 63, -32) if Lk % s == 0), None)
+        split = split or next((s for s in range(min(384, Lk), 63, -1) if Lk % s == 0), None) or \
             next(s for s in range(min(512, Lk), 0, -1) if Lk % s == 0)
         if split < 64 and Lk > 512:
             raise AtlasB200Error(f"n_context*text_maxlength = {Lk} has no divisor in [64, 512] for the split-KV kernel")
         flat = enc.reshape(-1, d)
         if flat.dtype != dt:
             flat = flat.to(dt)
-        h = g.embedding(W["shared.weight"], decoder_input_ids)
+        if pdrop and split % 32 != 0 and split != Lk:
+            raise AtlasB200Error(f"dropout on the cross-attention probabilities needs a key split that is a multiple of 32 "
+                                 f"(n_context*text_maxlength = {Lk} gave {split})")
+        h = g.dropout(g.embedding(W["shared.weight"], decoder_input_ids), pdrop)
+
+        def lin_res(x, w, res):
+            if pdrop:
+                return g.dropout(g.linear(x, w), pdrop, residual=res)
+            return g.linear(x, w, None, residual=res)
+
         bias = bias_by_delta(W["decoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight"], T, T, False,
                              c.relative_attention_num_buckets)
         neg = -1e4 if dt == torch.float16 else -1e9
@@ -548,23 +573,24 @@ class FiD(nn.Module):
             p = f"decoder.block.{i}.layer.0."
             n = g.layernorm(h, W[p + "layer_norm.weight"], None, eps, kind=1)
             qkv = g.linear(n, G[p + "SelfAttention.qkv"])
-            ctx = g.self_attention(qkv, B, H, T, bias_delta=bias, scale=1.0, causal_value=-10000.0)
-            h = g.linear(ctx, W[p + "SelfAttention.o.weight"], None, residual=h)
+            ctx = g.self_attention(qkv, B, H, T, bias_delta=bias, scale=1.0, causal_value=-10000.0, dropout_p=pdrop)
+            h = lin_res(ctx, W[p + "SelfAttention.o.weight"], h)
             p = f"decoder.block.{i}.layer.1."
             n = g.layernorm(h, W[p + "layer_norm.weight"], None, eps, kind=1)
             q = g.linear(n, W[p + "EncDecAttention.q.weight"])
             kv = g.linear(flat, G[p + "EncDecAttention.kv"])
-            ctx, lse = g.cross_attention(q, kv, B, H, T, Lk, add_mask=cross_mask, scale=1.0, split=split, return_lse=True)
+            ctx, lse = g.cross_attention(q, kv, B, H, T, Lk, add_mask=cross_mask, scale=1.0, split=split, return_lse=True,
+                                         dropout_p=pdrop)
             self._record_xattn(q, kv, B, H, T, Lk, lse, cross_mask, layer=i)
-            h = g.linear(ctx, W[p + "EncDecAttention.o.weight"], None, residual=h)
+            h = lin_res(ctx, W[p + "EncDecAttention.o.weight"], h)
             p = f"decoder.block.{i}.layer.2."
             n = g.layernorm(h, W[p + "layer_norm.weight"], None, eps, kind=1)
             u = g.linear(n, G[p + "DenseReluDense.wi_01"])
-            return g.linear(g.gated_gelu(u), W[p + "DenseReluDense.wo.weight"], None, residual=h)
+            return lin_res(g.dropout(g.gated_gelu(u), pdrop), W[p + "DenseReluDense.wo.weight"], h)
 
         for i in range(c.num_decoder_layers):
             h = self._maybe_ckpt(block, i, h, bias, flat)
-        h = g.layernorm(h, W["decoder.final_layer_norm.weight"], None, eps, kind=1)
+        h = g.dropout(g.layernorm(h, W["decoder.final_layer_norm.weight"], None, eps, kind=1), pdrop)
         if getattr(c, "tie_word_embeddings", False):
             raise AtlasB200Error("tied LM head (T5 v1.0) is not supported on the training path (T5 v1.1 is untied)")
         logits = g.linear(h, W["lm_head.weight"])

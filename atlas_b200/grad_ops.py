@@ -13,7 +13,8 @@ What autograd would derive through the reference's modules is implemented by han
   Embedding, BertEmbedSum, MaskedMeanPool, CrossEntropy
 Weights arrive as 16-bit tensors that require grad (the caller derives them from the fp32 / bf16 parameters with
 differentiable casts / concatenations, so autograd routes dW back to the reference-named parameters).
-Dropout is not implemented: the training path computes without it (callers warn once when dropout > 0 is configured).
+Dropout (hidden states: `dropout`; attention probabilities: inside the attention kernels) draws counter-based masks
+from (seed, offset) keys of torch's CUDA generator and re-derives them in the backward (csrc/dropout.cuh).
 """
 import torch
 
@@ -79,9 +80,11 @@ class _SelfAttention(torch.autograd.Function):
     """qkv [B*L, 3*H*64] (q | k | v as written by the fused projection) -> ctx [B*L, H*64]."""
 
     @staticmethod
-    def forward(ctx, qkv, bias_delta, add_mask, B, H, L, scale, causal_value):
+    def forward(ctx, qkv, bias_delta, add_mask, B, H, L, scale, causal_value, dropout_p):
+        ctx.drop = (dropout_p,) + next_dropout_key(qkv.device) if dropout_p else None
         out, lse = ops.attention(qkv, 0, qkv, H * 64, qkv, 2 * H * 64, B, H, L, L, add_mask=add_mask,
-                                 bias_delta=bias_delta, scale=scale, causal_value=causal_value, return_lse=True)
+                                 bias_delta=bias_delta, scale=scale, causal_value=causal_value, return_lse=True,
+                                 dropout=ctx.drop)
         ctx.save_for_backward(qkv, out, bias_delta, add_mask, lse)
         ctx.dims = (B, H, L, scale, causal_value)
         return out
@@ -94,21 +97,23 @@ class _SelfAttention(torch.autograd.Function):
         dbias = ops.attention_bwd(qkv, 0, qkv, H * 64, qkv, 2 * H * 64, out, dout.contiguous(), dqkv, 0, dqkv, H * 64,
                                   dqkv, 2 * H * 64, B, H, L, L, add_mask=add_mask, bias_delta=bias_delta,
                                   need_dbias=bias_delta is not None and _need(ctx, 1), scale=scale,
-                                  causal_value=causal_value, lse=lse)
-        return dqkv, dbias, None, None, None, None, None, None
+                                  causal_value=causal_value, lse=lse, dropout=ctx.drop)
+        return dqkv, dbias, None, None, None, None, None, None, None
 
 
-def self_attention(qkv, B, H, L, add_mask=None, bias_delta=None, scale=1.0, causal_value=0.0):
-    return _SelfAttention.apply(qkv, bias_delta, add_mask, B, H, L, scale, causal_value)
+def self_attention(qkv, B, H, L, add_mask=None, bias_delta=None, scale=1.0, causal_value=0.0, dropout_p=0.0):
+    """dropout_p: nn.Dropout on the attention probabilities (training), inside the kernels."""
+    return _SelfAttention.apply(qkv, bias_delta, add_mask, B, H, L, scale, causal_value, float(dropout_p or 0.0))
 
 
 class _CrossAttention(torch.autograd.Function):
     """q [B*T, H*64], kv [B*Lk, 2*H*64] (k | v) -> ctx [B*T, H*64]; forward = split-KV kernel + combine."""
 
     @staticmethod
-    def forward(ctx, q, kv, add_mask, B, H, T, Lk, scale, split):
+    def forward(ctx, q, kv, add_mask, B, H, T, Lk, scale, split, dropout_p):
+        ctx.drop = (dropout_p,) + next_dropout_key(q.device) if dropout_p else None
         out, lse = ops.cross_attention_split(q, 0, kv, 0, H * 64, B, H, T, Lk, add_mask=add_mask, scale=scale,
-                                             split=split, return_lse=True)
+                                             split=split, return_lse=True, dropout=ctx.drop)
         ctx.save_for_backward(q, kv, out, add_mask, lse)
         ctx.dims = (B, H, T, Lk, scale)
         ctx.mark_non_differentiable(lse)
@@ -121,13 +126,47 @@ class _CrossAttention(torch.autograd.Function):
         dq = torch.empty((B * T, H * 64), dtype=q.dtype, device=q.device)
         dkv = torch.empty_like(kv)
         ops.attention_bwd(q, 0, kv, 0, kv, H * 64, out, dout.contiguous(), dq, 0, dkv, 0, dkv, H * 64, B, H, T, Lk,
-                          add_mask=add_mask, scale=scale, lse=lse, split_keys=Lk > 1024)
-        return dq, dkv, None, None, None, None, None, None, None
+                          add_mask=add_mask, scale=scale, lse=lse, split_keys=Lk > 1024, dropout=ctx.drop)
+        return dq, dkv, None, None, None, None, None, None, None, None
 
 
-def cross_attention(q, kv, B, H, T, Lk, add_mask=None, scale=1.0, split=384, return_lse=False):
-    out, lse = _CrossAttention.apply(q, kv, add_mask, B, H, T, Lk, scale, split)
+def cross_attention(q, kv, B, H, T, Lk, add_mask=None, scale=1.0, split=384, return_lse=False, dropout_p=0.0):
+    out, lse = _CrossAttention.apply(q, kv, add_mask, B, H, T, Lk, scale, split, float(dropout_p or 0.0))
     return (out, lse) if return_lse else out
+
+
+def next_dropout_key(device):
+    """(seed, offset) for one dropout site, drawn from torch's CUDA generator of `device`: `torch.manual_seed` makes a run
+    reproducible and `torch.utils.checkpoint` (which saves / restores the generator state) re-derives the same masks
+    when a block is recomputed in the backward.  No device synchronisation."""
+    gen = torch.cuda.default_generators[device.index if device.index is not None else torch.cuda.current_device()]
+    seed, off = gen.initial_seed(), gen.get_offset()
+    gen.set_offset(off + 4)
+    return seed & 0xFFFFFFFFFFFFFFFF, off
+
+
+class _Dropout(torch.autograd.Function):
+    """y = (residual +) dropout(x) (nn.Dropout on hidden states, training mode); masks re-derived in the backward."""
+
+    @staticmethod
+    def forward(ctx, x, residual, p):
+        ctx.key = next_dropout_key(x.device)
+        ctx.p = p
+        ctx.has_res = residual is not None
+        return ops.dropout(x, p, ctx.key[0], ctx.key[1], residual=residual)
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = dy.contiguous()
+        dx = ops.dropout(dy, ctx.p, ctx.key[0], ctx.key[1]) if _need(ctx, 0) else None
+        return dx, (dy if (ctx.has_res and _need(ctx, 1)) else None), None
+
+
+def dropout(x, p, residual=None):
+    """(residual +) dropout(x) with rate p; p == 0 is the identity (plus the residual add)."""
+    if not p:
+        return x if residual is None else x + residual
+    return _Dropout.apply(x, residual, float(p))
 
 
 class _GatedGelu(torch.autograd.Function):

@@ -253,25 +253,27 @@ def masked_mean_pool(x, mask, out=None):
 
 
 def attention(q, q_col0, k, k_col0, v, v_col0, B, H, Lq, Lk, add_mask=None, bias_delta=None, scale=1.0,
-              causal_value=0.0, out=None, return_lse=False):
+              causal_value=0.0, out=None, return_lse=False, dropout=None):
     """Fused attention reading Q/K/V in place from [B*L, ld] projection buffers (head h at col0 + 64h).
-    return_lse: also return the row log-sum-exp [B, H, Lq] fp32 (saved for the backward pass)."""
+    return_lse: also return the row log-sum-exp [B, H, Lq] fp32 (saved for the backward pass).
+    dropout = (p, seed, offset): dropout on the probabilities (training), mask re-derived by attention_bwd."""
     require_cuda(q, "q")
     if out is None:
         out = torch.empty((B * Lq, H * 64), dtype=q.dtype, device=q.device)
     am = add_mask.float().contiguous() if add_mask is not None else None
     bd = bias_delta.float().contiguous() if bias_delta is not None else None
     lse = torch.empty((B, H, Lq), dtype=torch.float32, device=q.device) if return_lse else None
-    check(lib().atlas_b200_attention_ex(_ptr(q), q.stride(0), q_col0, _ptr(k), k.stride(0), k_col0, _ptr(v), v.stride(0),
-                                        v_col0, _ptr(out), out.stride(0), _ptr(am) if am is not None else None,
-                                        _ptr(bd) if bd is not None else None, B, H, Lq, Lk, float(scale),
-                                        float(causal_value), 1, None, None, _ptr(lse) if lse is not None else None,
-                                        _bf(q), current_stream_ptr()))
+    dp, dseed, doff = dropout if dropout is not None else (0.0, 0, 0)
+    check(lib().atlas_b200_attention_train(_ptr(q), q.stride(0), q_col0, _ptr(k), k.stride(0), k_col0, _ptr(v), v.stride(0),
+                                           v_col0, _ptr(out), out.stride(0), _ptr(am) if am is not None else None,
+                                           _ptr(bd) if bd is not None else None, B, H, Lq, Lk, float(scale),
+                                           float(causal_value), 1, None, None, _ptr(lse) if lse is not None else None,
+                                           float(dp), int(dseed), int(doff), _bf(q), current_stream_ptr()))
     return (out, lse) if return_lse else out
 
 
 def cross_attention_split(q, q_col0, kv, k_col0, v_col0, B, H, Lq, Lk_total, add_mask=None, scale=1.0, split=512,
-                          return_lse=False):
+                          return_lse=False, dropout=None):
     """Attention of Lq (<= 128) queries per batch element over Lk_total keys (FiD decoder cross-attention,
     Lk_total = n_ctx * L): split-KV over segments of `split` keys + combine.  q [B*Lq, ld], kv [B*Lk_total, ld]."""
     require_cuda(q, "q")
@@ -282,10 +284,11 @@ def cross_attention_split(q, q_col0, kv, k_col0, v_col0, B, H, Lq, Lk_total, add
     ml = torch.empty((B * splits * Lq, H, 2), dtype=torch.float32, device=q.device)
     am = add_mask.float().contiguous() if add_mask is not None else None
     dummy = torch.empty((8,), dtype=q.dtype, device=q.device)
-    check(lib().atlas_b200_attention(_ptr(q), q.stride(0), q_col0, _ptr(kv), kv.stride(0), k_col0, _ptr(kv),
-                                     kv.stride(0), v_col0, _ptr(dummy), 8, _ptr(am) if am is not None else None, None,
-                                     B * splits, H, Lq, split, float(scale), 0.0, splits, _ptr(o_part), _ptr(ml), _bf(q),
-                                     current_stream_ptr()))
+    dp, dseed, doff = dropout if dropout is not None else (0.0, 0, 0)
+    check(lib().atlas_b200_attention_train(_ptr(q), q.stride(0), q_col0, _ptr(kv), kv.stride(0), k_col0, _ptr(kv),
+                                           kv.stride(0), v_col0, _ptr(dummy), 8, _ptr(am) if am is not None else None, None,
+                                           B * splits, H, Lq, split, float(scale), 0.0, splits, _ptr(o_part), _ptr(ml),
+                                           None, float(dp), int(dseed), int(doff), _bf(q), current_stream_ptr()))
     out = torch.empty((B * Lq, H * 64), dtype=q.dtype, device=q.device)
     lse = torch.empty((B, H, Lq), dtype=torch.float32, device=q.device) if return_lse else None
     check(lib().atlas_b200_attention_combine_ex(_ptr(o_part), _ptr(ml), B, splits, Lq, H, _ptr(out), out.stride(0),
@@ -393,6 +396,34 @@ def gelu_erf(z, dy=None):
     return out.reshape(z.shape)
 
 
+def dropout(x, p, seed, offset, residual=None):
+    """out = (residual +) dropout(x): keep decisions are a pure function of (seed, offset, position), so calling this on
+    dy with the same (seed, offset) is the backward of the forward call (csrc/dropout.cu)."""
+    require_cuda(x, "x")
+    x2 = _rows2d(x)
+    r2 = _rows2d(residual) if residual is not None else None
+    out = torch.empty_like(x2)
+    check(lib().atlas_b200_dropout(_ptr(x2), x2.stride(0), _ptr(r2) if r2 is not None else None,
+                                   r2.stride(0) if r2 is not None else 0, _ptr(out), out.stride(0), x2.shape[0],
+                                   x2.shape[1], float(p), int(seed), int(offset), _bf(x), current_stream_ptr()))
+    return out.reshape(x.shape)
+
+
+def dropout_mask(M, N, p, seed, offset, device):
+    """The keep mask (uint8 [M, N]) `dropout` applies to an [M, N] tensor with this (seed, offset)."""
+    out = torch.empty((M, N), dtype=torch.uint8, device=device)
+    check(lib().atlas_b200_dropout_mask(_ptr(out), M, N, float(p), int(seed), int(offset), current_stream_ptr()))
+    return out
+
+
+def attention_dropout_mask(B, H, Lq, Lk, p, seed, offset, device):
+    """The keep mask (uint8 [B, H, Lq, Lk]) the attention kernels apply to the probabilities with this (seed, offset)."""
+    out = torch.empty((B, H, Lq, Lk), dtype=torch.uint8, device=device)
+    check(lib().atlas_b200_attention_dropout_mask(_ptr(out), B * H * Lq, Lk, float(p), int(seed), int(offset),
+                                                  current_stream_ptr()))
+    return out
+
+
 def bert_embed_sum(input_ids, token_type_ids, word_emb, type_emb, pos_emb):
     require_cuda(input_ids, "input_ids")
     B, L = input_ids.shape
@@ -456,7 +487,7 @@ def cross_entropy_bwd(logits, labels, lse, gscale):
 
 def attention_bwd(q, q_col0, k, k_col0, v, v_col0, out, dout, dq, dq_col0, dk, dk_col0, dv, dv_col0, B, H, Lq, Lk,
                   add_mask=None, bias_delta=None, need_dbias=False, scale=1.0, causal_value=0.0, lse=None,
-                  split_keys=False):
+                  split_keys=False, dropout=None):
     """Backward of `attention` / `cross_attention_split` (un-split key range).  dq / dk / dv are written in place at
     their column offsets; returns dbias_delta fp32 [H, Lq+Lk-1] (or None).  `lse` = the forward's log-sum-exp
     (return_lse=True) saves the recomputation pass; split_keys (needs lse, no dbias; dq must be a whole contiguous
@@ -474,13 +505,14 @@ def attention_bwd(q, q_col0, k, k_col0, v, v_col0, out, dout, dq, dq_col0, dk, d
         if lse is None or dbias is not None or dq_col0 != 0 or not dq.is_contiguous() or dq.shape[1] != H * 64:
             raise AtlasB200Error("attention_bwd: split_keys needs the forward's lse, no dbias and a contiguous dq")
         accum = torch.zeros((B * Lq, H * 64), dtype=torch.float32, device=q.device)
-    check(lib().atlas_b200_attention_bwd(
+    dp, dseed, doff = dropout if dropout is not None else (0.0, 0, 0)
+    check(lib().atlas_b200_attention_bwd_train(
         _ptr(q), q.stride(0), q_col0, _ptr(k), k.stride(0), k_col0, _ptr(v), v.stride(0), v_col0, _ptr(o2), o2.stride(0),
         _ptr(do2), do2.stride(0), _ptr(dq), dq.stride(0), dq_col0, _ptr(dk), dk.stride(0), dk_col0, _ptr(dv),
         dv.stride(0), dv_col0, _ptr(am) if am is not None else None, _ptr(bd) if bd is not None else None,
         _ptr(dbias) if dbias is not None else None, _ptr(lse_buf), 1 if lse is not None else 0, _ptr(dsum),
-        _ptr(accum) if accum is not None else None, B, H, Lq, Lk, float(scale), float(causal_value), _bf(q),
-        current_stream_ptr()))
+        _ptr(accum) if accum is not None else None, B, H, Lq, Lk, float(scale), float(causal_value), float(dp),
+        int(dseed), int(doff), _bf(q), current_stream_ptr()))
     if accum is not None:
         check(lib().atlas_b200_cast_f32(_ptr(accum), _ptr(dq), accum.numel(), _bf(q), current_stream_ptr()))
     return dbias

@@ -106,13 +106,8 @@ _warned = set()
 
 
 def _warn_no_dropout(who):
-    """The training path has no dropout kernels yet: say so once instead of silently diverging from the reference."""
-    if who not in _warned:
-        _warned.add(who)
-        import warnings
-
-        warnings.warn(f"atlas_b200.{who}: dropout > 0 is configured but the B200 training path runs WITHOUT dropout "
-                      "(not implemented yet); use --dropout 0 for exact agreement with the reference")
+    """Kept for callers of round 1: dropout IS implemented now (grad_ops.dropout / attention dropout_p); nothing to warn."""
+    return None
 
 
 _WEIGHTS_EPOCH = [0]
@@ -277,9 +272,10 @@ class Contriever(nn.Module):
         pd = self.embeddings.word_embeddings.weight.dtype
         # fp32 master parameters train through bf16 activations / gradients (fp16 gradients would need loss scaling)
         dt = pd if pd in (torch.float16, torch.bfloat16) else torch.bfloat16
-        if self.training and max(float(_cfg(c, "hidden_dropout_prob", 0.0) or 0.0),
-                                 float(_cfg(c, "attention_probs_dropout_prob", 0.0) or 0.0)) > 0.0:
-            _warn_no_dropout("Contriever")
+        # nn.Dropout of the reference in training mode (src/modeling_bert.py:246,356,384,463): counter-based masks inside
+        # the kernels, re-derived in the backward (csrc/dropout.cuh)
+        ph = float(_cfg(c, "hidden_dropout_prob", 0.0) or 0.0) if self.training else 0.0
+        pa = float(_cfg(c, "attention_probs_dropout_prob", 0.0) or 0.0) if self.training else 0.0
         W = {n: (p if p.dtype == dt else p.to(dt)) for n, p in self.named_parameters()}
         B, L = input_ids.shape
         H, nh = c.hidden_size, c.num_attention_heads
@@ -289,7 +285,14 @@ class Contriever(nn.Module):
                              -1 if pad is None else int(pad))
         h = g.layernorm(x.view(B * L, H), W["embeddings.LayerNorm.weight"], W["embeddings.LayerNorm.bias"],
                         c.layer_norm_eps, kind=0)
+        h = g.dropout(h, ph)
         add_mask = (1.0 - attention_mask.to(torch.float32)) * -10000.0
+
+        def dense_res(x, w, b, res):
+            # BertSelfOutput / BertOutput: dense -> dropout -> + input (fused into the GEMM epilogue without dropout)
+            if ph:
+                return g.dropout(g.linear(x, w, b), ph, residual=res)
+            return g.linear(x, w, b, residual=res)
 
         def layer(i, h):
             p = f"encoder.layer.{i}."
@@ -297,12 +300,12 @@ class Contriever(nn.Module):
             wqkv = torch.cat([W[a + "query.weight"], W[a + "key.weight"], W[a + "value.weight"]], 0)
             bqkv = torch.cat([W[a + "query.bias"], W[a + "key.bias"], W[a + "value.bias"]], 0)
             qkv = g.linear(h, wqkv, bqkv)
-            ctx = g.self_attention(qkv, B, nh, L, add_mask=add_mask, scale=1.0 / math.sqrt(64))
-            s1 = g.linear(ctx, W[p + "attention.output.dense.weight"], W[p + "attention.output.dense.bias"], residual=h)
+            ctx = g.self_attention(qkv, B, nh, L, add_mask=add_mask, scale=1.0 / math.sqrt(64), dropout_p=pa)
+            s1 = dense_res(ctx, W[p + "attention.output.dense.weight"], W[p + "attention.output.dense.bias"], h)
             h1 = g.layernorm(s1, W[p + "attention.output.LayerNorm.weight"], W[p + "attention.output.LayerNorm.bias"],
                              c.layer_norm_eps, kind=0)
             z = g.linear(h1, W[p + "intermediate.dense.weight"], W[p + "intermediate.dense.bias"])
-            s2 = g.linear(g.gelu_erf(z), W[p + "output.dense.weight"], W[p + "output.dense.bias"], residual=h1)
+            s2 = dense_res(g.gelu_erf(z), W[p + "output.dense.weight"], W[p + "output.dense.bias"], h1)
             return g.layernorm(s2, W[p + "output.LayerNorm.weight"], W[p + "output.LayerNorm.bias"], c.layer_norm_eps,
                                kind=0)
 

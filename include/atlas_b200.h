@@ -322,6 +322,38 @@ int atlas_b200_cross_entropy_bwd(const void* logits, int64_t ld, const int64_t* 
                                  const float* gscale, void* dlogits, int64_t ldd, int32_t rows, int32_t V, int32_t is_bf16,
                                  void* stream);
 
+/* nn.Dropout on 16-bit hidden states in the TRAINING path (src/modeling_t5.py:266,286,310,561,960,1070;
+ * src/modeling_bert.py:222,378,459):  out = (residual +) r16(keep ? x / (1 - p) : 0).  The keep decisions are a pure
+ * function of (seed, offset, element position) - Philox4x32-7, 16-bit uniforms, realised drop rate round(p * 65536) / 65536
+ * (csrc/dropout.cuh) - so the backward of y = dropout(x) is the same call on dy with the same (seed, offset).
+ * atlas_b200_dropout_mask / atlas_b200_attention_dropout_mask export the keep masks (1 byte per element) of the
+ * elementwise layout ([M, N]) and of the attention-probability layout ([B * H * Lq, Lk], see atlas_b200_attention_train)
+ * for the parity tests. */
+int atlas_b200_dropout(const void* x, int64_t ldx, const void* residual, int64_t ldr, void* out, int64_t ldo, int64_t M,
+                       int32_t N, float p, uint64_t seed, uint64_t offset, int32_t is_bf16, void* stream);
+int atlas_b200_dropout_mask(uint8_t* out, int64_t M, int32_t N, float p, uint64_t seed, uint64_t offset, void* stream);
+int atlas_b200_attention_dropout_mask(uint8_t* out, int64_t rows, int32_t Lk, float p, uint64_t seed, uint64_t offset,
+                                      void* stream);
+
+/* atlas_b200_attention_ex with dropout on the attention probabilities (training: src/modeling_t5.py:515-516,
+ * src/modeling_bert.py:354):  O = (keep o softmax(S)) V / (1 - p), the row log-sum-exp is that of the un-dropped softmax.
+ * keep[b, h, i, j] is a function of (seed, offset, (b * H + h) * Lq + i, j) (csrc/dropout.cuh; j = key index over the whole
+ * key range when the keys are split: segment s of `q_div` covers j = s * Lk ..., Lk % 32 == 0 required then);
+ * atlas_b200_attention_bwd_train re-derives the same mask.  dropout_p == 0 is atlas_b200_attention_ex. */
+int atlas_b200_attention_train(const void* q, int64_t ldq, int32_t q_col0, const void* k, int64_t ldk, int32_t k_col0,
+                               const void* v, int64_t ldv, int32_t v_col0, void* out, int64_t ldo, const float* add_mask,
+                               const float* bias_delta, int32_t B, int32_t H, int32_t Lq, int32_t Lk, float scale,
+                               float causal_value, int32_t q_div, float* o_partial, float* ml_partial, float* lse_out,
+                               float dropout_p, uint64_t seed, uint64_t offset, int32_t is_bf16, void* stream);
+int atlas_b200_attention_bwd_train(const void* q, int64_t ldq, int32_t q_col0, const void* k, int64_t ldk, int32_t k_col0,
+                                   const void* v, int64_t ldv, int32_t v_col0, const void* out, int64_t ldo,
+                                   const void* dout, int64_t lddo, void* dq, int64_t lddq, int32_t dq_col0, void* dk,
+                                   int64_t lddk, int32_t dk_col0, void* dv, int64_t lddv, int32_t dv_col0,
+                                   const float* add_mask, const float* bias_delta, float* dbias_delta, float* lse,
+                                   int32_t lse_given, float* dsum, float* dq_accum, int32_t B, int32_t H, int32_t Lq,
+                                   int32_t Lk, float scale, float causal_value, float dropout_p, uint64_t seed,
+                                   uint64_t offset, int32_t is_bf16, void* stream);
+
 /* Measurement hook for bench.py's roofline: while enabled, every launch of ONE kind of kernel is bracketed
  * with CUDA events on its launching stream:
  *   kind 1  the bank sweep of atlas_b200_mips_topk (work = algorithmic bytes swept)
