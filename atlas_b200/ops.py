@@ -455,7 +455,10 @@ def masked_mean_pool_bwd(demb, mask, L, H):
     B = d2.shape[0]
     m = mask.to(torch.int64).contiguous()
     dx = torch.empty((B, L, H), dtype=demb.dtype, device=demb.device)
-    check(lib().atlas_b200_masked_mean_pool_bwd(_ptr(d2), d2.stride(0), _ptr(m), _ptr(dx), B, L, H, _bf(demb),
+    if B > 1 and d2.stride(0) % 2:
+        d2 = d2.clone(memory_format=torch.contiguous_format)
+    ld = d2.stride(0) if B > 1 else H          # a single row: its (arbitrary) stride is never used
+    check(lib().atlas_b200_masked_mean_pool_bwd(_ptr(d2), ld, _ptr(m), _ptr(dx), B, L, H, _bf(demb),
                                                 current_stream_ptr()))
     return dx
 

@@ -150,4 +150,11 @@ def test_untied_dual_encoder_matches_reference(dev, qside):
             else:
                 assert prm.grad is not None, (tower, n)
                 got = float(prm.grad.float().norm())
+                if n.endswith("attention.self.key.bias"):
+                    # softmax is invariant to a per-query shift of the scores: this gradient is identically zero in exact
+                    # arithmetic (the reference's 1e-7 is fp32 rounding noise, ours is bf16 rounding noise of the dS tile);
+                    # it must stay noise-sized next to the query bias of the same layer
+                    qb = float(params[n.replace("key.bias", "query.bias")].grad.float().norm())
+                    assert got <= 0.05 * qb + 1e-4, (tower, n, got, qb)
+                    continue
                 assert abs(got - want) <= 0.08 * want + 1e-4, (tower, n, got, want)

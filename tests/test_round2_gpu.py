@@ -86,18 +86,20 @@ def test_generate_kv_cached_matches_prefix_rerun(dev, dtype):
         a = model.generate(input_ids=ids.to(dev), attention_mask=mask.to(dev), max_length=9, min_length=3)
         b = model.generate(input_ids=ids.to(dev), attention_mask=mask.to(dev), max_length=9, min_length=3, use_cache=False)
         a2 = model.generate(input_ids=ids.to(dev), attention_mask=mask.to(dev), max_length=9, min_length=3)   # graph replay
-    assert torch.equal(a, a2)
     assert a.shape[0] == 2 and a.shape[1] <= 9 and int(a[0, 0]) == 0
-    n = min(a.shape[1], b.shape[1])
     with torch.no_grad():
         tf = model(input_ids=ids.to(dev), attention_mask=mask.to(dev), decoder_input_ids=b[:, :-1], use_cache=False).logits.float()
     top2 = tf.topk(2, dim=-1)[0]
     gap_ok = (top2[..., 0] - top2[..., 1]) > (0.05 if dtype == torch.bfloat16 else 0.01)
-    for bi in range(2):
-        for t in range(1, n):
-            if not bool(gap_ok[bi, t - 1]):
-                break                                  # a near-tie may legitimately fork the greedy chains from here on
-            assert int(a[bi, t]) == int(b[bi, t]), (bi, t, a[bi].tolist(), b[bi].tolist())
+    # the encoder is not bit-reproducible run to run (the fused RMSNorm accumulates each row's sum of squares with fp32
+    # atomics, csrc/gemm.cu), so the first run and the graph replay are held to the same near-tie rule as the two paths
+    for got in (a, a2):
+        n = min(got.shape[1], b.shape[1])
+        for bi in range(2):
+            for t in range(1, n):
+                if not bool(gap_ok[bi, t - 1]):
+                    break                              # a near-tie may legitimately fork the greedy chains from here on
+                assert int(got[bi, t]) == int(b[bi, t]), (bi, t, got[bi].tolist(), b[bi].tolist())
 
 
 def test_generate_with_prefix_constraint(dev):
