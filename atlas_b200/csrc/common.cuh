@@ -157,6 +157,19 @@ __device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint64_t
         : "memory");
 }
 
+// 2-CTA + multicast: the box lands at the same shared-memory offset in every CTA of `cta_mask`; each destination's bytes
+// are counted on the barrier at this offset in the leader of THAT destination's CTA pair.
+__device__ __forceinline__ void tma_load_2d_2sm_mc(const CUtensorMap* map, uint64_t* bar, void* smem_dst, int32_t c0,
+                                                   int32_t c1, uint16_t cta_mask, uint64_t cache_hint) {
+    uint32_t bar_addr = smem_u32(bar) & 0xFEFFFFFFu;
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        ".L2::cache_hint [%0], [%1, {%4, %5}], [%2], %3, %6;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_addr), "h"(cta_mask), "r"(c0), "r"(c1),
+        "l"(cache_hint)
+        : "memory");
+}
+
 __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* smem_dst, int32_t c0,
                                             int32_t c1, int32_t c2, uint64_t cache_hint) {
     asm volatile(

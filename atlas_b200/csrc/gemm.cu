@@ -134,7 +134,14 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint3
 // kTN = true : C[M, N] = A[K, M]^T . W[K, N]: both operands MN-major, i.e. the contraction runs over the ROWS of two
 //              row-major matrices - the weight gradient dW[N_out, K_in] = dY[tokens, N_out]^T . X[tokens, K_in] without
 //              transposing either activation matrix (rows past K are zero-filled by TMA: no padding needed).
-template <bool kBF16, int BLOCK_N, bool kPair, bool kTN>
+// kQuad (with kPair, K-major operands): a cluster of FOUR CTAs = two CTA pairs working on M-adjacent 256 x 256 tiles of the
+//              same column block.  Both pairs need the same W tile, so every CTA fetches only 64 of the 128 W rows its
+//              pair-half consumes and TMA-multicasts them to the CTA with the same rank in the other pair: per 64-wide K
+//              block a CTA pulls 16 KB of A + 8 KB of W from L2 instead of 16 + 16.  The pair kernel is bound by L2 -> SM
+//              throughput (~6.3 KB/clk chip-wide: 148 CTAs x 32 KB per 512-clk K block is already 1.1x that), not by the
+//              tensor pipe (profiles/r02_gemm.md).  Ring stages are shared by the two pairs: a stage is free when BOTH
+//              pairs' MMAs have consumed it (empty barrier counts 2, commits multicast to all four CTAs).
+template <bool kBF16, int BLOCK_N, bool kPair, bool kTN, bool kQuad>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
     using C = Cfg<BLOCK_N, kPair>;
@@ -150,11 +157,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const uint32_t smem_base = (ab::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - ab::smem_u32(smem_raw));
 
-    const uint32_t cta_rank = kPair ? ab::cluster_ctarank() : 0u;
+    static_assert(!kQuad || (kPair && !kTN), "the 4-CTA cluster builds on the K-major pair kernel");
+    constexpr int CLUSTER = kQuad ? 4 : (kPair ? 2 : 1);
+    const uint32_t cluster_rank = kPair ? ab::cluster_ctarank() : 0u;
+    const uint32_t cta_rank = cluster_rank & 1u;                   // rank inside the CTA pair
+    const uint32_t pair_id = kQuad ? (cluster_rank >> 1) : 0u;     // which pair of the cluster
     const bool leader = cta_rank == 0;
-    const int group = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
-    const int num_groups = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
-    constexpr int TILE_M = BLOCK_M * C::CTAS;
+    const int group = static_cast<int>(blockIdx.x) / CLUSTER;
+    const int num_groups = static_cast<int>(gridDim.x) / CLUSTER;
+    constexpr int PAIR_M = BLOCK_M * C::CTAS;                      // rows of one (pair) tile
+    constexpr int TILE_M = PAIR_M * (kQuad ? 2 : 1);               // rows one scheduling group covers per work item
     const int num_m = (p.M + TILE_M - 1) / TILE_M;
     const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
     const int num_tiles = num_m * num_n * p.splits;     // work items: (tile, split), split fastest
@@ -167,7 +179,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
             ab::mbar_init(&full_bar[s], 1);
-            ab::mbar_init(&empty_bar[s], 1);
+            ab::mbar_init(&empty_bar[s], kQuad ? 2 : 1);          // one commit per pair that reads the stage
         }
         for (int b = 0; b < 2; ++b) {
             ab::mbar_init(&tmem_full_bar[b], 1);
@@ -191,7 +203,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             for (int t = group; t < num_tiles; t += num_groups) {
                 const int tile = t / p.splits, split = t % p.splits;
                 const int m_blk = tile / num_n, n_blk = tile % num_n;
-                const int a_row = m_blk * TILE_M + static_cast<int>(cta_rank) * BLOCK_M;
+                const int a_row = m_blk * TILE_M + static_cast<int>(pair_id) * PAIR_M + static_cast<int>(cta_rank) * BLOCK_M;
                 const int b_row = n_blk * BLOCK_N + static_cast<int>(cta_rank) * C::B_ROWS;
                 const int kb0 = split * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
@@ -222,6 +234,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                                 ab::tma_load_2d(&tmap_b, &full_bar[stage], st + C::A_BYTES + j * 8192, b_row + 64 * j,
                                                 kb * BLOCK_K, ab::kEvictNormal);
                         }
+                    } else if constexpr (kQuad) {
+                        // 2 x (A 16 KB + W 2 x 8 KB) land in this pair's shared memory per stage, whoever issued them
+                        if (leader) ab::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+                        ab::tma_load_2d_2sm(&tmap_a, &full_bar[stage], st, kb * BLOCK_K, a_row, ab::kEvictNormal);
+                        // W box = 64 rows: this CTA's quarter of the pair-half, multicast to the same rank of both pairs
+                        ab::tma_load_2d_2sm_mc(&tmap_b, &full_bar[stage], st + C::A_BYTES + pair_id * (64 * BLOCK_K * 2),
+                                               kb * BLOCK_K, b_row + static_cast<int>(pair_id) * 64,
+                                               static_cast<uint16_t>(0x5u << cta_rank), ab::kEvictLast);
                     } else if constexpr (kPair) {
                         // the leader's barrier collects the bytes of BOTH CTAs' boxes
                         if (leader) ab::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
@@ -274,7 +294,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                                                  bdesc0 + ((k * UMMA_K * 2) >> 4), idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
                         }
                     }
-                    if constexpr (kPair) {
+                    if constexpr (kQuad) {
+                        ab::umma_commit_2sm(&empty_bar[stage], 0xF);        // the stage is shared with the other pair
+                    } else if constexpr (kPair) {
                         ab::umma_commit_2sm(&empty_bar[stage], 0x3);
                     } else {
                         ab::umma_commit(&empty_bar[stage]);
@@ -285,7 +307,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                     }
                 }
                 if constexpr (kPair) {
-                    ab::umma_commit_2sm(&tmem_full_bar[buf], 0x3);
+                    ab::umma_commit_2sm(&tmem_full_bar[buf], static_cast<uint16_t>(0x3u << (2 * pair_id)));
                 } else {
                     ab::umma_commit(&tmem_full_bar[buf]);
                 }
@@ -301,7 +323,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             const uint32_t buf = it & 1;
             const int tile = t / p.splits, split = t % p.splits;
             const int m_blk = tile / num_n, n_blk = tile % num_n;
-            const int row = m_blk * TILE_M + static_cast<int>(cta_rank) * BLOCK_M + static_cast<int>(lg * 32 + lane);
+            const int row = m_blk * TILE_M + static_cast<int>(pair_id) * PAIR_M + static_cast<int>(cta_rank) * BLOCK_M +
+                            static_cast<int>(lg * 32 + lane);
             // fused RMSNorm of the A rows: a per-row scale of the accumulator (loaded while the MMAs run)
             const float rscale = (p.row_ss != nullptr && row < p.M)
                                      ? rsqrtf(__ldg(p.row_ss + row) / static_cast<float>(p.K) + p.rs_eps) : 1.0f;
@@ -321,7 +344,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                     __syncwarp();
                     if (lane == 0) {
                         if (leader) ab::mbar_arrive(&tmem_empty_bar[buf]);
-                        else ab::mbar_arrive_cluster(&tmem_empty_bar[buf], 0);   // the leader issues the next MMAs
+                        else ab::mbar_arrive_cluster(&tmem_empty_bar[buf], 2 * pair_id);   // the pair's leader issues the next MMAs
                     }
                 }
                 if (row >= p.M || col0 >= p.N) continue;
@@ -418,19 +441,47 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
 }
 
-template <bool kBF16, int BLOCK_N, bool kPair, bool kTN = false>
+// number of 4-CTA clusters of the quad kernel that can be resident at once (GPC boundaries may leave SMs unused), 0 = unknown
+template <bool kBF16>
+static int quad_clusters() {
+    static int cached = -1;
+    if (cached >= 0) return cached;
+    using C = Cfg<256, true>;
+    auto kernel = gemm_kernel<kBF16, 256, true, false, true>;
+    cached = 0;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess) return cached;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(abh::num_sms() / 4 * 4));
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 4;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) == cudaSuccess && n > 0) cached = n;
+    else (void)cudaGetLastError();
+    return cached;
+}
+
+template <bool kBF16, int BLOCK_N, bool kPair, bool kTN = false, bool kQuad = false>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, cudaStream_t s) {
     using C = Cfg<BLOCK_N, kPair>;
     static bool attr_set = false;
     if (!attr_set) {
-        AB_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<kBF16, BLOCK_N, kPair, kTN>,
+        AB_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<kBF16, BLOCK_N, kPair, kTN, kQuad>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         attr_set = true;
     }
-    const int tile_m = BLOCK_M * C::CTAS;
+    constexpr int CLUSTER = kQuad ? 4 : C::CTAS;
+    const int tile_m = BLOCK_M * CLUSTER;
     const int tiles = ((p.M + tile_m - 1) / tile_m) * ((p.N + BLOCK_N - 1) / BLOCK_N) * p.splits;
-    const int groups_max = abh::num_sms() / C::CTAS;
-    const int grid = (tiles < groups_max ? tiles : groups_max) * C::CTAS;
+    int groups_max = abh::num_sms() / CLUSTER;
+    if constexpr (kQuad) groups_max = quad_clusters<kBF16>();
+    const int grid = (tiles < groups_max ? tiles : groups_max) * CLUSTER;
     abh::prof_begin(s, abh::PROF_LINEAR);
     if constexpr (kPair) {
         cudaLaunchConfig_t cfg = {};
@@ -440,14 +491,14 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
         cfg.stream = s;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.x = CLUSTER;
         attr[0].val.clusterDim.y = 1;
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        AB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<kBF16, BLOCK_N, kPair, kTN>, ta, tb, p));
+        AB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<kBF16, BLOCK_N, kPair, kTN, kQuad>, ta, tb, p));
     } else {
-        gemm_kernel<kBF16, BLOCK_N, kPair, kTN><<<grid, THREADS, C::SMEM_BYTES, s>>>(ta, tb, p);
+        gemm_kernel<kBF16, BLOCK_N, kPair, kTN, kQuad><<<grid, THREADS, C::SMEM_BYTES, s>>>(ta, tb, p);
     }
     abh::prof_end(s, abh::PROF_LINEAR, 2.0 * p.M * static_cast<double>(p.N) * p.K);
     abh::count_launch();
@@ -523,8 +574,14 @@ int atlas_b200_linear_ex(const void* A, int64_t lda, const void* W, int64_t ldw,
     // 256 x 256 pair tiles once there are enough of them to fill the 74 CTA pairs (encoder-sized M)
     const bool pair = N >= 256 && M >= 256 &&
                       (static_cast<int64_t>((M + 255) / 256) * ((N + 255) / 256) >= abh::num_sms() / 2);
+    // 4-CTA clusters (two pairs sharing the W tile through TMA multicast) once every resident cluster gets >= 2 work items:
+    // ATLAS_B200_GEMM_QUAD=0 keeps the pair kernel (A/B measurements)
+    static const bool quad_off = getenv("ATLAS_B200_GEMM_QUAD") != nullptr && getenv("ATLAS_B200_GEMM_QUAD")[0] == '0';
+    static const bool no_pair = getenv("ATLAS_B200_GEMM_NO_PAIR") != nullptr;   // A/B measurements
+    const int qc = (pair && !quad_off && !no_pair && M >= 512) ? (is_bf16 ? quad_clusters<true>() : quad_clusters<false>()) : 0;
+    const bool quad = qc > 0 && (static_cast<int64_t>((M + 511) / 512) * ((N + 255) / 256) >= 2ll * qc);
     const int block_n = (wide || pair) ? 256 : 128;
-    const int b_box_rows = pair ? 128 : block_n;
+    const int b_box_rows = quad ? 64 : (pair ? 128 : block_n);
     CUtensorMap ta, tb;
     int rc = abh::make_tmap_2d_16bit(&ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K),
                                      static_cast<uint64_t>(lda), BLOCK_M, BLOCK_K, is_bf16 != 0);
@@ -533,7 +590,8 @@ int atlas_b200_linear_ex(const void* A, int64_t lda, const void* W, int64_t ldw,
                                  static_cast<uint32_t>(b_box_rows), BLOCK_K, is_bf16 != 0);
     if (rc) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    static const bool no_pair = getenv("ATLAS_B200_GEMM_NO_PAIR") != nullptr;   // A/B measurements
+    if (quad)
+        return is_bf16 ? launch<true, 256, true, false, true>(ta, tb, p, s) : launch<false, 256, true, false, true>(ta, tb, p, s);
     if (pair && !no_pair) return is_bf16 ? launch<true, 256, true>(ta, tb, p, s) : launch<false, 256, true>(ta, tb, p, s);
     if (pair && no_pair) {   // the 1-CTA kernel needs the full-height W box
         rc = abh::make_tmap_2d_16bit(&tb, W, static_cast<uint64_t>(N), static_cast<uint64_t>(K),

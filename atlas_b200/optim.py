@@ -7,7 +7,7 @@ keys (`step`, `float32copy`, `exp_avg`, `exp_avg_sq`), so checkpoints written by
 One kernel launch updates every parameter of a group (the reference runs torch's foreach AdamW on the fp32 copies plus
 one `p.copy_(float32copy)` per parameter); the statistics come back as ONE [n, 4] device tensor instead of four `.item()`
 synchronisations per parameter.  After a step the 16-bit weight caches of the models are marked stale
-(`retrievers.invalidate_weight_caches`), which the reference does not need.
+(`retrievers._WEIGHTS_EPOCH`), which the reference does not need.
 
 No CPU path: parameters must live on a CUDA device; `amsgrad`, `maximize` and sparse gradients raise.
 """
@@ -78,8 +78,8 @@ class AdamWFP32Copy(torch.optim.AdamW):
                 state = self.state[p]
                 if len(state) == 0:
                     state["step"] = 0
-                    state["float32copy"] = p.to(torch.float32, memory_format=torch.preserve_format).clone() \\
-                        if p.dtype == torch.float32 else p.to(torch.float32, memory_format=torch.preserve_format)
+                    copy = p.detach().to(torch.float32, memory_format=torch.preserve_format)
+                    state["float32copy"] = copy.clone() if copy.data_ptr() == p.data_ptr() else copy
                     state["exp_avg"] = torch.zeros_like(state["float32copy"], memory_format=torch.preserve_format)
                     state["exp_avg_sq"] = torch.zeros_like(state["float32copy"], memory_format=torch.preserve_format)
                 state["step"] += 1
@@ -102,12 +102,9 @@ class AdamWFP32Copy(torch.optim.AdamW):
                                                       current_stream_ptr()))
             # the tables are read by the kernel asynchronously: keep them (and the pinned staging copies) until the next step
             self._live = (d_dev, c_dev, h1, h2, keep)
-        try:
-            from .retrievers import invalidate_weight_caches
+        from .retrievers import _bump_weights_epoch
 
-            invalidate_weight_caches()
-        except ImportError:
-            pass
+        _bump_weights_epoch()          # the kernel wrote the parameters behind autograd's version counters
         return loss
 
 

@@ -134,3 +134,51 @@ def test_fused_rmsnorm_around_the_gemm(dev, dtype, M):
     y2 = ops.linear(ops.layernorm(h, ln, None, eps, kind=1), wi)
     tol = 4 * torch.finfo(dtype).eps
     assert float((y.float() - y2.float()).abs().max()) <= tol * float(y2.float().abs().max()) + 1e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("M,N,K,epi", [
+    (30720, 2304, 768, 0),      # FiD-base fused q|k|v projection of 2 queries x 40 passages
+    (30720, 768, 2048, 3),      # wo + residual
+    (20580, 768, 768, 3),       # M = 40 x 512 + 100: the second pair of the last cluster is entirely out of range
+    (20780, 1032, 520, 1),      # M = 40 x 512 + 300: ... partly out of range; ragged N and K
+    (16384, 4096, 768, 4),      # gated-GELU epilogue
+])
+def test_quad_cluster_multicast_tiles(dev, dtype, M, N, K, epi):
+    """Shapes large enough for the 4-CTA-cluster kernel (two CTA pairs sharing the W tile through TMA multicast): against the
+    fp32 reference, and bit-identical to the 2-CTA pair kernel (same MMA order per output element: the accumulation over K
+    is the same sequence of UMMA K = 16 steps in both)."""
+    import os
+    import subprocess
+    import sys
+
+    from atlas_b200 import ops
+
+    g = torch.Generator(device="cpu").manual_seed(M + N + K + epi)
+    x = (torch.randn(M, K, generator=g) * 0.5).to(dtype).to(dev)
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(dtype).to(dev)
+    bias = (torch.randn(N, generator=g) * 0.1).to(dtype).to(dev)
+    res = (torch.randn(M, N, generator=g)).to(dtype).to(dev)
+    y = ops.linear(x, w, bias if epi in (1, 2, 3) else None, res if epi == 3 else None, epilogue=epi)
+    ok, err = _close(y, _ref(x, w, bias, res, epi), dtype)
+    assert ok, f"max abs err {err}"
+    # the pair kernel in a child process (the switch is read once per process)
+    code = (
+        "import sys, math, torch; sys.path.insert(0, %r)\n"
+        "from atlas_b200 import ops\n"
+        "M, N, K, epi, dt = %d, %d, %d, %d, torch.%s\n"
+        "g = torch.Generator(device='cpu').manual_seed(M + N + K + epi)\n"
+        "dev = torch.device('cuda:0')\n"
+        "x = (torch.randn(M, K, generator=g) * 0.5).to(dt).to(dev)\n"
+        "w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(dt).to(dev)\n"
+        "bias = (torch.randn(N, generator=g) * 0.1).to(dt).to(dev)\n"
+        "res = (torch.randn(M, N, generator=g)).to(dt).to(dev)\n"
+        "y = ops.linear(x, w, bias if epi in (1, 2, 3) else None, res if epi == 3 else None, epilogue=epi)\n"
+        "torch.save(y.cpu(), sys.argv[1])\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), M, N, K, epi, str(dtype).split(".")[1])
+    path = f"/tmp/_pair_{M}_{N}_{K}_{epi}_{str(dtype).split('.')[1]}.pt"
+    env = dict(os.environ, ATLAS_B200_GEMM_QUAD="0")
+    subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=300)
+    y_pair = torch.load(path)
+    os.remove(path)
+    assert torch.equal(y.cpu(), y_pair), "the quad-cluster kernel and the pair kernel disagree"
