@@ -33,6 +33,27 @@ elif what == "gemm":
     fn = lambda: ops.linear(x, w, epilogue=ops.EPI_GATED)
     ms = timed(fn, reps)
     print(f"gemm M={M} N={N} K={K} gated: {ms:.3f} ms = {2 * M * N * K / ms / 1e9:.0f} TFLOP/s")
+elif what == "gemm4":
+    # the four linear-layer shapes of a FiD-base encoder block at 4 queries x 40 passages x 384 tokens, next to cuBLAS
+    # (torch.matmul of the same shape, plain epilogue): ATLAS_B200_GEMM_QUAD=0 selects the 2-CTA pair kernel for A/B runs
+    M = 61440
+    for name, N, K, epi in (("qkv", 2304, 768, None), ("o-proj+res", 768, 768, "res"), ("wi gated", 4096, 768, "gated"),
+                            ("wo+res", 768, 2048, "res")):
+        x = torch.randn(M, K, device=dev).bfloat16() * 0.1
+        w = torch.randn(N, K, device=dev).bfloat16() * 0.03
+        r = torch.randn(M, N, device=dev).bfloat16() if epi == "res" else None
+        if epi == "gated":
+            fn = lambda: ops.linear(x, w, epilogue=ops.EPI_GATED)
+        elif epi == "res":
+            fn = lambda: ops.linear(x, w, None, residual=r, epilogue=ops.EPI_RESIDUAL)
+        else:
+            fn = lambda: ops.linear(x, w)
+        ms = timed(fn, reps)
+        wt = w.t().contiguous()
+        ms_ref = timed(lambda: torch.matmul(x, wt), reps)
+        fl = 2 * M * N * K
+        print(f"gemm {name:12s} M={M} N={N} K={K}: {ms:.3f} ms = {fl / ms / 1e9:.0f} TFLOP/s   cuBLAS plain: {ms_ref:.3f} ms = "
+              f"{fl / ms_ref / 1e9:.0f} TFLOP/s")
 elif what == "attn_bwd":
     S, H, L = 80, 12, 384       # FiD-base encoder, 2 queries x 40 passages (the bench's training leg)
     qkv = torch.randn(S * L, 3 * H * 64, device=dev).bfloat16() * 0.2
