@@ -16,6 +16,7 @@ Same public surface: `embeddings` ([768, N] fp16 CUDA, slice-as
 
 There is no CPU path: `is_in_gpu = False` (the reference's FAISS-only mode) raises.
 """
+import ctypes
 import math
 import os
 import pickle
@@ -25,7 +26,7 @@ import numpy as np
 import torch
 
 from . import dist_utils, ops
-from ._lib import MAX_TOPK, AtlasB200Error
+from ._lib import MAX_TOPK, AtlasB200Error, check, lib
 from .passage_store import make_store
 
 EMBEDDINGS_DIM: int = 768  # src/retrievers.py:13
@@ -124,23 +125,78 @@ class DistributedIndex(object):
         ws = dist_utils.get_world_size()
         assert total_saved_shards % ws == 0, f"N workers must be a multiple of shards to save"
         shards_per_worker = total_saved_shards // ws
-        passages, rows = [], []
-        for shard_id in range(rank * shards_per_worker, (rank + 1) * shards_per_worker):
+        passages = []
+        shard_ids = list(range(rank * shards_per_worker, (rank + 1) * shards_per_worker))
+        for shard_id in shard_ids:
             with open(self._get_saved_passages_path(path, shard_id), "rb") as fobj:
                 passages.append(pickle.load(fobj))
-            shard = torch.load(self._get_saved_embedding_path(path, shard_id), map_location="cpu")
-            rows.append(shard.t().to(torch.float16))
         self.doc_map = {}
         n_passages = 0
         for chunk in passages:
             for p in chunk:
                 self.doc_map[n_passages] = p
                 n_passages += 1
-        self._bank = torch.cat(rows, dim=0).contiguous().to(self._device())
+        device = self._device()
+        files = [self._get_saved_embedding_path(path, s) for s in shard_ids]
+        if device.type == "cuda":
+            self._bank = self._load_bank_streamed(files, device)
+        else:       # CPU test doubles of this class (tests/test_index_gloo.py)
+            rows = [torch.load(f, map_location="cpu").t().to(torch.float16) for f in files]
+            self._bank = torch.cat(rows, dim=0).contiguous().to(device)
         sizes = dist_utils.get_varsize(self._bank)
         self._offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
         self._id_base, self._id_stride = int(self._offsets[rank]), 1
         self._reset_store()
+
+    @staticmethod
+    def _load_bank_streamed(files, device, chunk_cols=262144):
+        """The shard files (`embeddings.{s}.pt` = [768, n_s] fp16, src/index.py:75-87) straight into the device bank
+        [sum n_s, 768]: every file is memory-mapped (`torch.load(mmap=True)`: no host copy of the whole tensor), column
+        chunks are staged through two pinned buffers, copied H2D asynchronously and transposed into their bank rows by
+        `atlas_b200_transpose` on the GPU.  The reference (and round 1 here) reads every shard into host memory,
+        transposes it on ONE CPU core (`.t()` + `cat` -> a strided 2-byte copy, ~1 GB/s) and only then uploads it."""
+        shards = []
+        for f in files:
+            try:
+                t = torch.load(f, map_location="cpu", mmap=True)
+            except (RuntimeError, ValueError, TypeError):     # legacy (non-zip) checkpoint: no mmap
+                t = torch.load(f, map_location="cpu")
+            if t.dim() != 2 or t.shape[0] != EMBEDDINGS_DIM:
+                raise AtlasB200Error(f"{f}: expected a [{EMBEDDINGS_DIM}, n] embedding shard, got {tuple(t.shape)}")
+            shards.append(t)
+        total = sum(int(t.shape[1]) for t in shards)
+        bank = torch.empty((total, EMBEDDINGS_DIM), dtype=torch.float16, device=device)
+        width = max(8, min(chunk_cols, max((int(t.shape[1]) for t in shards), default=8)))
+        width = (width + 7) // 8 * 8
+        stage = [torch.empty((EMBEDDINGS_DIM, width), dtype=torch.float16).pin_memory() for _ in range(2)]
+        dstage = [torch.empty((EMBEDDINGS_DIM, width), dtype=torch.float16, device=device) for _ in range(2)]
+        done = [torch.cuda.Event(), torch.cuda.Event()]
+        used = [False, False]
+        stream = torch.cuda.current_stream(device)
+        row0, it = 0, 0
+        for t in shards:
+            n = int(t.shape[1])
+            for a in range(0, n, width):
+                w = min(width, n - a)
+                k = it & 1
+                if used[k]:
+                    done[k].synchronize()                      # the pinned buffer is free again
+                src = t[:, a:a + w]
+                stage[k][:, :w].copy_(src if src.dtype == torch.float16 else src.to(torch.float16))   # the disk read
+                dstage[k][:, :w].copy_(stage[k][:, :w], non_blocking=True)
+                done[k].record(stream)
+                used[k] = True
+                view = dstage[k][:, :w]
+                if w % 2 == 0:
+                    dst = bank.data_ptr() + (row0 + a) * bank.stride(0) * 2
+                    check(lib().atlas_b200_transpose(view.data_ptr(), view.stride(0), dst, bank.stride(0), EMBEDDINGS_DIM, w,
+                                                     EMBEDDINGS_DIM, ctypes.c_void_p(stream.cuda_stream)))
+                else:   # odd tail width: the transpose kernel moves 2-column words
+                    bank[row0 + a:row0 + a + w].copy_(view.t())
+                it += 1
+            row0 += n
+        torch.cuda.current_stream(device).synchronize()
+        return bank
 
     # ------------------------------------------------------------------ search
     def _compute_scores_and_indices(self, allqueries: torch.Tensor, topk: int):

@@ -260,3 +260,22 @@ def test_distributed_search_nccl(tmp_path):
          "127.0.0.1", "--master-port", "29877", script],
         capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+def test_streamed_index_load(dev, tmp_path):
+    """`load_index` streams the reference-format shard files ([768, n] fp16, src/index.py:75-87) through pinned chunks and a
+    GPU transpose: any chunk width (even / odd tails, wider than a shard) reproduces the bank bit for bit."""
+    from atlas_b200.index import DistributedIndex
+
+    g = torch.Generator().manual_seed(77)
+    shards = [torch.randn(768, n, generator=g).half() for n in (2501, 64, 1999)]
+    files = []
+    for i, t in enumerate(shards):
+        f = str(tmp_path / f"embeddings.{i}.pt")
+        torch.save(t, f)
+        files.append(f)
+    want = torch.cat([t.t() for t in shards], 0).contiguous()
+    for width in (262144, 1000, 333, 8):
+        bank = DistributedIndex._load_bank_streamed(files, dev, chunk_cols=width)
+        assert bank.shape == want.shape and bank.is_contiguous()
+        assert torch.equal(bank.cpu(), want), width
