@@ -240,9 +240,80 @@ __global__ void splice_tokens_kernel(const int32_t* __restrict__ bank_ids, const
     }
 }
 
+// ---- fp16 overflow clamp of the T5 blocks (src/modeling_t5.py:657-708) ----------------------------------------------
+// The reference runs, after the self-attention, cross-attention and feed-forward sub-layers of every block,
+//     if hidden_states.dtype == torch.float16 and torch.isinf(hidden_states).any():
+//         hidden_states = torch.clamp(hidden_states, min=-(finfo.max - 1000), max=finfo.max - 1000)
+// i.e. three host synchronisations per block.  Here: a detect pass raises a device flag, the clamp pass reads it and leaves
+// at once when it is clear - same values, no synchronisation, capturable in a CUDA graph.  65504 - 1000 rounds to 64512
+// (0x7BE0) in fp16; NaNs stay NaNs (torch.clamp propagates them).
+__global__ void __launch_bounds__(256)
+inf_detect_kernel(const uint16_t* __restrict__ x, int64_t ld, int64_t M, int N, int* __restrict__ flag) {
+    const int vec_per_row = N / 8;
+    const int64_t nvec = M * vec_per_row;
+    bool found = false;
+    for (int64_t v = blockIdx.x * 256ll + threadIdx.x; v < nvec; v += gridDim.x * 256ll) {
+        const uint4 w = __ldg(reinterpret_cast<const uint4*>(x + (v / vec_per_row) * ld + (v % vec_per_row) * 8));
+        const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) found |= ((ws[e] & 0x7FFFu) == 0x7C00u) | ((ws[e] & 0x7FFF0000u) == 0x7C000000u);
+    }
+    if (__any_sync(0xffffffffu, found) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+
+// one warp per row; only runs its body when the flag is raised.  row_ss (optional): the row's sum of squares of the clamped
+// values, the statistic the fused RMSNorm of the next GEMM consumes (the GEMM that produced x accumulated it from the
+// un-clamped values, inf included).
+__global__ void __launch_bounds__(256)
+inf_clamp_kernel(uint16_t* __restrict__ x, int64_t ld, int64_t M, int N, const int* __restrict__ flag,
+                 float* __restrict__ row_ss) {
+    if (*flag == 0) return;
+    const int lane = threadIdx.x & 31;
+    for (int64_t row = blockIdx.x * 8ll + (threadIdx.x >> 5); row < M; row += gridDim.x * 8ll) {
+        uint16_t* xr = x + row * ld;
+        float ss = 0.f;
+        for (int c = lane * 2; c < N; c += 64) {
+            uint32_t w = *reinterpret_cast<uint32_t*>(xr + c);
+            uint32_t o = 0;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                uint32_t h = (w >> (16 * e)) & 0xFFFFu;
+                const uint32_t mag = h & 0x7FFFu;
+                if (mag <= 0x7C00u && mag > 0x7BE0u) h = (h & 0x8000u) | 0x7BE0u;     // finite-or-inf above the bound; NaN kept
+                const float f = __half2float(__ushort_as_half(static_cast<unsigned short>(h)));
+                ss = fmaf(f, f, ss);
+                o |= h << (16 * e);
+            }
+            *reinterpret_cast<uint32_t*>(xr + c) = o;
+        }
+        if (row_ss != nullptr) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+            if (lane == 0) row_ss[row] = ss;
+        }
+    }
+}
+
 }  // namespace ew
 
 extern "C" {
+
+int atlas_b200_clamp_inf_fp16(void* x, int64_t ld, int64_t M, int32_t N, int32_t* flag, float* row_ss, void* stream) {
+    AB_REQUIRE(M >= 0 && N > 0 && N % 8 == 0 && ld % 8 == 0 && flag != nullptr, "clamp_inf_fp16: N and ld must be multiples of 8");
+    if (M == 0) return ATLAS_B200_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    AB_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(int32_t), s));
+    const int64_t blocks = (M * (N / 8) + 255) / 256;
+    const int64_t cap = static_cast<int64_t>(abh::num_sms()) * 16;
+    ew::inf_detect_kernel<<<static_cast<unsigned>(blocks < cap ? blocks : cap), 256, 0, s>>>(
+        static_cast<const uint16_t*>(x), ld, M, N, flag);
+    const int64_t rb = (M + 7) / 8;
+    ew::inf_clamp_kernel<<<static_cast<unsigned>(rb < cap ? rb : cap), 256, 0, s>>>(static_cast<uint16_t*>(x), ld, M, N, flag,
+                                                                                   row_ss);
+    abh::count_launch(2);
+    AB_CUDA_CHECK(cudaGetLastError());
+    return ATLAS_B200_OK;
+}
 
 int atlas_b200_layernorm(const void* x, int64_t ldx, const void* weight, const void* bias, void* y, int64_t ldy,
                          int32_t rows, int32_t H, float eps, int32_t kind, int32_t is_bf16, void* stream) {

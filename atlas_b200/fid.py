@@ -15,8 +15,8 @@ tcgen05 GEMM with fused residual and gated-GELU epilogues (modeling_t5.py:281-28
 B*n independent L-token segments with the relative-position bias added on the fly from a [H, 2L-1] table
 (modeling_t5.py:352-416,478-524) - the [B*n, H, L, L] bias / probability tensors are never materialised;
 decoder cross-attention over the n*L concatenated keys as split-KV + combine (fid.py:298-349).
-Dropout: counter-based masks inside the kernels (csrc/dropout.cuh).  Not reproduced: the `isinf` clamps and their three host
-syncs per block (modeling_t5.py:657-708).
+Dropout: counter-based masks inside the kernels (csrc/dropout.cuh).  The fp16 `isinf` clamps of every sub-layer
+(modeling_t5.py:657-708, three host syncs per block in the reference) are decided on the device (ops.clamp_inf_).
 """
 import copy
 import math
@@ -348,7 +348,9 @@ class FiD(nn.Module):
     def _ff(self, W, G, prefix, h, eps):
         n = ops.layernorm(h, W[prefix + "layer_norm.weight"], None, eps, kind=1)
         g = ops.linear(n, G[prefix + "DenseReluDense.wi_01"], epilogue=ops.EPI_GATED)
-        return ops.linear(g, W[prefix + "DenseReluDense.wo.weight"], None, residual=h, epilogue=ops.EPI_RESIDUAL)
+        # + the fp16 overflow clamp the reference applies after every sub-layer (src/modeling_t5.py:657-708; no-op in bf16)
+        return ops.clamp_inf_(ops.linear(g, W[prefix + "DenseReluDense.wo.weight"], None, residual=h,
+                                         epilogue=ops.EPI_RESIDUAL))
 
     @torch.no_grad()
     def encode(self, input_ids, attention_mask):
@@ -383,10 +385,12 @@ class FiD(nn.Module):
                                     scale=1.0)
                 h = ops.linear(ctx, W[p + "SelfAttention.o.weight"], None, residual=h, epilogue=ops.EPI_RESIDUAL,
                                out_ss=ss[2 * i])
+                ops.clamp_inf_(h, row_ss=ss[2 * i])
                 p = f"encoder.block.{i}.layer.1."
                 g = ops.linear(h, G[p + "DenseReluDense.wi_01_n"], epilogue=ops.EPI_GATED, row_ss=ss[2 * i], rs_eps=eps)
                 h = ops.linear(g, W[p + "DenseReluDense.wo.weight"], None, residual=h, epilogue=ops.EPI_RESIDUAL,
                                out_ss=ss[2 * i + 1])
+                ops.clamp_inf_(h, row_ss=ss[2 * i + 1])
         else:
             for i in range(c.num_layers):
                 p = f"encoder.block.{i}.layer.0."
@@ -394,7 +398,8 @@ class FiD(nn.Module):
                 ops.linear(n, G[p + "SelfAttention.qkv"], out=qkv)
                 ctx = ops.attention(qkv, 0, qkv, H * 64, qkv, 2 * H * 64, S, H, L, L, add_mask=add_mask, bias_delta=bias,
                                     scale=1.0)
-                h = ops.linear(ctx, W[p + "SelfAttention.o.weight"], None, residual=h, epilogue=ops.EPI_RESIDUAL)
+                h = ops.clamp_inf_(ops.linear(ctx, W[p + "SelfAttention.o.weight"], None, residual=h,
+                                              epilogue=ops.EPI_RESIDUAL))
                 h = self._ff(W, G, f"encoder.block.{i}.layer.1.", h, eps)
         h = ops.layernorm(h, W["encoder.final_layer_norm.weight"], None, c.layer_norm_epsilon, kind=1)
         return h.view(bsz, -1, d)
@@ -443,7 +448,7 @@ class FiD(nn.Module):
             ops.linear(n, G[p + "SelfAttention.qkv"], out=qkv)
             ctx = ops.attention(qkv, 0, qkv, H * 64, qkv, 2 * H * 64, B, H, T, T, bias_delta=bias, scale=1.0,
                                 causal_value=-10000.0)
-            h = ops.linear(ctx, W[p + "SelfAttention.o.weight"], None, residual=h, epilogue=ops.EPI_RESIDUAL)
+            h = ops.clamp_inf_(ops.linear(ctx, W[p + "SelfAttention.o.weight"], None, residual=h, epilogue=ops.EPI_RESIDUAL))
             p = f"decoder.block.{i}.layer.1."
             n = ops.layernorm(h, W[p + "layer_norm.weight"], None, c.layer_norm_epsilon, kind=1)
             q = ops.linear(n, W[p + "EncDecAttention.q.weight"])
@@ -454,7 +459,8 @@ class FiD(nn.Module):
             else:
                 ctx = ops.cross_attention_split(q, 0, cross_kv[i], 0, H * 64, B, H, T, Lk, add_mask=cross_mask,
                                                 scale=1.0, split=split)
-            h = ops.linear(ctx, W[p + "EncDecAttention.o.weight"], None, residual=h, epilogue=ops.EPI_RESIDUAL)
+            h = ops.clamp_inf_(ops.linear(ctx, W[p + "EncDecAttention.o.weight"], None, residual=h,
+                                          epilogue=ops.EPI_RESIDUAL))
             h = self._ff(W, G, f"decoder.block.{i}.layer.2.", h, c.layer_norm_epsilon)
         h = ops.layernorm(h, W["decoder.final_layer_norm.weight"], None, c.layer_norm_epsilon, kind=1)
         if getattr(c, "tie_word_embeddings", False):
@@ -511,10 +517,11 @@ class FiD(nn.Module):
         add_mask = (1.0 - mask.to(torch.float32)) * -10000.0
 
         def lin_res(x, w, res):
-            # h + dropout(linear(x)) (T5LayerSelfAttention / T5LayerFF); without dropout the add is the GEMM's epilogue
+            # h + dropout(linear(x)) (T5LayerSelfAttention / T5LayerFF); without dropout the add is the GEMM's epilogue;
+            # then the fp16 overflow clamp of the block (a no-op for bf16)
             if pdrop:
-                return g.dropout(g.linear(x, w), pdrop, residual=res)
-            return g.linear(x, w, None, residual=res)
+                return g.clamp_inf(g.dropout(g.linear(x, w), pdrop, residual=res))
+            return g.clamp_inf(g.linear(x, w, None, residual=res))
 
         bias = bias_by_delta(W["encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight"], L, L, True,
                              c.relative_attention_num_buckets)
@@ -561,8 +568,8 @@ class FiD(nn.Module):
 
         def lin_res(x, w, res):
             if pdrop:
-                return g.dropout(g.linear(x, w), pdrop, residual=res)
-            return g.linear(x, w, None, residual=res)
+                return g.clamp_inf(g.dropout(g.linear(x, w), pdrop, residual=res))
+            return g.clamp_inf(g.linear(x, w, None, residual=res))
 
         bias = bias_by_delta(W["decoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight"], T, T, False,
                              c.relative_attention_num_buckets)
@@ -701,13 +708,14 @@ class FiD(nn.Module):
             n = ops.layernorm(h, W[p + "layer_norm.weight"], None, eps, kind=1)
             qkv = ops.linear(n, G[p + "SelfAttention.qkv"])
             ctx = ops.decode_self_attention(qkv, st.self_kv[i], st.t_dev, H, bias_delta=st.bias, scale=1.0)
-            h = ops.linear(ctx, W[p + "SelfAttention.o.weight"], None, residual=h, epilogue=ops.EPI_RESIDUAL)
+            h = ops.clamp_inf_(ops.linear(ctx, W[p + "SelfAttention.o.weight"], None, residual=h, epilogue=ops.EPI_RESIDUAL))
             p = f"decoder.block.{i}.layer.1."
             n = ops.layernorm(h, W[p + "layer_norm.weight"], None, eps, kind=1)
             q = ops.linear(n, W[p + "EncDecAttention.q.weight"])
             ctx = ops.decode_cross_attention(q, st.cross_kv[i], B, H, Lk, add_mask=st.cross_mask, scale=1.0,
                                              chunk=st.chunk)
-            h = ops.linear(ctx, W[p + "EncDecAttention.o.weight"], None, residual=h, epilogue=ops.EPI_RESIDUAL)
+            h = ops.clamp_inf_(ops.linear(ctx, W[p + "EncDecAttention.o.weight"], None, residual=h,
+                                          epilogue=ops.EPI_RESIDUAL))
             h = self._ff(W, G, f"decoder.block.{i}.layer.2.", h, eps)
         h = ops.layernorm(h, W["decoder.final_layer_norm.weight"], None, eps, kind=1)
         if getattr(c, "tie_word_embeddings", False):

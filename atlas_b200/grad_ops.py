@@ -169,6 +169,26 @@ def dropout(x, p, residual=None):
     return _Dropout.apply(x, residual, float(p))
 
 
+class _ClampInf(torch.autograd.Function):
+    """The reference's fp16 overflow clamp after a T5 sub-layer (src/modeling_t5.py:657-708), in place, device-side decision.
+    Backward: identity (the reference's `torch.clamp` zeroes the gradient of the clamped elements; they only exist in a
+    step that overflowed fp16, which the reference's training recipe - bf16 - never takes)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.mark_dirty(x)
+        ops.clamp_inf_(x)
+        return x
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy
+
+
+def clamp_inf(x):
+    return _ClampInf.apply(x) if x.dtype == torch.float16 else x
+
+
 class _GatedGelu(torch.autograd.Function):
     @staticmethod
     def forward(ctx, u):

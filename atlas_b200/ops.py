@@ -424,6 +424,24 @@ def attention_dropout_mask(B, H, Lq, Lk, p, seed, offset, device):
     return out
 
 
+_inf_flags = {}
+
+
+def clamp_inf_(x, row_ss=None):
+    """The reference's per-sub-layer fp16 overflow clamp (src/modeling_t5.py:657-708), in place, decided on the device
+    (no host synchronisation).  A no-op for any other dtype, like the reference's `dtype == torch.float16` test."""
+    if x.dtype != torch.float16:
+        return x
+    require_cuda(x, "x")
+    x2 = _rows2d(x)
+    flag = _inf_flags.get(x.device)
+    if flag is None:
+        flag = _inf_flags[x.device] = torch.zeros(1, dtype=torch.int32, device=x.device)
+    check(lib().atlas_b200_clamp_inf_fp16(_ptr(x2), x2.stride(0), x2.shape[0], x2.shape[1], _ptr(flag),
+                                          _ptr(row_ss) if row_ss is not None else None, current_stream_ptr()))
+    return x
+
+
 def bert_embed_sum(input_ids, token_type_ids, word_emb, type_emb, pos_emb):
     require_cuda(input_ids, "input_ids")
     B, L = input_ids.shape

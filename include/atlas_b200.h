@@ -384,6 +384,12 @@ int atlas_b200_adamw_fp32copy(const AtlasB200AdamTensor* descs_dev, const int32_
 int atlas_b200_grad_stats(const AtlasB200GradTensor* descs_dev, int32_t n_tensors, const int32_t* chunks_dev,
                           int32_t n_chunks, int32_t chunk_elems, float* stats, void* stream);
 
+/* fp16 overflow clamp of the T5 blocks (src/modeling_t5.py:657-708: `if dtype == fp16 and isinf(h).any(): h = clamp(h,
+ * +-(65504 - 1000))` after every sub-layer, three host synchronisations per block in the reference): in place on x [M, N]
+ * fp16, decided on the device through `flag` (one int32 of scratch), no synchronisation.  row_ss (optional, [M] fp32) is
+ * rewritten with the rows' sums of squares when (and only when) the clamp fires (fused-RMSNorm statistic). */
+int atlas_b200_clamp_inf_fp16(void* x, int64_t ld, int64_t M, int32_t N, int32_t* flag, float* row_ss, void* stream);
+
 /* Measurement hook for bench.py's roofline: while enabled, every launch of ONE kind of kernel is bracketed
  * with CUDA events on its launching stream:
  *   kind 1  the bank sweep of atlas_b200_mips_topk (work = algorithmic bytes swept)

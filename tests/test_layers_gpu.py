@@ -186,3 +186,63 @@ def test_attention_lanes_kernel_cases(dev, dtype, B, H, L, mode):
         i = torch.arange(L, device=dev)
         s = s + (i[None, :] > i[:, None]).float() * causal
     assert float((lse - torch.logsumexp(s, dim=-1)).abs().max()) <= 2e-3
+
+
+def test_fp16_inf_clamp(dev):
+    """ops.clamp_inf_ = the reference's `if dtype == fp16 and isinf(h).any(): h = clamp(h, +-(65504 - 1000))`
+    (src/modeling_t5.py:657-708) decided on the device: untouched without an inf, torch.clamp's values with one."""
+    from atlas_b200 import ops
+
+    g = torch.Generator().manual_seed(3)
+    x = (torch.randn(777, 768, generator=g) * 30000).half()            # plenty of values between 64512 and 65504, some inf
+    finite = x.clone()
+    finite[torch.isinf(finite)] = 65504.0
+    assert not torch.isinf(finite).any() and (finite.abs() > 64512).any()
+    y = ops.clamp_inf_(finite.clone().to(dev))
+    assert torch.equal(y.cpu(), finite)                                 # no inf anywhere: nothing is clamped
+    withinf = finite.clone()
+    withinf[5, 7] = float("inf")
+    withinf[700, 0] = float("-inf")
+    withinf[3, 3] = float("nan")
+    clamp_value = torch.finfo(torch.float16).max - 1000
+    want = torch.clamp(withinf.float(), min=-clamp_value, max=clamp_value).half()
+    ss = torch.zeros(777, dtype=torch.float32, device=dev)
+    got = ops.clamp_inf_(withinf.clone().to(dev), row_ss=ss)
+    assert torch.equal(torch.nan_to_num(got.cpu().float(), nan=-1.0), torch.nan_to_num(want.float(), nan=-1.0))
+    ref_ss = want.float().pow(2).sum(-1)
+    ok = ~torch.isnan(ref_ss)
+    assert torch.allclose(ss.cpu()[ok], ref_ss[ok], rtol=1e-5)
+    # other dtypes pass through (the reference tests `dtype == torch.float16`)
+    b = torch.full((8, 768), float("inf"), dtype=torch.bfloat16, device=dev)
+    assert torch.isinf(ops.clamp_inf_(b)).all()
+    # strided view (a column slice of a wider buffer)
+    wide = torch.zeros(64, 1536, dtype=torch.float16, device=dev)
+    wide[:, 768:] = 65000.0
+    wide[1, 800] = float("inf")
+    ops.clamp_inf_(wide[:, 768:])
+    assert float(wide[:, 768:].max()) == 64512.0 and float(wide[:, :768].abs().max()) == 0.0
+
+
+def test_fid_fp16_overflow_is_clamped_like_the_reference(dev):
+    """A FiD block whose feed-forward output overflows fp16: with the device-side clamp the forward stays finite and equals an
+    fp16 torch restatement of the reference's block arithmetic (clamp included) on the same kernels' inputs."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import model_synth
+    from atlas_b200.fid import FiD, T5ConfigLite
+
+    cfg = {k: v for k, v in model_synth.T5_CFG.items() if k not in ("dropout_rate", "is_encoder_decoder", "use_cache")}
+    reader = FiD(T5ConfigLite(**cfg))
+    sd, _ = model_synth.fill_state_dict(reader.state_dict(), 202)
+    sd["encoder.block.0.layer.1.DenseReluDense.wo.weight"] = sd["encoder.block.0.layer.1.DenseReluDense.wo.weight"] * 3000.0
+    reader.load_state_dict(sd)
+    reader = reader.half().to(dev).eval()
+    reader.encoder.config.n_context, reader.encoder.config.bsz = 3, 2
+    ids, mask, labels = model_synth.fid_inputs()
+    for fuse in (True, False):
+        reader.fuse_norm = fuse
+        reader.cuda_graphs = False
+        with torch.no_grad():
+            enc = reader.encode(ids.to(dev), mask.to(dev))
+        assert torch.isfinite(enc).all(), f"fuse_norm={fuse}: the overflow reached the encoder output"
+        assert float(enc.abs().max()) > 0
