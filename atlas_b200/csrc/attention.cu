@@ -883,8 +883,8 @@ int atlas_b200_attention_lanes_launch(const void* q, int64_t ldq, int32_t q_col0
                                       const float* add_mask, const float* bias_delta, int32_t B, int32_t H, int32_t Lq,
                                       int32_t Lk, float scale, float causal_value, float* lse_out, int32_t is_bf16,
                                       cudaStream_t s);
-// csrc/attention_lanes2.cu: the 48-key / double-buffered-S experiment (ATLAS_B200_ATTN_LANES=2)
-int atlas_b200_attention_lanes2_launch(const void* q, int64_t ldq, int32_t q_col0, const void* k, int64_t ldk, int32_t k_col0,
+// csrc/attention_lanes96.cu: the first three-lane kernel (96-key blocks), ATLAS_B200_ATTN_LANES=3
+int atlas_b200_attention_lanes96_launch(const void* q, int64_t ldq, int32_t q_col0, const void* k, int64_t ldk, int32_t k_col0,
                                        const void* v, int64_t ldv, int32_t v_col0, void* out, int64_t ldo,
                                        const float* add_mask, const float* bias_delta, int32_t B, int32_t H, int32_t Lq,
                                        int32_t Lk, float scale, float causal_value, float* lse_out, int32_t is_bf16,
@@ -938,7 +938,7 @@ int atlas_b200_attention_train(const void* q, int64_t ldq, int32_t q_col0, const
     if (lanes_sel != 0 && !dropping && o_partial == nullptr && q_div == 1 && Lq > 128 && Lq <= 512 && Lk <= 576) {
         cudaStream_t ls = static_cast<cudaStream_t>(stream);
         abh::prof_begin(ls, abh::PROF_ATTENTION);
-        int lrc = (lanes_sel == 2 ? atlas_b200_attention_lanes2_launch : atlas_b200_attention_lanes_launch)(
+        int lrc = (lanes_sel == 3 ? atlas_b200_attention_lanes96_launch : atlas_b200_attention_lanes_launch)(
             q, ldq, q_col0, k, ldk, k_col0, v, ldv, v_col0, out, ldo, add_mask, bias_delta, B, H, Lq, Lk, scale, causal_value,
             lse_out, is_bf16, ls);
         if (lrc) return lrc;

@@ -11,13 +11,19 @@
 //     FiD passage are in flight at once.  Every lane has its own MMA-issuer thread, its own softmax warpgroup (one thread
 //     per query row: no cross-thread reductions, no named barriers) and its own barriers; the lanes only share the K / V
 //     stream.  While lane A waits for its P.V(j) -> S(j+1) hand-over, lanes B and C keep the MUFU / FMA pipes busy.
-//   * K and V stream ONCE per (segment, head) through a ring of 96-key chunks (12 KB, TMA, 128B swizzle) shared by the
+//   * K and V stream ONCE per (segment, head) through a ring of 64-key chunks (8 KB, TMA, 128B swizzle) shared by the
 //     lanes (a stage is released when every query tile of the item has consumed it): L2 -> SM traffic stays at
 //     (K + V) per item, the next item's chunks prefetch into the freed stages.
-//   * Online softmax over 96-key blocks with a LAZY reference maximum: block 0 fixes m; a later block only triggers a
+//   * Online softmax over 64-key blocks with a LAZY reference maximum: block 0 fixes m; a later block only triggers a
 //     rescale of the 64-column O accumulator when its maximum exceeds m by more than 8 (log2 units), otherwise the stale m
 //     is kept (probabilities up to 2^8, exact in fp32 / harmless in 16 bits) - the common case costs nothing.
-//   * TMEM (480 of 512 columns): per lane S (96 fp32 columns, overwritten in place by the packed 16-bit P) | O (64).
+//   * TMEM (480 of 512 columns): per lane S (64 fp32 columns) | P (32 columns of packed 16-bit pairs) | O (64).  P has its OWN
+//     columns, so S(j+1) = Q K_{j+1}^T is issued as soon as the softmax threads have READ S(j) into registers (`s_read`
+//     barrier) and runs on the tensor pipe while they do the arithmetic of block j: a softmax warp never waits for an MMA
+//     round trip.  The first version (csrc/attention_lanes96.cu: P written over S, S(j+1) only after P.V(j) had retired)
+//     spent 24 % of its softmax-warp samples in that wait (profiles/r02_attention_lanes.md).  The issuer never waits for
+//     its own MMAs either: tcgen05.mma executes in issue order, so P.V(j) -> S(j+2) -> ... need no completion barrier
+//     between them; only the softmax threads wait for P.V(j-1) before they overwrite P (it has long retired by then).
 //   * The score pipeline per element: 1/4 LDS.128 (relative-position bias from FOUR alignment-shifted copies of the
 //     [2L - 1] table, so that every thread reads its diagonal run with 16-byte loads) + 1/2 FFMA2 + 1/2 FMNMX3 + 1/2 FADD2
 //     + 1 MUFU.EX2 + 1/2 FADD2 + 1/2 F2FP: 3.75 issue slots (packed f32x2 arithmetic and the 3-input max are sm_100
@@ -37,16 +43,17 @@ namespace attn4 {
 
 constexpr int D = 64;
 constexpr int BQ = 128;                 // query rows per tile / lane
-constexpr int BK = 96;                  // keys per block (UMMA N of S, K extent of P.V)
+constexpr int BK = 64;                  // keys per block (UMMA N of S, K extent of P.V)
 constexpr int LANES = 3;
-constexpr int RING = 12;                // K / V chunk stages (12 KB each): a whole 576-key item, or 384 keys + prefetch
+constexpr int RING = 18;                // K / V chunk stages (8 KB each): a whole 576-key item, or 384 keys + prefetch
 constexpr int STAGE_BYTES = BK * D * 2;
 constexpr int Q_BYTES = BQ * D * 2;
-constexpr int MAX_BLOCKS = 6;           // <= 576 keys
+constexpr int MAX_BLOCKS = 9;           // <= 576 keys
 constexpr int MAXK = MAX_BLOCKS * BK;
 constexpr int THREADS = 512;
 constexpr int SM_THREADS = 128 * LANES;
-constexpr int LANE_COLS = 160;          // TMEM columns per lane: S / P at +0 (96), O at +96 (64)
+constexpr int LANE_COLS = 160;          // TMEM columns per lane: S at +0 (64), P at +64 (32), O at +96 (64)
+constexpr int P_OFF = 64;
 constexpr int O_OFF = 96;
 constexpr int TMEM_COLS = 512;
 constexpr int CPLEN = 1152;             // floats per shifted bias copy (>= MAXK + 512 + 4), multiple of 32
@@ -175,7 +182,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 attention_lanes_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                        const __grid_constant__ CUtensorMap tmap_v, const Params p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t q_full[LANES], q_empty[LANES], s_full[LANES], p_ready[LANES], pv_done[LANES];
+    __shared__ __align__(8) uint64_t q_full[LANES], q_empty[LANES], s_full[LANES], s_read[LANES], p_ready[LANES], pv_done[LANES];
     __shared__ __align__(8) uint64_t kv_full[RING], kv_empty[RING], tab_full[2], tab_empty[2];
     __shared__ uint32_t tmem_base_smem;
     __shared__ int s_mask_flag[2];                              // this item's key mask has a non-zero entry
@@ -209,6 +216,7 @@ attention_lanes_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
             ab::mbar_init(&q_full[l], 1);
             ab::mbar_init(&q_empty[l], 1);
             ab::mbar_init(&s_full[l], 1);
+            ab::mbar_init(&s_read[l], 128);
             ab::mbar_init(&p_ready[l], 128);
             ab::mbar_init(&pv_done[l], 1);
         }
@@ -239,15 +247,28 @@ attention_lanes_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
             for (int it = it_begin; it < it_end; ++it, ++item_it) {
                 const int h = it / p.B, b = it % p.B;
                 const int buf = item_it & 1;
+                // the item's mask row in two batches of independent loads (two L2 latencies instead of MAXK / 32 dependent ones;
+                // this warp runs on 40 registers)
                 ab::mbar_wait_nocall(&tab_empty[buf], ((item_it >> 1) & 1) ^ 1u);
                 bool nonzero = false;
-                for (int j = static_cast<int>(lane); j < lk_pad; j += 32) {
-                    float v = -INFINITY;
-                    if (j < p.Lk) {
-                        v = p.add_mask ? p.add_mask[static_cast<size_t>(b) * p.Lk + j] * LOG2E : 0.f;
-                        nonzero |= (v != 0.f);
+                constexpr int HALF = MAXK / 64;
+#pragma unroll 1
+                for (int hf = 0; hf < 2; ++hf) {
+                    float mv[HALF];
+#pragma unroll
+                    for (int q = 0; q < HALF; ++q) {
+                        const int j = static_cast<int>(lane) + 32 * (hf * HALF + q);
+                        mv[q] = (p.add_mask != nullptr && j < p.Lk) ? __ldg(p.add_mask + static_cast<size_t>(b) * p.Lk + j) : 0.f;
                     }
-                    s_mask[buf][j] = v;
+#pragma unroll
+                    for (int q = 0; q < HALF; ++q) {
+                        const int j = static_cast<int>(lane) + 32 * (hf * HALF + q);
+                        if (j < lk_pad) {
+                            const float v = j < p.Lk ? mv[q] * LOG2E : -INFINITY;
+                            nonzero |= (j < p.Lk) && (v != 0.f);
+                            s_mask[buf][j] = v;
+                        }
+                    }
                 }
                 nonzero = __any_sync(0xffffffffu, nonzero);
                 if (lane == 0) s_mask_flag[buf] = nonzero ? 1 : 0;
@@ -303,33 +324,42 @@ attention_lanes_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
             const uint32_t s_tmem = tmem_base + l * LANE_COLS;
             const uint32_t o_tmem = s_tmem + O_OFF;
             const uint64_t qdesc = ab::umma_desc_k_sw128(aQ + l * Q_BYTES);
-            uint32_t tile_ctr = 0, blk_ctr = 0;
+            const uint32_t p_tmem = s_tmem + P_OFF;
+            uint32_t tile_ctr = 0, blk_ctr = 0;     // blk_ctr: blocks whose P.V has been issued
+            uint32_t s_ctr = 0;                     // blocks whose S has been issued (runs one ahead inside a tile)
             int item_it = 0;
+            // S(n): needs the K chunk and the softmax threads' read of S(n - 1) (they hold it in registers: s_read)
+            auto issue_s = [&](uint32_t ck, bool last_of_tile) {
+                const uint32_t sk = ck % RING;
+                ab::mbar_wait_nocall(&kv_full[sk], (ck / RING) & 1u);
+                if (s_ctr > 0) ab::mbar_wait_nocall(&s_read[l], (s_ctr - 1) & 1u);
+                ab::tc_fence_after();
+                const uint64_t kdesc = ab::umma_desc_k_sw128(aRing + sk * STAGE_BYTES);
+#pragma unroll
+                for (int k = 0; k < D / 16; ++k)
+                    ab::umma_ss<1>(s_tmem, qdesc + ((k * 32) >> 4), kdesc + ((k * 32) >> 4), idesc_s, k != 0 ? 1u : 0u);
+                ab::umma_commit(&kv_empty[sk]);
+                if (last_of_tile) ab::umma_commit(&q_empty[l]);
+                ab::umma_commit(&s_full[l]);
+                ++s_ctr;
+            };
             for (int it = it_begin; it < it_end; ++it, ++item_it) {
                 const uint32_t chunk_base = static_cast<uint32_t>(item_it) * 2u * nb;
                 for (int qt = l; qt < n_qt; qt += LANES, ++tile_ctr) {
                     ab::mbar_wait_nocall(&q_full[l], tile_ctr & 1u);
+                    issue_s(chunk_base, nb == 1);
                     for (int j = 0; j < nb; ++j, ++blk_ctr) {
-                        const uint32_t ck = chunk_base + 2u * j, cv = ck + 1u;
-                        const uint32_t sk = ck % RING, sv = cv % RING;
-                        ab::mbar_wait_nocall(&kv_full[sk], (ck / RING) & 1u);
-                        // P(j-1) lives in the S columns: its P.V must have retired before S(j) overwrites them
-                        if (blk_ctr > 0) ab::mbar_wait_nocall(&pv_done[l], (blk_ctr - 1) & 1u);
-                        ab::tc_fence_after();
-                        const uint64_t kdesc = ab::umma_desc_k_sw128(aRing + sk * STAGE_BYTES);
-#pragma unroll
-                        for (int k = 0; k < D / 16; ++k)
-                            ab::umma_ss<1>(s_tmem, qdesc + ((k * 32) >> 4), kdesc + ((k * 32) >> 4), idesc_s, k != 0 ? 1u : 0u);
-                        ab::umma_commit(&kv_empty[sk]);
-                        if (j == nb - 1) ab::umma_commit(&q_empty[l]);
-                        ab::umma_commit(&s_full[l]);
+                        // S(j + 1) goes to the tensor pipe while the softmax threads work on block j
+                        if (j + 1 < nb) issue_s(chunk_base + 2u * (j + 1), j + 2 == nb);
+                        const uint32_t cv = chunk_base + 2u * j + 1u;
+                        const uint32_t sv = cv % RING;
                         ab::mbar_wait_nocall(&kv_full[sv], (cv / RING) & 1u);
                         ab::mbar_wait_nocall(&p_ready[l], blk_ctr & 1u);
                         ab::tc_fence_after();
                         const uint64_t vdesc = umma_desc_mn_sw128(aRing + sv * STAGE_BYTES);
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k)
-                            ab::umma_ts<1>(o_tmem, s_tmem + k * 8, vdesc + static_cast<uint64_t>((k * 2048) >> 4), idesc_o,
+                            ab::umma_ts<1>(o_tmem, p_tmem + k * 8, vdesc + static_cast<uint64_t>((k * 2048) >> 4), idesc_o,
                                            (j != 0 || k != 0) ? 1u : 0u);
                         ab::umma_commit(&kv_empty[sv]);
                         ab::umma_commit(&pv_done[l]);
@@ -344,6 +374,7 @@ attention_lanes_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
         const uint32_t quad = warp & 3u;
         const int row = static_cast<int>(quad * 32u + lane);
         const uint32_t s_addr = tmem_base + ((quad * 32u) << 16) + static_cast<uint32_t>(l * LANE_COLS);
+        const uint32_t p_addr = s_addr + P_OFF;
         const uint32_t o_addr = s_addr + O_OFF;
         const float scale2 = p.scale * LOG2E;
         const bool partial_last = (p.Lk != lk_pad);
@@ -359,20 +390,28 @@ attention_lanes_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                 const bool use_mask = kMaskAll || (j == nb - 1 && partial_last);
                 ab::mbar_wait_nocall(&s_full[l], blk_ctr & 1u);
                 ab::tc_fence_after();
-                uint32_t r[3][32];
+                uint32_t r[BK / 32][32];
 #pragma unroll
-                for (int c = 0; c < 3; ++c) ab::tmem_ld32(s_addr + c * 32, r[c]);
+                for (int c = 0; c < BK / 32; ++c) ab::tmem_ld32(s_addr + c * 32, r[c]);
                 ab::tmem_ld_wait();
+                ab::tc_fence_before();
+                ab::mbar_arrive(&s_read[l]);             // S(j) is in registers: the issuer may overwrite it with S(j + 1)
                 // ---- pass 1: t = scaled score + bias (+ mask), block maximum ----
                 float mb = -INFINITY;
                 const float* pb = pb_row + j * BK;
                 const float* mk = mask2 + j * BK;
                 if (use_mask) {
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) mb = chunk_scores<kBias, true>(r[c], scale2, pb + c * 32, mk + c * 32, mb);
+                    for (int c = 0; c < BK / 32; ++c) mb = chunk_scores<kBias, true>(r[c], scale2, pb + c * 32, mk + c * 32, mb);
                 } else {
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) mb = chunk_scores<kBias, false>(r[c], scale2, pb + c * 32, mk + c * 32, mb);
+                    for (int c = 0; c < BK / 32; ++c) mb = chunk_scores<kBias, false>(r[c], scale2, pb + c * 32, mk + c * 32, mb);
+                }
+                // P(j - 1) must have been consumed before P(j) overwrites its columns, and O must be quiescent for a rescale:
+                // P.V(j - 1) was issued when this block started and has normally retired by now
+                if (blk_ctr > 0) {
+                    ab::mbar_wait_nocall(&pv_done[l], (blk_ctr - 1) & 1u);
+                    ab::tc_fence_after();
                 }
                 // ---- lazy reference maximum ----
                 if (j == 0) {
@@ -380,7 +419,6 @@ attention_lanes_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                 } else {
                     const bool need = mb > m_ref + RESCALE_GAP;
                     if (__any_sync(0xffffffffu, need)) {
-                        // P.V(j-1) retired before S(j) was issued: O is final up to block j-1 and may be rescaled in place
                         const float f = need ? ex2_approx(m_ref - mb) : 1.0f;
                         if (need) m_ref = mb;
                         sum0 *= f;
@@ -396,13 +434,13 @@ attention_lanes_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                         }
                     }
                 }
-                // ---- pass 2: p = 2^(t - m_ref), packed P over the first half of the S columns ----
+                // ---- pass 2: p = 2^(t - m_ref), packed into the lane's P columns ----
                 const float neg_m = -m_ref;
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
+                for (int c = 0; c < BK / 32; ++c) {
                     uint32_t pk[16];
                     chunk_probs<kBF16>(r[c], pk, neg_m, sum0, sum1);
-                    tmem_st16(s_addr + c * 16, pk);
+                    tmem_st16(p_addr + c * 16, pk);
                 }
                 ab::tmem_st_wait();
                 ab::tc_fence_before();

@@ -1,6 +1,7 @@
-// EXPERIMENT (ATLAS_B200_ATTN_LANES=2): 48-key blocks with a double-buffered S per lane.  Round-2 visit C measured it no faster
-// than the 96-key kernel of attention_lanes.cu and wrong at the +48 column buffer; kept for the A/B record, not dispatched by default.
-// attention_lanes2_kernel: the encoder-shaped attention of Contriever and FiD (>= 2 query tiles per (segment, head), <= 576
+// First version of the three-lane kernel (96-key blocks, one S buffer per lane), kept selectable for A/B measurements
+// (ATLAS_B200_ATTN_LANES=3): csrc/attention_lanes.cu is the current one (64-key blocks, P in its own TMEM columns, S(j+1) issued
+// while the softmax of block j runs).  321 TFLOP/s at 160 x 12 x 384 x 384 (profiles/r02_attention_ab_visit_e.log).
+// attention_lanes96_kernel: the encoder-shaped attention of Contriever and FiD (>= 2 query tiles per (segment, head), <= 576
 // keys) - the second-generation forward kernel.  Same math and the same call (atlas_b200_attention_ex) as csrc/attention.cu:
 //     O[b, i, h, :] = softmax_j( scale * Q.K + rel_bias[h, j - i] + key_mask[b, j] (+ causal) ) V
 // replacing BertSelfAttention.forward (src/modeling_bert.py:328-366) and T5Attention.forward (src/modeling_t5.py:478-524).
@@ -13,16 +14,13 @@
 //     FiD passage are in flight at once.  Every lane has its own MMA-issuer thread, its own softmax warpgroup (one thread
 //     per query row: no cross-thread reductions, no named barriers) and its own barriers; the lanes only share the K / V
 //     stream.  While lane A waits for its P.V(j) -> S(j+1) hand-over, lanes B and C keep the MUFU / FMA pipes busy.
-//   * K and V stream ONCE per (segment, head) through a ring of 48-key chunks (6 KB, TMA, 128B swizzle) shared by the
+//   * K and V stream ONCE per (segment, head) through a ring of 96-key chunks (12 KB, TMA, 128B swizzle) shared by the
 //     lanes (a stage is released when every query tile of the item has consumed it): L2 -> SM traffic stays at
 //     (K + V) per item, the next item's chunks prefetch into the freed stages.
-//   * S is DOUBLE-BUFFERED per lane: the issuer runs S(j+1) = Q K_{j+1}^T into the other buffer while the softmax
-//     warpgroup works on block j, so a softmax warp never waits for an MMA round trip (v1 of this kernel had one 96-key
-//     S buffer per lane and spent half of its time in those waits: profiles/r02_attention_lanes.md).
-//   * Online softmax over 48-key blocks with a LAZY reference maximum: block 0 fixes m; a later block only triggers a
+//   * Online softmax over 96-key blocks with a LAZY reference maximum: block 0 fixes m; a later block only triggers a
 //     rescale of the 64-column O accumulator when its maximum exceeds m by more than 8 (log2 units), otherwise the stale m
 //     is kept (probabilities up to 2^8, exact in fp32 / harmless in 16 bits) - the common case costs nothing.
-//   * TMEM (480 of 512 columns): per lane S0 | S1 (48 fp32 columns each, overwritten in place by the packed 16-bit P) | O (64).
+//   * TMEM (480 of 512 columns): per lane S (96 fp32 columns, overwritten in place by the packed 16-bit P) | O (64).
 //   * The score pipeline per element: 1/4 LDS.128 (relative-position bias from FOUR alignment-shifted copies of the
 //     [2L - 1] table, so that every thread reads its diagonal run with 16-byte loads) + 1/2 FFMA2 + 1/2 FMNMX3 + 1/2 FADD2
 //     + 1 MUFU.EX2 + 1/2 FADD2 + 1/2 F2FP: 3.75 issue slots (packed f32x2 arithmetic and the 3-input max are sm_100
@@ -38,20 +36,20 @@
 
 #include <type_traits>
 
-namespace attn5 {
+namespace attn96 {
 
 constexpr int D = 64;
 constexpr int BQ = 128;                 // query rows per tile / lane
-constexpr int BK = 48;                  // keys per block (UMMA N of S, K extent of P.V)
+constexpr int BK = 96;                  // keys per block (UMMA N of S, K extent of P.V)
 constexpr int LANES = 3;
-constexpr int RING = 24;                // K / V chunk stages (6 KB each): a whole 576-key item, or 384 keys + prefetch
+constexpr int RING = 12;                // K / V chunk stages (12 KB each): a whole 576-key item, or 384 keys + prefetch
 constexpr int STAGE_BYTES = BK * D * 2;
 constexpr int Q_BYTES = BQ * D * 2;
-constexpr int MAX_BLOCKS = 12;          // <= 576 keys
+constexpr int MAX_BLOCKS = 6;           // <= 576 keys
 constexpr int MAXK = MAX_BLOCKS * BK;
 constexpr int THREADS = 512;
 constexpr int SM_THREADS = 128 * LANES;
-constexpr int LANE_COLS = 160;          // TMEM columns per lane: S / P buffer 0 at +0 (48), buffer 1 at +48, O at +96 (64)
+constexpr int LANE_COLS = 160;          // TMEM columns per lane: S / P at +0 (96), O at +96 (64)
 constexpr int O_OFF = 96;
 constexpr int TMEM_COLS = 512;
 constexpr int CPLEN = 1152;             // floats per shifted bias copy (>= MAXK + 512 + 4), multiple of 32
@@ -70,8 +68,6 @@ struct Params {
     float scale;
     float causal_value;
     float* lse_out;             // [B, H, Lq] or nullptr
-    int debug;                  // ATLAS_B200_ATTN_DEBUG bit mask (timing experiments only; results are wrong when set):
-                                //   1 = no bias / mask loads, 2 = no MUFU (p = t), 4 = no output stores, 8 = no S load
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -129,79 +125,60 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
     return d;
 }
 
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
-                 "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-                 : "memory");
-}
-
-// Pass 1 on the 48 keys of a block, in place: t = S * scale2 (+ bias2[j]) (+ mask2[j]) in the log2 domain; returns the block
-// maximum.  `pb` points at this thread's diagonal run of its alignment copy of the bias table (16-byte aligned: block and
-// unit offsets are multiples of 4); the key mask is the same for every row (broadcast 16-byte loads).  All twelve bias
-// loads are issued before the first use and four independent maxima are kept: the block is latency-, not issue-bound.
+// Pass 1 on one 32-key chunk, in place: r[jj] <- t = S * scale2 (+ bias2[j]) (+ mask2[j]) in the log2 domain; returns
+// max(mx, chunk maximum).  `pb` points at this thread's diagonal run of its alignment copy of the bias table (16-byte
+// aligned for j0 % 4 == 0); the key mask is the same for every row (broadcast 16-byte loads).
 template <bool kBias, bool kMask>
-__device__ __forceinline__ float block_scores(uint32_t (&r)[BK], float scale2, const float* __restrict__ pb,
-                                              const float* __restrict__ mask2) {
-    float4 add[BK / 4];
+__device__ __forceinline__ float chunk_scores(uint32_t (&r)[32], float scale2, const float* __restrict__ pb,
+                                              const float* __restrict__ mask2, float mx) {
 #pragma unroll
-    for (int q = 0; q < BK / 4; ++q) {
-        if constexpr (kBias) add[q] = *reinterpret_cast<const float4*>(pb + 4 * q);
-        else add[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    if constexpr (kMask) {
-#pragma unroll
-        for (int q = 0; q < BK / 4; ++q) {
+    for (int q = 0; q < 8; ++q) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        if constexpr (kBias) {
+            const float4 b = *reinterpret_cast<const float4*>(pb + 4 * q);
+            a0 = b.x, a1 = b.y, a2 = b.z, a3 = b.w;
+        }
+        if constexpr (kMask) {
             const float4 m = *reinterpret_cast<const float4*>(mask2 + 4 * q);
             if constexpr (kBias) {
-                fadd2(add[q].x, add[q].y, add[q].x, add[q].y, m.x, m.y);
-                fadd2(add[q].z, add[q].w, add[q].z, add[q].w, m.z, m.w);
+                fadd2(a0, a1, a0, a1, m.x, m.y);
+                fadd2(a2, a3, a2, a3, m.z, m.w);
             } else {
-                add[q] = m;
+                a0 = m.x, a1 = m.y, a2 = m.z, a3 = m.w;
             }
         }
-    }
-    float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-    for (int q = 0; q < BK / 4; ++q) {
         float t0, t1, t2, t3;
-        ffma2(t0, t1, __uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), scale2, add[q].x, add[q].y);
-        ffma2(t2, t3, __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]), scale2, add[q].z, add[q].w);
+        ffma2(t0, t1, __uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), scale2, a0, a1);
+        ffma2(t2, t3, __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]), scale2, a2, a3);
         r[4 * q] = __float_as_uint(t0);
         r[4 * q + 1] = __float_as_uint(t1);
         r[4 * q + 2] = __float_as_uint(t2);
         r[4 * q + 3] = __float_as_uint(t3);
-        mx[q & 1] = fmax3(mx[q & 1], t0, t1);
-        mx[2 + (q & 1)] = fmax3(mx[2 + (q & 1)], t2, t3);
+        mx = fmax3(mx, t0, t1);
+        mx = fmax3(mx, t2, t3);
     }
-    return fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+    return mx;
 }
 
-// Pass 2 on the block: p = 2^(t - m) packed to 16 bits (24 words); the row sum accumulates in two independent pairs.
+// Pass 2 on one chunk: p = 2^(t - m), packed to 16 bits; the partial sums accumulate as a pair.
 template <bool kBF16>
-__device__ __forceinline__ void block_probs(uint32_t (&r)[BK], uint32_t (&pk)[BK / 2], float neg_m, float (&sum)[4]) {
+__device__ __forceinline__ void chunk_probs(const uint32_t (&r)[32], uint32_t (&pk)[16], float neg_m, float& s0, float& s1) {
 #pragma unroll
-    for (int jj = 0; jj < BK; jj += 2) {
+    for (int jj = 0; jj < 32; jj += 2) {
         float d0, d1;
         fadd2(d0, d1, __uint_as_float(r[jj]), __uint_as_float(r[jj + 1]), neg_m, neg_m);
-        r[jj] = __float_as_uint(d0);
-        r[jj + 1] = __float_as_uint(d1);
-    }
-#pragma unroll
-    for (int jj = 0; jj < BK; ++jj) r[jj] = __float_as_uint(ex2_approx(__uint_as_float(r[jj])));
-#pragma unroll
-    for (int jj = 0; jj < BK; jj += 2) {
-        const int a = (jj >> 1) & 1;
-        fadd2(sum[2 * a], sum[2 * a + 1], sum[2 * a], sum[2 * a + 1], __uint_as_float(r[jj]), __uint_as_float(r[jj + 1]));
-        pk[jj >> 1] = ab::pack2_rn<kBF16>(__uint_as_float(r[jj]), __uint_as_float(r[jj + 1]));
+        const float e0 = ex2_approx(d0), e1 = ex2_approx(d1);
+        fadd2(s0, s1, s0, s1, e0, e1);
+        pk[jj >> 1] = ab::pack2_rn<kBF16>(e0, e1);
     }
 }
 
 template <bool kBF16>
 __global__ void __launch_bounds__(THREADS, 1)
-attention_lanes2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+attention_lanes96_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                        const __grid_constant__ CUtensorMap tmap_v, const Params p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t q_full[LANES], q_empty[LANES], s_full[LANES][2], p_ready[LANES][2], pv_done[LANES];
+    __shared__ __align__(8) uint64_t q_full[LANES], q_empty[LANES], s_full[LANES], p_ready[LANES], pv_done[LANES];
     __shared__ __align__(8) uint64_t kv_full[RING], kv_empty[RING], tab_full[2], tab_empty[2];
     __shared__ uint32_t tmem_base_smem;
     __shared__ int s_mask_flag[2];                              // this item's key mask has a non-zero entry
@@ -234,10 +211,8 @@ attention_lanes2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         for (int l = 0; l < LANES; ++l) {
             ab::mbar_init(&q_full[l], 1);
             ab::mbar_init(&q_empty[l], 1);
-            ab::mbar_init(&s_full[l][0], 1);
-            ab::mbar_init(&s_full[l][1], 1);
-            ab::mbar_init(&p_ready[l][0], 128);
-            ab::mbar_init(&p_ready[l][1], 128);
+            ab::mbar_init(&s_full[l], 1);
+            ab::mbar_init(&p_ready[l], 128);
             ab::mbar_init(&pv_done[l], 1);
         }
         for (int s = 0; s < RING; ++s) {
@@ -314,16 +289,8 @@ attention_lanes2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
                                         ab::kEvictNormal);
                         ++chunk_ctr;
                     };
-                    // the first two key blocks go first (they land in stages the previous item no longer needs, so they
-                    // are resident when the lanes reach this item), then the query tiles (each waits for its lane's last
-                    // S MMA of the previous tile), then the rest of K / V
-                    const int head_blocks = nb < 2 ? nb : 2;
-                    for (int j = 0; j < head_blocks; ++j) {
-                        load_chunk(&tmap_k, p.k_col0, j);
-                        load_chunk(&tmap_v, p.v_col0, j);
-                    }
                     for (int qt = 0; qt < n_qt && qt < LANES; ++qt) load_q(qt);
-                    for (int j = head_blocks; j < nb; ++j) {
+                    for (int j = 0; j < nb; ++j) {
                         load_chunk(&tmap_k, p.k_col0, j);
                         load_chunk(&tmap_v, p.v_col0, j);
                     }
@@ -332,52 +299,40 @@ attention_lanes2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
                 __syncwarp();
             }
         } else if (lane == 0) {
-            // ===================== MMA issuer of lane `l` =====================
-            // Block n (global count over this lane's tiles) uses S / P buffer n % 2.  Order per tile:
-            //   S(0) | S(1), P.V(0) | S(2), P.V(1) | ... | P.V(nb-1)      - S runs one block ahead of the softmax.
-            // S(n) overwrites the buffer that held P(n-2): P.V(n-2) must have retired (pv_done), which it has long before
-            // the softmax of block n-1 ends.
+            // ===================== MMA issuer of lane `l`: S(j) = Q K_j^T, then O (+)= P(j) V_j =====================
             const int l = static_cast<int>(warp) - 1;
             constexpr uint32_t idesc_s = ab::umma_idesc_f16(BQ, BK, kBF16);
             constexpr uint32_t idesc_o = ab::umma_idesc_f16(BQ, D, kBF16) | (1u << 16);   // B = V rows, MN-major
-            const uint32_t lane_tmem = tmem_base + l * LANE_COLS;
-            const uint32_t o_tmem = lane_tmem + O_OFF;
+            const uint32_t s_tmem = tmem_base + l * LANE_COLS;
+            const uint32_t o_tmem = s_tmem + O_OFF;
             const uint64_t qdesc = ab::umma_desc_k_sw128(aQ + l * Q_BYTES);
-            uint32_t tile_ctr = 0, blk_ctr = 0;     // blk_ctr: blocks whose P.V has been issued
+            uint32_t tile_ctr = 0, blk_ctr = 0;
             int item_it = 0;
-            // `wait_pv`: index of the P.V completion to wait for (always the LATEST one issued so far, so the parity test is
-            // unambiguous); -1 = none.  S(n) needs P.V(n-2) retired; at a tile start all P.V of the previous tile are issued.
-            auto issue_s = [&](uint32_t n, uint32_t ck, bool last_of_tile, int wait_pv) {
-                const uint32_t sk = ck % RING;
-                ab::mbar_wait_nocall(&kv_full[sk], (ck / RING) & 1u);
-                if (wait_pv >= 0) ab::mbar_wait_nocall(&pv_done[l], static_cast<uint32_t>(wait_pv) & 1u);
-                ab::tc_fence_after();
-                const uint64_t kdesc = ab::umma_desc_k_sw128(aRing + sk * STAGE_BYTES);
-                const uint32_t s_tmem = lane_tmem + (n & 1u) * BK;
-#pragma unroll
-                for (int k = 0; k < D / 16; ++k)
-                    ab::umma_ss<1>(s_tmem, qdesc + ((k * 32) >> 4), kdesc + ((k * 32) >> 4), idesc_s, k != 0 ? 1u : 0u);
-                ab::umma_commit(&kv_empty[sk]);
-                if (last_of_tile) ab::umma_commit(&q_empty[l]);
-                ab::umma_commit(&s_full[l][n & 1u]);
-            };
             for (int it = it_begin; it < it_end; ++it, ++item_it) {
                 const uint32_t chunk_base = static_cast<uint32_t>(item_it) * 2u * nb;
                 for (int qt = l; qt < n_qt; qt += LANES, ++tile_ctr) {
                     ab::mbar_wait_nocall(&q_full[l], tile_ctr & 1u);
-                    issue_s(blk_ctr, chunk_base, nb == 1, static_cast<int>(blk_ctr) - 1);
                     for (int j = 0; j < nb; ++j, ++blk_ctr) {
-                        if (j + 1 < nb) issue_s(blk_ctr + 1, chunk_base + 2u * (j + 1), j + 2 == nb, static_cast<int>(blk_ctr) - 1);
-                        const uint32_t cv = chunk_base + 2u * j + 1u;
-                        const uint32_t sv = cv % RING;
+                        const uint32_t ck = chunk_base + 2u * j, cv = ck + 1u;
+                        const uint32_t sk = ck % RING, sv = cv % RING;
+                        ab::mbar_wait_nocall(&kv_full[sk], (ck / RING) & 1u);
+                        // P(j-1) lives in the S columns: its P.V must have retired before S(j) overwrites them
+                        if (blk_ctr > 0) ab::mbar_wait_nocall(&pv_done[l], (blk_ctr - 1) & 1u);
+                        ab::tc_fence_after();
+                        const uint64_t kdesc = ab::umma_desc_k_sw128(aRing + sk * STAGE_BYTES);
+#pragma unroll
+                        for (int k = 0; k < D / 16; ++k)
+                            ab::umma_ss<1>(s_tmem, qdesc + ((k * 32) >> 4), kdesc + ((k * 32) >> 4), idesc_s, k != 0 ? 1u : 0u);
+                        ab::umma_commit(&kv_empty[sk]);
+                        if (j == nb - 1) ab::umma_commit(&q_empty[l]);
+                        ab::umma_commit(&s_full[l]);
                         ab::mbar_wait_nocall(&kv_full[sv], (cv / RING) & 1u);
-                        ab::mbar_wait_nocall(&p_ready[l][blk_ctr & 1u], (blk_ctr >> 1) & 1u);
+                        ab::mbar_wait_nocall(&p_ready[l], blk_ctr & 1u);
                         ab::tc_fence_after();
                         const uint64_t vdesc = umma_desc_mn_sw128(aRing + sv * STAGE_BYTES);
-                        const uint32_t p_tmem = lane_tmem + (blk_ctr & 1u) * BK;
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k)
-                            ab::umma_ts<1>(o_tmem, p_tmem + k * 8, vdesc + static_cast<uint64_t>((k * 2048) >> 4), idesc_o,
+                            ab::umma_ts<1>(o_tmem, s_tmem + k * 8, vdesc + static_cast<uint64_t>((k * 2048) >> 4), idesc_o,
                                            (j != 0 || k != 0) ? 1u : 0u);
                         ab::umma_commit(&kv_empty[sv]);
                         ab::umma_commit(&pv_done[l]);
@@ -391,57 +346,48 @@ attention_lanes2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         const int l = static_cast<int>(warp - 4u) >> 2;
         const uint32_t quad = warp & 3u;
         const int row = static_cast<int>(quad * 32u + lane);
-        const uint32_t lane_addr = tmem_base + ((quad * 32u) << 16) + static_cast<uint32_t>(l * LANE_COLS);
-        const uint32_t o_addr = lane_addr + O_OFF;
+        const uint32_t s_addr = tmem_base + ((quad * 32u) << 16) + static_cast<uint32_t>(l * LANE_COLS);
+        const uint32_t o_addr = s_addr + O_OFF;
         const float scale2 = p.scale * LOG2E;
         const bool partial_last = (p.Lk != lk_pad);
         uint32_t blk_ctr = 0;
 
         // all key blocks of one query tile; kBias / kMaskAll are tile-uniform, the last block of a ragged segment always
         // applies the mask (its pad keys carry -inf)
-        auto run_tile = [&](auto bias_tag, auto mask_tag, const float* pb_row, const float* mask2, float& m_ref, float& sum_out) {
+        auto run_tile = [&](auto bias_tag, auto mask_tag, const float* pb_row, const float* mask2, float& m_ref, float& sum0,
+                            float& sum1) {
             constexpr bool kBias = decltype(bias_tag)::value;
             constexpr bool kMaskAll = decltype(mask_tag)::value;
-            float sum[4] = {0.f, 0.f, 0.f, 0.f};
             for (int j = 0; j < nb; ++j, ++blk_ctr) {
                 const bool use_mask = kMaskAll || (j == nb - 1 && partial_last);
-                const uint32_t s_addr = lane_addr + (blk_ctr & 1u) * BK;
-                ab::mbar_wait_nocall(&s_full[l][blk_ctr & 1u], (blk_ctr >> 1) & 1u);
+                ab::mbar_wait_nocall(&s_full[l], blk_ctr & 1u);
                 ab::tc_fence_after();
-                uint32_t r[BK];
-                if (!(p.debug & 8)) {
-                    uint32_t r0[32], r1[16];
-                    ab::tmem_ld32(s_addr, r0);
-                    tmem_ld16(s_addr + 32, r1);
-                    ab::tmem_ld_wait();
+                uint32_t r[3][32];
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) r[e] = r0[e];
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) r[32 + e] = r1[e];
-                } else {
-#pragma unroll
-                    for (int e = 0; e < BK; ++e) r[e] = __float_as_uint(0.001f * static_cast<float>(e + row));
-                }
+                for (int c = 0; c < 3; ++c) ab::tmem_ld32(s_addr + c * 32, r[c]);
+                ab::tmem_ld_wait();
                 // ---- pass 1: t = scaled score + bias (+ mask), block maximum ----
+                float mb = -INFINITY;
                 const float* pb = pb_row + j * BK;
                 const float* mk = mask2 + j * BK;
-                float mb;
-                if (p.debug & 1) mb = block_scores<false, false>(r, scale2, pb, mk);
-                else if (use_mask) mb = block_scores<kBias, true>(r, scale2, pb, mk);
-                else mb = block_scores<kBias, false>(r, scale2, pb, mk);
+                if (use_mask) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) mb = chunk_scores<kBias, true>(r[c], scale2, pb + c * 32, mk + c * 32, mb);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) mb = chunk_scores<kBias, false>(r[c], scale2, pb + c * 32, mk + c * 32, mb);
+                }
                 // ---- lazy reference maximum ----
                 if (j == 0) {
                     m_ref = (mb == -INFINITY) ? 0.f : mb;
                 } else {
                     const bool need = mb > m_ref + RESCALE_GAP;
                     if (__any_sync(0xffffffffu, need)) {
-                        // O may only be touched once P.V(j-1) has retired (S runs ahead of it): rare path, explicit wait
-                        ab::mbar_wait_nocall(&pv_done[l], (blk_ctr - 1) & 1u);
-                        ab::tc_fence_after();
+                        // P.V(j-1) retired before S(j) was issued: O is final up to block j-1 and may be rescaled in place
                         const float f = need ? ex2_approx(m_ref - mb) : 1.0f;
                         if (need) m_ref = mb;
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) sum[e] *= f;
+                        sum0 *= f;
+                        sum1 *= f;
 #pragma unroll 1
                         for (int cc = 0; cc < D / 16; ++cc) {
                             uint32_t ro[16];
@@ -453,31 +399,18 @@ attention_lanes2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
                         }
                     }
                 }
-                // ---- pass 2: p = 2^(t - m_ref), packed P over the first half of this S buffer ----
-                uint32_t pk[BK / 2];
-                if (p.debug & 2) {
+                // ---- pass 2: p = 2^(t - m_ref), packed P over the first half of the S columns ----
+                const float neg_m = -m_ref;
 #pragma unroll
-                    for (int e = 0; e < BK / 2; ++e) {
-                        pk[e] = ab::pack2_rn<kBF16>(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1]));
-                        sum[0] += __uint_as_float(r[2 * e]);
-                    }
-                } else {
-                    block_probs<kBF16>(r, pk, -m_ref, sum);
-                }
-                {
-                    uint32_t p0[16], p1[8];
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) p0[e] = pk[e];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) p1[e] = pk[16 + e];
-                    tmem_st16(s_addr, p0);
-                    tmem_st8(s_addr + 16, p1);
+                for (int c = 0; c < 3; ++c) {
+                    uint32_t pk[16];
+                    chunk_probs<kBF16>(r[c], pk, neg_m, sum0, sum1);
+                    tmem_st16(s_addr + c * 16, pk);
                 }
                 ab::tmem_st_wait();
                 ab::tc_fence_before();
-                ab::mbar_arrive(&p_ready[l][blk_ctr & 1u]);
+                ab::mbar_arrive(&p_ready[l]);
             }
-            sum_out = (sum[0] + sum[1]) + (sum[2] + sum[3]);
         };
 
         int item_it = 0;
@@ -491,17 +424,18 @@ attention_lanes2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
                 const int i = qt * BQ + row;                          // query position inside the segment
                 const int off = max(p.Lq - 1 - i, 0);                 // bias index = j + off (clamped for pad rows)
                 const float* pb_row = s_bias + (off & 3) * CPSTRIDE + (off & ~3);
-                float m_ref = 0.f, sum = 0.f;
+                float m_ref = 0.f, sum0 = 0.f, sum1 = 0.f;
                 if (has_bias) {
-                    if (item_mask) run_tile(std::true_type{}, std::true_type{}, pb_row, mask2, m_ref, sum);
-                    else run_tile(std::true_type{}, std::false_type{}, pb_row, mask2, m_ref, sum);
+                    if (item_mask) run_tile(std::true_type{}, std::true_type{}, pb_row, mask2, m_ref, sum0, sum1);
+                    else run_tile(std::true_type{}, std::false_type{}, pb_row, mask2, m_ref, sum0, sum1);
                 } else {
-                    if (item_mask) run_tile(std::false_type{}, std::true_type{}, pb_row, mask2, m_ref, sum);
-                    else run_tile(std::false_type{}, std::false_type{}, pb_row, mask2, m_ref, sum);
+                    if (item_mask) run_tile(std::false_type{}, std::true_type{}, pb_row, mask2, m_ref, sum0, sum1);
+                    else run_tile(std::false_type{}, std::false_type{}, pb_row, mask2, m_ref, sum0, sum1);
                 }
                 // ---- output: O / sum ----
                 ab::mbar_wait_nocall(&pv_done[l], (blk_ctr - 1) & 1u);
                 ab::tc_fence_after();
+                const float sum = sum0 + sum1;
                 const float inv = 1.0f / sum;
                 if (p.lse_out != nullptr && i < p.Lq)
                     p.lse_out[(static_cast<size_t>(b) * p.H + h) * p.Lq + i] = m_ref * (1.0f / LOG2E) + __logf(sum);
@@ -510,7 +444,7 @@ attention_lanes2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
                     uint32_t ro[32];
                     ab::tmem_ld32(o_addr + cc * 32, ro);
                     ab::tmem_ld_wait();
-                    if (i < p.Lq && !(p.debug & 4)) {
+                    if (i < p.Lq) {
                         uint4* dst = reinterpret_cast<uint4*>(p.O + (static_cast<size_t>(b) * p.Lq + i) * p.ldo + h * D + cc * 32);
 #pragma unroll
                         for (int v4 = 0; v4 < 4; ++v4)
@@ -535,15 +469,15 @@ attention_lanes2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     }
 }
 
-}  // namespace attn5
+}  // namespace attn96
 
 // Launched by atlas_b200_attention_ex (csrc/attention.cu) for >= 2 query tiles per item; returns ATLAS_B200_OK or an error.
-int atlas_b200_attention_lanes2_launch(const void* q, int64_t ldq, int32_t q_col0, const void* k, int64_t ldk, int32_t k_col0,
+int atlas_b200_attention_lanes96_launch(const void* q, int64_t ldq, int32_t q_col0, const void* k, int64_t ldk, int32_t k_col0,
                                       const void* v, int64_t ldv, int32_t v_col0, void* out, int64_t ldo,
                                       const float* add_mask, const float* bias_delta, int32_t B, int32_t H, int32_t Lq,
                                       int32_t Lk, float scale, float causal_value, float* lse_out, int32_t is_bf16,
                                       cudaStream_t s) {
-    using namespace attn5;
+    using namespace attn96;
     AB_REQUIRE(Lk <= MAXK && Lq <= 512, "attention_lanes: Lq <= 512 and Lk <= %d", MAXK);
     CUtensorMap tq, tk, tv;
     int rc = abh::make_tmap_2d_16bit(&tq, q, static_cast<uint64_t>(B) * Lq, static_cast<uint64_t>(q_col0 + H * D),
@@ -565,23 +499,21 @@ int atlas_b200_attention_lanes2_launch(const void* q, int64_t ldq, int32_t q_col
     p.scale = scale;
     p.causal_value = causal_value;
     p.lse_out = lse_out;
-    static const int dbg = getenv("ATLAS_B200_ATTN_DEBUG") ? atoi(getenv("ATLAS_B200_ATTN_DEBUG")) : 0;
-    p.debug = dbg;
     const int items = B * H;
     const int grid = items < abh::num_sms() ? items : abh::num_sms();
     static bool attr_set[2] = {false, false};
     if (is_bf16) {
         if (!attr_set[0]) {
-            AB_CUDA_CHECK(cudaFuncSetAttribute(attention_lanes2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+            AB_CUDA_CHECK(cudaFuncSetAttribute(attention_lanes96_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
             attr_set[0] = true;
         }
-        attention_lanes2_kernel<true><<<grid, THREADS, SMEM_BYTES, s>>>(tq, tk, tv, p);
+        attention_lanes96_kernel<true><<<grid, THREADS, SMEM_BYTES, s>>>(tq, tk, tv, p);
     } else {
         if (!attr_set[1]) {
-            AB_CUDA_CHECK(cudaFuncSetAttribute(attention_lanes2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+            AB_CUDA_CHECK(cudaFuncSetAttribute(attention_lanes96_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
             attr_set[1] = true;
         }
-        attention_lanes2_kernel<false><<<grid, THREADS, SMEM_BYTES, s>>>(tq, tk, tv, p);
+        attention_lanes96_kernel<false><<<grid, THREADS, SMEM_BYTES, s>>>(tq, tk, tv, p);
     }
     AB_CUDA_CHECK(cudaGetLastError());
     return ATLAS_B200_OK;

@@ -157,6 +157,13 @@ __device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint64_t
         : "memory");
 }
 
+// L2 prefetch of a tensor-map box (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int32_t c0, int32_t c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0),
+                 "r"(c1)
+                 : "memory");
+}
+
 // 2-CTA + multicast: the box lands at the same shared-memory offset in every CTA of `cta_mask`; each destination's bytes
 // are counted on the barrier at this offset in the leader of THAT destination's CTA pair.
 __device__ __forceinline__ void tma_load_2d_2sm_mc(const CUtensorMap* map, uint64_t* bar, void* smem_dst, int32_t c0,

@@ -77,6 +77,7 @@ struct Params {
     // splitk_reduce_kernel sums the partials and rounds once.  splits == 1 / C32 == nullptr: the ordinary epilogues.
     int splits, kb_per_split;
     float* C32;
+    int l2_prefetch;      // producer prefetches the next work item's A rows into L2 (ATLAS_B200_GEMM_PREFETCH=0: off)
 };
 
 template <bool kBF16>
@@ -206,7 +207,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 const int a_row = m_blk * TILE_M + static_cast<int>(pair_id) * PAIR_M + static_cast<int>(cta_rank) * BLOCK_M;
                 const int b_row = n_blk * BLOCK_N + static_cast<int>(cta_rank) * C::B_ROWS;
                 const int kb0 = split * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
+                // L2 prefetch of the A rows of this group's NEXT work item (K-major activations stream from HBM once per
+                // 256-row block; the ring covers ~6 x 512 clk of latency, an HBM miss costs more).  The groups that work on
+                // the column blocks of one row block run side by side: only the one whose next item has n_blk == 0 prefetches.
+                int pf_row = -1;
+                if constexpr (!kTN) {
+                    const int t2 = t + num_groups;
+                    if (p.l2_prefetch && t2 < num_tiles && (t2 / p.splits) % num_n == 0)
+                        pf_row = ((t2 / p.splits) / num_n) * TILE_M + static_cast<int>(pair_id) * PAIR_M +
+                                 static_cast<int>(cta_rank) * BLOCK_M;
+                }
                 for (int kb = kb0; kb < kb1; ++kb) {
+                    if (pf_row >= 0) ab::tma_prefetch_2d(&tmap_a, kb * BLOCK_K, pf_row);
                     ab::mbar_wait(&empty_bar[stage], phase ^ 1u, 11);
                     uint8_t* st = smem_gen + stage * C::STAGE_BYTES;
                     if constexpr (kTN) {
@@ -558,6 +570,8 @@ int atlas_b200_linear_ex(const void* A, int64_t lda, const void* W, int64_t ldw,
     p.splits = 1;
     p.kb_per_split = (K + BLOCK_K - 1) / BLOCK_K;
     p.C32 = nullptr;
+    static const int pf_on = (getenv("ATLAS_B200_GEMM_PREFETCH") != nullptr && getenv("ATLAS_B200_GEMM_PREFETCH")[0] == '0') ? 0 : 1;
+    p.l2_prefetch = pf_on;
     p.row_ss = row_ss;
     p.out_ss = out_ss;
     p.rs_eps = rs_eps;
@@ -574,9 +588,10 @@ int atlas_b200_linear_ex(const void* A, int64_t lda, const void* W, int64_t ldw,
     // 256 x 256 pair tiles once there are enough of them to fill the 74 CTA pairs (encoder-sized M)
     const bool pair = N >= 256 && M >= 256 &&
                       (static_cast<int64_t>((M + 255) / 256) * ((N + 255) / 256) >= abh::num_sms() / 2);
-    // 4-CTA clusters (two pairs sharing the W tile through TMA multicast) once every resident cluster gets >= 2 work items:
-    // ATLAS_B200_GEMM_QUAD=0 keeps the pair kernel (A/B measurements)
-    static const bool quad_off = getenv("ATLAS_B200_GEMM_QUAD") != nullptr && getenv("ATLAS_B200_GEMM_QUAD")[0] == '0';
+    // 4-CTA clusters (two pairs sharing the W tile through TMA multicast), opt-in with ATLAS_B200_GEMM_QUAD=1: measured
+    // 3 - 5 % SLOWER than the pair kernel on the FiD-base shapes (profiles/r02_gemm.md) - the mainloop is bound by the
+    // latency of the A stream, not by L2 -> SM throughput, and the two pairs of a cluster run in lockstep.
+    static const bool quad_off = getenv("ATLAS_B200_GEMM_QUAD") == nullptr || getenv("ATLAS_B200_GEMM_QUAD")[0] != '1';
     static const bool no_pair = getenv("ATLAS_B200_GEMM_NO_PAIR") != nullptr;   // A/B measurements
     const int qc = (pair && !quad_off && !no_pair && M >= 512) ? (is_bf16 ? quad_clusters<true>() : quad_clusters<false>()) : 0;
     const bool quad = qc > 0 && (static_cast<int64_t>((M + 511) / 512) * ((N + 255) / 256) >= 2ll * qc);
@@ -647,6 +662,7 @@ int atlas_b200_linear_wgrad(const void* dY, int64_t lddy, const void* X, int64_t
         return ATLAS_B200_OK;
     }
     Params p;
+    p.l2_prefetch = 0;
     p.row_ss = nullptr;
     p.out_ss = nullptr;
     p.rs_eps = 0.f;

@@ -223,13 +223,16 @@ def test_fid_train_step_with_dropout(dev):
     l2, _ = _step(reader, ids, mask, labels, 6)
     assert math.isfinite(l1) and l1 == l1b and l1 != l2
     assert all(torch.isfinite(v).all() for v in g1.values()) and len(g1) > 40
+    def same(a, b):     # norm-weight / embedding gradients accumulate with fp32 atomics: equal up to summation order;
+        return float((a - b).abs().max()) <= 1e-3 * float(a.abs().max()) + 1e-7     # a different MASK would be an O(1) change
+
     for n in g1:
-        assert torch.equal(g1[n], g1b[n]), n
+        assert same(g1[n], g1b[n]), n
     reader.gradient_checkpointing_enable()
     l1c, g1c = _step(reader, ids, mask, labels, 5)
     assert l1c == l1
     for n in g1:
-        assert torch.equal(g1[n], g1c[n]), f"checkpointed recompute drew different masks: {n}"
+        assert same(g1[n], g1c[n]), f"checkpointed recompute drew different masks: {n}"
     # dropout really acts: the undropped loss differs, and is what --dropout 0 gives
     ref0, ids0, mask0, labels0 = _tiny_fid(dev, 0.0)
     ref0.train()
@@ -271,7 +274,7 @@ def test_contriever_train_step_with_dropout(dev):
     assert torch.equal(e1, e1b) and not torch.equal(e1, e2)
     assert all(torch.isfinite(v).all() for v in g1.values())
     for n in g1:
-        assert torch.equal(g1[n], g1b[n]), n
+        assert float((g1[n] - g1b[n]).abs().max()) <= 1e-3 * float(g1[n].abs().max()) + 1e-7, n
     model.eval()
     with torch.no_grad():
         ee = model(input_ids=ids, attention_mask=mask).float()

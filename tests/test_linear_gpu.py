@@ -162,7 +162,7 @@ def test_quad_cluster_multicast_tiles(dev, dtype, M, N, K, epi):
     y = ops.linear(x, w, bias if epi in (1, 2, 3) else None, res if epi == 3 else None, epilogue=epi)
     ok, err = _close(y, _ref(x, w, bias, res, epi), dtype)
     assert ok, f"max abs err {err}"
-    # the pair kernel in a child process (the switch is read once per process)
+    # the quad-cluster kernel in a child process (the switch is read once per process; the default is the pair kernel)
     code = (
         "import sys, math, torch; sys.path.insert(0, %r)\n"
         "from atlas_b200 import ops\n"
@@ -177,7 +177,7 @@ def test_quad_cluster_multicast_tiles(dev, dtype, M, N, K, epi):
         "torch.save(y.cpu(), sys.argv[1])\n"
     ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), M, N, K, epi, str(dtype).split(".")[1])
     path = f"/tmp/_pair_{M}_{N}_{K}_{epi}_{str(dtype).split('.')[1]}.pt"
-    env = dict(os.environ, ATLAS_B200_GEMM_QUAD="0")
+    env = dict(os.environ, ATLAS_B200_GEMM_QUAD="1")     # the child runs the opt-in quad-cluster kernel
     subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=300)
     y_pair = torch.load(path)
     os.remove(path)
