@@ -916,16 +916,25 @@ int atlas_b200_attention_bwd_train(const void* q, int64_t ldq, int32_t q_col0, c
         attr_set = true;
     }
     abh::prof_begin(s, abh::PROF_ATTENTION_BWD);
-    // experimental tcgen05 kernels: 1 = dQ kernel, 2 = dQ + dK/dV kernels (see the status notes in attention_bwd_tc*.cu)
+    // tcgen05 kernels (attention_bwd_tc*.cu), ATLAS_B200_ATTN_BWD_TC: 1 = dQ kernel, 2 = dQ + dK/dV kernels, 3 = dK/dV kernel
+    // only (the dQ kernel is not yet faster than its warp-MMA twin; the dK/dV kernel is: 0.23 vs 0.33 ms at
+    // 80 x 12 x 384 x 384).  The warp-MMA dQ kernel runs first in mode 3: it writes D = rowsum(dO o O), which the
+    // tcgen05 dK/dV kernel reads.
     static const int tc_level = getenv("ATLAS_B200_ATTN_BWD_TC") ? atoi(getenv("ATLAS_B200_ATTN_BWD_TC")) : 0;
     const bool use_tc = tc_level >= 1 && drop.thr16 == 0u;     // the tcgen05 kernels do not implement dropout
     bool dq_done = false, dkv_done = false;
     if (v2 && use_tc && dq_accum == nullptr) {
-        const int rc = atlas_b200_attn_bwd_dq_tc(q, ldq, q_col0, k, ldk, k_col0, v, ldv, v_col0, out, ldo, dout, lddo, dq, lddq,
-                                                 dq_col0, add_mask, bias_delta, dbias_delta, lse, dsum, B, H, Lq, Lk, scale,
-                                                 causal_value, is_bf16, s);
-        if (rc == ATLAS_B200_OK) dq_done = true;
-        else if (rc != ATLAS_B200_EUNSUPPORTED) return rc;
+        if (tc_level != 3) {
+            const int rc = atlas_b200_attn_bwd_dq_tc(q, ldq, q_col0, k, ldk, k_col0, v, ldv, v_col0, out, ldo, dout, lddo, dq,
+                                                     lddq, dq_col0, add_mask, bias_delta, dbias_delta, lse, dsum, B, H, Lq, Lk,
+                                                     scale, causal_value, is_bf16, s);
+            if (rc == ATLAS_B200_OK) dq_done = true;
+            else if (rc != ATLAS_B200_EUNSUPPORTED) return rc;
+        } else if (Lq <= 512 && Lk <= 512) {
+            if (is_bf16) attn_bwd_dq2_kernel<true><<<static_cast<unsigned>(nq_ctas), THREADS, smem_dq, s>>>(p);
+            else attn_bwd_dq2_kernel<false><<<static_cast<unsigned>(nq_ctas), THREADS, smem_dq, s>>>(p);
+            dq_done = true;
+        }
         if (dq_done && tc_level >= 2) {
             const int rc2 = atlas_b200_attn_bwd_dkv_tc(q, ldq, q_col0, k, ldk, k_col0, v, ldv, v_col0, dout, lddo, dk, lddk,
                                                        dk_col0, dv, lddv, dv_col0, add_mask, bias_delta, lse, dsum, B, H, Lq, Lk,
