@@ -51,7 +51,10 @@ struct Cfg {
     static constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
+    // epilogue staging (BLOCK_N = 256 kernels): 4 KB per epilogue warp = 32 rows x 128 B (64 output columns), 128B swizzle,
+    // the source of the TMA stores of C
+    static constexpr int EPI_STAGE_BYTES = BLOCK_N == 256 ? EPI_WARPS * 4096 : 0;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024;
     static constexpr int TMEM_COLS = 2 * BLOCK_N;  // 256 or 512 (power of two)
     static constexpr int UMMA_M = BLOCK_M * CTAS;
 };
@@ -78,6 +81,7 @@ struct Params {
     int splits, kb_per_split;
     float* C32;
     int l2_prefetch;      // producer prefetches the next work item's A rows into L2 (ATLAS_B200_GEMM_PREFETCH=0: off)
+    int tma_store;        // 16-bit C leaves through shared memory + TMA stores (BLOCK_N = 256 kernels; tmap_c is valid)
 };
 
 template <bool kBF16>
@@ -144,7 +148,8 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint3
 //              pairs' MMAs have consumed it (empty barrier counts 2, commits multicast to all four CTAs).
 template <bool kBF16, int BLOCK_N, bool kPair, bool kTN, bool kQuad>
 __global__ void __launch_bounds__(THREADS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+            const __grid_constant__ CUtensorMap tmap_c, const Params p) {
     using C = Cfg<BLOCK_N, kPair>;
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[C::STAGES];
@@ -341,6 +346,140 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             const float rscale = (p.row_ss != nullptr && row < p.M)
                                      ? rsqrtf(__ldg(p.row_ss + row) / static_cast<float>(p.K) + p.rs_eps) : 1.0f;
             float ss_out = 0.f;
+            if constexpr (BLOCK_N == 256) {
+                if (p.tma_store && p.C32 == nullptr) {
+                    // ---- staged epilogue: accumulator rows -> 16-bit -> this warp's swizzled shared tile -> ONE TMA store per
+                    // 64 output columns (full 128-byte lines) instead of 32-row-strided 16-byte stores per thread; the residual
+                    // rows arrive through coalesced 128-byte loads and the same tile (a transpose scratch).
+                    uint8_t* stg = smem_gen + C::STAGES * C::STAGE_BYTES + (warp - 4u) * 4096u;
+                    const uint32_t swz = lane & 7u;
+                    const bool gated = p.epi == EPI_GATED;
+                    const int n_groups = gated ? 1 : 2;                       // groups of 64 OUTPUT columns of this warp
+                    const int row_warp = m_blk * TILE_M + static_cast<int>(pair_id) * PAIR_M + static_cast<int>(cta_rank) * BLOCK_M +
+                                         static_cast<int>(lg * 32);
+                    const int acc_col_w = static_cast<int>(half) * (BLOCK_N / 2);   // first accumulator column of this warp
+                    const int out_col_w = gated ? n_blk * (BLOCK_N / 2) + static_cast<int>(half) * (BLOCK_N / 4)
+                                                : n_blk * BLOCK_N + acc_col_w;
+                    const bool use_res = p.epi == EPI_RESIDUAL;
+                    uint4 rq[8];                                             // residual pieces in flight (coalesced layout)
+                    auto load_res = [&](int g) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int rr = row_warp + static_cast<int>(lane >> 3) + 4 * i;
+                            const int cc = out_col_w + g * 64 + static_cast<int>(lane & 7u) * 8;
+                            rq[i] = (rr < p.M && cc < p.N)
+                                        ? __ldg(reinterpret_cast<const uint4*>(p.residual + static_cast<size_t>(rr) * p.ldr + cc))
+                                        : make_uint4(0u, 0u, 0u, 0u);
+                        }
+                    };
+                    if (use_res) load_res(0);                                 // in flight while the MMAs of this tile finish
+                    ab::mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1, 14);
+                    ab::tc_fence_after();
+#pragma unroll 1
+                    for (int g = 0; g < n_groups; ++g) {
+                        if (lane == 0) ab::tma_store_wait_read();              // the previous store has read the tile
+                        __syncwarp();
+                        uint4 rown[8];                                        // this thread's residual row, 64 columns
+                        if (use_res) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const uint32_t rr = (lane >> 3) + 4u * i;
+                                *reinterpret_cast<uint4*>(stg + rr * 128u + (((lane & 7u) ^ (rr & 7u)) << 4)) = rq[i];
+                            }
+                            __syncwarp();
+#pragma unroll
+                            for (int k = 0; k < 8; ++k)
+                                rown[k] = *reinterpret_cast<const uint4*>(stg + lane * 128u + ((static_cast<uint32_t>(k) ^ swz) << 4));
+                            if (g + 1 < n_groups) load_res(g + 1);
+                        }
+                        const int chunks_in_group = gated ? 4 : 2;
+#pragma unroll 1
+                        for (int cg = 0; cg < chunks_in_group; ++cg) {
+                            const int c = gated ? cg : g * 2 + cg;            // 32-column accumulator chunk of this warp
+                            const int col_local = acc_col_w + c * 32;
+                            const int col0 = n_blk * BLOCK_N + col_local;
+                            uint32_t r[32];
+                            ab::tmem_ld32(tmem_base + ((lg * 32u) << 16) + buf * BLOCK_N + col_local, r);
+                            ab::tmem_ld_wait();
+                            if (c == CHUNKS - 1) {
+                                ab::tc_fence_before();
+                                __syncwarp();
+                                if (lane == 0) {
+                                    if (leader) ab::mbar_arrive(&tmem_empty_bar[buf]);
+                                    else ab::mbar_arrive_cluster(&tmem_empty_bar[buf], 2 * pair_id);
+                                }
+                            }
+                            float v[32];
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * rscale;
+                            if (p.epi != EPI_NONE && !gated && p.bias != nullptr) {
+#pragma unroll
+                                for (int j8 = 0; j8 < 4; ++j8) {
+                                    if (col0 + j8 * 8 < p.N) {
+                                        const uint4 b = __ldg(reinterpret_cast<const uint4*>(p.bias + col0 + j8 * 8));
+                                        const uint32_t w[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                                        for (int e = 0; e < 4; ++e) {
+                                            v[j8 * 8 + 2 * e] += to_f32<kBF16>(static_cast<uint16_t>(w[e] & 0xFFFFu));
+                                            v[j8 * 8 + 2 * e + 1] += to_f32<kBF16>(static_cast<uint16_t>(w[e] >> 16));
+                                        }
+                                    }
+                                }
+                            }
+                            if (p.epi == EPI_GELU) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                            } else if (use_res) {
+#pragma unroll
+                                for (int j8 = 0; j8 < 4; ++j8) {
+                                    const uint4 b = cg ? rown[4 + j8] : rown[j8];     // static register indices
+                                    const uint32_t w[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        v[j8 * 8 + 2 * e] += to_f32<kBF16>(static_cast<uint16_t>(w[e] & 0xFFFFu));
+                                        v[j8 * 8 + 2 * e + 1] += to_f32<kBF16>(static_cast<uint16_t>(w[e] >> 16));
+                                    }
+                                }
+                            }
+                            if (gated) {
+                                uint32_t o[8];
+#pragma unroll
+                                for (int e = 0; e < 8; ++e)
+                                    o[e] = pack2<kBF16>(gelu_new(v[4 * e]) * v[4 * e + 1], gelu_new(v[4 * e + 2]) * v[4 * e + 3]);
+#pragma unroll
+                                for (int k = 0; k < 2; ++k)
+                                    *reinterpret_cast<uint4*>(stg + lane * 128u + ((static_cast<uint32_t>(cg * 2 + k) ^ swz) << 4)) =
+                                        make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+                            } else {
+#pragma unroll
+                                for (int j8 = 0; j8 < 4; ++j8) {
+                                    const uint4 o = make_uint4(
+                                        pack2<kBF16>(v[j8 * 8 + 0], v[j8 * 8 + 1]), pack2<kBF16>(v[j8 * 8 + 2], v[j8 * 8 + 3]),
+                                        pack2<kBF16>(v[j8 * 8 + 4], v[j8 * 8 + 5]), pack2<kBF16>(v[j8 * 8 + 6], v[j8 * 8 + 7]));
+                                    *reinterpret_cast<uint4*>(stg + lane * 128u + ((static_cast<uint32_t>(cg * 4 + j8) ^ swz) << 4)) = o;
+                                    if (p.out_ss != nullptr && col0 + j8 * 8 < p.N) {   // squares of the values as STORED
+                                        const uint32_t w[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                                        for (int e = 0; e < 4; ++e) {
+                                            const float a = to_f32<kBF16>(static_cast<uint16_t>(w[e] & 0xFFFFu));
+                                            const float b = to_f32<kBF16>(static_cast<uint16_t>(w[e] >> 16));
+                                            ss_out = fmaf(a, a, fmaf(b, b, ss_out));
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                        ab::fence_proxy_async_smem();                          // generic-proxy writes -> visible to the TMA engine
+                        __syncwarp();
+                        if (lane == 0 && row_warp < p.M) {                     // rows / columns past M / N are clipped by the tensor map
+                            ab::tma_store_2d(&tmap_c, stg, out_col_w + g * 64, row_warp);
+                            ab::tma_store_commit();
+                        }
+                    }
+                    if (p.out_ss != nullptr && row < p.M) atomicAdd(p.out_ss + row, ss_out);
+                    continue;
+                }
+            }
             ab::mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1, 14);
             ab::tc_fence_after();
 #pragma unroll 1
@@ -439,6 +578,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             }
             if (p.out_ss != nullptr && row < p.M) atomicAdd(p.out_ss + row, ss_out);
         }
+        if constexpr (BLOCK_N == 256) {
+            if (lane == 0) ab::tma_store_wait_all();     // every TMA store of this warp has landed before the CTA exits
+        }
     }
 
     ab::tc_fence_before();
@@ -480,8 +622,20 @@ static int quad_clusters() {
 }
 
 template <bool kBF16, int BLOCK_N, bool kPair, bool kTN = false, bool kQuad = false>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, cudaStream_t s) {
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p_in, cudaStream_t s) {
     using C = Cfg<BLOCK_N, kPair>;
+    // C through shared memory + TMA stores (BLOCK_N = 256 kernels, 16-bit output): box = {64 columns, 32 rows}
+    Params p = p_in;
+    CUtensorMap tc = ta;      // placeholder when the staged epilogue is off
+    static const bool stage_off = getenv("ATLAS_B200_GEMM_TMA_STORE") != nullptr && getenv("ATLAS_B200_GEMM_TMA_STORE")[0] == '0';
+    p.tma_store = 0;
+    if (BLOCK_N == 256 && p.C32 == nullptr && !stage_off) {
+        const int n_out = p.epi == EPI_GATED ? p.N / 2 : p.N;
+        const int rc = abh::make_tmap_2d_16bit(&tc, p.C, static_cast<uint64_t>(p.M), static_cast<uint64_t>(n_out),
+                                               static_cast<uint64_t>(p.ldc), 32, 64, kBF16);
+        if (rc) return rc;
+        p.tma_store = 1;
+    }
     static bool attr_set = false;
     if (!attr_set) {
         AB_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<kBF16, BLOCK_N, kPair, kTN, kQuad>,
@@ -508,9 +662,9 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        AB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<kBF16, BLOCK_N, kPair, kTN, kQuad>, ta, tb, p));
+        AB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<kBF16, BLOCK_N, kPair, kTN, kQuad>, ta, tb, tc, p));
     } else {
-        gemm_kernel<kBF16, BLOCK_N, kPair, kTN, kQuad><<<grid, THREADS, C::SMEM_BYTES, s>>>(ta, tb, p);
+        gemm_kernel<kBF16, BLOCK_N, kPair, kTN, kQuad><<<grid, THREADS, C::SMEM_BYTES, s>>>(ta, tb, tc, p);
     }
     abh::prof_end(s, abh::PROF_LINEAR, 2.0 * p.M * static_cast<double>(p.N) * p.K);
     abh::count_launch();
