@@ -380,6 +380,37 @@ attention_lanes_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
         const bool partial_last = (p.Lk != lk_pad);
         uint32_t blk_ctr = 0;
 
+        // The output of a finished tile is written one block LATE, inside block 0 of the lane's next tile (after that block's
+        // pass 1): by then P.V(last) of the finished tile has long retired, so its completion latency and the TMEM read of O
+        // hide behind useful work instead of stalling the warpgroup at every tile end (17 % of the softmax-warp samples in
+        // the ncu capture of the previous version, profiles/r02_attention_lanes64_ncu_source_top.csv).  O stays intact until
+        // this lane's next P.V(0), which is issued only after the p_ready(0) that follows the write-out.
+        bool pend = false;
+        int pend_b = 0, pend_h = 0, pend_i = 0;
+        float pend_m = 0.f, pend_sum = 1.f;
+        auto emit_pending = [&]() {
+            const float inv = 1.0f / pend_sum;
+            if (p.lse_out != nullptr && pend_i < p.Lq)
+                p.lse_out[(static_cast<size_t>(pend_b) * p.H + pend_h) * p.Lq + pend_i] = pend_m * (1.0f / LOG2E) + __logf(pend_sum);
+#pragma unroll 1
+            for (int cc = 0; cc < D / 32; ++cc) {
+                uint32_t ro[32];
+                ab::tmem_ld32(o_addr + cc * 32, ro);
+                ab::tmem_ld_wait();
+                if (pend_i < p.Lq) {
+                    uint4* dst = reinterpret_cast<uint4*>(p.O + (static_cast<size_t>(pend_b) * p.Lq + pend_i) * p.ldo + pend_h * D + cc * 32);
+#pragma unroll
+                    for (int v4 = 0; v4 < 4; ++v4)
+                        dst[v4] = make_uint4(
+                            ab::pack2_rn<kBF16>(__uint_as_float(ro[8 * v4]) * inv, __uint_as_float(ro[8 * v4 + 1]) * inv),
+                            ab::pack2_rn<kBF16>(__uint_as_float(ro[8 * v4 + 2]) * inv, __uint_as_float(ro[8 * v4 + 3]) * inv),
+                            ab::pack2_rn<kBF16>(__uint_as_float(ro[8 * v4 + 4]) * inv, __uint_as_float(ro[8 * v4 + 5]) * inv),
+                            ab::pack2_rn<kBF16>(__uint_as_float(ro[8 * v4 + 6]) * inv, __uint_as_float(ro[8 * v4 + 7]) * inv));
+                }
+            }
+            pend = false;
+        };
+
         // all key blocks of one query tile; kBias / kMaskAll are tile-uniform, the last block of a ragged segment always
         // applies the mask (its pad keys carry -inf)
         auto run_tile = [&](auto bias_tag, auto mask_tag, const float* pb_row, const float* mask2, float& m_ref, float& sum0,
@@ -415,6 +446,7 @@ attention_lanes_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                 }
                 // ---- lazy reference maximum ----
                 if (j == 0) {
+                    if (pend) emit_pending();            // the previous tile's output (its last P.V retired above)
                     m_ref = (mb == -INFINITY) ? 0.f : mb;
                 } else {
                     const bool need = mb > m_ref + RESCALE_GAP;
@@ -467,32 +499,16 @@ attention_lanes_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                     if (item_mask) run_tile(std::false_type{}, std::true_type{}, pb_row, mask2, m_ref, sum0, sum1);
                     else run_tile(std::false_type{}, std::false_type{}, pb_row, mask2, m_ref, sum0, sum1);
                 }
-                // ---- output: O / sum ----
-                ab::mbar_wait_nocall(&pv_done[l], (blk_ctr - 1) & 1u);
-                ab::tc_fence_after();
-                const float sum = sum0 + sum1;
-                const float inv = 1.0f / sum;
-                if (p.lse_out != nullptr && i < p.Lq)
-                    p.lse_out[(static_cast<size_t>(b) * p.H + h) * p.Lq + i] = m_ref * (1.0f / LOG2E) + __logf(sum);
-#pragma unroll 1
-                for (int cc = 0; cc < D / 32; ++cc) {
-                    uint32_t ro[32];
-                    ab::tmem_ld32(o_addr + cc * 32, ro);
-                    ab::tmem_ld_wait();
-                    if (i < p.Lq) {
-                        uint4* dst = reinterpret_cast<uint4*>(p.O + (static_cast<size_t>(b) * p.Lq + i) * p.ldo + h * D + cc * 32);
-#pragma unroll
-                        for (int v4 = 0; v4 < 4; ++v4)
-                            dst[v4] = make_uint4(
-                                ab::pack2_rn<kBF16>(__uint_as_float(ro[8 * v4]) * inv, __uint_as_float(ro[8 * v4 + 1]) * inv),
-                                ab::pack2_rn<kBF16>(__uint_as_float(ro[8 * v4 + 2]) * inv, __uint_as_float(ro[8 * v4 + 3]) * inv),
-                                ab::pack2_rn<kBF16>(__uint_as_float(ro[8 * v4 + 4]) * inv, __uint_as_float(ro[8 * v4 + 5]) * inv),
-                                ab::pack2_rn<kBF16>(__uint_as_float(ro[8 * v4 + 6]) * inv, __uint_as_float(ro[8 * v4 + 7]) * inv));
-                    }
-                }
-                ab::tc_fence_before();      // the next tile's first p_ready orders these O reads before P.V(0) overwrites O
+                // ---- output: deferred into block 0 of this lane's next tile (emit_pending) ----
+                pend = true;
+                pend_b = b, pend_h = h, pend_i = i, pend_m = m_ref, pend_sum = sum0 + sum1;
             }
             ab::mbar_arrive(&tab_empty[buf]);
+        }
+        if (pend) {                                      // the lane's last tile
+            ab::mbar_wait_nocall(&pv_done[l], (blk_ctr - 1) & 1u);
+            ab::tc_fence_after();
+            emit_pending();
         }
     }
 
