@@ -532,7 +532,7 @@ __global__ void __launch_bounds__(THREADS_SPLIT, 1)   // 10 warps (allocated as 
 attention_split_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                        const __grid_constant__ CUtensorMap tmap_v, const Params p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t k_full, k_empty, v_full, v_empty, q_full[2], q_empty[2];
+    __shared__ __align__(8) uint64_t k_full[2], k_empty[2], v_full[2], v_empty[2], q_full[2], q_empty[2];
     __shared__ __align__(8) uint64_t s_full[2], p_ready[2], o_full[2], aux_full[2], aux_empty[2];
     __shared__ uint32_t tmem_base_smem;
     __shared__ float s_bias[2][2 * MAX_LK];
@@ -546,12 +546,17 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
     const uint32_t smem_base = (ab::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - ab::smem_u32(smem_raw));
     uint8_t* sQ = smem_gen;
-    uint8_t* sK = smem_gen + 2 * Q_BYTES;
-    uint8_t* sV = sK + KV_BYTES;
-    const uint32_t aQ = smem_base, aK = smem_base + 2 * Q_BYTES, aV = aK + KV_BYTES;
-
     const int n_chunks = (p.Lk + 127) / 128;
     const int lk_pad = n_chunks * 128;          // <= 384 (host dispatch)
+    // K and V of <= 256 keys are DOUBLE-buffered inside the same 2 x 64 KB region (4 x 32 KB): the next (segment, head)'s K
+    // and V stream in while this one computes.  The split-KV cross-attention of the FiD decoder is a pure K / V stream
+    // (32 queries against 15 360 keys per (batch, head)); with single buffers every item paid its own load latency
+    // (160 us per layer = 36 % of the HBM roofline, profiles/r02_launches_step_visit_f.csv).
+    const int nbuf = lk_pad <= 256 ? 2 : 1;
+    const uint32_t kvb = static_cast<uint32_t>(lk_pad) * (D * 2);           // bytes of one K (or V) buffer
+    uint8_t* sK = smem_gen + 2 * Q_BYTES;
+    uint8_t* sV = sK + nbuf * kvb;
+    const uint32_t aQ = smem_base, aK = smem_base + 2 * Q_BYTES, aV = aK + nbuf * kvb;
     const int half = lk_pad / 2;                // keys per half: 64, 128 or 192
     const int n_qt = (p.Lq + BLOCK_Q - 1) / BLOCK_Q;
     const int n_items = p.B * p.H;
@@ -565,11 +570,11 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
         ab::tma_prefetch_desc(&tmap_v);
     }
     if (warp == 1 && lane == 0) {
-        ab::mbar_init(&k_full, 1);
-        ab::mbar_init(&k_empty, 1);
-        ab::mbar_init(&v_full, 1);
-        ab::mbar_init(&v_empty, 1);
         for (int i = 0; i < 2; ++i) {
+            ab::mbar_init(&k_full[i], 1);
+            ab::mbar_init(&k_empty[i], 1);
+            ab::mbar_init(&v_full[i], 1);
+            ab::mbar_init(&v_empty[i], 1);
             ab::mbar_init(&q_full[i], 1);
             ab::mbar_init(&q_empty[i], 1);
             ab::mbar_init(&s_full[i], 1);
@@ -623,17 +628,19 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                                     (b / p.q_div) * p.Lq + qt * BLOCK_Q, ab::kEvictFirst);
                     ++qt_it;
                 };
-                ab::mbar_wait(&k_empty, (item_it & 1) ^ 1u, 41);
-                ab::mbar_arrive_expect_tx(&k_full, kv_bytes);
+                const int kb = item_it % nbuf;
+                const uint32_t kph = static_cast<uint32_t>(item_it / nbuf) & 1u;
+                ab::mbar_wait(&k_empty[kb], kph ^ 1u, 41);
+                ab::mbar_arrive_expect_tx(&k_full[kb], kv_bytes);
                 for (int c = 0; c < n_chunks; ++c)
-                    ab::tma_load_2d(&tmap_k, &k_full, sK + c * (128 * D * 2), p.k_col0 + h * D, b * p.Lk + c * 128,
-                                    ab::kEvictNormal);
+                    ab::tma_load_2d(&tmap_k, &k_full[kb], sK + kb * kvb + c * (128 * D * 2), p.k_col0 + h * D,
+                                    b * p.Lk + c * 128, ab::kEvictNormal);
                 load_q(0);
-                ab::mbar_wait(&v_empty, (item_it & 1) ^ 1u, 49);
-                ab::mbar_arrive_expect_tx(&v_full, kv_bytes);
+                ab::mbar_wait(&v_empty[kb], kph ^ 1u, 49);
+                ab::mbar_arrive_expect_tx(&v_full[kb], kv_bytes);
                 for (int c = 0; c < n_chunks; ++c)
-                    ab::tma_load_2d(&tmap_v, &v_full, sV + c * (128 * D * 2), p.v_col0 + h * D, b * p.Lk + c * 128,
-                                    ab::kEvictNormal);
+                    ab::tma_load_2d(&tmap_v, &v_full[kb], sV + kb * kvb + c * (128 * D * 2), p.v_col0 + h * D,
+                                    b * p.Lk + c * 128, ab::kEvictNormal);
                 for (int qt = 1; qt < n_qt; ++qt) load_q(qt);
             }
             __syncwarp();
@@ -646,43 +653,45 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
             // S_h(g) = Q(g) . K_h^T  -> columns [h*half, h*half + half)
             auto issue_s = [&](int hh, int g) {
                 const uint64_t qdesc = ab::umma_desc_k_sw128(aQ + (g & 1) * Q_BYTES);
-                const uint64_t kdesc = ab::umma_desc_k_sw128(aK + hh * half * (D * 2));
+                const uint64_t kdesc = ab::umma_desc_k_sw128(aK + ((g / n_qt) % nbuf) * kvb + hh * half * (D * 2));
 #pragma unroll
                 for (int k = 0; k < D / 16; ++k)
                     ab::umma_ss<1>(tmem_base + hh * half, qdesc + ((k * 32) >> 4), kdesc + ((k * 32) >> 4), idesc_s,
                                    k != 0 ? 1u : 0u);
             };
             // O_h(g) = P_h . V_h : A = packed P in TMEM, B = V rows of this half
-            auto issue_pv = [&](int hh) {
-                const uint64_t vdesc = umma_desc_mn_sw128(aV + hh * half * (D * 2));
+            auto issue_pv = [&](int hh, int g) {
+                const uint64_t vdesc = umma_desc_mn_sw128(aV + ((g / n_qt) % nbuf) * kvb + hh * half * (D * 2));
                 for (int k = 0; k < half / 16; ++k)
                     ab::umma_ts<1>(tmem_base + O_COL0 + 64 * hh, tmem_base + hh * half + k * 8,
                                    vdesc + static_cast<uint64_t>((k * 2048) >> 4), idesc_o, k != 0 ? 1u : 0u);
             };
             // prologue: both halves of tile 0
-            ab::mbar_wait(&k_full, 0, 43);
+            ab::mbar_wait(&k_full[0], 0, 43);
             ab::mbar_wait(&q_full[0], 0, 44);
             ab::tc_fence_after();
             issue_s(0, 0);
             ab::umma_commit(&s_full[0]);
             issue_s(1, 0);
             ab::umma_commit(&q_empty[0]);
-            if (n_qt == 1) ab::umma_commit(&k_empty);
+            if (n_qt == 1) ab::umma_commit(&k_empty[0]);
             ab::umma_commit(&s_full[1]);
             for (int g = 0; g < n_tiles; ++g) {
                 const int item_it = g / n_qt, qt = g % n_qt;
                 const bool has_next = g + 1 < n_tiles;
                 const int nitem_it = (g + 1) / n_qt, nqt = (g + 1) % n_qt;
-                if (qt == 0) ab::mbar_wait(&v_full, item_it & 1, 50);
+                const int ib = item_it % nbuf, nib = nitem_it % nbuf;
+                if (qt == 0) ab::mbar_wait(&v_full[ib], static_cast<uint32_t>(item_it / nbuf) & 1u, 50);
                 // ---- half a ----
                 ab::mbar_wait(&p_ready[0], g & 1, 46);
                 ab::tc_fence_after();
-                issue_pv(0);
+                issue_pv(0, g);
                 ab::umma_commit(&o_full[0]);
                 if (has_next) {
-                    if (nqt == 0) ab::mbar_wait(&k_full, nitem_it & 1, 43);
+                    if (nqt == 0) ab::mbar_wait(&k_full[nib], static_cast<uint32_t>(nitem_it / nbuf) & 1u, 43);
                     ab::mbar_wait(&q_full[(g + 1) & 1], ((g + 1) >> 1) & 1, 44);
-                    ab::mbar_wait(&o_full[0], g & 1, 51);     // P_a(g) consumed: its columns may take S_a(g+1)
+                    // S_a(g+1) takes the columns of P_a(g): tcgen05.mma executes in issue order, P_a.V_a(g) above reads them
+                    // first - no completion round trip (round 1 waited for o_full here)
                     ab::tc_fence_after();
                     issue_s(0, g + 1);
                     ab::umma_commit(&s_full[0]);
@@ -690,15 +699,13 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                 // ---- half b ----
                 ab::mbar_wait(&p_ready[1], g & 1, 47);
                 ab::tc_fence_after();
-                issue_pv(1);
-                if (qt == n_qt - 1) ab::umma_commit(&v_empty);   // last use of this (segment, head)'s V
+                issue_pv(1, g);
+                if (qt == n_qt - 1) ab::umma_commit(&v_empty[ib]);   // last use of this (segment, head)'s V
                 ab::umma_commit(&o_full[1]);
                 if (has_next) {
-                    ab::mbar_wait(&o_full[1], g & 1, 52);
-                    ab::tc_fence_after();
                     issue_s(1, g + 1);
                     ab::umma_commit(&q_empty[(g + 1) & 1]);
-                    if (nqt == n_qt - 1) ab::umma_commit(&k_empty);
+                    if (nqt == n_qt - 1) ab::umma_commit(&k_empty[nib]);
                     ab::umma_commit(&s_full[1]);
                 }
             }

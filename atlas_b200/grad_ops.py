@@ -170,15 +170,15 @@ def dropout(x, p, residual=None):
 
 
 class _ClampInf(torch.autograd.Function):
-    """The reference's fp16 overflow clamp after a T5 sub-layer (src/modeling_t5.py:657-708), in place, device-side decision.
+    """The reference's fp16 overflow clamp after a T5 sub-layer (src/modeling_t5.py:657-708), device-side decision.
     Backward: identity (the reference's `torch.clamp` zeroes the gradient of the clamped elements; they only exist in a
     step that overflowed fp16, which the reference's training recipe - bf16 - never takes)."""
 
     @staticmethod
     def forward(ctx, x):
-        ctx.mark_dirty(x)
-        ops.clamp_inf_(x)
-        return x
+        y = x.clone()            # outputs of the custom Functions upstream may be views: no in-place edit under autograd
+        ops.clamp_inf_(y)
+        return y
 
     @staticmethod
     def backward(ctx, dy):
