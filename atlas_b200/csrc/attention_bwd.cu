@@ -920,7 +920,9 @@ int atlas_b200_attention_bwd_train(const void* q, int64_t ldq, int32_t q_col0, c
     // only (the dQ kernel is not yet faster than its warp-MMA twin; the dK/dV kernel is: 0.23 vs 0.33 ms at
     // 80 x 12 x 384 x 384).  The warp-MMA dQ kernel runs first in mode 3: it writes D = rowsum(dO o O), which the
     // tcgen05 dK/dV kernel reads.
-    static const int tc_level = getenv("ATLAS_B200_ATTN_BWD_TC") ? atoi(getenv("ATLAS_B200_ATTN_BWD_TC")) : 0;
+    // Default (round 2): mode 3 - it passes the backward / training suites and is 16 % faster than the two warp-MMA kernels
+    // at 80 x 12 x 384 x 384 (0.66 vs 0.80 ms, profiles/r02_attention_bwd_tc_ab_visit_h.log); 0 = warp-MMA kernels only.
+    static const int tc_level = getenv("ATLAS_B200_ATTN_BWD_TC") ? atoi(getenv("ATLAS_B200_ATTN_BWD_TC")) : 3;
     const bool use_tc = tc_level >= 1 && drop.thr16 == 0u;     // the tcgen05 kernels do not implement dropout
     bool dq_done = false, dkv_done = false;
     if (v2 && use_tc && dq_accum == nullptr) {
