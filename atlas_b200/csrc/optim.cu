@@ -34,22 +34,22 @@ __device__ __forceinline__ void store_param(void* p, int kind, int64_t i, float 
 //   p -= (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps);      then param <- cast(p)
 __global__ void __launch_bounds__(THREADS)
 adamw_fp32copy_kernel(const AtlasB200AdamTensor* __restrict__ descs, const int2* __restrict__ chunks, int chunk_elems,
-                      float lr, float beta1, float beta2, float eps, float weight_decay, float inv_scale) {
+                      float decay, float beta2, float one_minus_beta1, float one_minus_beta2, float eps, float inv_scale) {
     const int2 item = chunks[blockIdx.x];
     const AtlasB200AdamTensor d = descs[item.x];
     const int64_t begin = static_cast<int64_t>(item.y) * chunk_elems;
     const int64_t end = min(begin + chunk_elems, d.numel);
-    const float decay = 1.0f - lr * weight_decay;
-    const float step_size = lr / d.bias_correction1;
-    const float inv_bc2_sqrt = 1.0f / d.bias_correction2_sqrt;
-    const float w = 1.0f - beta1, w2 = 1.0f - beta2;
+    // the scalars torch derives in double precision (1 - lr*wd, 1 - beta, lr / bias_correction1) arrive pre-computed
+    const float step_size = d.step_size;
+    const float bc2_sqrt = d.bias_correction2_sqrt;
+    const float w = one_minus_beta1, w2 = one_minus_beta2;
     for (int64_t i = begin + threadIdx.x; i < end; i += THREADS) {
         const float g = load_grad(d.grad, d.grad_kind, i) * inv_scale;
         float p = d.master[i] * decay;
         float m = d.exp_avg[i];
         m = m + w * (g - m);                                   // Tensor.lerp_ for weight < 0.5
         const float v = d.exp_avg_sq[i] * beta2 + w2 * g * g;
-        const float denom = sqrtf(v) * inv_bc2_sqrt + eps;
+        const float denom = sqrtf(v) / bc2_sqrt + eps;         // (exp_avg_sq.sqrt() / bias_correction2_sqrt).add_(eps)
         p -= step_size * (m / denom);
         d.master[i] = p;
         d.exp_avg[i] = m;
@@ -138,12 +138,13 @@ __global__ void grad_stats_final_kernel(const AtlasB200GradTensor* __restrict__ 
 extern "C" {
 
 int atlas_b200_adamw_fp32copy(const AtlasB200AdamTensor* descs_dev, const int32_t* chunks_dev, int32_t n_chunks,
-                              int32_t chunk_elems, float lr, float beta1, float beta2, float eps, float weight_decay,
-                              float inv_scale, void* stream) {
+                              int32_t chunk_elems, float decay, float beta2, float one_minus_beta1, float one_minus_beta2,
+                              float eps, float inv_scale, void* stream) {
     AB_REQUIRE(n_chunks >= 0 && chunk_elems > 0 && chunk_elems % 4 == 0, "adamw_fp32copy: bad chunk table");
     if (n_chunks == 0) return ATLAS_B200_OK;
     opt::adamw_fp32copy_kernel<<<n_chunks, opt::THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-        descs_dev, reinterpret_cast<const int2*>(chunks_dev), chunk_elems, lr, beta1, beta2, eps, weight_decay, inv_scale);
+        descs_dev, reinterpret_cast<const int2*>(chunks_dev), chunk_elems, decay, beta2, one_minus_beta1, one_minus_beta2, eps,
+        inv_scale);
     abh::count_launch();
     AB_CUDA_CHECK(cudaGetLastError());
     return ATLAS_B200_OK;

@@ -426,11 +426,11 @@ class FiD(nn.Module):
         B, T = decoder_input_ids.shape
         d, H = c.d_model, c.num_heads
         Lk = enc.shape[1]
-        # key segments of the split-KV cross-attention: the largest divisor of Lk up to 256 keys (attention_split_kernel
-        # double-buffers K and V of <= 256 keys: the stream of the next segment overlaps this one's arithmetic), else up
-        # to 384 (same kernel, single buffers), else up to 512 (single-accumulator kernel)
-        split = next((s for s in range(min(256, Lk), 127, -1) if Lk % s == 0), None) or \
-            next((s for s in range(min(384, Lk), 63, -1) if Lk % s == 0), None) or \
+        # key segments of the split-KV cross-attention: the largest divisor of Lk up to 384 keys (the two-half kernel,
+        # attention_split_kernel), else up to 512 (single-accumulator kernel).  256-key segments (K / V double-buffered by
+        # that kernel) were measured SLOWER for the FiD decoder: 2.32 vs 1.92 ms per 8-query step - the per-segment
+        # softmax / MMA chain, not the load latency, sets the segment time (profiles/r02_launches_step_visit_i.csv)
+        split = next((s for s in range(min(384, Lk), 63, -1) if Lk % s == 0), None) or \
             next(s for s in range(min(512, Lk), 0, -1) if Lk % s == 0)
         if split < 64 and Lk > 512:
             raise AtlasB200Error(f"n_context*text_maxlength = {Lk} has no divisor in [64, 512] for the split-KV kernel")
@@ -556,8 +556,7 @@ class FiD(nn.Module):
         split = None
         if pdrop:    # the dropout mask is addressed in 32-key groups over the whole key range (csrc/dropout.cuh)
             split = next((s for s in range(min(512, Lk) // 32 * 32, 63, -32) if Lk % s == 0), None)
-        split = split or next((s for s in range(min(256, Lk), 127, -1) if Lk % s == 0), None) or \
-            next((s for s in range(min(384, Lk), 63, -1) if Lk % s == 0), None) or \
+        split = split or next((s for s in range(min(384, Lk), 63, -1) if Lk % s == 0), None) or \
             next(s for s in range(min(512, Lk), 0, -1) if Lk % s == 0)
         if split < 64 and Lk > 512:
             raise AtlasB200Error(f"n_context*text_maxlength = {Lk} has no divisor in [64, 512] for the split-KV kernel")

@@ -88,7 +88,7 @@ class AdamWFP32Copy(torch.optim.AdamW):
                 keep.append(g)
                 rows.append((p.data_ptr(), state["float32copy"].data_ptr(), state["exp_avg"].data_ptr(),
                              state["exp_avg_sq"].data_ptr(), g.data_ptr(), p.numel(), _kind(p, "parameter"),
-                             _kind(g, "gradient"), 1.0 - beta1 ** t, math.sqrt(1.0 - beta2 ** t)))
+                             _kind(g, "gradient"), group["lr"] / (1.0 - beta1 ** t), math.sqrt(1.0 - beta2 ** t)))
             if not rows:
                 continue
             descs = np.array(rows, dtype=_ADAM_DESC)
@@ -96,10 +96,11 @@ class AdamWFP32Copy(torch.optim.AdamW):
             d_dev, h1 = _to_device(descs, device)
             c_dev, h2 = _to_device(chunks, device)
             with torch.cuda.device(device):
+                # torch derives these scalars in double precision and rounds them once: do the same
                 check(lib().atlas_b200_adamw_fp32copy(d_dev.data_ptr(), c_dev.data_ptr(), int(chunks.shape[0]), CHUNK,
-                                                      float(group["lr"]), float(beta1), float(beta2), float(group["eps"]),
-                                                      float(group["weight_decay"]), 1.0 / float(scale),
-                                                      current_stream_ptr()))
+                                                      1.0 - float(group["lr"]) * float(group["weight_decay"]), float(beta2),
+                                                      1.0 - float(beta1), 1.0 - float(beta2), float(group["eps"]),
+                                                      1.0 / float(scale), current_stream_ptr()))
             # the tables are read by the kernel asynchronously: keep them (and the pinned staging copies) until the next step
             self._live = (d_dev, c_dev, h1, h2, keep)
         from .retrievers import _bump_weights_epoch

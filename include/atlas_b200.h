@@ -357,9 +357,11 @@ int atlas_b200_attention_bwd_train(const void* q, int64_t ldq, int32_t q_col0, c
 /* Multi-tensor optimiser step and gradient statistics of the training loop.  The work list is a device
  * table of (tensor index, chunk index) int32 pairs, `chunk_elems` elements per chunk (multiple of 4).
  *   atlas_b200_adamw_fp32copy: src/AdamWFP32Copy.py:79-169 for one param group - per element, on the fp32 master copy:
- *     g = grad * inv_scale; p *= 1 - lr*wd; m = lerp(m, g, 1-b1); v = b2*v + (1-b2)*g*g;
- *     p -= (lr / bias_correction1) * m / (sqrt(v) / bias_correction2_sqrt + eps); param = cast(p)
- *     (torch.optim AdamW, amsgrad = False, maximize = False; the bias corrections are per tensor: state["step"]).
+ *     g = grad * inv_scale; p *= decay; m = lerp(m, g, one_minus_beta1); v = beta2*v + one_minus_beta2*g*g;
+ *     p -= step_size * m / (sqrt(v) / bias_correction2_sqrt + eps); param = cast(p)
+ *     (torch.optim AdamW, amsgrad = False, maximize = False).  decay = 1 - lr*wd, 1 - beta and step_size = lr /
+ *     bias_correction1 are passed as the caller computed them in DOUBLE precision (as torch does) and rounded once to fp32;
+ *     step_size and bias_correction2_sqrt are per tensor (state["step"] may differ between parameters).
  *   atlas_b200_grad_stats: src/util.py:200-222 - stats[i] = (min |g|, max |g|, mean |g|, ||g||_2) per tensor in fp32 on the
  *     device (zeros for a tensor without gradient), instead of four `.item()` synchronisations per parameter. */
 typedef struct {
@@ -370,7 +372,7 @@ typedef struct {
     const void* grad;        /* p.grad (grad_kind: 0 fp32, 1 bf16, 2 fp16) */
     int64_t numel;
     int32_t param_kind, grad_kind;
-    float bias_correction1;       /* 1 - beta1^step */
+    float step_size;              /* lr / (1 - beta1^step) */
     float bias_correction2_sqrt;  /* sqrt(1 - beta2^step) */
 } AtlasB200AdamTensor;
 typedef struct {
@@ -379,8 +381,8 @@ typedef struct {
     int32_t grad_kind, pad_;
 } AtlasB200GradTensor;
 int atlas_b200_adamw_fp32copy(const AtlasB200AdamTensor* descs_dev, const int32_t* chunks_dev, int32_t n_chunks,
-                              int32_t chunk_elems, float lr, float beta1, float beta2, float eps, float weight_decay,
-                              float inv_scale, void* stream);
+                              int32_t chunk_elems, float decay, float beta2, float one_minus_beta1, float one_minus_beta2,
+                              float eps, float inv_scale, void* stream);
 int atlas_b200_grad_stats(const AtlasB200GradTensor* descs_dev, int32_t n_tensors, const int32_t* chunks_dev,
                           int32_t n_chunks, int32_t chunk_elems, float* stats, void* stream);
 

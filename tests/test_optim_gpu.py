@@ -81,9 +81,10 @@ def test_grad_stats_match_torch(dev):
 
     g = torch.Generator(device="cpu").manual_seed(9)
     shapes = [(768, 768), (3,), (4096, 65), (1,), (200000,)]
-    params = [torch.nn.Parameter(torch.zeros(*s, dtype=torch.bfloat16, device=dev)) for s in shapes]
+    dts = [torch.bfloat16 if i % 2 == 0 else torch.float32 for i in range(len(shapes))]     # grad dtype = parameter dtype
+    params = [torch.nn.Parameter(torch.zeros(*s, dtype=dt, device=dev)) for s, dt in zip(shapes, dts)]
     for i, p in enumerate(params):
-        p.grad = (torch.randn(*shapes[i], generator=g) * (0.1 + i)).to(torch.bfloat16 if i % 2 == 0 else torch.float32).to(dev)
+        p.grad = (torch.randn(*shapes[i], generator=g) * (0.1 + i)).to(dts[i]).to(dev)
     params[3].grad = None
     stats = grad_stats_tensor(params).cpu()
     for i, p in enumerate(params):

@@ -54,6 +54,16 @@ elif what == "gemm4":
         fl = 2 * M * N * K
         print(f"gemm {name:12s} M={M} N={N} K={K}: {ms:.3f} ms = {fl / ms / 1e9:.0f} TFLOP/s   cuBLAS plain: {ms_ref:.3f} ms = "
               f"{fl / ms_ref / 1e9:.0f} TFLOP/s")
+elif what == "mips":
+    # one 256-query top-40 search over a 4 Mi x 768 fp16 bank (BASELINE configs[1]): for `ncu --metrics gpu__time_duration.sum`
+    n, nq, k = 4 * 1024 * 1024, 256, 40
+    bank = torch.empty((n, 768), dtype=torch.float16, device=dev)
+    for a in range(0, n, 1 << 19):
+        bank[a:a + (1 << 19)] = (torch.randn((1 << 19, 768), device=dev) * 0.05).half()
+    q = (torch.randn(nq, 768, device=dev) * 0.05).half()
+    fn = lambda: ops.mips_topk(bank, q, k)
+    ms = timed(fn, reps)
+    print(f"mips n={n} nq={nq} k={k}: {ms:.3f} ms = {n * 768 * 2 / ms / 1e6:.0f} GB/s over the bank")
 elif what == "attn_bwd":
     S, H, L = 80, 12, 384       # FiD-base encoder, 2 queries x 40 passages (the bench's training leg)
     qkv = torch.randn(S * L, 3 * H * 64, device=dev).bfloat16() * 0.2
