@@ -157,6 +157,9 @@ def lib():
     L.atlas_b200_grad_stats.argtypes = [vp, i32, vp, i32, i32, vp, vp]
     L.atlas_b200_clamp_inf_fp16.restype = c.c_int
     L.atlas_b200_clamp_inf_fp16.argtypes = [vp, i64, i64, i32, vp, vp, vp]
+    L.atlas_b200_cross_attention_stream.restype = c.c_int
+    L.atlas_b200_cross_attention_stream.argtypes = [vp, i64, i32, vp, i64, i32, i32, vp, i32, i32, i32, i32, i32, f32, vp, vp,
+                                                    i32, vp]
     L.atlas_b200_attention_dropout_mask.restype = c.c_int
     L.atlas_b200_attention_dropout_mask.argtypes = [vp, i64, i32, f32, u64, u64, vp]
     _lib = L
@@ -213,6 +216,7 @@ EXPORTED_SYMBOLS = [
     "atlas_b200_adamw_fp32copy",
     "atlas_b200_grad_stats",
     "atlas_b200_clamp_inf_fp16",
+    "atlas_b200_cross_attention_stream",
 ]
 
 

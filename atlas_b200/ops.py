@@ -272,17 +272,35 @@ def attention(q, q_col0, k, k_col0, v, v_col0, B, H, Lq, Lk, add_mask=None, bias
     return (out, lse) if return_lse else out
 
 
+_XATTN_STREAM = os.environ.get("ATLAS_B200_XATTN_STREAM", "1") != "0"      # A/B switch of the stream kernel
+_XATTN_CHUNK = int(os.environ.get("ATLAS_B200_XATTN_CHUNK", "512"))        # keys per CTA (multiple of 64)
+
+
 def cross_attention_split(q, q_col0, kv, k_col0, v_col0, B, H, Lq, Lk_total, add_mask=None, scale=1.0, split=512,
                           return_lse=False, dropout=None):
     """Attention of Lq (<= 128) queries per batch element over Lk_total keys (FiD decoder cross-attention,
     Lk_total = n_ctx * L): split-KV over segments of `split` keys + combine.  q [B*Lq, ld], kv [B*Lk_total, ld]."""
     require_cuda(q, "q")
+    am = add_mask.float().contiguous() if add_mask is not None else None
+    if Lq <= 64 and dropout is None and Lk_total >= 1024 and _XATTN_STREAM:
+        # few target tokens against the concatenated encoder keys: the K / V stream kernel (csrc/attention_stream.cu)
+        chunk = _XATTN_CHUNK
+        chunks = (Lk_total + chunk - 1) // chunk
+        o_part = torch.empty((B * chunks * Lq, H * 64), dtype=torch.float32, device=q.device)
+        ml = torch.empty((B * chunks * Lq, H, 2), dtype=torch.float32, device=q.device)
+        check(lib().atlas_b200_cross_attention_stream(_ptr(q), q.stride(0), q_col0, _ptr(kv), kv.stride(0), k_col0, v_col0,
+                                                      _ptr(am) if am is not None else None, B, H, Lq, Lk_total, chunk,
+                                                      float(scale), _ptr(o_part), _ptr(ml), _bf(q), current_stream_ptr()))
+        out = torch.empty((B * Lq, H * 64), dtype=q.dtype, device=q.device)
+        lse = torch.empty((B, H, Lq), dtype=torch.float32, device=q.device) if return_lse else None
+        check(lib().atlas_b200_attention_combine_ex(_ptr(o_part), _ptr(ml), B, chunks, Lq, H, _ptr(out), out.stride(0),
+                                                    _ptr(lse) if lse is not None else None, _bf(q), current_stream_ptr()))
+        return (out, lse) if return_lse else out
     if Lk_total % split != 0:
         raise AtlasB200Error(f"cross_attention_split: Lk_total={Lk_total} must be a multiple of {split}")
     splits = Lk_total // split
     o_part = torch.empty((B * splits * Lq, H * 64), dtype=torch.float32, device=q.device)
     ml = torch.empty((B * splits * Lq, H, 2), dtype=torch.float32, device=q.device)
-    am = add_mask.float().contiguous() if add_mask is not None else None
     dummy = torch.empty((8,), dtype=q.dtype, device=q.device)
     dp, dseed, doff = dropout if dropout is not None else (0.0, 0, 0)
     check(lib().atlas_b200_attention_train(_ptr(q), q.stride(0), q_col0, _ptr(kv), kv.stride(0), k_col0, _ptr(kv),

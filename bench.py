@@ -658,6 +658,25 @@ def run_ours(args):
     barrier_sync()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
     assert loss_host == loss_host and len(passages) == B and len(passages[0]) == TOPK
+    # where the e2e step spends its time (untimed diagnostic pass: a device synchronisation after every phase)
+    e2e_phases = {}
+    for _ in range(3):
+        marks = [time.perf_counter()]
+
+        def mark(name):
+            torch.cuda.synchronize()
+            marks.append(time.perf_counter())
+            e2e_phases[name] = e2e_phases.get(name, 0.0) + (marks[-1] - marks[-2]) * 1e3 / 3
+
+        enc = atlas.retriever_tokenize(queries)
+        lab, dec_ids = atlas.reader_tokenize(queries, targets, None)
+        mark("tokenize_queries_and_targets_h2d")
+        psg, _ = atlas.retrieve(index, TOPK, queries, enc["input_ids"], enc["attention_mask"])
+        mark("retrieve_contriever_search_knn_passage_dicts")
+        tok = atlas.reader_passage_tokens(queries, psg)
+        mark("reader_passage_tokens_device_bank")
+        atlas.compute_reader_loss_and_logits(tok, dec_ids, lab)
+        mark("reader_forward_loss_item")
     h2d = (sum(t.numel() * t.element_size() for t in q_enc.values()) + labels.numel() * 8 + dec.numel() * 8
            + rq_ids.numel() * 8 + rq_lens.numel() * 4 + B * N_DOCS * 8) * world
     d2h = (4 + B * TOPK * (8 + 4) + 8) * world
@@ -750,6 +769,7 @@ def run_ours(args):
                      "model_flops_utilisation": FID_FLOPS_PER_QUERY * B / (ms_per_step * 1e-3) / 1e12 / peak},
         "e2e": {"value": B * world / (e2e_ms * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
+                "phases_ms_synchronised": {k: round(v, 3) for k, v in e2e_phases.items()},
                 "call": "query strings -> Atlas.retriever_tokenize / reader_tokenize -> Atlas.retrieve (Contriever.forward + "
                         "DistributedIndex.search_knn incl. passage dicts) -> Atlas.reader_passage_tokens (device token "
                         "bank) -> Atlas.compute_reader_loss_and_logits (loss.item())"},

@@ -392,6 +392,16 @@ int atlas_b200_grad_stats(const AtlasB200GradTensor* descs_dev, int32_t n_tensor
  * rewritten with the rows' sums of squares when (and only when) the clamp fires (fused-RMSNorm statistic). */
 int atlas_b200_clamp_inf_fp16(void* x, int64_t ld, int64_t M, int32_t N, int32_t* flag, float* row_ss, void* stream);
 
+/* FiD decoder cross-attention for FEW queries (Lq <= 64 target tokens) against Lk concatenated encoder keys per batch element
+ * (src/fid.py:298-349 at the teacher-forced / training forward shape): an HBM-bound K / V stream.  q [B*Lq, ldq], kv [B*Lk, ldkv]
+ * (k at k_col0 + 64 h, v at v_col0 + 64 h).  Every CTA covers `chunk` keys (multiple of 64) of one (batch, head) and writes
+ * un-normalised fp32 partials o_partial [(b * chunks + c) * Lq + i, H*64] and ml_partial [.., H, 2] = (row max, row sum) in the
+ * layout atlas_b200_attention_combine_ex merges (splits = ceil(Lk / chunk)). */
+int atlas_b200_cross_attention_stream(const void* q, int64_t ldq, int32_t q_col0, const void* kv, int64_t ldkv, int32_t k_col0,
+                                      int32_t v_col0, const float* add_mask, int32_t B, int32_t H, int32_t Lq, int32_t Lk,
+                                      int32_t chunk, float scale, float* o_partial, float* ml_partial, int32_t is_bf16,
+                                      void* stream);
+
 /* Measurement hook for bench.py's roofline: while enabled, every launch of ONE kind of kernel is bracketed
  * with CUDA events on its launching stream:
  *   kind 1  the bank sweep of atlas_b200_mips_topk (work = algorithmic bytes swept)

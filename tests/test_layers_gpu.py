@@ -246,3 +246,38 @@ def test_fid_fp16_overflow_is_clamped_like_the_reference(dev):
             enc = reader.encode(ids.to(dev), mask.to(dev))
         assert torch.isfinite(enc).all(), f"fuse_norm={fuse}: the overflow reached the encoder output"
         assert float(enc.abs().max()) > 0
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("B,H,T,Lk", [(2, 3, 32, 4000), (1, 12, 7, 15360), (3, 2, 64, 1088), (2, 1, 1, 2048)])
+def test_cross_attention_stream_kernel(dev, dtype, B, H, T, Lk):
+    """csrc/attention_stream.cu (few target tokens against the concatenated encoder keys, src/fid.py:298-349): against an fp32
+    restatement, ragged key counts, masked keys, and against the tcgen05 split-KV path where that one applies."""
+    from atlas_b200 import ops
+
+    g = torch.Generator().manual_seed(B * 1000 + T)
+    q = (torch.randn(B * T, H * 64, generator=g) * 0.5).to(dtype).to(dev)
+    kv = (torch.randn(B * Lk, 2 * H * 64, generator=g) * 0.5).to(dtype).to(dev)
+    valid = torch.rand(B, Lk, generator=g) > 0.25
+    valid[:, 0] = True
+    valid[0, Lk // 2:] = False                       # a long fully-masked tail (whole chunks without a live key)
+    neg = -1e4 if dtype == torch.float16 else -1e9
+    mask = ((~valid).float() * neg).to(dev)
+    assert ops._XATTN_STREAM
+    out, lse = ops.cross_attention_split(q, 0, kv, 0, H * 64, B, H, T, Lk, add_mask=mask, scale=1.0, split=Lk, return_lse=True)
+    qf = q.float().reshape(B, T, H, 64)
+    kf, vf = (t.reshape(B, Lk, H, 64) for t in kv.float().split(H * 64, dim=1))
+    s = torch.einsum("bihd,bjhd->bhij", qf, kf) + mask[:, None, None, :]
+    ref = torch.einsum("bhij,bjhd->bihd", torch.softmax(s, -1), vf).reshape(B * T, H * 64)
+    tol = 2e-2 if dtype == torch.bfloat16 else 3e-3
+    err = float((out.float() - ref).abs().max())
+    assert err <= tol * max(1.0, float(ref.abs().max())), err
+    assert torch.allclose(lse, torch.logsumexp(s, -1), rtol=1e-3, atol=2e-3)
+    split = next((x for x in range(384, 63, -1) if Lk % x == 0), None)
+    if split is not None:
+        ops._XATTN_STREAM = False
+        try:
+            old = ops.cross_attention_split(q, 0, kv, 0, H * 64, B, H, T, Lk, add_mask=mask, scale=1.0, split=split)
+        finally:
+            ops._XATTN_STREAM = True
+        assert float((old.float() - out.float()).abs().max()) <= tol * max(1.0, float(ref.abs().max()))
