@@ -146,7 +146,7 @@ def lib():
     L.atlas_b200_dropout_mask.argtypes = [vp, i64, i32, f32, u64, u64, vp]
     L.atlas_b200_attention_train.restype = c.c_int
     L.atlas_b200_attention_train.argtypes = [vp, i64, i32, vp, i64, i32, vp, i64, i32, vp, i64, vp, vp, i32, i32, i32, i32,
-                                             f32, f32, i32, vp, vp, vp, f32, u64, u64, i32, vp]
+                                             f32, f32, i32, vp, vp, vp, f32, u64, u64, vp, i32, vp]
     L.atlas_b200_attention_bwd_train.restype = c.c_int
     L.atlas_b200_attention_bwd_train.argtypes = [vp, i64, i32, vp, i64, i32, vp, i64, i32, vp, i64, vp, i64, vp, i64, i32,
                                                  vp, i64, i32, vp, i64, i32, vp, vp, vp, vp, i32, vp, vp, i32, i32, i32,
@@ -158,8 +158,8 @@ def lib():
     L.atlas_b200_clamp_inf_fp16.restype = c.c_int
     L.atlas_b200_clamp_inf_fp16.argtypes = [vp, i64, i64, i32, vp, vp, vp]
     L.atlas_b200_cross_attention_stream.restype = c.c_int
-    L.atlas_b200_cross_attention_stream.argtypes = [vp, i64, i32, vp, i64, i32, i32, vp, i32, i32, i32, i32, i32, f32, vp, vp,
-                                                    i32, vp]
+    L.atlas_b200_cross_attention_stream.argtypes = [vp, i64, i32, vp, i64, i32, i32, vp, vp, i32, i32, i32, i32, i32, f32, vp,
+                                                    vp, i32, vp]
     L.atlas_b200_attention_dropout_mask.restype = c.c_int
     L.atlas_b200_attention_dropout_mask.argtypes = [vp, i64, i32, f32, u64, u64, vp]
     _lib = L

@@ -888,14 +888,14 @@ __global__ void combine_splits_kernel(const float* __restrict__ o_partial, const
 int atlas_b200_attention_lanes_launch(const void* q, int64_t ldq, int32_t q_col0, const void* k, int64_t ldk, int32_t k_col0,
                                       const void* v, int64_t ldv, int32_t v_col0, void* out, int64_t ldo,
                                       const float* add_mask, const float* bias_delta, int32_t B, int32_t H, int32_t Lq,
-                                      int32_t Lk, float scale, float causal_value, float* lse_out, int32_t is_bf16,
-                                      cudaStream_t s);
+                                      int32_t Lk, float scale, float causal_value, float* lse_out, const uint8_t* blk_live,
+                                      int32_t is_bf16, cudaStream_t s);
 // csrc/attention_lanes96.cu: the first three-lane kernel (96-key blocks), ATLAS_B200_ATTN_LANES=3
 int atlas_b200_attention_lanes96_launch(const void* q, int64_t ldq, int32_t q_col0, const void* k, int64_t ldk, int32_t k_col0,
                                        const void* v, int64_t ldv, int32_t v_col0, void* out, int64_t ldo,
                                        const float* add_mask, const float* bias_delta, int32_t B, int32_t H, int32_t Lq,
-                                       int32_t Lk, float scale, float causal_value, float* lse_out, int32_t is_bf16,
-                                       cudaStream_t s);
+                                       int32_t Lk, float scale, float causal_value, float* lse_out, const uint8_t* blk_live,
+                                       int32_t is_bf16, cudaStream_t s);
 
 extern "C" {
 
@@ -914,15 +914,16 @@ int atlas_b200_attention_ex(const void* q, int64_t ldq, int32_t q_col0, const vo
                             float causal_value, int32_t q_div, float* o_partial, float* ml_partial, float* lse_out,
                             int32_t is_bf16, void* stream) {
     return atlas_b200_attention_train(q, ldq, q_col0, k, ldk, k_col0, v, ldv, v_col0, out, ldo, add_mask, bias_delta, B, H, Lq,
-                                      Lk, scale, causal_value, q_div, o_partial, ml_partial, lse_out, 0.f, 0, 0, is_bf16,
-                                      stream);
+                                      Lk, scale, causal_value, q_div, o_partial, ml_partial, lse_out, 0.f, 0, 0, nullptr,
+                                      is_bf16, stream);
 }
 
 int atlas_b200_attention_train(const void* q, int64_t ldq, int32_t q_col0, const void* k, int64_t ldk, int32_t k_col0,
                                const void* v, int64_t ldv, int32_t v_col0, void* out, int64_t ldo, const float* add_mask,
                                const float* bias_delta, int32_t B, int32_t H, int32_t Lq, int32_t Lk, float scale,
                                float causal_value, int32_t q_div, float* o_partial, float* ml_partial, float* lse_out,
-                               float dropout_p, uint64_t seed, uint64_t offset, int32_t is_bf16, void* stream) {
+                               float dropout_p, uint64_t seed, uint64_t offset, const uint8_t* key_block_live,
+                               int32_t is_bf16, void* stream) {
     using namespace attn;
     AB_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "attention: need 0 <= dropout_p < 1 (got %f)", dropout_p);
     const abdrop::Key drop = abdrop::make_key(dropout_p, seed, offset);
@@ -947,7 +948,7 @@ int atlas_b200_attention_train(const void* q, int64_t ldq, int32_t q_col0, const
         abh::prof_begin(ls, abh::PROF_ATTENTION);
         int lrc = (lanes_sel == 3 ? atlas_b200_attention_lanes96_launch : atlas_b200_attention_lanes_launch)(
             q, ldq, q_col0, k, ldk, k_col0, v, ldv, v_col0, out, ldo, add_mask, bias_delta, B, H, Lq, Lk, scale, causal_value,
-            lse_out, is_bf16, ls);
+            lse_out, key_block_live, is_bf16, ls);
         if (lrc) return lrc;
         abh::prof_end(ls, abh::PROF_ATTENTION, 4.0 * B * H * static_cast<double>(Lq) * Lk * D);
         abh::count_launch();

@@ -72,6 +72,9 @@ struct Params {
     float scale;
     float causal_value;
     float* lse_out;             // [B, H, Lq] or nullptr
+    const uint8_t* blk_live;    // [B, ceil(Lk / 64)] or nullptr: 0 = every key of the 64-key block is masked out (additive mask
+                                // <= -5000: softmax weight exactly 0 in fp32) -> the block is neither loaded nor computed.
+                                // FiD passages are padded to text_maxlength; a segment keeps at least one live block.
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -186,6 +189,7 @@ attention_lanes_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
     __shared__ __align__(8) uint64_t kv_full[RING], kv_empty[RING], tab_full[2], tab_empty[2];
     __shared__ uint32_t tmem_base_smem;
     __shared__ int s_mask_flag[2];                              // this item's key mask has a non-zero entry
+    __shared__ uint32_t s_live[2];                              // this item's live key blocks (bit j = block j)
     __shared__ __align__(16) float s_bias[4 * CPSTRIDE];        // 4 alignment-shifted copies of (bias (+ causal)) * log2e
     __shared__ __align__(16) float s_mask[2][MAXK];             // additive key mask * log2e, -inf beyond Lk
 
@@ -272,6 +276,13 @@ attention_lanes_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                 }
                 nonzero = __any_sync(0xffffffffu, nonzero);
                 if (lane == 0) s_mask_flag[buf] = nonzero ? 1 : 0;
+                uint32_t live = (1u << nb) - 1u;
+                if (p.blk_live != nullptr) {
+                    const bool lv = static_cast<int>(lane) < nb && __ldg(p.blk_live + static_cast<size_t>(b) * nb + lane) != 0;
+                    const uint32_t m = __ballot_sync(0xffffffffu, lv);
+                    if (m != 0u) live = m;
+                }
+                if (lane == 0) s_live[buf] = live;
                 if (has_bias && h != prev_h) {
                     // the single bias buffer is shared by consecutive items of one head: before rewriting it every reader of
                     // the previous item must be done (rare: the head changes at most twice per CTA)
@@ -308,7 +319,8 @@ attention_lanes_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                         ++chunk_ctr;
                     };
                     for (int qt = 0; qt < n_qt && qt < LANES; ++qt) load_q(qt);
-                    for (int j = 0; j < nb; ++j) {
+                    for (uint32_t lm = live; lm != 0u; lm &= lm - 1u) {      // live key blocks only, in order
+                        const int j = __ffs(lm) - 1;
                         load_chunk(&tmap_k, p.k_col0, j);
                         load_chunk(&tmap_v, p.v_col0, j);
                     }
@@ -343,14 +355,18 @@ attention_lanes_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                 ab::umma_commit(&s_full[l]);
                 ++s_ctr;
             };
+            uint32_t chunk_base = 0;                 // K / V chunks of the items before this one (2 per live block)
             for (int it = it_begin; it < it_end; ++it, ++item_it) {
-                const uint32_t chunk_base = static_cast<uint32_t>(item_it) * 2u * nb;
+                // the item's live key blocks: published by warp 0 with the tables (read once, at the item's start)
+                ab::mbar_wait_nocall(&tab_full[item_it & 1], (item_it >> 1) & 1u);
+                const uint32_t live = s_live[item_it & 1];
+                const int nl = __popc(live);
                 for (int qt = l; qt < n_qt; qt += LANES, ++tile_ctr) {
                     ab::mbar_wait_nocall(&q_full[l], tile_ctr & 1u);
-                    issue_s(chunk_base, nb == 1);
-                    for (int j = 0; j < nb; ++j, ++blk_ctr) {
+                    issue_s(chunk_base, nl == 1);
+                    for (int j = 0; j < nl; ++j, ++blk_ctr) {           // j = ordinal among the live blocks
                         // S(j + 1) goes to the tensor pipe while the softmax threads work on block j
-                        if (j + 1 < nb) issue_s(chunk_base + 2u * (j + 1), j + 2 == nb);
+                        if (j + 1 < nl) issue_s(chunk_base + 2u * (j + 1), j + 2 == nl);
                         const uint32_t cv = chunk_base + 2u * j + 1u;
                         const uint32_t sv = cv % RING;
                         ab::mbar_wait_nocall(&kv_full[sv], (cv / RING) & 1u);
@@ -365,6 +381,7 @@ attention_lanes_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                         ab::umma_commit(&pv_done[l]);
                     }
                 }
+                chunk_base += 2u * static_cast<uint32_t>(nl);
             }
         }
     } else {
@@ -413,11 +430,14 @@ attention_lanes_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
 
         // all key blocks of one query tile; kBias / kMaskAll are tile-uniform, the last block of a ragged segment always
         // applies the mask (its pad keys carry -inf)
+        uint32_t tile_live = 0;                        // live key blocks of the current item
         auto run_tile = [&](auto bias_tag, auto mask_tag, const float* pb_row, const float* mask2, float& m_ref, float& sum0,
                             float& sum1) {
             constexpr bool kBias = decltype(bias_tag)::value;
             constexpr bool kMaskAll = decltype(mask_tag)::value;
-            for (int j = 0; j < nb; ++j, ++blk_ctr) {
+            bool first = true;
+            for (uint32_t lm = tile_live; lm != 0u; lm &= lm - 1u, ++blk_ctr, first = false) {
+                const int j = __ffs(lm) - 1;                           // key block index (live blocks only)
                 const bool use_mask = kMaskAll || (j == nb - 1 && partial_last);
                 ab::mbar_wait_nocall(&s_full[l], blk_ctr & 1u);
                 ab::tc_fence_after();
@@ -445,7 +465,7 @@ attention_lanes_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                     ab::tc_fence_after();
                 }
                 // ---- lazy reference maximum ----
-                if (j == 0) {
+                if (first) {
                     if (pend) emit_pending();            // the previous tile's output (its last P.V retired above)
                     m_ref = (mb == -INFINITY) ? 0.f : mb;
                 } else {
@@ -487,6 +507,7 @@ attention_lanes_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
             ab::mbar_wait_nocall(&tab_full[buf], (item_it >> 1) & 1u);
             const float* mask2 = s_mask[buf];
             const bool item_mask = s_mask_flag[buf] != 0;
+            tile_live = s_live[buf];
             for (int qt = l; qt < n_qt; qt += LANES) {
                 const int i = qt * BQ + row;                          // query position inside the segment
                 const int off = max(p.Lq - 1 - i, 0);                 // bias index = j + off (clamped for pad rows)
@@ -526,8 +547,8 @@ attention_lanes_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
 int atlas_b200_attention_lanes_launch(const void* q, int64_t ldq, int32_t q_col0, const void* k, int64_t ldk, int32_t k_col0,
                                       const void* v, int64_t ldv, int32_t v_col0, void* out, int64_t ldo,
                                       const float* add_mask, const float* bias_delta, int32_t B, int32_t H, int32_t Lq,
-                                      int32_t Lk, float scale, float causal_value, float* lse_out, int32_t is_bf16,
-                                      cudaStream_t s) {
+                                      int32_t Lk, float scale, float causal_value, float* lse_out, const uint8_t* blk_live,
+                                      int32_t is_bf16, cudaStream_t s) {
     using namespace attn4;
     AB_REQUIRE(Lk <= MAXK && Lq <= 512, "attention_lanes: Lq <= 512 and Lk <= %d", MAXK);
     CUtensorMap tq, tk, tv;
@@ -550,6 +571,7 @@ int atlas_b200_attention_lanes_launch(const void* q, int64_t ldq, int32_t q_col0
     p.scale = scale;
     p.causal_value = causal_value;
     p.lse_out = lse_out;
+    p.blk_live = blk_live;
     const int items = B * H;
     const int grid = items < abh::num_sms() ? items : abh::num_sms();
     static bool attr_set[2] = {false, false};

@@ -475,8 +475,8 @@ attention_lanes96_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
 int atlas_b200_attention_lanes96_launch(const void* q, int64_t ldq, int32_t q_col0, const void* k, int64_t ldk, int32_t k_col0,
                                       const void* v, int64_t ldv, int32_t v_col0, void* out, int64_t ldo,
                                       const float* add_mask, const float* bias_delta, int32_t B, int32_t H, int32_t Lq,
-                                      int32_t Lk, float scale, float causal_value, float* lse_out, int32_t is_bf16,
-                                      cudaStream_t s) {
+                                      int32_t Lk, float scale, float causal_value, float* lse_out, const uint8_t* /*blk_live*/,
+                                      int32_t is_bf16, cudaStream_t s) {
     using namespace attn96;
     AB_REQUIRE(Lk <= MAXK && Lq <= 512, "attention_lanes: Lq <= 512 and Lk <= %d", MAXK);
     CUtensorMap tq, tk, tv;

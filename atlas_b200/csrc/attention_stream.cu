@@ -33,6 +33,9 @@ struct Params {
     int64_t ldq, ldkv;
     int q_col0, k_col0, v_col0;
     const float* add_mask;     // [B, Lk] or nullptr
+    const uint8_t* tile_live;  // [B, ceil(Lk / 64)] or nullptr: 0 = every key of the 64-key tile is masked out (its
+                               // probabilities are exactly 0 in fp32: exp(-10000 + s - max) underflows) -> neither loaded nor
+                               // computed.  FiD passages are padded to text_maxlength: ~45 % of the keys at BASELINE configs[3]
     float* o_partial;          // [(B * chunks + c) * Lq + i, H * 64] fp32, un-normalised
     float* ml_partial;         // [(B * chunks + c) * Lq + i, H, 2]: (row max, natural log units; row sum)
     int H, Lq, Lk, chunk;
@@ -101,11 +104,26 @@ cross_stream_kernel(const Params p) {
     const uint32_t sQ = smem_a;
     const int64_t qrow_base = static_cast<int64_t>(b) * p.Lq, krow_base = static_cast<int64_t>(b) * p.Lk;
     const int j_begin = c * p.chunk, j_end = min(p.Lk, (c + 1) * p.chunk);
-    const int n_tiles = (j_end - j_begin + BN - 1) / BN;
+    const int n_all = (j_end - j_begin + BN - 1) / BN;
     const float* mask_row = p.add_mask ? p.add_mask + static_cast<int64_t>(b) * p.Lk : nullptr;
+    // the live 64-key tiles of this chunk (uniform over the CTA; chunk <= 64 tiles)
+    uint64_t live = n_all >= 64 ? ~0ull : ((1ull << n_all) - 1ull);
+    if (p.tile_live != nullptr) {
+        const uint8_t* fl = p.tile_live + static_cast<int64_t>(b) * ((p.Lk + BN - 1) / BN) + j_begin / BN;
+        uint64_t m = 0;
+        for (int i = 0; i < n_all; ++i) m |= static_cast<uint64_t>(__ldg(fl + i) != 0) << i;
+        live = m;
+    }
+    const int n_tiles = __popcll(live);
+    // ordinal -> tile index of the chunk
+    auto tile_at = [&](int ord) {
+        uint64_t m = live;
+        for (int i = 0; i < ord; ++i) m &= m - 1;
+        return __ffsll(static_cast<long long>(m)) - 1;
+    };
 
-    auto prefetch = [&](int kt, int buf) {
-        const int j0 = j_begin + kt * BN;
+    auto prefetch = [&](int ord, int buf) {
+        const int j0 = j_begin + tile_at(ord) * BN;
         load_tile_async(smem_a + (1 + buf) * TILE_BYTES, p.kv, p.ldkv, p.k_col0 + h * D, krow_base, j0, j_end);
         load_tile_async(smem_a + (3 + buf) * TILE_BYTES, p.kv, p.ldkv, p.v_col0 + h * D, krow_base, j0, j_end);
         if (threadIdx.x < BN) {
@@ -116,7 +134,8 @@ cross_stream_kernel(const Params p) {
     };
     // Q rows (zero-filled past Lq) ride in the first cp.async group together with tile 0
     load_tile_async(sQ, p.q, p.ldq, p.q_col0 + h * D, qrow_base, 0, p.Lq);
-    prefetch(0, 0);
+    if (n_tiles > 0) prefetch(0, 0);        // a chunk without a live tile writes (0, -inf, 0): weight 0 in the merge
+    else cp_async_commit();
 
     const bool active = warp * 16 < p.Lq;                 // warps whose 16 rows are all padding only help with the loads
     const float scale2 = p.scale * LOG2E;
@@ -234,12 +253,13 @@ cross_stream_kernel(const Params p) {
 extern "C" {
 
 int atlas_b200_cross_attention_stream(const void* q, int64_t ldq, int32_t q_col0, const void* kv, int64_t ldkv, int32_t k_col0,
-                                      int32_t v_col0, const float* add_mask, int32_t B, int32_t H, int32_t Lq, int32_t Lk,
-                                      int32_t chunk, float scale, float* o_partial, float* ml_partial, int32_t is_bf16,
-                                      void* stream) {
+                                      int32_t v_col0, const float* add_mask, const uint8_t* tile_live, int32_t B, int32_t H,
+                                      int32_t Lq, int32_t Lk, int32_t chunk, float scale, float* o_partial, float* ml_partial,
+                                      int32_t is_bf16, void* stream) {
     using namespace xs;
-    AB_REQUIRE(B >= 0 && H > 0 && Lq > 0 && Lq <= BQ && Lk > 0 && chunk > 0 && chunk % BN == 0,
-               "cross_attention_stream: need Lq <= %d and a chunk that is a multiple of %d (Lq=%d chunk=%d)", BQ, BN, Lq, chunk);
+    AB_REQUIRE(B >= 0 && H > 0 && Lq > 0 && Lq <= BQ && Lk > 0 && chunk > 0 && chunk % BN == 0 && chunk <= 64 * BN,
+               "cross_attention_stream: need Lq <= %d and a chunk that is a multiple of %d, <= %d (Lq=%d chunk=%d)", BQ, BN,
+               64 * BN, Lq, chunk);
     AB_REQUIRE(ldq % 8 == 0 && ldkv % 8 == 0 && q_col0 % 8 == 0 && k_col0 % 8 == 0 && v_col0 % 8 == 0,
                "cross_attention_stream: strides and column offsets must be multiples of 8 elements");
     AB_REQUIRE(o_partial != nullptr && ml_partial != nullptr, "cross_attention_stream: partial buffers required");
@@ -252,6 +272,7 @@ int atlas_b200_cross_attention_stream(const void* q, int64_t ldq, int32_t q_col0
     p.ldq = ldq, p.ldkv = ldkv;
     p.q_col0 = q_col0, p.k_col0 = k_col0, p.v_col0 = v_col0;
     p.add_mask = add_mask;
+    p.tile_live = tile_live;
     p.o_partial = o_partial, p.ml_partial = ml_partial;
     p.H = H, p.Lq = Lq, p.Lk = Lk, p.chunk = chunk;
     p.scale = scale;

@@ -364,6 +364,9 @@ class FiD(nn.Module):
         d, H = c.d_model, c.num_heads
         h = W["shared.weight"][ids.reshape(-1)]                                  # embedding gather, [S*L, d]
         add_mask = (1.0 - mask.to(torch.float32)) * -10000.0                      # 4.18 get_extended_attention_mask
+        # 64-key blocks made of padding only (every passage is padded to text_maxlength) weigh exactly 0 in the softmax:
+        # the attention kernel skips them (ops.key_block_live), once per forward for all layers
+        live = ops.key_block_live(add_mask)
         bias = bias_by_delta(W["encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight"], L, L, True,
                              c.relative_attention_num_buckets)
         qkv = torch.empty((S * L, 3 * H * 64), dtype=dt, device=h.device)
@@ -382,7 +385,7 @@ class FiD(nn.Module):
                 else:
                     ops.linear(h, G[p + "SelfAttention.qkv_n"], out=qkv, row_ss=ss[2 * i - 1], rs_eps=eps)
                 ctx = ops.attention(qkv, 0, qkv, H * 64, qkv, 2 * H * 64, S, H, L, L, add_mask=add_mask, bias_delta=bias,
-                                    scale=1.0)
+                                    scale=1.0, block_live=live)
                 h = ops.linear(ctx, W[p + "SelfAttention.o.weight"], None, residual=h, epilogue=ops.EPI_RESIDUAL,
                                out_ss=ss[2 * i])
                 ops.clamp_inf_(h, row_ss=ss[2 * i])
@@ -397,7 +400,7 @@ class FiD(nn.Module):
                 n = ops.layernorm(h, W[p + "layer_norm.weight"], None, eps, kind=1)
                 ops.linear(n, G[p + "SelfAttention.qkv"], out=qkv)
                 ctx = ops.attention(qkv, 0, qkv, H * 64, qkv, 2 * H * 64, S, H, L, L, add_mask=add_mask, bias_delta=bias,
-                                    scale=1.0)
+                                    scale=1.0, block_live=live)
                 h = ops.clamp_inf_(ops.linear(ctx, W[p + "SelfAttention.o.weight"], None, residual=h,
                                               epilogue=ops.EPI_RESIDUAL))
                 h = self._ff(W, G, f"encoder.block.{i}.layer.1.", h, eps)
@@ -442,6 +445,7 @@ class FiD(nn.Module):
         # invert_attention_mask (4.18): -1e4 for fp16, -1e9 otherwise (src/modeling_t5.py:950)
         neg = -1e4 if dt == torch.float16 else -1e9
         cross_mask = (1.0 - enc_mask.reshape(B, Lk).to(torch.float32)) * neg
+        cross_live = ops.key_block_live(cross_mask)           # padded 64-key tiles of the encoder output: skipped, once
         qkv = torch.empty((B * T, 3 * H * 64), dtype=dt, device=h.device)
         capture = getattr(self, "_capture", False)
         for i in range(c.num_decoder_layers):
@@ -456,11 +460,11 @@ class FiD(nn.Module):
             q = ops.linear(n, W[p + "EncDecAttention.q.weight"])
             if capture:
                 ctx, lse = ops.cross_attention_split(q, 0, cross_kv[i], 0, H * 64, B, H, T, Lk, add_mask=cross_mask,
-                                                     scale=1.0, split=split, return_lse=True)
+                                                     scale=1.0, split=split, return_lse=True, tile_live=cross_live)
                 self._record_xattn(q, cross_kv[i], B, H, T, Lk, lse, cross_mask, layer=i)
             else:
                 ctx = ops.cross_attention_split(q, 0, cross_kv[i], 0, H * 64, B, H, T, Lk, add_mask=cross_mask,
-                                                scale=1.0, split=split)
+                                                scale=1.0, split=split, tile_live=cross_live)
             h = ops.clamp_inf_(ops.linear(ctx, W[p + "EncDecAttention.o.weight"], None, residual=h,
                                           epilogue=ops.EPI_RESIDUAL))
             h = self._ff(W, G, f"decoder.block.{i}.layer.2.", h, c.layer_norm_epsilon)
@@ -517,6 +521,7 @@ class FiD(nn.Module):
         pdrop = self._dropout_p()
         h = g.dropout(g.embedding(W["shared.weight"], ids), pdrop)
         add_mask = (1.0 - mask.to(torch.float32)) * -10000.0
+        add_mask._atlas_block_live = ops.key_block_live(add_mask)     # read by grad_ops._SelfAttention (all layers share it)
 
         def lin_res(x, w, res):
             # h + dropout(linear(x)) (T5LayerSelfAttention / T5LayerFF); without dropout the add is the GEMM's epilogue;

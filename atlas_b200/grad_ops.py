@@ -84,7 +84,7 @@ class _SelfAttention(torch.autograd.Function):
         ctx.drop = (dropout_p,) + next_dropout_key(qkv.device) if dropout_p else None
         out, lse = ops.attention(qkv, 0, qkv, H * 64, qkv, 2 * H * 64, B, H, L, L, add_mask=add_mask,
                                  bias_delta=bias_delta, scale=scale, causal_value=causal_value, return_lse=True,
-                                 dropout=ctx.drop)
+                                 dropout=ctx.drop, block_live=getattr(add_mask, "_atlas_block_live", None))
         ctx.save_for_backward(qkv, out, bias_delta, add_mask, lse)
         ctx.dims = (B, H, L, scale, causal_value)
         return out

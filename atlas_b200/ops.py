@@ -253,9 +253,10 @@ def masked_mean_pool(x, mask, out=None):
 
 
 def attention(q, q_col0, k, k_col0, v, v_col0, B, H, Lq, Lk, add_mask=None, bias_delta=None, scale=1.0,
-              causal_value=0.0, out=None, return_lse=False, dropout=None):
+              causal_value=0.0, out=None, return_lse=False, dropout=None, block_live=None):
     """Fused attention reading Q/K/V in place from [B*L, ld] projection buffers (head h at col0 + 64h).
     return_lse: also return the row log-sum-exp [B, H, Lq] fp32 (saved for the backward pass).
+    block_live = key_block_live(add_mask): fully masked 64-key blocks are skipped by the encoder kernel (identical results).
     dropout = (p, seed, offset): dropout on the probabilities (training), mask re-derived by attention_bwd."""
     require_cuda(q, "q")
     if out is None:
@@ -268,8 +269,33 @@ def attention(q, q_col0, k, k_col0, v, v_col0, B, H, Lq, Lk, add_mask=None, bias
                                            v_col0, _ptr(out), out.stride(0), _ptr(am) if am is not None else None,
                                            _ptr(bd) if bd is not None else None, B, H, Lq, Lk, float(scale),
                                            float(causal_value), 1, None, None, _ptr(lse) if lse is not None else None,
-                                           float(dp), int(dseed), int(doff), _bf(q), current_stream_ptr()))
+                                           float(dp), int(dseed), int(doff),
+                                           _ptr(block_live) if block_live is not None else None, _bf(q),
+                                           current_stream_ptr()))
     return (out, lse) if return_lse else out
+
+
+_SKIP_MASKED = os.environ.get("ATLAS_B200_ATTN_SKIP_MASKED", "1") != "0"    # A/B switch of the masked-key-block skipping
+
+
+def key_block_live(add_mask, block=64):
+    """uint8 [B, ceil(Lk / block)]: 1 where a block of `block` consecutive keys holds at least one key whose additive mask is
+    > -5000 (a live key).  The reference masks with -10000 (`get_extended_attention_mask`, transformers 4.18) or -1e4 / -1e9
+    (`invert_attention_mask`): the softmax weight of such a key is exp(-10000 + s - max) = 0.0 exactly in fp32, so a block
+    without a live key contributes nothing and the attention kernels skip its loads, MMAs and exponentials - bit-identical
+    results.  (Assumes |score| < ~4000, like the reference's own fp32 softmax needs to stay finite.)  A batch element without
+    any live key keeps every block live: its uniform-over-masked-keys softmax is computed like the reference's.  Returns None
+    when skipping is switched off (ATLAS_B200_ATTN_SKIP_MASKED=0) or there is no mask."""
+    if add_mask is None or not _SKIP_MASKED:
+        return None
+    B, Lk = add_mask.shape
+    nb = (Lk + block - 1) // block
+    m = add_mask
+    if nb * block != Lk:
+        m = torch.nn.functional.pad(m, (0, nb * block - Lk), value=float("-inf"))
+    live = (m.view(B, nb, block) > -5000.0).any(-1)
+    live = live | ~live.any(-1, keepdim=True)
+    return live.to(torch.uint8).contiguous()
 
 
 _XATTN_STREAM = os.environ.get("ATLAS_B200_XATTN_STREAM", "1") != "0"      # A/B switch of the stream kernel
@@ -277,7 +303,7 @@ _XATTN_CHUNK = int(os.environ.get("ATLAS_B200_XATTN_CHUNK", "512"))        # key
 
 
 def cross_attention_split(q, q_col0, kv, k_col0, v_col0, B, H, Lq, Lk_total, add_mask=None, scale=1.0, split=512,
-                          return_lse=False, dropout=None):
+                          return_lse=False, dropout=None, tile_live=None):
     """Attention of Lq (<= 128) queries per batch element over Lk_total keys (FiD decoder cross-attention,
     Lk_total = n_ctx * L): split-KV over segments of `split` keys + combine.  q [B*Lq, ld], kv [B*Lk_total, ld]."""
     require_cuda(q, "q")
@@ -288,9 +314,13 @@ def cross_attention_split(q, q_col0, kv, k_col0, v_col0, B, H, Lq, Lk_total, add
         chunks = (Lk_total + chunk - 1) // chunk
         o_part = torch.empty((B * chunks * Lq, H * 64), dtype=torch.float32, device=q.device)
         ml = torch.empty((B * chunks * Lq, H, 2), dtype=torch.float32, device=q.device)
+        if tile_live is None:
+            tile_live = key_block_live(am)          # callers with many layers compute it once (fid.py)
         check(lib().atlas_b200_cross_attention_stream(_ptr(q), q.stride(0), q_col0, _ptr(kv), kv.stride(0), k_col0, v_col0,
-                                                      _ptr(am) if am is not None else None, B, H, Lq, Lk_total, chunk,
-                                                      float(scale), _ptr(o_part), _ptr(ml), _bf(q), current_stream_ptr()))
+                                                      _ptr(am) if am is not None else None,
+                                                      _ptr(tile_live) if tile_live is not None else None, B, H, Lq, Lk_total,
+                                                      chunk, float(scale), _ptr(o_part), _ptr(ml), _bf(q),
+                                                      current_stream_ptr()))
         out = torch.empty((B * Lq, H * 64), dtype=q.dtype, device=q.device)
         lse = torch.empty((B, H, Lq), dtype=torch.float32, device=q.device) if return_lse else None
         check(lib().atlas_b200_attention_combine_ex(_ptr(o_part), _ptr(ml), B, chunks, Lq, H, _ptr(out), out.stride(0),
@@ -306,7 +336,7 @@ def cross_attention_split(q, q_col0, kv, k_col0, v_col0, B, H, Lq, Lk_total, add
     check(lib().atlas_b200_attention_train(_ptr(q), q.stride(0), q_col0, _ptr(kv), kv.stride(0), k_col0, _ptr(kv),
                                            kv.stride(0), v_col0, _ptr(dummy), 8, _ptr(am) if am is not None else None, None,
                                            B * splits, H, Lq, split, float(scale), 0.0, splits, _ptr(o_part), _ptr(ml),
-                                           None, float(dp), int(dseed), int(doff), _bf(q), current_stream_ptr()))
+                                           None, float(dp), int(dseed), int(doff), None, _bf(q), current_stream_ptr()))
     out = torch.empty((B * Lq, H * 64), dtype=q.dtype, device=q.device)
     lse = torch.empty((B, H, Lq), dtype=torch.float32, device=q.device) if return_lse else None
     check(lib().atlas_b200_attention_combine_ex(_ptr(o_part), _ptr(ml), B, splits, Lq, H, _ptr(out), out.stride(0),

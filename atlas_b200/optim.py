@@ -82,7 +82,10 @@ class AdamWFP32Copy(torch.optim.AdamW):
                     state["float32copy"] = copy.clone() if copy.data_ptr() == p.data_ptr() else copy
                     state["exp_avg"] = torch.zeros_like(state["float32copy"], memory_format=torch.preserve_format)
                     state["exp_avg_sq"] = torch.zeros_like(state["float32copy"], memory_format=torch.preserve_format)
-                state["step"] += 1
+                for key in ("float32copy", "exp_avg", "exp_avg_sq"):      # a loaded checkpoint: torch cast the state to bf16
+                    if state[key].dtype != torch.float32 or not state[key].is_contiguous():
+                        state[key] = state[key].to(torch.float32).contiguous()
+                state["step"] = int(state["step"]) + 1
                 t = int(state["step"])
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
                 keep.append(g)

@@ -247,11 +247,13 @@ class Contriever(nn.Module):
         h = h.view(B * L, H)
         # transformers==4.18 get_extended_attention_mask: (1 - mask) * -10000 (src/modeling_bert.py:993)
         add_mask = (1.0 - attention_mask.to(torch.float32)) * -10000.0
+        live = ops.key_block_live(add_mask)       # all-padding 64-key blocks (queries are padded to text_maxlength): skipped
         qkv = torch.empty((B * L, 3 * H), dtype=dt, device=h.device)
         for i in range(c.num_hidden_layers):
             p = f"encoder.layer.{i}."
             ops.linear(h, F[p + "attention.self.qkv.weight"], F[p + "attention.self.qkv.bias"], out=qkv)
-            ctx = ops.attention(qkv, 0, qkv, H, qkv, 2 * H, B, nh, L, L, add_mask=add_mask, scale=1.0 / math.sqrt(64))
+            ctx = ops.attention(qkv, 0, qkv, H, qkv, 2 * H, B, nh, L, L, add_mask=add_mask, scale=1.0 / math.sqrt(64),
+                                block_live=live)
             s1 = ops.linear(ctx, W[p + "attention.output.dense.weight"], W[p + "attention.output.dense.bias"], residual=h)
             h1 = ops.layernorm(s1, W[p + "attention.output.LayerNorm.weight"], W[p + "attention.output.LayerNorm.bias"],
                                c.layer_norm_eps, kind=0)

@@ -339,12 +339,16 @@ int atlas_b200_attention_dropout_mask(uint8_t* out, int64_t rows, int32_t Lk, fl
  * src/modeling_bert.py:354):  O = (keep o softmax(S)) V / (1 - p), the row log-sum-exp is that of the un-dropped softmax.
  * keep[b, h, i, j] is a function of (seed, offset, (b * H + h) * Lq + i, j) (csrc/dropout.cuh; j = key index over the whole
  * key range when the keys are split: segment s of `q_div` covers j = s * Lk ..., Lk % 32 == 0 required then);
- * atlas_b200_attention_bwd_train re-derives the same mask.  dropout_p == 0 is atlas_b200_attention_ex. */
+ * atlas_b200_attention_bwd_train re-derives the same mask.  dropout_p == 0 is atlas_b200_attention_ex.
+ * key_block_live (optional, uint8 [B, ceil(Lk / 64)], used by the three-lane encoder kernel): 0 marks a 64-key block whose keys
+ * are ALL masked out (additive mask <= -5000, softmax weight exactly 0 in fp32): it is neither loaded nor computed - identical
+ * results; every row keeps at least one live block (see atlas_b200_cross_attention_stream). */
 int atlas_b200_attention_train(const void* q, int64_t ldq, int32_t q_col0, const void* k, int64_t ldk, int32_t k_col0,
                                const void* v, int64_t ldv, int32_t v_col0, void* out, int64_t ldo, const float* add_mask,
                                const float* bias_delta, int32_t B, int32_t H, int32_t Lq, int32_t Lk, float scale,
                                float causal_value, int32_t q_div, float* o_partial, float* ml_partial, float* lse_out,
-                               float dropout_p, uint64_t seed, uint64_t offset, int32_t is_bf16, void* stream);
+                               float dropout_p, uint64_t seed, uint64_t offset, const uint8_t* key_block_live,
+                               int32_t is_bf16, void* stream);
 int atlas_b200_attention_bwd_train(const void* q, int64_t ldq, int32_t q_col0, const void* k, int64_t ldk, int32_t k_col0,
                                    const void* v, int64_t ldv, int32_t v_col0, const void* out, int64_t ldo,
                                    const void* dout, int64_t lddo, void* dq, int64_t lddq, int32_t dq_col0, void* dk,
@@ -396,11 +400,15 @@ int atlas_b200_clamp_inf_fp16(void* x, int64_t ld, int64_t M, int32_t N, int32_t
  * (src/fid.py:298-349 at the teacher-forced / training forward shape): an HBM-bound K / V stream.  q [B*Lq, ldq], kv [B*Lk, ldkv]
  * (k at k_col0 + 64 h, v at v_col0 + 64 h).  Every CTA covers `chunk` keys (multiple of 64) of one (batch, head) and writes
  * un-normalised fp32 partials o_partial [(b * chunks + c) * Lq + i, H*64] and ml_partial [.., H, 2] = (row max, row sum) in the
- * layout atlas_b200_attention_combine_ex merges (splits = ceil(Lk / chunk)). */
+ * layout atlas_b200_attention_combine_ex merges (splits = ceil(Lk / chunk)).
+ * tile_live (optional, uint8 [B, ceil(Lk / 64)]): 0 marks a 64-key tile whose keys are ALL masked out (additive mask <= -5000:
+ * their probabilities are exactly 0 in fp32, the reference's `exp(-10000 + s - max)` underflows); such tiles are neither
+ * loaded nor computed - same result, ~45 % fewer K / V bytes on text_maxlength-padded FiD passages.  A row of tile_live must
+ * keep at least one live tile (the caller marks all tiles live for a fully masked batch element). */
 int atlas_b200_cross_attention_stream(const void* q, int64_t ldq, int32_t q_col0, const void* kv, int64_t ldkv, int32_t k_col0,
-                                      int32_t v_col0, const float* add_mask, int32_t B, int32_t H, int32_t Lq, int32_t Lk,
-                                      int32_t chunk, float scale, float* o_partial, float* ml_partial, int32_t is_bf16,
-                                      void* stream);
+                                      int32_t v_col0, const float* add_mask, const uint8_t* tile_live, int32_t B, int32_t H,
+                                      int32_t Lq, int32_t Lk, int32_t chunk, float scale, float* o_partial, float* ml_partial,
+                                      int32_t is_bf16, void* stream);
 
 /* Measurement hook for bench.py's roofline: while enabled, every launch of ONE kind of kernel is bracketed
  * with CUDA events on its launching stream:

