@@ -150,7 +150,7 @@ def lib():
     L.atlas_b200_attention_bwd_train.restype = c.c_int
     L.atlas_b200_attention_bwd_train.argtypes = [vp, i64, i32, vp, i64, i32, vp, i64, i32, vp, i64, vp, i64, vp, i64, i32,
                                                  vp, i64, i32, vp, i64, i32, vp, vp, vp, vp, i32, vp, vp, i32, i32, i32,
-                                                 i32, f32, f32, f32, u64, u64, i32, vp]
+                                                 i32, f32, f32, f32, u64, u64, vp, i32, vp]
     L.atlas_b200_adamw_fp32copy.restype = c.c_int
     L.atlas_b200_adamw_fp32copy.argtypes = [vp, vp, i32, i32, f32, f32, f32, f32, f32, f32, vp]
     L.atlas_b200_grad_stats.restype = c.c_int

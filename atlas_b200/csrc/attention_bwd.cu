@@ -53,6 +53,8 @@ struct Params {
     int B, H, Lq, Lk;
     float scale, causal_value;
     abdrop::Key drop;         // attention-probability dropout of the forward (second-generation kernels only); thr16 == 0: off
+    const uint8_t* blk_live;  // [B, ceil(Lk / 64)] or nullptr: 64-key blocks whose keys are all masked out (softmax weight exactly
+                              // 0 in fp32, so dS = 0, dK = dV = 0 there): skipped by the second-generation kernels
 };
 
 // ---- shared-memory tiles: 64 rows x 128 bytes, 16-byte chunks XOR-swizzled by the row ------------------------------
@@ -568,7 +570,14 @@ attn_bwd_dq2_kernel(const Params p) {
         }
         cp_async_commit();
     };
-    if (kb_begin < kb_end) prefetch(kb_begin, 0);
+    // key blocks whose keys are all masked out contribute dS = 0 exactly: walk the live ones only
+    const uint8_t* live_row = p.blk_live ? p.blk_live + static_cast<int64_t>(b) * nkb : nullptr;
+    auto next_live = [&](int kb) {
+        while (kb < kb_end && live_row != nullptr && __ldg(live_row + kb) == 0) ++kb;
+        return kb;
+    };
+    int kb_cur = next_live(kb_begin);
+    if (kb_cur < kb_end) prefetch(kb_cur, 0);
 
     float dqacc[8][4];
 #pragma unroll
@@ -576,11 +585,13 @@ attn_bwd_dq2_kernel(const Params p) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) dqacc[nt][e] = 0.f;
     const float* bias_c = bias_s ? bias_s + BIAS_PAD : nullptr;
-    for (int kb = kb_begin; kb < kb_end; ++kb) {
-        const int buf = (kb - kb_begin) & 1;
+    for (int nblk = 0; kb_cur < kb_end; ++nblk) {
+        const int kb = kb_cur;
+        const int buf = nblk & 1;
         cp_async_wait_all();
         __syncthreads();                       // this block's tiles are visible; everyone is done with the other buffer
-        if (kb + 1 < kb_end) prefetch(kb + 1, buf ^ 1);
+        kb_cur = next_live(kb + 1);
+        if (kb_cur < kb_end) prefetch(kb_cur, buf ^ 1);
         const uint32_t sK_a = smem_a + (2 + buf) * TILE_BYTES, sV_a = smem_a + (4 + buf) * TILE_BYTES;
         float acc[8][4], dp[8][4];
 #pragma unroll
@@ -702,6 +713,21 @@ attn_bwd_dkv2_kernel(const Params p) {
     const float* lse_g = p.lse + (static_cast<int64_t>(b) * p.H + h) * p.Lq;
     const float* d_g = p.dsum + (static_cast<int64_t>(b) * p.H + h) * p.Lq;
 
+    if (p.blk_live != nullptr && __ldg(p.blk_live + static_cast<int64_t>(b) * nkb + kb) == 0) {
+        // every key of this block is masked out: P = 0 exactly, so dK = dV = 0 (what the full computation would store)
+        const int r = k0 + (static_cast<int>(threadIdx.x) >> 1), c0 = (static_cast<int>(threadIdx.x) & 1) * 32;
+        if (r < p.Lk) {
+            uint4* dkp = reinterpret_cast<uint4*>(p.dk + (krow_base + r) * p.lddk + p.dk_col0 + h * D + c0);
+            uint4* dvp = reinterpret_cast<uint4*>(p.dv + (krow_base + r) * p.lddv + p.dv_col0 + h * D + c0);
+#pragma unroll
+            for (int v4 = 0; v4 < 4; ++v4) {
+                dkp[v4] = make_uint4(0u, 0u, 0u, 0u);
+                dvp[v4] = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+        return;
+    }
+
     if (bias_s)
         for (int x = threadIdx.x; x < ntab + 2 * BIAS_PAD; x += THREADS) {
             const int d = x - BIAS_PAD;
@@ -813,8 +839,9 @@ int atlas_b200_attn_bwd_dq_tc(const void* q, int64_t ldq, int32_t q_col0, const 
 int atlas_b200_attn_bwd_dkv_tc(const void* q, int64_t ldq, int32_t q_col0, const void* k, int64_t ldk, int32_t k_col0,
                                const void* v, int64_t ldv, int32_t v_col0, const void* dout, int64_t lddo, void* dk,
                                int64_t lddk, int32_t dk_col0, void* dv, int64_t lddv, int32_t dv_col0, const float* add_mask,
-                               const float* bias_delta, const float* lse, const float* dsum, int32_t B, int32_t H, int32_t Lq,
-                               int32_t Lk, float scale, float causal_value, int32_t is_bf16, cudaStream_t s);
+                               const float* bias_delta, const float* lse, const float* dsum, const uint8_t* blk_live,
+                               int32_t B, int32_t H, int32_t Lq, int32_t Lk, float scale, float causal_value, int32_t is_bf16,
+                               cudaStream_t s);
 
 extern "C" {
 
@@ -827,7 +854,7 @@ int atlas_b200_attention_bwd(const void* q, int64_t ldq, int32_t q_col0, const v
                              float causal_value, int32_t is_bf16, void* stream) {
     return atlas_b200_attention_bwd_train(q, ldq, q_col0, k, ldk, k_col0, v, ldv, v_col0, out, ldo, dout, lddo, dq, lddq,
                                           dq_col0, dk, lddk, dk_col0, dv, lddv, dv_col0, add_mask, bias_delta, dbias_delta,
-                                          lse, lse_given, dsum, dq_accum, B, H, Lq, Lk, scale, causal_value, 0.f, 0, 0,
+                                          lse, lse_given, dsum, dq_accum, B, H, Lq, Lk, scale, causal_value, 0.f, 0, 0, nullptr,
                                           is_bf16, stream);
 }
 
@@ -838,7 +865,7 @@ int atlas_b200_attention_bwd_train(const void* q, int64_t ldq, int32_t q_col0, c
                                    const float* add_mask, const float* bias_delta, float* dbias_delta, float* lse,
                                    int32_t lse_given, float* dsum, float* dq_accum, int32_t B, int32_t H, int32_t Lq,
                                    int32_t Lk, float scale, float causal_value, float dropout_p, uint64_t seed,
-                                   uint64_t offset, int32_t is_bf16, void* stream) {
+                                   uint64_t offset, const uint8_t* key_block_live, int32_t is_bf16, void* stream) {
     using namespace attnb;
     AB_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "attention_bwd: need 0 <= dropout_p < 1 (got %f)", dropout_p);
     const abdrop::Key drop = abdrop::make_key(dropout_p, seed, offset);
@@ -894,6 +921,7 @@ int atlas_b200_attention_bwd_train(const void* q, int64_t ldq, int32_t q_col0, c
     p.scale = scale;
     p.causal_value = causal_value;
     p.drop = drop;
+    p.blk_live = key_block_live;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     static const bool force_v1 = getenv("ATLAS_B200_ATTN_BWD_V1") != nullptr;   // A/B measurements
     const bool v2 = lse_given != 0 && (!force_v1 || drop.thr16 != 0u);
@@ -939,8 +967,8 @@ int atlas_b200_attention_bwd_train(const void* q, int64_t ldq, int32_t q_col0, c
         }
         if (dq_done && tc_level >= 2) {
             const int rc2 = atlas_b200_attn_bwd_dkv_tc(q, ldq, q_col0, k, ldk, k_col0, v, ldv, v_col0, dout, lddo, dk, lddk,
-                                                       dk_col0, dv, lddv, dv_col0, add_mask, bias_delta, lse, dsum, B, H, Lq, Lk,
-                                                       scale, causal_value, is_bf16, s);
+                                                       dk_col0, dv, lddv, dv_col0, add_mask, bias_delta, lse, dsum, key_block_live, B,
+                                                       H, Lq, Lk, scale, causal_value, is_bf16, s);
             if (rc2 == ATLAS_B200_OK) dkv_done = true;
             else if (rc2 != ATLAS_B200_EUNSUPPORTED) return rc2;
         }

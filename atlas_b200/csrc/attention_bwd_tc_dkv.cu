@@ -51,6 +51,8 @@ struct Params {
     const float* bias_delta;
     const float* lse;
     const float* dsum;
+    const uint8_t* blk_live;     // [B, ceil(Lk / 64)] or nullptr: key blocks whose keys are all masked out (probability exactly 0
+                                 // in fp32 -> dK = dV = 0 exactly): a 128-key tile of two dead blocks is skipped by every role
     float scale, causal_value;
 };
 
@@ -108,6 +110,13 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
     const int lq_pad = n_qc * BLOCK, lk_pad = n_kt * BLOCK;
     const int n_items = p.B * p.H;
     const int ntab = p.Lq + p.Lk - 1;
+    const int nb64 = (p.Lk + 63) / 64;
+    // identical in every role (uniform global reads): the barrier phase counters only advance for live tiles
+    auto tile_dead = [&](int b, int kt) -> bool {
+        if (p.blk_live == nullptr) return false;
+        const uint8_t* f = p.blk_live + static_cast<size_t>(b) * nb64 + 2 * kt;
+        return f[0] == 0 && (2 * kt + 1 >= nb64 || f[1] == 0);
+    };
 
     if (warp == 0 && lane == 0) {
         ab::tma_prefetch_desc(&tmap_q);
@@ -150,7 +159,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                                     ab::kEvictNormal);
                     ab::tma_load_2d(&tmap_do, &qdo_full, sdO + c * TILE_BYTES, h * D, b * p.Lq + c * BLOCK, ab::kEvictNormal);
                 }
-                for (int kt = 0; kt < n_kt; ++kt, ++kt_it) {
+                for (int kt = 0; kt < n_kt; ++kt) {
+                    if (tile_dead(b, kt)) continue;
                     const int kb = kt_it & 1;
                     ab::mbar_wait(&kv_empty[kb], ((kt_it >> 1) & 1) ^ 1u, 82);
                     ab::mbar_arrive_expect_tx(&kv_full[kb], 2 * TILE_BYTES);
@@ -158,6 +168,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                                     ab::kEvictFirst);
                     ab::tma_load_2d(&tmap_v, &kv_full[kb], sV + kb * TILE_BYTES, p.v_col0 + h * D, b * p.Lk + kt * BLOCK,
                                     ab::kEvictFirst);
+                    ++kt_it;
                 }
             }
         }
@@ -169,7 +180,9 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
             int item_it = 0, kt_it = 0, ch = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_it) {
                 ab::mbar_wait(&qdo_full, item_it & 1, 83);
-                for (int kt = 0; kt < n_kt; ++kt, ++kt_it) {
+                const int b = item / p.H;
+                for (int kt = 0; kt < n_kt; ++kt) {
+                    if (tile_dead(b, kt)) continue;
                     const int kb = kt_it & 1;
                     ab::mbar_wait(&kv_full[kb], (kt_it >> 1) & 1, 84);
                     ab::tc_fence_after();
@@ -207,6 +220,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                         if (c + 1 < n_qc) issue_sp(c + 1);
                     }
                     ab::umma_commit(&kv_empty[kb]);     // every MMA reading this K / V tile has been issued
+                    ++kt_it;
                 }
                 ab::umma_commit(&qdo_empty);            // ... and this item's Q / dO
             }
@@ -256,9 +270,22 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
             const int buf = item_it & 1;
             ab::mbar_wait(&aux_full[buf], (item_it >> 1) & 1, 88);
             const float* bias2 = s_bias[buf];
-            for (int kt = 0; kt < n_kt; ++kt, ++kt_it) {
+            for (int kt = 0; kt < n_kt; ++kt) {
                 const int j = kt * BLOCK + row;                 // this thread's key
                 const bool live = j < p.Lk;
+                if (tile_dead(b, kt)) {                         // all-masked keys: dK = dV = 0 (what the full computation yields)
+                    if (live) {
+                        const int64_t grow = static_cast<int64_t>(b) * p.Lk + j;
+                        uint4* dv_dst = reinterpret_cast<uint4*>(p.dv + grow * p.lddv + p.dv_col0 + h * D + part * 32);
+                        uint4* dk_dst = reinterpret_cast<uint4*>(p.dk + grow * p.lddk + p.dk_col0 + h * D + part * 32);
+#pragma unroll
+                        for (int v4 = 0; v4 < 4; ++v4) {
+                            dv_dst[v4] = make_uint4(0u, 0u, 0u, 0u);
+                            dk_dst[v4] = make_uint4(0u, 0u, 0u, 0u);
+                        }
+                    }
+                    continue;
+                }
                 const float mk = s_mask[buf][min(j, lk_pad - 1)];
                 const int jb = j + p.Lq - 1;                    // bias index = jb - i
                 for (int c = 0; c < n_qc; ++c, ++ch) {
@@ -334,6 +361,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                 }
                 ab::tc_fence_before();
                 ab::mbar_arrive(&dkv_free);
+                ++kt_it;
             }
             ab::mbar_arrive(&aux_empty[buf]);       // last read of this item's tables
         }
@@ -354,8 +382,9 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
 int atlas_b200_attn_bwd_dkv_tc(const void* q, int64_t ldq, int32_t q_col0, const void* k, int64_t ldk, int32_t k_col0,
                                const void* v, int64_t ldv, int32_t v_col0, const void* dout, int64_t lddo, void* dk,
                                int64_t lddk, int32_t dk_col0, void* dv, int64_t lddv, int32_t dv_col0, const float* add_mask,
-                               const float* bias_delta, const float* lse, const float* dsum, int32_t B, int32_t H, int32_t Lq,
-                               int32_t Lk, float scale, float causal_value, int32_t is_bf16, cudaStream_t s) {
+                               const float* bias_delta, const float* lse, const float* dsum, const uint8_t* blk_live,
+                               int32_t B, int32_t H, int32_t Lq, int32_t Lk, float scale, float causal_value, int32_t is_bf16,
+                               cudaStream_t s) {
     using namespace attnb_tc_dkv;
     if (Lk > MAX_L || Lq > MAX_L || Lq + Lk - 1 > 2 * MAX_L) return ATLAS_B200_EUNSUPPORTED;
     CUtensorMap tq, tk, tv, tdo;
@@ -382,6 +411,7 @@ int atlas_b200_attn_bwd_dkv_tc(const void* q, int64_t ldq, int32_t q_col0, const
     p.bias_delta = bias_delta;
     p.lse = lse;
     p.dsum = dsum;
+    p.blk_live = blk_live;
     p.scale = scale;
     p.causal_value = causal_value;
     const int items = B * H;

@@ -582,6 +582,7 @@ class FiD(nn.Module):
                              c.relative_attention_num_buckets)
         neg = -1e4 if dt == torch.float16 else -1e9
         cross_mask = (1.0 - enc_mask.reshape(B, Lk).to(torch.float32)) * neg
+        cross_mask._atlas_block_live = ops.key_block_live(cross_mask)     # padded 64-key tiles: skipped forward and backward
 
         def block(i, h, bias, flat):
             p = f"decoder.block.{i}.layer.0."

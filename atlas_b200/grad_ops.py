@@ -97,7 +97,8 @@ class _SelfAttention(torch.autograd.Function):
         dbias = ops.attention_bwd(qkv, 0, qkv, H * 64, qkv, 2 * H * 64, out, dout.contiguous(), dqkv, 0, dqkv, H * 64,
                                   dqkv, 2 * H * 64, B, H, L, L, add_mask=add_mask, bias_delta=bias_delta,
                                   need_dbias=bias_delta is not None and _need(ctx, 1), scale=scale,
-                                  causal_value=causal_value, lse=lse, dropout=ctx.drop)
+                                  causal_value=causal_value, lse=lse, dropout=ctx.drop,
+                                  block_live=getattr(add_mask, "_atlas_block_live", None))
         return dqkv, dbias, None, None, None, None, None, None, None
 
 
@@ -113,7 +114,8 @@ class _CrossAttention(torch.autograd.Function):
     def forward(ctx, q, kv, add_mask, B, H, T, Lk, scale, split, dropout_p):
         ctx.drop = (dropout_p,) + next_dropout_key(q.device) if dropout_p else None
         out, lse = ops.cross_attention_split(q, 0, kv, 0, H * 64, B, H, T, Lk, add_mask=add_mask, scale=scale,
-                                             split=split, return_lse=True, dropout=ctx.drop)
+                                             split=split, return_lse=True, dropout=ctx.drop,
+                                             tile_live=getattr(add_mask, "_atlas_block_live", None))
         ctx.save_for_backward(q, kv, out, add_mask, lse)
         ctx.dims = (B, H, T, Lk, scale)
         ctx.mark_non_differentiable(lse)
@@ -126,7 +128,8 @@ class _CrossAttention(torch.autograd.Function):
         dq = torch.empty((B * T, H * 64), dtype=q.dtype, device=q.device)
         dkv = torch.empty_like(kv)
         ops.attention_bwd(q, 0, kv, 0, kv, H * 64, out, dout.contiguous(), dq, 0, dkv, 0, dkv, H * 64, B, H, T, Lk,
-                          add_mask=add_mask, scale=scale, lse=lse, split_keys=Lk > 1024, dropout=ctx.drop)
+                          add_mask=add_mask, scale=scale, lse=lse, split_keys=Lk > 1024, dropout=ctx.drop,
+                          block_live=getattr(add_mask, "_atlas_block_live", None))
         return dq, dkv, None, None, None, None, None, None, None, None
 
 

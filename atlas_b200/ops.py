@@ -299,7 +299,7 @@ def key_block_live(add_mask, block=64):
 
 
 _XATTN_STREAM = os.environ.get("ATLAS_B200_XATTN_STREAM", "1") != "0"      # A/B switch of the stream kernel
-_XATTN_CHUNK = int(os.environ.get("ATLAS_B200_XATTN_CHUNK", "512"))        # keys per CTA (multiple of 64)
+_XATTN_CHUNK = int(os.environ.get("ATLAS_B200_XATTN_CHUNK", "1024"))        # keys per CTA (multiple of 64)
 
 
 def cross_attention_split(q, q_col0, kv, k_col0, v_col0, B, H, Lq, Lk_total, add_mask=None, scale=1.0, split=512,
@@ -556,7 +556,7 @@ def cross_entropy_bwd(logits, labels, lse, gscale):
 
 def attention_bwd(q, q_col0, k, k_col0, v, v_col0, out, dout, dq, dq_col0, dk, dk_col0, dv, dv_col0, B, H, Lq, Lk,
                   add_mask=None, bias_delta=None, need_dbias=False, scale=1.0, causal_value=0.0, lse=None,
-                  split_keys=False, dropout=None):
+                  split_keys=False, dropout=None, block_live=None):
     """Backward of `attention` / `cross_attention_split` (un-split key range).  dq / dk / dv are written in place at
     their column offsets; returns dbias_delta fp32 [H, Lq+Lk-1] (or None).  `lse` = the forward's log-sum-exp
     (return_lse=True) saves the recomputation pass; split_keys (needs lse, no dbias; dq must be a whole contiguous
@@ -581,7 +581,7 @@ def attention_bwd(q, q_col0, k, k_col0, v, v_col0, out, dout, dq, dq_col0, dk, d
         dv.stride(0), dv_col0, _ptr(am) if am is not None else None, _ptr(bd) if bd is not None else None,
         _ptr(dbias) if dbias is not None else None, _ptr(lse_buf), 1 if lse is not None else 0, _ptr(dsum),
         _ptr(accum) if accum is not None else None, B, H, Lq, Lk, float(scale), float(causal_value), float(dp),
-        int(dseed), int(doff), _bf(q), current_stream_ptr()))
+        int(dseed), int(doff), _ptr(block_live) if block_live is not None else None, _bf(q), current_stream_ptr()))
     if accum is not None:
         check(lib().atlas_b200_cast_f32(_ptr(accum), _ptr(dq), accum.numel(), _bf(q), current_stream_ptr()))
     return dbias

@@ -356,7 +356,7 @@ int atlas_b200_attention_bwd_train(const void* q, int64_t ldq, int32_t q_col0, c
                                    const float* add_mask, const float* bias_delta, float* dbias_delta, float* lse,
                                    int32_t lse_given, float* dsum, float* dq_accum, int32_t B, int32_t H, int32_t Lq,
                                    int32_t Lk, float scale, float causal_value, float dropout_p, uint64_t seed,
-                                   uint64_t offset, int32_t is_bf16, void* stream);
+                                   uint64_t offset, const uint8_t* key_block_live, int32_t is_bf16, void* stream);
 
 /* Multi-tensor optimiser step and gradient statistics of the training loop.  The work list is a device
  * table of (tensor index, chunk index) int32 pairs, `chunk_elems` elements per chunk (multiple of 4).
