@@ -327,6 +327,11 @@ class Contriever(nn.Module):
         if position_ids is not None or inputs_embeds is not None:
             raise AtlasB200Error("position_ids / inputs_embeds are not used by Atlas and not supported")
         with_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if not with_grad and self.config.pooling == "average" and not normalize:
+            emb = self._embed_graphed(input_ids, attention_mask, token_type_ids)
+            if emb is not None:
+                pd = self.embeddings.word_embeddings.weight.dtype
+                return emb if emb.dtype == pd else emb.to(pd)
         if with_grad:   # retriever training (src/atlas.py:457-465): autograd through the kernels
             last_hidden = self._encode_train(input_ids, attention_mask, token_type_ids)
         else:
@@ -342,6 +347,43 @@ class Contriever(nn.Module):
             emb = torch.nn.functional.normalize(emb.float(), dim=-1).to(emb.dtype)
         pd = self.embeddings.word_embeddings.weight.dtype
         return emb if emb.dtype == pd else emb.to(pd)
+
+    @torch.no_grad()
+    def _embed_graphed(self, input_ids, attention_mask, token_type_ids):
+        """Small no-grad batches (query embedding: 8 x 384 tokens at BASELINE configs[3]) are launch-bound - ~100 kernel
+        launches for well under a millisecond of GPU work - so the whole encode + pooling is replayed from one CUDA graph per
+        (shape, dtype, weight-buffer generation), like the reader's forward (fid._GraphRunner).  Larger batches (index refresh)
+        keep the eager path: they are GPU-bound and would pin large activation pools.  Returns None when not applicable."""
+        import os
+
+        if os.environ.get("ATLAS_B200_CUDA_GRAPH", "1") == "0" or not input_ids.is_cuda:
+            return None
+        B, L = input_ids.shape
+        if B * L > 16384 or torch.cuda.is_current_stream_capturing():
+            return None
+        from .fid import _GraphRunner
+
+        dt = self._dtype()
+        self._half.get(self, dt)                              # the 16-bit weight buffers exist / are current before capture
+        self._half.derived(dt, self._fuse)                    # ... and the fused q|k|v copies (refreshed in place, never in a replay)
+        gen = self._half.sets[dt]["gen"]
+        mask = attention_mask if attention_mask is not None else torch.ones_like(input_ids)
+        has_tt = token_type_ids is not None
+        key = (B, L, dt, gen, has_tt, input_ids.device, mask.dtype)
+        graphs = self.__dict__.setdefault("_graphs", {})
+        runner = graphs.get(key)
+        if runner is None:
+            if len(graphs) >= 4:
+                graphs.pop(next(iter(graphs)))
+
+            def fn(ids, m, *tt):
+                hidden = self.encode(ids, m, tt[0] if tt else None)
+                return ops.masked_mean_pool(hidden, m)
+
+            example = (input_ids, mask) + ((token_type_ids,) if has_tt else ())
+            runner = graphs[key] = _GraphRunner(fn, example)
+        args = (input_ids, mask) + ((token_type_ids,) if has_tt else ())
+        return runner(*args).clone()
 
     @torch.no_grad()
     def embed_fp16(self, input_ids, attention_mask):
