@@ -622,6 +622,12 @@ def run_ours(args):
         parity = parity_check(index, q_par, dev, world, rank)
     assert parity["status"] == "ok", f"search parity check failed: {parity}"
 
+    # the interpreter's cyclic GC is kept out of the timed regions of BOTH arms of this process (a generation-2 pass over the
+    # millions of objects transformers / torch import costs 10 - 30 ms, i.e. a whole step, whenever it happens to trigger)
+    import gc
+
+    gc.collect()
+    gc.freeze()
     # ---------------- value: device-resident inputs -----------------------------------------
     n_warm = max(args.warmup, 3 if world == 1 else 10)     # NCCL connections / graph capture settle before timing
     for _ in range(n_warm):
