@@ -64,6 +64,23 @@ elif what == "mips":
     fn = lambda: ops.mips_topk(bank, q, k)
     ms = timed(fn, reps)
     print(f"mips n={n} nq={nq} k={k}: {ms:.3f} ms = {n * 768 * 2 / ms / 1e6:.0f} GB/s over the bank")
+elif what == "xattn":
+    # FiD-base decoder cross-attention of the teacher-forced forward: 8 queries x 32 target tokens against 40 x 384 encoder keys,
+    # passages of U[148, 276] real tokens padded to 384 (the bench's length distribution)
+    B, H, T, n, Lp = 8, 12, 32, 40, 384
+    Lk = n * Lp
+    q = torch.randn(B * T, H * 64, device=dev).bfloat16() * 0.3
+    kv = torch.randn(B * Lk, 2 * H * 64, device=dev).bfloat16() * 0.3
+    lens = torch.randint(148, 277, (B, n), device=dev)
+    valid = torch.arange(Lp, device=dev)[None, None, :] < lens[..., None]
+    mask = ((~valid).reshape(B, Lk).float() * -1e9)
+    live = ops.key_block_live(mask)
+    fn = lambda: ops.cross_attention_split(q, 0, kv, 0, H * 64, B, H, T, Lk, add_mask=mask, scale=1.0, split=384, tile_live=live)
+    ms = timed(fn, reps)
+    frac = float(live.float().mean()) if live is not None else 1.0
+    byt = B * Lk * 2 * H * 64 * 2
+    print(f"cross-attention B={B} H={H} T={T} Lk={Lk}: {ms:.3f} ms (stream + combine); K/V {byt / 1e6:.0f} MB, live tiles {frac:.2f}: "
+          f"{byt * frac / ms / 1e6:.0f} GB/s on the live bytes, {byt / ms / 1e6:.0f} GB/s dense-equivalent")
 elif what == "attn_bwd":
     S, H, L = 80, 12, 384       # FiD-base encoder, 2 queries x 40 passages (the bench's training leg)
     qkv = torch.randn(S * L, 3 * H * 64, device=dev).bfloat16() * 0.2
