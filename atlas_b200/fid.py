@@ -333,8 +333,8 @@ class FiD(nn.Module):
                     [W[name], W[name.replace("q.weight", "k.weight")], W[name.replace("q.weight", "v.weight")]], 0)
             elif name.endswith("EncDecAttention.k.weight"):
                 g[name.replace("k.weight", "kv")] = torch.cat([W[name], W[name.replace("k.weight", "v.weight")]], 0)
-        # encoder projections with the preceding RMSNorm weight folded in (W'[n, k] = W[n, k] * ln[k]) for the fused norm
-        for name in [n for n in g if n.startswith("encoder.")]:
+        # projections with the preceding RMSNorm weight folded in (W'[n, k] = W[n, k] * ln[k]) for the fused norm
+        for name in list(g):
             if name.endswith("SelfAttention.qkv"):
                 ln = W[name.replace("SelfAttention.qkv", "layer_norm.weight")]
             elif name.endswith("DenseReluDense.wi_01"):
@@ -342,6 +342,10 @@ class FiD(nn.Module):
             else:
                 continue
             g[name + "_n"] = (g[name].float() * ln.float()[None, :]).to(g[name].dtype).contiguous()
+        for name in list(W):        # decoder cross-attention query projection behind layer.1's norm
+            if name.endswith("EncDecAttention.q.weight"):
+                ln = W[name.replace("EncDecAttention.q.weight", "layer_norm.weight")]
+                g[name + "_n"] = (W[name].float() * ln.float()[None, :]).to(W[name].dtype).contiguous()
         return g
 
     # ---- encoder ---------------------------------------------------------------------------
@@ -448,6 +452,41 @@ class FiD(nn.Module):
         cross_live = ops.key_block_live(cross_mask)           # padded 64-key tiles of the encoder output: skipped, once
         qkv = torch.empty((B * T, 3 * H * 64), dtype=dt, device=h.device)
         capture = getattr(self, "_capture", False)
+        if self.fuse_norm and not capture:
+            # RMSNorm fused around the decoder GEMMs exactly like the encoder's (see encode): the three residual GEMMs of a
+            # block emit each row's sum of squares, the consuming projections read the un-normalised rows with the norm weight
+            # folded into their matrices.  3 x num_decoder_layers - 1 launches of a ~150-launch dependent chain disappear.
+            eps = c.layer_norm_epsilon
+            nl = c.num_decoder_layers
+            ss = torch.zeros((3 * nl, B * T), dtype=torch.float32, device=h.device)
+            for i in range(nl):
+                p = f"decoder.block.{i}.layer.0."
+                if i == 0:
+                    n = ops.layernorm(h, W[p + "layer_norm.weight"], None, eps, kind=1)
+                    ops.linear(n, G[p + "SelfAttention.qkv"], out=qkv)
+                else:
+                    ops.linear(h, G[p + "SelfAttention.qkv_n"], out=qkv, row_ss=ss[3 * i - 1], rs_eps=eps)
+                ctx = ops.attention(qkv, 0, qkv, H * 64, qkv, 2 * H * 64, B, H, T, T, bias_delta=bias, scale=1.0,
+                                    causal_value=-10000.0)
+                h = ops.linear(ctx, W[p + "SelfAttention.o.weight"], None, residual=h, epilogue=ops.EPI_RESIDUAL,
+                               out_ss=ss[3 * i])
+                ops.clamp_inf_(h, row_ss=ss[3 * i])
+                p = f"decoder.block.{i}.layer.1."
+                q = ops.linear(h, G[p + "EncDecAttention.q.weight_n"], row_ss=ss[3 * i], rs_eps=eps)
+                ctx = ops.cross_attention_split(q, 0, cross_kv[i], 0, H * 64, B, H, T, Lk, add_mask=cross_mask,
+                                                scale=1.0, split=split, tile_live=cross_live)
+                h = ops.linear(ctx, W[p + "EncDecAttention.o.weight"], None, residual=h, epilogue=ops.EPI_RESIDUAL,
+                               out_ss=ss[3 * i + 1])
+                ops.clamp_inf_(h, row_ss=ss[3 * i + 1])
+                p = f"decoder.block.{i}.layer.2."
+                g = ops.linear(h, G[p + "DenseReluDense.wi_01_n"], epilogue=ops.EPI_GATED, row_ss=ss[3 * i + 1], rs_eps=eps)
+                h = ops.linear(g, W[p + "DenseReluDense.wo.weight"], None, residual=h, epilogue=ops.EPI_RESIDUAL,
+                               out_ss=ss[3 * i + 2])
+                ops.clamp_inf_(h, row_ss=ss[3 * i + 2])
+            h = ops.layernorm(h, W["decoder.final_layer_norm.weight"], None, eps, kind=1)
+            if getattr(c, "tie_word_embeddings", False):
+                h = (h.float() * (d ** -0.5)).to(dt)                              # src/modeling_t5.py:1642-1645
+            return ops.linear(h, W["lm_head.weight"]).view(B, T, -1)
         for i in range(c.num_decoder_layers):
             p = f"decoder.block.{i}.layer.0."
             n = ops.layernorm(h, W[p + "layer_norm.weight"], None, c.layer_norm_epsilon, kind=1)

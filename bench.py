@@ -747,7 +747,9 @@ def run_ours(args):
 
     peak, peak_src = peaks("tensor")
     gemm_traffic, gemm_traffic_note = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")
+    if not os.path.exists(tpath):
+        tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
     if os.path.exists(tpath):     # dram bytes of ONE representative launch from the committed `ncu --set full` capture
         with open(tpath) as f:
             tj = json.load(f)
