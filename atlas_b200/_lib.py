@@ -160,6 +160,13 @@ def lib():
     L.atlas_b200_cross_attention_stream.restype = c.c_int
     L.atlas_b200_cross_attention_stream.argtypes = [vp, i64, i32, vp, i64, i32, i32, vp, vp, i32, i32, i32, i32, i32, f32, vp,
                                                     vp, i32, vp]
+    L.atlas_b200_compact_live_tiles.restype = c.c_int
+    L.atlas_b200_compact_live_tiles.argtypes = [vp, i64, vp, i32, i32, vp, i64, vp, vp, vp]
+    L.atlas_b200_linear_dynm.restype = c.c_int
+    L.atlas_b200_linear_dynm.argtypes = [vp, i64, vp, i64, vp, i64, i32, i32, i32, vp, i32, vp]
+    L.atlas_b200_cross_attention_stream_compact.restype = c.c_int
+    L.atlas_b200_cross_attention_stream_compact.argtypes = [vp, i64, i32, vp, i64, i32, i32, vp, vp, vp, i32, i32, i32, i32, i32,
+                                                            f32, vp, vp, i32, vp]
     L.atlas_b200_attention_dropout_mask.restype = c.c_int
     L.atlas_b200_attention_dropout_mask.argtypes = [vp, i64, i32, f32, u64, u64, vp]
     _lib = L
@@ -217,6 +224,9 @@ EXPORTED_SYMBOLS = [
     "atlas_b200_grad_stats",
     "atlas_b200_clamp_inf_fp16",
     "atlas_b200_cross_attention_stream",
+    "atlas_b200_compact_live_tiles",
+    "atlas_b200_linear_dynm",
+    "atlas_b200_cross_attention_stream_compact",
 ]
 
 

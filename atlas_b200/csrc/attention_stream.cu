@@ -36,6 +36,8 @@ struct Params {
     const uint8_t* tile_live;  // [B, ceil(Lk / 64)] or nullptr: 0 = every key of the 64-key tile is masked out (its
                                // probabilities are exactly 0 in fp32: exp(-10000 + s - max) underflows) -> neither loaded nor
                                // computed.  FiD passages are padded to text_maxlength: ~45 % of the keys at BASELINE configs[3]
+    const int32_t* tile_row;   // [B, Lk / 64] or nullptr: kv holds only the LIVE 64-key tiles, compacted; tile t of batch b
+                               // starts at row 64 * tile_row[b * (Lk / 64) + t] of kv (atlas_b200_compact_live_tiles)
     float* o_partial;          // [(B * chunks + c) * Lq + i, H * 64] fp32, un-normalised
     float* ml_partial;         // [(B * chunks + c) * Lq + i, H, 2]: (row max, natural log units; row sum)
     int H, Lq, Lk, chunk;
@@ -124,8 +126,14 @@ cross_stream_kernel(const Params p) {
 
     auto prefetch = [&](int ord, int buf) {
         const int j0 = j_begin + tile_at(ord) * BN;
-        load_tile_async(smem_a + (1 + buf) * TILE_BYTES, p.kv, p.ldkv, p.k_col0 + h * D, krow_base, j0, j_end);
-        load_tile_async(smem_a + (3 + buf) * TILE_BYTES, p.kv, p.ldkv, p.v_col0 + h * D, krow_base, j0, j_end);
+        if (p.tile_row != nullptr) {      // compacted K | V: whole 64-row tiles, addressed through the table
+            const int64_t r0 = static_cast<int64_t>(__ldg(p.tile_row + static_cast<int64_t>(b) * (p.Lk / BN) + j0 / BN)) * BN;
+            load_tile_async(smem_a + (1 + buf) * TILE_BYTES, p.kv, p.ldkv, p.k_col0 + h * D, r0, 0, BN);
+            load_tile_async(smem_a + (3 + buf) * TILE_BYTES, p.kv, p.ldkv, p.v_col0 + h * D, r0, 0, BN);
+        } else {
+            load_tile_async(smem_a + (1 + buf) * TILE_BYTES, p.kv, p.ldkv, p.k_col0 + h * D, krow_base, j0, j_end);
+            load_tile_async(smem_a + (3 + buf) * TILE_BYTES, p.kv, p.ldkv, p.v_col0 + h * D, krow_base, j0, j_end);
+        }
         if (threadIdx.x < BN) {
             const int j = j0 + static_cast<int>(threadIdx.x);
             mask_s[buf * BN + threadIdx.x] = j < j_end ? (mask_row ? __ldg(mask_row + j) * LOG2E : 0.f) : -INFINITY;
@@ -256,7 +264,18 @@ int atlas_b200_cross_attention_stream(const void* q, int64_t ldq, int32_t q_col0
                                       int32_t v_col0, const float* add_mask, const uint8_t* tile_live, int32_t B, int32_t H,
                                       int32_t Lq, int32_t Lk, int32_t chunk, float scale, float* o_partial, float* ml_partial,
                                       int32_t is_bf16, void* stream) {
+    return atlas_b200_cross_attention_stream_compact(q, ldq, q_col0, kv, ldkv, k_col0, v_col0, add_mask, tile_live, nullptr, B, H,
+                                                     Lq, Lk, chunk, scale, o_partial, ml_partial, is_bf16, stream);
+}
+
+int atlas_b200_cross_attention_stream_compact(const void* q, int64_t ldq, int32_t q_col0, const void* kv, int64_t ldkv,
+                                              int32_t k_col0, int32_t v_col0, const float* add_mask, const uint8_t* tile_live,
+                                              const int32_t* tile_row, int32_t B, int32_t H, int32_t Lq, int32_t Lk,
+                                              int32_t chunk, float scale, float* o_partial, float* ml_partial, int32_t is_bf16,
+                                              void* stream) {
     using namespace xs;
+    AB_REQUIRE(tile_row == nullptr || (tile_live != nullptr && Lk % BN == 0),
+               "cross_attention_stream: compacted K | V needs the live-tile flags and Lk %% 64 == 0");
     AB_REQUIRE(B >= 0 && H > 0 && Lq > 0 && Lq <= BQ && Lk > 0 && chunk > 0 && chunk % BN == 0 && chunk <= 64 * BN,
                "cross_attention_stream: need Lq <= %d and a chunk that is a multiple of %d, <= %d (Lq=%d chunk=%d)", BQ, BN,
                64 * BN, Lq, chunk);
@@ -273,6 +292,7 @@ int atlas_b200_cross_attention_stream(const void* q, int64_t ldq, int32_t q_col0
     p.q_col0 = q_col0, p.k_col0 = k_col0, p.v_col0 = v_col0;
     p.add_mask = add_mask;
     p.tile_live = tile_live;
+    p.tile_row = tile_row;
     p.o_partial = o_partial, p.ml_partial = ml_partial;
     p.H = H, p.Lq = Lq, p.Lk = Lk, p.chunk = chunk;
     p.scale = scale;

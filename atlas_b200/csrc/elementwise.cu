@@ -294,9 +294,78 @@ inf_clamp_kernel(uint16_t* __restrict__ x, int64_t ld, int64_t M, int N, const i
     }
 }
 
+// ---- compaction of the live 64-row tiles of a [rows, d] matrix (FiD decoder: only the encoder positions whose 64-key block holds a
+// live key are ever read by the cross-attention, so only they get a K | V projection) --------------------------------------
+// scan: tile_off[t] = number of live tiles before t (-1 for a dead tile), *count_rows = 64 x (number of live tiles)
+__global__ void __launch_bounds__(1024)
+live_tile_scan_kernel(const uint8_t* __restrict__ live, int n_tiles, int32_t* __restrict__ tile_off,
+                      int32_t* __restrict__ count_rows) {
+    __shared__ int s_warp[32];
+    __shared__ int s_base;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int t0 = 0; t0 < n_tiles; t0 += 1024) {
+        const int t = t0 + static_cast<int>(threadIdx.x);
+        const int f = (t < n_tiles && live[t] != 0) ? 1 : 0;
+        int x = f;                                           // inclusive scan inside the warp
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, x, o);
+            if (static_cast<int>(threadIdx.x & 31u) >= o) x += y;
+        }
+        if ((threadIdx.x & 31u) == 31u) s_warp[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int w = s_warp[threadIdx.x];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, w, o);
+                if (static_cast<int>(threadIdx.x) >= o) w += y;
+            }
+            s_warp[threadIdx.x] = w;                         // inclusive prefix over the warps
+        }
+        __syncthreads();
+        const int before = s_base + (threadIdx.x >= 32 ? s_warp[(threadIdx.x >> 5) - 1] : 0) + x - f;
+        if (t < n_tiles) tile_off[t] = f ? before : -1;
+        __syncthreads();
+        if (threadIdx.x == 0) s_base += s_warp[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *count_rows = s_base * 64;
+}
+
+// copy: block t moves the 64 rows of live tile t to rows [64 tile_off[t], +64) of dst (16-byte vectors)
+__global__ void __launch_bounds__(256)
+live_tile_copy_kernel(const uint16_t* __restrict__ src, int64_t lds, const int32_t* __restrict__ tile_off,
+                      uint16_t* __restrict__ dst, int64_t ldd, int d) {
+    const int t = blockIdx.x;
+    const int off = tile_off[t];
+    if (off < 0) return;
+    const int vec_per_row = d / 8;
+    for (int v = threadIdx.x; v < 64 * vec_per_row; v += 256) {
+        const int r = v / vec_per_row, c = (v % vec_per_row) * 8;
+        *reinterpret_cast<uint4*>(dst + (static_cast<int64_t>(off) * 64 + r) * ldd + c) =
+            __ldg(reinterpret_cast<const uint4*>(src + (static_cast<int64_t>(t) * 64 + r) * lds + c));
+    }
+}
+
 }  // namespace ew
 
 extern "C" {
+
+int atlas_b200_compact_live_tiles(const void* src, int64_t lds, const uint8_t* tile_live, int32_t n_tiles, int32_t d, void* dst,
+                                  int64_t ldd, int32_t* tile_off, int32_t* count_rows, void* stream) {
+    AB_REQUIRE(n_tiles >= 0 && d > 0 && d % 8 == 0 && lds % 8 == 0 && ldd % 8 == 0 && tile_off != nullptr && count_rows != nullptr,
+               "compact_live_tiles: d and the strides must be multiples of 8");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    ew::live_tile_scan_kernel<<<1, 1024, 0, s>>>(tile_live, n_tiles, tile_off, count_rows);
+    if (n_tiles > 0)
+        ew::live_tile_copy_kernel<<<n_tiles, 256, 0, s>>>(static_cast<const uint16_t*>(src), lds, tile_off,
+                                                          static_cast<uint16_t*>(dst), ldd, d);
+    abh::count_launch(2);
+    AB_CUDA_CHECK(cudaGetLastError());
+    return ATLAS_B200_OK;
+}
 
 int atlas_b200_clamp_inf_fp16(void* x, int64_t ld, int64_t M, int32_t N, int32_t* flag, float* row_ss, void* stream) {
     AB_REQUIRE(M >= 0 && N > 0 && N % 8 == 0 && ld % 8 == 0 && flag != nullptr, "clamp_inf_fp16: N and ld must be multiples of 8");

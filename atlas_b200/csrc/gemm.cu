@@ -82,6 +82,8 @@ struct Params {
     float* C32;
     int l2_prefetch;      // producer prefetches the next work item's A rows into L2 (ATLAS_B200_GEMM_PREFETCH=0: off)
     int tma_store;        // 16-bit C leaves through shared memory + TMA stores (BLOCK_N = 256 kernels; tmap_c is valid)
+    const int32_t* m_dev; // optional: the number of valid rows lives in device memory (<= M): only ceil(*m_dev / tile) row blocks
+                          // are computed (compacted activations under a CUDA graph: the launch shape stays static)
 };
 
 template <bool kBF16>
@@ -173,7 +175,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const int num_groups = static_cast<int>(gridDim.x) / CLUSTER;
     constexpr int PAIR_M = BLOCK_M * C::CTAS;                      // rows of one (pair) tile
     constexpr int TILE_M = PAIR_M * (kQuad ? 2 : 1);               // rows one scheduling group covers per work item
-    const int num_m = (p.M + TILE_M - 1) / TILE_M;
+    const int m_rows = p.m_dev != nullptr ? min(p.M, max(__ldg(p.m_dev), 0)) : p.M;     // identical in every role and CTA
+    const int num_m = (m_rows + TILE_M - 1) / TILE_M;
     const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
     const int num_tiles = num_m * num_n * p.splits;     // work items: (tile, split), split fastest
     const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
@@ -694,11 +697,24 @@ splitk_reduce_kernel(const float* __restrict__ part, uint16_t* __restrict__ out,
 
 }  // namespace gemm
 
+// device-side row count of the NEXT atlas_b200_linear_ex call of this thread (atlas_b200_linear_dynm sets it)
+static thread_local const int32_t* g_next_m_dev = nullptr;
+
 extern "C" {
 
 int atlas_b200_linear_ex(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, const void* residual,
                          int64_t ldr, void* C, int64_t ldc, int32_t M, int32_t N, int32_t K, int32_t epilogue,
                          int32_t is_bf16, const float* row_ss, float* out_ss, float rs_eps, void* stream);
+
+int atlas_b200_linear_dynm(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int32_t M_max, int32_t N,
+                           int32_t K, const int32_t* m_dev, int32_t is_bf16, void* stream) {
+    AB_REQUIRE(m_dev != nullptr, "linear_dynm: m_dev is required");
+    g_next_m_dev = m_dev;
+    const int rc = atlas_b200_linear_ex(A, lda, W, ldw, nullptr, nullptr, 0, C, ldc, M_max, N, K, gemm::EPI_NONE, is_bf16, nullptr,
+                                        nullptr, 0.f, stream);
+    g_next_m_dev = nullptr;
+    return rc;
+}
 
 int atlas_b200_linear(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, const void* residual,
                       int64_t ldr, void* C, int64_t ldc, int32_t M, int32_t N, int32_t K, int32_t epilogue,
@@ -726,6 +742,8 @@ int atlas_b200_linear_ex(const void* A, int64_t lda, const void* W, int64_t ldw,
     p.C32 = nullptr;
     static const int pf_on = (getenv("ATLAS_B200_GEMM_PREFETCH") != nullptr && getenv("ATLAS_B200_GEMM_PREFETCH")[0] == '0') ? 0 : 1;
     p.l2_prefetch = pf_on;
+    p.m_dev = g_next_m_dev;
+    g_next_m_dev = nullptr;
     p.row_ss = row_ss;
     p.out_ss = out_ss;
     p.rs_eps = rs_eps;
@@ -817,6 +835,7 @@ int atlas_b200_linear_wgrad(const void* dY, int64_t lddy, const void* X, int64_t
     }
     Params p;
     p.l2_prefetch = 0;
+    p.m_dev = nullptr;
     p.row_ss = nullptr;
     p.out_ss = nullptr;
     p.rs_eps = 0.f;

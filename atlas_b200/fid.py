@@ -441,17 +441,37 @@ class FiD(nn.Module):
             next(s for s in range(min(512, Lk), 0, -1) if Lk % s == 0)
         if split < 64 and Lk > 512:
             raise AtlasB200Error(f"n_context*text_maxlength = {Lk} has no divisor in [64, 512] for the split-KV kernel")
-        if cross_kv is None:
-            cross_kv = self.cross_kv(enc)
-        h = W["shared.weight"][decoder_input_ids.reshape(-1)]
-        bias = bias_by_delta(W["decoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight"], T, T, False,
-                             c.relative_attention_num_buckets)
         # invert_attention_mask (4.18): -1e4 for fp16, -1e9 otherwise (src/modeling_t5.py:950)
         neg = -1e4 if dt == torch.float16 else -1e9
         cross_mask = (1.0 - enc_mask.reshape(B, Lk).to(torch.float32)) * neg
         cross_live = ops.key_block_live(cross_mask)           # padded 64-key tiles of the encoder output: skipped, once
-        qkv = torch.empty((B * T, 3 * H * 64), dtype=dt, device=h.device)
         capture = getattr(self, "_capture", False)
+        # Only the encoder positions inside a live 64-key tile are ever read by the cross-attention: project K | V for those
+        # rows only (compacted, device-side row count: the shapes stay static for the CUDA graph).  At BASELINE configs[3]
+        # the 12 K | V projections are 14 % of the step's FLOPs and ~36 % of their rows are padding-only tiles.
+        compact = (cross_kv is None and cross_live is not None and not capture and ops._XKV_COMPACT and ops._XATTN_STREAM
+                   and T <= 64 and Lk % 64 == 0 and Lk >= 1024)
+        xkv = None
+        if compact:
+            flat = enc.reshape(-1, d)
+            if flat.dtype != dt:
+                flat = flat.to(dt)
+            enc_live, tile_off, n_live_rows = ops.compact_live_tiles(flat, cross_live)
+            xkv = [ops.linear_dynm(enc_live, G[f"decoder.block.{i}.layer.1.EncDecAttention.kv"], n_live_rows)
+                   for i in range(c.num_decoder_layers)]
+        elif cross_kv is None:
+            cross_kv = self.cross_kv(enc)
+        h = W["shared.weight"][decoder_input_ids.reshape(-1)]
+        bias = bias_by_delta(W["decoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight"], T, T, False,
+                             c.relative_attention_num_buckets)
+        qkv = torch.empty((B * T, 3 * H * 64), dtype=dt, device=h.device)
+
+        def cross(q, i):
+            if xkv is not None:
+                return ops.cross_attention_stream_compact(q, xkv[i], cross_live, tile_off, B, H, T, Lk, cross_mask, scale=1.0)
+            return ops.cross_attention_split(q, 0, cross_kv[i], 0, H * 64, B, H, T, Lk, add_mask=cross_mask, scale=1.0,
+                                             split=split, tile_live=cross_live)
+
         if self.fuse_norm and not capture:
             # RMSNorm fused around the decoder GEMMs exactly like the encoder's (see encode): the three residual GEMMs of a
             # block emit each row's sum of squares, the consuming projections read the un-normalised rows with the norm weight
@@ -473,8 +493,7 @@ class FiD(nn.Module):
                 ops.clamp_inf_(h, row_ss=ss[3 * i])
                 p = f"decoder.block.{i}.layer.1."
                 q = ops.linear(h, G[p + "EncDecAttention.q.weight_n"], row_ss=ss[3 * i], rs_eps=eps)
-                ctx = ops.cross_attention_split(q, 0, cross_kv[i], 0, H * 64, B, H, T, Lk, add_mask=cross_mask,
-                                                scale=1.0, split=split, tile_live=cross_live)
+                ctx = cross(q, i)
                 h = ops.linear(ctx, W[p + "EncDecAttention.o.weight"], None, residual=h, epilogue=ops.EPI_RESIDUAL,
                                out_ss=ss[3 * i + 1])
                 ops.clamp_inf_(h, row_ss=ss[3 * i + 1])
@@ -502,8 +521,7 @@ class FiD(nn.Module):
                                                      scale=1.0, split=split, return_lse=True, tile_live=cross_live)
                 self._record_xattn(q, cross_kv[i], B, H, T, Lk, lse, cross_mask, layer=i)
             else:
-                ctx = ops.cross_attention_split(q, 0, cross_kv[i], 0, H * 64, B, H, T, Lk, add_mask=cross_mask,
-                                                scale=1.0, split=split, tile_live=cross_live)
+                ctx = cross(q, i)
             h = ops.clamp_inf_(ops.linear(ctx, W[p + "EncDecAttention.o.weight"], None, residual=h,
                                           epilogue=ops.EPI_RESIDUAL))
             h = self._ff(W, G, f"decoder.block.{i}.layer.2.", h, c.layer_norm_epsilon)

@@ -298,6 +298,59 @@ def key_block_live(add_mask, block=64):
     return live.to(torch.uint8).contiguous()
 
 
+_XKV_COMPACT = os.environ.get("ATLAS_B200_XKV_COMPACT", "1") != "0"        # A/B switch of the compacted cross K | V
+
+
+def compact_live_tiles(x, tile_live):
+    """x [n_tiles * 64, d] 16-bit, tile_live uint8 [n_tiles] (flattened key_block_live) -> (x_live: the rows of the live 64-row
+    tiles packed to the front of a buffer of the same shape, tile_off int32 [n_tiles]: position of every live tile in it (-1 =
+    dead), count_rows int32 [1] on the device = 64 x #live).  Static shapes, no host synchronisation."""
+    require_cuda(x, "x")
+    x2 = _rows2d(x)
+    flags = tile_live.reshape(-1)
+    n_tiles = flags.numel()
+    if x2.shape[0] != n_tiles * 64:
+        raise AtlasB200Error(f"compact_live_tiles: {x2.shape[0]} rows for {n_tiles} tiles of 64")
+    dst = torch.empty_like(x2)
+    tile_off = torch.empty(n_tiles, dtype=torch.int32, device=x.device)
+    count = torch.empty(1, dtype=torch.int32, device=x.device)
+    check(lib().atlas_b200_compact_live_tiles(_ptr(x2), x2.stride(0), _ptr(flags), n_tiles, x2.shape[1], _ptr(dst),
+                                              dst.stride(0), _ptr(tile_off), _ptr(count), current_stream_ptr()))
+    return dst, tile_off, count
+
+
+def linear_dynm(x, weight, m_dev, out=None):
+    """y[m] = x[m] @ weight.T for m < *m_dev (device int32): row blocks past the device-side count are skipped."""
+    require_cuda(x, "x")
+    M, K = x.shape
+    N = weight.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=x.dtype, device=x.device)
+    check(lib().atlas_b200_linear_dynm(_ptr(x), x.stride(0), _ptr(weight), weight.stride(0), _ptr(out), out.stride(0), M, N, K,
+                                       _ptr(m_dev), _bf(x), current_stream_ptr()))
+    return out
+
+
+def cross_attention_stream_compact(q, kv_live, tile_live, tile_off, B, H, Lq, Lk_total, add_mask, scale=1.0, return_lse=False):
+    """`cross_attention_split` on the stream kernel with K | V given as the compacted live tiles (`compact_live_tiles` of the
+    encoder output, projected by `linear_dynm`)."""
+    require_cuda(q, "q")
+    am = add_mask.float().contiguous()
+    chunk = _XATTN_CHUNK
+    chunks = (Lk_total + chunk - 1) // chunk
+    o_part = torch.empty((B * chunks * Lq, H * 64), dtype=torch.float32, device=q.device)
+    ml = torch.empty((B * chunks * Lq, H, 2), dtype=torch.float32, device=q.device)
+    check(lib().atlas_b200_cross_attention_stream_compact(_ptr(q), q.stride(0), 0, _ptr(kv_live), kv_live.stride(0), 0, H * 64,
+                                                          _ptr(am), _ptr(tile_live), _ptr(tile_off), B, H, Lq, Lk_total,
+                                                          chunk, float(scale), _ptr(o_part), _ptr(ml), _bf(q),
+                                                          current_stream_ptr()))
+    out = torch.empty((B * Lq, H * 64), dtype=q.dtype, device=q.device)
+    lse = torch.empty((B, H, Lq), dtype=torch.float32, device=q.device) if return_lse else None
+    check(lib().atlas_b200_attention_combine_ex(_ptr(o_part), _ptr(ml), B, chunks, Lq, H, _ptr(out), out.stride(0),
+                                                _ptr(lse) if lse is not None else None, _bf(q), current_stream_ptr()))
+    return (out, lse) if return_lse else out
+
+
 _XATTN_STREAM = os.environ.get("ATLAS_B200_XATTN_STREAM", "1") != "0"      # A/B switch of the stream kernel
 _XATTN_CHUNK = int(os.environ.get("ATLAS_B200_XATTN_CHUNK", "1024"))        # keys per CTA (multiple of 64)
 

@@ -410,6 +410,25 @@ int atlas_b200_cross_attention_stream(const void* q, int64_t ldq, int32_t q_col0
                                       int32_t Lq, int32_t Lk, int32_t chunk, float scale, float* o_partial, float* ml_partial,
                                       int32_t is_bf16, void* stream);
 
+/* Compacted cross-attention K | V (FiD decoder, inference forward): only the encoder positions whose 64-key block holds a live
+ * key are ever read by the cross-attention (atlas_b200_cross_attention_stream skips the others), so only they get a K | V
+ * projection.  Everything keeps STATIC launch shapes (CUDA graphs): the live-row count lives in device memory.
+ *   atlas_b200_compact_live_tiles: tile_off[t] = index of live 64-row tile t among the live tiles (-1 = dead), *count_rows =
+ *     64 x #live; the rows of the live tiles of src [n_tiles * 64, d] are copied to dst rows [64 tile_off[t], +64).
+ *   atlas_b200_linear_dynm: C[m, :] = A[m, :] . W^T for m < min(M_max, *m_dev) (plain epilogue): row blocks past *m_dev are
+ *     not computed; rows of the last computed block past *m_dev hold unspecified values.
+ *   atlas_b200_cross_attention_stream_compact: as atlas_b200_cross_attention_stream with kv holding only the live tiles:
+ *     tile t of batch b starts at row 64 * tile_row[b * (Lk / 64) + t] (tile_row = the tile_off table above). */
+int atlas_b200_compact_live_tiles(const void* src, int64_t lds, const uint8_t* tile_live, int32_t n_tiles, int32_t d, void* dst,
+                                  int64_t ldd, int32_t* tile_off, int32_t* count_rows, void* stream);
+int atlas_b200_linear_dynm(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int32_t M_max, int32_t N,
+                           int32_t K, const int32_t* m_dev, int32_t is_bf16, void* stream);
+int atlas_b200_cross_attention_stream_compact(const void* q, int64_t ldq, int32_t q_col0, const void* kv, int64_t ldkv,
+                                              int32_t k_col0, int32_t v_col0, const float* add_mask, const uint8_t* tile_live,
+                                              const int32_t* tile_row, int32_t B, int32_t H, int32_t Lq, int32_t Lk,
+                                              int32_t chunk, float scale, float* o_partial, float* ml_partial, int32_t is_bf16,
+                                              void* stream);
+
 /* Measurement hook for bench.py's roofline: while enabled, every launch of ONE kind of kernel is bracketed
  * with CUDA events on its launching stream:
  *   kind 1  the bank sweep of atlas_b200_mips_topk (work = algorithmic bytes swept)

@@ -323,3 +323,36 @@ def test_masked_key_blocks_are_skipped_without_changing_the_result(dev, dtype, S
     # a fully masked segment keeps every block (uniform-over-masked-keys softmax like the reference)
     allm = torch.full((2, L), -10000.0, device=dev)
     assert bool(ops.key_block_live(allm).all())
+
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_compacted_cross_kv_path_is_identical(dev, dtype):
+    """Cross K | V projected only for the encoder positions inside live 64-key tiles (ops.compact_live_tiles + linear_dynm with
+    a device-side row count + the stream kernel reading the compacted rows) against the dense projection + the same kernel:
+    bit-identical attention output; the compaction tables against a torch restatement."""
+    from atlas_b200 import ops
+
+    g = torch.Generator().manual_seed(5)
+    B, H, T, n, Lp, d = 3, 12, 32, 5, 384, 768
+    Lk = n * Lp
+    enc = (torch.randn(B * Lk, d, generator=g) * 0.5).to(dtype).to(dev)
+    wkv = (torch.randn(2 * H * 64, d, generator=g) / 27.7).to(dtype).to(dev)
+    q = (torch.randn(B * T, H * 64, generator=g) * 0.5).to(dtype).to(dev)
+    lens = torch.randint(20, Lp + 1, (B, n), generator=g)
+    lens[0, 0], lens[1, 2] = Lp, 1
+    valid = torch.arange(Lp)[None, None, :] < lens[..., None]
+    mask = ((~valid).reshape(B, Lk).float() * -1e9).to(dev)
+    live = ops.key_block_live(mask)
+    enc_live, tile_off, count = ops.compact_live_tiles(enc, live)
+    flags = live.reshape(-1).bool().cpu()
+    want_off = torch.where(flags, torch.cumsum(flags.int(), 0) - 1, torch.full_like(flags.int(), -1))
+    assert torch.equal(tile_off.cpu(), want_off.int()) and int(count) == 64 * int(flags.sum())
+    rows = enc.view(-1, 64, d)[flags.to(dev)].reshape(-1, d)
+    assert torch.equal(enc_live[: rows.shape[0]], rows)
+    kv_live = ops.linear_dynm(enc_live, wkv, count)
+    kv_dense = ops.linear(enc, wkv)
+    assert torch.equal(kv_live[: rows.shape[0]].view(-1, 64, 2 * H * 64), kv_dense.view(-1, 64, 2 * H * 64)[flags.to(dev)])
+    a = ops.cross_attention_stream_compact(q, kv_live, live, tile_off, B, H, T, Lk, mask, scale=1.0)
+    b = ops.cross_attention_split(q, 0, kv_dense, 0, H * 64, B, H, T, Lk, add_mask=mask, scale=1.0, split=384, tile_live=live)
+    assert torch.equal(a, b)
