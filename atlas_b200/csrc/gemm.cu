@@ -669,7 +669,8 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p_
     } else {
         gemm_kernel<kBF16, BLOCK_N, kPair, kTN, kQuad><<<grid, THREADS, C::SMEM_BYTES, s>>>(ta, tb, tc, p);
     }
-    abh::prof_end(s, abh::PROF_LINEAR, 2.0 * p.M * static_cast<double>(p.N) * p.K);
+    if (p.m_dev != nullptr) abh::prof_end_dyn(s, abh::PROF_LINEAR, 2.0 * static_cast<double>(p.N) * p.K, p.m_dev, p.M);
+    else abh::prof_end(s, abh::PROF_LINEAR, 2.0 * p.M * static_cast<double>(p.N) * p.K);
     abh::count_launch();
     AB_CUDA_CHECK(cudaGetLastError());
     return ATLAS_B200_OK;

@@ -99,6 +99,12 @@ static int g_prof_on = 0;   // 0 off, otherwise the ProfKind being bracketed
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
 static size_t g_prof_used = 0;
 static double g_prof_work = 0;
+struct DynWork {                 // launches whose row count lives in device memory: resolved when the work is read
+    double work_per_row;
+    const int32_t* m_dev;
+    int32_t m_max;
+};
+static std::vector<DynWork> g_prof_dyn;
 
 void prof_begin(cudaStream_t s, int kind) {
     if (g_prof_on != kind) return;
@@ -117,6 +123,13 @@ void prof_end(cudaStream_t s, int kind, double work) {
     g_prof_work += work;
 }
 
+void prof_end_dyn(cudaStream_t s, int kind, double work_per_row, const int32_t* m_dev, int32_t m_max) {
+    if (g_prof_on != kind || g_prof_used >= g_prof_events.size()) return;
+    cudaEventRecord(g_prof_events[g_prof_used].second, s);
+    ++g_prof_used;
+    g_prof_dyn.push_back({work_per_row, m_dev, m_max});
+}
+
 }  // namespace abh
 
 extern "C" {
@@ -125,9 +138,22 @@ void atlas_b200_profile_enable(int32_t kind) {
     abh::g_prof_on = kind;
     abh::g_prof_used = 0;
     abh::g_prof_work = 0;
+    abh::g_prof_dyn.clear();
 }
 
-double atlas_b200_profile_work(void) { return abh::g_prof_work; }
+// the work of the bracketed launches; launches with a device-side row count are counted with the rows they really computed
+// (read back here: call after the stream has been synchronised)
+double atlas_b200_profile_work(void) {
+    double w = abh::g_prof_work;
+    for (const auto& d : abh::g_prof_dyn) {
+        int32_t m = 0;
+        if (cudaMemcpy(&m, d.m_dev, sizeof(m), cudaMemcpyDeviceToHost) != cudaSuccess) m = d.m_max;
+        if (m > d.m_max) m = d.m_max;
+        if (m < 0) m = 0;
+        w += d.work_per_row * m;
+    }
+    return w;
+}
 
 int atlas_b200_profile_collect(double* total_ms, int32_t* launches) {
     double tot = 0;

@@ -55,6 +55,8 @@ int num_sms();
 enum ProfKind { PROF_SCAN = 1, PROF_LINEAR = 2, PROF_ATTENTION = 3, PROF_ATTENTION_BWD = 4, PROF_DECODE_CROSS = 5 };
 void prof_begin(cudaStream_t s, int kind);
 void prof_end(cudaStream_t s, int kind, double work);   // work = algorithmic bytes (scan) or FLOPs of this launch
+// ... of a launch whose row count lives in device memory: work = work_per_row * min(m_max, *m_dev), resolved when read
+void prof_end_dyn(cudaStream_t s, int kind, double work_per_row, const int32_t* m_dev, int32_t m_max);
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
