@@ -133,6 +133,9 @@ def lib():
     L.atlas_b200_cross_entropy_bwd.argtypes = [vp, i64, vp, vp, vp, vp, i64, i32, i32, i32, vp]
     L.atlas_b200_decode_cross_attention.restype = c.c_int
     L.atlas_b200_decode_cross_attention.argtypes = [vp, i64, vp, i64, i32, i32, vp, i32, i32, i32, i32, f32, vp, vp, i32, vp]
+    L.atlas_b200_decode_cross_attention_live.restype = c.c_int
+    L.atlas_b200_decode_cross_attention_live.argtypes = [vp, i64, vp, i64, i32, i32, vp, vp, i32, i32, i32, i32, f32, vp, vp, i32,
+                                                         vp]
     L.atlas_b200_decode_self_attention.restype = c.c_int
     L.atlas_b200_decode_self_attention.argtypes = [vp, i64, vp, i32, vp, vp, f32, vp, i64, i32, i32, i32, vp]
     L.atlas_b200_decode_argmax.restype = c.c_int
@@ -224,6 +227,7 @@ EXPORTED_SYMBOLS = [
     "atlas_b200_grad_stats",
     "atlas_b200_clamp_inf_fp16",
     "atlas_b200_cross_attention_stream",
+    "atlas_b200_decode_cross_attention_live",
     "atlas_b200_compact_live_tiles",
     "atlas_b200_linear_dynm",
     "atlas_b200_cross_attention_stream_compact",

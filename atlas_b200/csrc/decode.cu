@@ -43,8 +43,9 @@ __device__ __forceinline__ void unpack8(const uint4& w, float (&f)[8]) {
 template <bool kBF16>
 __global__ void __launch_bounds__(CROSS_THREADS)
 decode_cross_attention_kernel(const uint16_t* __restrict__ q, int64_t ldq, const uint16_t* __restrict__ kv, int64_t ldkv,
-                              int k_col0, int v_col0, const float* __restrict__ add_mask, int Lk, int chunk, float scale,
-                              float* __restrict__ o_partial, float* __restrict__ ml_partial, int H) {
+                              int k_col0, int v_col0, const float* __restrict__ add_mask, const uint8_t* __restrict__ tile_live,
+                              int Lk, int chunk, float scale, float* __restrict__ o_partial, float* __restrict__ ml_partial,
+                              int H) {
     const int c = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int chunks = gridDim.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -63,12 +64,16 @@ decode_cross_attention_kernel(const uint16_t* __restrict__ q, int64_t ldq, const
     const int j_begin = c * chunk, j_end = min(Lk, (c + 1) * chunk);
     const uint16_t* base = kv + (static_cast<int64_t>(b) * Lk) * ldkv + h * D + seg * 8;
     const float* mrow = add_mask ? add_mask + static_cast<int64_t>(b) * Lk : nullptr;
+    // 64-key tiles whose keys are all masked out weigh exactly 0 in the softmax (see atlas_b200_cross_attention_stream): skipped.
+    // A warp's 16-key group never straddles a tile (chunk and the group offsets are multiples of 16, tiles of 64).
+    const uint8_t* live_row = tile_live ? tile_live + static_cast<int64_t>(b) * ((Lk + 63) / 64) : nullptr;
 
     float m = -INFINITY, l = 0.f, acc[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = 0.f;
     constexpr int UNROLL = 4;                                        // 4 x (K row + V row) 16-byte loads in flight per lane
     for (int j0 = j_begin + warp * 4 * UNROLL; j0 < j_end; j0 += (CROSS_THREADS / 32) * 4 * UNROLL) {
+        if (live_row != nullptr && __ldg(live_row + (j0 >> 6)) == 0) continue;
         uint4 kw[UNROLL], vw[UNROLL];
         float madd[UNROLL];
 #pragma unroll
@@ -242,6 +247,14 @@ int atlas_b200_decode_cross_attention(const void* q, int64_t ldq, const void* kv
                                       int32_t v_col0, const float* add_mask, int32_t B, int32_t H, int32_t Lk,
                                       int32_t chunk, float scale, float* o_partial, float* ml_partial, int32_t is_bf16,
                                       void* stream) {
+    return atlas_b200_decode_cross_attention_live(q, ldq, kv, ldkv, k_col0, v_col0, add_mask, nullptr, B, H, Lk, chunk, scale,
+                                                  o_partial, ml_partial, is_bf16, stream);
+}
+
+int atlas_b200_decode_cross_attention_live(const void* q, int64_t ldq, const void* kv, int64_t ldkv, int32_t k_col0,
+                                           int32_t v_col0, const float* add_mask, const uint8_t* tile_live, int32_t B,
+                                           int32_t H, int32_t Lk, int32_t chunk, float scale, float* o_partial,
+                                           float* ml_partial, int32_t is_bf16, void* stream) {
     AB_REQUIRE(B >= 0 && H > 0 && Lk > 0 && chunk > 0 && chunk % 16 == 0, "decode_cross_attention: bad shape");
     AB_REQUIRE(ldq % 8 == 0 && ldkv % 8 == 0 && k_col0 % 8 == 0 && v_col0 % 8 == 0,
                "decode_cross_attention: strides and column offsets must be multiples of 8 elements");
@@ -253,12 +266,12 @@ int atlas_b200_decode_cross_attention(const void* q, int64_t ldq, const void* kv
     abh::prof_begin(s, abh::PROF_DECODE_CROSS);
     if (is_bf16)
         dec::decode_cross_attention_kernel<true><<<grid, dec::CROSS_THREADS, 0, s>>>(
-            static_cast<const uint16_t*>(q), ldq, static_cast<const uint16_t*>(kv), ldkv, k_col0, v_col0, add_mask, Lk, chunk,
-            scale, o_partial, ml_partial, H);
+            static_cast<const uint16_t*>(q), ldq, static_cast<const uint16_t*>(kv), ldkv, k_col0, v_col0, add_mask, tile_live, Lk,
+            chunk, scale, o_partial, ml_partial, H);
     else
         dec::decode_cross_attention_kernel<false><<<grid, dec::CROSS_THREADS, 0, s>>>(
-            static_cast<const uint16_t*>(q), ldq, static_cast<const uint16_t*>(kv), ldkv, k_col0, v_col0, add_mask, Lk, chunk,
-            scale, o_partial, ml_partial, H);
+            static_cast<const uint16_t*>(q), ldq, static_cast<const uint16_t*>(kv), ldkv, k_col0, v_col0, add_mask, tile_live, Lk,
+            chunk, scale, o_partial, ml_partial, H);
     abh::prof_end(s, abh::PROF_DECODE_CROSS, 4.0 * B * H * static_cast<double>(Lk) * dec::D);   // = K | V bytes read
     abh::count_launch();
     AB_CUDA_CHECK(cudaGetLastError());

@@ -757,6 +757,7 @@ class FiD(nn.Module):
             self.t_dev = torch.zeros(1, dtype=torch.int32, device=dev)
             self.logits = None
             self.graph = None
+            self.cross_live = None
 
     @torch.no_grad()
     def _decode_step_logits(self, st):
@@ -778,7 +779,7 @@ class FiD(nn.Module):
             n = ops.layernorm(h, W[p + "layer_norm.weight"], None, eps, kind=1)
             q = ops.linear(n, W[p + "EncDecAttention.q.weight"])
             ctx = ops.decode_cross_attention(q, st.cross_kv[i], B, H, Lk, add_mask=st.cross_mask, scale=1.0,
-                                             chunk=st.chunk)
+                                             chunk=st.chunk, tile_live=st.cross_live)
             h = ops.clamp_inf_(ops.linear(ctx, W[p + "EncDecAttention.o.weight"], None, residual=h,
                                           epilogue=ops.EPI_RESIDUAL))
             h = self._ff(W, G, f"decoder.block.{i}.layer.2.", h, eps)
@@ -822,6 +823,12 @@ class FiD(nn.Module):
         self.cross_kv(enc, out=st.cross_kv)
         neg = -1e4 if dt == torch.float16 else -1e9                                 # invert_attention_mask (4.18)
         st.cross_mask.copy_((1.0 - attention_mask.reshape(B, Lk).to(torch.float32)) * neg)
+        live = ops.key_block_live(st.cross_mask)              # padded 64-key tiles: not read by the decode steps
+        if live is not None:
+            if st.cross_live is None:
+                st.cross_live = live                          # fixed buffer: the captured step graph reads it
+            else:
+                st.cross_live.copy_(live)
         wkey = (self._half.sets[dt]["gen"], self._half.sets[dt]["key"])
         if getattr(st, "wkey", None) != wkey:                                       # weights changed: the bias table is stale
             fresh = bias_by_delta(W["decoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight"], st.Tmax,

@@ -669,16 +669,20 @@ def decode_self_attention(qkv, cache, t_dev, H, bias_delta=None, scale=1.0, out=
     return out
 
 
-def decode_cross_attention(q, kv, B, H, Lk, add_mask=None, scale=1.0, chunk=256, out=None):
-    """q [B, H*64] against kv [B*Lk, 2*H*64] (k | v): chunked partials + the split-KV combine -> ctx [B, H*64]."""
+def decode_cross_attention(q, kv, B, H, Lk, add_mask=None, scale=1.0, chunk=256, out=None, tile_live=None):
+    """q [B, H*64] against kv [B*Lk, 2*H*64] (k | v): chunked partials + the split-KV combine -> ctx [B, H*64].
+    tile_live = key_block_live(add_mask): 64-key tiles of masked keys only are not read (identical result)."""
     require_cuda(q, "q")
+    if tile_live is not None and chunk % 64 != 0:
+        tile_live = None
     chunks = (Lk + chunk - 1) // chunk
     o_part = torch.empty((B * chunks, H * 64), dtype=torch.float32, device=q.device)
     ml = torch.empty((B * chunks, H, 2), dtype=torch.float32, device=q.device)
     am = add_mask.float().contiguous() if add_mask is not None else None
-    check(lib().atlas_b200_decode_cross_attention(_ptr(q), q.stride(0), _ptr(kv), kv.stride(0), 0, H * 64,
-                                                  _ptr(am) if am is not None else None, B, H, Lk, chunk, float(scale),
-                                                  _ptr(o_part), _ptr(ml), _bf(q), current_stream_ptr()))
+    check(lib().atlas_b200_decode_cross_attention_live(_ptr(q), q.stride(0), _ptr(kv), kv.stride(0), 0, H * 64,
+                                                       _ptr(am) if am is not None else None,
+                                                       _ptr(tile_live) if tile_live is not None else None, B, H, Lk, chunk,
+                                                       float(scale), _ptr(o_part), _ptr(ml), _bf(q), current_stream_ptr()))
     if out is None:
         out = torch.empty((B, H * 64), dtype=q.dtype, device=q.device)
     check(lib().atlas_b200_attention_combine_ex(_ptr(o_part), _ptr(ml), B, chunks, 1, H, _ptr(out), out.stride(0), None,

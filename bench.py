@@ -1028,10 +1028,15 @@ def train_leg(args, reader, dev, world, L, barrier_sync, max_over_ranks, steps=3
     ids = torch.randint(2, 32000, (tb, N_DOCS * TEXT_LEN), generator=g).to(dev)
     mask = torch.ones(tb, N_DOCS * TEXT_LEN, dtype=torch.bool, device=dev)
     labels = torch.randint(2, 32000, (tb, TARGET_LEN), generator=g).to(dev)
+    # the supplementary `padded` figure: passages of the forward step's length distribution (query + U[128, 256] passage tokens,
+    # padded to text_maxlength like src/atlas.py:261-270 pads) - the attention kernels skip all-padding key blocks
+    plen = QUERY_TOKENS + torch.randint(PASSAGE_TOKENS // 2, PASSAGE_TOKENS + 1, (tb, N_DOCS), generator=g)
+    mask_padded = (torch.arange(TEXT_LEN)[None, None, :] < plen[..., None]).reshape(tb, N_DOCS * TEXT_LEN).to(dev)
+    ids_padded = ids * mask_padded
 
-    def step():
+    def step(padded=False):
         reader.zero_grad(set_to_none=True)
-        out = reader(input_ids=ids, attention_mask=mask, labels=labels)
+        out = reader(input_ids=ids_padded if padded else ids, attention_mask=mask_padded if padded else mask, labels=labels)
         out[0].backward()
         if world > 1:
             flat = torch.cat([p.grad.reshape(-1) for p in reader.parameters() if p.grad is not None])
@@ -1062,6 +1067,16 @@ def train_leg(args, reader, dev, world, L, barrier_sync, max_over_ranks, steps=3
             shares[name] = {"ms_per_step": kms.value, "launches_per_step": kn.value,
                             "achieved_tflops": work / (kms.value * 1e-3) / 1e12 if kms.value > 0 else None,
                             "share_of_step": kms.value / ms if ms else None}
+        for _ in range(warmup):
+            loss_p = step(True)
+        barrier_sync()
+        e0.record()
+        for _ in range(steps):
+            loss_p = step(True)
+        e1.record()
+        barrier_sync()
+        ms_padded = max_over_ranks(e0.elapsed_time(e1)) / steps
+        assert bool(torch.isfinite(loss_p.float())), "non-finite training loss (padded passages)"
     finally:
         reader.zero_grad(set_to_none=True)
         reader.eval()
@@ -1071,7 +1086,13 @@ def train_leg(args, reader, dev, world, L, barrier_sync, max_over_ranks, steps=3
             "value": tokens / (ms * 1e-3), "unit": "tokens/s", "ms_per_step": ms, "steps": steps,
             "queries_per_step": tb * world, "reader_tokens_per_step": tokens,
             "gradient_allreduce": "one NCCL all-reduce of the flattened bf16 gradients" if world > 1 else "none (1 GPU)",
-            "kernels": shares}
+            "kernels": shares,
+            "mask": "every position real (no padding: the dense worst case)",
+            "padded_passages": {"value": tokens / (ms_padded * 1e-3), "unit": "tokens/s (padded positions counted)",
+                                "ms_per_step": ms_padded,
+                                "what": f"the same step on passages of the forward step's length distribution (query + "
+                                        f"U[{PASSAGE_TOKENS // 2}, {PASSAGE_TOKENS}] passage tokens padded to {TEXT_LEN}): "
+                                        "all-padding key blocks are skipped by the attention kernels, forward and backward"}}
 
 
 def mips_leg(args, index, dev, world, rank, L, barrier_sync, max_over_ranks):

@@ -169,6 +169,12 @@ int atlas_b200_decode_cross_attention(const void* q, int64_t ldq, const void* kv
                                       int32_t v_col0, const float* add_mask, int32_t B, int32_t H, int32_t Lk,
                                       int32_t chunk, float scale, float* o_partial, float* ml_partial, int32_t is_bf16,
                                       void* stream);
+/* ... with the live-tile flags of atlas_b200_cross_attention_stream (uint8 [B, ceil(Lk / 64)], NULL = all live): 64-key tiles of
+ * masked keys only are not read.  chunk must be a multiple of 64 when flags are given. */
+int atlas_b200_decode_cross_attention_live(const void* q, int64_t ldq, const void* kv, int64_t ldkv, int32_t k_col0,
+                                      int32_t v_col0, const float* add_mask, const uint8_t* tile_live, int32_t B, int32_t H, int32_t Lk,
+                                      int32_t chunk, float scale, float* o_partial, float* ml_partial, int32_t is_bf16,
+                                      void* stream);
 int atlas_b200_decode_self_attention(const void* qkv, int64_t ldqkv, void* cache, int32_t Tmax, const int32_t* t_dev,
                                      const float* bias_delta, float scale, void* out, int64_t ldo, int32_t B, int32_t H,
                                      int32_t is_bf16, void* stream);
