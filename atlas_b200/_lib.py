@@ -172,6 +172,16 @@ def lib():
                                                             f32, vp, vp, i32, vp]
     L.atlas_b200_attention_dropout_mask.restype = c.c_int
     L.atlas_b200_attention_dropout_mask.argtypes = [vp, i64, i32, f32, u64, u64, vp]
+    L.atlas_b200_segment_tile_scan.restype = c.c_int
+    L.atlas_b200_segment_tile_scan.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
+    L.atlas_b200_embed_packed_tiles.restype = c.c_int
+    L.atlas_b200_embed_packed_tiles.argtypes = [vp, vp, i64, i32, vp, i32, vp, i64, i32, vp]
+    L.atlas_b200_linear_rows.restype = c.c_int
+    L.atlas_b200_linear_rows.argtypes = [vp, i64, vp, i64, vp, vp, i64, vp, i64, i32, i32, i32, i32, i32, vp, vp, f32, vp, vp]
+    L.atlas_b200_attention_packed.restype = c.c_int
+    L.atlas_b200_attention_packed.argtypes = [vp, i64, i32, i32, i32, vp, i64, vp, vp, vp, vp, i32, i32, i32, f32, i32, vp]
+    L.atlas_b200_expand_packed_tiles.restype = c.c_int
+    L.atlas_b200_expand_packed_tiles.argtypes = [vp, i64, vp, i32, vp, i64, i32, vp]
     _lib = L
     return L
 
@@ -231,6 +241,11 @@ EXPORTED_SYMBOLS = [
     "atlas_b200_compact_live_tiles",
     "atlas_b200_linear_dynm",
     "atlas_b200_cross_attention_stream_compact",
+    "atlas_b200_segment_tile_scan",
+    "atlas_b200_embed_packed_tiles",
+    "atlas_b200_linear_rows",
+    "atlas_b200_attention_packed",
+    "atlas_b200_expand_packed_tiles",
 ]
 
 

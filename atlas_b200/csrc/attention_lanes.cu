@@ -29,6 +29,9 @@
 //     + 1 MUFU.EX2 + 1/2 FADD2 + 1/2 F2FP: 3.75 issue slots (packed f32x2 arithmetic and the 3-input max are sm_100
 //     instructions), the t values stay in registers between the two passes (setmaxnreg moves registers from the four
 //     helper warps to the twelve softmax warps).
+// Packed layout (Params::seg_tile, the padding-compacted FiD encoder): an item has 1 - 3 query tiles; tile qt of the item runs on
+// lane (rot + qt) % 3, rot = the number of tiles of the CTA's earlier items - the lanes stay evenly loaded and drift apart by up
+// to the ring's depth.  A lane without a tile in an item passes its K / V chunks (waits for the chunk, releases it).
 // Warp roles (512 threads): warp 0 = tables (all lanes) + TMA producer (lane 0); warps 1-3 = MMA issuers of lanes 0-2;
 // warps 4-7 / 8-11 / 12-15 = softmax + output of lanes 0 / 1 / 2 (thread = query row = TMEM lane).
 #include "common.cuh"
@@ -75,6 +78,10 @@ struct Params {
     const uint8_t* blk_live;    // [B, ceil(Lk / 64)] or nullptr: 0 = every key of the 64-key block is masked out (additive mask
                                 // <= -5000: softmax weight exactly 0 in fp32) -> the block is neither loaded nor computed.
                                 // FiD passages are padded to text_maxlength; a segment keeps at least one live block.
+    const int32_t* seg_tile;    // nullptr, or [B * ceil(Lk / 64)] (atlas_b200_segment_tile_scan): PACKED layout - segment b's rows
+                                // are the 64-row tiles it keeps (blk_live: a prefix of its tiles), stored back to back from row
+                                // 64 * seg_tile[b * nb] of q / k / v / out; query tiles past the kept rows do not exist.  Needs
+                                // Lq == Lk <= 384 and blk_live.
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -209,6 +216,7 @@ attention_lanes_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
     const int it_begin = static_cast<int>(static_cast<int64_t>(blockIdx.x) * n_items / gridDim.x);
     const int it_end = static_cast<int>(static_cast<int64_t>(blockIdx.x + 1) * n_items / gridDim.x);
     const bool has_bias = (p.bias_delta != nullptr) || (p.causal_value != 0.f);
+    const bool packed = p.seg_tile != nullptr;
 
     if (warp == 0 && lane == 0) {
         ab::tma_prefetch_desc(&tmap_q);
@@ -226,7 +234,8 @@ attention_lanes_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
         }
         for (int s = 0; s < RING; ++s) {
             ab::mbar_init(&kv_full[s], 1);
-            ab::mbar_init(&kv_empty[s], static_cast<uint32_t>(n_qt));   // every query tile of the item consumes the chunk once
+            // every query tile of the item consumes the chunk once; packed layout: every lane releases it once (use or pass)
+            ab::mbar_init(&kv_empty[s], static_cast<uint32_t>(packed ? LANES : n_qt));
         }
         for (int i = 0; i < 2; ++i) {
             ab::mbar_init(&tab_full[i], 32);
@@ -248,6 +257,7 @@ attention_lanes_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
             uint32_t q_ctr[LANES] = {0, 0, 0};
             int prev_h = -1;
             int item_it = 0;
+            int rot = 0;
             for (int it = it_begin; it < it_end; ++it, ++item_it) {
                 const int h = it / p.B, b = it % p.B;
                 const int buf = item_it & 1;
@@ -301,12 +311,16 @@ attention_lanes_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                     prev_h = h;
                 }
                 ab::mbar_arrive(&tab_full[buf]);
+                // rows of the item: packed layout = the segment's kept tiles, back to back
+                const int item_qt = packed ? (__popc(live) + 1) / 2 : n_qt;
+                const int q_row0 = packed ? 64 * __ldg(p.seg_tile + static_cast<size_t>(b) * nb) : b * p.Lq;
+                const int k_row0 = packed ? q_row0 : b * p.Lk;
                 if (lane == 0) {
                     auto load_q = [&](int qt) {
-                        const int l = qt % LANES;
+                        const int l = (rot + qt) % LANES;
                         ab::mbar_wait_nocall(&q_empty[l], (q_ctr[l] & 1u) ^ 1u);
                         ab::mbar_arrive_expect_tx(&q_full[l], Q_BYTES);
-                        ab::tma_load_2d(&tmap_q, &q_full[l], sQ + l * Q_BYTES, p.q_col0 + h * D, b * p.Lq + qt * BQ,
+                        ab::tma_load_2d(&tmap_q, &q_full[l], sQ + l * Q_BYTES, p.q_col0 + h * D, q_row0 + qt * BQ,
                                         ab::kEvictFirst);
                         ++q_ctr[l];
                     };
@@ -314,18 +328,19 @@ attention_lanes_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                         const uint32_t st = chunk_ctr % RING;
                         ab::mbar_wait_nocall(&kv_empty[st], ((chunk_ctr / RING) & 1u) ^ 1u);
                         ab::mbar_arrive_expect_tx(&kv_full[st], STAGE_BYTES);
-                        ab::tma_load_2d(map, &kv_full[st], sRing + st * STAGE_BYTES, col0 + h * D, b * p.Lk + j * BK,
+                        ab::tma_load_2d(map, &kv_full[st], sRing + st * STAGE_BYTES, col0 + h * D, k_row0 + j * BK,
                                         ab::kEvictNormal);
                         ++chunk_ctr;
                     };
-                    for (int qt = 0; qt < n_qt && qt < LANES; ++qt) load_q(qt);
+                    for (int qt = 0; qt < item_qt && qt < LANES; ++qt) load_q(qt);
                     for (uint32_t lm = live; lm != 0u; lm &= lm - 1u) {      // live key blocks only, in order
                         const int j = __ffs(lm) - 1;
                         load_chunk(&tmap_k, p.k_col0, j);
                         load_chunk(&tmap_v, p.v_col0, j);
                     }
-                    for (int qt = LANES; qt < n_qt; ++qt) load_q(qt);
+                    for (int qt = LANES; qt < item_qt; ++qt) load_q(qt);
                 }
+                if (packed) rot = (rot + item_qt) % LANES;
                 __syncwarp();
             }
         } else if (lane == 0) {
@@ -356,12 +371,26 @@ attention_lanes_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                 ++s_ctr;
             };
             uint32_t chunk_base = 0;                 // K / V chunks of the items before this one (2 per live block)
+            int rot = 0;
             for (int it = it_begin; it < it_end; ++it, ++item_it) {
                 // the item's live key blocks: published by warp 0 with the tables (read once, at the item's start)
                 ab::mbar_wait_nocall(&tab_full[item_it & 1], (item_it >> 1) & 1u);
                 const uint32_t live = s_live[item_it & 1];
                 const int nl = __popc(live);
-                for (int qt = l; qt < n_qt; qt += LANES, ++tile_ctr) {
+                const int item_qt = packed ? (nl + 1) / 2 : n_qt;
+                const int qt0 = packed ? (l + LANES - rot) % LANES : l;
+                if (packed) {
+                    rot = (rot + item_qt) % LANES;
+                    if (qt0 >= item_qt) {
+                        // no tile of this item on this lane: pass its chunks (the stage is released when all lanes have)
+                        for (uint32_t c = 0; c < 2u * static_cast<uint32_t>(nl); ++c) {
+                            const uint32_t ck = chunk_base + c;
+                            ab::mbar_wait_nocall(&kv_full[ck % RING], (ck / RING) & 1u);
+                            ab::mbar_arrive(&kv_empty[ck % RING]);
+                        }
+                    }
+                }
+                for (int qt = qt0; qt < item_qt; qt += LANES, ++tile_ctr) {
                     ab::mbar_wait_nocall(&q_full[l], tile_ctr & 1u);
                     issue_s(chunk_base, nl == 1);
                     for (int j = 0; j < nl; ++j, ++blk_ctr) {           // j = ordinal among the live blocks
@@ -403,19 +432,20 @@ attention_lanes_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
         // the ncu capture of the previous version, profiles/r02_attention_lanes64_ncu_source_top.csv).  O stays intact until
         // this lane's next P.V(0), which is issued only after the p_ready(0) that follows the write-out.
         bool pend = false;
-        int pend_b = 0, pend_h = 0, pend_i = 0;
+        int pend_b = 0, pend_h = 0, pend_i = 0, pend_lq = 0;
+        int64_t pend_row0 = 0;                           // first output row of the pending tile's item
         float pend_m = 0.f, pend_sum = 1.f;
         auto emit_pending = [&]() {
             const float inv = 1.0f / pend_sum;
-            if (p.lse_out != nullptr && pend_i < p.Lq)
+            if (p.lse_out != nullptr && pend_i < pend_lq)
                 p.lse_out[(static_cast<size_t>(pend_b) * p.H + pend_h) * p.Lq + pend_i] = pend_m * (1.0f / LOG2E) + __logf(pend_sum);
 #pragma unroll 1
             for (int cc = 0; cc < D / 32; ++cc) {
                 uint32_t ro[32];
                 ab::tmem_ld32(o_addr + cc * 32, ro);
                 ab::tmem_ld_wait();
-                if (pend_i < p.Lq) {
-                    uint4* dst = reinterpret_cast<uint4*>(p.O + (static_cast<size_t>(pend_b) * p.Lq + pend_i) * p.ldo + pend_h * D + cc * 32);
+                if (pend_i < pend_lq) {
+                    uint4* dst = reinterpret_cast<uint4*>(p.O + (pend_row0 + pend_i) * p.ldo + pend_h * D + cc * 32);
 #pragma unroll
                     for (int v4 = 0; v4 < 4; ++v4)
                         dst[v4] = make_uint4(
@@ -501,6 +531,7 @@ attention_lanes_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
         };
 
         int item_it = 0;
+        int rot = 0;
         for (int it = it_begin; it < it_end; ++it, ++item_it) {
             const int h = it / p.B, b = it % p.B;
             const int buf = item_it & 1;
@@ -508,7 +539,13 @@ attention_lanes_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
             const float* mask2 = s_mask[buf];
             const bool item_mask = s_mask_flag[buf] != 0;
             tile_live = s_live[buf];
-            for (int qt = l; qt < n_qt; qt += LANES) {
+            const int nl = __popc(tile_live);
+            const int item_qt = packed ? (nl + 1) / 2 : n_qt;
+            const int qt0 = packed ? (l + LANES - rot) % LANES : l;
+            if (packed) rot = (rot + item_qt) % LANES;
+            const int item_lq = packed ? nl * BK : p.Lq;
+            const int64_t item_row0 = packed ? 64ll * __ldg(p.seg_tile + static_cast<size_t>(b) * nb) : static_cast<int64_t>(b) * p.Lq;
+            for (int qt = qt0; qt < item_qt; qt += LANES) {
                 const int i = qt * BQ + row;                          // query position inside the segment
                 const int off = max(p.Lq - 1 - i, 0);                 // bias index = j + off (clamped for pad rows)
                 const float* pb_row = s_bias + (off & 3) * CPSTRIDE + (off & ~3);
@@ -523,6 +560,7 @@ attention_lanes_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                 // ---- output: deferred into block 0 of this lane's next tile (emit_pending) ----
                 pend = true;
                 pend_b = b, pend_h = h, pend_i = i, pend_m = m_ref, pend_sum = sum0 + sum1;
+                pend_lq = item_lq, pend_row0 = item_row0;
             }
             ab::mbar_arrive(&tab_empty[buf]);
         }
@@ -548,9 +586,11 @@ int atlas_b200_attention_lanes_launch(const void* q, int64_t ldq, int32_t q_col0
                                       const void* v, int64_t ldv, int32_t v_col0, void* out, int64_t ldo,
                                       const float* add_mask, const float* bias_delta, int32_t B, int32_t H, int32_t Lq,
                                       int32_t Lk, float scale, float causal_value, float* lse_out, const uint8_t* blk_live,
-                                      int32_t is_bf16, cudaStream_t s) {
+                                      const int32_t* seg_tile, int32_t is_bf16, cudaStream_t s) {
     using namespace attn4;
     AB_REQUIRE(Lk <= MAXK && Lq <= 512, "attention_lanes: Lq <= 512 and Lk <= %d", MAXK);
+    AB_REQUIRE(seg_tile == nullptr || (blk_live != nullptr && Lq == Lk && Lk % BK == 0 && Lq <= LANES * BQ && lse_out == nullptr),
+               "attention_lanes: the packed layout needs blk_live, Lq == Lk <= %d, Lk %% 64 == 0, no lse", LANES * BQ);
     CUtensorMap tq, tk, tv;
     int rc = abh::make_tmap_2d_16bit(&tq, q, static_cast<uint64_t>(B) * Lq, static_cast<uint64_t>(q_col0 + H * D),
                                      static_cast<uint64_t>(ldq), BQ, D, is_bf16 != 0);
@@ -572,6 +612,7 @@ int atlas_b200_attention_lanes_launch(const void* q, int64_t ldq, int32_t q_col0
     p.causal_value = causal_value;
     p.lse_out = lse_out;
     p.blk_live = blk_live;
+    p.seg_tile = seg_tile;
     const int items = B * H;
     const int grid = items < abh::num_sms() ? items : abh::num_sms();
     static bool attr_set[2] = {false, false};

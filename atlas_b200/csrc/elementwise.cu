@@ -349,9 +349,133 @@ live_tile_copy_kernel(const uint16_t* __restrict__ src, int64_t lds, const int32
     }
 }
 
+// ---- padding-compacted encoder (fid.py: encode_compact): every segment (FiD passage) keeps its 64-row tiles up to the last one
+// that holds a live key; the kept tiles of all segments are packed back to back ------------------------------------------------
+// One block.  live [S, nb] -> keep [S, nb] (1 for tiles 0 .. last live tile of the segment; all nb tiles if none is live),
+// tile_off [S * nb] (index of a kept tile in the packed order, -1 = dropped), tile_src [S * nb] (inverse: source tile of packed
+// tile o, -1 past the end), *count_rows = 64 x (number of kept tiles).
+__global__ void __launch_bounds__(1024)
+segment_tile_scan_kernel(const uint8_t* __restrict__ live, int S, int nb, uint8_t* __restrict__ keep, int32_t* __restrict__ tile_off,
+                         int32_t* __restrict__ tile_src, int32_t* __restrict__ count_rows) {
+    __shared__ int s_warp[32];
+    __shared__ int s_base;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int s0 = 0; s0 < S; s0 += 1024) {
+        const int sg = s0 + static_cast<int>(threadIdx.x);
+        int f = 0;                                           // tiles this segment keeps
+        if (sg < S) {
+            for (int j = 0; j < nb; ++j)
+                if (live[static_cast<size_t>(sg) * nb + j] != 0) f = j + 1;
+            if (f == 0) f = nb;
+        }
+        int x = f;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, x, o);
+            if (static_cast<int>(threadIdx.x & 31u) >= o) x += y;
+        }
+        if ((threadIdx.x & 31u) == 31u) s_warp[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int w = s_warp[threadIdx.x];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, w, o);
+                if (static_cast<int>(threadIdx.x) >= o) w += y;
+            }
+            s_warp[threadIdx.x] = w;
+        }
+        __syncthreads();
+        const int before = s_base + (threadIdx.x >= 32 ? s_warp[(threadIdx.x >> 5) - 1] : 0) + x - f;
+        if (sg < S) {
+            for (int j = 0; j < nb; ++j) {
+                const int t = sg * nb + j;
+                keep[t] = j < f ? 1 : 0;
+                tile_off[t] = j < f ? before + j : -1;
+                if (j < f) tile_src[before + j] = t;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_base += s_warp[31];
+        __syncthreads();
+    }
+    const int total = s_base;
+    for (int o = total + static_cast<int>(threadIdx.x); o < S * nb; o += 1024) tile_src[o] = -1;
+    if (threadIdx.x == 0) *count_rows = total * 64;
+}
+
+// block o writes packed tile o: the embedding rows of the 64 token ids of its source tile, zeros past the end
+__global__ void __launch_bounds__(256)
+embed_packed_tiles_kernel(const int64_t* __restrict__ ids, const uint16_t* __restrict__ table, int64_t ldt, int vocab,
+                          const int32_t* __restrict__ tile_src, uint16_t* __restrict__ dst, int64_t ldd, int d) {
+    const int o = blockIdx.x;
+    const int src = tile_src[o];
+    const int vec_per_row = d / 8;
+    for (int v = threadIdx.x; v < 64 * vec_per_row; v += 256) {
+        const int r = v / vec_per_row, c = (v % vec_per_row) * 8;
+        uint4 val = make_uint4(0u, 0u, 0u, 0u);
+        if (src >= 0) {
+            int64_t id = __ldg(ids + static_cast<int64_t>(src) * 64 + r);
+            id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+            val = __ldg(reinterpret_cast<const uint4*>(table + id * ldt + c));
+        }
+        *reinterpret_cast<uint4*>(dst + (static_cast<int64_t>(o) * 64 + r) * ldd + c) = val;
+    }
+}
+
+// block t writes source tile t of the padded layout: its packed rows, zeros for a dropped tile
+__global__ void __launch_bounds__(256)
+expand_packed_tiles_kernel(const uint16_t* __restrict__ src, int64_t lds, const int32_t* __restrict__ tile_off,
+                           uint16_t* __restrict__ dst, int64_t ldd, int d) {
+    const int t = blockIdx.x;
+    const int off = tile_off[t];
+    const int vec_per_row = d / 8;
+    for (int v = threadIdx.x; v < 64 * vec_per_row; v += 256) {
+        const int r = v / vec_per_row, c = (v % vec_per_row) * 8;
+        uint4 val = make_uint4(0u, 0u, 0u, 0u);
+        if (off >= 0) val = __ldg(reinterpret_cast<const uint4*>(src + (static_cast<int64_t>(off) * 64 + r) * lds + c));
+        *reinterpret_cast<uint4*>(dst + (static_cast<int64_t>(t) * 64 + r) * ldd + c) = val;
+    }
+}
+
 }  // namespace ew
 
 extern "C" {
+
+int atlas_b200_segment_tile_scan(const uint8_t* live, int32_t S, int32_t nb, uint8_t* keep, int32_t* tile_off, int32_t* tile_src,
+                                 int32_t* count_rows, void* stream) {
+    AB_REQUIRE(S > 0 && nb > 0 && nb <= 64 && live != nullptr && keep != nullptr && tile_off != nullptr && tile_src != nullptr &&
+                   count_rows != nullptr, "segment_tile_scan: S > 0, 0 < nb <= 64, all tables required");
+    ew::segment_tile_scan_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(live, S, nb, keep, tile_off, tile_src, count_rows);
+    abh::count_launch(1);
+    AB_CUDA_CHECK(cudaGetLastError());
+    return ATLAS_B200_OK;
+}
+
+int atlas_b200_embed_packed_tiles(const int64_t* ids, const void* table, int64_t ldt, int32_t vocab, const int32_t* tile_src,
+                                  int32_t n_tiles, void* dst, int64_t ldd, int32_t d, void* stream) {
+    AB_REQUIRE(n_tiles >= 0 && vocab > 0 && d > 0 && d % 8 == 0 && ldt % 8 == 0 && ldd % 8 == 0 && ids != nullptr && tile_src != nullptr,
+               "embed_packed_tiles: d and the strides must be multiples of 8");
+    if (n_tiles == 0) return ATLAS_B200_OK;
+    ew::embed_packed_tiles_kernel<<<n_tiles, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        ids, static_cast<const uint16_t*>(table), ldt, vocab, tile_src, static_cast<uint16_t*>(dst), ldd, d);
+    abh::count_launch(1);
+    AB_CUDA_CHECK(cudaGetLastError());
+    return ATLAS_B200_OK;
+}
+
+int atlas_b200_expand_packed_tiles(const void* src, int64_t lds, const int32_t* tile_off, int32_t n_tiles, void* dst, int64_t ldd,
+                                   int32_t d, void* stream) {
+    AB_REQUIRE(n_tiles >= 0 && d > 0 && d % 8 == 0 && lds % 8 == 0 && ldd % 8 == 0 && tile_off != nullptr,
+               "expand_packed_tiles: d and the strides must be multiples of 8");
+    if (n_tiles == 0) return ATLAS_B200_OK;
+    ew::expand_packed_tiles_kernel<<<n_tiles, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint16_t*>(src), lds, tile_off, static_cast<uint16_t*>(dst), ldd, d);
+    abh::count_launch(1);
+    AB_CUDA_CHECK(cudaGetLastError());
+    return ATLAS_B200_OK;
+}
 
 int atlas_b200_compact_live_tiles(const void* src, int64_t lds, const uint8_t* tile_live, int32_t n_tiles, int32_t d, void* dst,
                                   int64_t ldd, int32_t* tile_off, int32_t* count_rows, void* stream) {

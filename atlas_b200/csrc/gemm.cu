@@ -717,6 +717,18 @@ int atlas_b200_linear_dynm(const void* A, int64_t lda, const void* W, int64_t ld
     return rc;
 }
 
+// atlas_b200_linear_ex over the first *m_dev rows only (m_dev in device memory, <= M_max; nullptr = all M_max rows): the encoder
+// of the padding-compacted FiD forward (fid.py: encode_compact) runs every projection this way
+int atlas_b200_linear_rows(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, const void* residual,
+                           int64_t ldr, void* C, int64_t ldc, int32_t M_max, int32_t N, int32_t K, int32_t epilogue,
+                           int32_t is_bf16, const float* row_ss, float* out_ss, float rs_eps, const int32_t* m_dev, void* stream) {
+    g_next_m_dev = m_dev;
+    const int rc = atlas_b200_linear_ex(A, lda, W, ldw, bias, residual, ldr, C, ldc, M_max, N, K, epilogue, is_bf16, row_ss, out_ss,
+                                        rs_eps, stream);
+    g_next_m_dev = nullptr;
+    return rc;
+}
+
 int atlas_b200_linear(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, const void* residual,
                       int64_t ldr, void* C, int64_t ldc, int32_t M, int32_t N, int32_t K, int32_t epilogue,
                       int32_t is_bf16, void* stream) {

@@ -349,30 +349,58 @@ class FiD(nn.Module):
         return g
 
     # ---- encoder ---------------------------------------------------------------------------
-    def _ff(self, W, G, prefix, h, eps):
+    def _ff(self, W, G, prefix, h, eps, rows=None):
         n = ops.layernorm(h, W[prefix + "layer_norm.weight"], None, eps, kind=1)
-        g = ops.linear(n, G[prefix + "DenseReluDense.wi_01"], epilogue=ops.EPI_GATED)
+        g = ops.linear(n, G[prefix + "DenseReluDense.wi_01"], epilogue=ops.EPI_GATED, rows=rows)
         # + the fp16 overflow clamp the reference applies after every sub-layer (src/modeling_t5.py:657-708; no-op in bf16)
         return ops.clamp_inf_(ops.linear(g, W[prefix + "DenseReluDense.wo.weight"], None, residual=h,
-                                         epilogue=ops.EPI_RESIDUAL))
+                                         epilogue=ops.EPI_RESIDUAL, rows=rows))
 
     @torch.no_grad()
     def encode(self, input_ids, attention_mask):
         """FiDStack encoder (src/fid.py:32-78): [B, n*L] -> each passage encoded independently -> [B, n*L, d]."""
+        r = self._encode_rows(input_ids, attention_mask, packed=ops._ENC_PACKED)
+        if isinstance(r, tuple):                    # packed rows -> the reference's padded layout (zeros at dropped tiles)
+            r = ops.expand_packed_tiles(r[0], r[2])
+        return r.view(self.encoder.config.bsz, -1, self.config.d_model)
+
+    @torch.no_grad()
+    def _encode_rows(self, input_ids, attention_mask, packed):
+        """The encoder stack on a [rows, d] matrix.  packed=False (or a shape the packed path does not take): all S * L padded
+        positions, returns the final hidden states [S * L, d].  packed=True: the PADDING-COMPACTED encoder - every passage keeps
+        its 64-row tiles up to its last live key, packed back to back (ops.segment_tile_scan); the embedding, all projections
+        (device-side row count, static launch shapes), the attention (ops.attention_packed) and the norms only see those rows.
+        A padded position never influences a live one (its softmax weight is exactly 0; everything else is row-wise) and the
+        cross-attention masks it, so logits, loss and generated tokens are those of the padded computation; the dropped rows
+        of the returned encoder states read 0 instead of the reference's never-read values.  Returns (rows [S * L, d] of which
+        the first *count are valid, keep uint8 [S, L / 64], tile_off int32 [S * L / 64], count int32 [1])."""
         c = self.config
         W, G, dt = self._weights()
-        n_ctx, bsz = self.encoder.config.n_context, self.encoder.config.bsz
+        n_ctx = self.encoder.config.n_context
         ids = input_ids.reshape(input_ids.size(0) * n_ctx, -1)
         mask = attention_mask.reshape(attention_mask.size(0) * n_ctx, -1)
         S, L = ids.shape
         d, H = c.d_model, c.num_heads
-        h = W["shared.weight"][ids.reshape(-1)]                                  # embedding gather, [S*L, d]
         add_mask = (1.0 - mask.to(torch.float32)) * -10000.0                      # 4.18 get_extended_attention_mask
         # 64-key blocks made of padding only (every passage is padded to text_maxlength) weigh exactly 0 in the softmax:
         # the attention kernel skips them (ops.key_block_live), once per forward for all layers
         live = ops.key_block_live(add_mask)
         bias = bias_by_delta(W["encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight"], L, L, True,
                              c.relative_attention_num_buckets)
+        packed = packed and live is not None and L % 64 == 0 and 64 <= L <= 384
+        rows = None
+        if packed:
+            keep, tile_off, tile_src, rows = ops.segment_tile_scan(live)
+            h = ops.embed_packed_tiles(ids, W["shared.weight"], tile_src)         # embedding gather of the kept tiles
+
+            def attn(qkv):
+                return ops.attention_packed(qkv, keep, tile_off, S, H, L, add_mask, bias, scale=1.0)
+        else:
+            h = W["shared.weight"][ids.reshape(-1)]                              # embedding gather, [S*L, d]
+
+            def attn(qkv):
+                return ops.attention(qkv, 0, qkv, H * 64, qkv, 2 * H * 64, S, H, L, L, add_mask=add_mask, bias_delta=bias,
+                                     scale=1.0, block_live=live)
         qkv = torch.empty((S * L, 3 * H * 64), dtype=dt, device=h.device)
         eps = c.layer_norm_epsilon
         if self.fuse_norm:
@@ -385,31 +413,30 @@ class FiD(nn.Module):
                 p = f"encoder.block.{i}.layer.0."
                 if i == 0:
                     n = ops.layernorm(h, W[p + "layer_norm.weight"], None, eps, kind=1)
-                    ops.linear(n, G[p + "SelfAttention.qkv"], out=qkv)
+                    ops.linear(n, G[p + "SelfAttention.qkv"], out=qkv, rows=rows)
                 else:
-                    ops.linear(h, G[p + "SelfAttention.qkv_n"], out=qkv, row_ss=ss[2 * i - 1], rs_eps=eps)
-                ctx = ops.attention(qkv, 0, qkv, H * 64, qkv, 2 * H * 64, S, H, L, L, add_mask=add_mask, bias_delta=bias,
-                                    scale=1.0, block_live=live)
+                    ops.linear(h, G[p + "SelfAttention.qkv_n"], out=qkv, row_ss=ss[2 * i - 1], rs_eps=eps, rows=rows)
+                ctx = attn(qkv)
                 h = ops.linear(ctx, W[p + "SelfAttention.o.weight"], None, residual=h, epilogue=ops.EPI_RESIDUAL,
-                               out_ss=ss[2 * i])
+                               out_ss=ss[2 * i], rows=rows)
                 ops.clamp_inf_(h, row_ss=ss[2 * i])
                 p = f"encoder.block.{i}.layer.1."
-                g = ops.linear(h, G[p + "DenseReluDense.wi_01_n"], epilogue=ops.EPI_GATED, row_ss=ss[2 * i], rs_eps=eps)
+                g = ops.linear(h, G[p + "DenseReluDense.wi_01_n"], epilogue=ops.EPI_GATED, row_ss=ss[2 * i], rs_eps=eps,
+                               rows=rows)
                 h = ops.linear(g, W[p + "DenseReluDense.wo.weight"], None, residual=h, epilogue=ops.EPI_RESIDUAL,
-                               out_ss=ss[2 * i + 1])
+                               out_ss=ss[2 * i + 1], rows=rows)
                 ops.clamp_inf_(h, row_ss=ss[2 * i + 1])
         else:
             for i in range(c.num_layers):
                 p = f"encoder.block.{i}.layer.0."
                 n = ops.layernorm(h, W[p + "layer_norm.weight"], None, eps, kind=1)
-                ops.linear(n, G[p + "SelfAttention.qkv"], out=qkv)
-                ctx = ops.attention(qkv, 0, qkv, H * 64, qkv, 2 * H * 64, S, H, L, L, add_mask=add_mask, bias_delta=bias,
-                                    scale=1.0, block_live=live)
+                ops.linear(n, G[p + "SelfAttention.qkv"], out=qkv, rows=rows)
+                ctx = attn(qkv)
                 h = ops.clamp_inf_(ops.linear(ctx, W[p + "SelfAttention.o.weight"], None, residual=h,
-                                              epilogue=ops.EPI_RESIDUAL))
-                h = self._ff(W, G, f"encoder.block.{i}.layer.1.", h, eps)
+                                              epilogue=ops.EPI_RESIDUAL, rows=rows))
+                h = self._ff(W, G, f"encoder.block.{i}.layer.1.", h, eps, rows=rows)
         h = ops.layernorm(h, W["encoder.final_layer_norm.weight"], None, c.layer_norm_epsilon, kind=1)
-        return h.view(bsz, -1, d)
+        return (h, keep, tile_off, rows) if packed else h
 
     # ---- decoder ---------------------------------------------------------------------------
     @torch.no_grad()
@@ -426,8 +453,10 @@ class FiD(nn.Module):
                 for i in range(c.num_decoder_layers)]
 
     @torch.no_grad()
-    def decode(self, decoder_input_ids, enc, enc_mask, cross_kv=None):
-        """Decoder stack + LM head: [B, T] -> logits [B, T, vocab] (src/modeling_t5.py:875-1083,1619-1647)."""
+    def decode(self, decoder_input_ids, enc, enc_mask, cross_kv=None, enc_packed=None):
+        """Decoder stack + LM head: [B, T] -> logits [B, T, vocab] (src/modeling_t5.py:875-1083,1619-1647).
+        enc_packed: the tuple of `_encode_rows(packed=True)` that `enc` was expanded from - the cross K | V projections then
+        read the packed rows directly."""
         c = self.config
         W, G, dt = self._weights()
         B, T = decoder_input_ids.shape
@@ -452,7 +481,13 @@ class FiD(nn.Module):
         compact = (cross_kv is None and cross_live is not None and not capture and ops._XKV_COMPACT and ops._XATTN_STREAM
                    and T <= 64 and Lk % 64 == 0 and Lk >= 1024)
         xkv = None
-        if compact:
+        if compact and enc_packed is not None:
+            # the encoder already ran on its kept tiles (a superset of the live ones, same tile order): project those rows
+            enc_live, keep, tile_off, n_live_rows = enc_packed
+            cross_live = keep.view(B, Lk // 64)
+            xkv = [ops.linear_dynm(enc_live, G[f"decoder.block.{i}.layer.1.EncDecAttention.kv"], n_live_rows)
+                   for i in range(c.num_decoder_layers)]
+        elif compact:
             flat = enc.reshape(-1, d)
             if flat.dtype != dt:
                 flat = flat.to(dt)
@@ -693,7 +728,7 @@ class FiD(nn.Module):
         self._weights()                                      # make sure the 16-bit weight copies exist / are current
         dt = self._dtype()
         # the 16-bit weight buffers are refreshed in place (HalfCache): the graph key only holds their allocation generation
-        key = (tag, dt, self.fuse_norm, self._half.sets[dt]["gen"],
+        key = (tag, dt, self.fuse_norm, ops._ENC_PACKED, self._half.sets[dt]["gen"],
                tuple((tuple(t.shape), t.dtype, t.device) for t in inputs))
         runner = self._graphs.get(key)
         if runner is None:
@@ -722,8 +757,10 @@ class FiD(nn.Module):
             n_ctx, bsz = self.encoder.config.n_context, self.encoder.config.bsz
 
             def full(ids, mask, dec):
-                e = self.encode(ids, mask)
-                return self.decode(dec, e, mask.reshape(e.shape[0], -1)), e
+                r = self._encode_rows(ids, mask, packed=ops._ENC_PACKED)
+                packed = r if isinstance(r, tuple) else None
+                e = (ops.expand_packed_tiles(r[0], r[2]) if packed else r).view(bsz, -1, self.config.d_model)
+                return self.decode(dec, e, mask.reshape(e.shape[0], -1), enc_packed=packed), e
 
             logits, enc = self._run(("full", n_ctx, bsz), full,
                                     (input_ids, attention_mask.to(torch.bool), decoder_input_ids))

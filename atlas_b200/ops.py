@@ -163,14 +163,15 @@ def topk_merge_blob(blob_all, ids_off, world, nq_total, k, q_begin, nq_out, dtyp
 EPI_NONE, EPI_BIAS, EPI_GELU, EPI_RESIDUAL, EPI_GATED = 0, 1, 2, 3, 4
 
 
-def linear(x, weight, bias=None, residual=None, epilogue=None, out=None, row_ss=None, out_ss=None, rs_eps=1e-6):
+def linear(x, weight, bias=None, residual=None, epilogue=None, out=None, row_ss=None, out_ss=None, rs_eps=1e-6, rows=None):
     """y = epilogue(x @ weight.T) on tcgen05.  x [..., K], weight [N, K] (nn.Linear layout), 16-bit.
 
     epilogue: EPI_NONE / EPI_BIAS / EPI_GELU / EPI_RESIDUAL / EPI_GATED (see include/atlas_b200.h);
     default: EPI_RESIDUAL if `residual` is given, else EPI_BIAS if `bias` is given, else EPI_NONE.
     Fused T5 RMSNorm (atlas_b200_linear_ex): `row_ss` fp32 [M] = sum of squares of the rows of x -> accumulator rows are
     scaled by rsqrt(row_ss / K + rs_eps) (x is the UN-normalised hidden state, the norm weight is folded into `weight`);
-    `out_ss` fp32 [M] (pre-zeroed) receives the sum of squares of the stored output rows."""
+    `out_ss` fp32 [M] (pre-zeroed) receives the sum of squares of the stored output rows.
+    `rows`: int32 [1] device tensor - only the first *rows rows are computed (atlas_b200_linear_rows; static launch shape)."""
     require_cuda(x, "x")
     if x.dtype not in (torch.float16, torch.bfloat16) or weight.dtype != x.dtype:
         raise AtlasB200Error(f"linear: x and weight must both be fp16 or bf16 (got {x.dtype}, {weight.dtype})")
@@ -196,11 +197,12 @@ def linear(x, weight, bias=None, residual=None, epilogue=None, out=None, row_ss=
     for t in (row_ss, out_ss):
         if t is not None and (t.dtype != torch.float32 or t.numel() != M or not t.is_contiguous() or not t.is_cuda):
             raise AtlasB200Error("linear: row_ss / out_ss must be contiguous CUDA fp32 tensors with one element per row")
-    check(lib().atlas_b200_linear_ex(
+    check(lib().atlas_b200_linear_rows(
         _ptr(x2), x2.stride(0), _ptr(w), w.stride(0), _ptr(bias) if bias is not None else None,
         _ptr(r2) if r2 is not None else None, r2.stride(0) if r2 is not None else 0, _ptr(out), out.stride(0),
         M, N, K, epilogue, 1 if x.dtype == torch.bfloat16 else 0, _ptr(row_ss) if row_ss is not None else None,
-        _ptr(out_ss) if out_ss is not None else None, float(rs_eps), current_stream_ptr()))
+        _ptr(out_ss) if out_ss is not None else None, float(rs_eps), _ptr(rows) if rows is not None else None,
+        current_stream_ptr()))
     return out.reshape(*x.shape[:-1], n_out)
 
 
@@ -317,6 +319,60 @@ def compact_live_tiles(x, tile_live):
     check(lib().atlas_b200_compact_live_tiles(_ptr(x2), x2.stride(0), _ptr(flags), n_tiles, x2.shape[1], _ptr(dst),
                                               dst.stride(0), _ptr(tile_off), _ptr(count), current_stream_ptr()))
     return dst, tile_off, count
+
+
+_ENC_PACKED = os.environ.get("ATLAS_B200_ENC_PACKED", "1") != "0"          # A/B switch of the padding-compacted FiD encoder
+
+
+def segment_tile_scan(live):
+    """live uint8 [S, nb] (key_block_live) -> (keep uint8 [S, nb], tile_off int32 [S * nb], tile_src int32 [S * nb], count_rows
+    int32 [1]): the packed layout of the padding-compacted encoder (include/atlas_b200.h).  No host synchronisation."""
+    require_cuda(live, "live")
+    S, nb = live.shape
+    live = live.contiguous()
+    keep = torch.empty_like(live)
+    tile_off = torch.empty(S * nb, dtype=torch.int32, device=live.device)
+    tile_src = torch.empty(S * nb, dtype=torch.int32, device=live.device)
+    count = torch.empty(1, dtype=torch.int32, device=live.device)
+    check(lib().atlas_b200_segment_tile_scan(_ptr(live), S, nb, _ptr(keep), _ptr(tile_off), _ptr(tile_src), _ptr(count),
+                                             current_stream_ptr()))
+    return keep, tile_off, tile_src, count
+
+
+def embed_packed_tiles(ids, table, tile_src):
+    """Embedding rows of the token ids (int64 [n_tiles * 64]) of the kept tiles, in packed order; zeros past the end."""
+    require_cuda(table, "table")
+    ids = ids.reshape(-1).contiguous()
+    n_tiles = tile_src.numel()
+    if ids.dtype != torch.int64 or ids.numel() != n_tiles * 64:
+        raise AtlasB200Error(f"embed_packed_tiles: need {n_tiles * 64} int64 ids (got {ids.numel()} {ids.dtype})")
+    out = torch.empty((n_tiles * 64, table.shape[1]), dtype=table.dtype, device=table.device)
+    check(lib().atlas_b200_embed_packed_tiles(_ptr(ids), _ptr(table), table.stride(0), table.shape[0], _ptr(tile_src), n_tiles,
+                                              _ptr(out), out.stride(0), table.shape[1], current_stream_ptr()))
+    return out
+
+
+def attention_packed(qkv, keep, tile_off, S, H, L, add_mask, bias_delta, scale=1.0, out=None):
+    """Encoder self-attention on the packed rows (segment s = its kept tiles, back to back): atlas_b200_attention_packed."""
+    require_cuda(qkv, "qkv")
+    if out is None:
+        out = torch.empty((qkv.shape[0], H * 64), dtype=qkv.dtype, device=qkv.device)
+    am = add_mask.float().contiguous()
+    bd = bias_delta.float().contiguous() if bias_delta is not None else None
+    check(lib().atlas_b200_attention_packed(_ptr(qkv), qkv.stride(0), 0, H * 64, 2 * H * 64, _ptr(out), out.stride(0), _ptr(am),
+                                            _ptr(bd) if bd is not None else None, _ptr(keep), _ptr(tile_off), S, H, L,
+                                            float(scale), _bf(qkv), current_stream_ptr()))
+    return out
+
+
+def expand_packed_tiles(x, tile_off):
+    """Packed rows -> the padded layout [n_tiles * 64, d]; dropped tiles are zero."""
+    require_cuda(x, "x")
+    n_tiles = tile_off.numel()
+    out = torch.empty((n_tiles * 64, x.shape[1]), dtype=x.dtype, device=x.device)
+    check(lib().atlas_b200_expand_packed_tiles(_ptr(x), x.stride(0), _ptr(tile_off), n_tiles, _ptr(out), out.stride(0),
+                                               x.shape[1], current_stream_ptr()))
+    return out
 
 
 def linear_dynm(x, weight, m_dev, out=None):

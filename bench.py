@@ -687,6 +687,31 @@ def run_ours(args):
            + rq_ids.numel() * 8 + rq_lens.numel() * 4 + B * N_DOCS * 8) * world
     d2h = (4 + B * TOPK * (8 + 4) + 8) * world
 
+    # ---------------- the same device-resident step with the encoder on every padded position (for the record) ---------
+    from atlas_b200 import ops as _ops
+
+    padded_encoder = None
+    if _ops._ENC_PACKED:
+        _ops._ENC_PACKED = False
+        try:
+            for _ in range(3):
+                step_device()
+            barrier_sync()
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record()
+            for _ in range(args.steps):
+                step_device()
+            p1.record()
+            barrier_sync()
+            pms = max_over_ranks(p0.elapsed_time(p1)) / args.steps
+            padded_encoder = {"value": B * world / (pms * 1e-3), "unit": "queries/s", "ms_per_step": pms,
+                              "what": "ATLAS_B200_ENC_PACKED=0: embedding, projections and norms of the FiD encoder on all "
+                                      f"{N_DOCS} x {TEXT_LEN} padded positions per query like the reference (all-padding key "
+                                      "blocks still skipped by the attention kernels)"}
+        finally:
+            _ops._ENC_PACKED = True
+        step_device()
+
     # ---------------- per-kernel time of the step (eager launches bracketed with CUDA events in the library) -------
     reader.cuda_graphs = False
     prof = {}
@@ -774,7 +799,13 @@ def run_ours(args):
                                           "frac_of_tensor_peak": a_tflops / peak if (a_tflops and peak) else None,
                                           "share_of_step": a_ms / ms_per_step if ms_per_step else None},
                      "mips_scan": mips.get("roofline"),
-                     "model_flops_utilisation": FID_FLOPS_PER_QUERY * B / (ms_per_step * 1e-3) / 1e12 / peak},
+                     "model_flops_utilisation": FID_FLOPS_PER_QUERY * B / (ms_per_step * 1e-3) / 1e12 / peak,
+                     "model_flops_utilisation_note": "dense-model FLOPs (every padded position counted) over the step time; "
+                                                     "`achieved` / `frac` above count only the rows the GEMMs computed"},
+        "encoder": "padding-compacted: each passage keeps its 64-row tiles up to its last real token "
+                   "(FiD._encode_rows, DESIGN.md 3.10); `padded_encoder` = the same step with ATLAS_B200_ENC_PACKED=0"
+                   if _ops._ENC_PACKED else "every padded position (ATLAS_B200_ENC_PACKED=0)",
+        "padded_encoder": padded_encoder,
         "e2e": {"value": B * world / (e2e_ms * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
                 "phases_ms_synchronised": {k: round(v, 3) for k, v in e2e_phases.items()},
@@ -867,7 +898,13 @@ def generate_leg(args, atlas, bank_tokens, index, q_enc, rq_ids, rq_lens, dev, w
         reader.cuda_graphs = True
     peak, peak_src = peaks("hbm")
     c = reader.config
-    bytes_per_launch = B * N_DOCS * TEXT_LEN * 2 * c.num_heads * 64 * 2
+    from atlas_b200 import ops as _ops
+
+    # the decode steps skip 64-key tiles of padding only (exact zeros of the softmax): bytes actually read = the live tiles'
+    live = _ops.key_block_live((1.0 - mask.float()) * -1e9)
+    live_frac = float(live.float().mean()) if live is not None else 1.0
+    bytes_dense = B * N_DOCS * TEXT_LEN * 2 * c.num_heads * 64 * 2
+    bytes_per_launch = int(bytes_dense * live_frac)
     k_ms = kms.value / max(1, kn.value)
     achieved = bytes_per_launch / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
     return {"metric": "greedy generation tokens/sec (FiD-base, n_docs 40, KV-cached decode, encoder + cross K|V once)",
@@ -879,6 +916,9 @@ def generate_leg(args, atlas, bank_tokens, index, q_enc, rq_ids, rq_lens, dev, w
                          "kernel": "decode_cross_attention_kernel (one new token against the cached cross K|V)",
                          "kernel_ms_per_launch": k_ms, "launches_timed": kn.value,
                          "algorithmic_bytes_per_launch": bytes_per_launch,
+                         "bytes_note": f"K | V rows of the live 64-key tiles ({live_frac:.3f} of all tiles; the others hold padding "
+                                       f"only and are skipped): dense K | V = {bytes_dense} B per launch",
+                         "dense_equivalent_GBps": bytes_dense / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None,
                          "step_bytes_all_layers": bytes_per_launch * c.num_decoder_layers,
                          "step_level_GBps": bytes_per_launch * c.num_decoder_layers / (step_ms * 1e-3) / 1e9 if step_ms > 0 else None}}
 

@@ -435,6 +435,36 @@ int atlas_b200_cross_attention_stream_compact(const void* q, int64_t ldq, int32_
                                               int32_t chunk, float scale, float* o_partial, float* ml_partial, int32_t is_bf16,
                                               void* stream);
 
+/* Padding-compacted FiD encoder (inference forward, fid.py: FiD.encode_packed).  The reference encodes every passage padded to
+ * text_maxlength (src/atlas.py:261-270, src/fid.py:32-78) and masks the padding keys; a padded position never influences a live
+ * one (its softmax weight is exactly 0, every other encoder op is row-wise) and the decoder's cross-attention masks it too, so
+ * the encoder runs on the 64-row tiles up to each segment's last live key only, packed back to back.  Static launch shapes:
+ * the packed row count lives in device memory.
+ *   atlas_b200_segment_tile_scan: live uint8 [S, nb] (key_block_live) -> keep [S, nb] (tiles 0 .. last live tile of the segment;
+ *     all nb if none is live), tile_off int32 [S * nb] (packed index of a kept tile, -1 = dropped), tile_src int32 [S * nb] (source
+ *     tile of packed tile o, -1 past the end), *count_rows = 64 x #kept.
+ *   atlas_b200_embed_packed_tiles: dst[64 o + r, :] = table[ids[64 tile_src[o] + r], :] (zeros past the end): T5Stack's
+ *     embed_tokens (src/modeling_t5.py:930-934) straight into the packed layout.
+ *   atlas_b200_linear_rows: atlas_b200_linear_ex over the first *m_dev rows (row blocks past it are not computed; rows of the
+ *     last computed block past *m_dev hold unspecified values); m_dev == NULL = atlas_b200_linear_ex.
+ *   atlas_b200_attention_packed: T5Attention.forward (src/modeling_t5.py:478-524) of the encoder on the packed rows: segment b =
+ *     rows [64 tile_off[b * nb], + 64 popcount(keep[b, :])) of qkv / out; add_mask [B, L] and bias_delta [H, 2L - 1] as in
+ *     atlas_b200_attention_ex (positions are those of the padded layout: kept tiles are a prefix of the segment).
+ *   atlas_b200_expand_packed_tiles: back to the padded layout [S * nb * 64, d] (zeros at dropped tiles - the positions the
+ *     reference fills with values nothing reads). */
+int atlas_b200_segment_tile_scan(const uint8_t* live, int32_t S, int32_t nb, uint8_t* keep, int32_t* tile_off, int32_t* tile_src,
+                                 int32_t* count_rows, void* stream);
+int atlas_b200_embed_packed_tiles(const int64_t* ids, const void* table, int64_t ldt, int32_t vocab, const int32_t* tile_src,
+                                  int32_t n_tiles, void* dst, int64_t ldd, int32_t d, void* stream);
+int atlas_b200_linear_rows(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, const void* residual,
+                           int64_t ldr, void* C, int64_t ldc, int32_t M_max, int32_t N, int32_t K, int32_t epilogue,
+                           int32_t is_bf16, const float* row_ss, float* out_ss, float rs_eps, const int32_t* m_dev, void* stream);
+int atlas_b200_attention_packed(const void* qkv, int64_t ld, int32_t q_col0, int32_t k_col0, int32_t v_col0, void* out, int64_t ldo,
+                                const float* add_mask, const float* bias_delta, const uint8_t* keep, const int32_t* tile_off,
+                                int32_t B, int32_t H, int32_t L, float scale, int32_t is_bf16, void* stream);
+int atlas_b200_expand_packed_tiles(const void* src, int64_t lds, const int32_t* tile_off, int32_t n_tiles, void* dst, int64_t ldd,
+                                   int32_t d, void* stream);
+
 /* Measurement hook for bench.py's roofline: while enabled, every launch of ONE kind of kernel is bracketed
  * with CUDA events on its launching stream:
  *   kind 1  the bank sweep of atlas_b200_mips_topk (work = algorithmic bytes swept)
