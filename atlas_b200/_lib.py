@@ -173,13 +173,13 @@ def lib():
     L.atlas_b200_attention_dropout_mask.restype = c.c_int
     L.atlas_b200_attention_dropout_mask.argtypes = [vp, i64, i32, f32, u64, u64, vp]
     L.atlas_b200_segment_tile_scan.restype = c.c_int
-    L.atlas_b200_segment_tile_scan.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
+    L.atlas_b200_segment_tile_scan.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp]
     L.atlas_b200_embed_packed_tiles.restype = c.c_int
     L.atlas_b200_embed_packed_tiles.argtypes = [vp, vp, i64, i32, vp, i32, vp, i64, i32, vp]
     L.atlas_b200_linear_rows.restype = c.c_int
     L.atlas_b200_linear_rows.argtypes = [vp, i64, vp, i64, vp, vp, i64, vp, i64, i32, i32, i32, i32, i32, vp, vp, f32, vp, vp]
     L.atlas_b200_attention_packed.restype = c.c_int
-    L.atlas_b200_attention_packed.argtypes = [vp, i64, i32, i32, i32, vp, i64, vp, vp, vp, vp, i32, i32, i32, f32, i32, vp]
+    L.atlas_b200_attention_packed.argtypes = [vp, i64, i32, i32, i32, vp, i64, vp, vp, vp, vp, vp, i32, i32, i32, f32, i32, vp]
     L.atlas_b200_expand_packed_tiles.restype = c.c_int
     L.atlas_b200_expand_packed_tiles.argtypes = [vp, i64, vp, i32, vp, i64, i32, vp]
     _lib = L

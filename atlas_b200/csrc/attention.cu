@@ -889,7 +889,7 @@ int atlas_b200_attention_lanes_launch(const void* q, int64_t ldq, int32_t q_col0
                                       const void* v, int64_t ldv, int32_t v_col0, void* out, int64_t ldo,
                                       const float* add_mask, const float* bias_delta, int32_t B, int32_t H, int32_t Lq,
                                       int32_t Lk, float scale, float causal_value, float* lse_out, const uint8_t* blk_live,
-                                      const int32_t* seg_tile, int32_t is_bf16, cudaStream_t s);
+                                      const int32_t* seg_tile, const int32_t* seg_work, int32_t is_bf16, cudaStream_t s);
 // csrc/attention_lanes96.cu: the first three-lane kernel (96-key blocks), ATLAS_B200_ATTN_LANES=3
 int atlas_b200_attention_lanes96_launch(const void* q, int64_t ldq, int32_t q_col0, const void* k, int64_t ldk, int32_t k_col0,
                                        const void* v, int64_t ldv, int32_t v_col0, void* out, int64_t ldo,
@@ -922,7 +922,8 @@ int atlas_b200_attention_ex(const void* q, int64_t ldq, int32_t q_col0, const vo
 // first popcount(keep[b, :]) of its L / 64 tiles, stored back to back from row 64 * tile_off[b * (L / 64)] of qkv / out.
 int atlas_b200_attention_packed(const void* qkv, int64_t ld, int32_t q_col0, int32_t k_col0, int32_t v_col0, void* out, int64_t ldo,
                                 const float* add_mask, const float* bias_delta, const uint8_t* keep, const int32_t* tile_off,
-                                int32_t B, int32_t H, int32_t L, float scale, int32_t is_bf16, void* stream) {
+                                const int32_t* work_prefix, int32_t B, int32_t H, int32_t L, float scale, int32_t is_bf16,
+                                void* stream) {
     AB_REQUIRE(B > 0 && H > 0 && L > 0 && L % 64 == 0 && L <= 384 && keep != nullptr && tile_off != nullptr,
                "attention_packed: 0 < L <= 384, L %% 64 == 0 and the segment tables are required (got L=%d)", L);
     AB_REQUIRE(ld % 8 == 0 && ldo % 8 == 0 && q_col0 % 8 == 0 && k_col0 % 8 == 0 && v_col0 % 8 == 0,
@@ -930,7 +931,8 @@ int atlas_b200_attention_packed(const void* qkv, int64_t ld, int32_t q_col0, int
     cudaStream_t ls = static_cast<cudaStream_t>(stream);
     abh::prof_begin(ls, abh::PROF_ATTENTION);
     const int lrc = atlas_b200_attention_lanes_launch(qkv, ld, q_col0, qkv, ld, k_col0, qkv, ld, v_col0, out, ldo, add_mask,
-                                                      bias_delta, B, H, L, L, scale, 0.f, nullptr, keep, tile_off, is_bf16, ls);
+                                                      bias_delta, B, H, L, L, scale, 0.f, nullptr, keep, tile_off, work_prefix, is_bf16,
+                                                      ls);
     if (lrc) return lrc;
     // dense-equivalent work, like the masked-block skipping of the padded layout
     abh::prof_end(ls, abh::PROF_ATTENTION, 4.0 * B * H * static_cast<double>(L) * L * attn::D);
@@ -972,7 +974,7 @@ int atlas_b200_attention_train(const void* q, int64_t ldq, int32_t q_col0, const
                                                             is_bf16, ls)
                       : atlas_b200_attention_lanes_launch(q, ldq, q_col0, k, ldk, k_col0, v, ldv, v_col0, out, ldo, add_mask,
                                                           bias_delta, B, H, Lq, Lk, scale, causal_value, lse_out, key_block_live,
-                                                          nullptr, is_bf16, ls);
+                                                          nullptr, nullptr, is_bf16, ls);
         if (lrc) return lrc;
         abh::prof_end(ls, abh::PROF_ATTENTION, 4.0 * B * H * static_cast<double>(Lq) * Lk * D);
         abh::count_launch();

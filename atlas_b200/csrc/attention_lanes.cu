@@ -82,6 +82,8 @@ struct Params {
                                 // are the 64-row tiles it keeps (blk_live: a prefix of its tiles), stored back to back from row
                                 // 64 * seg_tile[b * nb] of q / k / v / out; query tiles past the kept rows do not exist.  Needs
                                 // Lq == Lk <= 384 and blk_live.
+    const int32_t* seg_work;    // optional with seg_tile: [B + 1] exclusive prefix of the segments' work (kept key blocks x query
+                                // tiles): the CTAs split the head-major item list by work instead of by item count
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -212,9 +214,7 @@ attention_lanes_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
     const int lk_pad = nb * BK;
     const int n_qt = (p.Lq + BQ - 1) / BQ;                      // query tiles per item; tile t belongs to lane t % 3
     const int n_items = p.B * p.H;
-    // contiguous item range of this CTA, head-major (item = h * B + b): the bias tables change at most twice per CTA
-    const int it_begin = static_cast<int>(static_cast<int64_t>(blockIdx.x) * n_items / gridDim.x);
-    const int it_end = static_cast<int>(static_cast<int64_t>(blockIdx.x + 1) * n_items / gridDim.x);
+    __shared__ int s_range[2];
     const bool has_bias = (p.bias_delta != nullptr) || (p.causal_value != 0.f);
     const bool packed = p.seg_tile != nullptr;
 
@@ -244,10 +244,31 @@ attention_lanes_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
         ab::fence_barrier_init();
     }
     if (warp == 2) ab::tmem_alloc<1>(&tmem_base_smem, TMEM_COLS);
+    if (warp == 3 && lane < 2) {
+        // contiguous item range of this CTA, head-major (item = h * B + b): the bias tables change at most twice per CTA.
+        // Packed layout: the items differ in size (1 - 6 kept key blocks x 1 - 3 query tiles) - split by work, not by count.
+        const int64_t c = static_cast<int64_t>(blockIdx.x) + lane;
+        int bound = static_cast<int>(c * n_items / gridDim.x);
+        if (p.seg_work != nullptr) {
+            const int64_t w_seg = __ldg(p.seg_work + p.B);                       // work of one head (> 0)
+            const int64_t t = c * (w_seg * p.H) / gridDim.x;
+            const int h = static_cast<int>(t / w_seg);
+            const int r = static_cast<int>(t % w_seg);
+            int lo = 0, hi = p.B;                                                // first b with prefix[b + 1] > r
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (__ldg(p.seg_work + mid + 1) > r) hi = mid;
+                else lo = mid + 1;
+            }
+            bound = c >= gridDim.x ? n_items : min(h * p.B + lo, n_items);
+        }
+        s_range[lane] = bound;
+    }
     ab::tc_fence_before();
     __syncthreads();
     ab::tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    const int it_begin = s_range[0], it_end = s_range[1];
 
     if (warp < 4) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
@@ -586,7 +607,7 @@ int atlas_b200_attention_lanes_launch(const void* q, int64_t ldq, int32_t q_col0
                                       const void* v, int64_t ldv, int32_t v_col0, void* out, int64_t ldo,
                                       const float* add_mask, const float* bias_delta, int32_t B, int32_t H, int32_t Lq,
                                       int32_t Lk, float scale, float causal_value, float* lse_out, const uint8_t* blk_live,
-                                      const int32_t* seg_tile, int32_t is_bf16, cudaStream_t s) {
+                                      const int32_t* seg_tile, const int32_t* seg_work, int32_t is_bf16, cudaStream_t s) {
     using namespace attn4;
     AB_REQUIRE(Lk <= MAXK && Lq <= 512, "attention_lanes: Lq <= 512 and Lk <= %d", MAXK);
     AB_REQUIRE(seg_tile == nullptr || (blk_live != nullptr && Lq == Lk && Lk % BK == 0 && Lq <= LANES * BQ && lse_out == nullptr),
@@ -613,6 +634,7 @@ int atlas_b200_attention_lanes_launch(const void* q, int64_t ldq, int32_t q_col0
     p.lse_out = lse_out;
     p.blk_live = blk_live;
     p.seg_tile = seg_tile;
+    p.seg_work = seg_tile != nullptr ? seg_work : nullptr;
     const int items = B * H;
     const int grid = items < abh::num_sms() ? items : abh::num_sms();
     static bool attr_set[2] = {false, false};

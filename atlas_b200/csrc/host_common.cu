@@ -99,12 +99,14 @@ static int g_prof_on = 0;   // 0 off, otherwise the ProfKind being bracketed
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
 static size_t g_prof_used = 0;
 static double g_prof_work = 0;
-struct DynWork {                 // launches whose row count lives in device memory: resolved when the work is read
-    double work_per_row;
-    const int32_t* m_dev;
+struct DynWork {                 // launches whose row count lives in device memory: the count is copied to a pinned host slot
+    double work_per_row;         // in stream order right behind the launch (the device tensor may be recycled by the caller's
+    int slot;                    // allocator before the work is read) and resolved when the work is read
     int32_t m_max;
 };
 static std::vector<DynWork> g_prof_dyn;
+static int32_t* g_prof_rows = nullptr;          // pinned host slots
+constexpr int PROF_ROW_SLOTS = 4096;
 
 void prof_begin(cudaStream_t s, int kind) {
     if (g_prof_on != kind) return;
@@ -127,7 +129,17 @@ void prof_end_dyn(cudaStream_t s, int kind, double work_per_row, const int32_t* 
     if (g_prof_on != kind || g_prof_used >= g_prof_events.size()) return;
     cudaEventRecord(g_prof_events[g_prof_used].second, s);
     ++g_prof_used;
-    g_prof_dyn.push_back({work_per_row, m_dev, m_max});
+    if (g_prof_rows == nullptr && cudaMallocHost(reinterpret_cast<void**>(&g_prof_rows), PROF_ROW_SLOTS * sizeof(int32_t)) != cudaSuccess)
+        g_prof_rows = nullptr;
+    const int slot = static_cast<int>(g_prof_dyn.size());
+    if (g_prof_rows != nullptr && slot < PROF_ROW_SLOTS) {
+        g_prof_rows[slot] = m_max;
+        if (cudaMemcpyAsync(g_prof_rows + slot, m_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, s) == cudaSuccess) {
+            g_prof_dyn.push_back({work_per_row, slot, m_max});
+            return;
+        }
+    }
+    g_prof_work += work_per_row * m_max;          // no slot: counted at full height
 }
 
 }  // namespace abh
@@ -146,8 +158,7 @@ void atlas_b200_profile_enable(int32_t kind) {
 double atlas_b200_profile_work(void) {
     double w = abh::g_prof_work;
     for (const auto& d : abh::g_prof_dyn) {
-        int32_t m = 0;
-        if (cudaMemcpy(&m, d.m_dev, sizeof(m), cudaMemcpyDeviceToHost) != cudaSuccess) m = d.m_max;
+        int32_t m = abh::g_prof_rows[d.slot];
         if (m > d.m_max) m = d.m_max;
         if (m < 0) m = 0;
         w += d.work_per_row * m;

@@ -322,11 +322,13 @@ def compact_live_tiles(x, tile_live):
 
 
 _ENC_PACKED = os.environ.get("ATLAS_B200_ENC_PACKED", "1") != "0"          # A/B switch of the padding-compacted FiD encoder
+_PACKED_BALANCE = os.environ.get("ATLAS_B200_PACKED_BALANCE", "1") != "0"  # A/B: packed attention CTAs split by work, not count
 
 
 def segment_tile_scan(live):
     """live uint8 [S, nb] (key_block_live) -> (keep uint8 [S, nb], tile_off int32 [S * nb], tile_src int32 [S * nb], count_rows
-    int32 [1]): the packed layout of the padding-compacted encoder (include/atlas_b200.h).  No host synchronisation."""
+    int32 [1]): the packed layout of the padding-compacted encoder (include/atlas_b200.h).  No host synchronisation.
+    `keep` carries the work prefix of the segments (`keep._atlas_work`, int32 [S + 1]) that attention_packed balances its CTAs by."""
     require_cuda(live, "live")
     S, nb = live.shape
     live = live.contiguous()
@@ -334,8 +336,10 @@ def segment_tile_scan(live):
     tile_off = torch.empty(S * nb, dtype=torch.int32, device=live.device)
     tile_src = torch.empty(S * nb, dtype=torch.int32, device=live.device)
     count = torch.empty(1, dtype=torch.int32, device=live.device)
+    work = torch.empty(S + 1, dtype=torch.int32, device=live.device)
     check(lib().atlas_b200_segment_tile_scan(_ptr(live), S, nb, _ptr(keep), _ptr(tile_off), _ptr(tile_src), _ptr(count),
-                                             current_stream_ptr()))
+                                             _ptr(work), current_stream_ptr()))
+    keep._atlas_work = work
     return keep, tile_off, tile_src, count
 
 
@@ -359,9 +363,11 @@ def attention_packed(qkv, keep, tile_off, S, H, L, add_mask, bias_delta, scale=1
         out = torch.empty((qkv.shape[0], H * 64), dtype=qkv.dtype, device=qkv.device)
     am = add_mask.float().contiguous()
     bd = bias_delta.float().contiguous() if bias_delta is not None else None
+    work = getattr(keep, "_atlas_work", None) if _PACKED_BALANCE else None
     check(lib().atlas_b200_attention_packed(_ptr(qkv), qkv.stride(0), 0, H * 64, 2 * H * 64, _ptr(out), out.stride(0), _ptr(am),
-                                            _ptr(bd) if bd is not None else None, _ptr(keep), _ptr(tile_off), S, H, L,
-                                            float(scale), _bf(qkv), current_stream_ptr()))
+                                            _ptr(bd) if bd is not None else None, _ptr(keep), _ptr(tile_off),
+                                            _ptr(work) if work is not None else None, S, H, L, float(scale), _bf(qkv),
+                                            current_stream_ptr()))
     return out
 
 

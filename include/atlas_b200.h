@@ -442,7 +442,8 @@ int atlas_b200_cross_attention_stream_compact(const void* q, int64_t ldq, int32_
  * the packed row count lives in device memory.
  *   atlas_b200_segment_tile_scan: live uint8 [S, nb] (key_block_live) -> keep [S, nb] (tiles 0 .. last live tile of the segment;
  *     all nb if none is live), tile_off int32 [S * nb] (packed index of a kept tile, -1 = dropped), tile_src int32 [S * nb] (source
- *     tile of packed tile o, -1 past the end), *count_rows = 64 x #kept.
+ *     tile of packed tile o, -1 past the end), *count_rows = 64 x #kept; work_prefix int32 [S + 1] (optional): exclusive prefix
+ *     of kept tiles x kept 128-row query tiles per segment - atlas_b200_attention_packed balances its CTAs by it.
  *   atlas_b200_embed_packed_tiles: dst[64 o + r, :] = table[ids[64 tile_src[o] + r], :] (zeros past the end): T5Stack's
  *     embed_tokens (src/modeling_t5.py:930-934) straight into the packed layout.
  *   atlas_b200_linear_rows: atlas_b200_linear_ex over the first *m_dev rows (row blocks past it are not computed; rows of the
@@ -453,7 +454,7 @@ int atlas_b200_cross_attention_stream_compact(const void* q, int64_t ldq, int32_
  *   atlas_b200_expand_packed_tiles: back to the padded layout [S * nb * 64, d] (zeros at dropped tiles - the positions the
  *     reference fills with values nothing reads). */
 int atlas_b200_segment_tile_scan(const uint8_t* live, int32_t S, int32_t nb, uint8_t* keep, int32_t* tile_off, int32_t* tile_src,
-                                 int32_t* count_rows, void* stream);
+                                 int32_t* count_rows, int32_t* work_prefix, void* stream);
 int atlas_b200_embed_packed_tiles(const int64_t* ids, const void* table, int64_t ldt, int32_t vocab, const int32_t* tile_src,
                                   int32_t n_tiles, void* dst, int64_t ldd, int32_t d, void* stream);
 int atlas_b200_linear_rows(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, const void* residual,
@@ -461,7 +462,8 @@ int atlas_b200_linear_rows(const void* A, int64_t lda, const void* W, int64_t ld
                            int32_t is_bf16, const float* row_ss, float* out_ss, float rs_eps, const int32_t* m_dev, void* stream);
 int atlas_b200_attention_packed(const void* qkv, int64_t ld, int32_t q_col0, int32_t k_col0, int32_t v_col0, void* out, int64_t ldo,
                                 const float* add_mask, const float* bias_delta, const uint8_t* keep, const int32_t* tile_off,
-                                int32_t B, int32_t H, int32_t L, float scale, int32_t is_bf16, void* stream);
+                                const int32_t* work_prefix, int32_t B, int32_t H, int32_t L, float scale, int32_t is_bf16,
+                                void* stream);
 int atlas_b200_expand_packed_tiles(const void* src, int64_t lds, const int32_t* tile_off, int32_t n_tiles, void* dst, int64_t ldd,
                                    int32_t d, void* stream);
 

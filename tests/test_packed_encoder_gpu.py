@@ -52,6 +52,9 @@ def test_segment_tile_scan(dev, S, nb):
     keep, off, src, count = ops.segment_tile_scan(live.to(dev))
     wk, wo, ws, wc = _keep_tables(live)
     assert torch.equal(keep.cpu(), wk) and torch.equal(off.cpu(), wo) and torch.equal(src.cpu(), ws) and int(count) == wc
+    f = wk.sum(1).long()                                           # work prefix: kept key blocks x kept 128-row query tiles
+    want_work = torch.cat([torch.zeros(1, dtype=torch.long), torch.cumsum(f * ((f + 1) // 2), 0)]).int()
+    assert torch.equal(keep._atlas_work.cpu(), want_work)
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
@@ -88,6 +91,14 @@ def test_attention_packed_equals_padded(dev, dtype, S, H, L, use_bias):
     out_d = ops.attention(qkv.to(dev), 0, qkv.to(dev), H * 64, qkv.to(dev), 2 * H * 64, S, H, L, L, add_mask=mask,
                           bias_delta=bias, scale=1.0, block_live=keep)
     want = out_d.view(-1, 64, H * 64)[kept].reshape(n_rows, -1)
+    # the CTAs split the items by work (default) or by count: the same rows either way
+    saved = ops._PACKED_BALANCE
+    try:
+        ops._PACKED_BALANCE = False
+        out_c = ops.attention_packed(packed, keep, off, S, H, L, mask, bias, scale=1.0)
+    finally:
+        ops._PACKED_BALANCE = saved
+    assert torch.equal(out_c[:n_rows], out_p[:n_rows])
     if L > 128:
         assert torch.equal(out_p[:n_rows], want), float((out_p[:n_rows].float() - want.float()).abs().max())
     else:

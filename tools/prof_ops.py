@@ -64,6 +64,34 @@ elif what == "mips":
     fn = lambda: ops.mips_topk(bank, q, k)
     ms = timed(fn, reps)
     print(f"mips n={n} nq={nq} k={k}: {ms:.3f} ms = {n * 768 * 2 / ms / 1e6:.0f} GB/s over the bank")
+elif what == "packed":
+    # the padding-compacted FiD-base encoder ops at the bench's length distribution (8 queries x 40 passages, U[148, 276] real
+    # tokens padded to 384): packed three-lane attention vs the padded kernel with block skipping vs no skipping, and the gated
+    # projection over the packed rows (device-side row count) vs all rows
+    S, H, L = 320, 12, 384
+    lens = torch.randint(148, 277, (S,), device=dev)
+    mask = (torch.arange(L, device=dev)[None, :] >= lens[:, None]).float() * -10000.0
+    live = ops.key_block_live(mask)
+    keep, off, src, count = ops.segment_tile_scan(live)
+    qkv = torch.randn(S * L, 3 * H * 64, device=dev).bfloat16() * 0.2
+    bias = torch.randn(H, 2 * L - 1, device=dev)
+    dense_fl = 4 * S * H * L * L * 64
+    frac = float(keep.float().mean())
+    ms_p = timed(lambda: ops.attention_packed(qkv, keep, off, S, H, L, mask, bias), reps)
+    ms_s = timed(lambda: ops.attention(qkv, 0, qkv, H * 64, qkv, 2 * H * 64, S, H, L, L, add_mask=mask, bias_delta=bias,
+                                       block_live=live), reps)
+    ms_d = timed(lambda: ops.attention(qkv, 0, qkv, H * 64, qkv, 2 * H * 64, S, H, L, L, add_mask=mask, bias_delta=bias), reps)
+    print(f"attention S={S} H={H} L={L}, kept tiles {frac:.3f}: packed {ms_p:.3f} ms | padded, dead key blocks skipped {ms_s:.3f} ms | "
+          f"padded, every block {ms_d:.3f} ms = {dense_fl / ms_d / 1e9:.0f} TFLOP/s; packed executes "
+          f"{dense_fl * float((keep.float().sum(1) ** 2).mean()) / 36 / ms_p / 1e9:.0f} TFLOP/s on kept x kept tiles")
+    M, N, K = S * L, 4096, 768
+    x = torch.randn(M, K, device=dev).bfloat16() * 0.1
+    w = torch.randn(N, K, device=dev).bfloat16() * 0.03
+    ms_r = timed(lambda: ops.linear(x, w, epilogue=ops.EPI_GATED, rows=count), reps)
+    ms_a = timed(lambda: ops.linear(x, w, epilogue=ops.EPI_GATED), reps)
+    rows = int(count)
+    print(f"gemm gated M={M} N={N} K={K}: first {rows} rows (device-side count) {ms_r:.3f} ms = {2 * rows * N * K / ms_r / 1e9:.0f} "
+          f"TFLOP/s | all rows {ms_a:.3f} ms = {2 * M * N * K / ms_a / 1e9:.0f} TFLOP/s")
 elif what == "xattn":
     # FiD-base decoder cross-attention of the teacher-forced forward: 8 queries x 32 target tokens against 40 x 384 encoder keys,
     # passages of U[148, 276] real tokens padded to 384 (the bench's length distribution)
