@@ -92,6 +92,8 @@ def lib():
     L.atlas_b200_profile_enable.argtypes = [c.c_int32]
     L.atlas_b200_profile_work.restype = c.c_double
     L.atlas_b200_profile_work.argtypes = []
+    L.atlas_b200_profile_launches.restype = c.c_int32
+    L.atlas_b200_profile_launches.argtypes = [c.POINTER(c.c_double), c.POINTER(c.c_double), c.c_int32]
     L.atlas_b200_profile_collect.restype = c.c_int
     L.atlas_b200_profile_collect.argtypes = [c.POINTER(c.c_double), c.POINTER(c.c_int32)]
     i32, i64, vp, f32 = c.c_int32, c.c_int64, c.c_void_p, c.c_float
@@ -208,6 +210,7 @@ EXPORTED_SYMBOLS = [
     "atlas_b200_profile_enable",
     "atlas_b200_profile_work",
     "atlas_b200_profile_collect",
+    "atlas_b200_profile_launches",
     "atlas_b200_attention_bwd",
     "atlas_b200_attention_ex",
     "atlas_b200_attention_combine_ex",

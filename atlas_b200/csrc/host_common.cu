@@ -105,6 +105,11 @@ struct DynWork {                 // launches whose row count lives in device mem
     int32_t m_max;
 };
 static std::vector<DynWork> g_prof_dyn;
+struct LaunchWork {              // per bracketed launch, in launch order: static work, or the index of its DynWork entry
+    double work;
+    int dyn;
+};
+static std::vector<LaunchWork> g_prof_launch;
 static int32_t* g_prof_rows = nullptr;          // pinned host slots
 constexpr int PROF_ROW_SLOTS = 4096;
 
@@ -123,6 +128,7 @@ void prof_end(cudaStream_t s, int kind, double work) {
     cudaEventRecord(g_prof_events[g_prof_used].second, s);
     ++g_prof_used;
     g_prof_work += work;
+    g_prof_launch.push_back({work, -1});
 }
 
 void prof_end_dyn(cudaStream_t s, int kind, double work_per_row, const int32_t* m_dev, int32_t m_max) {
@@ -136,10 +142,12 @@ void prof_end_dyn(cudaStream_t s, int kind, double work_per_row, const int32_t* 
         g_prof_rows[slot] = m_max;
         if (cudaMemcpyAsync(g_prof_rows + slot, m_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, s) == cudaSuccess) {
             g_prof_dyn.push_back({work_per_row, slot, m_max});
+            g_prof_launch.push_back({0.0, slot});
             return;
         }
     }
     g_prof_work += work_per_row * m_max;          // no slot: counted at full height
+    g_prof_launch.push_back({work_per_row * m_max, -1});
 }
 
 }  // namespace abh
@@ -151,6 +159,7 @@ void atlas_b200_profile_enable(int32_t kind) {
     abh::g_prof_used = 0;
     abh::g_prof_work = 0;
     abh::g_prof_dyn.clear();
+    abh::g_prof_launch.clear();
 }
 
 // the work of the bracketed launches; launches with a device-side row count are counted with the rows they really computed
@@ -164,6 +173,30 @@ double atlas_b200_profile_work(void) {
         w += d.work_per_row * m;
     }
     return w;
+}
+
+// per bracketed launch, in launch order: its event-bracketed time and its work (device-side row counts resolved); returns the number
+// of launches written (<= cap).  Call after the stream has been synchronised and BEFORE atlas_b200_profile_collect.
+int32_t atlas_b200_profile_launches(double* ms, double* work, int32_t cap) {
+    const size_t n = abh::g_prof_used < abh::g_prof_launch.size() ? abh::g_prof_used : abh::g_prof_launch.size();
+    int32_t written = 0;
+    for (size_t i = 0; i < n && written < cap; ++i, ++written) {
+        float t = 0;
+        if (cudaEventSynchronize(abh::g_prof_events[i].second) != cudaSuccess ||
+            cudaEventElapsedTime(&t, abh::g_prof_events[i].first, abh::g_prof_events[i].second) != cudaSuccess)
+            t = 0;
+        const abh::LaunchWork& lw = abh::g_prof_launch[i];
+        double w = lw.work;
+        if (lw.dyn >= 0) {
+            const abh::DynWork& d = abh::g_prof_dyn[lw.dyn];
+            int32_t m = abh::g_prof_rows[d.slot];
+            m = m > d.m_max ? d.m_max : (m < 0 ? 0 : m);
+            w = d.work_per_row * m;
+        }
+        if (ms) ms[written] = t;
+        if (work) work[written] = w;
+    }
+    return written;
 }
 
 int atlas_b200_profile_collect(double* total_ms, int32_t* launches) {

@@ -716,6 +716,7 @@ def run_ours(args):
     # ---------------- per-kernel time of the step (eager launches bracketed with CUDA events in the library) -------
     reader.cuda_graphs = False
     prof = {}
+    gemm_launches = []
     for kind, name in ((2, "gemm"), (3, "attention")):
         step_device()
         torch.cuda.synchronize()
@@ -724,6 +725,11 @@ def run_ours(args):
         step_device()
         torch.cuda.synchronize()
         work = L.atlas_b200_profile_work()
+        if name == "gemm":      # per-launch records: the encoder-sized launches are a different instantiation of the kernel
+            cap = 1024
+            lms, lwk = (ctypes.c_double * cap)(), (ctypes.c_double * cap)()
+            ln = L.atlas_b200_profile_launches(lms, lwk, cap)
+            gemm_launches = [(lms[i], lwk[i]) for i in range(ln)]
         kms, kn = ctypes.c_double(0), ctypes.c_int32(0)
         L.atlas_b200_profile_collect(ctypes.byref(kms), ctypes.byref(kn))
         L.atlas_b200_profile_enable(0)
@@ -783,6 +789,14 @@ def run_ours(args):
         gemm_traffic_note = f"{tj.get('launch')}: algorithmic {tj.get('algorithmic_bytes_per_launch')} B; {tj.get('source')}"
     g_ms, g_n, g_flops = prof["gemm"]
     a_ms, a_n, a_flops = prof["attention"]
+    all_gemm = {"ms_per_step": g_ms, "launches_per_step": g_n, "flops_per_step": g_flops,
+                "achieved_tflops": g_flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0}
+    all_gemm["frac"] = all_gemm["achieved_tflops"] / peak if peak else None
+    # the dominant kernel: gemm_kernel<bf16, 256, pair> - the launches of the encoder blocks and the cross K | V projections
+    # (>= 20 GFLOP each; the decoder's 256-row launches run the 128-wide single-CTA instantiation and are latency-bound)
+    big = [(m, w) for m, w in gemm_launches if w >= 2e10]
+    if big:
+        g_ms, g_n, g_flops = sum(m for m, _ in big), len(big), sum(w for _, w in big)
     achieved = g_flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
     a_tflops = a_flops / (a_ms * 1e-3) / 1e12 if a_ms > 0 else None
     line = {
@@ -793,7 +807,9 @@ def run_ours(args):
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved / peak if peak else None, "traffic": gemm_traffic, "traffic_note": gemm_traffic_note,
                      "peak_source": peak_src,
-                     "kernel": "gemm_kernel (tcgen05 linear layers of FiD-base / Contriever-base, fused epilogues)",
+                     "kernel": "gemm_kernel<bf16, 256, pair> (tcgen05 2-CTA tiles: the linear layers of the FiD-base encoder blocks "
+                               "and the cross K | V projections, fused epilogues; launches >= 20 GFLOP, rows counted as computed)",
+                     "all_gemm_launches": all_gemm,
                      "kernel_ms_per_step": g_ms, "kernel_launches_per_step": g_n, "algorithmic_flops_per_step": g_flops,
                      "kernel_share_of_step": g_ms / ms_per_step if ms_per_step else None,
                      "attention_kernel": {"ms_per_step": a_ms, "launches_per_step": a_n, "achieved_tflops": a_tflops,

@@ -476,8 +476,10 @@ int atlas_b200_expand_packed_tiles(const void* src, int64_t lds, const int32_t* 
  *   kind 0  off (default).
  * atlas_b200_profile_work() returns the work summed over the bracketed launches so far;
  * atlas_b200_profile_collect() synchronises the events, returns the summed kernel time and the number of
- * bracketed launches, and resets the list (call profile_work first).  Not thread safe. */
+ * bracketed launches, and resets the list (call profile_work first).  atlas_b200_profile_launches() (before collect) returns
+ * each bracketed launch's time and work in launch order.  Not thread safe. */
 void atlas_b200_profile_enable(int32_t kind);
+int32_t atlas_b200_profile_launches(double* ms, double* work, int32_t cap);
 double atlas_b200_profile_work(void);
 int atlas_b200_profile_collect(double* total_ms, int32_t* launches);
 
