@@ -322,6 +322,7 @@ def compact_live_tiles(x, tile_live):
 
 
 _ENC_PACKED = os.environ.get("ATLAS_B200_ENC_PACKED", "1") != "0"          # A/B switch of the padding-compacted FiD encoder
+_BERT_PACKED = os.environ.get("ATLAS_B200_BERT_PACKED", "1") != "0"        # ... of the Contriever encoder (needs _ENC_PACKED too)
 _PACKED_BALANCE = os.environ.get("ATLAS_B200_PACKED_BALANCE", "1") != "0"  # A/B: packed attention CTAs split by work, not count
 
 

@@ -248,20 +248,35 @@ class Contriever(nn.Module):
         # transformers==4.18 get_extended_attention_mask: (1 - mask) * -10000 (src/modeling_bert.py:993)
         add_mask = (1.0 - attention_mask.to(torch.float32)) * -10000.0
         live = ops.key_block_live(add_mask)       # all-padding 64-key blocks (queries are padded to text_maxlength): skipped
+        # Padding-compacted encoder (same scheme as FiD._encode_rows): every sequence keeps its 64-row tiles up
+        # to its last live key, packed back to back; projections run over the device-side row count, the attention on the
+        # packed rows.  Padded positions never influence live ones and every consumer of the result masks them (mean pooling)
+        # or reads position 0 (cls pooling): the returned rows of dropped tiles are 0.
+        packed = ops._ENC_PACKED and ops._BERT_PACKED and live is not None and L % 64 == 0 and 64 <= L <= 384
+        rows = None
+        if packed:
+            keep, tile_off, _, rows = ops.segment_tile_scan(live)
+            h = ops.compact_live_tiles(h, keep)[0]
         qkv = torch.empty((B * L, 3 * H), dtype=dt, device=h.device)
         for i in range(c.num_hidden_layers):
             p = f"encoder.layer.{i}."
-            ops.linear(h, F[p + "attention.self.qkv.weight"], F[p + "attention.self.qkv.bias"], out=qkv)
-            ctx = ops.attention(qkv, 0, qkv, H, qkv, 2 * H, B, nh, L, L, add_mask=add_mask, scale=1.0 / math.sqrt(64),
-                                block_live=live)
-            s1 = ops.linear(ctx, W[p + "attention.output.dense.weight"], W[p + "attention.output.dense.bias"], residual=h)
+            ops.linear(h, F[p + "attention.self.qkv.weight"], F[p + "attention.self.qkv.bias"], out=qkv, rows=rows)
+            if packed:
+                ctx = ops.attention_packed(qkv, keep, tile_off, B, nh, L, add_mask, None, scale=1.0 / math.sqrt(64))
+            else:
+                ctx = ops.attention(qkv, 0, qkv, H, qkv, 2 * H, B, nh, L, L, add_mask=add_mask, scale=1.0 / math.sqrt(64),
+                                    block_live=live)
+            s1 = ops.linear(ctx, W[p + "attention.output.dense.weight"], W[p + "attention.output.dense.bias"], residual=h,
+                            rows=rows)
             h1 = ops.layernorm(s1, W[p + "attention.output.LayerNorm.weight"], W[p + "attention.output.LayerNorm.bias"],
                                c.layer_norm_eps, kind=0)
             inter = ops.linear(h1, W[p + "intermediate.dense.weight"], W[p + "intermediate.dense.bias"],
-                               epilogue=ops.EPI_GELU)
-            s2 = ops.linear(inter, W[p + "output.dense.weight"], W[p + "output.dense.bias"], residual=h1)
+                               epilogue=ops.EPI_GELU, rows=rows)
+            s2 = ops.linear(inter, W[p + "output.dense.weight"], W[p + "output.dense.bias"], residual=h1, rows=rows)
             h = ops.layernorm(s2, W[p + "output.LayerNorm.weight"], W[p + "output.LayerNorm.bias"], c.layer_norm_eps,
                               kind=0)
+        if packed:
+            h = ops.expand_packed_tiles(h, tile_off)
         return h.view(B, L, H)
 
     # ---- training path (autograd through the kernels, grad_ops.py) ---------------------------------------
@@ -369,7 +384,7 @@ class Contriever(nn.Module):
         gen = self._half.sets[dt]["gen"]
         mask = attention_mask if attention_mask is not None else torch.ones_like(input_ids)
         has_tt = token_type_ids is not None
-        key = (B, L, dt, gen, has_tt, input_ids.device, mask.dtype)
+        key = (B, L, dt, gen, has_tt, input_ids.device, mask.dtype, ops._ENC_PACKED and ops._BERT_PACKED)
         graphs = self.__dict__.setdefault("_graphs", {})
         runner = graphs.get(key)
         if runner is None:

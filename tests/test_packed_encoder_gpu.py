@@ -198,3 +198,50 @@ def test_fid_forward_packed_equals_padded(dev, dtype, fuse_norm):
     escale = max(1.0, float(eb[keep].abs().max()))
     assert float((ea[keep] - eb[keep]).abs().max()) <= 8 * ulp * escale
     assert int(keep.sum()) < keep.numel()
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("B,L", [(8, 384), (37, 192), (5, 128), (3, 64), (4, 200)])
+def test_contriever_packed_equals_padded(dev, dtype, B, L):
+    """`Contriever.encode` on the packed rows (queries padded to text_maxlength, index-refresh batches padded to the longest
+    passage) against the padded encoder: the hidden states of the kept tiles (bit-identical where both runs take the three-lane
+    attention kernel, L > 128), zeros at the dropped tiles, and the pooled embeddings.  L = 200 is not a multiple of 64: padded."""
+    from atlas_b200 import ops
+    from atlas_b200.retrievers import BertConfigLite, Contriever
+
+    model = Contriever(BertConfigLite(**dict(model_synth.CONTRIEVER_CFG, num_hidden_layers=3)))
+    sd, _ = model_synth.fill_state_dict(model.state_dict(), 77)
+    model.load_state_dict(sd)
+    model = model.to(dtype).to(dev).eval()
+    ids, mask = model_synth.contriever_inputs(seed=B + L, B=B, L=L, vocab=model_synth.CONTRIEVER_CFG["vocab_size"])
+    mask = mask.clone()
+    mask[0, 5:] = 0                                                # a 5-token query: one tile
+    mask[1, :] = 1
+    ids, mask = (ids * mask).to(dev), mask.to(dev)
+    if not ops._BERT_PACKED:
+        pytest.skip("ATLAS_B200_BERT_PACKED=0")
+    saved = ops._ENC_PACKED
+    try:
+        ops._ENC_PACKED = True
+        with torch.no_grad():
+            hp = model.encode(ids, mask)
+            ep = model(input_ids=ids, attention_mask=mask)
+        ops._ENC_PACKED = False
+        with torch.no_grad():
+            hd = model.encode(ids, mask)
+            ed = model(input_ids=ids, attention_mask=mask)
+    finally:
+        ops._ENC_PACKED = saved
+    if L % 64 == 0:
+        live = ops.key_block_live((1.0 - mask.float()) * -10000.0)
+        keep = ops.segment_tile_scan(live)[0].bool().repeat_interleave(64, dim=1)      # [B, L]
+        assert float(hp[~keep].abs().max() if bool((~keep).any()) else 0.0) == 0.0
+    else:
+        keep = torch.ones_like(mask, dtype=torch.bool)
+    tol = (2.0 ** -7 if dtype == torch.bfloat16 else 2.0 ** -10) * max(1.0, float(hd.abs().max()))
+    if L > 128:
+        assert torch.equal(hp[keep], hd[keep])
+        assert torch.equal(ep, ed)
+    else:
+        assert float((hp[keep].float() - hd[keep].float()).abs().max()) <= 4 * tol
+        assert float((ep.float() - ed.float()).abs().max()) <= 4 * tol
