@@ -92,6 +92,23 @@ elif what == "packed":
     rows = int(count)
     print(f"gemm gated M={M} N={N} K={K}: first {rows} rows (device-side count) {ms_r:.3f} ms = {2 * rows * N * K / ms_r / 1e9:.0f} "
           f"TFLOP/s | all rows {ms_a:.3f} ms = {2 * M * N * K / ms_a / 1e9:.0f} TFLOP/s")
+elif what == "refresh":
+    # one index-refresh embedder batch (bench.py refresh leg): 512 passages of U[64, 192] tokens padded to 192 through
+    # Contriever-base with fp16 weight copies, pooled rows written into bank rows (Contriever.embed_into)
+    from atlas_b200.retrievers import BertConfigLite, Contriever
+    model = Contriever(BertConfigLite()).to(torch.bfloat16).to(dev).eval()
+    nb, lmax = 512, 192
+    g = torch.Generator().manual_seed(4242)
+    lens = torch.randint(64, lmax + 1, (nb,), generator=g)
+    lens[0] = lmax
+    ids = torch.randint(1000, 30000, (nb, lmax), generator=g)
+    mask = (torch.arange(lmax)[None, :] < lens[:, None]).to(torch.int64)
+    ids, mask = (ids * mask).to(dev), mask.to(dev)
+    rows = torch.zeros((nb, 768), dtype=torch.float16, device=dev)
+    fn = lambda: model.embed_into(ids, mask, rows, dtype=torch.float16)
+    ms = timed(fn, reps)
+    print(f"refresh batch {nb} x {lmax} (kept tiles {float(((lens + 63) // 64).sum()) / (nb * 3):.3f}): {ms:.3f} ms = "
+          f"{nb / ms * 1e3:.0f} passages/s")
 elif what == "xattn":
     # FiD-base decoder cross-attention of the teacher-forced forward: 8 queries x 32 target tokens against 40 x 384 encoder keys,
     # passages of U[148, 276] real tokens padded to 384 (the bench's length distribution)
