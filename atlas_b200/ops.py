@@ -347,10 +347,15 @@ def segment_tile_scan(live):
 def embed_packed_tiles(ids, table, tile_src):
     """Embedding rows of the token ids (int64 [n_tiles * 64]) of the kept tiles, in packed order; zeros past the end."""
     require_cuda(table, "table")
-    ids = ids.reshape(-1).contiguous()
+    ids = ids.reshape(-1)
+    if ids.dtype != torch.int64:                   # torch's own embedding lookup takes int32 ids too
+        if ids.dtype not in (torch.int32, torch.int16, torch.uint8):
+            raise AtlasB200Error(f"embed_packed_tiles: integer token ids expected (got {ids.dtype})")
+        ids = ids.to(torch.int64)
+    ids = ids.contiguous()
     n_tiles = tile_src.numel()
-    if ids.dtype != torch.int64 or ids.numel() != n_tiles * 64:
-        raise AtlasB200Error(f"embed_packed_tiles: need {n_tiles * 64} int64 ids (got {ids.numel()} {ids.dtype})")
+    if ids.numel() != n_tiles * 64:
+        raise AtlasB200Error(f"embed_packed_tiles: need {n_tiles * 64} token ids (got {ids.numel()})")
     out = torch.empty((n_tiles * 64, table.shape[1]), dtype=table.dtype, device=table.device)
     check(lib().atlas_b200_embed_packed_tiles(_ptr(ids), _ptr(table), table.stride(0), table.shape[0], _ptr(tile_src), n_tiles,
                                               _ptr(out), out.stride(0), table.shape[1], current_stream_ptr()))
