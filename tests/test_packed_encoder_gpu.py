@@ -124,6 +124,7 @@ def test_embed_and_expand_packed_tiles(dev):
     kept = keep.reshape(-1).bool()
     h = ops.embed_packed_tiles(ids, table, src)
     assert torch.equal(h[:n_rows], table[ids].view(-1, 64, d)[kept].reshape(n_rows, d)) and float(h[n_rows:].abs().max()) == 0
+    assert torch.equal(ops.embed_packed_tiles(ids.to(torch.int32), table, src), h)      # int32 ids like torch's lookup
     back = ops.expand_packed_tiles(h, off).view(-1, 64, d)
     assert torch.equal(back[kept], table[ids].view(-1, 64, d)[kept]) and float(back[~kept].abs().max()) == 0
 
