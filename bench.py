@@ -272,6 +272,9 @@ def workload_config(args):
             "reader_tokens": f"synthetic device-resident token bank: {PASSAGE_TOKENS}-token rows keyed by global passage "
                              f"id (lengths U[{PASSAGE_TOKENS // 2}, {PASSAGE_TOKENS}]), spliced behind the query tokens "
                              "on the GPU (atlas_b200_splice_tokens); no tokenizer vocabulary offline",
+            "padding": "every reader passage is padded to text_maxlength like src/atlas.py:261-270 pads (148 - 276 of 384 positions "
+                       "real); the repo arm encodes each passage's 64-position tiles up to its last real token (same logits / loss, "
+                       "DESIGN.md 3.10) and also reports the step with every padded position encoded (`padded_encoder`)",
             "weights": "random init (Contriever-base / T5-v1.1-base shapes), bf16 reader + retriever, fp16 bank",
             "l2": "bank (6.4 GB) and per-step activations (> 1 GB) exceed the 126 MB L2; no explicit flush"}
 
