@@ -24,18 +24,11 @@ def dev():
 
 
 def _keep_tables(live):
-    """torch restatement of atlas_b200_segment_tile_scan."""
-    S, nb = live.shape
-    keep = torch.zeros_like(live)
-    for s in range(S):
-        nz = live[s].nonzero()
-        f = int(nz.max()) + 1 if len(nz) else nb
-        keep[s, :f] = 1
-    flat = keep.reshape(-1).bool()
-    off = torch.where(flat, torch.cumsum(flat.int(), 0) - 1, torch.full_like(flat.int(), -1)).int()
-    src = torch.full((S * nb,), -1, dtype=torch.int32)
-    src[: int(flat.sum())] = flat.nonzero().reshape(-1).int()
-    return keep, off, src, 64 * int(flat.sum())
+    """The CPU restatement of atlas_b200_segment_tile_scan (oracle/packing_oracle.py) as torch tensors."""
+    import packing_oracle
+
+    keep, off, src, rows, _ = packing_oracle.segment_tables(live.cpu().numpy())
+    return torch.from_numpy(keep), torch.from_numpy(off), torch.from_numpy(src), rows
 
 
 @pytest.mark.parametrize("S,nb", [(1, 1), (7, 6), (320, 6), (2500, 3), (33, 9)])
@@ -52,9 +45,14 @@ def test_segment_tile_scan(dev, S, nb):
     keep, off, src, count = ops.segment_tile_scan(live.to(dev))
     wk, wo, ws, wc = _keep_tables(live)
     assert torch.equal(keep.cpu(), wk) and torch.equal(off.cpu(), wo) and torch.equal(src.cpu(), ws) and int(count) == wc
-    f = wk.sum(1).long()                                           # work prefix: kept key blocks x kept 128-row query tiles
-    want_work = torch.cat([torch.zeros(1, dtype=torch.long), torch.cumsum(f * ((f + 1) // 2), 0)]).int()
+    import packing_oracle                                          # work prefix: kept key blocks x kept 128-row query tiles
+
+    want_work = torch.from_numpy(packing_oracle.segment_tables(live.numpy())[4])
     assert torch.equal(keep._atlas_work.cpu(), want_work)
+    # and key_block_live against the oracle's rule on a token mask
+    tok = (torch.rand(S, nb * 64, generator=g) < 0.02).long()
+    got = ops.key_block_live(((1 - tok).float() * -10000.0).to(dev))
+    assert torch.equal(got.cpu(), torch.from_numpy(packing_oracle.live_tiles(tok.numpy())))
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])

@@ -11,6 +11,7 @@ import numpy as np
 import torch
 
 import fid_cpu
+import packing_oracle
 
 T5_SMALL = dict(vocab_size=300, d_model=128, d_kv=64, d_ff=256, num_layers=2, num_decoder_layers=2, num_heads=2,
                 relative_attention_num_buckets=32, layer_norm_epsilon=1e-6)
@@ -79,3 +80,22 @@ def test_contriever_embedding_does_not_depend_on_padding():
             kept = -(-n // 64) * 64
             e = fid_cpu.contriever_forward(sd, BERT_SMALL, ids[r:r + 1, :kept], mask[r:r + 1, :kept])
             assert np.allclose(e[0].numpy(), full[r].numpy(), rtol=0, atol=2e-6)
+
+
+def test_segment_table_rule_on_hand_written_cases():
+    """The packing rule itself (oracle/packing_oracle.py, which the CUDA tables are checked against on the GPU)."""
+    mask = np.zeros((4, 256), dtype=np.int64)
+    mask[0, :70] = 1                    # 2 tiles
+    mask[1, :256] = 1                   # 4 tiles
+    mask[2, :10] = 1                    # a hole: tile 0 and tile 2 live, tile 1 dead but inside the prefix
+    mask[2, 130:140] = 1
+    live = packing_oracle.live_tiles(mask)          # row 3: no real token at all -> every tile live
+    assert live.tolist() == [[1, 1, 0, 0], [1, 1, 1, 1], [1, 0, 1, 0], [1, 1, 1, 1]]
+    keep, off, src, rows, work = packing_oracle.segment_tables(live)
+    assert keep.tolist() == [[1, 1, 0, 0], [1, 1, 1, 1], [1, 1, 1, 0], [1, 1, 1, 1]]
+    assert off.tolist() == [0, 1, -1, -1, 2, 3, 4, 5, 6, 7, 8, -1, 9, 10, 11, 12]
+    assert src.tolist() == [0, 1, 4, 5, 6, 7, 8, 9, 10, 12, 13, 14, 15, -1, -1, -1]
+    assert rows == 13 * 64
+    assert work.tolist() == [0, 2, 10, 16, 24]          # kept x ceil(kept / 2): 2*1, 4*2, 3*2, 4*2
+    # ragged length: the last tile is partial
+    assert packing_oracle.live_tiles(np.ones((1, 100), dtype=np.int64)).tolist() == [[1, 1]]
